@@ -1,0 +1,67 @@
+// df_common.cuh -- shared device helpers for the sm_100a kernels.
+//
+// Numerics contract (DESIGN.md "Numerics"): every float operation is the IEEE round-to-nearest operation at the same
+// position and in the same order as the reference kernel it replaces; translation units are compiled with
+// -fmad=false so nvcc never contracts a*b+c, and fused multiply-adds appear ONLY where the reference wrote
+// __fmaf_rn (dot(), Projector).  This is what makes the kernels bit-comparable with oracle/ (gcc -ffp-contract=off).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include "../../include/dfusion.h"
+
+namespace dfb {
+
+struct Aff { float3 r0, r1, r2, t; };
+
+__host__ inline Aff make_aff(const df_aff3f &a)
+{
+    Aff o;
+    o.r0 = make_float3(a.R[0], a.R[1], a.R[2]);
+    o.r1 = make_float3(a.R[3], a.R[4], a.R[5]);
+    o.r2 = make_float3(a.R[6], a.R[7], a.R[8]);
+    o.t = make_float3(a.t[0], a.t[1], a.t[2]);
+    return o;
+}
+struct Mat3 { float3 r0, r1, r2; };
+__host__ inline Mat3 make_mat3(const float *R)
+{
+    Mat3 o;
+    o.r0 = make_float3(R[0], R[1], R[2]); o.r1 = make_float3(R[3], R[4], R[5]); o.r2 = make_float3(R[6], R[7], R[8]);
+    return o;
+}
+
+// reference temp_utils.hpp:27-30
+__device__ __forceinline__ float dot3(const float3 a, const float3 b) { return __fmaf_rn(a.x, b.x, __fmaf_rn(a.y, b.y, a.z * b.z)); }
+__device__ __forceinline__ float3 add3(const float3 a, const float3 b) { return make_float3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 sub3(const float3 a, const float3 b) { return make_float3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 mul3(const float3 a, const float3 b) { return make_float3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ float3 scale3(const float3 a, const float s) { return make_float3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float3 cross3(const float3 a, const float3 b)
+{ return make_float3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+// normalized(): v * rsqrt(dot) in the reference (temp_utils.hpp:95-98); IEEE restatement 1/sqrt
+__device__ __forceinline__ float3 normalized3(const float3 v) { return scale3(v, 1.0f / sqrtf(dot3(v, v))); }
+// device.hpp:71-74
+__device__ __forceinline__ float3 mat_mul(const float3 r0, const float3 r1, const float3 r2, const float3 v)
+{ return make_float3(dot3(r0, v), dot3(r1, v), dot3(r2, v)); }
+__device__ __forceinline__ float3 aff_mul(const Aff &a, const float3 v) { return add3(mat_mul(a.r0, a.r1, a.r2, v), a.t); }
+__device__ __forceinline__ float3 mat3_mul(const Mat3 &m, const float3 v) { return mat_mul(m.r0, m.r1, m.r2, v); }
+
+__device__ __forceinline__ float half_bits_to_float(unsigned short h) { return __half2float(__ushort_as_half(h)); }
+__device__ __forceinline__ unsigned short float_to_half_bits(float f) { return __half_as_ushort(__float2half_rn(f)); }
+__device__ __forceinline__ float qnan() { return __int_as_float(0x7fffffff); }
+
+template <typename T> __device__ __forceinline__ const T *row_ptr(const T *base, size_t pitch, int y)
+{ return (const T *)((const char *)base + (size_t)y * pitch); }
+template <typename T> __device__ __forceinline__ T *row_ptr(T *base, size_t pitch, int y)
+{ return (T *)((char *)base + (size_t)y * pitch); }
+
+static inline int div_up(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace dfb
+
+#define DF_LAUNCH_CHECK()                                  \
+    do {                                                   \
+        cudaError_t e__ = cudaGetLastError();              \
+        if (e__ != cudaSuccess) return (int)e__;           \
+    } while (0)

@@ -1,0 +1,333 @@
+"""Python host-side mirror of the reference's component API for the hot path, over the C ABI (capi.py).
+
+Names, argument meaning and defaults follow the reference's host classes so parity tests read like the reference:
+  TsdfVolume       <- kfusion::cuda::TsdfVolume      (kfusion/include/kfusion/cuda/tsdf_volume.hpp:11-100)
+  computeDists ... <- kfusion::cuda::* free functions (kfusion/include/kfusion/cuda/imgproc.hpp:9-33)
+  ProjectiveICP    <- kfusion::cuda::ProjectiveICP   (kfusion/include/kfusion/cuda/projective_icp.hpp:9-46)
+  WarpField        <- kfusion::WarpField             (kfusion/include/kfusion/warp_field.hpp:41-88)
+torch supplies device memory and streams; every compute call goes through libdfusion.so.
+Images: depth/dists are torch.int16 (u16 bits) [rows, cols]; vertex/normal maps torch.float32 [rows, cols, 4].
+Poses are (R 3x3 float32, t 3 float32) numpy pairs (cv::Affine3f).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import capi
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _lib():
+    if not torch.cuda.is_available():
+        raise RuntimeError("dynamicfusion_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return capi.load()
+
+
+def aff_inv(pose):
+    """cv::Affine3f::inv(): R^-1 (closed form 3x3), t' = -R^-1 t, in float32"""
+    R, t = np.asarray(pose[0], np.float32), np.asarray(pose[1], np.float32)
+    Ri = np.linalg.inv(R.astype(np.float64)).astype(np.float32)
+    return Ri, (-(Ri @ t)).astype(np.float32)
+
+
+def aff_mul(A, B):
+    RA, tA = np.asarray(A[0], np.float32), np.asarray(A[1], np.float32)
+    RB, tB = np.asarray(B[0], np.float32), np.asarray(B[1], np.float32)
+    return (RA @ RB).astype(np.float32), (RA @ tB + tA).astype(np.float32)
+
+
+def identity_pose():
+    return np.eye(3, dtype=np.float32), np.zeros(3, np.float32)
+
+
+def u16_to_device(a: np.ndarray, device="cuda") -> torch.Tensor:
+    assert a.dtype == np.uint16
+    return torch.from_numpy(a.view(np.int16).copy()).to(device)
+
+
+def u16_from_device(t: torch.Tensor) -> np.ndarray:
+    return t.cpu().numpy().view(np.uint16)
+
+
+# ------------------------------------------------------------------ imgproc free functions ---------------------------------------------------
+def computeDists(depth: torch.Tensor, intr) -> torch.Tensor:
+    rows, cols = depth.shape
+    dists = torch.empty_like(depth)
+    capi.check(_lib().df_compute_dists(depth.data_ptr(), cols * 2, cols, rows, capi.make_intr(*intr), dists.data_ptr(), cols * 2, _stream()))
+    return dists
+
+
+def depthBilateralFilter(depth: torch.Tensor, ksz: int, sigma_spatial: float, sigma_depth: float) -> torch.Tensor:
+    rows, cols = depth.shape
+    out = torch.empty_like(depth)
+    capi.check(_lib().df_bilateral(depth.data_ptr(), cols * 2, cols, rows, out.data_ptr(), cols * 2, ksz, sigma_spatial, sigma_depth, _stream()))
+    return out
+
+
+def depthTruncation(depth: torch.Tensor, threshold: float) -> None:
+    rows, cols = depth.shape
+    capi.check(_lib().df_truncate_depth(depth.data_ptr(), cols * 2, cols, rows, threshold, _stream()))
+
+
+def depthBuildPyramid(depth: torch.Tensor, sigma_depth: float) -> torch.Tensor:
+    rows, cols = depth.shape
+    out = torch.empty((rows // 2, cols // 2), dtype=depth.dtype, device=depth.device)
+    capi.check(_lib().df_pyr_down(depth.data_ptr(), cols * 2, cols, rows, out.data_ptr(), (cols // 2) * 2, sigma_depth, _stream()))
+    return out
+
+
+def computePointNormals(intr, depth: torch.Tensor):
+    rows, cols = depth.shape
+    pts = torch.empty((rows, cols, 4), dtype=torch.float32, device=depth.device)
+    nrm = torch.empty_like(pts)
+    capi.check(_lib().df_points_normals(capi.make_intr(*intr), depth.data_ptr(), cols * 2, cols, rows, pts.data_ptr(), cols * 16,
+                                        nrm.data_ptr(), cols * 16, _stream()))
+    return pts, nrm
+
+
+def resizePointsNormals(points: torch.Tensor, normals: torch.Tensor):
+    rows, cols = points.shape[:2]
+    vd = torch.empty((rows // 2, cols // 2, 4), dtype=torch.float32, device=points.device)
+    nd = torch.empty_like(vd)
+    capi.check(_lib().df_resize_points_normals(points.data_ptr(), cols * 16, normals.data_ptr(), cols * 16, cols, rows,
+                                               vd.data_ptr(), (cols // 2) * 16, nd.data_ptr(), (cols // 2) * 16, _stream()))
+    return vd, nd
+
+
+# ------------------------------------------------------------------ TsdfVolume ---------------------------------------------------------------
+class TsdfVolume:
+    """cuda::TsdfVolume (tsdf_volume.hpp:11-100, tsdf_volume.cpp).  Class defaults as tsdf_volume.cpp:7-14."""
+
+    def __init__(self, dims, device="cuda"):
+        self.device = device
+        self.trunc_dist_ = 0.03
+        self.max_weight_ = 128
+        self.size_ = np.array([3.0, 3.0, 3.0], np.float32)
+        self.pose_ = identity_pose()
+        self.gradient_delta_factor_ = 0.75
+        self.raycast_step_factor_ = 0.75
+        self.cloud_capacity = 0
+        self._ws = None
+        self._proj_ws = None
+        self.create(dims)
+
+    def create(self, dims):
+        self.dims_ = np.array(dims, np.int32)
+        n = int(self.dims_[0]) * int(self.dims_[1]) * int(self.dims_[2])
+        self.data_ = torch.empty(n, dtype=torch.int32, device=self.device)
+        self.setTruncDist(self.trunc_dist_)
+        self.clear()
+
+    def getDims(self):
+        return self.dims_
+
+    def getVoxelSize(self):
+        return (self.size_ / self.dims_.astype(np.float32)).astype(np.float32)
+
+    def getSize(self):
+        return self.size_
+
+    def setSize(self, size):
+        self.size_ = np.asarray(size, np.float32).reshape(3)
+        self.setTruncDist(self.trunc_dist_)
+
+    def getTruncDist(self):
+        return self.trunc_dist_
+
+    def setTruncDist(self, distance):
+        vsz = self.getVoxelSize()
+        self.trunc_dist_ = float(max(np.float32(distance), np.float32(2.1) * vsz.max()))   # tsdf_volume.cpp:68-73
+
+    def setMaxWeight(self, w):
+        self.max_weight_ = int(w)
+
+    def getMaxWeight(self):
+        return self.max_weight_
+
+    def setPose(self, pose):
+        self.pose_ = (np.asarray(pose[0], np.float32), np.asarray(pose[1], np.float32))
+
+    def getPose(self):
+        return self.pose_
+
+    def setRaycastStepFactor(self, f):
+        self.raycast_step_factor_ = float(f)
+
+    def setGradientDeltaFactor(self, f):
+        self.gradient_delta_factor_ = float(f)
+
+    def applyAffine(self, affine):
+        self.pose_ = aff_mul(affine, self.pose_)
+
+    def _vol(self) -> capi.Volume:
+        return capi.make_volume(self.data_.data_ptr(), self.dims_, self.getVoxelSize(), self.trunc_dist_, self.max_weight_)
+
+    def clear(self):
+        capi.check(_lib().df_clear_volume(self._vol(), _stream()))
+
+    def integrate(self, dists: torch.Tensor, camera_pose, intr, n_updated: torch.Tensor | None = None):
+        vol2cam = aff_mul(aff_inv(camera_pose), self.pose_)                           # tsdf_volume.cpp:112
+        rows, cols = dists.shape
+        capi.check(_lib().df_integrate(self._vol(), dists.data_ptr(), cols * 2, cols, rows, capi.make_aff(*vol2cam),
+                                       capi.make_intr(*intr), n_updated.data_ptr() if n_updated is not None else None, _stream()))
+        return vol2cam
+
+    def raycast(self, camera_pose, intr, cols: int, rows: int):
+        cam2vol = aff_mul(aff_inv(self.pose_), camera_pose)                           # tsdf_volume.cpp:162
+        Rinv = np.linalg.inv(cam2vol[0].astype(np.float64)).astype(np.float32)
+        pts = torch.empty((rows, cols, 4), dtype=torch.float32, device=self.device)
+        nrm = torch.empty_like(pts)
+        capi.check(_lib().df_raycast_points(self._vol(), capi.make_aff(*cam2vol), capi.f9(Rinv), capi.make_intr(*intr), cols, rows,
+                                            self.raycast_step_factor_, self.gradient_delta_factor_, pts.data_ptr(), cols * 16,
+                                            nrm.data_ptr(), cols * 16, _stream()))
+        return pts, nrm, (cam2vol, Rinv)
+
+    def project_and_remove(self, dists: torch.Tensor, intr, points: torch.Tensor):
+        rows, cols = dists.shape
+        prow, pcol = points.shape[:2]
+        need = _lib().df_project_workspace_bytes(cols, rows)
+        if self._proj_ws is None or self._proj_ws.numel() < need:
+            self._proj_ws = torch.zeros(need, dtype=torch.uint8, device=self.device)
+        capi.check(_lib().df_project_and_remove(dists.data_ptr(), cols * 2, cols, rows, capi.make_intr(*intr), points.data_ptr(),
+                                                pcol * 16, pcol, prow, self._proj_ws.data_ptr(), _stream()))
+
+    def fetchCloud(self, capacity: int = 256 * 256 * 256):
+        """returns (points [capacity,4] device tensor, count device int32 tensor) -- no host sync"""
+        need = _lib().df_extract_workspace_bytes(self._vol())
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        out = torch.empty((capacity, 4), dtype=torch.float32, device=self.device)
+        count = torch.zeros(1, dtype=torch.int32, device=self.device)
+        capi.check(_lib().df_extract_cloud(self._vol(), capi.make_aff(*self.pose_), out.data_ptr(), capacity, count.data_ptr(),
+                                           self._ws.data_ptr(), _stream()))
+        return out, count
+
+    def fetchNormals(self, cloud: torch.Tensor, n: int, count_dev: torch.Tensor | None = None):
+        Rinv = np.linalg.inv(self.pose_[0].astype(np.float64)).astype(np.float32)
+        out = torch.empty((max(n, 1), 4), dtype=torch.float32, device=self.device)
+        capi.check(_lib().df_extract_normals(self._vol(), cloud.data_ptr(), n, count_dev.data_ptr() if count_dev is not None else None,
+                                             capi.make_aff(*self.pose_), capi.f9(Rinv), self.gradient_delta_factor_, out.data_ptr(), _stream()))
+        return out[:n]
+
+
+# ------------------------------------------------------------------ ProjectiveICP ------------------------------------------------------------
+class ProjectiveICP:
+    """cuda::ProjectiveICP (projective_icp.hpp:9-46); defaults projective_icp.cpp:68-76"""
+    MAX_PYRAMID_LEVELS = 4
+
+    def __init__(self, device="cuda"):
+        self.device = device
+        self.angle_thres_ = 20.0 * 0.017453293
+        self.dist_thres_ = 0.1
+        self.iters_ = [10, 5, 4, 0]
+        self._T = torch.zeros(12, dtype=torch.float32, device=device)
+        self._ok = torch.zeros(1, dtype=torch.int32, device=device)
+        self._scratch = torch.zeros(32, dtype=torch.float64, device=device)
+
+    def setDistThreshold(self, d):
+        self.dist_thres_ = float(d)
+
+    def setAngleThreshold(self, a):
+        self.angle_thres_ = float(a)
+
+    def setIterationsNum(self, iters):
+        it = list(iters)[: self.MAX_PYRAMID_LEVELS]
+        self.iters_ = it + [0] * (self.MAX_PYRAMID_LEVELS - len(it))
+
+    def getUsedLevelsNum(self):
+        i = self.MAX_PYRAMID_LEVELS - 1
+        while i >= 0 and not self.iters_[i]:
+            i -= 1
+        return i + 1
+
+    def accumulate(self, vcurr, ncurr, vprev, nprev, intr_level, T):
+        rows, cols = vcurr.shape[:2]
+        out = torch.zeros(27, dtype=torch.float64, device=self.device)
+        capi.check(_lib().df_icp_accumulate(vcurr.data_ptr(), cols * 16, ncurr.data_ptr(), cols * 16, vprev.data_ptr(), cols * 16,
+                                            nprev.data_ptr(), cols * 16, cols, rows, capi.make_intr(*intr_level), capi.make_aff(*T),
+                                            self.dist_thres_ * self.dist_thres_, math.cos(self.angle_thres_), out.data_ptr(), _stream()))
+        return out
+
+    def estimateTransform(self, intr, vcurr, ncurr, vprev, nprev):
+        """returns (ok, (R, t)) -- syncs to read the result (the fused pipeline never does)"""
+        L = self.getUsedLevelsNum()
+        vp = lambda xs: (C.c_void_p * L)(*[x.data_ptr() for x in xs[:L]])
+        cols = (C.c_int * L)(*[x.shape[1] for x in vcurr[:L]])
+        rows = (C.c_int * L)(*[x.shape[0] for x in vcurr[:L]])
+        pitch = (C.c_size_t * L)(*[x.shape[1] * 16 for x in vcurr[:L]])
+        it = (C.c_int * L)(*self.iters_[:L])
+        capi.check(_lib().df_icp_estimate(vp(vcurr), vp(ncurr), vp(vprev), vp(nprev), cols, rows, pitch, L, it, capi.make_intr(*intr),
+                                          self.dist_thres_, self.angle_thres_, self._T.data_ptr(), self._ok.data_ptr(),
+                                          self._scratch.data_ptr(), _stream()))
+        T = self._T.cpu().numpy()
+        return bool(self._ok.item()), (T[:9].reshape(3, 3).copy(), T[9:].copy())
+
+
+# ------------------------------------------------------------------ WarpField ----------------------------------------------------------------
+NODE_STRIDE = 12
+KNN_NEIGHBOURS = 8
+
+
+class WarpField:
+    """kfusion::WarpField (warp_field.hpp:41-88).  Nodes live on the device as [M, 12] float32 (see dfusion.h)."""
+
+    def __init__(self, device="cuda"):
+        self.device = device
+        self.nodes_ = torch.zeros((0, NODE_STRIDE), dtype=torch.float32, device=device)
+        self.warp_to_live_ = identity_pose()
+        self._ws = None
+
+    def init(self, first_frame):
+        """WarpField::init(std::vector<Vec3f>) (warp_field.cpp:70-88): every non-NaN point becomes a node with the
+        identity DualQuaternion() (rot (1,0,0,0), dual (1,0,0,0)) and weight 3*voxel_size with voxel_size forced to 1."""
+        v = np.asarray(first_frame, np.float32).reshape(-1, 3)
+        v = v[~np.isnan(v[:, 0])]
+        n = np.zeros((len(v), NODE_STRIDE), np.float32)
+        n[:, 0:3] = v
+        n[:, 3] = 1.0
+        n[:, 7] = 1.0
+        n[:, 11] = 3.0
+        self.nodes_ = torch.from_numpy(n).to(self.device)
+
+    def setWarpToLive(self, pose):
+        self.warp_to_live_ = pose
+
+    def getNodes(self):
+        return self.nodes_
+
+    def KNN(self, points: torch.Tensor):
+        N, stride = points.shape
+        idx = torch.empty((N, 8), dtype=torch.int32, device=self.device)
+        d2 = torch.empty((N, 8), dtype=torch.float32, device=self.device)
+        capi.check(_lib().df_knn8(self.nodes_.data_ptr(), self.nodes_.shape[0], points.data_ptr(), N, stride, idx.data_ptr(), d2.data_ptr(), _stream()))
+        return idx, d2
+
+    def warp(self, points: torch.Tensor, normals: torch.Tensor, flags: int = 0, want_knn: bool = False):
+        N, stride = points.shape
+        idx = w = None
+        if want_knn:
+            idx = torch.empty((N, 8), dtype=torch.int32, device=self.device)
+            w = torch.empty((N, 8), dtype=torch.float32, device=self.device)
+        capi.check(_lib().df_warp(self.nodes_.data_ptr(), self.nodes_.shape[0], points.data_ptr(), normals.data_ptr(), N, stride,
+                                  capi.make_aff(*self.warp_to_live_), flags, idx.data_ptr() if want_knn else None,
+                                  w.data_ptr() if want_knn else None, _stream()))
+        return idx, w
+
+    def optimiseWarpData(self, canonical: torch.Tensor, live: torch.Tensor, nonlinear_iters=5, linear_iters=100, flags=0):
+        """WarpFieldOptimiser::optimiseWarpData (warp_field_optimiser.cpp:7-16) -> device LM/PCG"""
+        N, stride = canonical.shape
+        M = self.nodes_.shape[0]
+        need = _lib().df_solve_workspace_bytes(M, N)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        stats = torch.zeros(4, dtype=torch.float64, device=self.device)
+        capi.check(_lib().df_solve_data_term(self.nodes_.data_ptr(), M, canonical.data_ptr(), live.data_ptr(), N, stride, nonlinear_iters,
+                                             linear_iters, flags, stats.data_ptr(), self._ws.data_ptr(), _stream()))
+        return stats

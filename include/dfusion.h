@@ -1,0 +1,154 @@
+/*
+ * dfusion.h -- C ABI of the B200-native DynamicFusion hot path (libdfusion.so).
+ *
+ * The reference (mihaibujanca/dynamicfusion) has no FFI layer; its seam is the internal launcher layer
+ * `kfusion::device::*` declared in kfusion/src/internal.hpp:105-147, called by the host classes
+ * cuda::TsdfVolume / cuda::ProjectiveICP / imgproc free functions / WarpField / KinFu.  Every entry point
+ * below replaces one of those launchers (cited per function) and is what the C++ mirror classes in
+ * include/kfusion/ (and the ctypes binding in dynamicfusion_b200/capi.py) bind.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - 2-D images are (ptr, pitch in BYTES, cols, rows), as kfusion::cuda::PtrStepSz (kernel_containers.hpp:37-63);
+ *   - float4 maps hold (x, y, z, w) per pixel: kfusion::Point / Normal (types.hpp:31-42);
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream); calls are asynchronous unless stated;
+ *   - return value: 0 on success, otherwise a cudaError_t value (df_error_string() describes it).  The C++
+ *     mirror turns a non-zero status into the reference's behaviour (print "KinFu2 error: ..." and exit,
+ *     device_memory.cpp:7-11).
+ * No torch / C++ types cross this boundary.
+ */
+#ifndef DFUSION_H
+#define DFUSION_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* device::TsdfVolume POD (internal.hpp:29-49).  data: one u32 per voxel, low 16 bits = fp16 TSDF, high 16 bits =
+ * u16 weight (ushort2{x,y}); linear index x + y*dims[0] + z*dims[0]*dims[1] (device.hpp:17-27). */
+typedef struct df_volume {
+    uint32_t *data;
+    int dims[3];
+    float voxel_size[3];
+    float trunc_dist;
+    int max_weight;
+} df_volume;
+
+/* device::Aff3f (internal.hpp:26-27): R row-major, then t */
+typedef struct df_aff3f { float R[9]; float t[3]; } df_aff3f;
+/* kfusion::Intr (types.hpp:20-27) */
+typedef struct df_intr { float fx, fy, cx, cy; } df_intr;
+
+const char *df_error_string(int status);
+int df_version(void);
+
+/* ------------------------------------------------------------------ TSDF volume ---------------------------------------------------------- */
+/* device::clear_volume (internal.hpp:105, tsdf_volume.cu:15-41) */
+int df_clear_volume(df_volume vol, void *stream);
+
+/* device::compute_dists (internal.hpp:121, imgproc.cu:259-294): u16 mm depth -> fp16 metric ray length */
+int df_compute_dists(const uint16_t *depth, size_t depth_pitch, int cols, int rows, df_intr intr,
+                     uint16_t *dists, size_t dists_pitch, void *stream);
+
+/* device::integrate (internal.hpp:106, tsdf_volume.cu:51-112,141-161).  vol2cam = camera_pose^-1 * volume_pose
+ * (tsdf_volume.cpp:112).  If n_updated (device, u64) is non-NULL the number of voxels written is ADDED to it. */
+int df_integrate(df_volume vol, const uint16_t *dists, size_t dists_pitch, int cols, int rows,
+                 df_aff3f vol2cam, df_intr intr, unsigned long long *n_updated, void *stream);
+
+/* device::raycast, points variant (internal.hpp:113-114, tsdf_volume.cu:341-405,459-474).
+ * cam2vol = volume_pose^-1 * camera_pose, Rinv = cam2vol.R^-1 (tsdf_volume.cpp:157-174). */
+int df_raycast_points(df_volume vol, df_aff3f cam2vol, const float *Rinv_host9, df_intr intr, int cols, int rows,
+                      float step_factor, float delta_factor,
+                      float *points, size_t points_pitch, float *normals, size_t normals_pitch, void *stream);
+
+/* device::project_and_remove (internal.hpp:108-109, tsdf_volume.cu:114-137,164-177): `dists` is sampled as fp16 and
+ * the pixels the vertices land on are zeroed; vertices become (u*Dp, v*Dp, Dp, 0) or NaN when off-image.
+ * Deterministic (the reference races the scatter with the sampling): samples always see the original image.
+ * workspace: df_project_workspace_bytes(cols, rows) bytes, zero on entry, returned zeroed. */
+size_t df_project_workspace_bytes(int cols, int rows);
+int df_project_and_remove(uint16_t *dists, size_t dists_pitch, int cols, int rows, df_intr intr,
+                          float *points, size_t points_pitch, int pcols, int prows, void *workspace, void *stream);
+
+/* device::extractCloud (internal.hpp:138, tsdf_volume.cu:486-710,799-815).  Deterministic: points are emitted in
+ * ascending (z, y, x) voxel order, +x,+y,+z edge within a voxel.  `workspace` needs df_extract_workspace_bytes();
+ * the point count (clamped to capacity) is written to *count (device, int32) -- no host sync. */
+size_t df_extract_workspace_bytes(df_volume vol);
+int df_extract_cloud(df_volume vol, df_aff3f pose, float *out_points, int capacity, int *count,
+                     void *workspace, void *stream);
+
+/* device::extractNormals (internal.hpp:139, tsdf_volume.cu:714-795,817-831).  n_points may be given on the host
+ * (count_dev == NULL) or read from device memory (count_dev != NULL, upper bound n_points). */
+int df_extract_normals(df_volume vol, const float *points, int n_points, const int *count_dev, df_aff3f pose,
+                       const float *Rinv_host9, float delta_factor, float *out_normals, void *stream);
+
+/* ------------------------------------------------------------------ image processing ----------------------------------------------------- */
+/* device::bilateralFilter (internal.hpp:125, imgproc.cu:11-57) */
+int df_bilateral(const uint16_t *src, size_t src_pitch, int cols, int rows, uint16_t *dst, size_t dst_pitch,
+                 int kernel_size, float sigma_spatial, float sigma_depth, void *stream);
+/* device::truncateDepth (internal.hpp:124, imgproc.cu:66-85) */
+int df_truncate_depth(uint16_t *depth, size_t pitch, int cols, int rows, float max_dist, void *stream);
+/* device::depthPyr (internal.hpp:126, imgproc.cu:94-136): dst is (src_cols/2, src_rows/2) */
+int df_pyr_down(const uint16_t *src, size_t src_pitch, int src_cols, int src_rows, uint16_t *dst, size_t dst_pitch,
+                float sigma_depth, void *stream);
+/* device::computePointNormals (internal.hpp:132, imgproc.cu:210-250) */
+int df_points_normals(df_intr intr, const uint16_t *depth, size_t depth_pitch, int cols, int rows,
+                      float *points, size_t points_pitch, float *normals, size_t normals_pitch, void *stream);
+/* device::resizePointsNormals (internal.hpp:129, imgproc.cu:368-414): dst is (src_cols/2, src_rows/2) */
+int df_resize_points_normals(const float *vsrc, size_t vsrc_pitch, const float *nsrc, size_t nsrc_pitch,
+                             int src_cols, int src_rows, float *vdst, size_t vdst_pitch, float *ndst, size_t ndst_pitch,
+                             void *stream);
+
+/* ------------------------------------------------------------------ projective ICP -------------------------------------------------------- */
+/* ComputeIcpHelper::operator() points variant (internal.hpp:67-102, proj_icp.cu:80-108,350-394,448-467): one
+ * data-association + 27-term reduction pass at one pyramid level.  out27 (device, 27 doubles, order (i, j>=i) for
+ * i = 0..5, j = 0..6) is OVERWRITTEN.  intr_level are the level's intrinsics (setLevelIntr, projective_icp.cpp:17-23). */
+int df_icp_accumulate(const float *vcurr, size_t vcurr_pitch, const float *ncurr, size_t ncurr_pitch,
+                      const float *vprev, size_t vprev_pitch, const float *nprev, size_t nprev_pitch,
+                      int cols, int rows, df_intr intr_level, df_aff3f T, float dist2_thres, float min_cosine,
+                      double *out27, void *stream);
+
+/* ProjectiveICP::estimateTransform, points variant (projective_icp.hpp:39, projective_icp.cpp:169-213) executed
+ * entirely on the device: per iteration the association/reduction kernel, then the 6x6 solve + Rodrigues update in a
+ * one-thread tail (replaces StreamHelper::get + cv::solve + 19 host round trips).  Arrays of `levels` entries, index 0 =
+ * finest.  T_dev (device, 12 floats: R row-major + t) receives curr->prev; ok_dev (device int) is 0 when the
+ * reference would have returned false (|det| < 1e-15 or NaN). */
+int df_icp_estimate(const float *const *vcurr, const float *const *ncurr, const float *const *vprev, const float *const *nprev,
+                    const int *cols, const int *rows, const size_t *pitch, int levels, const int *iters,
+                    df_intr intr, float dist_thres, float angle_thres, float *T_dev, int *ok_dev, double *scratch27,
+                    void *stream);
+
+/* ------------------------------------------------------------------ warp field ------------------------------------------------------------ */
+/* deformation_node (warp_field.hpp:35-40) as 12 floats: vertex[3], rotation quat (w,x,y,z), dual/translation quat
+ * (w,x,y,z) = 0.5*t*r (dual_quaternion.hpp:59-63), weight. */
+#define DF_NODE_STRIDE 12
+#define DF_KNN 8                          /* KNN_NEIGHBOURS, warp_field.hpp:10 */
+
+/* WarpField::KNN (warp_field.hpp:66, warp_field.cpp:247-251) for N queries: exact 8-NN, ascending squared distance,
+ * ties -> lower node index; idx = -1 / d2 = FLT_MAX for NaN queries or when M < 8.  qstride in floats. */
+int df_knn8(const float *nodes, int M, const float *queries, int N, int qstride, int32_t *idx, float *d2, void *stream);
+
+/* WarpField::warp (warp_field.hpp:62, warp_field.cpp:180-195): k-NN + weights + DQB + transform of points and
+ * normals in place (stride in floats, 3 or 4).  flags: bit0 = reference normal cursor (advance only on valid points),
+ * bit1 = rotate normals only (extension).  idx_out / w_out (optional, N*8) receive the neighbours and weights. */
+#define DF_WARP_REF_NORMAL_INDEX 1
+#define DF_WARP_NORMAL_ROTATE_ONLY 2
+int df_warp(const float *nodes, int M, float *points, float *normals, int N, int stride, df_aff3f warp_to_live, int flags,
+            int32_t *idx_out, float *w_out, void *stream);
+
+/* WarpFieldOptimiser::optimiseWarpData (warp_field_optimiser.hpp:14-17) -> CombinedSolver (CombinedSolver.h:25-110)
+ * -> Opt LM/PCG on kfusion/solvers/dynamicfusion.t: translation-only data term solved on the device; node
+ * translations are updated in place (encodeTranslation, CombinedSolver.h:189-197).
+ * params: nonlinear (LM) iterations, linear (PCG) iterations; stats_dev (device, 4 doubles): initial cost, final cost,
+ * LM iterations run, valid rows.  workspace from df_solve_workspace_bytes(M, N). */
+size_t df_solve_workspace_bytes(int M, int N);
+#define DF_SOLVE_REF_GRAPH_QUIRK 1
+int df_solve_data_term(float *nodes, int M, const float *canon, const float *live, int N, int stride,
+                       int nonlinear_iters, int linear_iters, int flags, double *stats_dev, void *workspace, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFUSION_H */

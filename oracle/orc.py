@@ -1,0 +1,248 @@
+"""ctypes/numpy binding of the CPU oracle (oracle/liborc.so).  TEST INFRASTRUCTURE ONLY:
+importable from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg, never from
+dynamicfusion_b200/ (tests/test_no_oracle_in_product.py enforces it)."""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+LIB = HERE / "liborc.so"
+_lib = None
+
+
+class Volume(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("dims", C.c_int * 3), ("voxel_size", C.c_float * 3),
+                ("trunc_dist", C.c_float), ("max_weight", C.c_int)]
+
+
+class Aff3f(C.Structure):
+    _fields_ = [("R", C.c_float * 9), ("t", C.c_float * 3)]
+
+
+class Intr(C.Structure):
+    _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float)]
+
+
+def build(force: bool = False) -> Path:
+    srcs = list(HERE.glob("orc_*.c")) + [HERE / "orc_common.h", HERE / "Makefile"]
+    if force or not LIB.exists() or any(s.stat().st_mtime > LIB.stat().st_mtime for s in srcs):
+        subprocess.run(["make", "-C", str(HERE), "-B", "liborc.so"], check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    return LIB
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not LIB.exists():
+            build()
+        _lib = C.CDLL(str(LIB))
+        _lib.orc_integrate.restype = C.c_longlong
+        _lib.orc_extract_cloud.restype = C.c_longlong
+        _lib.orc_icp_accumulate.restype = C.c_longlong
+        _lib.orc_float2half_rn.restype = C.c_uint16
+        _lib.orc_float2half_rn.argtypes = [C.c_float]
+        _lib.orc_half2float.restype = C.c_float
+        _lib.orc_half2float.argtypes = [C.c_uint16]
+        _lib.orc_interpolate.restype = C.c_float
+    return _lib
+
+
+def aff(R, t) -> Aff3f:
+    a = Aff3f()
+    R = np.asarray(R, np.float32).reshape(9)
+    t = np.asarray(t, np.float32).reshape(3)
+    for i in range(9):
+        a.R[i] = float(R[i])
+    for i in range(3):
+        a.t[i] = float(t[i])
+    return a
+
+
+def intr(fx, fy, cx, cy) -> Intr:
+    return Intr(float(fx), float(fy), float(cx), float(cy))
+
+
+def volume(data: np.ndarray, dims, voxel_size, trunc, max_weight) -> Volume:
+    assert data.dtype == np.uint32 and data.flags.c_contiguous
+    v = Volume()
+    v.data = data.ctypes.data
+    for i in range(3):
+        v.dims[i] = int(dims[i])
+        v.voxel_size[i] = float(voxel_size[i])
+    v.trunc_dist = float(trunc)
+    v.max_weight = int(max_weight)
+    return v
+
+
+def _p(a: np.ndarray):
+    assert a.flags.c_contiguous
+    return C.c_void_p(a.ctypes.data)
+
+
+def _f9(R):
+    arr = (C.c_float * 9)(*[float(v) for v in np.asarray(R, np.float32).reshape(9)])
+    return arr
+
+
+# ------------------------------------------------------------------ wrappers (numpy in / numpy out) ------------------------------------------
+def clear_volume(vol_data, dims, vs, trunc, mw):
+    load().orc_clear_volume(volume(vol_data, dims, vs, trunc, mw))
+
+
+def compute_dists(depth: np.ndarray, K) -> np.ndarray:
+    rows, cols = depth.shape
+    out = np.empty_like(depth)
+    load().orc_compute_dists(_p(depth), C.c_size_t(cols * 2), cols, rows, intr(*K), _p(out), C.c_size_t(cols * 2))
+    return out
+
+
+def integrate(vol_data, dims, vs, trunc, mw, dists, vol2cam, K) -> int:
+    rows, cols = dists.shape
+    return int(load().orc_integrate(volume(vol_data, dims, vs, trunc, mw), _p(dists), C.c_size_t(cols * 2), cols, rows,
+                                    aff(*vol2cam), intr(*K)))
+
+
+def raycast_points(vol_data, dims, vs, trunc, mw, cam2vol, Rinv, K, cols, rows, step_factor, delta_factor):
+    pts = np.empty((rows, cols, 4), np.float32)
+    nrm = np.empty((rows, cols, 4), np.float32)
+    stats = (C.c_longlong * 3)()
+    load().orc_raycast_points(volume(vol_data, dims, vs, trunc, mw), aff(*cam2vol), _f9(Rinv), intr(*K), cols, rows,
+                              C.c_float(step_factor), C.c_float(delta_factor), _p(pts), C.c_size_t(cols * 16), _p(nrm),
+                              C.c_size_t(cols * 16), stats)
+    return pts, nrm, [int(s) for s in stats]
+
+
+def project_and_remove(dists: np.ndarray, K, points: np.ndarray):
+    rows, cols = dists.shape
+    prow, pcol = points.shape[:2]
+    load().orc_project_and_remove(_p(dists), C.c_size_t(cols * 2), cols, rows, intr(*K), _p(points), C.c_size_t(pcol * 16), pcol, prow)
+
+
+def extract_cloud(vol_data, dims, vs, trunc, mw, pose, capacity) -> np.ndarray:
+    out = np.empty((capacity, 4), np.float32)
+    n = int(load().orc_extract_cloud(volume(vol_data, dims, vs, trunc, mw), aff(*pose), _p(out), C.c_longlong(capacity)))
+    return out[:n].copy()
+
+
+def extract_normals(vol_data, dims, vs, trunc, mw, pts, pose, Rinv, delta_factor) -> np.ndarray:
+    out = np.empty_like(pts)
+    load().orc_extract_normals(volume(vol_data, dims, vs, trunc, mw), _p(pts), C.c_longlong(len(pts)), aff(*pose), _f9(Rinv),
+                               C.c_float(delta_factor), _p(out))
+    return out
+
+
+def bilateral(depth, ksz, sigma_spatial, sigma_depth):
+    rows, cols = depth.shape
+    out = np.empty_like(depth)
+    load().orc_bilateral(_p(depth), C.c_size_t(cols * 2), cols, rows, _p(out), C.c_size_t(cols * 2), ksz, C.c_float(sigma_spatial),
+                         C.c_float(sigma_depth))
+    return out
+
+
+def truncate_depth(depth, max_dist):
+    rows, cols = depth.shape
+    load().orc_truncate_depth(_p(depth), C.c_size_t(cols * 2), cols, rows, C.c_float(max_dist))
+
+
+def pyr_down(depth, sigma_depth):
+    rows, cols = depth.shape
+    out = np.empty((rows // 2, cols // 2), np.uint16)
+    load().orc_pyr_down(_p(depth), C.c_size_t(cols * 2), cols, rows, _p(out), C.c_size_t((cols // 2) * 2), C.c_float(sigma_depth))
+    return out
+
+
+def points_normals(K, depth):
+    rows, cols = depth.shape
+    pts = np.empty((rows, cols, 4), np.float32)
+    nrm = np.empty((rows, cols, 4), np.float32)
+    load().orc_points_normals(intr(*K), _p(depth), C.c_size_t(cols * 2), cols, rows, _p(pts), C.c_size_t(cols * 16), _p(nrm), C.c_size_t(cols * 16))
+    return pts, nrm
+
+
+def resize_points_normals(v, n):
+    rows, cols = v.shape[:2]
+    vd = np.empty((rows // 2, cols // 2, 4), np.float32)
+    nd = np.empty((rows // 2, cols // 2, 4), np.float32)
+    load().orc_resize_points_normals(_p(v), C.c_size_t(cols * 16), _p(n), C.c_size_t(cols * 16), cols, rows, _p(vd),
+                                     C.c_size_t((cols // 2) * 16), _p(nd), C.c_size_t((cols // 2) * 16))
+    return vd, nd
+
+
+def icp_accumulate(vcurr, ncurr, vprev, nprev, K_level, T, dist2, min_cos):
+    rows, cols = vcurr.shape[:2]
+    out = np.zeros(27, np.float64)
+    n = load().orc_icp_accumulate(_p(vcurr), C.c_size_t(cols * 16), _p(ncurr), C.c_size_t(cols * 16), _p(vprev), C.c_size_t(cols * 16),
+                                  _p(nprev), C.c_size_t(cols * 16), cols, rows, intr(*K_level), aff(*T), C.c_float(dist2),
+                                  C.c_float(min_cos), _p(out))
+    return out, int(n)
+
+
+def icp_solve_update(sums27, T):
+    a = aff(*T)
+    s = np.ascontiguousarray(sums27, np.float64)
+    ok = load().orc_icp_solve_update(_p(s), C.byref(a))
+    return bool(ok), (np.array(list(a.R), np.float32).reshape(3, 3), np.array(list(a.t), np.float32))
+
+
+def icp_estimate(vcurr, ncurr, vprev, nprev, iters, K, dist_thres, angle_thres):
+    L = len(vcurr)
+    arr = lambda xs: (C.c_void_p * L)(*[x.ctypes.data for x in xs])
+    cols = (C.c_int * L)(*[x.shape[1] for x in vcurr])
+    rows = (C.c_int * L)(*[x.shape[0] for x in vcurr])
+    pitch = (C.c_size_t * L)(*[x.shape[1] * 16 for x in vcurr])
+    it = (C.c_int * L)(*iters[:L])
+    a = Aff3f()
+    ok = load().orc_icp_estimate(arr(vcurr), arr(ncurr), arr(vprev), arr(nprev), cols, rows, pitch, L, it, intr(*K),
+                                 C.c_float(dist_thres), C.c_float(angle_thres), C.byref(a))
+    return bool(ok), (np.array(list(a.R), np.float32).reshape(3, 3), np.array(list(a.t), np.float32))
+
+
+NODE_STRIDE = 12
+
+
+def make_nodes(vertices, weight=3.0) -> np.ndarray:
+    """deformation_node defaults (warp_field.cpp:68-80): identity DualQuaternion() = rot (1,0,0,0), dual (1,0,0,0)"""
+    v = np.asarray(vertices, np.float32).reshape(-1, 3)
+    n = np.zeros((len(v), NODE_STRIDE), np.float32)
+    n[:, 0:3] = v
+    n[:, 3] = 1.0
+    n[:, 7] = 1.0
+    n[:, 11] = weight
+    return n
+
+
+def knn8(nodes, queries):
+    q = np.ascontiguousarray(queries, np.float32)
+    N, stride = q.shape
+    idx = np.empty((N, 8), np.int32)
+    d2 = np.empty((N, 8), np.float32)
+    load().orc_knn8(_p(nodes), len(nodes), _p(q), C.c_longlong(N), stride, _p(idx), _p(d2))
+    return idx, d2
+
+
+def warp(nodes, points, normals, warp_to_live=None, flags=0):
+    """in place on float32 (N, stride) arrays"""
+    if warp_to_live is None:
+        warp_to_live = (np.eye(3, dtype=np.float32), np.zeros(3, np.float32))
+    N, stride = points.shape
+    load().orc_warp(_p(nodes), len(nodes), _p(points), _p(normals), C.c_longlong(N), stride, aff(*warp_to_live), flags)
+
+
+def node_translations(nodes) -> np.ndarray:
+    out = np.empty((len(nodes), 4), np.float32)
+    for i in range(len(nodes)):
+        load().orc_node_translation(C.c_void_p(nodes[i].ctypes.data), C.c_void_p(out[i].ctypes.data))
+    return out
+
+
+def solve_data_term(nodes, canon, live, flags=0, lm_iters=5):
+    c = np.ascontiguousarray(canon, np.float32)
+    l = np.ascontiguousarray(live, np.float32)
+    N, stride = c.shape
+    stats = np.zeros(4, np.float64)
+    load().orc_solve_data_term(_p(nodes), len(nodes), _p(c), _p(l), C.c_longlong(N), stride, flags, lm_iters, _p(stats))
+    return stats

@@ -1,0 +1,139 @@
+/*
+ * CPU ORACLE -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Plain-C restatement of the reference's per-frame hot path (mihaibujanca/dynamicfusion).
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
+ * load this library.  The product path (dynamicfusion_b200/) never links or calls it.
+ *
+ * Numerics policy: every operation is the IEEE-754 single-precision
+ * operation at the SAME POSITION and in the SAME ORDER as the reference .cu/.cpp; the
+ * approximate intrinsics of the legacy build (__fdividef, rsqrt, __expf, --prec-div=false,
+ * --prec-sqrt=false, --ftz=true) are restated as '/', 1/sqrtf, expf with round-to-nearest.
+ * Multiply-adds are fused ONLY where the reference writes __fmaf_rn explicitly
+ * (compile with -ffp-contract=off).
+ *
+ * PARITY STATUS: the reference's own .cu kernels cannot be compiled by CUDA 12.9 (texture
+ * references were removed), and the reference has no tests/fixtures for integrate / raycast /
+ * extract / ICP / imgproc.  Those stages are pinned by oracle/_ref (the reference's own kernel
+ * SOURCE compiled for the host through a CUDA-on-CPU shim, see oracle/ref_shim/) where that
+ * builds; otherwise "parity unpinned".  Quaternion / dual-quaternion / k-NN / warp-solve are
+ * pinned by the golden vectors in the reference's tests/ (see tests/test_oracle_golden.py).
+ */
+#ifndef ORC_COMMON_H
+#define ORC_COMMON_H
+
+#include <math.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <string.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { float x, y, z; } orc_f3;
+
+/* mirrors device::TsdfVolume POD, kfusion/src/internal.hpp:29-49 */
+typedef struct {
+    uint32_t *data;      /* ushort2{x = f16 tsdf bits, y = u16 weight}: low 16 bits = tsdf */
+    int dims[3];
+    float voxel_size[3];
+    float trunc_dist;
+    int max_weight;
+} orc_volume;
+
+/* device::Aff3f, internal.hpp:26-27: R row-major, then t */
+typedef struct { float R[9]; float t[3]; } orc_aff3f;
+typedef struct { float fx, fy, cx, cy; } orc_intr;
+
+/* ---- float helpers in the reference's operation order (temp_utils.hpp:27-105) ---- */
+static inline orc_f3 f3(float x, float y, float z) { orc_f3 r = {x, y, z}; return r; }
+static inline float orc_dot(orc_f3 a, orc_f3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
+static inline orc_f3 orc_add(orc_f3 a, orc_f3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+static inline orc_f3 orc_sub(orc_f3 a, orc_f3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+static inline orc_f3 orc_mul(orc_f3 a, orc_f3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
+static inline orc_f3 orc_scale(orc_f3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+static inline orc_f3 orc_cross(orc_f3 a, orc_f3 b)
+{ return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+/* normalized(v) = v * rsqrt(dot(v,v))  (temp_utils.hpp:95-98); rsqrt restated as 1/sqrtf */
+static inline orc_f3 orc_normalized(orc_f3 v) { return orc_scale(v, 1.0f / sqrtf(orc_dot(v, v))); }
+/* Mat3f * v and Aff3f * v, device.hpp:71-74 */
+static inline orc_f3 orc_mat_mul(const float *R, orc_f3 v)
+{ return f3(orc_dot(f3(R[0], R[1], R[2]), v), orc_dot(f3(R[3], R[4], R[5]), v), orc_dot(f3(R[6], R[7], R[8]), v)); }
+static inline orc_f3 orc_aff_mul(const orc_aff3f *a, orc_f3 v)
+{ return orc_add(orc_mat_mul(a->R, v), f3(a->t[0], a->t[1], a->t[2])); }
+
+/* __float2half_rn / __half2float (device.hpp:53-61) */
+uint16_t orc_float2half_rn(float f);
+float orc_half2float(uint16_t h);
+
+static inline uint32_t orc_pack_tsdf(float tsdf, int weight)
+{ return (uint32_t)orc_float2half_rn(tsdf) | ((uint32_t)(uint16_t)weight << 16); }
+static inline float orc_unpack_tsdf(uint32_t v, int *weight)
+{ if (weight) *weight = (int)(v >> 16); return orc_half2float((uint16_t)(v & 0xffffu)); }
+
+static inline const float *orc_row_f4(const float *base, size_t pitch, int y)
+{ return (const float *)((const char *)base + (size_t)y * pitch); }
+static inline float *orc_row_f4w(float *base, size_t pitch, int y)
+{ return (float *)((char *)base + (size_t)y * pitch); }
+static inline const uint16_t *orc_row_u16(const uint16_t *base, size_t pitch, int y)
+{ return (const uint16_t *)((const char *)base + (size_t)y * pitch); }
+static inline uint16_t *orc_row_u16w(uint16_t *base, size_t pitch, int y)
+{ return (uint16_t *)((char *)base + (size_t)y * pitch); }
+
+static inline float orc_qnan(void) { union { uint32_t u; float f; } c; c.u = 0x7fffffffu; return c.f; }
+
+/* ------------------------------------------------------------------ API ------------------------------------------------------------------ */
+/* tsdf */
+void orc_clear_volume(orc_volume vol);
+void orc_compute_dists(const uint16_t *depth, size_t dpitch, int cols, int rows, orc_intr intr, uint16_t *dists, size_t pitch);
+long long orc_integrate(orc_volume vol, const uint16_t *dists, size_t pitch, int cols, int rows, orc_aff3f vol2cam, orc_intr intr);
+/* stats: [0] = hit rays, [1] = total march steps, [2] = rays entering the box */
+void orc_raycast_points(orc_volume vol, orc_aff3f cam2vol, const float *Rinv, orc_intr intr, int cols, int rows,
+                        float step_factor, float delta_factor, float *points, size_t ppitch, float *normals, size_t npitch,
+                        long long *stats);
+void orc_project_and_remove(uint16_t *dists, size_t pitch, int cols, int rows, orc_intr intr, float *points, size_t ppitch,
+                            int pcols, int prows);
+long long orc_extract_cloud(orc_volume vol, orc_aff3f pose, float *out, long long capacity);
+void orc_extract_normals(orc_volume vol, const float *pts, long long n, orc_aff3f pose, const float *Rinv, float delta_factor, float *out);
+float orc_interpolate(const orc_volume *vol, orc_f3 p_voxels);
+
+/* imgproc */
+void orc_bilateral(const uint16_t *src, size_t spitch, int cols, int rows, uint16_t *dst, size_t dpitch, int ksz,
+                   float sigma_spatial, float sigma_depth);
+void orc_truncate_depth(uint16_t *depth, size_t pitch, int cols, int rows, float max_dist);
+void orc_pyr_down(const uint16_t *src, size_t spitch, int scols, int srows, uint16_t *dst, size_t dpitch, float sigma_depth);
+void orc_points_normals(orc_intr intr, const uint16_t *depth, size_t dpitch, int cols, int rows, float *points, size_t ppitch,
+                        float *normals, size_t npitch);
+void orc_resize_points_normals(const float *vsrc, size_t vspitch, const float *nsrc, size_t nspitch, int scols, int srows,
+                               float *vdst, size_t vdpitch, float *ndst, size_t ndpitch);
+
+/* icp */
+long long orc_icp_accumulate(const float *vcurr, size_t vcpitch, const float *ncurr, size_t ncpitch, const float *vprev, size_t vppitch,
+                             const float *nprev, size_t nppitch, int cols, int rows, orc_intr intr_level, orc_aff3f T,
+                             float dist2_thres, float min_cosine, double *out27);
+int orc_icp_solve_update(const double *sums27, orc_aff3f *T);
+int orc_icp_estimate(const float *const *vcurr, const float *const *ncurr, const float *const *vprev, const float *const *nprev,
+                     const int *cols, const int *rows, const size_t *pitch, int levels, const int *iters, orc_intr intr,
+                     float dist_thres, float angle_thres, orc_aff3f *T_out);
+
+/* warp field: nodes are 12 floats each: vertex[3], rot quat (w,x,y,z), dual/translation quat (w,x,y,z), weight */
+#define ORC_NODE_STRIDE 12
+void orc_knn8(const float *nodes, int M, const float *queries, long long N, int qstride, int32_t *idx, float *d2);
+void orc_node_translation(const float *node, float *t4);
+void orc_dqb(const float *nodes, const int32_t *idx8, const float *d2_8, float *rot4, float *trans4, float *weights8);
+void orc_warp(const float *nodes, int M, float *points, float *normals, long long N, int stride, orc_aff3f warp_to_live, int flags);
+void orc_dq_from_euler(float x, float y, float z, float roll, float pitch, float yaw, float *rot4, float *dual4);
+void orc_quat_mul(const float *a, const float *b, float *out);
+void orc_quat_rotate_vec(const float *q, float *v3);
+void orc_quat_encode_rotation(float theta, float x, float y, float z, float *q);
+void orc_quat_rotate_sandwich(const float *q, float *v3);
+void orc_node_encode_translation(float *node, float x, float y, float z);
+
+/* data-term solve */
+int orc_solve_data_term(float *nodes, int M, const float *canon, const float *live, long long N, int stride, int flags, int max_lm, double *stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
