@@ -1,0 +1,320 @@
+// icp.cu -- projective point-to-plane ICP on sm_100a, fully device-resident.
+// Replaces kfusion/src/cuda/proj_icp.cu (icp_helper_kernel + 27 sequential 256-thread smem tree reductions +
+// icp_final_reduce_kernel) and the host loop of kfusion/src/projective_icp.cpp:169-213 (per iteration: D2H of 27
+// floats, stream sync, cv::determinant, cv::solve(DECOMP_SVD), Rodrigues, H2D of the pose = 19 round trips a frame).
+//
+// Per iteration two launches, no host involvement:
+//   icp_accumulate_kernel  persistent tiles; each thread forms its 7-vector row and keeps the 27 products in registers
+//                          across its tiles (float products as the reference, proj_icp.cu:137-345), then one
+//                          double-precision warp-shuffle reduction and one partial row per block (deterministic order);
+//   icp_solve_kernel       one block: fixed-order sum of the partials, 6x6 solve, Rodrigues, T <- Tinc * T in place.
+#include "df_common.cuh"
+#include <float.h>
+
+using namespace dfb;
+
+namespace {
+
+constexpr int ICP_MAX_BLOCKS = 1024;
+
+struct IcpParams {
+    const float4 *vcurr; size_t vcpitch;
+    const float4 *ncurr; size_t ncpitch;
+    const float4 *vprev; size_t vppitch;
+    const float4 *nprev; size_t nppitch;
+    int cols, rows;
+    float fcols, frows;
+    float fx, fy, cx, cy;
+    float dist2_thres, min_cosine;
+    Aff T_val;
+    const float *T_ptr;       // when non-null: 12 floats (R row-major, t) in device memory
+    const int *ok_ptr;        // when non-null and *ok_ptr == 0 the iteration is skipped
+    double *partials;         // [gridDim.x][27]
+    int tiles_x, tiles;
+};
+
+// find_coresp (points variant) proj_icp.cu:80-108 + row build :359-368
+__device__ __forceinline__ bool icp_row(const IcpParams &p, const Aff &T, int x, int y, float row[7])
+{
+    const float4 vc = __ldg(row_ptr(p.vcurr, p.vcpitch, y) + x);
+    float3 s = make_float3(vc.x, vc.y, vc.z);
+    if (isnan(s.x)) return false;
+    s = aff_mul(T, s);
+    const float u = __fmaf_rn(p.fx, s.x / s.z, p.cx);
+    const float v = __fmaf_rn(p.fy, s.y / s.z, p.cy);
+    if (s.z <= 0 || u < 0 || v < 0 || u >= p.fcols || v >= p.frows) return false;
+    if (!(u == u) || !(v == v)) return false;
+    const float4 dp = __ldg(row_ptr(p.vprev, p.vppitch, (int)v) + (int)u);     // point sampling of the previous maps
+    const float3 d = make_float3(dp.x, dp.y, dp.z);
+    if (isnan(d.x)) return false;
+    const float3 df = sub3(s, d);
+    if (dot3(df, df) > p.dist2_thres) return false;
+    const float4 nc = __ldg(row_ptr(p.ncurr, p.ncpitch, y) + x);
+    const float3 ns = mat_mul(T.r0, T.r1, T.r2, make_float3(nc.x, nc.y, nc.z));
+    const float4 np = __ldg(row_ptr(p.nprev, p.nppitch, (int)v) + (int)u);
+    const float3 nd = make_float3(np.x, np.y, np.z);
+    if (fabsf(dot3(ns, nd)) < p.min_cosine) return false;
+    const float3 c = cross3(s, nd);
+    row[0] = c.x; row[1] = c.y; row[2] = c.z; row[3] = nd.x; row[4] = nd.y; row[5] = nd.z;
+    row[6] = dot3(nd, sub3(d, s));
+    return true;
+}
+
+__global__ void __launch_bounds__(256) icp_accumulate_kernel(const IcpParams p)
+{
+    __shared__ double smem[8][27];
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    float acc[27];
+#pragma unroll
+    for (int i = 0; i < 27; ++i) acc[i] = 0.f;
+
+    const bool active = p.ok_ptr ? (*p.ok_ptr != 0) : true;
+    if (active) {
+        Aff T = p.T_val;
+        if (p.T_ptr) {
+            T.r0 = make_float3(p.T_ptr[0], p.T_ptr[1], p.T_ptr[2]);
+            T.r1 = make_float3(p.T_ptr[3], p.T_ptr[4], p.T_ptr[5]);
+            T.r2 = make_float3(p.T_ptr[6], p.T_ptr[7], p.T_ptr[8]);
+            T.t = make_float3(p.T_ptr[9], p.T_ptr[10], p.T_ptr[11]);
+        }
+        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+            const int x = (tile % p.tiles_x) * 32 + threadIdx.x;
+            const int y = (tile / p.tiles_x) * 8 + threadIdx.y;
+            float row[7];
+            if (x < p.cols && y < p.rows && icp_row(p, T, x, y, row)) {
+                int k = 0;
+#pragma unroll
+                for (int i = 0; i < 6; ++i)
+#pragma unroll
+                    for (int j = i; j < 7; ++j) acc[k++] += row[i] * row[j];
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 27; ++i) {
+        double v = (double)acc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) smem[warp][i] = v;
+    }
+    __syncthreads();
+    if (tid < 27) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += smem[w][tid];
+        p.partials[(size_t)blockIdx.x * 27 + tid] = v;
+    }
+}
+
+// fixed-order reduction of the block partials into sums[27]
+__device__ void reduce_partials(const double *partials, int nblocks, double *sums_smem)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int s = warp; s < 27; s += nwarps) {
+        double v = 0.0;
+        for (int b = lane; b < nblocks; b += 32) v += partials[(size_t)b * 27 + s];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) sums_smem[s] = v;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) icp_reduce_kernel(const double *partials, int nblocks, double *out27)
+{
+    __shared__ double sums[27];
+    reduce_partials(partials, nblocks, sums);
+    if (threadIdx.x < 27) out27[threadIdx.x] = sums[threadIdx.x];
+}
+
+__device__ double det6_dev(const double *Ain)
+{
+    double A[36];
+    for (int i = 0; i < 36; ++i) A[i] = Ain[i];
+    double det = 1.0;
+    for (int c = 0; c < 6; ++c) {
+        int pv = c;
+        for (int r = c + 1; r < 6; ++r) if (fabs(A[r * 6 + c]) > fabs(A[pv * 6 + c])) pv = r;
+        if (A[pv * 6 + c] == 0.0) return 0.0;
+        if (pv != c) { for (int j = 0; j < 6; ++j) { const double t = A[c * 6 + j]; A[c * 6 + j] = A[pv * 6 + j]; A[pv * 6 + j] = t; } det = -det; }
+        det *= A[c * 6 + c];
+        for (int r = c + 1; r < 6; ++r) {
+            const double f = A[r * 6 + c] / A[c * 6 + c];
+            for (int j = c; j < 6; ++j) A[r * 6 + j] -= f * A[c * 6 + j];
+        }
+    }
+    return det;
+}
+
+// Cholesky solve; returns false when a pivot is not safely positive (caller falls back to the eigen solve)
+__device__ bool chol6_solve(const double *Ain, const double *b, double *x)
+{
+    double L[36];
+    double dmax = 0.0;
+    for (int i = 0; i < 6; ++i) dmax = fmax(dmax, fabs(Ain[i * 6 + i]));
+    for (int j = 0; j < 6; ++j) {
+        double d = Ain[j * 6 + j];
+        for (int k = 0; k < j; ++k) d -= L[j * 6 + k] * L[j * 6 + k];
+        if (!(d > dmax * 1e-13)) return false;
+        d = sqrt(d);
+        L[j * 6 + j] = d;
+        for (int i = j + 1; i < 6; ++i) {
+            double s = Ain[i * 6 + j];
+            for (int k = 0; k < j; ++k) s -= L[i * 6 + k] * L[j * 6 + k];
+            L[i * 6 + j] = s / d;
+        }
+    }
+    double y[6];
+    for (int i = 0; i < 6; ++i) { double s = b[i]; for (int k = 0; k < i; ++k) s -= L[i * 6 + k] * y[k]; y[i] = s / L[i * 6 + i]; }
+    for (int i = 5; i >= 0; --i) { double s = y[i]; for (int k = i + 1; k < 6; ++k) s -= L[k * 6 + i] * x[k]; x[i] = s / L[i * 6 + i]; }
+    return true;
+}
+
+// symmetric-eigen pseudo-inverse (what cv::solve(DECOMP_SVD) computes for a symmetric matrix); slow path
+__device__ void sym6_solve_dev(const double *Ain, const double *b, double *x)
+{
+    double A[36], V[36];
+    for (int i = 0; i < 36; ++i) { A[i] = Ain[i]; V[i] = 0.0; }
+    for (int i = 0; i < 6; ++i) V[i * 6 + i] = 1.0;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0;
+        for (int p = 0; p < 6; ++p) for (int q = p + 1; q < 6; ++q) off += A[p * 6 + q] * A[p * 6 + q];
+        if (off < 1e-300) break;
+        for (int p = 0; p < 6; ++p)
+            for (int q = p + 1; q < 6; ++q) {
+                const double apq = A[p * 6 + q];
+                if (apq == 0.0) continue;
+                const double theta = (A[q * 6 + q] - A[p * 6 + p]) / (2.0 * apq);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < 6; ++k) { const double akp = A[k * 6 + p], akq = A[k * 6 + q]; A[k * 6 + p] = c * akp - s * akq; A[k * 6 + q] = s * akp + c * akq; }
+                for (int k = 0; k < 6; ++k) { const double apk = A[p * 6 + k], aqk = A[q * 6 + k]; A[p * 6 + k] = c * apk - s * aqk; A[q * 6 + k] = s * apk + c * aqk; }
+                for (int k = 0; k < 6; ++k) { const double vkp = V[k * 6 + p], vkq = V[k * 6 + q]; V[k * 6 + p] = c * vkp - s * vkq; V[k * 6 + q] = s * vkp + c * vkq; }
+            }
+    }
+    double wmax = 0.0;
+    for (int i = 0; i < 6; ++i) wmax = fmax(wmax, fabs(A[i * 6 + i]));
+    const double thr = wmax * 6 * DBL_EPSILON;
+    for (int i = 0; i < 6; ++i) x[i] = 0.0;
+    for (int e = 0; e < 6; ++e) {
+        const double w = A[e * 6 + e];
+        if (fabs(w) <= thr) continue;
+        double proj = 0.0;
+        for (int i = 0; i < 6; ++i) proj += V[i * 6 + e] * b[i];
+        proj /= w;
+        for (int i = 0; i < 6; ++i) x[i] += V[i * 6 + e] * proj;
+    }
+}
+
+// StreamHelper::get (projective_icp.cpp:43-62) + host step :195-209, on the device
+__global__ void __launch_bounds__(256) icp_solve_kernel(const double *partials, int nblocks, float *T, int *ok)
+{
+    __shared__ double sums[27];
+    if (*ok == 0) return;
+    reduce_partials(partials, nblocks, sums);
+    if (threadIdx.x != 0) return;
+    double A[36], b[6];
+    int shift = 0;
+    for (int i = 0; i < 6; ++i)
+        for (int j = i; j < 7; ++j) {
+            const double value = (double)(float)sums[shift++];          // the reference's buffer is float
+            if (j == 6) b[i] = value; else A[j * 6 + i] = A[i * 6 + j] = value;
+        }
+    const double det = det6_dev(A);
+    if (fabs(det) < 1e-15 || det != det) { *ok = 0; return; }
+    double r[6];
+    if (!chol6_solve(A, b, r)) sym6_solve_dev(A, b, r);
+    float rf[6];
+    for (int i = 0; i < 6; ++i) rf[i] = (float)r[i];
+
+    // cv::Affine3f(rvec, t): Rodrigues evaluated in double on float inputs (opencv2/core/affine.hpp)
+    float Rinc[9];
+    const double theta = sqrt((double)rf[0] * rf[0] + (double)rf[1] * rf[1] + (double)rf[2] * rf[2]);
+    if (theta < DBL_EPSILON) {
+        for (int i = 0; i < 9; ++i) Rinc[i] = (i % 4 == 0) ? 1.f : 0.f;
+    } else {
+        const double c = cos(theta), s = sin(theta), c1 = 1. - c, itheta = 1. / theta;
+        const float rx = (float)(rf[0] * itheta), ry = (float)(rf[1] * itheta), rz = (float)(rf[2] * itheta);
+        const float rrt[9] = {rx * rx, rx * ry, rx * rz, rx * ry, ry * ry, ry * rz, rx * rz, ry * rz, rz * rz};
+        const float r_x[9] = {0, -rz, ry, rz, 0, -rx, -ry, rx, 0};
+        for (int i = 0; i < 9; ++i) Rinc[i] = (float)(c * ((i % 4 == 0) ? 1.0 : 0.0) + c1 * rrt[i] + s * r_x[i]);
+    }
+    float Rn[9], tn[3];
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j)
+            Rn[i * 3 + j] = Rinc[i * 3 + 0] * T[0 * 3 + j] + Rinc[i * 3 + 1] * T[1 * 3 + j] + Rinc[i * 3 + 2] * T[2 * 3 + j];
+        tn[i] = Rinc[i * 3 + 0] * T[9] + Rinc[i * 3 + 1] * T[10] + Rinc[i * 3 + 2] * T[11] + rf[3 + i];
+    }
+    for (int i = 0; i < 9; ++i) T[i] = Rn[i];
+    for (int i = 0; i < 3; ++i) T[9 + i] = tn[i];
+}
+
+__global__ void icp_init_kernel(float *T, int *ok)
+{
+    if (threadIdx.x < 12) T[threadIdx.x] = (threadIdx.x < 9 && threadIdx.x % 4 == 0) ? 1.f : 0.f;
+    if (threadIdx.x == 0) *ok = 1;
+}
+
+int launch_accumulate(IcpParams &p, cudaStream_t s)
+{
+    p.tiles_x = div_up(p.cols, 32);
+    p.tiles = p.tiles_x * div_up(p.rows, 8);
+    const int blocks = p.tiles < 148 * 4 ? p.tiles : 148 * 4;
+    icp_accumulate_kernel<<<blocks, dim3(32, 8), 0, s>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return -(int)e;
+    return blocks;
+}
+
+}  // namespace
+
+extern "C" int df_icp_accumulate(const float *vcurr, size_t vcurr_pitch, const float *ncurr, size_t ncurr_pitch,
+                                 const float *vprev, size_t vprev_pitch, const float *nprev, size_t nprev_pitch,
+                                 int cols, int rows, df_intr intr_level, df_aff3f T, float dist2_thres, float min_cosine,
+                                 double *scratch, void *stream)
+{
+    IcpParams p;
+    p.vcurr = (const float4 *)vcurr; p.vcpitch = vcurr_pitch; p.ncurr = (const float4 *)ncurr; p.ncpitch = ncurr_pitch;
+    p.vprev = (const float4 *)vprev; p.vppitch = vprev_pitch; p.nprev = (const float4 *)nprev; p.nppitch = nprev_pitch;
+    p.cols = cols; p.rows = rows; p.fcols = (float)cols; p.frows = (float)rows;
+    p.fx = intr_level.fx; p.fy = intr_level.fy; p.cx = intr_level.cx; p.cy = intr_level.cy;
+    p.dist2_thres = dist2_thres; p.min_cosine = min_cosine;
+    p.T_val = make_aff(T); p.T_ptr = nullptr; p.ok_ptr = nullptr;
+    p.partials = scratch + 32;
+    const int blocks = launch_accumulate(p, (cudaStream_t)stream);
+    if (blocks < 0) return -blocks;
+    icp_reduce_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(p.partials, blocks, scratch);
+    DF_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int df_icp_estimate(const float *const *vcurr, const float *const *ncurr, const float *const *vprev, const float *const *nprev,
+                               const int *cols, const int *rows, const size_t *pitch, int levels, const int *iters,
+                               df_intr intr, float dist_thres, float angle_thres, float *T_dev, int *ok_dev, double *scratch,
+                               void *stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    icp_init_kernel<<<1, 32, 0, s>>>(T_dev, ok_dev);        // affine = Identity, projective_icp.cpp:175
+    DF_LAUNCH_CHECK();
+    for (int level = levels - 1; level >= 0; --level) {
+        const int div = 1 << level;                          // setLevelIntr, projective_icp.cpp:17-23
+        IcpParams p;
+        p.vcurr = (const float4 *)vcurr[level]; p.ncurr = (const float4 *)ncurr[level];
+        p.vprev = (const float4 *)vprev[level]; p.nprev = (const float4 *)nprev[level];
+        p.vcpitch = p.ncpitch = p.vppitch = p.nppitch = pitch[level];
+        p.cols = cols[level]; p.rows = rows[level]; p.fcols = (float)cols[level]; p.frows = (float)rows[level];
+        p.fx = intr.fx / div; p.fy = intr.fy / div; p.cx = intr.cx / div; p.cy = intr.cy / div;
+        p.dist2_thres = dist_thres * dist_thres;             // ComputeIcpHelper ctor, projective_icp.cpp:11-15
+        p.min_cosine = cosf(angle_thres);
+        p.T_val = Aff(); p.T_ptr = T_dev; p.ok_ptr = ok_dev;
+        p.partials = scratch + 32;
+        for (int it = 0; it < iters[level]; ++it) {
+            const int blocks = launch_accumulate(p, s);
+            if (blocks < 0) return -blocks;
+            icp_solve_kernel<<<1, 256, 0, s>>>(p.partials, blocks, T_dev, ok_dev);
+            DF_LAUNCH_CHECK();
+        }
+    }
+    return 0;
+}

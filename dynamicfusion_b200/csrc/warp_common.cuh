@@ -1,0 +1,136 @@
+// warp_common.cuh -- device-side warp-field primitives shared by warp.cu and solve.cu:
+// exact 8-NN over a GPU-resident node table, node weights, dual-quaternion blend.
+// Replaces the CPU path of the reference: nanoflann kd-tree queries (kfusion/src/warp_field.cpp:247-251,
+// kfusion/include/nanoflann/nanoflann.hpp:901-915) and the scalar DQB loop (warp_field.cpp:180-241).
+#pragma once
+#include "df_common.cuh"
+
+namespace dfb {
+
+constexpr int KNN_TILE = 1024;       // nodes staged per shared-memory tile (SoA, 12 KB)
+
+struct KnnSmem { float x[KNN_TILE], y[KNN_TILE], z[KNN_TILE]; };
+
+// Exact 8 nearest nodes of q by exhaustive scan in ascending node index.  Result-set semantics of nanoflann's
+// KNNResultSet::addPoint (nanoflann.hpp:110-131): accept iff dist < current worst (strict), equal distances keep
+// visiting order (=> ties resolve to the lower node index); distance d0*d0 + d1*d1 + d2*d2 evaluated left to right in
+// float (knn_point_cloud.hpp:26-32).  ALL threads of the block must call this (tile staging uses __syncthreads);
+// `valid` = false skips the scan for this thread (NaN query).
+__device__ __forceinline__ void knn8_scan(const float *__restrict__ nodes, int M, bool valid, float qx, float qy, float qz,
+                                          KnnSmem &sm, int (&bi)[8], float (&bd)[8])
+{
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { bi[i] = -1; bd[i] = 3.402823466e+38f; }
+    const int tid = threadIdx.x + threadIdx.y * blockDim.x;
+    const int nthreads = blockDim.x * blockDim.y;
+    for (int base = 0; base < M; base += KNN_TILE) {
+        const int n = min(KNN_TILE, M - base);
+        __syncthreads();
+        for (int i = tid; i < n; i += nthreads) {
+            const float *v = nodes + (size_t)(base + i) * DF_NODE_STRIDE;
+            sm.x[i] = __ldg(v); sm.y[i] = __ldg(v + 1); sm.z[i] = __ldg(v + 2);
+        }
+        __syncthreads();
+        if (!valid) continue;
+#pragma unroll 4
+        for (int i = 0; i < n; ++i) {
+            const float d0 = qx - sm.x[i], d1 = qy - sm.y[i], d2 = qz - sm.z[i];
+            const float dist = d0 * d0 + d1 * d1 + d2 * d2;
+            if (dist < bd[7]) {
+                bd[7] = dist; bi[7] = base + i;
+#pragma unroll
+                for (int k = 7; k > 0; --k) {
+                    if (bd[k] < bd[k - 1]) {
+                        const float td = bd[k]; bd[k] = bd[k - 1]; bd[k - 1] = td;
+                        const int ti = bi[k]; bi[k] = bi[k - 1]; bi[k - 1] = ti;
+                    }
+                }
+            }
+        }
+    }
+}
+
+struct Quat { float w, x, y, z; };
+
+// Quaternion::operator*, quaternion.hpp:191-199
+__device__ __forceinline__ Quat qmul(const Quat a, const Quat b)
+{
+    Quat r;
+    r.w = ((a.w * b.w) - (a.x * b.x) - (a.y * b.y) - (a.z * b.z));
+    r.x = ((a.w * b.x) + (a.x * b.w) + (a.y * b.z) - (a.z * b.y));
+    r.y = ((a.w * b.y) - (a.x * b.z) + (a.y * b.w) + (a.z * b.x));
+    r.z = ((a.w * b.z) + (a.x * b.y) - (a.y * b.x) + (a.z * b.w));
+    return r;
+}
+// Quaternion::normalize, quaternion.hpp:220-228: the scale 1.0/norm is a double, products narrowed to float
+__device__ __forceinline__ Quat qnormalize(const Quat q)
+{
+    const float n = sqrtf((q.w * q.w) + (q.x * q.x) + (q.y * q.y) + (q.z * q.z));
+    const double s = 1.0 / (double)n;
+    Quat r;
+    r.w = (float)(s * (double)q.w); r.x = (float)(s * (double)q.x); r.y = (float)(s * (double)q.y); r.z = (float)(s * (double)q.z);
+    return r;
+}
+// DualQuaternion::getTranslation, dual_quaternion.hpp:120-125: 2 * translation_ * conj(normalised rotation_)
+__device__ __forceinline__ Quat dq_translation(const Quat rot, const Quat dual)
+{
+    const Quat r = qnormalize(rot);
+    const Quat conj = {r.w, -r.x, -r.y, -r.z};
+    const Quat two = {2 * dual.w, 2 * dual.x, 2 * dual.y, 2 * dual.z};
+    return qmul(two, conj);
+}
+// 0.5 * q with a double scalar (DualQuaternion ctor / encodeTranslation, dual_quaternion.hpp:59-63,82-85)
+__device__ __forceinline__ Quat qhalf(const Quat q)
+{
+    Quat r;
+    r.w = (float)(0.5 * (double)q.w); r.x = (float)(0.5 * (double)q.x); r.y = (float)(0.5 * (double)q.y); r.z = (float)(0.5 * (double)q.z);
+    return r;
+}
+// Quaternion::rotate(Vec3f&), quaternion.hpp:124-130
+__device__ __forceinline__ float3 qrotate(const Quat q, const float3 v)
+{
+    const Quat r = qnormalize(q);
+    const float3 qv = make_float3(r.x, r.y, r.z);
+    const float3 inner = add3(cross3(qv, v), scale3(v, r.w));
+    const float3 c = cross3(scale3(qv, 2.f), inner);
+    return make_float3(v.x + c.x, v.y + c.y, v.z + c.z);
+}
+// WarpField::weighting, warp_field.cpp:238-241: double exp of a float argument, narrowed to float
+__device__ __forceinline__ float node_weighting(float d2, float node_w) { return (float)exp((double)(-d2 / (2 * node_w * node_w))); }
+
+struct Dqb { Quat rot, dual; };
+
+// WarpField::DQB (warp_field.cpp:203-217) from the 8 neighbours; weights8 (optional) receives the node weights
+__device__ __forceinline__ Dqb dqb_blend(const float *__restrict__ nodes, const int (&bi)[8], const float (&bd)[8], float *weights8)
+{
+    Quat tsum = {0.f, 0.f, 0.f, 0.f}, rsum = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float w = 0.f;
+        if (bi[i] >= 0) {
+            const float4 *n4 = reinterpret_cast<const float4 *>(nodes + (size_t)bi[i] * DF_NODE_STRIDE);
+            const float4 a = __ldg(n4), b = __ldg(n4 + 1), c = __ldg(n4 + 2);   // (vx,vy,vz,rw) (rx,ry,rz,dw) (dx,dy,dz,weight)
+            const Quat rot = {a.w, b.x, b.y, b.z};
+            const Quat dual = {b.w, c.x, c.y, c.z};
+            w = node_weighting(bd[i], c.w);
+            const Quat t = dq_translation(rot, dual);
+            tsum.w = tsum.w + w * t.w; tsum.x = tsum.x + w * t.x; tsum.y = tsum.y + w * t.y; tsum.z = tsum.z + w * t.z;
+            rsum.w = rsum.w + w * rot.w; rsum.x = rsum.x + w * rot.x; rsum.y = rsum.y + w * rot.y; rsum.z = rsum.z + w * rot.z;
+        }
+        if (weights8) weights8[i] = w;
+    }
+    Dqb r;
+    r.rot = qnormalize(rsum);
+    r.dual = qmul(qhalf(tsum), r.rot);     // DualQuaternion(translation, rotation) ctor
+    return r;
+}
+
+// DualQuaternion::transform, dual_quaternion.hpp:204-210
+__device__ __forceinline__ float3 dq_transform(const Dqb &d, const float3 v)
+{
+    const Quat t = dq_translation(d.rot, d.dual);
+    const float3 r = qrotate(d.rot, v);
+    return make_float3(r.x + t.x, r.y + t.y, r.z + t.z);
+}
+
+}  // namespace dfb

@@ -229,7 +229,7 @@ class ProjectiveICP:
         self.iters_ = [10, 5, 4, 0]
         self._T = torch.zeros(12, dtype=torch.float32, device=device)
         self._ok = torch.zeros(1, dtype=torch.int32, device=device)
-        self._scratch = torch.zeros(32, dtype=torch.float64, device=device)
+        self._scratch = torch.zeros(32 + 27 * 1024, dtype=torch.float64, device=device)
 
     def setDistThreshold(self, d):
         self.dist_thres_ = float(d)
@@ -249,11 +249,11 @@ class ProjectiveICP:
 
     def accumulate(self, vcurr, ncurr, vprev, nprev, intr_level, T):
         rows, cols = vcurr.shape[:2]
-        out = torch.zeros(27, dtype=torch.float64, device=self.device)
+        out = self._scratch
         capi.check(_lib().df_icp_accumulate(vcurr.data_ptr(), cols * 16, ncurr.data_ptr(), cols * 16, vprev.data_ptr(), cols * 16,
                                             nprev.data_ptr(), cols * 16, cols, rows, capi.make_intr(*intr_level), capi.make_aff(*T),
                                             self.dist_thres_ * self.dist_thres_, math.cos(self.angle_thres_), out.data_ptr(), _stream()))
-        return out
+        return out[:27].clone()
 
     def estimateTransform(self, intr, vcurr, ncurr, vprev, nprev):
         """returns (ok, (R, t)) -- syncs to read the result (the fused pipeline never does)"""

@@ -103,12 +103,15 @@ int df_resize_points_normals(const float *vsrc, size_t vsrc_pitch, const float *
 
 /* ------------------------------------------------------------------ projective ICP -------------------------------------------------------- */
 /* ComputeIcpHelper::operator() points variant (internal.hpp:67-102, proj_icp.cu:80-108,350-394,448-467): one
- * data-association + 27-term reduction pass at one pyramid level.  out27 (device, 27 doubles, order (i, j>=i) for
- * i = 0..5, j = 0..6) is OVERWRITTEN.  intr_level are the level's intrinsics (setLevelIntr, projective_icp.cpp:17-23). */
+ * data-association + 27-term reduction pass at one pyramid level.  scratch: device buffer of DF_ICP_SCRATCH_DOUBLES
+ * doubles; on completion scratch[0..26] hold the 27 sums, order (i, j>=i) for i = 0..5, j = 0..6 (the rest holds the
+ * per-block partials, summed in a fixed order: results are run-to-run deterministic).  intr_level are the level's
+ * intrinsics (setLevelIntr, projective_icp.cpp:17-23). */
+#define DF_ICP_SCRATCH_DOUBLES (32 + 27 * 1024)
 int df_icp_accumulate(const float *vcurr, size_t vcurr_pitch, const float *ncurr, size_t ncurr_pitch,
                       const float *vprev, size_t vprev_pitch, const float *nprev, size_t nprev_pitch,
                       int cols, int rows, df_intr intr_level, df_aff3f T, float dist2_thres, float min_cosine,
-                      double *out27, void *stream);
+                      double *scratch, void *stream);
 
 /* ProjectiveICP::estimateTransform, points variant (projective_icp.hpp:39, projective_icp.cpp:169-213) executed
  * entirely on the device: per iteration the association/reduction kernel, then the 6x6 solve + Rodrigues update in a
@@ -117,7 +120,7 @@ int df_icp_accumulate(const float *vcurr, size_t vcurr_pitch, const float *ncurr
  * reference would have returned false (|det| < 1e-15 or NaN). */
 int df_icp_estimate(const float *const *vcurr, const float *const *ncurr, const float *const *vprev, const float *const *nprev,
                     const int *cols, const int *rows, const size_t *pitch, int levels, const int *iters,
-                    df_intr intr, float dist_thres, float angle_thres, float *T_dev, int *ok_dev, double *scratch27,
+                    df_intr intr, float dist_thres, float angle_thres, float *T_dev, int *ok_dev, double *scratch,
                     void *stream);
 
 /* ------------------------------------------------------------------ warp field ------------------------------------------------------------ */

@@ -171,7 +171,7 @@ int orc_icp_estimate(const float *const *vcurr, const float *const *ncurr, const
     orc_aff3f T;
     for (int i = 0; i < 9; ++i) T.R[i] = (i % 4 == 0) ? 1.f : 0.f;
     T.t[0] = T.t[1] = T.t[2] = 0.f;
-    const float min_cosine = (float)cos((double)angle_thres);
+    const float min_cosine = cosf(angle_thres);
     const float dist2 = dist_thres * dist_thres;
     for (int level = levels - 1; level >= 0; --level) {
         int div = 1 << level;
