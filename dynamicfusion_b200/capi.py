@@ -74,7 +74,8 @@ PROTOTYPES = {
     "df_kinfu_destroy": (None, [_vp]),
     "df_kinfu_reset": (_i, [_vp]),
     "df_kinfu_process_host": (_i, [_vp, _vp, _sz]),
-    "df_kinfu_process_device": (_i, [_vp, _vp, _sz, _vp]),
+    "df_kinfu_process_device": (_i, [_vp, _vp, _sz]),
+    "df_kinfu_get_stage_ms": (_i, [_vp, C.POINTER(C.c_float), _i]),
     "df_kinfu_get_pose": (_i, [_vp, _i, C.POINTER(C.c_float)]),
     "df_kinfu_get_info": (_i, [_vp, C.POINTER(C.c_longlong), _i]),
     "df_kinfu_get_buffer": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_sz), C.POINTER(_i), C.POINTER(_i)]),

@@ -1,0 +1,483 @@
+// pipeline.cu -- the per-frame DynamicFusion loop, device-resident, behind the C ABI (df_kinfu_*).
+// Mirrors kfusion::KinFu (kfusion/include/kfusion/kinfu.hpp:49-97, kfusion/src/kinfu.cpp): same stage order, buffer swaps,
+// first-frame special case and pose chaining.  What changes is where the data lives: the reference's
+// KinFu::dynamicfusion (kinfu.cpp:344-400) downloads three 4.9 MB maps, runs ~1 M CPU k-NN queries, re-uploads, and
+// syncs ~25 times a frame; here the frame touches the host exactly once (ICP status + 12-float pose, needed for the
+// return value) and everything else is stream-ordered kernels on one stream.
+#include "df_common.cuh"
+#include "../../include/df_hostmath.h"
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+using namespace dfb;
+
+namespace {
+
+constexpr int MAX_LEVELS = 4;      // ProjectiveICP::MAX_PYRAMID_LEVELS, projective_icp.hpp:12
+constexpr int NSTAGES = 10;
+
+struct Img { void *ptr = nullptr; size_t pitch = 0; int cols = 0, rows = 0; };
+
+struct KinFu {
+    df_kinfu_params p;
+    cudaStream_t stream = 0;
+    int levels = 0;                       // icp used levels
+    float trunc_dist = 0.f;
+    float voxel_size[3];
+    uint32_t *volume = nullptr;
+    Img depth_in, dists;
+    Img cur_depth[MAX_LEVELS], cur_pts[MAX_LEVELS], cur_nrm[MAX_LEVELS], prev_pts[MAX_LEVELS], prev_nrm[MAX_LEVELS];
+    Img canon, canon_nrm, canon_visible;
+    float *cloud = nullptr, *cloud_nrm = nullptr; int *cloud_count = nullptr;
+    float *nodes = nullptr; int M = 0;
+    float *icp_T = nullptr; int *icp_ok = nullptr; double *icp_scratch = nullptr;
+    void *solve_ws = nullptr; size_t solve_ws_bytes = 0; double *solve_stats = nullptr;
+    void *extract_ws = nullptr; void *project_ws = nullptr;
+    float *pinned = nullptr;             // 16 floats: T(12) + ok
+    std::vector<float> poses;            // 12 floats per pose
+    int frame_counter = 0, resets = 0, last_ok = 1, launches = 0;
+    long long last_cloud = -1;
+    unsigned long long *n_upd = nullptr;   // voxels written by the last integrate (filled when DF_KINFU_STAGE_TIMING)
+    cudaEvent_t ev[NSTAGES + 1];
+    float stage_ms[NSTAGES];
+    int stage_mark[NSTAGES + 1];
+};
+
+#define CK(call)                                      \
+    do {                                              \
+        cudaError_t e__ = (call);                     \
+        if (e__ != cudaSuccess) return -(int)e__;     \
+    } while (0)
+#define CKD(call)                                     \
+    do {                                              \
+        int s__ = (call);                             \
+        if (s__ != 0) return -s__;                    \
+    } while (0)
+
+int alloc_img(Img &im, int rows, int cols, size_t elem)
+{
+    im.cols = cols; im.rows = rows; im.pitch = (size_t)cols * elem;     // dense rows (pitch is still carried everywhere)
+    return (int)cudaMalloc(&im.ptr, im.pitch * rows);
+}
+
+df_volume vol_of(const KinFu &k)
+{
+    df_volume v;
+    v.data = k.volume;
+    for (int i = 0; i < 3; ++i) { v.dims[i] = k.p.volume_dims[i]; v.voxel_size[i] = k.voxel_size[i]; }
+    v.trunc_dist = k.trunc_dist; v.max_weight = k.p.tsdf_max_weight;
+    return v;
+}
+
+df_aff3f to_aff(const float *a12) { df_aff3f a; memcpy(a.R, a12, 36); memcpy(a.t, a12 + 9, 12); return a; }
+
+// canonical[i] = inverse_pose * cloud[i]: cv::Affine3f * Vec3f, m0*x + m1*y + m2*z + m3 left to right (kinfu.cpp:356-362);
+// NaN pixels stay NaN.  Also writes the `canonical_visible` copy (kinfu.cpp:383).
+__global__ void __launch_bounds__(256) to_canonical_kernel(const float4 *src, Aff inv_pose, float4 *dst, float4 *dst_copy, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 v = src[i];
+    float4 o;
+    o.x = inv_pose.r0.x * v.x + inv_pose.r0.y * v.y + inv_pose.r0.z * v.z + inv_pose.t.x;
+    o.y = inv_pose.r1.x * v.x + inv_pose.r1.y * v.y + inv_pose.r1.z * v.z + inv_pose.t.y;
+    o.z = inv_pose.r2.x * v.x + inv_pose.r2.y * v.y + inv_pose.r2.z * v.z + inv_pose.t.z;
+    o.w = v.w;
+    dst[i] = o;
+    dst_copy[i] = o;
+}
+
+// WarpField::init (warp_field.cpp:41-62): every `step`-th extracted point becomes a node with the identity
+// DualQuaternion() (rotation (1,0,0,0), dual part (1,0,0,0)) and weight 3 * voxel_size with voxel_size forced to 1.
+__global__ void __launch_bounds__(256) init_nodes_kernel(const float4 *cloud, int step, int M, float *nodes)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const float4 p = cloud[(size_t)m * step];
+    float *n = nodes + (size_t)m * DF_NODE_STRIDE;
+    n[0] = p.x; n[1] = p.y; n[2] = p.z;
+    n[3] = 1.f; n[4] = 0.f; n[5] = 0.f; n[6] = 0.f;
+    n[7] = 1.f; n[8] = 0.f; n[9] = 0.f; n[10] = 0.f;
+    n[11] = 3.f;
+}
+
+void mark(KinFu &k, int stage)
+{
+    if (k.p.flags & DF_KINFU_STAGE_TIMING) cudaEventRecord(k.ev[stage], k.stream);
+    k.stage_mark[stage] = 1;
+}
+
+int do_reset(KinFu &k)
+{
+    if (k.frame_counter) { printf("Reset\n"); ++k.resets; }          // kinfu.cpp:198-199
+    k.frame_counter = 0;
+    k.poses.clear();
+    k.poses.resize(12);
+    dfh_aff_identity(k.poses.data());
+    return df_clear_volume(vol_of(k), k.stream);
+}
+
+int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch)
+{
+    const df_kinfu_params &p = k.p;
+    cudaStream_t s = k.stream;
+    const int LEVELS = k.levels;
+    k.launches = 0;
+    memset(k.stage_mark, 0, sizeof k.stage_mark);
+    mark(k, 0);
+
+    // ---- pre-processing, kinfu.cpp:226-242 -----------------------------------------------------------------------
+    CKD(df_compute_dists(depth_dev, depth_pitch, p.cols, p.rows, p.intr, (uint16_t *)k.dists.ptr, k.dists.pitch, s));
+    CKD(df_bilateral(depth_dev, depth_pitch, p.cols, p.rows, (uint16_t *)k.cur_depth[0].ptr, k.cur_depth[0].pitch,
+                     p.bilateral_kernel_size, p.bilateral_sigma_spatial, p.bilateral_sigma_depth, s));
+    k.launches += 2;
+    if (p.icp_truncate_depth_dist > 0) {
+        CKD(df_truncate_depth((uint16_t *)k.cur_depth[0].ptr, k.cur_depth[0].pitch, p.cols, p.rows, p.icp_truncate_depth_dist, s));
+        ++k.launches;
+    }
+    for (int i = 1; i < LEVELS; ++i) {
+        CKD(df_pyr_down((const uint16_t *)k.cur_depth[i - 1].ptr, k.cur_depth[i - 1].pitch, k.cur_depth[i - 1].cols, k.cur_depth[i - 1].rows,
+                        (uint16_t *)k.cur_depth[i].ptr, k.cur_depth[i].pitch, p.bilateral_sigma_depth, s));
+        ++k.launches;
+    }
+    for (int i = 0; i < LEVELS; ++i) {
+        const int div = 1 << i;                                       // Intr::operator()(level), precomp.cpp:10-14
+        const df_intr li = {p.intr.fx / div, p.intr.fy / div, p.intr.cx / div, p.intr.cy / div};
+        CKD(df_points_normals(li, (const uint16_t *)k.cur_depth[i].ptr, k.cur_depth[i].pitch, k.cur_depth[i].cols, k.cur_depth[i].rows,
+                              (float *)k.cur_pts[i].ptr, k.cur_pts[i].pitch, (float *)k.cur_nrm[i].ptr, k.cur_nrm[i].pitch, s));
+        ++k.launches;
+    }
+    mark(k, 1);
+
+    const df_volume vol = vol_of(k);
+    float vol_pose[12];
+    memcpy(vol_pose, p.volume_pose.R, 36); memcpy(vol_pose + 9, p.volume_pose.t, 12);
+    float Rinv_vol[9];
+    dfh_mat3_inv(vol_pose, Rinv_vol);
+
+    auto integrate_with = [&](const Img &dists, const float *cam_pose) -> int {
+        float inv[12], vol2cam[12];
+        dfh_aff_inv(cam_pose, inv);
+        dfh_aff_mul(inv, vol_pose, vol2cam);                           // camera_pose.inv() * pose_, tsdf_volume.cpp:112
+        ++k.launches;
+        unsigned long long *counter = (p.flags & DF_KINFU_STAGE_TIMING) ? k.n_upd : nullptr;
+        if (counter) cudaMemsetAsync(counter, 0, 8, s);
+        return df_integrate(vol, (const uint16_t *)dists.ptr, dists.pitch, p.cols, p.rows, to_aff(vol2cam), p.intr, counter, s);
+    };
+    auto raycast_to = [&](const float *cam_pose, Img &pts, Img &nrm) -> int {
+        float inv[12], cam2vol[12], Rinv[9];
+        dfh_aff_inv(vol_pose, inv);
+        dfh_aff_mul(inv, cam_pose, cam2vol);                           // pose_.inv() * camera_pose, tsdf_volume.cpp:162
+        dfh_mat3_inv(cam2vol, Rinv);
+        ++k.launches;
+        return df_raycast_points(vol, to_aff(cam2vol), Rinv, p.intr, p.cols, p.rows, p.raycast_step_factor, p.gradient_delta_factor,
+                                 (float *)pts.ptr, pts.pitch, (float *)nrm.ptr, nrm.pitch, s);
+    };
+    auto extract = [&]() -> int {                                      // compute_points + compute_normals, tsdf_volume.cpp:313-325
+        int st = df_extract_cloud(vol, p.volume_pose, k.cloud, p.cloud_capacity, k.cloud_count, k.extract_ws, s);
+        if (st) return st;
+        k.launches += 4;
+        k.last_cloud = -1;
+        return df_extract_normals(vol, k.cloud, p.cloud_capacity, k.cloud_count, p.volume_pose, Rinv_vol, p.gradient_delta_factor, k.cloud_nrm, s);
+    };
+
+    // ---- first frame, kinfu.cpp:245-264 ----------------------------------------------------------------------------
+    if (k.frame_counter == 0) {
+        CKD(integrate_with(k.dists, &k.poses[k.poses.size() - 12]));
+        CKD(extract());
+        if (!(p.flags & DF_KINFU_RIGID_ONLY)) {
+            int count = 0;
+            CK(cudaMemcpyAsync(&count, k.cloud_count, sizeof(int), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            k.last_cloud = count;
+            int step = p.node_step > 0 ? p.node_step : 50;
+            int M = (count + step - 1) / step;
+            if (p.max_nodes > 0 && M > p.max_nodes) { step = (count + p.max_nodes - 1) / p.max_nodes; M = (count + step - 1) / step; }
+            k.M = M;
+            if (M > 0) { init_nodes_kernel<<<div_up(M, 256), 256, 0, s>>>((const float4 *)k.cloud, step, M, k.nodes); ++k.launches; }
+        }
+        for (int i = 0; i < MAX_LEVELS; ++i) { std::swap(k.cur_pts[i], k.prev_pts[i]); std::swap(k.cur_nrm[i], k.prev_nrm[i]); }
+        ++k.frame_counter;
+        return 0;
+    }
+
+    // ---- ICP, kinfu.cpp:268-278 (device-resident; one host read of {ok, T}) -----------------------------------------
+    {
+        const float *vc[MAX_LEVELS], *nc[MAX_LEVELS], *vp[MAX_LEVELS], *np[MAX_LEVELS];
+        int cols[MAX_LEVELS], rows[MAX_LEVELS]; size_t pitch[MAX_LEVELS];
+        for (int i = 0; i < LEVELS; ++i) {
+            vc[i] = (const float *)k.cur_pts[i].ptr; nc[i] = (const float *)k.cur_nrm[i].ptr;
+            vp[i] = (const float *)k.prev_pts[i].ptr; np[i] = (const float *)k.prev_nrm[i].ptr;
+            cols[i] = k.cur_pts[i].cols; rows[i] = k.cur_pts[i].rows; pitch[i] = k.cur_pts[i].pitch;
+        }
+        CKD(df_icp_estimate(vc, nc, vp, np, cols, rows, pitch, LEVELS, p.icp_iter_num, p.intr, p.icp_dist_thres, p.icp_angle_thres,
+                            k.icp_T, k.icp_ok, k.icp_scratch, s));
+        for (int i = 0; i < LEVELS; ++i) k.launches += 2 * p.icp_iter_num[i];
+        ++k.launches;
+        CK(cudaMemcpyAsync(k.pinned, k.icp_T, 12 * sizeof(float), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(k.pinned + 12, k.icp_ok, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        int ok;
+        memcpy(&ok, k.pinned + 12, sizeof(int));
+        k.last_ok = ok;
+        if (!ok) { CKD(do_reset(k)); return 0; }                      // kinfu.cpp:276-277
+    }
+    mark(k, 2);
+    {
+        float pose[12];
+        dfh_aff_mul(&k.poses[k.poses.size() - 12], k.pinned, pose);   // poses_.back() * affine, kinfu.cpp:280
+        k.poses.insert(k.poses.end(), pose, pose + 12);
+    }
+    const float *cam_pose = &k.poses[k.poses.size() - 12];
+    const int npix = p.cols * p.rows;
+
+    if (!(p.flags & DF_KINFU_RIGID_ONLY) && k.M >= 8) {
+        // ---- KinFu::dynamicfusion, kinfu.cpp:344-400 ------------------------------------------------------------------
+        CKD(raycast_to(cam_pose, k.canon_visible, k.canon_nrm));       // tsdf().raycast(camera_pose, ...), :351 (camera frame)
+        float inv_pose[12];
+        dfh_aff_inv(cam_pose, inv_pose);
+        to_canonical_kernel<<<div_up(npix, 256), 256, 0, s>>>((const float4 *)k.canon_visible.ptr, make_aff(to_aff(inv_pose)),
+                                                               (float4 *)k.canon.ptr, (float4 *)k.canon_visible.ptr, npix);
+        ++k.launches;
+        mark(k, 3);
+        df_aff3f ident; float id12[12]; dfh_aff_identity(id12); ident = to_aff(id12);    // warp_to_live_ stays identity (never set)
+        CKD(df_warp(k.nodes, k.M, (float *)k.canon.ptr, (float *)k.canon_nrm.ptr, npix, 4, ident, 0, nullptr, nullptr, s));   // :385
+        ++k.launches;
+        mark(k, 4);
+        CKD(df_solve_data_term(k.nodes, k.M, (const float *)k.canon.ptr, (const float *)k.cur_pts[0].ptr, npix, 4,
+                               p.solver_nonlinear_iters, p.solver_linear_iters,
+                               (p.flags & DF_KINFU_REF_GRAPH_QUIRK) ? DF_SOLVE_REF_GRAPH_QUIRK : 0, k.solve_stats, k.solve_ws, s));   // :387
+        k.launches += 6;
+        mark(k, 5);
+        CKD(df_warp(k.nodes, k.M, (float *)k.canon.ptr, (float *)k.canon_nrm.ptr, npix, 4, ident, 0, nullptr, nullptr, s));   // :389
+        ++k.launches;
+        mark(k, 6);
+        // surface_fusion (tsdf_volume.cpp:228-255): psdf projects the warped vertices into the (bilateral-filtered) depth,
+        // zeroes the pixels they explain, then the ordinary rigid integrate runs on what is left.
+        CKD(df_project_and_remove((uint16_t *)k.cur_depth[0].ptr, k.cur_depth[0].pitch, p.cols, p.rows, p.intr,
+                                  (float *)k.canon.ptr, k.canon.pitch, p.cols, p.rows, k.project_ws, s));
+        k.launches += 2;
+        CKD(df_compute_dists((const uint16_t *)k.cur_depth[0].ptr, k.cur_depth[0].pitch, p.cols, p.rows, p.intr,
+                             (uint16_t *)k.dists.ptr, k.dists.pitch, s));
+        ++k.launches;
+        mark(k, 7);                                                    // stage "integrate" brackets the integrate kernel alone
+        CKD(integrate_with(k.dists, cam_pose));
+        mark(k, 8);
+        CKD(extract());                                                // compute_points / compute_normals, :398-399
+        mark(k, 9);
+    } else {
+        // plain KinFu (Nerei) loop: integrate the frame rigidly
+        mark(k, 3); mark(k, 4); mark(k, 5); mark(k, 6); mark(k, 7);
+        CKD(integrate_with(k.dists, cam_pose));
+        mark(k, 8); mark(k, 9);
+    }
+
+    // ---- ray-cast for the next frame's ICP, kinfu.cpp:297-301 --------------------------------------------------------
+    CKD(raycast_to(cam_pose, k.prev_pts[0], k.prev_nrm[0]));
+    for (int i = 1; i < LEVELS; ++i) {
+        CKD(df_resize_points_normals((const float *)k.prev_pts[i - 1].ptr, k.prev_pts[i - 1].pitch, (const float *)k.prev_nrm[i - 1].ptr,
+                                     k.prev_nrm[i - 1].pitch, k.prev_pts[i - 1].cols, k.prev_pts[i - 1].rows,
+                                     (float *)k.prev_pts[i].ptr, k.prev_pts[i].pitch, (float *)k.prev_nrm[i].ptr, k.prev_nrm[i].pitch, s));
+        ++k.launches;
+    }
+    mark(k, 10);
+    ++k.frame_counter;
+    return 1;
+}
+
+}  // namespace
+
+extern "C" void df_kinfu_default_params(df_kinfu_params *p, int which)
+{
+    memset(p, 0, sizeof *p);
+    p->cols = 640; p->rows = 480;
+    const int iters[4] = {10, 5, 4, 0};
+    memcpy(p->icp_iter_num, iters, sizeof iters);
+    float pose[12];
+    dfh_aff_identity(pose);
+    if (which == 0) {          // default_params_dynamicfusion, kinfu.cpp:14-49
+        p->intr = df_intr{570.342f, 570.342f, 320.f, 240.f};
+        for (int i = 0; i < 3; ++i) { p->volume_dims[i] = 256; p->volume_size[i] = 1.f; }
+    } else {                   // default_params, kinfu.cpp:55-89
+        p->intr = df_intr{525.f, 525.f, 640 / 2 - 0.5f, 480 / 2 - 0.5f};
+        for (int i = 0; i < 3; ++i) { p->volume_dims[i] = 512; p->volume_size[i] = 3.f; }
+    }
+    pose[9] = -p->volume_size[0] / 2; pose[10] = -p->volume_size[1] / 2; pose[11] = 0.5f;
+    memcpy(p->volume_pose.R, pose, 36); memcpy(p->volume_pose.t, pose + 9, 12);
+    p->bilateral_sigma_depth = 0.04f; p->bilateral_sigma_spatial = 4.5f; p->bilateral_kernel_size = 7;
+    p->icp_truncate_depth_dist = 0.f; p->icp_dist_thres = 0.1f; p->icp_angle_thres = 30.f * 0.017453293f;
+    p->tsdf_min_camera_movement = 0.f; p->tsdf_trunc_dist = 0.04f; p->tsdf_max_weight = 64;
+    p->raycast_step_factor = 0.75f; p->gradient_delta_factor = 0.5f;
+    p->solver_nonlinear_iters = 5; p->solver_linear_iters = 100;     // kinfu.cpp:116-117
+    p->max_nodes = 4096; p->node_step = 50; p->cloud_capacity = 256 * 256 * 256 / 4;
+    p->flags = 0;
+}
+
+extern "C" void *df_kinfu_create(const df_kinfu_params *pp)
+{
+    if (pp->volume_dims[0] % 32 != 0) {                               // CV_Assert, kinfu.cpp:97
+        fprintf(stderr, "df_kinfu_create: volume_dims[0] %% 32 != 0\n");
+        return nullptr;
+    }
+    KinFu *k = new KinFu();
+    k->p = *pp;
+    const df_kinfu_params &p = k->p;
+    int i = MAX_LEVELS - 1;                                           // getUsedLevelsNum, projective_icp.cpp:110-115
+    for (; i >= 0 && !p.icp_iter_num[i]; --i) {}
+    k->levels = i + 1;
+    float vmax = 0.f;
+    for (int d = 0; d < 3; ++d) { k->voxel_size[d] = p.volume_size[d] / p.volume_dims[d]; vmax = vmax > k->voxel_size[d] ? vmax : k->voxel_size[d]; }
+    k->trunc_dist = p.tsdf_trunc_dist > 2.1f * vmax ? p.tsdf_trunc_dist : 2.1f * vmax;   // setTruncDist, tsdf_volume.cpp:68-73
+    const size_t nvox = (size_t)p.volume_dims[0] * p.volume_dims[1] * p.volume_dims[2];
+    bool ok = cudaMalloc(&k->volume, nvox * 4) == cudaSuccess;
+    ok = ok && alloc_img(k->depth_in, p.rows, p.cols, 2) == 0 && alloc_img(k->dists, p.rows, p.cols, 2) == 0;
+    int cols = p.cols, rows = p.rows;
+    for (int l = 0; l < MAX_LEVELS && ok; ++l) {                      // allocate_buffers, kinfu.cpp:151-194
+        ok = ok && alloc_img(k->cur_depth[l], rows, cols, 2) == 0 && alloc_img(k->cur_pts[l], rows, cols, 16) == 0 &&
+             alloc_img(k->cur_nrm[l], rows, cols, 16) == 0 && alloc_img(k->prev_pts[l], rows, cols, 16) == 0 &&
+             alloc_img(k->prev_nrm[l], rows, cols, 16) == 0;
+        cols /= 2; rows /= 2;
+    }
+    ok = ok && alloc_img(k->canon, p.rows, p.cols, 16) == 0 && alloc_img(k->canon_nrm, p.rows, p.cols, 16) == 0 &&
+         alloc_img(k->canon_visible, p.rows, p.cols, 16) == 0;
+    ok = ok && cudaMalloc(&k->cloud, (size_t)p.cloud_capacity * 16) == cudaSuccess && cudaMalloc(&k->cloud_nrm, (size_t)p.cloud_capacity * 16) == cudaSuccess;
+    ok = ok && cudaMalloc(&k->cloud_count, 64) == cudaSuccess;
+    const int maxM = p.max_nodes > 0 ? p.max_nodes : (p.cloud_capacity + 49) / 50;
+    ok = ok && cudaMalloc(&k->nodes, (size_t)maxM * DF_NODE_STRIDE * 4) == cudaSuccess;
+    ok = ok && cudaMalloc(&k->icp_T, 64) == cudaSuccess && cudaMalloc(&k->icp_ok, 64) == cudaSuccess &&
+         cudaMalloc(&k->icp_scratch, (size_t)DF_ICP_SCRATCH_DOUBLES * 8) == cudaSuccess;
+    k->solve_ws_bytes = df_solve_workspace_bytes(maxM, p.cols * p.rows);
+    ok = ok && cudaMalloc(&k->solve_ws, k->solve_ws_bytes) == cudaSuccess && cudaMalloc(&k->solve_stats, 64) == cudaSuccess;
+    df_volume v = vol_of(*k);
+    ok = ok && cudaMalloc(&k->extract_ws, df_extract_workspace_bytes(v)) == cudaSuccess;
+    ok = ok && cudaMalloc(&k->project_ws, df_project_workspace_bytes(p.cols, p.rows)) == cudaSuccess;
+    ok = ok && cudaMemset(k->project_ws, 0, df_project_workspace_bytes(p.cols, p.rows)) == cudaSuccess;
+    ok = ok && cudaMemset(k->solve_stats, 0, 64) == cudaSuccess && cudaMemset(k->cloud_count, 0, 64) == cudaSuccess;
+    ok = ok && cudaMallocHost(&k->pinned, 64) == cudaSuccess && cudaMalloc(&k->n_upd, 64) == cudaSuccess && cudaMemset(k->n_upd, 0, 64) == cudaSuccess;
+    for (int e = 0; e <= NSTAGES && ok; ++e) ok = cudaEventCreate(&k->ev[e]) == cudaSuccess;
+    if (!ok) { fprintf(stderr, "df_kinfu_create: CUDA allocation failed: %s\n", cudaGetErrorString(cudaGetLastError())); delete k; return nullptr; }
+    memset(k->stage_ms, 0, sizeof k->stage_ms);
+    do_reset(*k);
+    cudaStreamSynchronize(k->stream);
+    return k;
+}
+
+extern "C" void df_kinfu_destroy(void *h)
+{
+    KinFu *k = (KinFu *)h;
+    if (!k) return;
+    cudaStreamSynchronize(k->stream);
+    cudaFree(k->volume); cudaFree(k->depth_in.ptr); cudaFree(k->dists.ptr);
+    for (int l = 0; l < MAX_LEVELS; ++l) { cudaFree(k->cur_depth[l].ptr); cudaFree(k->cur_pts[l].ptr); cudaFree(k->cur_nrm[l].ptr); cudaFree(k->prev_pts[l].ptr); cudaFree(k->prev_nrm[l].ptr); }
+    cudaFree(k->canon.ptr); cudaFree(k->canon_nrm.ptr); cudaFree(k->canon_visible.ptr);
+    cudaFree(k->cloud); cudaFree(k->cloud_nrm); cudaFree(k->cloud_count); cudaFree(k->nodes);
+    cudaFree(k->icp_T); cudaFree(k->icp_ok); cudaFree(k->icp_scratch); cudaFree(k->solve_ws); cudaFree(k->solve_stats);
+    cudaFree(k->extract_ws); cudaFree(k->project_ws); cudaFreeHost(k->pinned); cudaFree(k->n_upd);
+    for (int e = 0; e <= NSTAGES; ++e) cudaEventDestroy(k->ev[e]);
+    delete k;
+}
+
+extern "C" int df_kinfu_set_stream(void *h, void *stream) { ((KinFu *)h)->stream = (cudaStream_t)stream; return 0; }
+extern "C" int df_kinfu_reset(void *h) { KinFu *k = (KinFu *)h; int s = do_reset(*k); return s ? -s : 0; }
+
+static void finish_timing(KinFu &k)
+{
+    if (!(k.p.flags & DF_KINFU_STAGE_TIMING)) return;
+    cudaStreamSynchronize(k.stream);
+    int prev = 0;
+    for (int s = 1; s <= NSTAGES; ++s) {
+        k.stage_ms[s - 1] = 0.f;
+        if (!k.stage_mark[s]) continue;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, k.ev[prev], k.ev[s]) == cudaSuccess) k.stage_ms[s - 1] = ms;
+        prev = s;
+    }
+}
+
+extern "C" int df_kinfu_process_device(void *h, const uint16_t *depth_dev, size_t pitch)
+{
+    KinFu *k = (KinFu *)h;
+    const int r = process(*k, depth_dev, pitch);
+    finish_timing(*k);
+    return r;
+}
+
+extern "C" int df_kinfu_process_host(void *h, const uint16_t *depth_host, size_t pitch)
+{
+    KinFu *k = (KinFu *)h;
+    // depth_device_.upload(depth.data, depth.step, rows, cols), apps/demo.cpp:89
+    cudaError_t e = cudaMemcpy2DAsync(k->depth_in.ptr, k->depth_in.pitch, depth_host, pitch, (size_t)k->p.cols * 2, k->p.rows,
+                                      cudaMemcpyHostToDevice, k->stream);
+    if (e != cudaSuccess) return -(int)e;
+    const int r = process(*k, (const uint16_t *)k->depth_in.ptr, k->depth_in.pitch);
+    if (r < 0) return r;
+    e = cudaStreamSynchronize(k->stream);        // the caller owns the result when the call returns (renderImage / getCameraPose next)
+    finish_timing(*k);
+    return e == cudaSuccess ? r : -(int)e;
+}
+
+extern "C" int df_kinfu_get_pose(void *h, int time, float *pose12)
+{
+    KinFu *k = (KinFu *)h;
+    const int n = (int)(k->poses.size() / 12);
+    if (time > n || time < 0) time = n - 1;                            // kinfu.cpp:213-218
+    if (time >= n) time = n - 1;
+    memcpy(pose12, &k->poses[(size_t)time * 12], 48);
+    return 0;
+}
+
+extern "C" int df_kinfu_get_info(void *h, long long *info, int n)
+{
+    KinFu *k = (KinFu *)h;
+    if (k->last_cloud < 0) {
+        int c = 0;
+        cudaMemcpyAsync(&c, k->cloud_count, sizeof(int), cudaMemcpyDeviceToHost, k->stream);
+        cudaStreamSynchronize(k->stream);
+        k->last_cloud = c;
+    }
+    double st[8] = {0};
+    cudaMemcpyAsync(st, k->solve_stats, sizeof st, cudaMemcpyDeviceToHost, k->stream);
+    cudaStreamSynchronize(k->stream);
+    unsigned long long nu = 0;
+    cudaMemcpyAsync(&nu, k->n_upd, 8, cudaMemcpyDeviceToHost, k->stream);
+    cudaStreamSynchronize(k->stream);
+    const long long vals[10] = {k->frame_counter, k->M, k->last_cloud, (long long)(k->poses.size() / 12), k->last_ok, k->launches, k->resets,
+                                (long long)st[2], (long long)nu, (long long)st[4]};
+    for (int i = 0; i < n && i < 10; ++i) info[i] = vals[i];
+    return 0;
+}
+
+extern "C" int df_kinfu_get_buffer(void *h, int which, void **ptr, size_t *pitch, int *cols, int *rows)
+{
+    KinFu *k = (KinFu *)h;
+    Img im;
+    switch (which) {
+        case 0: im.ptr = k->volume; im.pitch = (size_t)k->p.volume_dims[0] * 4; im.cols = k->p.volume_dims[0]; im.rows = k->p.volume_dims[1] * k->p.volume_dims[2]; break;
+        case 1: im = k->dists; break;
+        case 2: im = k->cur_depth[0]; break;
+        case 3: im = k->cur_pts[0]; break;
+        case 4: im = k->cur_nrm[0]; break;
+        case 5: im = k->prev_pts[0]; break;
+        case 6: im = k->prev_nrm[0]; break;
+        case 7: im = k->canon; break;
+        case 8: im = k->canon_nrm; break;
+        case 9: im.ptr = k->cloud; im.pitch = 16; im.cols = 1; im.rows = k->p.cloud_capacity; break;
+        case 10: im.ptr = k->cloud_nrm; im.pitch = 16; im.cols = 1; im.rows = k->p.cloud_capacity; break;
+        case 11: im.ptr = k->nodes; im.pitch = DF_NODE_STRIDE * 4; im.cols = 1; im.rows = k->M; break;
+        case 12: im = k->canon_visible; break;
+        case 13: im.ptr = k->solve_stats; im.pitch = 64; im.cols = 8; im.rows = 1; break;
+        default: return (int)cudaErrorInvalidValue;
+    }
+    *ptr = im.ptr; *pitch = im.pitch; *cols = im.cols; *rows = im.rows;
+    return 0;
+}
+
+extern "C" int df_kinfu_get_stage_ms(void *h, float *ms, int n)
+{
+    KinFu *k = (KinFu *)h;
+    const int m = n < NSTAGES ? n : NSTAGES;
+    for (int i = 0; i < m; ++i) ms[i] = k->stage_ms[i];
+    return m;
+}

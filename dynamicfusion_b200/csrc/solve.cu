@@ -1,0 +1,410 @@
+// solve.cu -- warp-field data-term solve on sm_100a, fully device-resident.
+//
+// Replaces WarpFieldOptimiser::optimiseWarpData -> CombinedSolver -> Opt (Terra-JIT'd LM/PCG) of the reference
+// (kfusion/src/warp_field_optimiser.cpp:7-16, kfusion/include/opt/CombinedSolver.h:25-197,
+// kfusion/solvers/dynamicfusion.t:26-52, deps/Opt/API/src/solverGPUGaussNewton.t:1016-1177), which per frame
+// re-allocates seven device images, runs N more CPU k-NN queries to build the graph, and then iterates a matrix-free
+// PCG whose every product scatters through per-edge atomicAdd and whose every dot product is fetched to the host.
+//
+// The energy is LINEAR in the unknown node translations T (J block = -w_vk * I3, constant), so the B200 design builds the
+// small normal system once per frame and keeps the whole LM/PCG iteration on one SM:
+//   1. solve_prepare   per vertex: 8-NN of the (warped) canonical vertex (shared-memory node tiles), weights
+//                      exp(-d^2/2w^2), b_v = live_v - canon_v; per-node incidence counts (warp-aggregated atomics)
+//   2. solve_scan/fill CSR incidence lists node -> (vertex, k)
+//   3. solve_rows      one block per node i: A_i* = sum_v w_vi w_v* in a shared-memory hash (double), gb_i = sum_v w_vi b_v;
+//                      rows are written sorted by column (deterministic) in column-major ELL
+//   4. solve_lm        one 1024-thread block: Levenberg-Marquardt (Ceres-style trust region, radius 1e4) around a
+//                      Jacobi-preconditioned CG on the sparse M x M system for 3 right-hand sides, all in double;
+//                      writes the translations back into the nodes (encodeTranslation).  No host round trip.
+// Sums over vertices are accumulated in double, so the atomics' ordering does not change the rounded result.
+#include "warp_common.cuh"
+
+using namespace dfb;
+
+namespace {
+
+constexpr int HCAP = 1024;      // hash slots per node row
+constexpr int ROWCAP = 512;     // stored nonzeros per row (ELL stride); overflow is reported in stats[5]
+constexpr int LM_THREADS = 1024;
+
+struct SolveWs {
+    int *idx; float *w; float4 *b;                 // per vertex
+    int *cnt, *off, *cursor, *inc;                 // incidence CSR
+    int *rownnz; int *col; double *val;            // ELL (column-major): col[e * M + i]
+    double *gb, *diag;                             // [3*M], [M]
+    double *c0_partials;                           // per prepare-block 0.5*sum|b|^2 and valid count
+    double *vec;                                   // 7 vectors of 3*M doubles
+    int *flags;                                    // [0] overflow
+    int prepare_blocks;
+};
+
+size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+size_t layout(SolveWs &ws, char *base, int M, int N)
+{
+    size_t o = 0;
+    auto take = [&](size_t bytes) { char *p = base ? base + o : nullptr; o += align_up(bytes); return p; };
+    ws.idx = (int *)take((size_t)N * 8 * 4);
+    ws.w = (float *)take((size_t)N * 8 * 4);
+    ws.b = (float4 *)take((size_t)N * 16);
+    ws.cnt = (int *)take((size_t)(M + 1) * 4);
+    ws.off = (int *)take((size_t)(M + 1) * 4);
+    ws.cursor = (int *)take((size_t)(M + 1) * 4);
+    ws.inc = (int *)take((size_t)N * 8 * 4);
+    ws.rownnz = (int *)take((size_t)M * 4);
+    ws.col = (int *)take((size_t)M * ROWCAP * 4);
+    ws.val = (double *)take((size_t)M * ROWCAP * 8);
+    ws.gb = (double *)take((size_t)M * 3 * 8);
+    ws.diag = (double *)take((size_t)M * 8);
+    ws.prepare_blocks = (N + 255) / 256;
+    ws.c0_partials = (double *)take((size_t)ws.prepare_blocks * 2 * 8);
+    ws.vec = (double *)take((size_t)M * 3 * 8 * 7);
+    ws.flags = (int *)take(64);
+    return o;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) solve_prepare_kernel(const float *__restrict__ nodes, int M, const float *__restrict__ canon,
+                                                            const float *__restrict__ live, int N, int stride, SolveWs ws)
+{
+    __shared__ KnnSmem sm;
+    __shared__ double red[2][8];
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    float3 c = make_float3(0.f, 0.f, 0.f), l = c;
+    bool valid = false;
+    if (v < N) {
+        const float *cp = canon + (size_t)v * stride, *lp = live + (size_t)v * stride;
+        c = make_float3(cp[0], cp[1], cp[2]); l = make_float3(lp[0], lp[1], lp[2]);
+        valid = !(isnan(c.x) || isnan(c.y) || isnan(c.z) || isnan(l.x) || isnan(l.y) || isnan(l.z));
+    }
+    int bi[8]; float bd[8];
+    knn8_scan(nodes, M, valid, c.x, c.y, c.z, sm, bi, bd);
+    double half_b2 = 0.0;
+    if (v < N) {
+        float3 b = make_float3(0.f, 0.f, 0.f);
+        if (valid) { b = sub3(l, c); half_b2 = 0.5 * ((double)b.x * b.x + (double)b.y * b.y + (double)b.z * b.z); }
+        ws.b[v] = make_float4(b.x, b.y, b.z, valid ? 1.f : 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int n = (v < N && valid) ? bi[k] : -1;
+        float wk = 0.f;
+        if (n >= 0) wk = node_weighting(bd[k], __ldg(nodes + (size_t)n * DF_NODE_STRIDE + 11));
+        if (v < N) { ws.idx[(size_t)v * 8 + k] = n; ws.w[(size_t)v * 8 + k] = wk; }
+        // warp-aggregated incidence count: neighbouring pixels share nodes, one atomic per distinct node per warp
+        const unsigned grp = __match_any_sync(0xffffffffu, n);
+        if (n >= 0 && (int)(__ffs(grp) - 1) == (int)(threadIdx.x & 31)) atomicAdd(ws.cnt + n, __popc(grp));
+    }
+    // deterministic per-block partials of 0.5*|b|^2 and of the valid-row count
+    double vcount = valid ? 1.0 : 0.0;
+    for (int o = 16; o > 0; o >>= 1) { half_b2 += __shfl_xor_sync(0xffffffffu, half_b2, o); vcount += __shfl_xor_sync(0xffffffffu, vcount, o); }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = half_b2; red[1][threadIdx.x >> 5] = vcount; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, bb = 0.0;
+        for (int i = 0; i < 8; ++i) { a += red[0][i]; bb += red[1][i]; }
+        ws.c0_partials[2 * blockIdx.x] = a; ws.c0_partials[2 * blockIdx.x + 1] = bb;
+    }
+}
+
+__global__ void __launch_bounds__(1024) solve_scan_kernel(SolveWs ws, int M)
+{
+    __shared__ int partial[1024];
+    const int t = threadIdx.x;
+    const int per = (M + 1023) / 1024;
+    const int b = min(M, t * per), e = min(M, b + per);
+    int s = 0;
+    for (int i = b; i < e; ++i) s += ws.cnt[i];
+    partial[t] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int v = t >= o ? partial[t - o] : 0;
+        __syncthreads();
+        partial[t] += v;
+        __syncthreads();
+    }
+    int run = partial[t] - s;
+    for (int i = b; i < e; ++i) { ws.off[i] = run; run += ws.cnt[i]; ws.cursor[i] = 0; }
+    if (t == 1023) ws.off[M] = partial[1023];
+    if (t == 0) ws.flags[0] = 0;
+}
+
+__global__ void __launch_bounds__(256) solve_fill_kernel(SolveWs ws, int N)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int n = v < N ? ws.idx[(size_t)v * 8 + k] : -1;
+        const unsigned grp = __match_any_sync(0xffffffffu, n);
+        if (n < 0) continue;
+        const int lane = threadIdx.x & 31;
+        const int leader = __ffs(grp) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(ws.cursor + n, __popc(grp));
+        base = __shfl_sync(grp, base, leader);
+        const int rank = __popc(grp & ((1u << lane) - 1u));
+        ws.inc[ws.off[n] + base + rank] = v * 8 + k;
+    }
+}
+
+// One block per node i: A_i* (sparse, via shared-memory hash), gb_i, diag_i.
+__global__ void __launch_bounds__(256) solve_rows_kernel(SolveWs ws, int M, int N, int quirk)
+{
+    __shared__ int keys[HCAP];
+    __shared__ double vals[HCAP];
+    __shared__ int list[HCAP];
+    __shared__ int nlist;
+    __shared__ double red[3][8];
+    const int i = blockIdx.x;
+    const int tid = threadIdx.x;
+    for (int s = tid; s < HCAP; s += 256) { keys[s] = -1; vals[s] = 0.0; }
+    if (tid == 0) nlist = 0;
+    __syncthreads();
+    const int beg = ws.off[i], end = ws.off[i + 1];
+    double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+    for (int e = beg + tid; e < end; e += 256) {
+        const int entry = ws.inc[e];
+        const int v = entry >> 3;
+        const double wi = (double)ws.w[entry];
+        const float4 b = ws.b[v];
+        g0 += wi * (double)b.x; g1 += wi * (double)b.y; g2 += wi * (double)b.z;
+        const int4 ia = *reinterpret_cast<const int4 *>(ws.idx + (size_t)v * 8), ib = *reinterpret_cast<const int4 *>(ws.idx + (size_t)v * 8 + 4);
+        const float4 wa = *reinterpret_cast<const float4 *>(ws.w + (size_t)v * 8), wb = *reinterpret_cast<const float4 *>(ws.w + (size_t)v * 8 + 4);
+        const int js[8] = {ia.x, ia.y, ia.z, ia.w, ib.x, ib.y, ib.z, ib.w};
+        const float wj[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+            const int j = js[kk];
+            if (j < 0) continue;
+            unsigned slot = ((unsigned)j * 2654435761u) & (HCAP - 1);
+            for (int probe = 0; probe < HCAP; ++probe) {
+                const int prev = atomicCAS(&keys[slot], -1, j);
+                if (prev == -1 || prev == j) { atomicAdd(&vals[slot], wi * (double)wj[kk]); break; }
+                slot = (slot + 1) & (HCAP - 1);
+                if (probe == HCAP - 1) ws.flags[0] = 1;
+            }
+        }
+    }
+    if (quirk && i == 0 && tid == 0 && N > 0 && ws.b[0].w != 0.f) {
+        // CombinedSolver.h:70-79: N extra edges (v = 0, n_k = node 0 for every k), weights W[0][k]
+        double sw = 0.0;
+        for (int k = 0; k < 8; ++k) sw += (double)ws.w[k];
+        const float4 b = ws.b[0];
+        g0 += (double)N * sw * (double)b.x; g1 += (double)N * sw * (double)b.y; g2 += (double)N * sw * (double)b.z;
+        unsigned slot = 0u;
+        for (int probe = 0; probe < HCAP; ++probe) {
+            const int prev = atomicCAS(&keys[slot], -1, 0);
+            if (prev == -1 || prev == 0) { atomicAdd(&vals[slot], (double)N * sw * sw); break; }
+            slot = (slot + 1) & (HCAP - 1);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) { g0 += __shfl_xor_sync(0xffffffffu, g0, o); g1 += __shfl_xor_sync(0xffffffffu, g1, o); g2 += __shfl_xor_sync(0xffffffffu, g2, o); }
+    if ((tid & 31) == 0) { red[0][tid >> 5] = g0; red[1][tid >> 5] = g1; red[2][tid >> 5] = g2; }
+    __syncthreads();
+    for (int s = tid; s < HCAP; s += 256)
+        if (keys[s] >= 0) list[atomicAdd(&nlist, 1)] = s;
+    __syncthreads();
+    const int nn = nlist;
+    if (nn > ROWCAP && tid == 0) ws.flags[0] = 1;
+    double dg = 0.0;
+    for (int a = tid; a < nn; a += 256) {
+        const int sa = list[a], ka = keys[sa];
+        int rank = 0;
+        for (int bq = 0; bq < nn; ++bq) rank += keys[list[bq]] < ka;
+        if (rank < ROWCAP) { ws.col[(size_t)rank * M + i] = ka; ws.val[(size_t)rank * M + i] = vals[sa]; }
+        if (ka == i) dg = vals[sa];
+        if (ka == i) ws.diag[i] = dg;
+    }
+    if (tid == 0) {
+        ws.rownnz[i] = min(nn, ROWCAP);
+        double a = 0.0, b = 0.0, c = 0.0;
+        for (int q = 0; q < 8; ++q) { a += red[0][q]; b += red[1][q]; c += red[2][q]; }
+        ws.gb[i] = a; ws.gb[M + i] = b; ws.gb[2 * M + i] = c;
+        if (end == beg && !(quirk && i == 0)) ws.diag[i] = 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum(double v, double *smem)
+{
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x < 32) {
+        t = threadIdx.x < (blockDim.x >> 5) ? smem[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0) smem[32] = t;
+    }
+    __syncthreads();
+    return smem[32];
+}
+
+__device__ __forceinline__ void spmv(const SolveWs &ws, int M, const double *in, double *out)
+{
+    for (int n = threadIdx.x; n < M; n += blockDim.x) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        const int nnz = ws.rownnz[n];
+        for (int e = 0; e < nnz; ++e) {
+            const int j = ws.col[(size_t)e * M + n];
+            const double a = ws.val[(size_t)e * M + n];
+            a0 += a * in[j]; a1 += a * in[M + j]; a2 += a * in[2 * M + j];
+        }
+        out[n] = a0; out[M + n] = a1; out[2 * M + n] = a2;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(LM_THREADS) solve_lm_kernel(float *nodes, int M, SolveWs ws, int nl_iters, int lin_iters, double *stats)
+{
+    __shared__ double red[40];
+    const int tid = threadIdx.x;
+    const int M3 = 3 * M;
+    double *x = ws.vec, *g = x + M3, *dl = g + M3, *r = dl + M3, *z = r + M3, *p = z + M3, *Ap = p + M3;
+
+    // x0 = current node translations (CombinedSolver.h:165-172)
+    for (int n = tid; n < M; n += LM_THREADS) {
+        const float4 *n4 = reinterpret_cast<const float4 *>(nodes + (size_t)n * DF_NODE_STRIDE);
+        const float4 a = n4[0], b = n4[1], c = n4[2];
+        const Quat t = dq_translation(Quat{a.w, b.x, b.y, b.z}, Quat{b.w, c.x, c.y, c.z});
+        x[n] = t.x; x[M + n] = t.y; x[2 * M + n] = t.z;
+    }
+    __syncthreads();
+    // cost0 = 0.5|b|^2 - x.gb + 0.5 x^T A x
+    double c0 = 0.0, nvalid = 0.0;
+    for (int i = tid; i < ws.prepare_blocks; i += LM_THREADS) { c0 += ws.c0_partials[2 * i]; nvalid += ws.c0_partials[2 * i + 1]; }
+    c0 = block_sum(c0, red);
+    nvalid = block_sum(nvalid, red);
+    spmv(ws, M, x, Ap);
+    double t0 = 0.0;
+    for (int i = tid; i < M3; i += LM_THREADS) t0 += x[i] * (0.5 * Ap[i] - ws.gb[i]);
+    double cost = c0 + block_sum(t0, red);
+    const double cost0 = cost;
+
+    double radius = 1e4, decrease = 2.0;          // solverGPUGaussNewton.t:26-39
+    int it = 0, pcg_total = 0;
+    for (; it < nl_iters; ++it) {
+        // g = gb - A x
+        spmv(ws, M, x, Ap);
+        for (int i = tid; i < M3; i += LM_THREADS) g[i] = ws.gb[i] - Ap[i];
+        __syncthreads();
+        // PCG on (A + C) dl = g, C = clamp(diag, 1e-6, 1e32) / radius, Jacobi preconditioner
+        double rz_part = 0.0;
+        for (int i = tid; i < M3; i += LM_THREADS) {
+            const double d = ws.diag[i % M];
+            const double cdamp = fmin(fmax(d, 1e-6), 1e32) / radius;
+            dl[i] = 0.0; r[i] = g[i];
+            const double zi = g[i] / (d + cdamp);
+            z[i] = zi; p[i] = zi;
+            rz_part += g[i] * zi;
+        }
+        double rz = block_sum(rz_part, red);
+        double Q0 = 0.0;
+        for (int l = 0; l < lin_iters && rz > 0.0; ++l) {
+            spmv(ws, M, p, Ap);
+            double pAp_part = 0.0;
+            for (int i = tid; i < M3; i += LM_THREADS) {
+                const double d = ws.diag[i % M];
+                const double ap = Ap[i] + fmin(fmax(d, 1e-6), 1e32) / radius * p[i];
+                Ap[i] = ap;
+                pAp_part += p[i] * ap;
+            }
+            const double pAp = block_sum(pAp_part, red);
+            if (!(pAp > 0.0)) break;
+            const double alpha = rz / pAp;
+            double rz_new_part = 0.0, q_part = 0.0;
+            for (int i = tid; i < M3; i += LM_THREADS) {
+                const double d = ws.diag[i % M];
+                const double dli = dl[i] + alpha * p[i];
+                const double ri = r[i] - alpha * Ap[i];
+                const double zi = ri / (d + fmin(fmax(d, 1e-6), 1e32) / radius);
+                dl[i] = dli; r[i] = ri; z[i] = zi;
+                rz_new_part += ri * zi;
+                q_part += dli * (ri + g[i]);
+            }
+            const double rz_new = block_sum(rz_new_part, red);
+            const double Q1 = -0.5 * block_sum(q_part, red);
+            const double beta = rz_new / rz;
+            for (int i = tid; i < M3; i += LM_THREADS) p[i] = z[i] + beta * p[i];
+            __syncthreads();
+            rz = rz_new;
+            ++pcg_total;
+            // Ceres/Opt q-tolerance (solverGPUGaussNewton.t:1093-1101)
+            const double zeta = (double)(l + 1) * (Q1 - Q0) / Q1;
+            Q0 = Q1;
+            if (zeta < 1e-4) break;
+        }
+        // model change = 0.5 dl.(g + r + C dl);  A dl = g - r - C dl  => new cost = cost - dl.g + 0.5 dl.(A dl)
+        double m_part = 0.0, a_part = 0.0, dg_part = 0.0;
+        for (int i = tid; i < M3; i += LM_THREADS) {
+            const double d = ws.diag[i % M];
+            const double cd = fmin(fmax(d, 1e-6), 1e32) / radius * dl[i];
+            m_part += dl[i] * (g[i] + r[i] + cd);
+            a_part += dl[i] * (g[i] - r[i] - cd);
+            dg_part += dl[i] * g[i];
+        }
+        const double model = 0.5 * block_sum(m_part, red);
+        const double dAd = block_sum(a_part, red);
+        const double dg = block_sum(dg_part, red);
+        const double new_cost = cost - dg + 0.5 * dAd;
+        const double change = cost - new_cost;
+        const double rho = model > 0.0 ? change / model : 0.0;
+        if (change >= 0.0 && rho > 1e-3) {
+            for (int i = tid; i < M3; i += LM_THREADS) x[i] += dl[i];
+            __syncthreads();
+            const bool stop = change <= cost * 1e-6;        // function_tolerance, CombinedSolver.h:88
+            cost = new_cost;
+            const double f = 1.0 - (2.0 * rho - 1.0) * (2.0 * rho - 1.0) * (2.0 * rho - 1.0);
+            radius /= fmax(f, 1.0 / 3.0);
+            radius = fmin(radius, 1e16);
+            decrease = 2.0;
+            if (stop) { ++it; break; }
+        } else {
+            radius /= decrease; decrease *= 2.0;
+            if (radius <= 1e-32) break;
+        }
+    }
+    // write back: encodeTranslation (CombinedSolver.h:189-197, dual_quaternion.hpp:82-85)
+    for (int n = tid; n < M; n += LM_THREADS) {
+        float *nd = nodes + (size_t)n * DF_NODE_STRIDE;
+        const Quat rot = {nd[3], nd[4], nd[5], nd[6]};
+        const Quat h = qhalf(Quat{0.f, (float)x[n], (float)x[M + n], (float)x[2 * M + n]});
+        const Quat d = qmul(h, rot);
+        nd[7] = d.w; nd[8] = d.x; nd[9] = d.y; nd[10] = d.z;
+    }
+    if (tid == 0 && stats) {
+        stats[0] = cost0; stats[1] = cost; stats[2] = (double)it; stats[3] = nvalid; stats[4] = (double)pcg_total; stats[5] = (double)ws.flags[0];
+    }
+}
+
+}  // namespace
+
+extern "C" size_t df_solve_workspace_bytes(int M, int N)
+{
+    SolveWs ws;
+    return layout(ws, nullptr, M, N) + 256;
+}
+
+extern "C" int df_solve_data_term(float *nodes, int M, const float *canon, const float *live, int N, int stride,
+                                  int nonlinear_iters, int linear_iters, int flags, double *stats_dev, void *workspace, void *stream)
+{
+    if (M <= 0 || N <= 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    SolveWs ws;
+    char *base = (char *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    layout(ws, base, M, N);
+    cudaError_t e = cudaMemsetAsync(ws.cnt, 0, (size_t)(M + 1) * 4, s);
+    if (e != cudaSuccess) return (int)e;
+    solve_prepare_kernel<<<ws.prepare_blocks, 256, 0, s>>>(nodes, M, canon, live, N, stride, ws);
+    DF_LAUNCH_CHECK();
+    solve_scan_kernel<<<1, 1024, 0, s>>>(ws, M);
+    DF_LAUNCH_CHECK();
+    solve_fill_kernel<<<ws.prepare_blocks, 256, 0, s>>>(ws, N);
+    DF_LAUNCH_CHECK();
+    solve_rows_kernel<<<M, 256, 0, s>>>(ws, M, N, flags & DF_SOLVE_REF_GRAPH_QUIRK);
+    DF_LAUNCH_CHECK();
+    solve_lm_kernel<<<1, LM_THREADS, 0, s>>>(nodes, M, ws, nonlinear_iters, linear_iters, stats_dev);
+    DF_LAUNCH_CHECK();
+    return 0;
+}

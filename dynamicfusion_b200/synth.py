@@ -61,7 +61,7 @@ def camera_drift(t: int):
     return R, tr
 
 
-def umbrella_depth(t: int, cols=640, rows=480, K=DEFAULT_K, seed=0, wall_z=1.3, noise_mm=0.5, dropout=0.01, drift=True):
+def umbrella_depth(t: int, cols=640, rows=480, K=DEFAULT_K, seed=0, wall_z=1.3, noise_mm=0.5, dropout=0.01, drift=True, shape_t=None):
     """Config C2 frame t: breathing paraboloid cap z = 0.9 + a(t)(x^2+y^2), radius 0.3 m, a(t) = 0.6+0.4 sin(2 pi t/50),
     in front of a wall; the camera drifts rigidly (camera_drift)."""
     rng = np.random.default_rng(seed * 100003 + t)
@@ -69,7 +69,7 @@ def umbrella_depth(t: int, cols=640, rows=480, K=DEFAULT_K, seed=0, wall_z=1.3, 
     R, tr = camera_drift(t) if drift else (np.eye(3), np.zeros(3))
     d = np.stack([xl, yl, np.ones_like(xl)], -1) @ R.T            # world-frame ray directions (unnormalised, z_cam = 1)
     o = tr
-    a_t = 0.6 + 0.4 * np.sin(2 * np.pi * t / 50.0)
+    a_t = 0.6 + 0.4 * np.sin(2 * np.pi * (t if shape_t is None else shape_t) / 50.0)
     # world point p = o + s*d ;  p.z = 0.9 + a (p.x^2 + p.y^2)
     A = a_t * (d[..., 0] ** 2 + d[..., 1] ** 2)
     B = 2 * a_t * (o[0] * d[..., 0] + o[1] * d[..., 1]) - d[..., 2]
@@ -80,8 +80,21 @@ def umbrella_depth(t: int, cols=640, rows=480, K=DEFAULT_K, seed=0, wall_z=1.3, 
     px = o[0] + s_par * d[..., 0]
     py = o[1] + s_par * d[..., 1]
     hit = (disc >= 0) & (s_par > 0) & (px * px + py * py <= 0.3 * 0.3)
-    s_wall = (wall_z - o[2]) / d[..., 2]
+    # tilted wall n.(p - p0) = 0 and a small static off-axis sphere: they break the cap's rotational symmetry so that
+    # all six pose degrees of freedom are observable by ICP
+    n = np.array([-0.10, -0.05, 1.0])
+    p0 = np.array([0.0, 0.0, wall_z])
+    s_wall = ((p0 - o) @ n) / (d @ n)
+    sc, sr = np.array([0.27, -0.17, 1.02]), 0.07
+    oc = o - sc
+    qa = (d * d).sum(-1)
+    qb = 2.0 * (d @ oc)
+    qc = oc @ oc - sr * sr
+    qd = qb * qb - 4 * qa * qc
+    s_sph = np.where(qd >= 0, (-qb - np.sqrt(np.maximum(qd, 0))) / (2 * qa), np.inf)
+    s_sph = np.where(s_sph > 0, s_sph, np.inf)
     s = np.where(hit, s_par, s_wall)            # camera-frame depth == s because the camera-frame ray has z = 1
+    s = np.minimum(s, s_sph)
     return _finish(s, rng, noise_mm, dropout)
 
 

@@ -144,12 +144,68 @@ int df_warp(const float *nodes, int M, float *points, float *normals, int N, int
 /* WarpFieldOptimiser::optimiseWarpData (warp_field_optimiser.hpp:14-17) -> CombinedSolver (CombinedSolver.h:25-110)
  * -> Opt LM/PCG on kfusion/solvers/dynamicfusion.t: translation-only data term solved on the device; node
  * translations are updated in place (encodeTranslation, CombinedSolver.h:189-197).
- * params: nonlinear (LM) iterations, linear (PCG) iterations; stats_dev (device, 4 doubles): initial cost, final cost,
- * LM iterations run, valid rows.  workspace from df_solve_workspace_bytes(M, N). */
+ * params: nonlinear (LM) iterations, linear (PCG) iterations; stats_dev (device, 8 doubles): initial cost, final cost,
+ * LM iterations run, valid rows, PCG iterations run, row-overflow flag.  workspace from df_solve_workspace_bytes(M, N).
+ * Rows with a NaN in canon or live are skipped (the reference zero-fills them with stale k-NN scratch). */
 size_t df_solve_workspace_bytes(int M, int N);
 #define DF_SOLVE_REF_GRAPH_QUIRK 1
 int df_solve_data_term(float *nodes, int M, const float *canon, const float *live, int N, int stride,
                        int nonlinear_iters, int linear_iters, int flags, double *stats_dev, void *workspace, void *stream);
+
+/* ------------------------------------------------------------------ per-frame pipeline ----------------------------------------------------- */
+/* kfusion::KinFuParams (kinfu.hpp:15-47) as a POD, plus the solver settings KinFu::KinFu hard-codes (kinfu.cpp:114-120)
+ * and the knobs of the GPU-resident warp field. */
+typedef struct df_kinfu_params {
+    int cols, rows;
+    df_intr intr;
+    int volume_dims[3];
+    float volume_size[3];
+    df_aff3f volume_pose;
+    float bilateral_sigma_depth, bilateral_sigma_spatial;
+    int bilateral_kernel_size;
+    float icp_truncate_depth_dist, icp_dist_thres, icp_angle_thres;
+    int icp_iter_num[4];
+    float tsdf_min_camera_movement, tsdf_trunc_dist;
+    int tsdf_max_weight;
+    float raycast_step_factor, gradient_delta_factor;
+    float light_pose[3];
+    int solver_nonlinear_iters, solver_linear_iters;   /* 5, 100 (kinfu.cpp:116-117) */
+    int max_nodes;        /* cap on warp nodes; node_step grows to respect it */
+    int node_step;        /* every node_step-th extracted point becomes a node: 50 (warp_field.cpp:49) */
+    int cloud_capacity;   /* extracted-cloud buffer, points: 256^3 in the reference (tsdf_volume.cpp:184) */
+    int flags;            /* DF_KINFU_* */
+} df_kinfu_params;
+
+#define DF_KINFU_RIGID_ONLY 1      /* skip warp + solve (plain KinFu loop: config 1) */
+#define DF_KINFU_STAGE_TIMING 2    /* record CUDA events per stage (df_kinfu_get_stage_ms) */
+#define DF_KINFU_REF_GRAPH_QUIRK 4 /* forward DF_SOLVE_REF_GRAPH_QUIRK to the solve */
+
+/* which = 0: KinFuParams::default_params_dynamicfusion (kinfu.cpp:14-49); 1: default_params (kinfu.cpp:55-89) */
+void df_kinfu_default_params(df_kinfu_params *p, int which);
+/* KinFu::KinFu (kinfu.cpp:95-125): allocates volume, pyramids, ICP and warp/solver state on the current device */
+void *df_kinfu_create(const df_kinfu_params *p);
+void df_kinfu_destroy(void *kinfu);
+int df_kinfu_set_stream(void *kinfu, void *stream);
+/* KinFu::reset (kinfu.cpp:196-207) */
+int df_kinfu_reset(void *kinfu);
+/* KinFu::operator()(depth) (kinfu.cpp:221-305).  Returns 1 = frame fused and ray-cast image available, 0 = first frame or
+ * tracking reset (the reference's `false`), < 0 = -(cudaError).  _host: depth is a HOST u16 image (any pitch), copied to
+ * the device inside the call (the path apps/demo.cpp takes: imread -> upload -> operator()); _device: depth already in HBM. */
+int df_kinfu_process_host(void *kinfu, const uint16_t *depth_host, size_t pitch);
+int df_kinfu_process_device(void *kinfu, const uint16_t *depth_dev, size_t pitch);
+/* KinFu::getCameraPose(time) (kinfu.cpp:213-218): 12 floats, R row-major then t; time < 0 = latest */
+int df_kinfu_get_pose(void *kinfu, int time, float *pose12_host);
+/* info[0] frame counter, [1] warp nodes M, [2] extracted cloud points, [3] poses stored, [4] last ICP ok,
+ * [5] kernels launched in the last frame, [6] resets so far, [7] solver LM iterations (last frame),
+ * [8] voxels written by the last integrate (DF_KINFU_STAGE_TIMING only), [9] solver PCG iterations (last frame) */
+int df_kinfu_get_info(void *kinfu, long long *info_host, int n);
+/* device buffers of the current state: 0 volume(u32), 1 dists, 2 curr depth L0, 3 curr points L0, 4 curr normals L0,
+ * 5 prev points L0, 6 prev normals L0, 7 canonical (after 2nd warp), 8 canonical normals, 9 extracted cloud,
+ * 10 extracted normals, 11 nodes, 12 canonical_visible, 13 solver stats (8 doubles) */
+int df_kinfu_get_buffer(void *kinfu, int which, void **ptr, size_t *pitch, int *cols, int *rows);
+/* per-stage milliseconds of the last frame (DF_KINFU_STAGE_TIMING): preprocess, icp, raycast_canonical, warp1, solve,
+ * warp2, project_remove, integrate, extract, raycast_prev; returns the number written */
+int df_kinfu_get_stage_ms(void *kinfu, float *ms_host, int n);
 
 #ifdef __cplusplus
 }

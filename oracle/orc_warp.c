@@ -195,3 +195,112 @@ void orc_warp(const float *nodes, int M, float *points, float *normals, long lon
         ++cursor;
     }
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Grid-accelerated exact 8-NN with the SAME result as orc_knn8 (the 8 smallest by (distance, node index)); used by the
+ * pipeline restatement and the CPU baseline so the baseline is not handicapped by an O(N*M) scan (the reference uses a
+ * kd-tree, warp_field.cpp:247-251). */
+#include <stdlib.h>
+typedef struct { float mn[3]; float cell; int dim[3]; int *start; int *items; } orc_grid;
+
+static void grid_build(orc_grid *g, const float *nodes, int M)
+{
+    float mx[3];
+    for (int c = 0; c < 3; ++c) { g->mn[c] = 3.4e38f; mx[c] = -3.4e38f; }
+    for (int m = 0; m < M; ++m)
+        for (int c = 0; c < 3; ++c) {
+            float v = nodes[(size_t)m * ORC_NODE_STRIDE + c];
+            if (v < g->mn[c]) g->mn[c] = v;
+            if (v > mx[c]) mx[c] = v;
+        }
+    float ext = 0.f;
+    for (int c = 0; c < 3; ++c) if (mx[c] - g->mn[c] > ext) ext = mx[c] - g->mn[c];
+    int res = (int)ceil(cbrt((double)M / 2.0));
+    if (res < 1) res = 1;
+    if (res > 128) res = 128;
+    g->cell = ext > 0 ? ext / (float)res * 1.0001f : 1.f;
+    for (int c = 0; c < 3; ++c) { g->dim[c] = (int)((mx[c] - g->mn[c]) / g->cell) + 1; }
+    size_t ncell = (size_t)g->dim[0] * g->dim[1] * g->dim[2];
+    g->start = (int *)calloc(ncell + 1, sizeof(int));
+    g->items = (int *)malloc((size_t)(M > 0 ? M : 1) * sizeof(int));
+    int *cellof = (int *)malloc((size_t)(M > 0 ? M : 1) * sizeof(int));
+    for (int m = 0; m < M; ++m) {
+        int ci[3];
+        for (int c = 0; c < 3; ++c) {
+            ci[c] = (int)((nodes[(size_t)m * ORC_NODE_STRIDE + c] - g->mn[c]) / g->cell);
+            if (ci[c] >= g->dim[c]) ci[c] = g->dim[c] - 1;
+            if (ci[c] < 0) ci[c] = 0;
+        }
+        cellof[m] = ci[0] + g->dim[0] * (ci[1] + g->dim[1] * ci[2]);
+        g->start[cellof[m] + 1]++;
+    }
+    for (size_t i = 0; i < ncell; ++i) g->start[i + 1] += g->start[i];
+    int *cur = (int *)malloc((ncell + 1) * sizeof(int));
+    memcpy(cur, g->start, (ncell + 1) * sizeof(int));
+    for (int m = 0; m < M; ++m) g->items[cur[cellof[m]]++] = m;
+    free(cur); free(cellof);
+}
+
+static inline void knn_insert_lex(int32_t *bi, float *bd, float dist, int m)
+{
+    if (!(dist < bd[7] || (dist == bd[7] && m < bi[7]))) return;
+    int i = 7;
+    while (i > 0 && (bd[i - 1] > dist || (bd[i - 1] == dist && bi[i - 1] > m))) { bd[i] = bd[i - 1]; bi[i] = bi[i - 1]; --i; }
+    bd[i] = dist; bi[i] = m;
+}
+
+void orc_knn8_fast(const float *nodes, int M, const float *queries, long long N, int qstride, int32_t *idx, float *d2)
+{
+    if (M < 64) { orc_knn8(nodes, M, queries, N, qstride, idx, d2); return; }
+    orc_grid g;
+    grid_build(&g, nodes, M);
+#pragma omp parallel for schedule(dynamic, 256)
+    for (long long q = 0; q < N; ++q) {
+        const float *p = queries + (size_t)q * qstride;
+        int32_t bi[8]; float bd[8];
+        for (int i = 0; i < 8; ++i) { bi[i] = 0x7fffffff; bd[i] = 3.402823466e+38f; }
+        if (!(p[0] != p[0] || p[1] != p[1] || p[2] != p[2])) {
+            int c0[3];
+            float dout = 0.f;                      /* distance from p to the grid's bounding box (0 inside) */
+            for (int c = 0; c < 3; ++c) {
+                float rel = (p[c] - g.mn[c]) / g.cell;
+                c0[c] = (int)floorf(rel);
+                float lo = g.mn[c], hi = g.mn[c] + g.cell * (float)g.dim[c];
+                float dd = p[c] < lo ? lo - p[c] : (p[c] > hi ? p[c] - hi : 0.f);
+                dout += dd * dd;
+                if (c0[c] < 0) c0[c] = 0;
+                if (c0[c] >= g.dim[c]) c0[c] = g.dim[c] - 1;
+            }
+            (void)dout;
+            int maxr = g.dim[0] > g.dim[1] ? g.dim[0] : g.dim[1];
+            if (g.dim[2] > maxr) maxr = g.dim[2];
+            for (int r = 0; r <= maxr; ++r) {
+                /* every unvisited cell is at least (r-1)*cell away from p along some axis once p's own cell is clamped
+                 * into the grid; stop when that bound (conservatively shrunk) exceeds the current worst */
+                if (r >= 2 && bi[7] != 0x7fffffff) {
+                    float bound = (float)(r - 1) * g.cell * 0.999f;
+                    if (bound * bound > bd[7]) break;
+                }
+                for (int z = c0[2] - r; z <= c0[2] + r; ++z) {
+                    if (z < 0 || z >= g.dim[2]) continue;
+                    for (int y = c0[1] - r; y <= c0[1] + r; ++y) {
+                        if (y < 0 || y >= g.dim[1]) continue;
+                        int shell = (z == c0[2] - r || z == c0[2] + r || y == c0[1] - r || y == c0[1] + r);
+                        for (int x = c0[0] - r; x <= c0[0] + r; x += (shell ? 1 : (2 * r > 0 ? 2 * r : 1))) {
+                            if (x < 0 || x >= g.dim[0]) continue;
+                            size_t cid = (size_t)x + (size_t)g.dim[0] * ((size_t)y + (size_t)g.dim[1] * z);
+                            for (int it = g.start[cid]; it < g.start[cid + 1]; ++it) {
+                                int m = g.items[it];
+                                const float *v = nodes + (size_t)m * ORC_NODE_STRIDE;
+                                float d0 = p[0] - v[0], d1 = p[1] - v[1], dd2 = p[2] - v[2];
+                                knn_insert_lex(bi, bd, d0 * d0 + d1 * d1 + dd2 * dd2, m);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        for (int i = 0; i < 8; ++i) { idx[q * 8 + i] = bi[i] == 0x7fffffff ? -1 : bi[i]; d2[q * 8 + i] = bd[i]; }
+    }
+    free(g.start); free(g.items);
+}

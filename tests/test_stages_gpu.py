@@ -1,0 +1,210 @@
+"""GPU parity: extraction, ICP, k-NN + DQB warp and the data-term solve (through the C ABI) vs the CPU oracle."""
+import math
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from dynamicfusion_b200 import host, synth  # noqa: E402
+
+K = synth.DEFAULT_K
+
+
+def _volume_with_scene(dim, frames=2):
+    vol = host.TsdfVolume((dim, dim, dim))
+    vol.setTruncDist(0.04); vol.setMaxWeight(64); vol.setSize((1.0, 1.0, 1.0)); vol.setPose(synth.volume_pose(1.0))
+    vol.setRaycastStepFactor(0.75); vol.setGradientDeltaFactor(0.5); vol.clear()
+    for t in range(frames):
+        dists = host.computeDists(host.u16_to_device(synth.umbrella_depth(t, drift=False)), K)
+        vol.integrate(dists, host.identity_pose(), K)
+    return vol
+
+
+@pytest.mark.parametrize("dim", [64, 96])
+def test_extract_cloud_and_normals(orc, dim):
+    vol = _volume_with_scene(dim)
+    ref_vol = vol.data_.cpu().numpy().view(np.uint32).copy()
+    cap = 400000
+    pts, count = vol.fetchCloud(cap)
+    n = int(count.item())
+    ref = orc.extract_cloud(ref_vol, vol.getDims(), vol.getVoxelSize(), vol.getTruncDist(), vol.getMaxWeight(), vol.getPose(), cap)
+    assert n == len(ref) and n > 2000
+    got = pts[:n].cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), "extraction must match the oracle point for point, in order"
+    nrm = vol.fetchNormals(pts, n)
+    Rinv = np.linalg.inv(vol.getPose()[0].astype(np.float64)).astype(np.float32)
+    ref_n = orc.extract_normals(ref_vol, vol.getDims(), vol.getVoxelSize(), vol.getTruncDist(), vol.getMaxWeight(), ref, vol.getPose(), Rinv, 0.5)
+    assert np.array_equal(nrm.cpu().numpy().view(np.uint32), ref_n.view(np.uint32))
+    # device-side count path
+    nrm2 = vol.fetchNormals(pts, cap, count)[:n]
+    assert np.array_equal(nrm2.cpu().numpy().view(np.uint32), ref_n.view(np.uint32))
+
+
+def test_extract_capacity_clamp_and_empty(orc):
+    vol = _volume_with_scene(64)
+    pts, count = vol.fetchCloud(1000)
+    assert int(count.item()) == 1000
+    ref = orc.extract_cloud(vol.data_.cpu().numpy().view(np.uint32).copy(), vol.getDims(), vol.getVoxelSize(), vol.getTruncDist(),
+                            vol.getMaxWeight(), vol.getPose(), 1000)
+    assert np.array_equal(pts.cpu().numpy().view(np.uint32), ref.view(np.uint32))
+    vol.clear()
+    pts, count = vol.fetchCloud(1000)
+    assert int(count.item()) == 0
+
+
+def _pyramids(orc, depth):
+    d0 = orc.bilateral(depth, 7, 4.5, 0.04)
+    ds = [d0]
+    for _ in range(2):
+        ds.append(orc.pyr_down(ds[-1], 0.04))
+    return [orc.points_normals(tuple(k / (1 << i) for k in K), d) for i, d in enumerate(ds)]
+
+
+def test_icp_accumulate_and_estimate(orc):
+    a = _pyramids(orc, synth.umbrella_depth(0))
+    b = _pyramids(orc, synth.umbrella_depth(3, shape_t=0))
+    icp = host.ProjectiveICP()
+    icp.setDistThreshold(0.1); icp.setAngleThreshold(30 * 0.017453293); icp.setIterationsNum([10, 5, 4, 0])
+    dev = lambda x: torch.from_numpy(x).cuda()
+    T = (np.eye(3, dtype=np.float32), np.array([0.002, -0.001, 0.0], np.float32))
+    for lvl in range(3):
+        Kl = tuple(k / (1 << lvl) for k in K)
+        got = icp.accumulate(dev(b[lvl][0]), dev(b[lvl][1]), dev(a[lvl][0]), dev(a[lvl][1]), Kl, T).cpu().numpy()
+        ref, inl = orc.icp_accumulate(b[lvl][0], b[lvl][1], a[lvl][0], a[lvl][1], Kl, T, 0.1 * 0.1, math.cos(30 * 0.017453293))
+        assert inl > 1000
+        scale = np.abs(ref).max()
+        assert np.abs(got - ref).max() <= 1e-5 * scale, (lvl, got - ref)
+    ok, (R, t) = icp.estimateTransform(K, [dev(x[0]) for x in b], [dev(x[1]) for x in b], [dev(x[0]) for x in a], [dev(x[1]) for x in a])
+    ok_r, (Rr, tr) = orc.icp_estimate([x[0] for x in b], [x[1] for x in b], [x[0] for x in a], [x[1] for x in a], [10, 5, 4], K, 0.1,
+                                      np.float32(30 * 0.017453293))
+    assert ok and ok_r
+    assert np.abs(R - Rr).max() < 1e-5 and np.abs(t - tr).max() < 1e-5
+    # run-to-run determinism of the device path
+    ok2, (R2, t2) = icp.estimateTransform(K, [dev(x[0]) for x in b], [dev(x[1]) for x in b], [dev(x[0]) for x in a], [dev(x[1]) for x in a])
+    assert np.array_equal(R, R2) and np.array_equal(t, t2)
+
+
+def test_icp_degenerate_returns_false(orc):
+    a = _pyramids(orc, synth.umbrella_depth(0))
+    blank = _pyramids(orc, np.zeros((480, 640), np.uint16))
+    icp = host.ProjectiveICP()
+    dev = lambda x: torch.from_numpy(x).cuda()
+    ok, _ = icp.estimateTransform(K, [dev(x[0]) for x in blank], [dev(x[1]) for x in blank], [dev(x[0]) for x in a], [dev(x[1]) for x in a])
+    assert ok is False
+
+
+def _random_nodes(rng, M):
+    pts = rng.uniform(-0.3, 0.3, (M, 3)).astype(np.float32)
+    nodes = np.zeros((M, 12), np.float32)
+    nodes[:, 0:3] = pts
+    # random unit rotations + translations, encoded as the reference does (dual = 0.5 * (0,t) * r)
+    q = rng.normal(size=(M, 4)).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    q[:, 0] = np.abs(q[:, 0]) + 1.0                      # keep rotations in one hemisphere (no antipodal cancellation)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    nodes[:, 3:7] = q
+    nodes[:, 11] = rng.uniform(0.05, 3.0, M).astype(np.float32)
+    return nodes
+
+
+@pytest.mark.parametrize("M,N", [(8, 100), (300, 5000), (2500, 20000)])
+def test_knn_and_warp(orc, M, N):
+    import ctypes as C
+    rng = np.random.default_rng(M)
+    nodes = _random_nodes(rng, M)
+    for m in range(M):
+        t = rng.normal(scale=0.02, size=3).astype(np.float32)
+        orc.load().orc_node_encode_translation(C.c_void_p(nodes[m].ctypes.data), C.c_float(t[0]), C.c_float(t[1]), C.c_float(t[2]))
+    if M > 20:
+        nodes[10, :3] = nodes[11, :3]                    # duplicate vertex -> distance ties
+    pts = rng.uniform(-0.35, 0.35, (N, 4)).astype(np.float32)
+    pts[:, 3] = 0
+    nrm = rng.normal(size=(N, 4)).astype(np.float32)
+    pts[::13, 0] = np.nan
+    nrm[::17, 0] = np.nan
+    pts[1, :3] = nodes[min(10, M - 1), :3]               # query exactly on a (possibly duplicated) node
+    wf = host.WarpField()
+    wf.nodes_ = torch.from_numpy(nodes).cuda()
+    idx, d2 = wf.KNN(torch.from_numpy(pts).cuda())
+    ridx, rd2 = orc.knn8(nodes, pts)
+    assert np.array_equal(idx.cpu().numpy(), ridx), "k-NN indices must be bit-exact"
+    assert np.array_equal(d2.cpu().numpy().view(np.uint32), rd2.view(np.uint32))
+    for flags in (0, 2):
+        p_dev, n_dev = torch.from_numpy(pts).cuda(), torch.from_numpy(nrm).cuda()
+        kidx, kw = wf.warp(p_dev, n_dev, flags=flags, want_knn=True)
+        p_ref, n_ref = pts.copy(), nrm.copy()
+        orc.warp(nodes, p_ref, n_ref, flags=flags)
+        gp, gn = p_dev.cpu().numpy(), n_dev.cpu().numpy()
+        assert np.array_equal(np.isnan(gp), np.isnan(p_ref)) and np.array_equal(np.isnan(gn), np.isnan(n_ref))
+        m = ~np.isnan(p_ref[:, 0])
+        np.testing.assert_allclose(gp[m], p_ref[m], rtol=1e-4, atol=1e-6)       # north-star tolerance: 1e-4 relative
+        mn = ~np.isnan(n_ref[:, 0])
+        np.testing.assert_allclose(gn[mn], n_ref[mn], rtol=1e-4, atol=1e-6)
+        assert np.mean(gp[m].view(np.uint32) == p_ref[m].view(np.uint32)) > 0.99   # in practice bit-identical (double exp)
+    skipped = np.isnan(pts[:, 0]) | np.isnan(nrm[:, 0])
+    assert np.array_equal(p_dev.cpu().numpy()[skipped].view(np.uint32), pts[skipped].view(np.uint32)), "skipped points untouched"
+
+
+CUBE = [(1, 1, 1), (1, 1, -1), (1, -1, 1), (1, -1, -1), (-1, 1, 1), (-1, 1, -1), (-1, -1, 1), (-1, -1, -1)]
+
+
+def _gpu_solve(node_pts, src, dst, nl=300, lin=250, flags=0):
+    wf = host.WarpField()
+    wf.init(node_pts)
+    s = np.zeros((len(src), 4), np.float32); s[:, :3] = src
+    d = np.zeros((len(dst), 4), np.float32); d[:, :3] = dst
+    stats = wf.optimiseWarpData(torch.from_numpy(s).cuda(), torch.from_numpy(d).cuda(), nl, lin, flags)
+    nrm = np.zeros_like(s); nrm[:, 2] = 1
+    p_dev, n_dev = torch.from_numpy(s.copy()).cuda(), torch.from_numpy(nrm).cuda()
+    wf.warp(p_dev, n_dev)
+    return wf, p_dev.cpu().numpy()[:, :3], stats.cpu().numpy()
+
+
+def test_solve_reference_scenario_single_vertex():
+    """reference tests/warp_test.cpp:15-69: 8 cube-corner nodes, one vertex, tolerance 1e-5; closed form 0.05/(8w)"""
+    wf, warped, stats = _gpu_solve(CUBE, [(0, 0, 0)], [(0.05, 0.05, 0.05)], nl=15 * 20, lin=250)
+    np.testing.assert_allclose(warped, [[0.05, 0.05, 0.05]], atol=1e-5)
+    nodes = wf.nodes_.cpu().numpy()
+    w = math.exp(-3.0 / 18.0)
+    np.testing.assert_allclose(2 * nodes[:, 8:11], np.full((8, 3), 0.05 / (8 * w)), rtol=1e-4)   # identity rotation: t = 2*dual.xyz
+
+
+@pytest.mark.parametrize("name", ["rigid", "multiple_nodes", "non_rigid"])
+def test_solve_reference_scenarios_match_oracle(orc, name):
+    from tests.test_oracle_golden import SCENARIOS, _lsq_reference
+    node_pts, src, dst = SCENARIOS[name]
+    wf, warped, stats = _gpu_solve(node_pts, src, dst)
+    best, _, _ = _lsq_reference(node_pts, src, dst)
+    np.testing.assert_allclose(warped, best, atol=2e-4)
+    nodes_ref = orc.make_nodes(node_pts)
+    ostats = orc.solve_data_term(nodes_ref, np.array(src, np.float32), np.array(dst, np.float32), lm_iters=300)
+    assert abs(stats[1] - ostats[1]) <= 1e-4 * max(ostats[1], 1e-12) + 1e-10
+    assert abs(stats[0] - ostats[0]) <= 1e-9 * ostats[0]
+    assert stats[5] == 0
+
+
+def test_solve_large_matches_matrix_free_oracle(orc):
+    from oracle import orc_pipe
+    rng = np.random.default_rng(7)
+    M, N = 600, 40000
+    node_pts = rng.uniform(-0.3, 0.3, (M, 3)).astype(np.float32)
+    src = np.zeros((N, 4), np.float32)
+    src[:, :3] = rng.uniform(-0.3, 0.3, (N, 3))
+    dst = src.copy()
+    dst[:, :3] += (0.01 * np.stack([np.sin(5 * src[:, 0]), np.cos(4 * src[:, 1]), src[:, 2]], 1)).astype(np.float32)
+    src[::50, 1] = np.nan
+    dst[::77, 2] = np.nan
+    for flags in (0, 1):
+        wf = host.WarpField()
+        wf.init(node_pts)
+        stats = wf.optimiseWarpData(torch.from_numpy(src).cuda(), torch.from_numpy(dst).cuda(), 5, 100, flags).cpu().numpy()
+        nodes_ref = orc.make_nodes(node_pts)
+        ostats = orc_pipe.solve_data_term_big(nodes_ref, src, dst, flags=flags, lm_iters=5, lin_iters=100)
+        assert stats[3] == ostats[3] and stats[5] == 0
+        assert abs(stats[0] - ostats[0]) <= 1e-6 * ostats[0]
+        assert abs(stats[1] - ostats[1]) <= 1e-4 * ostats[1]
+        got = wf.nodes_.cpu().numpy()
+        t_got, t_ref = 2 * got[:, 8:11], orc.node_translations(nodes_ref)[:, 1:]
+        assert np.abs(t_got - t_ref).max() <= 1e-3 * np.abs(t_ref).max()
