@@ -65,10 +65,13 @@ PROTOTYPES = {
     "df_icp_accumulate": (_i, [_vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _i, _i, Intr, Aff3f, _f, _f, _vp, _vp]),
     "df_icp_estimate": (_i, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i),
                              C.POINTER(_sz), _i, C.POINTER(_i), Intr, _f, _f, _vp, _vp, _vp, _vp]),
-    "df_knn8": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _vp]),
-    "df_warp": (_i, [_vp, _i, _vp, _vp, _i, _i, Aff3f, _i, _vp, _vp, _vp]),
+    "df_knn8": (_i, [_vp, _i, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "df_node_grid_bytes": (_sz, [_i]),
+    "df_build_node_grid": (_i, [_vp, _i, _vp, _vp]),
+    "df_warp": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, Aff3f, _i, _vp, _vp, _vp]),
     "df_solve_workspace_bytes": (_sz, [_i, _i]),
-    "df_solve_data_term": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "df_solve_knn_buffers": (_i, [_vp, _i, _i, C.POINTER(_vp), C.POINTER(_vp)]),
+    "df_solve_data_term": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "df_kinfu_default_params": (None, [C.POINTER(KinfuParams), _i]),
     "df_kinfu_create": (_vp, [C.POINTER(KinfuParams)]),
     "df_kinfu_destroy": (None, [_vp]),
@@ -80,6 +83,7 @@ PROTOTYPES = {
     "df_kinfu_get_info": (_i, [_vp, C.POINTER(C.c_longlong), _i]),
     "df_kinfu_get_buffer": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_sz), C.POINTER(_i), C.POINTER(_i)]),
     "df_kinfu_set_stream": (_i, [_vp, _vp]),
+    "df_kinfu_read_buffer": (_i, [_vp, _i, _vp, _sz]),
 }
 
 

@@ -140,31 +140,56 @@ __global__ void __launch_bounds__(EX_THREADS) extract_count_kernel(const Extract
     if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
 }
 
-// single-block exclusive scan over the per-block counts (nblocks <= a few hundred thousand ints)
-__global__ void __launch_bounds__(1024) extract_scan_kernel(const int *counts, int *offsets, int n, int capacity, int *count_out)
+// two-level exclusive scan over the per-block counts: 1024 counts per "super" block (warp-shuffle scan), then one block
+// over the <= 1024 super totals.  (A single-block serial-chunk scan of the 131,072 counts of a 512^3 volume took 0.26 ms.)
+__global__ void __launch_bounds__(1024) extract_scan_local_kernel(const int *counts, int *offsets, int n, int *super_tot)
 {
-    __shared__ int partial[1024];
-    const int t = threadIdx.x;
-    const int per = (n + 1023) / 1024;
-    const int b = min(n, t * per), e = min(n, b + per);
-    int s = 0;
-    for (int i = b; i < e; ++i) s += counts[i];
-    partial[t] = s;
+    __shared__ int wsum[32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int i = blockIdx.x * 1024 + t;
+    const int c = i < n ? counts[i] : 0;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) wsum[warp] = incl;
     __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-        const int v = t >= o ? partial[t - o] : 0;
-        __syncthreads();
-        partial[t] += v;
-        __syncthreads();
+    if (warp == 0) {
+        int w = wsum[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += v; }
+        wsum[lane] = w;
     }
-    int run = partial[t] - s;
-    for (int i = b; i < e; ++i) { offsets[i] = run; run += counts[i]; }
-    if (t == 1023) *count_out = min(partial[1023], capacity);
+    __syncthreads();
+    const int base = warp ? wsum[warp - 1] : 0;
+    if (i < n) offsets[i] = base + incl - c;
+    if (t == 1023) super_tot[blockIdx.x] = wsum[31];
+}
+
+__global__ void __launch_bounds__(1024) extract_scan_super_kernel(const int *super_tot, int nsuper, int *super_off, int capacity, int *count_out)
+{
+    __shared__ int wsum[32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int c = t < nsuper ? super_tot[t] : 0;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = wsum[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += v; }
+        wsum[lane] = w;
+    }
+    __syncthreads();
+    const int base = warp ? wsum[warp - 1] : 0;
+    if (t < nsuper) super_off[t] = base + incl - c;
+    if (t == 1023) *count_out = min(wsum[31], capacity);
 }
 
 template <int VX>
 __global__ void __launch_bounds__(EX_THREADS) extract_emit_kernel(const ExtractParams p, const int *block_counts, const int *offsets,
-                                                                  float4 *out, int capacity)
+                                                                  const int *super_off, float4 *out, int capacity)
 {
     if (block_counts[blockIdx.x] == 0) return;
     const size_t v0 = ((size_t)blockIdx.x * EX_THREADS + threadIdx.x) * VX;
@@ -172,7 +197,7 @@ __global__ void __launch_bounds__(EX_THREADS) extract_emit_kernel(const ExtractP
     int n = 0;
     thread_crossings<VX>(p, v0, [&](const float3 q) { pts[n++] = q; });
     const int local = block_exclusive_scan(n, nullptr);
-    const int base = offsets[blockIdx.x] + local;
+    const int base = super_off[blockIdx.x >> 10] + offsets[blockIdx.x] + local;
 #pragma unroll
     for (int i = 0; i < 3 * VX; ++i)
         if (i < n && base + i < capacity) out[base + i] = make_float4(pts[i].x, pts[i].y, pts[i].z, 0.f);
@@ -198,7 +223,7 @@ extern "C" size_t df_extract_workspace_bytes(df_volume vol)
 {
     const size_t nvox = (size_t)vol.dims[0] * vol.dims[1] * vol.dims[2];
     const size_t nblocks = (nvox + EX_THREADS - 1) / EX_THREADS;          // upper bound (VX = 1)
-    return (2 * nblocks + 64) * sizeof(int);
+    return (2 * nblocks + 2048 + 64) * sizeof(int);
 }
 
 extern "C" int df_extract_cloud(df_volume vol, df_aff3f pose, float *out_points, int capacity, int *count, void *workspace, void *stream)
@@ -211,10 +236,15 @@ extern "C" int df_extract_cloud(df_volume vol, df_aff3f pose, float *out_points,
     if (vx == 4) extract_count_kernel<4><<<p.nblocks, EX_THREADS, 0, s>>>(p, block_counts);
     else extract_count_kernel<1><<<p.nblocks, EX_THREADS, 0, s>>>(p, block_counts);
     DF_LAUNCH_CHECK();
-    extract_scan_kernel<<<1, 1024, 0, s>>>(block_counts, offsets, p.nblocks, capacity, count);
+    const int nsuper = (p.nblocks + 1023) / 1024;
+    if (nsuper > 1024) return (int)cudaErrorInvalidValue;               // > 2^20 blocks (volume > 1024^3 voxels)
+    int *super_tot = offsets + p.nblocks, *super_off = super_tot + 1024;
+    extract_scan_local_kernel<<<nsuper, 1024, 0, s>>>(block_counts, offsets, p.nblocks, super_tot);
     DF_LAUNCH_CHECK();
-    if (vx == 4) extract_emit_kernel<4><<<p.nblocks, EX_THREADS, 0, s>>>(p, block_counts, offsets, (float4 *)out_points, capacity);
-    else extract_emit_kernel<1><<<p.nblocks, EX_THREADS, 0, s>>>(p, block_counts, offsets, (float4 *)out_points, capacity);
+    extract_scan_super_kernel<<<1, 1024, 0, s>>>(super_tot, nsuper, super_off, capacity, count);
+    DF_LAUNCH_CHECK();
+    if (vx == 4) extract_emit_kernel<4><<<p.nblocks, EX_THREADS, 0, s>>>(p, block_counts, offsets, super_off, (float4 *)out_points, capacity);
+    else extract_emit_kernel<1><<<p.nblocks, EX_THREADS, 0, s>>>(p, block_counts, offsets, super_off, (float4 *)out_points, capacity);
     DF_LAUNCH_CHECK();
     return 0;
 }

@@ -147,28 +147,52 @@ __device__ double det6_dev(const double *Ain)
     return det;
 }
 
-// Cholesky solve; returns false when a pivot is not safely positive (caller falls back to the eigen solve)
-__device__ bool chol6_solve(const double *Ain, const double *b, double *x)
+// Cholesky solve, fully unrolled so that L, y, x live in registers (the tail is one thread: local-memory round trips
+// were 20 us per ICP iteration).  Returns false when a pivot is not safely positive (caller falls back to LU + the eigen
+// solve).  *det receives det(A) = (prod L_jj)^2.
+__device__ __forceinline__ bool chol6_solve(const double (&A)[36], const double (&b)[6], double (&x)[6], double *det)
 {
     double L[36];
     double dmax = 0.0;
-    for (int i = 0; i < 6; ++i) dmax = fmax(dmax, fabs(Ain[i * 6 + i]));
+#pragma unroll
+    for (int i = 0; i < 6; ++i) dmax = fmax(dmax, fabs(A[i * 6 + i]));
+    bool ok = true;
+    double dprod = 1.0;
+#pragma unroll
     for (int j = 0; j < 6; ++j) {
-        double d = Ain[j * 6 + j];
+        double d = A[j * 6 + j];
+#pragma unroll
         for (int k = 0; k < j; ++k) d -= L[j * 6 + k] * L[j * 6 + k];
-        if (!(d > dmax * 1e-13)) return false;
+        if (!(d > dmax * 1e-13)) { ok = false; d = 1.0; }
         d = sqrt(d);
+        dprod *= d;
         L[j * 6 + j] = d;
+        const double dinv = 1.0 / d;
+#pragma unroll
         for (int i = j + 1; i < 6; ++i) {
-            double s = Ain[i * 6 + j];
+            double s = A[i * 6 + j];
+#pragma unroll
             for (int k = 0; k < j; ++k) s -= L[i * 6 + k] * L[j * 6 + k];
-            L[i * 6 + j] = s / d;
+            L[i * 6 + j] = s * dinv;
         }
     }
     double y[6];
-    for (int i = 0; i < 6; ++i) { double s = b[i]; for (int k = 0; k < i; ++k) s -= L[i * 6 + k] * y[k]; y[i] = s / L[i * 6 + i]; }
-    for (int i = 5; i >= 0; --i) { double s = y[i]; for (int k = i + 1; k < 6; ++k) s -= L[k * 6 + i] * x[k]; x[i] = s / L[i * 6 + i]; }
-    return true;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double s = b[i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) s -= L[i * 6 + k] * y[k];
+        y[i] = s / L[i * 6 + i];
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+        double s = y[i];
+#pragma unroll
+        for (int k = i + 1; k < 6; ++k) s -= L[k * 6 + i] * x[k];
+        x[i] = s / L[i * 6 + i];
+    }
+    *det = dprod * dprod;
+    return ok;
 }
 
 // symmetric-eigen pseudo-inverse (what cv::solve(DECOMP_SVD) computes for a symmetric matrix); slow path
@@ -215,16 +239,23 @@ __global__ void __launch_bounds__(256) icp_solve_kernel(const double *partials, 
     reduce_partials(partials, nblocks, sums);
     if (threadIdx.x != 0) return;
     double A[36], b[6];
-    int shift = 0;
-    for (int i = 0; i < 6; ++i)
-        for (int j = i; j < 7; ++j) {
-            const double value = (double)(float)sums[shift++];          // the reference's buffer is float
-            if (j == 6) b[i] = value; else A[j * 6 + i] = A[i * 6 + j] = value;
-        }
-    const double det = det6_dev(A);
-    if (fabs(det) < 1e-15 || det != det) { *ok = 0; return; }
+    {
+        int shift = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = i; j < 7; ++j) {
+                const double value = (double)(float)sums[shift++];      // the reference's buffer is float
+                if (j == 6) b[i] = value; else A[j * 6 + i] = A[i * 6 + j] = value;
+            }
+    }
     double r[6];
-    if (!chol6_solve(A, b, r)) sym6_solve_dev(A, b, r);
+    double det;
+    if (!chol6_solve(A, b, r, &det)) {                                  // not safely SPD (or NaN): general path
+        det = det6_dev(A);
+        if (fabs(det) < 1e-15 || det != det) { *ok = 0; return; }
+        sym6_solve_dev(A, b, r);
+    } else if (fabs(det) < 1e-15 || det != det) { *ok = 0; return; }     // projective_icp.cpp:197-203
     float rf[6];
     for (int i = 0; i < 6; ++i) rf[i] = (float)r[i];
 

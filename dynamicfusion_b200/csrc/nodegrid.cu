@@ -1,0 +1,106 @@
+// nodegrid.cu -- builds the uniform grid over the warp nodes' vertices (layout: warp_common.cuh, NodeGridHeader).
+// Replaces WarpField::buildKDTree (kfusion/src/warp_field.cpp:275-282, nanoflann index over nodes_).  Built once per node
+// set (node vertices are immutable after WarpField::init); one 1024-thread block, deterministic output: nodes are stored
+// cell by cell and, inside a cell, in ascending node index.
+#include "warp_common.cuh"
+
+using namespace dfb;
+
+namespace {
+
+__global__ void __launch_bounds__(1024) build_node_grid_kernel(const float *__restrict__ nodes, int M, void *grid, int *cid_tmp)
+{
+    __shared__ float smin[3][32], smax[3][32];
+    __shared__ NodeGridHeader h;
+    __shared__ int partial[1024];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+
+    // 1. bounding box of the vertices
+    float mn[3] = {3.4e38f, 3.4e38f, 3.4e38f}, mx[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+    for (int i = t; i < M; i += 1024)
+        for (int c = 0; c < 3; ++c) { const float v = nodes[(size_t)i * DF_NODE_STRIDE + c]; mn[c] = fminf(mn[c], v); mx[c] = fmaxf(mx[c], v); }
+    for (int c = 0; c < 3; ++c) {
+        for (int o = 16; o > 0; o >>= 1) { mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o)); mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o)); }
+        if (lane == 0) { smin[c][warp] = mn[c]; smax[c][warp] = mx[c]; }
+    }
+    __syncthreads();
+    if (t == 0) {
+        float lo[3], hi[3];
+        for (int c = 0; c < 3; ++c) {
+            lo[c] = smin[c][0]; hi[c] = smax[c][0];
+            for (int w = 1; w < 32; ++w) { lo[c] = fminf(lo[c], smin[c][w]); hi[c] = fmaxf(hi[c], smax[c][w]); }
+        }
+        const float ext = fmaxf(fmaxf(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
+        // nodes sample a surface: ~sqrt(M) nodes along the longest extent; aim at ~2 node spacings per cell
+        int res = (int)ceilf(sqrtf((float)M) / 1.5f);
+        res = max(1, min(res, NODEGRID_MAX_RES));
+        const float cell = ext > 0.f ? ext / (float)res * 1.0001f : 1.f;
+        h.ox = lo[0]; h.oy = lo[1]; h.oz = lo[2]; h.cell = cell; h.inv_cell = 1.f / cell;
+        h.gx = min(NODEGRID_MAX_RES, (int)((hi[0] - lo[0]) * h.inv_cell) + 1);
+        h.gy = min(NODEGRID_MAX_RES, (int)((hi[1] - lo[1]) * h.inv_cell) + 1);
+        h.gz = min(NODEGRID_MAX_RES, (int)((hi[2] - lo[2]) * h.inv_cell) + 1);
+        h.M = M; h.ncell = h.gx * h.gy * h.gz;
+        for (int i = 0; i < 6; ++i) h.pad[i] = 0;
+        *reinterpret_cast<NodeGridHeader *>(grid) = h;
+    }
+    __syncthreads();
+    int *cell_start = reinterpret_cast<int *>(reinterpret_cast<char *>(grid) + 64);
+    float4 *sorted = reinterpret_cast<float4 *>(reinterpret_cast<char *>(grid) + 64 + (((size_t)(h.ncell + 1) * 4 + 15) & ~(size_t)15));
+
+    // 2. cell of every node, per-cell counts
+    for (int i = t; i <= h.ncell; i += 1024) cell_start[i] = 0;
+    __syncthreads();
+    for (int i = t; i < M; i += 1024) {
+        const float *v = nodes + (size_t)i * DF_NODE_STRIDE;
+        const int cx = min(max((int)floorf((v[0] - h.ox) * h.inv_cell), 0), h.gx - 1);
+        const int cy = min(max((int)floorf((v[1] - h.oy) * h.inv_cell), 0), h.gy - 1);
+        const int cz = min(max((int)floorf((v[2] - h.oz) * h.inv_cell), 0), h.gz - 1);
+        const int cid = cx + h.gx * (cy + h.gy * cz);
+        cid_tmp[i] = cid;
+        atomicAdd(cell_start + cid + 1, 1);         // counts shifted by one: the inclusive scan below yields the starts
+    }
+    __syncthreads();
+    // 3. inclusive scan of cell_start[1..ncell] (chunked per thread + block scan of chunk sums)
+    const int n = h.ncell;
+    const int per = (n + 1023) / 1024;
+    const int b = min(n, t * per) + 1, e = min(n, t * per + per) + 1;
+    int s = 0;
+    for (int i = b; i < e; ++i) s += cell_start[i];
+    partial[t] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int v = t >= o ? partial[t - o] : 0;
+        __syncthreads();
+        partial[t] += v;
+        __syncthreads();
+    }
+    int run = partial[t] - s;
+    for (int i = b; i < e; ++i) { run += cell_start[i]; cell_start[i] = run; }
+    __syncthreads();
+    // 4. deterministic placement: rank inside the cell = number of lower-indexed nodes in the same cell
+    for (int i = t; i < M; i += 1024) {
+        const int cid = cid_tmp[i];
+        int rank = 0;
+        for (int j = 0; j < i; ++j) rank += (cid_tmp[j] == cid);
+        const float *v = nodes + (size_t)i * DF_NODE_STRIDE;
+        sorted[cell_start[cid] + rank] = make_float4(v[0], v[1], v[2], __int_as_float(i));
+    }
+}
+
+}  // namespace
+
+extern "C" size_t df_node_grid_bytes(int M)
+{
+    const size_t ncell = (size_t)NODEGRID_MAX_RES * NODEGRID_MAX_RES * NODEGRID_MAX_RES;
+    return 64 + (((ncell + 1) * 4 + 15) & ~(size_t)15) + (size_t)(M > 0 ? M : 1) * 16 + (size_t)(M > 0 ? M : 1) * 4 + 256;
+}
+
+extern "C" int df_build_node_grid(const float *nodes, int M, void *grid, void *stream)
+{
+    if (M <= 0) return (int)cudaErrorInvalidValue;
+    // scratch for the per-node cell ids lives at the very end of the buffer
+    int *cid_tmp = reinterpret_cast<int *>(reinterpret_cast<char *>(grid) + df_node_grid_bytes(M) - (size_t)M * 4 - 128);
+    build_node_grid_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(nodes, M, grid, cid_tmp);
+    DF_LAUNCH_CHECK();
+    return 0;
+}

@@ -31,7 +31,7 @@ struct KinFu {
     Img cur_depth[MAX_LEVELS], cur_pts[MAX_LEVELS], cur_nrm[MAX_LEVELS], prev_pts[MAX_LEVELS], prev_nrm[MAX_LEVELS];
     Img canon, canon_nrm, canon_visible;
     float *cloud = nullptr, *cloud_nrm = nullptr; int *cloud_count = nullptr;
-    float *nodes = nullptr; int M = 0;
+    float *nodes = nullptr; int M = 0; void *node_grid = nullptr;
     float *icp_T = nullptr; int *icp_ok = nullptr; double *icp_scratch = nullptr;
     void *solve_ws = nullptr; size_t solve_ws_bytes = 0; double *solve_stats = nullptr;
     void *extract_ws = nullptr; void *project_ws = nullptr;
@@ -196,7 +196,11 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch)
             int M = (count + step - 1) / step;
             if (p.max_nodes > 0 && M > p.max_nodes) { step = (count + p.max_nodes - 1) / p.max_nodes; M = (count + step - 1) / step; }
             k.M = M;
-            if (M > 0) { init_nodes_kernel<<<div_up(M, 256), 256, 0, s>>>((const float4 *)k.cloud, step, M, k.nodes); ++k.launches; }
+            if (M > 0) {
+                init_nodes_kernel<<<div_up(M, 256), 256, 0, s>>>((const float4 *)k.cloud, step, M, k.nodes);
+                CKD(df_build_node_grid(k.nodes, M, k.node_grid, s));       // buildKDTree(), warp_field.cpp:61
+                k.launches += 2;
+            }
         }
         for (int i = 0; i < MAX_LEVELS; ++i) { std::swap(k.cur_pts[i], k.prev_pts[i]); std::swap(k.cur_nrm[i], k.prev_nrm[i]); }
         ++k.frame_counter;
@@ -243,15 +247,21 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch)
         ++k.launches;
         mark(k, 3);
         df_aff3f ident; float id12[12]; dfh_aff_identity(id12); ident = to_aff(id12);    // warp_to_live_ stays identity (never set)
-        CKD(df_warp(k.nodes, k.M, (float *)k.canon.ptr, (float *)k.canon_nrm.ptr, npix, 4, ident, 0, nullptr, nullptr, s));   // :385
+        CKD(df_warp(k.nodes, k.M, k.node_grid, (float *)k.canon.ptr, (float *)k.canon_nrm.ptr, npix, 4, ident, 0, nullptr, nullptr, s));   // :385
         ++k.launches;
         mark(k, 4);
-        CKD(df_solve_data_term(k.nodes, k.M, (const float *)k.canon.ptr, (const float *)k.cur_pts[0].ptr, npix, 4,
+        CKD(df_solve_data_term(k.nodes, k.M, k.node_grid, (const float *)k.canon.ptr, (const float *)k.cur_pts[0].ptr, npix, 4,
                                p.solver_nonlinear_iters, p.solver_linear_iters,
                                (p.flags & DF_KINFU_REF_GRAPH_QUIRK) ? DF_SOLVE_REF_GRAPH_QUIRK : 0, k.solve_stats, k.solve_ws, s));   // :387
         k.launches += 6;
         mark(k, 5);
-        CKD(df_warp(k.nodes, k.M, (float *)k.canon.ptr, (float *)k.canon_nrm.ptr, npix, 4, ident, 0, nullptr, nullptr, s));   // :389
+        {
+            // second warp (:389) queries exactly the vertices the solve just built its graph for (CombinedSolver.h:66-84):
+            // re-use those neighbours + weights instead of a third k-NN pass
+            int32_t *knn_idx; float *knn_w;
+            CKD(df_solve_knn_buffers(k.solve_ws, k.M, npix, &knn_idx, &knn_w));
+            CKD(df_warp(k.nodes, k.M, k.node_grid, (float *)k.canon.ptr, (float *)k.canon_nrm.ptr, npix, 4, ident, DF_WARP_REUSE_KNN, knn_idx, knn_w, s));
+        }
         ++k.launches;
         mark(k, 6);
         // surface_fusion (tsdf_volume.cpp:228-255): psdf projects the warped vertices into the (bilateral-filtered) depth,
@@ -345,7 +355,7 @@ extern "C" void *df_kinfu_create(const df_kinfu_params *pp)
     ok = ok && cudaMalloc(&k->cloud, (size_t)p.cloud_capacity * 16) == cudaSuccess && cudaMalloc(&k->cloud_nrm, (size_t)p.cloud_capacity * 16) == cudaSuccess;
     ok = ok && cudaMalloc(&k->cloud_count, 64) == cudaSuccess;
     const int maxM = p.max_nodes > 0 ? p.max_nodes : (p.cloud_capacity + 49) / 50;
-    ok = ok && cudaMalloc(&k->nodes, (size_t)maxM * DF_NODE_STRIDE * 4) == cudaSuccess;
+    ok = ok && cudaMalloc(&k->nodes, (size_t)maxM * DF_NODE_STRIDE * 4) == cudaSuccess && cudaMalloc(&k->node_grid, df_node_grid_bytes(maxM)) == cudaSuccess;
     ok = ok && cudaMalloc(&k->icp_T, 64) == cudaSuccess && cudaMalloc(&k->icp_ok, 64) == cudaSuccess &&
          cudaMalloc(&k->icp_scratch, (size_t)DF_ICP_SCRATCH_DOUBLES * 8) == cudaSuccess;
     k->solve_ws_bytes = df_solve_workspace_bytes(maxM, p.cols * p.rows);
@@ -372,7 +382,7 @@ extern "C" void df_kinfu_destroy(void *h)
     cudaFree(k->volume); cudaFree(k->depth_in.ptr); cudaFree(k->dists.ptr);
     for (int l = 0; l < MAX_LEVELS; ++l) { cudaFree(k->cur_depth[l].ptr); cudaFree(k->cur_pts[l].ptr); cudaFree(k->cur_nrm[l].ptr); cudaFree(k->prev_pts[l].ptr); cudaFree(k->prev_nrm[l].ptr); }
     cudaFree(k->canon.ptr); cudaFree(k->canon_nrm.ptr); cudaFree(k->canon_visible.ptr);
-    cudaFree(k->cloud); cudaFree(k->cloud_nrm); cudaFree(k->cloud_count); cudaFree(k->nodes);
+    cudaFree(k->cloud); cudaFree(k->cloud_nrm); cudaFree(k->cloud_count); cudaFree(k->nodes); cudaFree(k->node_grid);
     cudaFree(k->icp_T); cudaFree(k->icp_ok); cudaFree(k->icp_scratch); cudaFree(k->solve_ws); cudaFree(k->solve_stats);
     cudaFree(k->extract_ws); cudaFree(k->project_ws); cudaFreeHost(k->pinned); cudaFree(k->n_upd);
     for (int e = 0; e <= NSTAGES; ++e) cudaEventDestroy(k->ev[e]);
@@ -472,6 +482,19 @@ extern "C" int df_kinfu_get_buffer(void *h, int which, void **ptr, size_t *pitch
     }
     *ptr = im.ptr; *pitch = im.pitch; *cols = im.cols; *rows = im.rows;
     return 0;
+}
+
+extern "C" int df_kinfu_read_buffer(void *h, int which, void *dst_host, size_t bytes)
+{
+    KinFu *k = (KinFu *)h;
+    void *ptr; size_t pitch; int cols, rows;
+    const int st = df_kinfu_get_buffer(h, which, &ptr, &pitch, &cols, &rows);
+    if (st) return st;
+    const size_t have = pitch * (size_t)rows;
+    cudaError_t e = cudaStreamSynchronize(k->stream);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemcpy(dst_host, ptr, bytes < have ? bytes : have, cudaMemcpyDeviceToHost);
+    return (int)e;
 }
 
 extern "C" int df_kinfu_get_stage_ms(void *h, float *ms, int n)

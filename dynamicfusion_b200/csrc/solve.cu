@@ -18,6 +18,10 @@
 //                      writes the translations back into the nodes (encodeTranslation).  No host round trip.
 // Sums over vertices are accumulated in double, so the atomics' ordering does not change the rounded result.
 #include "warp_common.cuh"
+#include <cooperative_groups.h>
+#include <cstdlib>
+
+namespace cg = cooperative_groups;
 
 using namespace dfb;
 
@@ -32,6 +36,7 @@ struct SolveWs {
     int *cnt, *off, *cursor, *inc;                 // incidence CSR
     int *rownnz; int *col; double *val;            // ELL (column-major): col[e * M + i]
     double *gb, *diag;                             // [3*M], [M]
+    double *cd, *minv;                             // [M], [M]
     double *c0_partials;                           // per prepare-block 0.5*sum|b|^2 and valid count
     double *vec;                                   // 7 vectors of 3*M doubles
     int *flags;                                    // [0] overflow
@@ -56,6 +61,8 @@ size_t layout(SolveWs &ws, char *base, int M, int N)
     ws.val = (double *)take((size_t)M * ROWCAP * 8);
     ws.gb = (double *)take((size_t)M * 3 * 8);
     ws.diag = (double *)take((size_t)M * 8);
+    ws.cd = (double *)take((size_t)M * 8);
+    ws.minv = (double *)take((size_t)M * 8);
     ws.prepare_blocks = (N + 255) / 256;
     ws.c0_partials = (double *)take((size_t)ws.prepare_blocks * 2 * 8);
     ws.vec = (double *)take((size_t)M * 3 * 8 * 7);
@@ -64,21 +71,24 @@ size_t layout(SolveWs &ws, char *base, int M, int N)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) solve_prepare_kernel(const float *__restrict__ nodes, int M, const float *__restrict__ canon,
-                                                            const float *__restrict__ live, int N, int stride, SolveWs ws)
+__global__ void __launch_bounds__(256) solve_prepare_kernel(const float *__restrict__ nodes, int M, const void *__restrict__ grid,
+                                                            const float *__restrict__ canon, const float *__restrict__ live, int N, int stride,
+                                                            SolveWs ws)
 {
     __shared__ KnnSmem sm;
     __shared__ double red[2][8];
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     float3 c = make_float3(0.f, 0.f, 0.f), l = c;
-    bool valid = false;
+    bool valid = false, valid_c = false;       // valid_c: the vertex can be queried; valid: the row enters the solve
     if (v < N) {
         const float *cp = canon + (size_t)v * stride, *lp = live + (size_t)v * stride;
         c = make_float3(cp[0], cp[1], cp[2]); l = make_float3(lp[0], lp[1], lp[2]);
-        valid = !(isnan(c.x) || isnan(c.y) || isnan(c.z) || isnan(l.x) || isnan(l.y) || isnan(l.z));
+        valid_c = !(isnan(c.x) || isnan(c.y) || isnan(c.z));
+        valid = valid_c && !(isnan(l.x) || isnan(l.y) || isnan(l.z));
     }
     int bi[8]; float bd[8];
-    knn8_scan(nodes, M, valid, c.x, c.y, c.z, sm, bi, bd);
+    if (grid) knn8_grid(grid, valid_c, c.x, c.y, c.z, bi, bd);
+    else knn8_scan(nodes, M, valid_c, c.x, c.y, c.z, sm, bi, bd);
     double half_b2 = 0.0;
     if (v < N) {
         float3 b = make_float3(0.f, 0.f, 0.f);
@@ -87,10 +97,13 @@ __global__ void __launch_bounds__(256) solve_prepare_kernel(const float *__restr
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const int n = (v < N && valid) ? bi[k] : -1;
+        // idx / w describe the vertex itself (re-used by the following warp, DF_WARP_REUSE_KNN); only rows that are valid
+        // for the solve are counted into the incidence lists
+        const int nq = (v < N && valid_c) ? bi[k] : -1;
         float wk = 0.f;
-        if (n >= 0) wk = node_weighting(bd[k], __ldg(nodes + (size_t)n * DF_NODE_STRIDE + 11));
-        if (v < N) { ws.idx[(size_t)v * 8 + k] = n; ws.w[(size_t)v * 8 + k] = wk; }
+        if (nq >= 0) wk = node_weighting(bd[k], __ldg(nodes + (size_t)nq * DF_NODE_STRIDE + 11));
+        if (v < N) { ws.idx[(size_t)v * 8 + k] = nq; ws.w[(size_t)v * 8 + k] = wk; }
+        const int n = valid ? nq : -1;
         // warp-aggregated incidence count: neighbouring pixels share nodes, one atomic per distinct node per warp
         const unsigned grp = __match_any_sync(0xffffffffu, n);
         if (n >= 0 && (int)(__ffs(grp) - 1) == (int)(threadIdx.x & 31)) atomicAdd(ws.cnt + n, __popc(grp));
@@ -134,7 +147,7 @@ __global__ void __launch_bounds__(256) solve_fill_kernel(SolveWs ws, int N)
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const int n = v < N ? ws.idx[(size_t)v * 8 + k] : -1;
+        const int n = (v < N && ws.b[v].w != 0.f) ? ws.idx[(size_t)v * 8 + k] : -1;
         const unsigned grp = __match_any_sync(0xffffffffu, n);
         if (n < 0) continue;
         const int lane = threadIdx.x & 31;
@@ -378,6 +391,263 @@ __global__ void __launch_bounds__(LM_THREADS) solve_lm_kernel(float *nodes, int 
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// LM / PCG on ONE THREAD-BLOCK CLUSTER (8 CTAs x 1024 threads on 8 SMs).  The linear system is tiny (M x M sparse,
+// ~2e5 non-zeros, L2-resident) and every PCG iteration needs two global dot products, so the iteration is bound by
+// barrier + reduction latency, not by bandwidth.  A whole-grid cooperative barrier costs microseconds; the cluster's
+// hardware barrier costs a few hundred cycles and the partial sums are exchanged through distributed shared memory,
+// so a PCG iteration is ~3 cluster barriers + one sparse mat-vec spread over 8192 threads (several threads per row,
+// combined with warp shuffles).  All sums are formed in a fixed order => every CTA sees bit-identical scalars and takes
+// the same branches; the result is deterministic for a given normal matrix.
+constexpr int LMC_CTAS = 8;
+
+struct ClusterRed {
+    double part[2][4];       // this CTA's partial sums, double-buffered by reduction parity
+    double warp[32][4];
+    double bcast[4];
+};
+
+template <int NV>
+__device__ __forceinline__ void cluster_sum(cg::cluster_group &cluster, ClusterRed &sm, int &parity, double (&v)[NV])
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) sm.warp[warp][k] = v[k];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double t = sm.warp[lane][k];                       // blockDim.x == 1024 -> 32 warps
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (lane == 0) sm.part[parity][k] = t;
+        }
+    }
+    cluster.sync();                                            // partials of all CTAs visible (release/acquire, cluster scope)
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double t = 0.0;
+            if (lane < LMC_CTAS) {
+                const double *remote = cluster.map_shared_rank(&sm.part[parity][k], lane);
+                t = *remote;
+            }
+            for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);   // lanes 0..7, fixed tree
+            if (lane == 0) sm.bcast[k] = t;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = sm.bcast[k];
+    parity ^= 1;
+    __syncthreads();
+}
+
+__global__ void __cluster_dims__(LMC_CTAS, 1, 1) __launch_bounds__(LM_THREADS)
+solve_lm_cluster_kernel(float *nodes, int M, SolveWs ws, int nl_iters, int lin_iters, double *stats, int use_smem)
+{
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ ClusterRed sm;
+    int parity = 0;
+    const int T = LMC_CTAS * LM_THREADS;
+    const int gt = (int)cluster.block_rank() * LM_THREADS + threadIdx.x;
+    int tpr = 1;                                               // threads per row: power of two, <= 32, tpr * M <= T when possible
+    while (tpr < 32 && tpr * 2 * M <= T) tpr *= 2;
+    const int rpp = T / tpr;                                   // rows per pass
+    const int row0 = gt / tpr, sub = gt % tpr;
+    const bool owner = sub == 0;
+    const int M3 = 3 * M;
+    double *x = ws.vec, *g = x + M3, *dl = g + M3, *r = dl + M3, *z = r + M3, *p = z + M3, *Ap = p + M3;
+    double *cd = ws.cd, *minv = ws.minv;                       // per-LM-iteration damping and Jacobi preconditioner
+
+    // sparse mat-vec for this thread's rows: out (owner lanes) = A * in.  `in` was written by other SMs: every CTA first
+    // stages the whole vector (3M doubles, 49 KB at M = 2k) from L2 into its shared memory with coalesced loads, so the
+    // per-entry gathers cost a shared-memory access instead of an L2 round trip each.
+    extern __shared__ double svec[];
+    auto spmv = [&](const double *in, double *out) {
+        const double *src = in;
+        if (use_smem) {
+            for (int i = threadIdx.x; i < M3; i += LM_THREADS) svec[i] = __ldcg(in + i);
+            __syncthreads();
+            src = svec;
+        }
+        for (int base = 0; base < M; base += rpp) {           // uniform trip count: the shuffles below need the whole warp
+            const int n = base + row0;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+            const int nnz = n < M ? ws.rownnz[n] : 0;
+            int e = sub;
+            for (; e + 3 * tpr < nnz; e += 4 * tpr) {          // 4 independent entries in flight
+                const int j0 = __ldg(ws.col + (size_t)e * M + n), j1 = __ldg(ws.col + (size_t)(e + tpr) * M + n);
+                const int j2 = __ldg(ws.col + (size_t)(e + 2 * tpr) * M + n), j3 = __ldg(ws.col + (size_t)(e + 3 * tpr) * M + n);
+                const double v0 = __ldg(ws.val + (size_t)e * M + n), v1 = __ldg(ws.val + (size_t)(e + tpr) * M + n);
+                const double v2 = __ldg(ws.val + (size_t)(e + 2 * tpr) * M + n), v3 = __ldg(ws.val + (size_t)(e + 3 * tpr) * M + n);
+                if (use_smem) {
+                    a0 += v0 * src[j0]; a1 += v0 * src[M + j0]; a2 += v0 * src[2 * M + j0];
+                    a0 += v1 * src[j1]; a1 += v1 * src[M + j1]; a2 += v1 * src[2 * M + j1];
+                    a0 += v2 * src[j2]; a1 += v2 * src[M + j2]; a2 += v2 * src[2 * M + j2];
+                    a0 += v3 * src[j3]; a1 += v3 * src[M + j3]; a2 += v3 * src[2 * M + j3];
+                } else {
+                    a0 += v0 * __ldcg(in + j0); a1 += v0 * __ldcg(in + M + j0); a2 += v0 * __ldcg(in + 2 * M + j0);
+                    a0 += v1 * __ldcg(in + j1); a1 += v1 * __ldcg(in + M + j1); a2 += v1 * __ldcg(in + 2 * M + j1);
+                    a0 += v2 * __ldcg(in + j2); a1 += v2 * __ldcg(in + M + j2); a2 += v2 * __ldcg(in + 2 * M + j2);
+                    a0 += v3 * __ldcg(in + j3); a1 += v3 * __ldcg(in + M + j3); a2 += v3 * __ldcg(in + 2 * M + j3);
+                }
+            }
+            for (; e < nnz; e += tpr) {
+                const int j = __ldg(ws.col + (size_t)e * M + n);
+                const double a = __ldg(ws.val + (size_t)e * M + n);
+                if (use_smem) { a0 += a * src[j]; a1 += a * src[M + j]; a2 += a * src[2 * M + j]; }
+                else { a0 += a * __ldcg(in + j); a1 += a * __ldcg(in + M + j); a2 += a * __ldcg(in + 2 * M + j); }
+            }
+            for (int o = tpr >> 1; o > 0; o >>= 1) {
+                a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+            }
+            if (owner && n < M) { out[n] = a0; out[M + n] = a1; out[2 * M + n] = a2; }
+        }
+    };
+
+    // x0 = current node translations (CombinedSolver.h:165-172)
+    if (owner)
+        for (int n = row0; n < M; n += rpp) {
+            const float4 *n4 = reinterpret_cast<const float4 *>(nodes + (size_t)n * DF_NODE_STRIDE);
+            const float4 a = n4[0], b = n4[1], c = n4[2];
+            const Quat t = dq_translation(Quat{a.w, b.x, b.y, b.z}, Quat{b.w, c.x, c.y, c.z});
+            x[n] = t.x; x[M + n] = t.y; x[2 * M + n] = t.z;
+        }
+    double c0n[2] = {0.0, 0.0};
+    for (int i = gt; i < ws.prepare_blocks; i += T) { c0n[0] += ws.c0_partials[2 * i]; c0n[1] += ws.c0_partials[2 * i + 1]; }
+    cluster_sum(cluster, sm, parity, c0n);                     // also publishes x
+    const double nvalid = c0n[1];
+    spmv(x, Ap);
+    double t0[1] = {0.0};
+    if (owner)
+        for (int n = row0; n < M; n += rpp)
+            for (int d = 0; d < 3; ++d) t0[0] += x[d * M + n] * (0.5 * Ap[d * M + n] - ws.gb[d * M + n]);
+    cluster_sum(cluster, sm, parity, t0);
+    double cost = c0n[0] + t0[0];
+    const double cost0 = cost;
+
+    double radius = 1e4, decrease = 2.0;                       // solverGPUGaussNewton.t:26-39
+    int it = 0, pcg_total = 0;
+    for (; it < nl_iters; ++it) {
+        spmv(x, Ap);                                           // x was published by the previous cluster barrier
+        double rzv[1] = {0.0};
+        if (owner)
+            for (int n = row0; n < M; n += rpp) {
+                const double dgn = ws.diag[n];
+                const double cdn = fmin(fmax(dgn, 1e-6), 1e32) / radius;
+                const double mi = 1.0 / (dgn + cdn);
+                cd[n] = cdn; minv[n] = mi;
+                for (int d = 0; d < 3; ++d) {
+                    const int i = d * M + n;
+                    const double gi = ws.gb[i] - Ap[i];
+                    g[i] = gi; dl[i] = 0.0; r[i] = gi;
+                    const double zi = gi * mi;
+                    z[i] = zi; p[i] = zi;
+                    rzv[0] += gi * zi;
+                }
+            }
+        cluster_sum(cluster, sm, parity, rzv);                 // publishes p
+        double rz = rzv[0];
+        double Q0 = 0.0;
+        for (int l = 0; l < lin_iters && rz > 0.0; ++l) {
+            spmv(p, Ap);
+            double pap[1] = {0.0};
+            if (owner)
+                for (int n = row0; n < M; n += rpp)
+                    for (int d = 0; d < 3; ++d) {
+                        const int i = d * M + n;
+                        const double ap = Ap[i] + cd[n] * p[i];
+                        Ap[i] = ap;
+                        pap[0] += p[i] * ap;
+                    }
+            cluster_sum(cluster, sm, parity, pap);
+            if (!(pap[0] > 0.0)) break;
+            const double alpha = rz / pap[0];
+            double rq[2] = {0.0, 0.0};
+            if (owner)
+                for (int n = row0; n < M; n += rpp)
+                    for (int d = 0; d < 3; ++d) {
+                        const int i = d * M + n;
+                        const double dli = dl[i] + alpha * p[i];
+                        const double ri = r[i] - alpha * Ap[i];
+                        const double zi = ri * minv[n];
+                        dl[i] = dli; r[i] = ri; z[i] = zi;
+                        rq[0] += ri * zi;
+                        rq[1] += dli * (ri + g[i]);
+                    }
+            cluster_sum(cluster, sm, parity, rq);
+            const double rz_new = rq[0], Q1 = -0.5 * rq[1];
+            const double beta = rz_new / rz;
+            if (owner)
+                for (int n = row0; n < M; n += rpp)
+                    for (int d = 0; d < 3; ++d) { const int i = d * M + n; p[i] = z[i] + beta * p[i]; }
+            rz = rz_new;
+            ++pcg_total;
+            const double zeta = (double)(l + 1) * (Q1 - Q0) / Q1;   // Ceres/Opt q-tolerance, solverGPUGaussNewton.t:1093-1101
+            Q0 = Q1;
+            cluster.sync();                                    // publish p for the next mat-vec
+            if (zeta < 1e-4) break;
+        }
+        // model change = 0.5 dl.(g + r + C dl);  A dl = g - r - C dl  => new cost = cost - dl.g + 0.5 dl.(A dl)
+        double mad[3] = {0.0, 0.0, 0.0};
+        if (owner)
+            for (int n = row0; n < M; n += rpp)
+                for (int d = 0; d < 3; ++d) {
+                    const int i = d * M + n;
+                    const double c = cd[n] * dl[i];
+                    mad[0] += dl[i] * (g[i] + r[i] + c);
+                    mad[1] += dl[i] * (g[i] - r[i] - c);
+                    mad[2] += dl[i] * g[i];
+                }
+        cluster_sum(cluster, sm, parity, mad);
+        const double model = 0.5 * mad[0];
+        const double new_cost = cost - mad[2] + 0.5 * mad[1];
+        const double change = cost - new_cost;
+        const double rho = model > 0.0 ? change / model : 0.0;
+        bool stop = false;
+        if (change >= 0.0 && rho > 1e-3) {
+            if (owner)
+                for (int n = row0; n < M; n += rpp)
+                    for (int d = 0; d < 3; ++d) x[d * M + n] += dl[d * M + n];
+            stop = change <= cost * 1e-6;                       // function_tolerance, CombinedSolver.h:88
+            cost = new_cost;
+            const double f = 1.0 - (2.0 * rho - 1.0) * (2.0 * rho - 1.0) * (2.0 * rho - 1.0);
+            radius /= fmax(f, 1.0 / 3.0);
+            radius = fmin(radius, 1e16);
+            decrease = 2.0;
+        } else {
+            radius /= decrease; decrease *= 2.0;
+            if (radius <= 1e-32) stop = true;
+        }
+        cluster.sync();                                        // publish x
+        if (stop) { ++it; break; }
+    }
+    // write back: encodeTranslation (CombinedSolver.h:189-197, dual_quaternion.hpp:82-85)
+    if (owner)
+        for (int n = row0; n < M; n += rpp) {
+            float *nd = nodes + (size_t)n * DF_NODE_STRIDE;
+            const Quat rot = {nd[3], nd[4], nd[5], nd[6]};
+            const Quat h = qhalf(Quat{0.f, (float)x[n], (float)x[M + n], (float)x[2 * M + n]});
+            const Quat d = qmul(h, rot);
+            nd[7] = d.w; nd[8] = d.x; nd[9] = d.y; nd[10] = d.z;
+        }
+    if (gt == 0 && stats) {
+        stats[0] = cost0; stats[1] = cost; stats[2] = (double)it; stats[3] = nvalid; stats[4] = (double)pcg_total; stats[5] = (double)ws.flags[0];
+    }
+}
+
+int solve_lm_impl()
+{
+    static int impl = -1;
+    if (impl < 0) { const char *e = getenv("DF_SOLVE_LM_IMPL"); impl = e ? atoi(e) : 2; }
+    return impl;
+}
+
 }  // namespace
 
 extern "C" size_t df_solve_workspace_bytes(int M, int N)
@@ -386,7 +656,16 @@ extern "C" size_t df_solve_workspace_bytes(int M, int N)
     return layout(ws, nullptr, M, N) + 256;
 }
 
-extern "C" int df_solve_data_term(float *nodes, int M, const float *canon, const float *live, int N, int stride,
+extern "C" int df_solve_knn_buffers(void *workspace, int M, int N, int32_t **idx, float **w)
+{
+    SolveWs ws;
+    char *base = (char *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    layout(ws, base, M, N);
+    *idx = ws.idx; *w = ws.w;
+    return 0;
+}
+
+extern "C" int df_solve_data_term(float *nodes, int M, const void *node_grid, const float *canon, const float *live, int N, int stride,
                                   int nonlinear_iters, int linear_iters, int flags, double *stats_dev, void *workspace, void *stream)
 {
     if (M <= 0 || N <= 0) return 0;
@@ -396,7 +675,7 @@ extern "C" int df_solve_data_term(float *nodes, int M, const float *canon, const
     layout(ws, base, M, N);
     cudaError_t e = cudaMemsetAsync(ws.cnt, 0, (size_t)(M + 1) * 4, s);
     if (e != cudaSuccess) return (int)e;
-    solve_prepare_kernel<<<ws.prepare_blocks, 256, 0, s>>>(nodes, M, canon, live, N, stride, ws);
+    solve_prepare_kernel<<<ws.prepare_blocks, 256, 0, s>>>(nodes, M, node_grid, canon, live, N, stride, ws);
     DF_LAUNCH_CHECK();
     solve_scan_kernel<<<1, 1024, 0, s>>>(ws, M);
     DF_LAUNCH_CHECK();
@@ -404,7 +683,17 @@ extern "C" int df_solve_data_term(float *nodes, int M, const float *canon, const
     DF_LAUNCH_CHECK();
     solve_rows_kernel<<<M, 256, 0, s>>>(ws, M, N, flags & DF_SOLVE_REF_GRAPH_QUIRK);
     DF_LAUNCH_CHECK();
-    solve_lm_kernel<<<1, LM_THREADS, 0, s>>>(nodes, M, ws, nonlinear_iters, linear_iters, stats_dev);
+    if (solve_lm_impl() == 1) solve_lm_kernel<<<1, LM_THREADS, 0, s>>>(nodes, M, ws, nonlinear_iters, linear_iters, stats_dev);
+    else {
+        const size_t vec_bytes = (size_t)3 * M * sizeof(double);
+        const int use_smem = vec_bytes <= 200 * 1024;
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(solve_lm_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            attr_set = true;
+        }
+        solve_lm_cluster_kernel<<<LMC_CTAS, LM_THREADS, use_smem ? vec_bytes : 0, s>>>(nodes, M, ws, nonlinear_iters, linear_iters, stats_dev, use_smem);
+    }
     DF_LAUNCH_CHECK();
     return 0;
 }

@@ -9,7 +9,8 @@ using namespace dfb;
 
 namespace {
 
-__global__ void __launch_bounds__(256) knn8_kernel(const float *__restrict__ nodes, int M, const float *__restrict__ queries, int N,
+__global__ void __launch_bounds__(256) knn8_kernel(const float *__restrict__ nodes, int M, const void *__restrict__ grid,
+                                                   const float *__restrict__ queries, int N,
                                                    int qstride, int *__restrict__ idx, float *__restrict__ d2)
 {
     __shared__ KnnSmem sm;
@@ -22,7 +23,8 @@ __global__ void __launch_bounds__(256) knn8_kernel(const float *__restrict__ nod
         valid = !(isnan(qx) || isnan(qy) || isnan(qz));
     }
     int bi[8]; float bd[8];
-    knn8_scan(nodes, M, valid, qx, qy, qz, sm, bi, bd);
+    if (grid) knn8_grid(grid, valid, qx, qy, qz, bi, bd);
+    else knn8_scan(nodes, M, valid, qx, qy, qz, sm, bi, bd);
     if (q < N) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) { idx[(size_t)q * 8 + i] = bi[i]; d2[(size_t)q * 8 + i] = bd[i]; }
@@ -30,13 +32,11 @@ __global__ void __launch_bounds__(256) knn8_kernel(const float *__restrict__ nod
 }
 
 struct WarpParams {
-    const float *nodes; int M;
+    const float *nodes; int M; const void *grid;
     float *points; float *normals; int N; int stride;
     Aff w2l;
     int flags;
-    int *idx_out; float *w_out;
-    const int *rank;          // REF_NORMAL_INDEX mode: rank of each point among coordinate-valid points
-    const int *first_nan;     // REF_NORMAL_INDEX mode: first normal index whose x is NaN (or N)
+    int *idx; float *w;       // neighbours / weights: outputs, or inputs when DF_WARP_REUSE_KNN
 };
 
 // cv::Affine3f * Vec3f (opencv2/core/affine.hpp): m0*x + m1*y + m2*z + m3 evaluated left to right
@@ -47,36 +47,44 @@ __device__ __forceinline__ float3 aff_apply_cv(const Aff &a, const float3 v)
                        a.r2.x * v.x + a.r2.y * v.y + a.r2.z * v.z + a.t.z);
 }
 
-// WarpField::warp, warp_field.cpp:180-195
+// WarpField::warp, warp_field.cpp:180-195.  kReuse: neighbours and weights of these very points were computed by an
+// earlier pass (the data-term solve queries the same warped vertices, CombinedSolver.h:66-84) and are read back instead
+// of being searched again.
+template <bool kReuse>
 __global__ void __launch_bounds__(256) warp_kernel(const WarpParams p)
 {
     __shared__ KnnSmem sm;
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     float3 pt = make_float3(0.f, 0.f, 0.f), nr = pt;
     bool valid = false;
-    int ni = q;
     if (q < p.N) {
         const float *pp = p.points + (size_t)q * p.stride;
         pt = make_float3(pp[0], pp[1], pp[2]);
         valid = !isnan(pt.x);
-        if (p.flags & DF_WARP_REF_NORMAL_INDEX) {
-            // the reference's normal cursor advances only on warped points and stalls for ever at the first NaN normal
-            ni = p.rank[q];
-            valid = valid && ni < *p.first_nan;
-        }
         if (valid) {
-            const float *np = p.normals + (size_t)ni * p.stride;
+            const float *np = p.normals + (size_t)q * p.stride;
             nr = make_float3(np[0], np[1], np[2]);
             valid = !isnan(nr.x);
         }
     }
-    int bi[8]; float bd[8];
-    knn8_scan(p.nodes, p.M, valid, pt.x, pt.y, pt.z, sm, bi, bd);
-    if (q >= p.N) return;
-    float w8[8];
+    int bi[8]; float bd[8]; float w8[8];
+    if (kReuse) {
+        if (q >= p.N) return;
+        const int4 ia = *reinterpret_cast<const int4 *>(p.idx + (size_t)q * 8), ib = *reinterpret_cast<const int4 *>(p.idx + (size_t)q * 8 + 4);
+        const float4 wa = *reinterpret_cast<const float4 *>(p.w + (size_t)q * 8), wb = *reinterpret_cast<const float4 *>(p.w + (size_t)q * 8 + 4);
+        bi[0] = ia.x; bi[1] = ia.y; bi[2] = ia.z; bi[3] = ia.w; bi[4] = ib.x; bi[5] = ib.y; bi[6] = ib.z; bi[7] = ib.w;
+        w8[0] = wa.x; w8[1] = wa.y; w8[2] = wa.z; w8[3] = wa.w; w8[4] = wb.x; w8[5] = wb.y; w8[6] = wb.z; w8[7] = wb.w;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) bd[i] = 0.f;
+        valid = valid && bi[0] >= 0;          // rows the earlier pass skipped (NaN) carry idx = -1
+    } else {
+        if (p.grid) knn8_grid(p.grid, valid, pt.x, pt.y, pt.z, bi, bd);
+        else knn8_scan(p.nodes, p.M, valid, pt.x, pt.y, pt.z, sm, bi, bd);
+        if (q >= p.N) return;
+    }
     if (valid) {
-        const Dqb d = dqb_blend(p.nodes, bi, bd, w8);
-        float3 wp = aff_apply_cv(p.w2l, dq_transform(d, pt));
+        const Dqb d = dqb_blend<kReuse>(p.nodes, bi, bd, w8);
+        const float3 wp = aff_apply_cv(p.w2l, dq_transform(d, pt));
         float3 wn;
         if (p.flags & DF_WARP_NORMAL_ROTATE_ONLY) {
             const float3 r = qrotate(d.rot, nr);
@@ -88,38 +96,40 @@ __global__ void __launch_bounds__(256) warp_kernel(const WarpParams p)
         }
         float *pp = p.points + (size_t)q * p.stride;
         pp[0] = wp.x; pp[1] = wp.y; pp[2] = wp.z;
-        float *np = p.normals + (size_t)ni * p.stride;
+        float *np = p.normals + (size_t)q * p.stride;
         np[0] = wn.x; np[1] = wn.y; np[2] = wn.z;
-    } else {
+    } else if (!kReuse) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) w8[i] = 0.f;
     }
-    if (p.idx_out) {
+    if (!kReuse && p.idx) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { p.idx_out[(size_t)q * 8 + i] = bi[i]; p.w_out[(size_t)q * 8 + i] = w8[i]; }
+        for (int i = 0; i < 8; ++i) { p.idx[(size_t)q * 8 + i] = bi[i]; p.w[(size_t)q * 8 + i] = w8[i]; }
     }
 }
 
 }  // namespace
 
-extern "C" int df_knn8(const float *nodes, int M, const float *queries, int N, int qstride, int32_t *idx, float *d2, void *stream)
+extern "C" int df_knn8(const float *nodes, int M, const void *node_grid, const float *queries, int N, int qstride, int32_t *idx, float *d2,
+                       void *stream)
 {
     if (N <= 0) return 0;
-    knn8_kernel<<<div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(nodes, M, queries, N, qstride, idx, d2);
+    knn8_kernel<<<div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(nodes, M, node_grid, queries, N, qstride, idx, d2);
     DF_LAUNCH_CHECK();
     return 0;
 }
 
-extern "C" int df_warp(const float *nodes, int M, float *points, float *normals, int N, int stride, df_aff3f warp_to_live, int flags,
-                       int32_t *idx_out, float *w_out, void *stream)
+extern "C" int df_warp(const float *nodes, int M, const void *node_grid, float *points, float *normals, int N, int stride,
+                       df_aff3f warp_to_live, int flags, int32_t *idx, float *w, void *stream)
 {
     if (N <= 0) return 0;
     if (flags & DF_WARP_REF_NORMAL_INDEX) return (int)cudaErrorNotSupported;   // reference normal-cursor quirk: not built yet
+    if ((flags & DF_WARP_REUSE_KNN) && (!idx || !w)) return (int)cudaErrorInvalidValue;
     WarpParams p;
-    p.nodes = nodes; p.M = M; p.points = points; p.normals = normals; p.N = N; p.stride = stride;
-    p.w2l = make_aff(warp_to_live); p.flags = flags; p.idx_out = idx_out; p.w_out = w_out;
-    p.rank = nullptr; p.first_nan = nullptr;
-    warp_kernel<<<div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    p.nodes = nodes; p.M = M; p.grid = node_grid; p.points = points; p.normals = normals; p.N = N; p.stride = stride;
+    p.w2l = make_aff(warp_to_live); p.flags = flags; p.idx = idx; p.w = w;
+    if (flags & DF_WARP_REUSE_KNN) warp_kernel<true><<<div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    else warp_kernel<false><<<div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(p);
     DF_LAUNCH_CHECK();
     return 0;
 }

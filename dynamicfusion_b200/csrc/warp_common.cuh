@@ -50,6 +50,79 @@ __device__ __forceinline__ void knn8_scan(const float *__restrict__ nodes, int M
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Uniform node grid: the GPU-resident replacement of the reference's nanoflann kd-tree (warp_field.cpp:17-27,275-282).
+// Node vertices never move after WarpField::init, so the grid is built once (nodegrid.cu) and every query walks cubic
+// shells of cells around its own cell until the 8 best cannot be beaten any more.  Candidates are ranked by
+// (squared distance, node index), so the result is exactly the exhaustive scan's (knn8_scan) whatever the visiting order.
+constexpr int NODEGRID_MAX_RES = 64;
+
+struct NodeGridHeader {
+    float ox, oy, oz, cell, inv_cell;
+    int gx, gy, gz, M, ncell;
+    int pad[6];
+};   // 64 bytes, followed by: int cell_start[ncell + 1] (padded to 16 B), float4 sorted[M] = (x, y, z, index bits)
+
+__device__ __forceinline__ const int *nodegrid_cell_start(const void *grid) { return reinterpret_cast<const int *>(reinterpret_cast<const char *>(grid) + 64); }
+__device__ __forceinline__ const float4 *nodegrid_sorted(const void *grid, int ncell)
+{ return reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(grid) + 64 + (((size_t)(ncell + 1) * 4 + 15) & ~(size_t)15)); }
+
+__device__ __forceinline__ void knn8_insert_lex(int (&bi)[8], float (&bd)[8], float dist, int idx)
+{
+    if (dist < bd[7] || (dist == bd[7] && idx < bi[7])) {
+        bd[7] = dist; bi[7] = idx;
+#pragma unroll
+        for (int k = 7; k > 0; --k) {
+            if (bd[k] < bd[k - 1] || (bd[k] == bd[k - 1] && bi[k] < bi[k - 1])) {
+                const float td = bd[k]; bd[k] = bd[k - 1]; bd[k - 1] = td;
+                const int ti = bi[k]; bi[k] = bi[k - 1]; bi[k - 1] = ti;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void knn8_grid(const void *__restrict__ grid, bool valid, float qx, float qy, float qz, int (&bi)[8], float (&bd)[8])
+{
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { bi[i] = 0x7fffffff; bd[i] = 3.402823466e+38f; }
+    if (valid) {
+        const NodeGridHeader h = *reinterpret_cast<const NodeGridHeader *>(grid);
+        const int *cell_start = nodegrid_cell_start(grid);
+        const float4 *sorted = nodegrid_sorted(grid, h.ncell);
+        const int cx = min(max((int)floorf((qx - h.ox) * h.inv_cell), 0), h.gx - 1);
+        const int cy = min(max((int)floorf((qy - h.oy) * h.inv_cell), 0), h.gy - 1);
+        const int cz = min(max((int)floorf((qz - h.oz) * h.inv_cell), 0), h.gz - 1);
+        const int rmax = max(max(h.gx, h.gy), h.gz);
+        for (int r = 0; r <= rmax; ++r) {
+            // every node in a cell at Chebyshev distance > r from (cx,cy,cz) is at least r*cell away from the query
+            if (r >= 1 && bi[7] != 0x7fffffff) {
+                const float bound = (float)r * h.cell * 0.999f;
+                if (bound * bound > bd[7]) break;
+            }
+            for (int z = cz - r; z <= cz + r; ++z) {
+                if (z < 0 || z >= h.gz) continue;
+                for (int y = cy - r; y <= cy + r; ++y) {
+                    if (y < 0 || y >= h.gy) continue;
+                    const bool shell = (z == cz - r) || (z == cz + r) || (y == cy - r) || (y == cy + r);
+                    const int xstep = shell ? 1 : max(2 * r, 1);
+                    for (int x = cx - r; x <= cx + r; x += xstep) {
+                        if (x < 0 || x >= h.gx) continue;
+                        const int cid = x + h.gx * (y + h.gy * z);
+                        const int b = __ldg(cell_start + cid), e = __ldg(cell_start + cid + 1);
+                        for (int it = b; it < e; ++it) {
+                            const float4 nd = __ldg(sorted + it);
+                            const float d0 = qx - nd.x, d1 = qy - nd.y, d2 = qz - nd.z;
+                            knn8_insert_lex(bi, bd, d0 * d0 + d1 * d1 + d2 * d2, __float_as_int(nd.w));
+                        }
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) if (bi[i] == 0x7fffffff) bi[i] = -1;
+}
+
 struct Quat { float w, x, y, z; };
 
 // Quaternion::operator*, quaternion.hpp:191-199
@@ -101,6 +174,9 @@ __device__ __forceinline__ float node_weighting(float d2, float node_w) { return
 struct Dqb { Quat rot, dual; };
 
 // WarpField::DQB (warp_field.cpp:203-217) from the 8 neighbours; weights8 (optional) receives the node weights
+// kPrecomputedWeights: weights8 holds the weights on entry (re-use of a previous k-NN + weighting pass over the same
+// query points); otherwise they are computed from the squared distances bd and written to weights8.
+template <bool kPrecomputedWeights = false>
 __device__ __forceinline__ Dqb dqb_blend(const float *__restrict__ nodes, const int (&bi)[8], const float (&bd)[8], float *weights8)
 {
     Quat tsum = {0.f, 0.f, 0.f, 0.f}, rsum = {0.f, 0.f, 0.f, 0.f};
@@ -112,12 +188,12 @@ __device__ __forceinline__ Dqb dqb_blend(const float *__restrict__ nodes, const 
             const float4 a = __ldg(n4), b = __ldg(n4 + 1), c = __ldg(n4 + 2);   // (vx,vy,vz,rw) (rx,ry,rz,dw) (dx,dy,dz,weight)
             const Quat rot = {a.w, b.x, b.y, b.z};
             const Quat dual = {b.w, c.x, c.y, c.z};
-            w = node_weighting(bd[i], c.w);
+            w = kPrecomputedWeights ? weights8[i] : node_weighting(bd[i], c.w);
             const Quat t = dq_translation(rot, dual);
             tsum.w = tsum.w + w * t.w; tsum.x = tsum.x + w * t.x; tsum.y = tsum.y + w * t.y; tsum.z = tsum.z + w * t.z;
             rsum.w = rsum.w + w * rot.w; rsum.x = rsum.x + w * rot.x; rsum.y = rsum.y + w * rot.y; rsum.z = rsum.z + w * rot.z;
         }
-        if (weights8) weights8[i] = w;
+        if (!kPrecomputedWeights && weights8) weights8[i] = w;
     }
     Dqb r;
     r.rot = qnormalize(rsum);

@@ -276,12 +276,16 @@ KNN_NEIGHBOURS = 8
 
 
 class WarpField:
-    """kfusion::WarpField (warp_field.hpp:41-88).  Nodes live on the device as [M, 12] float32 (see dfusion.h)."""
+    """kfusion::WarpField (warp_field.hpp:41-88).  Nodes live on the device as [M, 12] float32 (see dfusion.h).
+    `use_grid` selects the uniform node grid (buildKDTree's replacement) or the exhaustive shared-memory scan; both give
+    identical neighbours."""
 
-    def __init__(self, device="cuda"):
+    def __init__(self, device="cuda", use_grid=True):
         self.device = device
         self.nodes_ = torch.zeros((0, NODE_STRIDE), dtype=torch.float32, device=device)
         self.warp_to_live_ = identity_pose()
+        self.use_grid = use_grid
+        self.grid_ = None
         self._ws = None
 
     def init(self, first_frame):
@@ -294,7 +298,22 @@ class WarpField:
         n[:, 3] = 1.0
         n[:, 7] = 1.0
         n[:, 11] = 3.0
-        self.nodes_ = torch.from_numpy(n).to(self.device)
+        self.setNodes(torch.from_numpy(n).to(self.device))
+
+    def setNodes(self, nodes: torch.Tensor):
+        self.nodes_ = nodes
+        self.buildKDTree()
+
+    def buildKDTree(self):
+        """WarpField::buildKDTree (warp_field.cpp:275-282) -> df_build_node_grid"""
+        M = self.nodes_.shape[0]
+        self.grid_ = None
+        if self.use_grid and M > 0:
+            self.grid_ = torch.empty(_lib().df_node_grid_bytes(M), dtype=torch.uint8, device=self.device)
+            capi.check(_lib().df_build_node_grid(self.nodes_.data_ptr(), M, self.grid_.data_ptr(), _stream()))
+
+    def _grid(self):
+        return self.grid_.data_ptr() if self.grid_ is not None else None
 
     def setWarpToLive(self, pose):
         self.warp_to_live_ = pose
@@ -306,7 +325,8 @@ class WarpField:
         N, stride = points.shape
         idx = torch.empty((N, 8), dtype=torch.int32, device=self.device)
         d2 = torch.empty((N, 8), dtype=torch.float32, device=self.device)
-        capi.check(_lib().df_knn8(self.nodes_.data_ptr(), self.nodes_.shape[0], points.data_ptr(), N, stride, idx.data_ptr(), d2.data_ptr(), _stream()))
+        capi.check(_lib().df_knn8(self.nodes_.data_ptr(), self.nodes_.shape[0], self._grid(), points.data_ptr(), N, stride, idx.data_ptr(),
+                                  d2.data_ptr(), _stream()))
         return idx, d2
 
     def warp(self, points: torch.Tensor, normals: torch.Tensor, flags: int = 0, want_knn: bool = False):
@@ -315,7 +335,7 @@ class WarpField:
         if want_knn:
             idx = torch.empty((N, 8), dtype=torch.int32, device=self.device)
             w = torch.empty((N, 8), dtype=torch.float32, device=self.device)
-        capi.check(_lib().df_warp(self.nodes_.data_ptr(), self.nodes_.shape[0], points.data_ptr(), normals.data_ptr(), N, stride,
+        capi.check(_lib().df_warp(self.nodes_.data_ptr(), self.nodes_.shape[0], self._grid(), points.data_ptr(), normals.data_ptr(), N, stride,
                                   capi.make_aff(*self.warp_to_live_), flags, idx.data_ptr() if want_knn else None,
                                   w.data_ptr() if want_knn else None, _stream()))
         return idx, w
@@ -327,7 +347,7 @@ class WarpField:
         need = _lib().df_solve_workspace_bytes(M, N)
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-        stats = torch.zeros(4, dtype=torch.float64, device=self.device)
-        capi.check(_lib().df_solve_data_term(self.nodes_.data_ptr(), M, canonical.data_ptr(), live.data_ptr(), N, stride, nonlinear_iters,
-                                             linear_iters, flags, stats.data_ptr(), self._ws.data_ptr(), _stream()))
+        stats = torch.zeros(8, dtype=torch.float64, device=self.device)
+        capi.check(_lib().df_solve_data_term(self.nodes_.data_ptr(), M, self._grid(), canonical.data_ptr(), live.data_ptr(), N, stride,
+                                             nonlinear_iters, linear_iters, flags, stats.data_ptr(), self._ws.data_ptr(), _stream()))
         return stats

@@ -105,15 +105,11 @@ class KinFu:
         """copy a device buffer of the current state to the host as numpy (tests/diagnostics)"""
         ptr, pitch, cols, rows = C.c_void_p(), C.c_size_t(), C.c_int(), C.c_int()
         capi.check(self.lib.df_kinfu_get_buffer(self.h, BUF[name], C.byref(ptr), C.byref(pitch), C.byref(cols), C.byref(rows)))
-        torch.cuda.synchronize()
         nbytes = pitch.value * rows.value
         if nbytes == 0:
             return np.zeros(0, np.uint8)
-        host = torch.empty(nbytes, dtype=torch.uint8)
-        cudart = torch.cuda.cudart()
-        err = cudart.cudaMemcpy(host.data_ptr(), ptr.value, nbytes, 2)   # cudaMemcpyDeviceToHost
-        assert int(err) == 0, err
-        raw = host.numpy()
+        raw = np.empty(nbytes, np.uint8)
+        capi.check(self.lib.df_kinfu_read_buffer(self.h, BUF[name], raw.ctypes.data, nbytes))
         p = self.params
         if name == "volume":
             return raw.view(np.uint32)

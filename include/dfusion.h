@@ -131,15 +131,23 @@ int df_icp_estimate(const float *const *vcurr, const float *const *ncurr, const 
 
 /* WarpField::KNN (warp_field.hpp:66, warp_field.cpp:247-251) for N queries: exact 8-NN, ascending squared distance,
  * ties -> lower node index; idx = -1 / d2 = FLT_MAX for NaN queries or when M < 8.  qstride in floats. */
-int df_knn8(const float *nodes, int M, const float *queries, int N, int qstride, int32_t *idx, float *d2, void *stream);
+int df_knn8(const float *nodes, int M, const void *node_grid, const float *queries, int N, int qstride, int32_t *idx, float *d2,
+            void *stream);
+
+/* WarpField::buildKDTree (warp_field.hpp:84, warp_field.cpp:275-282): uniform grid over the node vertices that replaces the
+ * nanoflann index.  Optional everywhere (`node_grid` = NULL -> exhaustive shared-memory scan); results are identical either
+ * way (candidates ranked by (distance, index)).  Build once per node set: vertices do not move after WarpField::init. */
+size_t df_node_grid_bytes(int M);
+int df_build_node_grid(const float *nodes, int M, void *node_grid, void *stream);
 
 /* WarpField::warp (warp_field.hpp:62, warp_field.cpp:180-195): k-NN + weights + DQB + transform of points and
  * normals in place (stride in floats, 3 or 4).  flags: bit0 = reference normal cursor (advance only on valid points),
  * bit1 = rotate normals only (extension).  idx_out / w_out (optional, N*8) receive the neighbours and weights. */
 #define DF_WARP_REF_NORMAL_INDEX 1
 #define DF_WARP_NORMAL_ROTATE_ONLY 2
-int df_warp(const float *nodes, int M, float *points, float *normals, int N, int stride, df_aff3f warp_to_live, int flags,
-            int32_t *idx_out, float *w_out, void *stream);
+#define DF_WARP_REUSE_KNN 4        /* idx_out / w_out are INPUTS: neighbours + weights of these points from an earlier pass */
+int df_warp(const float *nodes, int M, const void *node_grid, float *points, float *normals, int N, int stride, df_aff3f warp_to_live,
+            int flags, int32_t *idx_out, float *w_out, void *stream);
 
 /* WarpFieldOptimiser::optimiseWarpData (warp_field_optimiser.hpp:14-17) -> CombinedSolver (CombinedSolver.h:25-110)
  * -> Opt LM/PCG on kfusion/solvers/dynamicfusion.t: translation-only data term solved on the device; node
@@ -148,8 +156,12 @@ int df_warp(const float *nodes, int M, float *points, float *normals, int N, int
  * LM iterations run, valid rows, PCG iterations run, row-overflow flag.  workspace from df_solve_workspace_bytes(M, N).
  * Rows with a NaN in canon or live are skipped (the reference zero-fills them with stale k-NN scratch). */
 size_t df_solve_workspace_bytes(int M, int N);
+/* after df_solve_data_term: the per-vertex neighbour indices (N*8, -1 for skipped rows) and weights (N*8) it computed for
+ * `canon`, inside `workspace` -- valid until the workspace is reused; lets the following warp of the same vertices skip its
+ * k-NN pass (DF_WARP_REUSE_KNN) */
+int df_solve_knn_buffers(void *workspace, int M, int N, int32_t **idx, float **w);
 #define DF_SOLVE_REF_GRAPH_QUIRK 1
-int df_solve_data_term(float *nodes, int M, const float *canon, const float *live, int N, int stride,
+int df_solve_data_term(float *nodes, int M, const void *node_grid, const float *canon, const float *live, int N, int stride,
                        int nonlinear_iters, int linear_iters, int flags, double *stats_dev, void *workspace, void *stream);
 
 /* ------------------------------------------------------------------ per-frame pipeline ----------------------------------------------------- */
@@ -203,6 +215,8 @@ int df_kinfu_get_info(void *kinfu, long long *info_host, int n);
  * 5 prev points L0, 6 prev normals L0, 7 canonical (after 2nd warp), 8 canonical normals, 9 extracted cloud,
  * 10 extracted normals, 11 nodes, 12 canonical_visible, 13 solver stats (8 doubles) */
 int df_kinfu_get_buffer(void *kinfu, int which, void **ptr, size_t *pitch, int *cols, int *rows);
+/* synchronous device-to-host copy of one of those buffers (diagnostics / tests), at most `bytes` bytes */
+int df_kinfu_read_buffer(void *kinfu, int which, void *dst_host, size_t bytes);
 /* per-stage milliseconds of the last frame (DF_KINFU_STAGE_TIMING): preprocess, icp, raycast_canonical, warp1, solve,
  * warp2, project_remove, integrate, extract, raycast_prev; returns the number written */
 int df_kinfu_get_stage_ms(void *kinfu, float *ms_host, int n);

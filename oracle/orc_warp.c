@@ -120,21 +120,35 @@ void orc_knn8(const float *nodes, int M, const float *queries, long long N, int 
 /* WarpField::weighting (warp_field.cpp:238-241, double exp of a float argument) +
  * WarpField::DQB (:203-217) + DualQuaternion(translation, rotation) ctor (dual_quaternion.hpp:59-63).
  * Outputs the blended dual quaternion (rot4 = rotation_, trans4 = translation_) and the 8 weights. */
+void orc_dqb_weighted(const float *nodes, const int32_t *idx8, const float *w8, float *rot4, float *trans4);
+
 void orc_dqb(const float *nodes, const int32_t *idx8, const float *d2_8, float *rot4, float *trans4, float *weights8)
+{
+    float w8[8];
+    for (int i = 0; i < 8; ++i) {
+        w8[i] = 0.f;
+        if (idx8[i] >= 0) {
+            float nw = nodes[(size_t)idx8[i] * ORC_NODE_STRIDE + 11];
+            w8[i] = (float)exp((double)(-d2_8[i] / (2 * nw * nw)));
+        }
+        if (weights8) weights8[i] = w8[i];
+    }
+    orc_dqb_weighted(nodes, idx8, w8, rot4, trans4);
+}
+
+/* the blend itself (warp_field.cpp:207-216) for given weights; pinned bit for bit against the reference's own
+ * Quaternion / DualQuaternion classes by tests/golden/dq_ref.json */
+void orc_dqb_weighted(const float *nodes, const int32_t *idx8, const float *w8, float *rot4, float *trans4)
 {
     float tsum[4] = {0, 0, 0, 0}, rsum[4] = {0, 0, 0, 0};
     for (int i = 0; i < 8; ++i) {
-        float w = 0.f;
-        if (idx8[i] >= 0) {
-            const float *node = nodes + (size_t)idx8[i] * ORC_NODE_STRIDE;
-            float nw = node[11];
-            w = (float)exp((double)(-d2_8[i] / (2 * nw * nw)));
-            float t4[4];
-            orc_node_translation(node, t4);
-            for (int c = 0; c < 4; ++c) tsum[c] = tsum[c] + w * t4[c];
-            for (int c = 0; c < 4; ++c) rsum[c] = rsum[c] + w * node[3 + c];
-        }
-        if (weights8) weights8[i] = w;
+        if (idx8[i] < 0) continue;
+        const float *node = nodes + (size_t)idx8[i] * ORC_NODE_STRIDE;
+        float w = w8[i];
+        float t4[4];
+        orc_node_translation(node, t4);
+        for (int c = 0; c < 4; ++c) tsum[c] = tsum[c] + w * t4[c];
+        for (int c = 0; c < 4; ++c) rsum[c] = rsum[c] + w * node[3 + c];
     }
     quat_normalize(rsum);
     for (int c = 0; c < 4; ++c) rot4[c] = rsum[c];
@@ -144,7 +158,7 @@ void orc_dqb(const float *nodes, const int32_t *idx8, const float *d2_8, float *
 }
 
 /* DualQuaternion::transform, dual_quaternion.hpp:204-210 */
-static void dq_transform(const float *rot4, const float *trans4, float *v)
+void orc_dq_transform(const float *rot4, const float *trans4, float *v)
 {
     float node[ORC_NODE_STRIDE] = {0};
     for (int c = 0; c < 4; ++c) { node[3 + c] = rot4[c]; node[7 + c] = trans4[c]; }
@@ -180,7 +194,7 @@ void orc_warp(const float *nodes, int M, float *points, float *normals, long lon
         orc_knn8(nodes, M, pt, 1, stride, idx, d2);
         float rot4[4], trans4[4];
         orc_dqb(nodes, idx, d2, rot4, trans4, NULL);
-        dq_transform(rot4, trans4, pt);
+        orc_dq_transform(rot4, trans4, pt);
         aff_apply_cv(&warp_to_live, pt);
         if (flags & 2) {
             orc_quat_rotate_vec(rot4, nr);
@@ -189,7 +203,7 @@ void orc_warp(const float *nodes, int M, float *points, float *normals, long lon
             nr[1] = warp_to_live.R[3] * x + warp_to_live.R[4] * y + warp_to_live.R[5] * z;
             nr[2] = warp_to_live.R[6] * x + warp_to_live.R[7] * y + warp_to_live.R[8] * z;
         } else {
-            dq_transform(rot4, trans4, nr);
+            orc_dq_transform(rot4, trans4, nr);
             aff_apply_cv(&warp_to_live, nr);
         }
         ++cursor;

@@ -125,12 +125,13 @@ def test_knn_and_warp(orc, M, N):
     pts[::13, 0] = np.nan
     nrm[::17, 0] = np.nan
     pts[1, :3] = nodes[min(10, M - 1), :3]               # query exactly on a (possibly duplicated) node
-    wf = host.WarpField()
-    wf.nodes_ = torch.from_numpy(nodes).cuda()
-    idx, d2 = wf.KNN(torch.from_numpy(pts).cuda())
     ridx, rd2 = orc.knn8(nodes, pts)
-    assert np.array_equal(idx.cpu().numpy(), ridx), "k-NN indices must be bit-exact"
-    assert np.array_equal(d2.cpu().numpy().view(np.uint32), rd2.view(np.uint32))
+    for use_grid in (False, True):                       # exhaustive shared-memory scan and uniform node grid: identical results
+        wf = host.WarpField(use_grid=use_grid)
+        wf.setNodes(torch.from_numpy(nodes).cuda())
+        idx, d2 = wf.KNN(torch.from_numpy(pts).cuda())
+        assert np.array_equal(idx.cpu().numpy(), ridx), f"k-NN indices must be bit-exact (use_grid={use_grid})"
+        assert np.array_equal(d2.cpu().numpy().view(np.uint32), rd2.view(np.uint32))
     for flags in (0, 2):
         p_dev, n_dev = torch.from_numpy(pts).cuda(), torch.from_numpy(nrm).cuda()
         kidx, kw = wf.warp(p_dev, n_dev, flags=flags, want_knn=True)
@@ -155,7 +156,15 @@ def _gpu_solve(node_pts, src, dst, nl=300, lin=250, flags=0):
     wf.init(node_pts)
     s = np.zeros((len(src), 4), np.float32); s[:, :3] = src
     d = np.zeros((len(dst), 4), np.float32); d[:, :3] = dst
-    stats = wf.optimiseWarpData(torch.from_numpy(s).cuda(), torch.from_numpy(d).cuda(), nl, lin, flags)
+    # the reference's tests run numIter = 20 outer passes of nonLinearIter = 15 LM steps; every pass re-initialises the
+    # trust region (Opt_ProblemInit), which keeps the LM damping away from the rank-deficient systems' null space
+    passes = max(1, nl // 15)
+    first = None
+    for _ in range(passes):
+        stats = wf.optimiseWarpData(torch.from_numpy(s).cuda(), torch.from_numpy(d).cuda(), min(nl, 15), lin, flags)
+        if first is None:
+            first = stats.clone()
+    stats[0] = first[0]
     nrm = np.zeros_like(s); nrm[:, 2] = 1
     p_dev, n_dev = torch.from_numpy(s.copy()).cuda(), torch.from_numpy(nrm).cuda()
     wf.warp(p_dev, n_dev)
@@ -173,10 +182,10 @@ def test_solve_reference_scenario_single_vertex():
 
 @pytest.mark.parametrize("name", ["rigid", "multiple_nodes", "non_rigid"])
 def test_solve_reference_scenarios_match_oracle(orc, name):
-    from tests.test_oracle_golden import SCENARIOS, _lsq_reference
+    from warp_scenarios import SCENARIOS, lsq_reference
     node_pts, src, dst = SCENARIOS[name]
     wf, warped, stats = _gpu_solve(node_pts, src, dst)
-    best, _, _ = _lsq_reference(node_pts, src, dst)
+    best, _, _ = lsq_reference(node_pts, src, dst)
     np.testing.assert_allclose(warped, best, atol=2e-4)
     nodes_ref = orc.make_nodes(node_pts)
     ostats = orc.solve_data_term(nodes_ref, np.array(src, np.float32), np.array(dst, np.float32), lm_iters=300)
