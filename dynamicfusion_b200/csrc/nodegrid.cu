@@ -31,8 +31,9 @@ __global__ void __launch_bounds__(1024) build_node_grid_kernel(const float *__re
             for (int w = 1; w < 32; ++w) { lo[c] = fminf(lo[c], smin[c][w]); hi[c] = fmaxf(hi[c], smax[c][w]); }
         }
         const float ext = fmaxf(fmaxf(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
-        // nodes sample a surface: ~sqrt(M) nodes along the longest extent; aim at ~2 node spacings per cell
-        int res = (int)ceilf(sqrtf((float)M) / 1.5f);
+        // nodes sample a surface: ~sqrt(M) nodes along the longest extent; ~3 node spacings per cell, so that the 8th
+        // neighbour (about 1.7 spacings away) is usually confirmed after the first shell (27 cells)
+        int res = (int)ceilf(sqrtf((float)M) / 3.0f);
         res = max(1, min(res, NODEGRID_MAX_RES));
         const float cell = ext > 0.f ? ext / (float)res * 1.0001f : 1.f;
         h.ox = lo[0]; h.oy = lo[1]; h.oz = lo[2]; h.cell = cell; h.inv_cell = 1.f / cell;

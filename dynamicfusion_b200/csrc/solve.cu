@@ -518,10 +518,11 @@ solve_lm_cluster_kernel(float *nodes, int M, SolveWs ws, int nl_iters, int lin_i
             const Quat t = dq_translation(Quat{a.w, b.x, b.y, b.z}, Quat{b.w, c.x, c.y, c.z});
             x[n] = t.x; x[M + n] = t.y; x[2 * M + n] = t.z;
         }
-    double c0n[2] = {0.0, 0.0};
+    double c0n[3] = {0.0, 0.0, 0.0};
     for (int i = gt; i < ws.prepare_blocks; i += T) { c0n[0] += ws.c0_partials[2 * i]; c0n[1] += ws.c0_partials[2 * i + 1]; }
+    for (int n = gt; n < M; n += T) c0n[2] += (double)ws.rownnz[n];
     cluster_sum(cluster, sm, parity, c0n);                     // also publishes x
-    const double nvalid = c0n[1];
+    const double nvalid = c0n[1], nnz_total = c0n[2];
     spmv(x, Ap);
     double t0[1] = {0.0};
     if (owner)
@@ -638,6 +639,7 @@ solve_lm_cluster_kernel(float *nodes, int M, SolveWs ws, int nl_iters, int lin_i
         }
     if (gt == 0 && stats) {
         stats[0] = cost0; stats[1] = cost; stats[2] = (double)it; stats[3] = nvalid; stats[4] = (double)pcg_total; stats[5] = (double)ws.flags[0];
+        stats[6] = nnz_total;
     }
 }
 

@@ -94,9 +94,10 @@ __device__ __forceinline__ void knn8_grid(const void *__restrict__ grid, bool va
         const int cz = min(max((int)floorf((qz - h.oz) * h.inv_cell), 0), h.gz - 1);
         const int rmax = max(max(h.gx, h.gy), h.gz);
         for (int r = 0; r <= rmax; ++r) {
-            // every node in a cell at Chebyshev distance > r from (cx,cy,cz) is at least r*cell away from the query
-            if (r >= 1 && bi[7] != 0x7fffffff) {
-                const float bound = (float)r * h.cell * 0.999f;
+            // shells 0..r-1 are done: every unvisited node sits in a cell at Chebyshev distance >= r from (cx,cy,cz), i.e. at
+            // least (r-1)*cell away from the query (the query lies anywhere inside its own, possibly clamped, cell)
+            if (r >= 2 && bi[7] != 0x7fffffff) {
+                const float bound = (float)(r - 1) * h.cell * 0.999f;
                 if (bound * bound > bd[7]) break;
             }
             for (int z = cz - r; z <= cz + r; ++z) {

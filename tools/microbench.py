@@ -57,6 +57,7 @@ def main():
         out["stage_ms"] = {kk: round(v / n, 4) for kk, v in acc.items()}
         out["frame_ms_sum"] = round(sum(out["stage_ms"].values()), 4)
         out["info"] = k.info()
+        out["solve_stats"] = [float(v) for v in k.buffer("solve_stats")]
         k.close()
         print(json.dumps(out, indent=1))
         return
