@@ -67,5 +67,39 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+MIRROR_LIB = HERE / "libkfusion.so"
+MIRROR_SRC = CSRC / "kfusion" / "kfusion_mirror.cpp"
+MIRROR_INC = ["-I", str(ROOT / "include"), "-I", str(ROOT / "include" / "cvcompat")]
+
+
+def build_mirror(force: bool = False) -> Path:
+    """libkfusion.so: the C++ mirror of the reference's public classes (include/kfusion) over libdfusion.so"""
+    build()
+    deps = [MIRROR_SRC, LIB] + sorted((ROOT / "include").rglob("*.h*"))
+    if not force and MIRROR_LIB.exists() and all(d.stat().st_mtime <= MIRROR_LIB.stat().st_mtime for d in deps):
+        return MIRROR_LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, "-std=c++17", "-O2", "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", *MIRROR_INC, "-shared", "-o", str(MIRROR_LIB),
+           str(MIRROR_SRC), "-L", str(HERE), "-ldfusion", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building libkfusion.so failed:\n" + r.stdout)
+    return MIRROR_LIB
+
+
+def build_cpp_program(src: Path, out: Path) -> Path:
+    """compile + link a C++ program against the mirror (used by tests/test_cpp_mirror.py)"""
+    build_mirror()
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, "-std=c++17", "-O1", *MIRROR_INC, "-o", str(out), str(src), "-L", str(HERE), "-lkfusion", "-ldfusion",
+           "-Xlinker", "-rpath", "-Xlinker", str(HERE)]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"building {src.name} failed:\n" + r.stdout)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--mirror" in sys.argv:
+        print(build_mirror(force="--force" in sys.argv))

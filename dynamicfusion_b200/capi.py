@@ -62,6 +62,8 @@ PROTOTYPES = {
     "df_pyr_down": (_i, [_vp, _sz, _i, _i, _vp, _sz, _f, _vp]),
     "df_points_normals": (_i, [Intr, _vp, _sz, _i, _i, _vp, _sz, _vp, _sz, _vp]),
     "df_resize_points_normals": (_i, [_vp, _sz, _vp, _sz, _i, _i, _vp, _sz, _vp, _sz, _vp]),
+    "df_render_image": (_i, [_vp, _sz, _vp, _sz, _i, _i, C.POINTER(C.c_float), _vp, _sz, _vp]),
+    "df_render_tangent_colors": (_i, [_vp, _sz, _i, _i, _vp, _sz, _vp]),
     "df_icp_accumulate": (_i, [_vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _i, _i, Intr, Aff3f, _f, _f, _vp, _vp]),
     "df_icp_estimate": (_i, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i),
                              C.POINTER(_sz), _i, C.POINTER(_i), Intr, _f, _f, _vp, _vp, _vp, _vp]),
@@ -79,6 +81,7 @@ PROTOTYPES = {
     "df_kinfu_process_host": (_i, [_vp, _vp, _sz]),
     "df_kinfu_process_device": (_i, [_vp, _vp, _sz]),
     "df_kinfu_get_stage_ms": (_i, [_vp, C.POINTER(C.c_float), _i]),
+    "df_kinfu_dynamicfusion": (_i, [_vp, _vp, _sz, _vp, _sz]),
     "df_kinfu_get_pose": (_i, [_vp, _i, C.POINTER(C.c_float)]),
     "df_kinfu_get_info": (_i, [_vp, C.POINTER(C.c_longlong), _i]),
     "df_kinfu_get_buffer": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_sz), C.POINTER(_i), C.POINTER(_i)]),

@@ -119,7 +119,7 @@ int do_reset(KinFu &k)
     return df_clear_volume(vol_of(k), k.stream);
 }
 
-int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch)
+int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_df = false)
 {
     const df_kinfu_params &p = k.p;
     cudaStream_t s = k.stream;
@@ -128,6 +128,7 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch)
     memset(k.stage_mark, 0, sizeof k.stage_mark);
     mark(k, 0);
 
+    if (!only_df) {
     // ---- pre-processing, kinfu.cpp:226-242 -----------------------------------------------------------------------
     CKD(df_compute_dists(depth_dev, depth_pitch, p.cols, p.rows, p.intr, (uint16_t *)k.dists.ptr, k.dists.pitch, s));
     CKD(df_bilateral(depth_dev, depth_pitch, p.cols, p.rows, (uint16_t *)k.cur_depth[0].ptr, k.cur_depth[0].pitch,
@@ -150,6 +151,7 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch)
         ++k.launches;
     }
     mark(k, 1);
+    }
 
     const df_volume vol = vol_of(k);
     float vol_pose[12];
@@ -184,7 +186,7 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch)
     };
 
     // ---- first frame, kinfu.cpp:245-264 ----------------------------------------------------------------------------
-    if (k.frame_counter == 0) {
+    if (!only_df && k.frame_counter == 0) {
         CKD(integrate_with(k.dists, &k.poses[k.poses.size() - 12]));
         CKD(extract());
         if (!(p.flags & DF_KINFU_RIGID_ONLY)) {
@@ -208,7 +210,7 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch)
     }
 
     // ---- ICP, kinfu.cpp:268-278 (device-resident; one host read of {ok, T}) -----------------------------------------
-    {
+    if (!only_df) {
         const float *vc[MAX_LEVELS], *nc[MAX_LEVELS], *vp[MAX_LEVELS], *np[MAX_LEVELS];
         int cols[MAX_LEVELS], rows[MAX_LEVELS]; size_t pitch[MAX_LEVELS];
         for (int i = 0; i < LEVELS; ++i) {
@@ -229,7 +231,7 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch)
         if (!ok) { CKD(do_reset(k)); return 0; }                      // kinfu.cpp:276-277
     }
     mark(k, 2);
-    {
+    if (!only_df) {
         float pose[12];
         dfh_aff_mul(&k.poses[k.poses.size() - 12], k.pinned, pose);   // poses_.back() * affine, kinfu.cpp:280
         k.poses.insert(k.poses.end(), pose, pose + 12);
@@ -284,6 +286,7 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch)
         mark(k, 8); mark(k, 9);
     }
 
+    if (only_df) return 1;
     // ---- ray-cast for the next frame's ICP, kinfu.cpp:297-301 --------------------------------------------------------
     CKD(raycast_to(cam_pose, k.prev_pts[0], k.prev_nrm[0]));
     for (int i = 1; i < LEVELS; ++i) {
@@ -411,6 +414,20 @@ extern "C" int df_kinfu_process_device(void *h, const uint16_t *depth_dev, size_
     KinFu *k = (KinFu *)h;
     const int r = process(*k, depth_dev, pitch);
     finish_timing(*k);
+    return r;
+}
+
+// KinFu::dynamicfusion(depth, live_frame, current_normals) (kinfu.hpp:87, kinfu.cpp:344-400) as a stand-alone call on
+// caller-provided device buffers (depth is modified in place by the project-and-remove step, like the reference)
+extern "C" int df_kinfu_dynamicfusion(void *h, uint16_t *depth_dev, size_t depth_pitch, const float *live_points_dev, size_t live_pitch)
+{
+    KinFu *k = (KinFu *)h;
+    if (k->poses.size() < 12) return 0;
+    const Img saved_depth = k->cur_depth[0], saved_pts = k->cur_pts[0];
+    k->cur_depth[0].ptr = depth_dev; k->cur_depth[0].pitch = depth_pitch;
+    k->cur_pts[0].ptr = (void *)live_points_dev; k->cur_pts[0].pitch = live_pitch;
+    const int r = process(*k, nullptr, 0, true);
+    k->cur_depth[0] = saved_depth; k->cur_pts[0] = saved_pts;
     return r;
 }
 

@@ -422,7 +422,7 @@ __device__ __forceinline__ void cluster_sum(cg::cluster_group &cluster, ClusterR
     if (warp == 0) {
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
-            double t = sm.warp[lane][k];                       // blockDim.x == 1024 -> 32 warps
+            double t = lane < (int)(blockDim.x >> 5) ? sm.warp[lane][k] : 0.0;
             for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
             if (lane == 0) sm.part[parity][k] = t;
         }
@@ -643,10 +643,243 @@ solve_lm_cluster_kernel(float *nodes, int M, SolveWs ws, int nl_iters, int lin_i
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// v3: the same LM/PCG, with EVERYTHING the iteration touches resident on-chip for the whole solve:
+//   * each CTA owns a contiguous block of rows; its slice of the sparse matrix (packed per thread), its slices of the CG
+//     vectors (x, g, dl, r, z, p, Ap, damping, preconditioner) live in its shared memory;
+//   * the search direction p is the only vector other CTAs need: after updating its rows an owner thread PUSHES its three
+//     values into every CTA's full-length copy through distributed shared memory (no L2 round trip);
+//   * dot products: warp shuffles -> CTA partial in shared memory -> one cluster barrier -> 8 DSMEM reads, fixed order.
+// A PCG iteration is then 3 cluster barriers + shared-memory traffic only (measured: see profiles/).  ncu of v2 showed the
+// iteration was latency-bound on L2 round trips (issue-active 29 %, 27 cycles/instruction) with a 56 k-nonzero matrix.
+constexpr int LM3_THREADS = 512;   // v3: 512 threads x 128 registers -- no spills (local memory is an L2 round trip after every cluster barrier's L1 flush)
+
+struct LmSmemLayout {
+    int rpc;            // rows per CTA
+    int tpr;            // threads per row
+    int ent_cap;        // matrix entries per thread kept in shared memory
+    size_t off_svec, off_loc, off_col, off_val, total;
+};
+
+__host__ __device__ inline LmSmemLayout lm_layout(int M, int ent_cap)
+{
+    LmSmemLayout L;
+    L.rpc = (M + LMC_CTAS - 1) / LMC_CTAS;
+    L.tpr = 1;
+    while (L.tpr < 32 && L.tpr * 2 * L.rpc <= LM3_THREADS) L.tpr *= 2;
+    L.ent_cap = ent_cap;
+    size_t o = 0;
+    L.off_svec = o; o += (size_t)3 * M * 8;
+    L.off_loc = o; o += (size_t)(7 * 3 + 2) * L.rpc * 8;          // x g dl r z p Ap (3 each) + cd + minv
+    L.off_val = o; o += (size_t)L.ent_cap * LM3_THREADS * 8;
+    L.off_col = o; o += (size_t)L.ent_cap * LM3_THREADS * 4;
+    L.total = o;
+    return L;
+}
+
+__global__ void __cluster_dims__(LMC_CTAS, 1, 1) __launch_bounds__(LM3_THREADS)
+solve_lm_cluster_smem_kernel(float *nodes, int M, SolveWs ws, int nl_iters, int lin_iters, double *stats, int ent_cap)
+{
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ ClusterRed sm;
+    extern __shared__ __align__(16) unsigned char dyn[];
+    const LmSmemLayout L = lm_layout(M, ent_cap);
+    double *svec = reinterpret_cast<double *>(dyn + L.off_svec);          // full-length copy of the vector being multiplied
+    double *loc = reinterpret_cast<double *>(dyn + L.off_loc);
+    double *mval = reinterpret_cast<double *>(dyn + L.off_val);           // [ent][thread]
+    int *mcol = reinterpret_cast<int *>(dyn + L.off_col);
+    const int rpc = L.rpc, tpr = L.tpr, R3 = 3 * rpc;
+    double *x = loc, *g = x + R3, *dl = g + R3, *r = dl + R3, *z = r + R3, *p = z + R3, *Ap = p + R3, *cd = Ap + R3, *minv = cd + rpc;
+
+    int parity = 0;
+    const int cta = (int)cluster.block_rank();
+    const int tid = threadIdx.x;
+    const int rl = tid / tpr, sub = tid % tpr;                 // local row, lane within the row
+    const int n = cta * rpc + rl;                              // global row
+    const bool has_row = rl < rpc && n < M;
+    const bool owner = has_row && sub == 0;
+    const int M3 = 3 * M;
+
+    // matrix slice -> shared memory (once)
+    const int nnz = has_row ? ws.rownnz[n] : 0;
+    int my_ent = 0;                                            // entries of this thread kept in shared memory (the first ent_cap)
+    for (int e = sub; e < nnz && my_ent < ent_cap; e += tpr, ++my_ent) {
+        mcol[my_ent * LM3_THREADS + tid] = ws.col[(size_t)e * M + n];
+        mval[my_ent * LM3_THREADS + tid] = ws.val[(size_t)e * M + n];
+    }
+    const int e_rest = sub + my_ent * tpr;                     // first entry that did not fit: streamed from L2 every time
+    const double diag_n = has_row ? ws.diag[n] : 0.0;
+    double gbn[3] = {0.0, 0.0, 0.0};
+    if (owner) { gbn[0] = ws.gb[n]; gbn[1] = ws.gb[M + n]; gbn[2] = ws.gb[2 * M + n]; }
+
+    // push this row's three values of a local vector into every CTA's svec
+    auto publish = [&](const double *v) {
+        if (owner) {
+            const double a0 = v[rl], a1 = v[rpc + rl], a2 = v[2 * rpc + rl];
+#pragma unroll
+            for (int c = 0; c < LMC_CTAS; ++c) {
+                double *remote = cluster.map_shared_rank(svec, c);
+                remote[n] = a0; remote[M + n] = a1; remote[2 * M + n] = a2;
+            }
+        }
+    };
+    // out (owner's local vector) = A * svec for this thread's row
+    auto spmv = [&](double *out) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        for (int k = 0; k < my_ent; ++k) {
+            const int j = mcol[k * LM3_THREADS + tid];
+            const double a = mval[k * LM3_THREADS + tid];
+            a0 += a * svec[j]; a1 += a * svec[M + j]; a2 += a * svec[2 * M + j];
+        }
+        for (int e = e_rest; e < nnz; e += tpr) {
+            const int j = __ldg(ws.col + (size_t)e * M + n);
+            const double a = __ldg(ws.val + (size_t)e * M + n);
+            a0 += a * svec[j]; a1 += a * svec[M + j]; a2 += a * svec[2 * M + j];
+        }
+        for (int o = tpr >> 1; o > 0; o >>= 1) {
+            a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+        }
+        if (owner) { out[rl] = a0; out[rpc + rl] = a1; out[2 * rpc + rl] = a2; }
+    };
+
+    // x0 = current node translations (CombinedSolver.h:165-172)
+    if (owner) {
+        const float4 *n4 = reinterpret_cast<const float4 *>(nodes + (size_t)n * DF_NODE_STRIDE);
+        const float4 a = n4[0], b = n4[1], c = n4[2];
+        const Quat t = dq_translation(Quat{a.w, b.x, b.y, b.z}, Quat{b.w, c.x, c.y, c.z});
+        x[rl] = t.x; x[rpc + rl] = t.y; x[2 * rpc + rl] = t.z;
+    }
+    const int T = LMC_CTAS * LM3_THREADS, gt = cta * LM3_THREADS + tid;
+    double c0n[3] = {0.0, 0.0, 0.0};
+    for (int i = gt; i < ws.prepare_blocks; i += T) { c0n[0] += ws.c0_partials[2 * i]; c0n[1] += ws.c0_partials[2 * i + 1]; }
+    c0n[2] = (owner ? (double)nnz : 0.0);
+    cluster.sync();                                            // every CTA is running: remote shared memory may be written
+    publish(x);
+    cluster_sum(cluster, sm, parity, c0n);                     // its barrier also completes the publish
+    const double nvalid = c0n[1], nnz_total = c0n[2];
+    spmv(Ap);
+    double t0[1] = {0.0};
+    if (owner)
+        for (int d = 0; d < 3; ++d) t0[0] += x[d * rpc + rl] * (0.5 * Ap[d * rpc + rl] - gbn[d]);
+    cluster_sum(cluster, sm, parity, t0);
+    double cost = c0n[0] + t0[0];
+    const double cost0 = cost;
+
+    double radius = 1e4, decrease = 2.0;                       // solverGPUGaussNewton.t:26-39
+    int it = 0, pcg_total = 0;
+    for (; it < nl_iters; ++it) {
+        spmv(Ap);                                              // svec holds x here
+        double rzv[1] = {0.0};
+        if (owner) {
+            const double cdn = fmin(fmax(diag_n, 1e-6), 1e32) / radius;
+            const double mi = 1.0 / (diag_n + cdn);
+            cd[rl] = cdn; minv[rl] = mi;
+            for (int d = 0; d < 3; ++d) {
+                const int i = d * rpc + rl;
+                const double gi = gbn[d] - Ap[i];
+                g[i] = gi; dl[i] = 0.0; r[i] = gi;
+                const double zi = gi * mi;
+                z[i] = zi; p[i] = zi;
+                rzv[0] += gi * zi;
+            }
+        }
+        __syncthreads();                                       // all spmv reads of svec (x) done in this CTA ...
+        cluster.sync();                                        // ... and in every other CTA, before p overwrites it
+        publish(p);
+        cluster_sum(cluster, sm, parity, rzv);
+        double rz = rzv[0];
+        double Q0 = 0.0;
+        for (int l = 0; l < lin_iters && rz > 0.0; ++l) {
+            spmv(Ap);
+            double pap[1] = {0.0};
+            if (owner)
+                for (int d = 0; d < 3; ++d) {
+                    const int i = d * rpc + rl;
+                    const double ap = Ap[i] + cd[rl] * p[i];
+                    Ap[i] = ap;
+                    pap[0] += p[i] * ap;
+                }
+            cluster_sum(cluster, sm, parity, pap);             // barrier: every CTA finished reading svec (p)
+            if (!(pap[0] > 0.0)) break;
+            const double alpha = rz / pap[0];
+            double rq[2] = {0.0, 0.0};
+            double znew[3] = {0.0, 0.0, 0.0};
+            if (owner)
+                for (int d = 0; d < 3; ++d) {
+                    const int i = d * rpc + rl;
+                    const double dli = dl[i] + alpha * p[i];
+                    const double ri = r[i] - alpha * Ap[i];
+                    const double zi = ri * minv[rl];
+                    dl[i] = dli; r[i] = ri; z[i] = zi; znew[d] = zi;
+                    rq[0] += ri * zi;
+                    rq[1] += dli * (ri + g[i]);
+                }
+            cluster_sum(cluster, sm, parity, rq);
+            const double rz_new = rq[0], Q1 = -0.5 * rq[1];
+            const double beta = rz_new / rz;
+            if (owner)
+                for (int d = 0; d < 3; ++d) { const int i = d * rpc + rl; p[i] = znew[d] + beta * p[i]; }
+            rz = rz_new;
+            ++pcg_total;
+            const double zeta = (double)(l + 1) * (Q1 - Q0) / Q1;   // Ceres/Opt q-tolerance, solverGPUGaussNewton.t:1093-1101
+            Q0 = Q1;
+            publish(p);
+            cluster.sync();                                    // publish complete everywhere
+            if (zeta < 1e-4) break;
+        }
+        // model change = 0.5 dl.(g + r + C dl);  A dl = g - r - C dl  => new cost = cost - dl.g + 0.5 dl.(A dl)
+        double mad[3] = {0.0, 0.0, 0.0};
+        if (owner)
+            for (int d = 0; d < 3; ++d) {
+                const int i = d * rpc + rl;
+                const double c = cd[rl] * dl[i];
+                mad[0] += dl[i] * (g[i] + r[i] + c);
+                mad[1] += dl[i] * (g[i] - r[i] - c);
+                mad[2] += dl[i] * g[i];
+            }
+        cluster_sum(cluster, sm, parity, mad);
+        const double model = 0.5 * mad[0];
+        const double new_cost = cost - mad[2] + 0.5 * mad[1];
+        const double change = cost - new_cost;
+        const double rho = model > 0.0 ? change / model : 0.0;
+        bool stop = false;
+        if (change >= 0.0 && rho > 1e-3) {
+            if (owner)
+                for (int d = 0; d < 3; ++d) x[d * rpc + rl] += dl[d * rpc + rl];
+            stop = change <= cost * 1e-6;                       // function_tolerance, CombinedSolver.h:88
+            cost = new_cost;
+            const double f = 1.0 - (2.0 * rho - 1.0) * (2.0 * rho - 1.0) * (2.0 * rho - 1.0);
+            radius /= fmax(f, 1.0 / 3.0);
+            radius = fmin(radius, 1e16);
+            decrease = 2.0;
+        } else {
+            radius /= decrease; decrease *= 2.0;
+            if (radius <= 1e-32) stop = true;
+        }
+        if (stop) { ++it; break; }
+        publish(x);                                            // svec <- x for the next linearisation (all CTAs passed the barrier
+        cluster.sync();                                        //  inside cluster_sum(mad), so nobody still reads p from svec)
+    }
+    cluster.sync();                                            // no CTA may exit while others can still write into its shared memory
+    // write back: encodeTranslation (CombinedSolver.h:189-197, dual_quaternion.hpp:82-85)
+    if (owner) {
+        float *nd = nodes + (size_t)n * DF_NODE_STRIDE;
+        const Quat rot = {nd[3], nd[4], nd[5], nd[6]};
+        const Quat h = qhalf(Quat{0.f, (float)x[rl], (float)x[rpc + rl], (float)x[2 * rpc + rl]});
+        const Quat d = qmul(h, rot);
+        nd[7] = d.w; nd[8] = d.x; nd[9] = d.y; nd[10] = d.z;
+    }
+    if (gt == 0 && stats) {
+        stats[0] = cost0; stats[1] = cost; stats[2] = (double)it; stats[3] = nvalid; stats[4] = (double)pcg_total; stats[5] = (double)ws.flags[0];
+        stats[6] = nnz_total;
+    }
+    (void)M3;
+}
+
 int solve_lm_impl()
 {
     static int impl = -1;
-    if (impl < 0) { const char *e = getenv("DF_SOLVE_LM_IMPL"); impl = e ? atoi(e) : 2; }
+    if (impl < 0) { const char *e = getenv("DF_SOLVE_LM_IMPL"); impl = e ? atoi(e) : 3; }
     return impl;
 }
 
@@ -685,7 +918,16 @@ extern "C" int df_solve_data_term(float *nodes, int M, const void *node_grid, co
     DF_LAUNCH_CHECK();
     solve_rows_kernel<<<M, 256, 0, s>>>(ws, M, N, flags & DF_SOLVE_REF_GRAPH_QUIRK);
     DF_LAUNCH_CHECK();
-    if (solve_lm_impl() == 1) solve_lm_kernel<<<1, LM_THREADS, 0, s>>>(nodes, M, ws, nonlinear_iters, linear_iters, stats_dev);
+    const size_t smem_budget = 200 * 1024;
+    const LmSmemLayout L0 = lm_layout(M, 0);
+    if (solve_lm_impl() >= 3 && L0.total + (size_t)LM3_THREADS * 12 <= smem_budget) {
+        const int ent_cap = (int)((smem_budget - L0.total) / ((size_t)LM3_THREADS * 12));
+        const LmSmemLayout L = lm_layout(M, ent_cap);
+        static bool attr3 = false;
+        if (!attr3) { cudaFuncSetAttribute(solve_lm_cluster_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_budget); attr3 = true; }
+        solve_lm_cluster_smem_kernel<<<LMC_CTAS, LM3_THREADS, L.total, s>>>(nodes, M, ws, nonlinear_iters, linear_iters, stats_dev, ent_cap);
+    }
+    else if (solve_lm_impl() == 1) solve_lm_kernel<<<1, LM_THREADS, 0, s>>>(nodes, M, ws, nonlinear_iters, linear_iters, stats_dev);
     else {
         const size_t vec_bytes = (size_t)3 * M * sizeof(double);
         const int use_smem = vec_bytes <= 200 * 1024;

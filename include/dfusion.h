@@ -101,6 +101,12 @@ int df_resize_points_normals(const float *vsrc, size_t vsrc_pitch, const float *
                              int src_cols, int src_rows, float *vdst, size_t vdst_pitch, float *ndst, size_t ndst_pitch,
                              void *stream);
 
+/* device::renderImage points variant / renderTangentColors (internal.hpp:134-136, imgproc.cu:484-583): display only, BGRA out */
+int df_render_image(const float *points, size_t points_pitch, const float *normals, size_t normals_pitch, int cols, int rows,
+                    const float *light_pose_host3, void *image_bgra, size_t image_pitch, void *stream);
+int df_render_tangent_colors(const float *normals, size_t normals_pitch, int cols, int rows, void *image_bgra, size_t image_pitch,
+                             void *stream);
+
 /* ------------------------------------------------------------------ projective ICP -------------------------------------------------------- */
 /* ComputeIcpHelper::operator() points variant (internal.hpp:67-102, proj_icp.cu:80-108,350-394,448-467): one
  * data-association + 27-term reduction pass at one pyramid level.  scratch: device buffer of DF_ICP_SCRATCH_DOUBLES
@@ -205,6 +211,9 @@ int df_kinfu_reset(void *kinfu);
  * the device inside the call (the path apps/demo.cpp takes: imread -> upload -> operator()); _device: depth already in HBM. */
 int df_kinfu_process_host(void *kinfu, const uint16_t *depth_host, size_t pitch);
 int df_kinfu_process_device(void *kinfu, const uint16_t *depth_dev, size_t pitch);
+/* KinFu::dynamicfusion(depth, live_frame, current_normals) (kinfu.hpp:87, kinfu.cpp:344-400) on caller-provided device buffers,
+ * at the latest pose: raycast -> warp -> solve -> warp -> project/remove -> integrate -> extract.  depth is modified in place. */
+int df_kinfu_dynamicfusion(void *kinfu, uint16_t *depth_dev, size_t depth_pitch, const float *live_points_dev, size_t live_pitch);
 /* KinFu::getCameraPose(time) (kinfu.cpp:213-218): 12 floats, R row-major then t; time < 0 = latest */
 int df_kinfu_get_pose(void *kinfu, int time, float *pose12_host);
 /* info[0] frame counter, [1] warp nodes M, [2] extracted cloud points, [3] poses stored, [4] last ICP ok,

@@ -1,0 +1,101 @@
+// demo_like.cpp -- drives the C++ mirror (include/kfusion, libkfusion.so) the way the reference's apps/demo.cpp does
+// (apps/demo.cpp:24-35,80-108), minus the OpenCV viz/highgui windows: default params -> KinFu::Ptr -> upload depth ->
+// operator() -> renderImage -> getCameraPose -> getWarp().getNodesAsMat().  Also exercises the component classes the
+// reference's tests use (WarpField::init / warp, WarpFieldOptimiser, Quaternion, DualQuaternion).
+// Build: see tests/test_cpp_mirror.py.  Needs a GPU to RUN (exit code 0 = all checks passed).
+#include <kfusion/kinfu.hpp>
+#include <cmath>
+#include <cstdio>
+#include <vector>
+
+using namespace kfusion;
+
+static int fails = 0;
+#define CHECK(c) do { if (!(c)) { std::printf("CHECK failed: %s (line %d)\n", #c, __LINE__); ++fails; } } while (0)
+
+// sphere in front of a wall, u16 millimetres
+static std::vector<unsigned short> make_depth(int cols, int rows, const Intr& K, float shift)
+{
+    std::vector<unsigned short> d((size_t)cols * rows);
+    for (int v = 0; v < rows; ++v)
+        for (int u = 0; u < cols; ++u) {
+            const double xl = (u - K.cx) / K.fx, yl = (v - K.cy) / K.fy;
+            const double cx = shift, cy = 0.0, cz = 1.0, r = 0.25;
+            const double a = xl * xl + yl * yl + 1.0, b = -2.0 * (xl * cx + yl * cy + cz), c = cx * cx + cy * cy + cz * cz - r * r;
+            const double disc = b * b - 4 * a * c;
+            const double z = disc >= 0 ? (-b - std::sqrt(disc)) / (2 * a) : 1.4;
+            d[(size_t)v * cols + u] = (unsigned short)std::lround(z * 1000.0);
+        }
+    return d;
+}
+
+int main()
+{
+    // --- quaternion golden values of the reference's tests/utils/test_quaternion.cc ---------------------------------
+    {
+        utils::Quaternion<float> q;
+        q.encodeRotation((float)M_PI_4, 0, 0, 1);
+        CHECK(std::fabs(q.w_ - 0.9238795f) < 1e-6f && std::fabs(q.z_ - 0.38268346f) < 1e-6f);
+        utils::Quaternion<float> a(1, 1, 2, 2), b(0, 0, 1, 1);
+        utils::Quaternion<float> p = a * b;
+        CHECK(p.w_ == -4 && p.x_ == 0 && p.y_ == 0 && p.z_ == 2);
+        CHECK(a.dotProduct(b) == 4);
+        utils::Quaternion<float> n(10, 10, 10, 10);
+        n.normalize();
+        CHECK(n == utils::Quaternion<float>(0.5, 0.5, 0.5, 0.5));
+        utils::DualQuaternion<float> dq(1, 2, 3, 1, 2, 3);
+        utils::Quaternion<float> t = dq.getTranslation();
+        CHECK(std::fabs(t.x_ - 1) < 0.1 && std::fabs(t.y_ - 2) < 0.1 && std::fabs(t.z_ - 3) < 0.1);
+    }
+    // --- tests/warp_test.cpp: EnergyDataSingleVertexTest (tolerance 1e-5) -------------------------------------------------
+    {
+        WarpField warp_field;
+        std::vector<cv::Vec3f> warp_init;
+        for (int i = 0; i < 8; ++i) warp_init.push_back(cv::Vec3f(i & 4 ? -1.f : 1.f, i & 2 ? -1.f : 1.f, i & 1 ? -1.f : 1.f));
+        warp_field.init(warp_init);
+        std::vector<cv::Vec3f> src(1, cv::Vec3f(0, 0, 0)), nrm(1, cv::Vec3f(0, 0, 1)), dst(1, cv::Vec3f(0.05f, 0.05f, 0.05f)), dnrm(1, cv::Vec3f(0, 0, 1));
+        CombinedSolverParameters params;
+        params.numIter = 20; params.nonLinearIter = 15; params.linearIter = 250; params.useOpt = false; params.useOptLM = true; params.earlyOut = true;
+        WarpFieldOptimiser optimiser(&warp_field, params);
+        optimiser.optimiseWarpData(src, nrm, dst, dnrm);
+        warp_field.warp(src, nrm);
+        for (int c = 0; c < 3; ++c) CHECK(std::fabs(src[0][c] - dst[0][c]) < 1e-5f);
+        warp_field.KNN(cv::Vec3f(1, 1, 1));
+        CHECK(warp_field.getRetIndex()->at(0) == 0 && warp_field.getDistSquared()->at(0) == 0.f);
+        CHECK(warp_field.getNodesAsMat().cols == 8);
+    }
+    // --- apps/demo.cpp flow -------------------------------------------------------------------------------------------------
+    KinFuParams params = KinFuParams::default_params_dynamicfusion();
+    params.volume_dims = Vec3i::all(128);                         // keep the demo small
+    KinFu::Ptr kinfu_ = KinFu::Ptr(new KinFu(params));
+    KinFu& dynamic_fusion = *kinfu_;
+    cuda::Depth depth_device_;
+    cuda::Image view_device_;
+    bool has_image = false;
+    for (int i = 0; i < 4; ++i) {
+        std::vector<unsigned short> depth = make_depth(params.cols, params.rows, params.intr, 0.002f * i);
+        depth_device_.upload(&depth[0], params.cols * sizeof(unsigned short), params.rows, params.cols);
+        has_image = dynamic_fusion(depth_device_);
+        CHECK(has_image == (i > 0));
+        if (has_image) {
+            dynamic_fusion.renderImage(view_device_, 3);
+            CHECK(view_device_.rows() == params.rows && view_device_.cols() == params.cols * 2);
+            std::vector<RGB> host((size_t)view_device_.rows() * view_device_.cols());
+            view_device_.download(&host[0], view_device_.cols() * sizeof(RGB));
+            long long lit = 0;
+            for (size_t k = 0; k < host.size(); ++k) lit += host[k].r > 40;
+            CHECK(lit > 10000);
+        }
+        Affine3f pose = dynamic_fusion.getCameraPose();
+        CHECK(std::fabs(pose.matrix(0, 0) - 1.f) < 0.05f && std::fabs(pose.matrix(0, 3)) < 0.05f);
+    }
+    cv::Mat warp_host = dynamic_fusion.getWarp().getNodesAsMat();
+    CHECK(warp_host.cols >= 8);
+    dynamic_fusion.renderImage(view_device_, dynamic_fusion.getCameraPose(), 0);
+    CHECK(view_device_.cols() == params.cols);
+    CHECK(dynamic_fusion.tsdf().getDims()[0] == 128 && dynamic_fusion.icp().getUsedLevelsNum() == 3);
+    dynamic_fusion.tsdf().compute_points();
+    CHECK(dynamic_fusion.tsdf().get_cloud_host().cols > 1000);
+    std::printf(fails ? "demo_like: %d check(s) FAILED\n" : "demo_like: all checks passed\n", fails);
+    return fails ? 1 : 0;
+}
