@@ -158,22 +158,19 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from dynamicfusion_b200 import kinfu as kf
+    from dynamicfusion_b200 import distrib, kinfu as kf
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device"
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    device = torch.device("cuda", local_rank)
+    distrib.init("nccl", device)
 
     def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        distrib.barrier(device)
 
     K, W = args.steps, args.warmup
     nframes = 1 + W + K
-    frames = make_frames(nframes, seed=rank)                     # independent sequence per rank (config 5)
+    frames = make_frames(nframes, seed=distrib.sequence_seed(rank))   # independent sequence per rank (config 5)
     frames_i16 = torch.from_numpy(frames.view(np.int16))
     frames_dev = frames_i16.cuda()
     frames_pinned = frames_i16.pin_memory()
@@ -205,12 +202,7 @@ def main():
         ms = e0.elapsed_time(e1)
         info = k.info()
         k.close()
-        if world > 1:
-            t_ms = torch.tensor([ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-            okt = torch.tensor([ok], device="cuda", dtype=torch.int64)
-            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
-            ms, ok = float(t_ms.item()), int(okt.item())
+        ms, _total, ok = distrib.aggregate(ms, ok, device)       # max time over ranks; ok = fewest fused frames on any rank
         return ms, ok, info, clocks
 
     pitch = COLS * 2

@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#include <chrono>
 
 using namespace dfb;
 
@@ -39,6 +40,7 @@ struct KinFu {
     std::vector<float> poses;            // 12 floats per pose
     int frame_counter = 0, resets = 0, last_ok = 1, launches = 0;
     long long last_cloud = -1;
+    double host_us[4] = {0, 0, 0, 0}; long long host_frames = 0;   // DF_KINFU_HOSTPROF: launch A, ICP wait, launch B, total
     unsigned long long *n_upd = nullptr;   // voxels written by the last integrate (filled when DF_KINFU_STAGE_TIMING)
     cudaEvent_t ev[NSTAGES + 1];
     float stage_ms[NSTAGES];
@@ -119,8 +121,12 @@ int do_reset(KinFu &k)
     return df_clear_volume(vol_of(k), k.stream);
 }
 
+static inline double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_df = false)
 {
+    const double t_begin = now_us();
+    double t_sync0 = t_begin, t_sync1 = t_begin;
     const df_kinfu_params &p = k.p;
     cudaStream_t s = k.stream;
     const int LEVELS = k.levels;
@@ -224,7 +230,9 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_d
         ++k.launches;
         CK(cudaMemcpyAsync(k.pinned, k.icp_T, 12 * sizeof(float), cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(k.pinned + 12, k.icp_ok, sizeof(int), cudaMemcpyDeviceToHost, s));
+        t_sync0 = now_us();
         CK(cudaStreamSynchronize(s));
+        t_sync1 = now_us();
         int ok;
         memcpy(&ok, k.pinned + 12, sizeof(int));
         k.last_ok = ok;
@@ -297,6 +305,11 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_d
     }
     mark(k, 10);
     ++k.frame_counter;
+    {
+        const double t_end = now_us();
+        k.host_us[0] += t_sync0 - t_begin; k.host_us[1] += t_sync1 - t_sync0; k.host_us[2] += t_end - t_sync1; k.host_us[3] += t_end - t_begin;
+        ++k.host_frames;
+    }
     return 1;
 }
 
@@ -381,6 +394,9 @@ extern "C" void df_kinfu_destroy(void *h)
 {
     KinFu *k = (KinFu *)h;
     if (!k) return;
+    if (getenv("DF_KINFU_HOSTPROF") && k->host_frames)
+        fprintf(stderr, "[df_kinfu host profile] frames %lld: launch-A %.1f us, ICP wait %.1f us, launch-B %.1f us, total %.1f us per frame\n", k->host_frames,
+                k->host_us[0] / k->host_frames, k->host_us[1] / k->host_frames, k->host_us[2] / k->host_frames, k->host_us[3] / k->host_frames);
     cudaStreamSynchronize(k->stream);
     cudaFree(k->volume); cudaFree(k->depth_in.ptr); cudaFree(k->dists.ptr);
     for (int l = 0; l < MAX_LEVELS; ++l) { cudaFree(k->cur_depth[l].ptr); cudaFree(k->cur_pts[l].ptr); cudaFree(k->cur_nrm[l].ptr); cudaFree(k->prev_pts[l].ptr); cudaFree(k->prev_nrm[l].ptr); }

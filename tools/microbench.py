@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--zchunk", type=int, default=0)
     ap.add_argument("--pipeline", action="store_true")
     ap.add_argument("--frames", type=int, default=12)
+    ap.add_argument("--trace", action="store_true")
     a = ap.parse_args()
     os.environ["DF_INTEGRATE_IMPL"] = str(a.integrate_impl)
     if a.zchunk:
@@ -50,6 +51,10 @@ def main():
         for t in range(a.frames):
             d = torch.from_numpy(synth.umbrella_depth(t).view(np.int16).copy()).cuda()
             k(d)
+            if a.trace and (t < 6 or t % 5 == 0):
+                i, sm = k.info(), k.stage_ms()
+                print(f"frame {t:3d} lm {i['lm_iters']} pcg {i['pcg_iters']:4d} cloud {i['cloud_points']:7d} n_upd {i['n_updated']:9d} "
+                      f"solve {sm['solve']:.3f} icp {sm['icp']:.3f} integ {sm['integrate']:.3f} extract {sm['extract']:.3f} total {sum(sm.values()):.3f}", flush=True)
             if t >= 3:
                 for name, v in k.stage_ms().items():
                     acc[name] = acc.get(name, 0.0) + v
