@@ -51,6 +51,49 @@ def load() -> C.CDLL:
     return _lib
 
 
+# ------------------------------------------------------------------ reference arm --------------------------------------------------
+# oracle/_ref/libkfref.so = the REFERENCE's own kfusion/src/cuda/*.cu kernels compiled for the host (oracle/ref_shim/cudahost),
+# exported with the orc_* signatures under the kfref_ prefix.  `with orc.reference(): orc.integrate(...)` runs the reference's
+# code instead of the restatement, on the same numpy buffers -- used by tests/ and golden/make_golden.py to pin the oracle.
+REF_LIB = HERE / "_ref" / "libkfref.so"
+_ref_lib = None
+_use_ref = False
+
+
+def reference_available() -> bool:
+    return REF_LIB.exists()
+
+
+def load_ref() -> C.CDLL:
+    global _ref_lib
+    if _ref_lib is None:
+        _ref_lib = C.CDLL(str(REF_LIB))
+        _ref_lib.kfref_integrate.restype = C.c_longlong
+        _ref_lib.kfref_icp_accumulate.restype = C.c_longlong
+    return _ref_lib
+
+
+class reference:
+    """context manager: route the wrappers below to the reference's own kernels (libkfref.so)"""
+
+    def __enter__(self):
+        global _use_ref
+        load_ref()
+        self.prev, _use_ref = _use_ref, True
+        return self
+
+    def __exit__(self, *exc):
+        global _use_ref
+        _use_ref = self.prev
+        return False
+
+
+def _fn(name: str):
+    if _use_ref:
+        return getattr(load_ref(), "kfref_" + name)
+    return getattr(load(), "orc_" + name)
+
+
 def aff(R, t) -> Aff3f:
     a = Aff3f()
     R = np.asarray(R, np.float32).reshape(9)
@@ -90,19 +133,19 @@ def _f9(R):
 
 # ------------------------------------------------------------------ wrappers (numpy in / numpy out) ------------------------------------------
 def clear_volume(vol_data, dims, vs, trunc, mw):
-    load().orc_clear_volume(volume(vol_data, dims, vs, trunc, mw))
+    _fn("clear_volume")(volume(vol_data, dims, vs, trunc, mw))
 
 
 def compute_dists(depth: np.ndarray, K) -> np.ndarray:
     rows, cols = depth.shape
     out = np.empty_like(depth)
-    load().orc_compute_dists(_p(depth), C.c_size_t(cols * 2), cols, rows, intr(*K), _p(out), C.c_size_t(cols * 2))
+    _fn("compute_dists")(_p(depth), C.c_size_t(cols * 2), cols, rows, intr(*K), _p(out), C.c_size_t(cols * 2))
     return out
 
 
 def integrate(vol_data, dims, vs, trunc, mw, dists, vol2cam, K) -> int:
     rows, cols = dists.shape
-    return int(load().orc_integrate(volume(vol_data, dims, vs, trunc, mw), _p(dists), C.c_size_t(cols * 2), cols, rows,
+    return int(_fn("integrate")(volume(vol_data, dims, vs, trunc, mw), _p(dists), C.c_size_t(cols * 2), cols, rows,
                                     aff(*vol2cam), intr(*K)))
 
 
@@ -110,7 +153,7 @@ def raycast_points(vol_data, dims, vs, trunc, mw, cam2vol, Rinv, K, cols, rows, 
     pts = np.empty((rows, cols, 4), np.float32)
     nrm = np.empty((rows, cols, 4), np.float32)
     stats = (C.c_longlong * 3)()
-    load().orc_raycast_points(volume(vol_data, dims, vs, trunc, mw), aff(*cam2vol), _f9(Rinv), intr(*K), cols, rows,
+    _fn("raycast_points")(volume(vol_data, dims, vs, trunc, mw), aff(*cam2vol), _f9(Rinv), intr(*K), cols, rows,
                               C.c_float(step_factor), C.c_float(delta_factor), _p(pts), C.c_size_t(cols * 16), _p(nrm),
                               C.c_size_t(cols * 16), stats)
     return pts, nrm, [int(s) for s in stats]
@@ -119,18 +162,18 @@ def raycast_points(vol_data, dims, vs, trunc, mw, cam2vol, Rinv, K, cols, rows, 
 def project_and_remove(dists: np.ndarray, K, points: np.ndarray):
     rows, cols = dists.shape
     prow, pcol = points.shape[:2]
-    load().orc_project_and_remove(_p(dists), C.c_size_t(cols * 2), cols, rows, intr(*K), _p(points), C.c_size_t(pcol * 16), pcol, prow)
+    _fn("project_and_remove")(_p(dists), C.c_size_t(cols * 2), cols, rows, intr(*K), _p(points), C.c_size_t(pcol * 16), pcol, prow)
 
 
 def extract_cloud(vol_data, dims, vs, trunc, mw, pose, capacity) -> np.ndarray:
     out = np.empty((capacity, 4), np.float32)
-    n = int(load().orc_extract_cloud(volume(vol_data, dims, vs, trunc, mw), aff(*pose), _p(out), C.c_longlong(capacity)))
+    n = int(_fn("extract_cloud")(volume(vol_data, dims, vs, trunc, mw), aff(*pose), _p(out), C.c_longlong(capacity)))
     return out[:n].copy()
 
 
 def extract_normals(vol_data, dims, vs, trunc, mw, pts, pose, Rinv, delta_factor) -> np.ndarray:
     out = np.empty_like(pts)
-    load().orc_extract_normals(volume(vol_data, dims, vs, trunc, mw), _p(pts), C.c_longlong(len(pts)), aff(*pose), _f9(Rinv),
+    _fn("extract_normals")(volume(vol_data, dims, vs, trunc, mw), _p(pts), C.c_longlong(len(pts)), aff(*pose), _f9(Rinv),
                                C.c_float(delta_factor), _p(out))
     return out
 
@@ -138,20 +181,20 @@ def extract_normals(vol_data, dims, vs, trunc, mw, pts, pose, Rinv, delta_factor
 def bilateral(depth, ksz, sigma_spatial, sigma_depth):
     rows, cols = depth.shape
     out = np.empty_like(depth)
-    load().orc_bilateral(_p(depth), C.c_size_t(cols * 2), cols, rows, _p(out), C.c_size_t(cols * 2), ksz, C.c_float(sigma_spatial),
+    _fn("bilateral")(_p(depth), C.c_size_t(cols * 2), cols, rows, _p(out), C.c_size_t(cols * 2), ksz, C.c_float(sigma_spatial),
                          C.c_float(sigma_depth))
     return out
 
 
 def truncate_depth(depth, max_dist):
     rows, cols = depth.shape
-    load().orc_truncate_depth(_p(depth), C.c_size_t(cols * 2), cols, rows, C.c_float(max_dist))
+    _fn("truncate_depth")(_p(depth), C.c_size_t(cols * 2), cols, rows, C.c_float(max_dist))
 
 
 def pyr_down(depth, sigma_depth):
     rows, cols = depth.shape
     out = np.empty((rows // 2, cols // 2), np.uint16)
-    load().orc_pyr_down(_p(depth), C.c_size_t(cols * 2), cols, rows, _p(out), C.c_size_t((cols // 2) * 2), C.c_float(sigma_depth))
+    _fn("pyr_down")(_p(depth), C.c_size_t(cols * 2), cols, rows, _p(out), C.c_size_t((cols // 2) * 2), C.c_float(sigma_depth))
     return out
 
 
@@ -159,7 +202,7 @@ def points_normals(K, depth):
     rows, cols = depth.shape
     pts = np.empty((rows, cols, 4), np.float32)
     nrm = np.empty((rows, cols, 4), np.float32)
-    load().orc_points_normals(intr(*K), _p(depth), C.c_size_t(cols * 2), cols, rows, _p(pts), C.c_size_t(cols * 16), _p(nrm), C.c_size_t(cols * 16))
+    _fn("points_normals")(intr(*K), _p(depth), C.c_size_t(cols * 2), cols, rows, _p(pts), C.c_size_t(cols * 16), _p(nrm), C.c_size_t(cols * 16))
     return pts, nrm
 
 
@@ -167,7 +210,7 @@ def resize_points_normals(v, n):
     rows, cols = v.shape[:2]
     vd = np.empty((rows // 2, cols // 2, 4), np.float32)
     nd = np.empty((rows // 2, cols // 2, 4), np.float32)
-    load().orc_resize_points_normals(_p(v), C.c_size_t(cols * 16), _p(n), C.c_size_t(cols * 16), cols, rows, _p(vd),
+    _fn("resize_points_normals")(_p(v), C.c_size_t(cols * 16), _p(n), C.c_size_t(cols * 16), cols, rows, _p(vd),
                                      C.c_size_t((cols // 2) * 16), _p(nd), C.c_size_t((cols // 2) * 16))
     return vd, nd
 
@@ -175,7 +218,7 @@ def resize_points_normals(v, n):
 def icp_accumulate(vcurr, ncurr, vprev, nprev, K_level, T, dist2, min_cos):
     rows, cols = vcurr.shape[:2]
     out = np.zeros(27, np.float64)
-    n = load().orc_icp_accumulate(_p(vcurr), C.c_size_t(cols * 16), _p(ncurr), C.c_size_t(cols * 16), _p(vprev), C.c_size_t(cols * 16),
+    n = _fn("icp_accumulate")(_p(vcurr), C.c_size_t(cols * 16), _p(ncurr), C.c_size_t(cols * 16), _p(vprev), C.c_size_t(cols * 16),
                                   _p(nprev), C.c_size_t(cols * 16), cols, rows, intr(*K_level), aff(*T), C.c_float(dist2),
                                   C.c_float(min_cos), _p(out))
     return out, int(n)
@@ -184,7 +227,7 @@ def icp_accumulate(vcurr, ncurr, vprev, nprev, K_level, T, dist2, min_cos):
 def icp_solve_update(sums27, T):
     a = aff(*T)
     s = np.ascontiguousarray(sums27, np.float64)
-    ok = load().orc_icp_solve_update(_p(s), C.byref(a))
+    ok = _fn("icp_solve_update")(_p(s), C.byref(a))
     return bool(ok), (np.array(list(a.R), np.float32).reshape(3, 3), np.array(list(a.t), np.float32))
 
 
@@ -196,7 +239,7 @@ def icp_estimate(vcurr, ncurr, vprev, nprev, iters, K, dist_thres, angle_thres):
     pitch = (C.c_size_t * L)(*[x.shape[1] * 16 for x in vcurr])
     it = (C.c_int * L)(*iters[:L])
     a = Aff3f()
-    ok = load().orc_icp_estimate(arr(vcurr), arr(ncurr), arr(vprev), arr(nprev), cols, rows, pitch, L, it, intr(*K),
+    ok = _fn("icp_estimate")(arr(vcurr), arr(ncurr), arr(vprev), arr(nprev), cols, rows, pitch, L, it, intr(*K),
                                  C.c_float(dist_thres), C.c_float(angle_thres), C.byref(a))
     return bool(ok), (np.array(list(a.R), np.float32).reshape(3, 3), np.array(list(a.t), np.float32))
 
@@ -220,7 +263,7 @@ def knn8(nodes, queries):
     N, stride = q.shape
     idx = np.empty((N, 8), np.int32)
     d2 = np.empty((N, 8), np.float32)
-    load().orc_knn8(_p(nodes), len(nodes), _p(q), C.c_longlong(N), stride, _p(idx), _p(d2))
+    _fn("knn8")(_p(nodes), len(nodes), _p(q), C.c_longlong(N), stride, _p(idx), _p(d2))
     return idx, d2
 
 
@@ -229,13 +272,13 @@ def warp(nodes, points, normals, warp_to_live=None, flags=0):
     if warp_to_live is None:
         warp_to_live = (np.eye(3, dtype=np.float32), np.zeros(3, np.float32))
     N, stride = points.shape
-    load().orc_warp(_p(nodes), len(nodes), _p(points), _p(normals), C.c_longlong(N), stride, aff(*warp_to_live), flags)
+    _fn("warp")(_p(nodes), len(nodes), _p(points), _p(normals), C.c_longlong(N), stride, aff(*warp_to_live), flags)
 
 
 def node_translations(nodes) -> np.ndarray:
     out = np.empty((len(nodes), 4), np.float32)
     for i in range(len(nodes)):
-        load().orc_node_translation(C.c_void_p(nodes[i].ctypes.data), C.c_void_p(out[i].ctypes.data))
+        _fn("node_translation")(C.c_void_p(nodes[i].ctypes.data), C.c_void_p(out[i].ctypes.data))
     return out
 
 
@@ -244,5 +287,5 @@ def solve_data_term(nodes, canon, live, flags=0, lm_iters=5):
     l = np.ascontiguousarray(live, np.float32)
     N, stride = c.shape
     stats = np.zeros(4, np.float64)
-    load().orc_solve_data_term(_p(nodes), len(nodes), _p(c), _p(l), C.c_longlong(N), stride, flags, lm_iters, _p(stats))
+    _fn("solve_data_term")(_p(nodes), len(nodes), _p(c), _p(l), C.c_longlong(N), stride, flags, lm_iters, _p(stats))
     return stats
