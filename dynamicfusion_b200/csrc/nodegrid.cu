@@ -8,7 +8,7 @@ using namespace dfb;
 
 namespace {
 
-__global__ void __launch_bounds__(1024) build_node_grid_kernel(const float *__restrict__ nodes, int M, void *grid, int *cid_tmp)
+__global__ void __launch_bounds__(1024) build_node_grid_kernel(const float *__restrict__ nodes, int M, void *grid, int *cid_tmp, int *order, int *slot)
 {
     __shared__ float smin[3][32], smax[3][32];
     __shared__ NodeGridHeader h;
@@ -86,6 +86,35 @@ __global__ void __launch_bounds__(1024) build_node_grid_kernel(const float *__re
         const float *v = nodes + (size_t)i * DF_NODE_STRIDE;
         sorted[cell_start[cid] + rank] = make_float4(v[0], v[1], v[2], __int_as_float(i));
     }
+    // 5. spatial (Morton) order of the nodes for the solver: consecutive slots are neighbours in space, so a CTA that owns a
+    //    contiguous range of slots couples almost only to its own rows (solve.cu, v4).  order[rank] = node, slot[node] = rank.
+    if (order) {
+        __syncthreads();
+        const float q = h.inv_cell * (1024.f / (float)max(max(h.gx, h.gy), h.gz));
+        for (int i = t; i < M; i += 1024) {
+            const float *v = nodes + (size_t)i * DF_NODE_STRIDE;
+            unsigned c[3];
+            c[0] = (unsigned)min(max((int)((v[0] - h.ox) * q), 0), 1023);
+            c[1] = (unsigned)min(max((int)((v[1] - h.oy) * q), 0), 1023);
+            c[2] = (unsigned)min(max((int)((v[2] - h.oz) * q), 0), 1023);
+            unsigned key = 0;
+            for (int b = 0; b < 10; ++b)
+                for (int a = 0; a < 3; ++a) key |= ((c[a] >> b) & 1u) << (3 * b + a);
+            cid_tmp[i] = (int)key;
+        }
+        __syncthreads();
+        for (int i = t; i < M; i += 1024) {
+            const int key = cid_tmp[i];
+            int rank = 0;
+            for (int j = 0; j < M; ++j) { const int kj = cid_tmp[j]; rank += (kj < key) || (kj == key && j < i); }
+            order[rank] = i; slot[i] = rank;
+        }
+        if (t == 0) {
+            NodeGridHeader *hg = reinterpret_cast<NodeGridHeader *>(grid);
+            hg->pad[0] = (int)(reinterpret_cast<char *>(order) - reinterpret_cast<char *>(grid));
+            hg->pad[1] = (int)(reinterpret_cast<char *>(slot) - reinterpret_cast<char *>(grid));
+        }
+    }
 }
 
 }  // namespace
@@ -93,15 +122,21 @@ __global__ void __launch_bounds__(1024) build_node_grid_kernel(const float *__re
 extern "C" size_t df_node_grid_bytes(int M)
 {
     const size_t ncell = (size_t)NODEGRID_MAX_RES * NODEGRID_MAX_RES * NODEGRID_MAX_RES;
-    return 64 + (((ncell + 1) * 4 + 15) & ~(size_t)15) + (size_t)(M > 0 ? M : 1) * 16 + (size_t)(M > 0 ? M : 1) * 4 + 256;
+    const size_t m = (size_t)(M > 0 ? M : 1);
+    return 64 + (((ncell + 1) * 4 + 15) & ~(size_t)15) + m * 16 + 3 * ((m * 4 + 15) & ~(size_t)15) + 256;   // + cell ids, order, slot
 }
 
 extern "C" int df_build_node_grid(const float *nodes, int M, void *grid, void *stream)
 {
     if (M <= 0) return (int)cudaErrorInvalidValue;
-    // scratch for the per-node cell ids lives at the very end of the buffer
-    int *cid_tmp = reinterpret_cast<int *>(reinterpret_cast<char *>(grid) + df_node_grid_bytes(M) - (size_t)M * 4 - 128);
-    build_node_grid_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(nodes, M, grid, cid_tmp);
+    // three int[M] arrays at the very end of the buffer: scratch cell ids / Morton keys, order, slot
+    const size_t arr = ((size_t)M * 4 + 15) & ~(size_t)15;
+    char *tail = reinterpret_cast<char *>(grid) + df_node_grid_bytes(M) - 3 * arr - 128;
+    int *cid_tmp = reinterpret_cast<int *>(tail);
+    const bool want_order = M <= NODEGRID_ORDER_MAX_M;        // the ranking is O(M^2) in one block
+    int *order = want_order ? reinterpret_cast<int *>(tail + arr) : nullptr;
+    int *slot = want_order ? reinterpret_cast<int *>(tail + 2 * arr) : nullptr;
+    build_node_grid_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(nodes, M, grid, cid_tmp, order, slot);
     DF_LAUNCH_CHECK();
     return 0;
 }

@@ -174,25 +174,48 @@ __global__ void __launch_bounds__(256) solve_rows_kernel(SolveWs ws, int M, int 
     if (tid == 0) nlist = 0;
     __syncthreads();
     const int beg = ws.off[i], end = ws.off[i + 1];
+    const int lane = tid & 31;
     double g0 = 0.0, g1 = 0.0, g2 = 0.0;
-    for (int e = beg + tid; e < end; e += 256) {
-        const int entry = ws.inc[e];
-        const int v = entry >> 3;
-        const double wi = (double)ws.w[entry];
-        const float4 b = ws.b[v];
-        g0 += wi * (double)b.x; g1 += wi * (double)b.y; g2 += wi * (double)b.z;
-        const int4 ia = *reinterpret_cast<const int4 *>(ws.idx + (size_t)v * 8), ib = *reinterpret_cast<const int4 *>(ws.idx + (size_t)v * 8 + 4);
-        const float4 wa = *reinterpret_cast<const float4 *>(ws.w + (size_t)v * 8), wb = *reinterpret_cast<const float4 *>(ws.w + (size_t)v * 8 + 4);
-        const int js[8] = {ia.x, ia.y, ia.z, ia.w, ib.x, ib.y, ib.z, ib.w};
-        const float wj[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+    // Pixels that are far from the node cloud share one neighbour set, so a node on the rim of the cloud sees the SAME eight
+    // keys in (nearly) all of its incident entries: without aggregation 256 threads serialise on eight shared-memory words.
+    // Lanes of a warp holding the same key are summed first (match.any + shuffles) and only the group leader probes the hash.
+    for (int base = beg; base < end; base += 256) {
+        const int e = base + tid;
+        const bool valid = e < end;
+        double wi = 0.0;
+        int js[8];
+        float wj[8];
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) { js[kk] = -1; wj[kk] = 0.f; }
+        if (valid) {
+            const int entry = ws.inc[e];
+            const int v = entry >> 3;
+            wi = (double)ws.w[entry];
+            const float4 b = ws.b[v];
+            g0 += wi * (double)b.x; g1 += wi * (double)b.y; g2 += wi * (double)b.z;
+            const int4 ia = *reinterpret_cast<const int4 *>(ws.idx + (size_t)v * 8), ib = *reinterpret_cast<const int4 *>(ws.idx + (size_t)v * 8 + 4);
+            const float4 wa = *reinterpret_cast<const float4 *>(ws.w + (size_t)v * 8), wb = *reinterpret_cast<const float4 *>(ws.w + (size_t)v * 8 + 4);
+            js[0] = ia.x; js[1] = ia.y; js[2] = ia.z; js[3] = ia.w; js[4] = ib.x; js[5] = ib.y; js[6] = ib.z; js[7] = ib.w;
+            wj[0] = wa.x; wj[1] = wa.y; wj[2] = wa.z; wj[3] = wa.w; wj[4] = wb.x; wj[5] = wb.y; wj[6] = wb.z; wj[7] = wb.w;
+        }
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
             const int j = js[kk];
+            const double contrib = wi * (double)wj[kk];
+            const unsigned grp = __match_any_sync(0xffffffffu, j);
             if (j < 0) continue;
+            double sum = contrib;
+            if (grp == 0xffffffffu) {
+                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            } else if (grp & (grp - 1u)) {
+                sum = 0.0;
+                for (unsigned m = grp; m; m &= m - 1u) sum += __shfl_sync(grp, contrib, __ffs(m) - 1);
+            }
+            if (lane != __ffs(grp) - 1) continue;
             unsigned slot = ((unsigned)j * 2654435761u) & (HCAP - 1);
             for (int probe = 0; probe < HCAP; ++probe) {
                 const int prev = atomicCAS(&keys[slot], -1, j);
-                if (prev == -1 || prev == j) { atomicAdd(&vals[slot], wi * (double)wj[kk]); break; }
+                if (prev == -1 || prev == j) { atomicAdd(&vals[slot], sum); break; }
                 slot = (slot + 1) & (HCAP - 1);
                 if (probe == HCAP - 1) ws.flags[0] = 1;
             }
@@ -876,10 +899,274 @@ solve_lm_cluster_smem_kernel(float *nodes, int M, SolveWs ws, int nl_iters, int 
     (void)M3;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// v4: v3's residency (matrix slice + full-length copy of the multiplied vector in shared memory, 8-CTA cluster), with the
+// iteration's critical path shortened.  ncu of v3 (profiles/r01_solve_lm_v3_ncu_raw.csv): 19 % issue-active, warps waiting on
+// barriers (23 %), shared-memory round trips of the CG vectors (18 %), the DSMEM store queue (13 %) and fences (12 %).  Here
+//   * every CG vector element lives in the REGISTERS of the lane that owns the row (x, g, dl, r, p, damping, preconditioner):
+//     the vector updates touch no memory at all;
+//   * a cluster-wide sum is one __syncthreads + one cluster barrier: each CTA pushes its partial into all eight CTAs and
+//     everybody adds the eight values it received, in CTA order (bit-identical scalars in every CTA);
+//   * matrix entries are (double value, u16 column*3): 10 B instead of 12, so ~68 entries per row stay on chip at 2 k nodes
+//     (rows grow past 42 once the camera has moved away from the node cloud), and the vector copy is interleaved xyz.
+// The arithmetic and its order are v3's; the scalars, and therefore the iterates, are identical.
+constexpr int LM4_THREADS = 512;
+
+struct Lm4Smem {
+    double wpart[LM4_THREADS / 32][4];
+    double red_in[2][LMC_CTAS][4];
+};
+
+template <int NV>
+__device__ __forceinline__ void cluster_sum4(cg::cluster_group &cluster, Lm4Smem &sm, int &parity, int cta, double (&v)[NV])
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) sm.wpart[warp][k] = v[k];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double t = lane < LM4_THREADS / 32 ? sm.wpart[lane][k] : 0.0;
+            for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (lane < LMC_CTAS) *cluster.map_shared_rank(&sm.red_in[parity][cta][k], lane) = t;    // lane = destination CTA
+        }
+    }
+    cluster.sync();                                            // pushes of all CTAs have landed (release/acquire, cluster scope)
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double t = 0.0;
+#pragma unroll
+        for (int c = 0; c < LMC_CTAS; ++c) t += sm.red_in[parity][c][k];
+        v[k] = t;
+    }
+    parity ^= 1;                                               // the other buffer is free: its readers passed the barrier above
+}
+
+struct Lm4Layout {
+    int rpc, tpr, ent_cap;
+    size_t off_svec, off_val, off_col, total;
+};
+
+__host__ __device__ inline Lm4Layout lm4_layout(int M, int ent_cap)
+{
+    Lm4Layout L;
+    L.rpc = (M + LMC_CTAS - 1) / LMC_CTAS;
+    L.tpr = 1;
+    while (L.tpr < 32 && L.tpr * 2 * L.rpc <= LM4_THREADS) L.tpr *= 2;
+    L.ent_cap = ent_cap;
+    size_t o = 0;
+    L.off_svec = o; o += (size_t)3 * M * 8;
+    L.off_val = o; o += (size_t)ent_cap * LM4_THREADS * 8;
+    L.off_col = o; o += (((size_t)ent_cap * LM4_THREADS * 2) + 15) & ~(size_t)15;
+    L.total = o;
+    return L;
+}
+
+__global__ void __cluster_dims__(LMC_CTAS, 1, 1) __launch_bounds__(LM4_THREADS)
+solve_lm_v4_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_iters, int lin_iters, double *stats, int ent_cap)
+{
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ Lm4Smem sm;
+    extern __shared__ __align__(16) unsigned char dyn[];
+    const Lm4Layout L = lm4_layout(M, ent_cap);
+    double *svec = reinterpret_cast<double *>(dyn + L.off_svec);          // full-length copy of the multiplied vector, [3 * node + axis]
+    double *mval = reinterpret_cast<double *>(dyn + L.off_val);           // [entry][thread]
+    unsigned short *mcol = reinterpret_cast<unsigned short *>(dyn + L.off_col);   // 3 * column
+    const int rpc = L.rpc, tpr = L.tpr;
+
+    int parity = 0;
+    const int cta = (int)cluster.block_rank();
+    const int tid = threadIdx.x;
+    const int rl = tid / tpr, sub = tid % tpr;
+    // Rows are dealt to the CTAs in the node grid's Morton order (nodegrid.cu step 5): a CTA's rows are neighbours in space, so
+    // most of the columns they touch are the CTA's own rows and a row's search-direction entry is needed by few other CTAs.
+    const int *order = grid ? nodegrid_order(grid) : nullptr;
+    const int *slot = grid ? nodegrid_slot(grid) : nullptr;
+    const int s_row = cta * rpc + rl;                          // slot of this thread's row
+    const bool has_row = rl < rpc && s_row < M;
+    const int n = has_row ? (order ? order[s_row] : s_row) : 0;   // node index = row/column index of the normal matrix
+    const bool owner = has_row && sub == 0;
+
+    const int nnz = has_row ? ws.rownnz[n] : 0;
+    int my_ent = 0;
+    unsigned need = 0u;                                        // CTAs that own a row coupled to this one (A is structurally symmetric)
+    for (int e = sub; e < nnz; e += tpr) {
+        const int j = ws.col[(size_t)e * M + n];
+        need |= 1u << ((slot ? slot[j] : j) / rpc);
+        if (my_ent < ent_cap) {
+            mcol[my_ent * LM4_THREADS + tid] = (unsigned short)(3 * j);
+            mval[my_ent * LM4_THREADS + tid] = ws.val[(size_t)e * M + n];
+            ++my_ent;
+        }
+    }
+    for (int o = tpr >> 1; o > 0; o >>= 1) need |= __shfl_xor_sync(0xffffffffu, need, o);
+    need |= 1u << cta;
+    const int e_rest = sub + my_ent * tpr;                     // entries that did not fit are streamed from L2 (rare)
+    const double diag_n = has_row ? ws.diag[n] : 0.0;
+    double gb0 = 0.0, gb1 = 0.0, gb2 = 0.0;
+    if (owner) { gb0 = ws.gb[n]; gb1 = ws.gb[M + n]; gb2 = ws.gb[2 * M + n]; }
+
+    auto publish = [&](double a0, double a1, double a2) {      // this row's three values -> every CTA's svec
+        if (owner) {
+#pragma unroll
+            for (int c = 0; c < LMC_CTAS; ++c) {
+                if (!((need >> c) & 1u)) continue;
+                double *remote = cluster.map_shared_rank(svec, c) + 3 * n;
+                remote[0] = a0; remote[1] = a1; remote[2] = a2;
+            }
+        }
+    };
+    auto spmv = [&](double &o0, double &o1, double &o2) {      // (A * svec)[row], valid in the owner lane
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll 4
+        for (int k = 0; k < my_ent; ++k) {
+            const double *sv = svec + mcol[k * LM4_THREADS + tid];
+            const double a = mval[k * LM4_THREADS + tid];
+            a0 += a * sv[0]; a1 += a * sv[1]; a2 += a * sv[2];
+        }
+        for (int e = e_rest; e < nnz; e += tpr) {
+            const double *sv = svec + 3 * __ldg(ws.col + (size_t)e * M + n);
+            const double a = __ldg(ws.val + (size_t)e * M + n);
+            a0 += a * sv[0]; a1 += a * sv[1]; a2 += a * sv[2];
+        }
+        for (int o = tpr >> 1; o > 0; o >>= 1) {
+            a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+        }
+        o0 = a0; o1 = a1; o2 = a2;
+    };
+
+    // x0 = current node translations (CombinedSolver.h:165-172)
+    double x0 = 0.0, x1 = 0.0, x2 = 0.0;
+    if (owner) {
+        const float4 *n4 = reinterpret_cast<const float4 *>(nodes + (size_t)n * DF_NODE_STRIDE);
+        const float4 a = n4[0], b = n4[1], c = n4[2];
+        const Quat t = dq_translation(Quat{a.w, b.x, b.y, b.z}, Quat{b.w, c.x, c.y, c.z});
+        x0 = t.x; x1 = t.y; x2 = t.z;
+    }
+    const int T = LMC_CTAS * LM4_THREADS, gt = cta * LM4_THREADS + tid;
+    double c0n[3] = {0.0, 0.0, 0.0};
+    for (int i = gt; i < ws.prepare_blocks; i += T) { c0n[0] += ws.c0_partials[2 * i]; c0n[1] += ws.c0_partials[2 * i + 1]; }
+    c0n[2] = (owner ? (double)nnz : 0.0);
+    cluster.sync();                                            // every CTA is running: remote shared memory may be written
+    publish(x0, x1, x2);
+    cluster_sum4(cluster, sm, parity, cta, c0n);               // its barrier also completes the publish
+    const double nvalid = c0n[1], nnz_total = c0n[2];
+    double Ap0, Ap1, Ap2;
+    spmv(Ap0, Ap1, Ap2);
+    double t0[1] = {0.0};
+    if (owner) {
+        t0[0] += x0 * (0.5 * Ap0 - gb0);
+        t0[0] += x1 * (0.5 * Ap1 - gb1);
+        t0[0] += x2 * (0.5 * Ap2 - gb2);
+    }
+    cluster_sum4(cluster, sm, parity, cta, t0);
+    double cost = c0n[0] + t0[0];
+    const double cost0 = cost;
+
+    double radius = 1e4, decrease = 2.0;                       // solverGPUGaussNewton.t:26-39
+    int it = 0, pcg_total = 0;
+    for (; it < nl_iters; ++it) {
+        spmv(Ap0, Ap1, Ap2);                                   // svec holds x here
+        double rzv[1] = {0.0};
+        double cdn = 0.0, mi = 0.0;
+        double g0 = 0.0, g1 = 0.0, g2 = 0.0, dl0 = 0.0, dl1 = 0.0, dl2 = 0.0, r0 = 0.0, r1 = 0.0, r2 = 0.0, p0 = 0.0, p1 = 0.0, p2 = 0.0;
+        if (owner) {
+            cdn = fmin(fmax(diag_n, 1e-6), 1e32) / radius;
+            mi = 1.0 / (diag_n + cdn);
+            g0 = gb0 - Ap0; g1 = gb1 - Ap1; g2 = gb2 - Ap2;
+            r0 = g0; r1 = g1; r2 = g2;
+            p0 = g0 * mi; p1 = g1 * mi; p2 = g2 * mi;
+            rzv[0] += g0 * p0; rzv[0] += g1 * p1; rzv[0] += g2 * p2;
+        }
+        cluster.sync();                                        // every CTA finished reading svec (x) before p overwrites it
+        publish(p0, p1, p2);
+        cluster_sum4(cluster, sm, parity, cta, rzv);
+        double rz = rzv[0];
+        double Q0 = 0.0;
+        for (int l = 0; l < lin_iters && rz > 0.0; ++l) {
+            spmv(Ap0, Ap1, Ap2);
+            double pap[1] = {0.0};
+            if (owner) {
+                Ap0 = Ap0 + cdn * p0; Ap1 = Ap1 + cdn * p1; Ap2 = Ap2 + cdn * p2;
+                pap[0] += p0 * Ap0; pap[0] += p1 * Ap1; pap[0] += p2 * Ap2;
+            }
+            cluster_sum4(cluster, sm, parity, cta, pap);       // barrier: every CTA finished reading svec (p)
+            if (!(pap[0] > 0.0)) break;
+            const double alpha = rz / pap[0];
+            double rq[2] = {0.0, 0.0};
+            double z0 = 0.0, z1 = 0.0, z2 = 0.0;
+            if (owner) {
+                dl0 = dl0 + alpha * p0; r0 = r0 - alpha * Ap0; z0 = r0 * mi; rq[0] += r0 * z0; rq[1] += dl0 * (r0 + g0);
+                dl1 = dl1 + alpha * p1; r1 = r1 - alpha * Ap1; z1 = r1 * mi; rq[0] += r1 * z1; rq[1] += dl1 * (r1 + g1);
+                dl2 = dl2 + alpha * p2; r2 = r2 - alpha * Ap2; z2 = r2 * mi; rq[0] += r2 * z2; rq[1] += dl2 * (r2 + g2);
+            }
+            cluster_sum4(cluster, sm, parity, cta, rq);
+            const double rz_new = rq[0], Q1 = -0.5 * rq[1];
+            const double beta = rz_new / rz;
+            if (owner) { p0 = z0 + beta * p0; p1 = z1 + beta * p1; p2 = z2 + beta * p2; }
+            rz = rz_new;
+            ++pcg_total;
+            const double zeta = (double)(l + 1) * (Q1 - Q0) / Q1;   // Ceres/Opt q-tolerance, solverGPUGaussNewton.t:1093-1101
+            Q0 = Q1;
+            publish(p0, p1, p2);
+            cluster.sync();                                    // publish complete everywhere
+            if (zeta < 1e-4) break;
+        }
+        // model change = 0.5 dl.(g + r + C dl);  A dl = g - r - C dl  => new cost = cost - dl.g + 0.5 dl.(A dl)
+        double mad[3] = {0.0, 0.0, 0.0};
+        if (owner) {
+            double c;
+            c = cdn * dl0; mad[0] += dl0 * (g0 + r0 + c); mad[1] += dl0 * (g0 - r0 - c); mad[2] += dl0 * g0;
+            c = cdn * dl1; mad[0] += dl1 * (g1 + r1 + c); mad[1] += dl1 * (g1 - r1 - c); mad[2] += dl1 * g1;
+            c = cdn * dl2; mad[0] += dl2 * (g2 + r2 + c); mad[1] += dl2 * (g2 - r2 - c); mad[2] += dl2 * g2;
+        }
+        cluster_sum4(cluster, sm, parity, cta, mad);
+        const double model = 0.5 * mad[0];
+        const double new_cost = cost - mad[2] + 0.5 * mad[1];
+        const double change = cost - new_cost;
+        const double rho = model > 0.0 ? change / model : 0.0;
+        bool stop = false;
+        if (change >= 0.0 && rho > 1e-3) {
+            if (owner) { x0 += dl0; x1 += dl1; x2 += dl2; }
+            stop = change <= cost * 1e-6;                       // function_tolerance, CombinedSolver.h:88
+            cost = new_cost;
+            const double f = 1.0 - (2.0 * rho - 1.0) * (2.0 * rho - 1.0) * (2.0 * rho - 1.0);
+            radius /= fmax(f, 1.0 / 3.0);
+            radius = fmin(radius, 1e16);
+            decrease = 2.0;
+        } else {
+            radius /= decrease; decrease *= 2.0;
+            if (radius <= 1e-32) stop = true;
+        }
+        if (stop) { ++it; break; }
+        publish(x0, x1, x2);                                   // svec <- x for the next linearisation (all CTAs passed the barrier
+        cluster.sync();                                        //  inside cluster_sum4(mad), so nobody still reads p from svec)
+    }
+    cluster.sync();                                            // no CTA may exit while others can still write into its shared memory
+    // write back: encodeTranslation (CombinedSolver.h:189-197, dual_quaternion.hpp:82-85)
+    if (owner) {
+        float *nd = nodes + (size_t)n * DF_NODE_STRIDE;
+        const Quat rot = {nd[3], nd[4], nd[5], nd[6]};
+        const Quat h = qhalf(Quat{0.f, (float)x0, (float)x1, (float)x2});
+        const Quat d = qmul(h, rot);
+        nd[7] = d.w; nd[8] = d.x; nd[9] = d.y; nd[10] = d.z;
+    }
+    if (gt == 0 && stats) {
+        stats[0] = cost0; stats[1] = cost; stats[2] = (double)it; stats[3] = nvalid; stats[4] = (double)pcg_total; stats[5] = (double)ws.flags[0];
+        stats[6] = nnz_total;
+    }
+}
+
 int solve_lm_impl()
 {
     static int impl = -1;
-    if (impl < 0) { const char *e = getenv("DF_SOLVE_LM_IMPL"); impl = e ? atoi(e) : 3; }
+    if (impl < 0) { const char *e = getenv("DF_SOLVE_LM_IMPL"); impl = e ? atoi(e) : 4; }
     return impl;
 }
 
@@ -920,7 +1207,16 @@ extern "C" int df_solve_data_term(float *nodes, int M, const void *node_grid, co
     DF_LAUNCH_CHECK();
     const size_t smem_budget = 200 * 1024;
     const LmSmemLayout L0 = lm_layout(M, 0);
-    if (solve_lm_impl() >= 3 && L0.total + (size_t)LM3_THREADS * 12 <= smem_budget) {
+    const size_t smem4_budget = 224 * 1024;
+    const Lm4Layout L40 = lm4_layout(M, 0);
+    if (solve_lm_impl() >= 4 && L40.rpc * L40.tpr <= LM4_THREADS && L40.total + (size_t)LM4_THREADS * 10 * 8 <= smem4_budget) {
+        const int ent_cap = (int)((smem4_budget - L40.total - 16) / ((size_t)LM4_THREADS * 10));
+        const Lm4Layout L = lm4_layout(M, ent_cap);
+        static bool attr4 = false;
+        if (!attr4) { cudaFuncSetAttribute(solve_lm_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4_budget); attr4 = true; }
+        solve_lm_v4_kernel<<<LMC_CTAS, LM4_THREADS, L.total, s>>>(nodes, M, node_grid, ws, nonlinear_iters, linear_iters, stats_dev, ent_cap);
+    }
+    else if (solve_lm_impl() >= 3 && L0.rpc * L0.tpr <= LM3_THREADS && L0.total + (size_t)LM3_THREADS * 12 <= smem_budget) {
         const int ent_cap = (int)((smem_budget - L0.total) / ((size_t)LM3_THREADS * 12));
         const LmSmemLayout L = lm_layout(M, ent_cap);
         static bool attr3 = false;

@@ -56,16 +56,23 @@ __device__ __forceinline__ void knn8_scan(const float *__restrict__ nodes, int M
 // shells of cells around its own cell until the 8 best cannot be beaten any more.  Candidates are ranked by
 // (squared distance, node index), so the result is exactly the exhaustive scan's (knn8_scan) whatever the visiting order.
 constexpr int NODEGRID_MAX_RES = 64;
+constexpr int NODEGRID_ORDER_MAX_M = 8192;
 
 struct NodeGridHeader {
     float ox, oy, oz, cell, inv_cell;
     int gx, gy, gz, M, ncell;
-    int pad[6];
+    int pad[6];            // pad[0], pad[1]: byte offsets of the Morton order[] / slot[] arrays (0 = absent)
 };   // 64 bytes, followed by: int cell_start[ncell + 1] (padded to 16 B), float4 sorted[M] = (x, y, z, index bits)
 
 __device__ __forceinline__ const int *nodegrid_cell_start(const void *grid) { return reinterpret_cast<const int *>(reinterpret_cast<const char *>(grid) + 64); }
 __device__ __forceinline__ const float4 *nodegrid_sorted(const void *grid, int ncell)
 { return reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(grid) + 64 + (((size_t)(ncell + 1) * 4 + 15) & ~(size_t)15)); }
+
+// Morton ordering of the nodes (nodegrid.cu step 5): order[rank] = node index, slot[node] = rank; nullptr when absent
+__device__ __forceinline__ const int *nodegrid_order(const void *grid)
+{ const int o = reinterpret_cast<const NodeGridHeader *>(grid)->pad[0]; return o ? reinterpret_cast<const int *>(reinterpret_cast<const char *>(grid) + o) : nullptr; }
+__device__ __forceinline__ const int *nodegrid_slot(const void *grid)
+{ const int o = reinterpret_cast<const NodeGridHeader *>(grid)->pad[1]; return o ? reinterpret_cast<const int *>(reinterpret_cast<const char *>(grid) + o) : nullptr; }
 
 __device__ __forceinline__ void knn8_insert_lex(int (&bi)[8], float (&bd)[8], float dist, int idx)
 {
@@ -81,6 +88,13 @@ __device__ __forceinline__ void knn8_insert_lex(int (&bi)[8], float (&bd)[8], fl
     }
 }
 
+// Shell walks are cheap while the query is within a few cells of the nodes; a query far outside the node cloud (the reference
+// feeds camera-frame points to a world-frame field, kinfu.cpp:356-361, so this is the common case once the camera has moved)
+// would visit thousands of empty cells.  After KNN_SHELL_CAP shells without a certified result the query is answered by one
+// exhaustive pass over the (cell-sorted) node array instead: every lane of a warp reads the same node, so the loads are
+// broadcasts.  Both paths rank by (distance, index): the result does not depend on which one ran.
+constexpr int KNN_SHELL_CAP = 3;
+
 __device__ __forceinline__ void knn8_grid(const void *__restrict__ grid, bool valid, float qx, float qy, float qz, int (&bi)[8], float (&bd)[8])
 {
 #pragma unroll
@@ -93,13 +107,15 @@ __device__ __forceinline__ void knn8_grid(const void *__restrict__ grid, bool va
         const int cy = min(max((int)floorf((qy - h.oy) * h.inv_cell), 0), h.gy - 1);
         const int cz = min(max((int)floorf((qz - h.oz) * h.inv_cell), 0), h.gz - 1);
         const int rmax = max(max(h.gx, h.gy), h.gz);
+        bool done = false;
         for (int r = 0; r <= rmax; ++r) {
             // shells 0..r-1 are done: every unvisited node sits in a cell at Chebyshev distance >= r from (cx,cy,cz), i.e. at
             // least (r-1)*cell away from the query (the query lies anywhere inside its own, possibly clamped, cell)
             if (r >= 2 && bi[7] != 0x7fffffff) {
                 const float bound = (float)(r - 1) * h.cell * 0.999f;
-                if (bound * bound > bd[7]) break;
+                if (bound * bound > bd[7]) { done = true; break; }
             }
+            if (r > KNN_SHELL_CAP) break;
             for (int z = cz - r; z <= cz + r; ++z) {
                 if (z < 0 || z >= h.gz) continue;
                 for (int y = cy - r; y <= cy + r; ++y) {
@@ -117,6 +133,17 @@ __device__ __forceinline__ void knn8_grid(const void *__restrict__ grid, bool va
                         }
                     }
                 }
+            }
+            if (r == rmax) done = true;                       // every cell has been visited
+        }
+        if (!done) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { bi[i] = 0x7fffffff; bd[i] = 3.402823466e+38f; }
+#pragma unroll 4
+            for (int it = 0; it < h.M; ++it) {
+                const float4 nd = __ldg(sorted + it);
+                const float d0 = qx - nd.x, d1 = qy - nd.y, d2 = qz - nd.z;
+                knn8_insert_lex(bi, bd, d0 * d0 + d1 * d1 + d2 * d2, __float_as_int(nd.w));
             }
         }
     }

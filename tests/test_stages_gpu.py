@@ -125,6 +125,10 @@ def test_knn_and_warp(orc, M, N):
     pts[::13, 0] = np.nan
     nrm[::17, 0] = np.nan
     pts[1, :3] = nodes[min(10, M - 1), :3]               # query exactly on a (possibly duplicated) node
+    # a third of the queries far outside the node cloud (up to ~1.5 m away, whole warps of them and isolated ones): the grid
+    # walk gives up after a few shells and answers them by an exhaustive pass -- same (distance, index) ranking
+    far = np.zeros(N, bool); far[N // 2: N // 2 + N // 3] = True; far[5::97] = True
+    pts[far, :3] += rng.uniform(0.4, 0.9, (int(far.sum()), 3)).astype(np.float32) * rng.choice([-1.0, 1.0], (int(far.sum()), 3)).astype(np.float32)
     ridx, rd2 = orc.knn8(nodes, pts)
     for use_grid in (False, True):                       # exhaustive shared-memory scan and uniform node grid: identical results
         wf = host.WarpField(use_grid=use_grid)
