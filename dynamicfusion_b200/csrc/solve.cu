@@ -1163,10 +1163,300 @@ solve_lm_v4_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// v5: v4 with every cluster barrier inside the iteration replaced by transaction barriers.  ncu of v4 (source view,
+// profiles/r01_late_frame_kernels_ncu_raw.csv): a third of the stall samples sit on the barrier's MEMBAR.ALL.GPU / ERRBAR /
+// UCGABAR_WAIT and a quarter on the generic remote stores that the barrier's release fence has to drain (lg_throttle).
+// Here a remote write is a `st.async` that carries its own completion: it lands in the destination CTA's shared memory and
+// decrements the transaction count of an mbarrier there.  A CTA that has received all the bytes it expects simply goes on:
+//   * cluster-wide sum: warp 0 sends the CTA's partial to all eight CTAs (8 x NV x 8 B expected per CTA), two mbarriers used
+//     alternately (a fast CTA can be one reduction ahead, never two: it needs my next partial first);
+//   * vector exchange: the owner lane sends its row's three values to the CTAs in its need-mask; the byte count every CTA will
+//     receive is fixed by the sparsity pattern and is established once with an ordinary all-reduce;
+//   * write-after-read safety comes for free: a partial is computed FROM the shared-memory reads of the mat-vec, so whoever has
+//     received everybody's partial knows that everybody has finished reading the vector it is about to overwrite.
+// No fence, no cluster barrier, no L1 flush inside the LM/PCG iteration; the arithmetic and its order are v4's.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect(uint32_t bar, uint32_t bytes)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile("{\n\t.reg .pred P1;\n\tLAB_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t@P1 bra DONE;\n\tbra LAB_WAIT;\n\tDONE:\n\t}"
+                 ::"r"(bar), "r"(parity), "r"(0x989680) : "memory");
+}
+__device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uint32_t remote_bar)
+{
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr), "l"(__double_as_longlong(v)), "r"(remote_bar) : "memory");
+}
+
+struct Lm5Smem {
+    double wpart[LM4_THREADS / 32][8];
+    double red_in[2][LMC_CTAS][8];
+    unsigned long long bar_red[2];
+    unsigned long long bar_pub;
+};
+
+struct Lm5Sync { int parity; uint32_t phase_red[2]; uint32_t phase_pub; };
+
+template <int NV>
+__device__ __forceinline__ void cluster_sum5(Lm5Smem &sm, Lm5Sync &sy, int cta, double (&v)[NV])
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int par = sy.parity;
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) sm.wpart[warp][k] = v[k];
+    }
+    __syncthreads();
+    const uint32_t bar = smem_u32(&sm.bar_red[par]);
+    if (warp == 0) {
+        const uint32_t rbar = mapa_u32(bar, (uint32_t)(lane & (LMC_CTAS - 1)));
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double t = lane < LM4_THREADS / 32 ? sm.wpart[lane][k] : 0.0;
+            for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (lane < LMC_CTAS) st_async_f64(mapa_u32(smem_u32(&sm.red_in[par][cta][k]), (uint32_t)lane), t, rbar);   // lane = destination CTA
+        }
+        if (lane == 0) mbar_arrive_expect(bar, (uint32_t)(LMC_CTAS * NV * 8));
+    }
+    mbar_wait(bar, sy.phase_red[par]);
+    sy.phase_red[par] ^= 1u;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double t = 0.0;
+#pragma unroll
+        for (int c = 0; c < LMC_CTAS; ++c) t += sm.red_in[par][c][k];
+        v[k] = t;
+    }
+    sy.parity = par ^ 1;
+}
+
+__global__ void __cluster_dims__(LMC_CTAS, 1, 1) __launch_bounds__(LM4_THREADS)
+solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_iters, int lin_iters, double *stats, int ent_cap)
+{
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ Lm5Smem sm;
+    extern __shared__ __align__(16) unsigned char dyn[];
+    const Lm4Layout L = lm4_layout(M, ent_cap);
+    double *svec = reinterpret_cast<double *>(dyn + L.off_svec);          // full-length copy of the multiplied vector, [3 * node + axis]
+    double *mval = reinterpret_cast<double *>(dyn + L.off_val);           // [entry][thread]
+    unsigned short *mcol = reinterpret_cast<unsigned short *>(dyn + L.off_col);   // 3 * column
+    const int rpc = L.rpc, tpr = L.tpr;
+
+    Lm5Sync sy; sy.parity = 0; sy.phase_red[0] = sy.phase_red[1] = 0u; sy.phase_pub = 0u;
+    const int cta = (int)cluster.block_rank();
+    const int tid = threadIdx.x;
+    const int rl = tid / tpr, sub = tid % tpr;
+    // Rows are dealt to the CTAs in the node grid's Morton order (nodegrid.cu step 5): a CTA's rows are neighbours in space, so
+    // most of the columns they touch are the CTA's own rows and a row's search-direction entry is needed by few other CTAs.
+    const int *order = grid ? nodegrid_order(grid) : nullptr;
+    const int *slot = grid ? nodegrid_slot(grid) : nullptr;
+    const int s_row = cta * rpc + rl;                          // slot of this thread's row
+    const bool has_row = rl < rpc && s_row < M;
+    const int n = has_row ? (order ? order[s_row] : s_row) : 0;   // node index = row/column index of the normal matrix
+    const bool owner = has_row && sub == 0;
+
+    const int nnz = has_row ? ws.rownnz[n] : 0;
+    int my_ent = 0;
+    unsigned need = 0u;                                        // CTAs that own a row coupled to this one (A is structurally symmetric)
+    for (int e = sub; e < nnz; e += tpr) {
+        const int j = ws.col[(size_t)e * M + n];
+        need |= 1u << ((slot ? slot[j] : j) / rpc);
+        if (my_ent < ent_cap) {
+            mcol[my_ent * LM4_THREADS + tid] = (unsigned short)(3 * j);
+            mval[my_ent * LM4_THREADS + tid] = ws.val[(size_t)e * M + n];
+            ++my_ent;
+        }
+    }
+    for (int o = tpr >> 1; o > 0; o >>= 1) need |= __shfl_xor_sync(0xffffffffu, need, o);
+    need |= 1u << cta;
+    const int e_rest = sub + my_ent * tpr;                     // entries that did not fit are streamed from L2 (rare)
+    const double diag_n = has_row ? ws.diag[n] : 0.0;
+    double gb0 = 0.0, gb1 = 0.0, gb2 = 0.0;
+    if (owner) { gb0 = ws.gb[n]; gb1 = ws.gb[M + n]; gb2 = ws.gb[2 * M + n]; }
+
+    const uint32_t svec_addr = smem_u32(svec), pub_bar = smem_u32(&sm.bar_pub);
+    uint32_t pub_bytes = 0;                                    // bytes this CTA receives per exchange (set once below)
+    // this row's three values -> the svec of every CTA that multiplies by them; then wait until this CTA's own svec is complete
+    auto publish = [&](double a0, double a1, double a2) {
+        if (owner) {
+#pragma unroll
+            for (int c = 0; c < LMC_CTAS; ++c) {
+                if (!((need >> c) & 1u)) continue;
+                const uint32_t dst = mapa_u32(svec_addr + 24u * (uint32_t)n, (uint32_t)c), rb = mapa_u32(pub_bar, (uint32_t)c);
+                st_async_f64(dst, a0, rb); st_async_f64(dst + 8u, a1, rb); st_async_f64(dst + 16u, a2, rb);
+            }
+        }
+        if (tid == 0) mbar_arrive_expect(pub_bar, pub_bytes);
+        mbar_wait(pub_bar, sy.phase_pub);
+        sy.phase_pub ^= 1u;
+    };
+    auto spmv = [&](double &o0, double &o1, double &o2) {      // (A * svec)[row], valid in the owner lane
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll 4
+        for (int k = 0; k < my_ent; ++k) {
+            const double *sv = svec + mcol[k * LM4_THREADS + tid];
+            const double a = mval[k * LM4_THREADS + tid];
+            a0 += a * sv[0]; a1 += a * sv[1]; a2 += a * sv[2];
+        }
+        for (int e = e_rest; e < nnz; e += tpr) {
+            const double *sv = svec + 3 * __ldg(ws.col + (size_t)e * M + n);
+            const double a = __ldg(ws.val + (size_t)e * M + n);
+            a0 += a * sv[0]; a1 += a * sv[1]; a2 += a * sv[2];
+        }
+        for (int o = tpr >> 1; o > 0; o >>= 1) {
+            a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+        }
+        o0 = a0; o1 = a1; o2 = a2;
+    };
+
+    // x0 = current node translations (CombinedSolver.h:165-172)
+    double x0 = 0.0, x1 = 0.0, x2 = 0.0;
+    if (owner) {
+        const float4 *n4 = reinterpret_cast<const float4 *>(nodes + (size_t)n * DF_NODE_STRIDE);
+        const float4 a = n4[0], b = n4[1], c = n4[2];
+        const Quat t = dq_translation(Quat{a.w, b.x, b.y, b.z}, Quat{b.w, c.x, c.y, c.z});
+        x0 = t.x; x1 = t.y; x2 = t.z;
+    }
+    const int T = LMC_CTAS * LM4_THREADS, gt = cta * LM4_THREADS + tid;
+    double c0n[3] = {0.0, 0.0, 0.0};
+    for (int i = gt; i < ws.prepare_blocks; i += T) { c0n[0] += ws.c0_partials[2 * i]; c0n[1] += ws.c0_partials[2 * i + 1]; }
+    c0n[2] = (owner ? (double)nnz : 0.0);
+    if (tid == 0) {
+        mbar_init(smem_u32(&sm.bar_red[0]), 1u); mbar_init(smem_u32(&sm.bar_red[1]), 1u); mbar_init(pub_bar, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cluster.sync();                                            // every CTA is running, its barriers are initialised
+    {   // how many rows will send to me: all-reduce of the per-destination row counts
+        double cnt[LMC_CTAS];
+#pragma unroll
+        for (int c = 0; c < LMC_CTAS; ++c) cnt[c] = (owner && ((need >> c) & 1u)) ? 1.0 : 0.0;
+        cluster_sum5(sm, sy, cta, cnt);
+        double mine = 0.0;
+#pragma unroll
+        for (int c = 0; c < LMC_CTAS; ++c) if (c == cta) mine = cnt[c];
+        pub_bytes = 24u * (uint32_t)mine;
+    }
+    publish(x0, x1, x2);
+    cluster_sum5(sm, sy, cta, c0n);
+    const double nvalid = c0n[1], nnz_total = c0n[2];
+    double Ap0, Ap1, Ap2;
+    spmv(Ap0, Ap1, Ap2);
+    double t0[1] = {0.0};
+    if (owner) {
+        t0[0] += x0 * (0.5 * Ap0 - gb0);
+        t0[0] += x1 * (0.5 * Ap1 - gb1);
+        t0[0] += x2 * (0.5 * Ap2 - gb2);
+    }
+    cluster_sum5(sm, sy, cta, t0);
+    double cost = c0n[0] + t0[0];
+    const double cost0 = cost;
+
+    double radius = 1e4, decrease = 2.0;                       // solverGPUGaussNewton.t:26-39
+    int it = 0, pcg_total = 0;
+    for (; it < nl_iters; ++it) {
+        spmv(Ap0, Ap1, Ap2);                                   // svec holds x here
+        double rzv[1] = {0.0};
+        double cdn = 0.0, mi = 0.0;
+        double g0 = 0.0, g1 = 0.0, g2 = 0.0, dl0 = 0.0, dl1 = 0.0, dl2 = 0.0, r0 = 0.0, r1 = 0.0, r2 = 0.0, p0 = 0.0, p1 = 0.0, p2 = 0.0;
+        if (owner) {
+            cdn = fmin(fmax(diag_n, 1e-6), 1e32) / radius;
+            mi = 1.0 / (diag_n + cdn);
+            g0 = gb0 - Ap0; g1 = gb1 - Ap1; g2 = gb2 - Ap2;
+            r0 = g0; r1 = g1; r2 = g2;
+            p0 = g0 * mi; p1 = g1 * mi; p2 = g2 * mi;
+            rzv[0] += g0 * p0; rzv[0] += g1 * p1; rzv[0] += g2 * p2;
+        }
+        cluster_sum5(sm, sy, cta, rzv);                        // completes only when every CTA has finished reading svec (x) ...
+        publish(p0, p1, p2);                                   // ... so p may overwrite it
+        double rz = rzv[0];
+        double Q0 = 0.0;
+        for (int l = 0; l < lin_iters && rz > 0.0; ++l) {
+            spmv(Ap0, Ap1, Ap2);
+            double pap[1] = {0.0};
+            if (owner) {
+                Ap0 = Ap0 + cdn * p0; Ap1 = Ap1 + cdn * p1; Ap2 = Ap2 + cdn * p2;
+                pap[0] += p0 * Ap0; pap[0] += p1 * Ap1; pap[0] += p2 * Ap2;
+            }
+            cluster_sum5(sm, sy, cta, pap);                    // every CTA finished reading svec (p)
+            if (!(pap[0] > 0.0)) break;
+            const double alpha = rz / pap[0];
+            double rq[2] = {0.0, 0.0};
+            double z0 = 0.0, z1 = 0.0, z2 = 0.0;
+            if (owner) {
+                dl0 = dl0 + alpha * p0; r0 = r0 - alpha * Ap0; z0 = r0 * mi; rq[0] += r0 * z0; rq[1] += dl0 * (r0 + g0);
+                dl1 = dl1 + alpha * p1; r1 = r1 - alpha * Ap1; z1 = r1 * mi; rq[0] += r1 * z1; rq[1] += dl1 * (r1 + g1);
+                dl2 = dl2 + alpha * p2; r2 = r2 - alpha * Ap2; z2 = r2 * mi; rq[0] += r2 * z2; rq[1] += dl2 * (r2 + g2);
+            }
+            cluster_sum5(sm, sy, cta, rq);
+            const double rz_new = rq[0], Q1 = -0.5 * rq[1];
+            const double beta = rz_new / rz;
+            if (owner) { p0 = z0 + beta * p0; p1 = z1 + beta * p1; p2 = z2 + beta * p2; }
+            rz = rz_new;
+            ++pcg_total;
+            const double zeta = (double)(l + 1) * (Q1 - Q0) / Q1;   // Ceres/Opt q-tolerance, solverGPUGaussNewton.t:1093-1101
+            Q0 = Q1;
+            publish(p0, p1, p2);
+            if (zeta < 1e-4) break;
+        }
+        // model change = 0.5 dl.(g + r + C dl);  A dl = g - r - C dl  => new cost = cost - dl.g + 0.5 dl.(A dl)
+        double mad[3] = {0.0, 0.0, 0.0};
+        if (owner) {
+            double c;
+            c = cdn * dl0; mad[0] += dl0 * (g0 + r0 + c); mad[1] += dl0 * (g0 - r0 - c); mad[2] += dl0 * g0;
+            c = cdn * dl1; mad[0] += dl1 * (g1 + r1 + c); mad[1] += dl1 * (g1 - r1 - c); mad[2] += dl1 * g1;
+            c = cdn * dl2; mad[0] += dl2 * (g2 + r2 + c); mad[1] += dl2 * (g2 - r2 - c); mad[2] += dl2 * g2;
+        }
+        cluster_sum5(sm, sy, cta, mad);
+        const double model = 0.5 * mad[0];
+        const double new_cost = cost - mad[2] + 0.5 * mad[1];
+        const double change = cost - new_cost;
+        const double rho = model > 0.0 ? change / model : 0.0;
+        bool stop = false;
+        if (change >= 0.0 && rho > 1e-3) {
+            if (owner) { x0 += dl0; x1 += dl1; x2 += dl2; }
+            stop = change <= cost * 1e-6;                       // function_tolerance, CombinedSolver.h:88
+            cost = new_cost;
+            const double f = 1.0 - (2.0 * rho - 1.0) * (2.0 * rho - 1.0) * (2.0 * rho - 1.0);
+            radius /= fmax(f, 1.0 / 3.0);
+            radius = fmin(radius, 1e16);
+            decrease = 2.0;
+        } else {
+            radius /= decrease; decrease *= 2.0;
+            if (radius <= 1e-32) stop = true;
+        }
+        if (stop) { ++it; break; }
+        publish(x0, x1, x2);                                   // svec <- x for the next linearisation (the mad reduction proves nobody reads p any more)
+    }
+    cluster.sync();                                            // no CTA may exit while others can still write into its shared memory
+    // write back: encodeTranslation (CombinedSolver.h:189-197, dual_quaternion.hpp:82-85)
+    if (owner) {
+        float *nd = nodes + (size_t)n * DF_NODE_STRIDE;
+        const Quat rot = {nd[3], nd[4], nd[5], nd[6]};
+        const Quat h = qhalf(Quat{0.f, (float)x0, (float)x1, (float)x2});
+        const Quat d = qmul(h, rot);
+        nd[7] = d.w; nd[8] = d.x; nd[9] = d.y; nd[10] = d.z;
+    }
+    if (gt == 0 && stats) {
+        stats[0] = cost0; stats[1] = cost; stats[2] = (double)it; stats[3] = nvalid; stats[4] = (double)pcg_total; stats[5] = (double)ws.flags[0];
+        stats[6] = nnz_total;
+    }
+}
+
 int solve_lm_impl()
 {
     static int impl = -1;
-    if (impl < 0) { const char *e = getenv("DF_SOLVE_LM_IMPL"); impl = e ? atoi(e) : 4; }
+    if (impl < 0) { const char *e = getenv("DF_SOLVE_LM_IMPL"); impl = e ? atoi(e) : 5; }
     return impl;
 }
 
@@ -1214,7 +1504,12 @@ extern "C" int df_solve_data_term(float *nodes, int M, const void *node_grid, co
         const Lm4Layout L = lm4_layout(M, ent_cap);
         static bool attr4 = false;
         if (!attr4) { cudaFuncSetAttribute(solve_lm_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4_budget); attr4 = true; }
-        solve_lm_v4_kernel<<<LMC_CTAS, LM4_THREADS, L.total, s>>>(nodes, M, node_grid, ws, nonlinear_iters, linear_iters, stats_dev, ent_cap);
+        if (solve_lm_impl() >= 5) {
+            static bool attr5 = false;
+            if (!attr5) { cudaFuncSetAttribute(solve_lm_v5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4_budget); attr5 = true; }
+            solve_lm_v5_kernel<<<LMC_CTAS, LM4_THREADS, L.total, s>>>(nodes, M, node_grid, ws, nonlinear_iters, linear_iters, stats_dev, ent_cap);
+        } else
+            solve_lm_v4_kernel<<<LMC_CTAS, LM4_THREADS, L.total, s>>>(nodes, M, node_grid, ws, nonlinear_iters, linear_iters, stats_dev, ent_cap);
     }
     else if (solve_lm_impl() >= 3 && L0.rpc * L0.tpr <= LM3_THREADS && L0.total + (size_t)LM3_THREADS * 12 <= smem_budget) {
         const int ent_cap = (int)((smem_budget - L0.total) / ((size_t)LM3_THREADS * 12));
