@@ -8,7 +8,8 @@ using namespace dfb;
 
 namespace {
 
-__global__ void __launch_bounds__(1024) build_node_grid_kernel(const float *__restrict__ nodes, int M, void *grid, int *cid_tmp, int *order, int *slot)
+__global__ void __launch_bounds__(1024) build_node_grid_kernel(const float *__restrict__ nodes, int M, void *grid, int *cid_tmp, int *order, int *slot,
+                                                               float4 *bvh_box, float4 *bvh_leaf, int L)
 {
     __shared__ float smin[3][32], smax[3][32];
     __shared__ NodeGridHeader h;
@@ -114,16 +115,64 @@ __global__ void __launch_bounds__(1024) build_node_grid_kernel(const float *__re
             hg->pad[0] = (int)(reinterpret_cast<char *>(order) - reinterpret_cast<char *>(grid));
             hg->pad[1] = (int)(reinterpret_cast<char *>(slot) - reinterpret_cast<char *>(grid));
         }
+        // 6. bounding-volume hierarchy over the Morton order for queries that lie far from every node (warp_common.cuh,
+        //    knn8_bvh): leaves = NODEGRID_BVH_LEAF consecutive nodes, implicit complete binary tree of L leaves, boxes bottom-up.
+        if (bvh_box) {
+            __syncthreads();
+            const float inf = __int_as_float(0x7f800000);
+            for (int sidx = t; sidx < L * NODEGRID_BVH_LEAF; sidx += 1024) {
+                float4 e = make_float4(inf, inf, inf, __int_as_float(0x7fffffff));
+                if (sidx < M) { const int i = order[sidx]; const float *v = nodes + (size_t)i * DF_NODE_STRIDE; e = make_float4(v[0], v[1], v[2], __int_as_float(i)); }
+                bvh_leaf[sidx] = e;
+            }
+            __syncthreads();
+            for (int l = t; l < L; l += 1024) {
+                float3 lo = make_float3(inf, inf, inf), hi = make_float3(-inf, -inf, -inf);
+                for (int k = 0; k < NODEGRID_BVH_LEAF; ++k) {
+                    const float4 e = bvh_leaf[l * NODEGRID_BVH_LEAF + k];
+                    if (__float_as_int(e.w) == 0x7fffffff) continue;
+                    lo = make_float3(fminf(lo.x, e.x), fminf(lo.y, e.y), fminf(lo.z, e.z));
+                    hi = make_float3(fmaxf(hi.x, e.x), fmaxf(hi.y, e.y), fmaxf(hi.z, e.z));
+                }
+                bvh_box[2 * (L - 1 + l)] = make_float4(lo.x, lo.y, lo.z, 0.f);
+                bvh_box[2 * (L - 1 + l) + 1] = make_float4(hi.x, hi.y, hi.z, 0.f);
+            }
+            for (int width = L / 2; width >= 1; width /= 2) {          // internal nodes [width - 1, 2 * width - 1), one level per pass
+                __syncthreads();
+                for (int k = t; k < width; k += 1024) {
+                    const int i = width - 1 + k;
+                    const float4 alo = bvh_box[2 * (2 * i + 1)], ahi = bvh_box[2 * (2 * i + 1) + 1];
+                    const float4 blo = bvh_box[2 * (2 * i + 2)], bhi = bvh_box[2 * (2 * i + 2) + 1];
+                    bvh_box[2 * i] = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), 0.f);
+                    bvh_box[2 * i + 1] = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.f);
+                }
+            }
+            if (t == 0) {
+                NodeGridHeader *hg = reinterpret_cast<NodeGridHeader *>(grid);
+                hg->pad[2] = (int)(reinterpret_cast<char *>(bvh_box) - reinterpret_cast<char *>(grid));
+                hg->pad[3] = (int)(reinterpret_cast<char *>(bvh_leaf) - reinterpret_cast<char *>(grid));
+                hg->pad[4] = L;
+            }
+        }
     }
 }
 
 }  // namespace
 
+static int bvh_leaves(int M)
+{
+    int L = 1;
+    while (L * NODEGRID_BVH_LEAF < M) L *= 2;
+    return L;
+}
+static size_t bvh_bytes(int M) { return M <= NODEGRID_ORDER_MAX_M ? (size_t)bvh_leaves(M) * (2 * 32 + NODEGRID_BVH_LEAF * 16) : 0; }
+
 extern "C" size_t df_node_grid_bytes(int M)
 {
     const size_t ncell = (size_t)NODEGRID_MAX_RES * NODEGRID_MAX_RES * NODEGRID_MAX_RES;
     const size_t m = (size_t)(M > 0 ? M : 1);
-    return 64 + (((ncell + 1) * 4 + 15) & ~(size_t)15) + m * 16 + 3 * ((m * 4 + 15) & ~(size_t)15) + 256;   // + cell ids, order, slot
+    // header, cell starts, cell-sorted nodes, [BVH boxes + Morton-sorted leaves], cell ids / order / slot
+    return 64 + (((ncell + 1) * 4 + 15) & ~(size_t)15) + m * 16 + bvh_bytes((int)m) + 3 * ((m * 4 + 15) & ~(size_t)15) + 256;
 }
 
 extern "C" int df_build_node_grid(const float *nodes, int M, void *grid, void *stream)
@@ -136,7 +185,10 @@ extern "C" int df_build_node_grid(const float *nodes, int M, void *grid, void *s
     const bool want_order = M <= NODEGRID_ORDER_MAX_M;        // the ranking is O(M^2) in one block
     int *order = want_order ? reinterpret_cast<int *>(tail + arr) : nullptr;
     int *slot = want_order ? reinterpret_cast<int *>(tail + 2 * arr) : nullptr;
-    build_node_grid_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(nodes, M, grid, cid_tmp, order, slot);
+    const int L = bvh_leaves(M);
+    float4 *bvh_box = want_order ? reinterpret_cast<float4 *>(tail - bvh_bytes(M)) : nullptr;      // 16-byte aligned: every block above is
+    float4 *bvh_leaf = want_order ? bvh_box + 4 * (size_t)L : nullptr;
+    build_node_grid_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(nodes, M, grid, cid_tmp, order, slot, bvh_box, bvh_leaf, L);
     DF_LAUNCH_CHECK();
     return 0;
 }

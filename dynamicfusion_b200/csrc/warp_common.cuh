@@ -57,11 +57,13 @@ __device__ __forceinline__ void knn8_scan(const float *__restrict__ nodes, int M
 // (squared distance, node index), so the result is exactly the exhaustive scan's (knn8_scan) whatever the visiting order.
 constexpr int NODEGRID_MAX_RES = 64;
 constexpr int NODEGRID_ORDER_MAX_M = 8192;
+constexpr int NODEGRID_BVH_LEAF = 8;
 
 struct NodeGridHeader {
     float ox, oy, oz, cell, inv_cell;
     int gx, gy, gz, M, ncell;
-    int pad[6];            // pad[0], pad[1]: byte offsets of the Morton order[] / slot[] arrays (0 = absent)
+    int pad[6];            // pad[0], pad[1]: byte offsets of the Morton order[] / slot[] arrays; pad[2], pad[3], pad[4]: BVH boxes, BVH
+                           // leaves (byte offsets) and leaf count L (0 = absent)
 };   // 64 bytes, followed by: int cell_start[ncell + 1] (padded to 16 B), float4 sorted[M] = (x, y, z, index bits)
 
 __device__ __forceinline__ const int *nodegrid_cell_start(const void *grid) { return reinterpret_cast<const int *>(reinterpret_cast<const char *>(grid) + 64); }
@@ -88,12 +90,52 @@ __device__ __forceinline__ void knn8_insert_lex(int (&bi)[8], float (&bd)[8], fl
     }
 }
 
-// Shell walks are cheap while the query is within a few cells of the nodes; a query far outside the node cloud (the reference
+// Shell walks are cheap while the query is within a cell or two of the nodes; a query far outside the node cloud (the reference
 // feeds camera-frame points to a world-frame field, kinfu.cpp:356-361, so this is the common case once the camera has moved)
-// would visit thousands of empty cells.  After KNN_SHELL_CAP shells without a certified result the query is answered by one
-// exhaustive pass over the (cell-sorted) node array instead: every lane of a warp reads the same node, so the loads are
-// broadcasts.  Both paths rank by (distance, index): the result does not depend on which one ran.
-constexpr int KNN_SHELL_CAP = 3;
+// would visit thousands of empty cells.  Such a query is answered by a bounding-volume hierarchy instead (nodegrid.cu step 6):
+// depth-first, nearer child first, a subtree is skipped when the squared distance to its box exceeds the current 8th best.
+// The box distance is formed with the same float operations as a node distance ((dx*dx + dy*dy) + dz*dz, |dx| no larger than
+// for any node inside), so it never exceeds the distance computed for a node of that subtree: pruning is exact, and since all
+// paths rank by (distance, index) the result does not depend on which one ran.  Without a BVH the fallback is exhaustive.
+constexpr int KNN_SHELL_CAP = 1;
+
+__device__ __forceinline__ float bvh_box_dist2(const float4 lo, const float4 hi, float qx, float qy, float qz)
+{
+    const float d0 = fmaxf(fmaxf(lo.x - qx, qx - hi.x), 0.f), d1 = fmaxf(fmaxf(lo.y - qy, qy - hi.y), 0.f), d2 = fmaxf(fmaxf(lo.z - qz, qz - hi.z), 0.f);
+    return d0 * d0 + d1 * d1 + d2 * d2;
+}
+
+__device__ __forceinline__ void knn8_bvh(const float4 *__restrict__ box, const float4 *__restrict__ leaf, int L, float qx, float qy, float qz,
+                                         int (&bi)[8], float (&bd)[8])
+{
+    int stack_i[24];
+    float stack_d[24];
+    int sp = 0;
+    stack_i[sp] = 0; stack_d[sp] = 0.f; ++sp;
+    while (sp > 0) {
+        --sp;
+        const int i = stack_i[sp];
+        if (stack_d[sp] > bd[7]) continue;                       // strict: an equal distance may still win on the index
+        if (i >= L - 1) {
+            const float4 *e = leaf + (size_t)(i - (L - 1)) * NODEGRID_BVH_LEAF;
+#pragma unroll
+            for (int k = 0; k < NODEGRID_BVH_LEAF; ++k) {
+                const float4 nd = __ldg(e + k);
+                const float d0 = qx - nd.x, d1 = qy - nd.y, d2 = qz - nd.z;
+                knn8_insert_lex(bi, bd, d0 * d0 + d1 * d1 + d2 * d2, __float_as_int(nd.w));   // padding: distance inf, index INT_MAX
+            }
+        } else {
+            const int a = 2 * i + 1, b = a + 1;
+            const float da = bvh_box_dist2(__ldg(box + 2 * a), __ldg(box + 2 * a + 1), qx, qy, qz);
+            const float db = bvh_box_dist2(__ldg(box + 2 * b), __ldg(box + 2 * b + 1), qx, qy, qz);
+            const bool a_first = da <= db;
+            const int far_i = a_first ? b : a, near_i = a_first ? a : b;
+            const float far_d = a_first ? db : da, near_d = a_first ? da : db;
+            if (far_d <= bd[7]) { stack_i[sp] = far_i; stack_d[sp] = far_d; ++sp; }      // empty subtrees have distance inf (NaN-free: inf - q)
+            if (near_d <= bd[7]) { stack_i[sp] = near_i; stack_d[sp] = near_d; ++sp; }
+        }
+    }
+}
 
 __device__ __forceinline__ void knn8_grid(const void *__restrict__ grid, bool valid, float qx, float qy, float qz, int (&bi)[8], float (&bd)[8])
 {
@@ -139,6 +181,10 @@ __device__ __forceinline__ void knn8_grid(const void *__restrict__ grid, bool va
         if (!done) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) { bi[i] = 0x7fffffff; bd[i] = 3.402823466e+38f; }
+            if (h.pad[2]) {
+                knn8_bvh(reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(grid) + h.pad[2]),
+                         reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(grid) + h.pad[3]), h.pad[4], qx, qy, qz, bi, bd);
+            } else
 #pragma unroll 4
             for (int it = 0; it < h.M; ++it) {
                 const float4 nd = __ldg(sorted + it);
