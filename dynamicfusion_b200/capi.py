@@ -51,11 +51,14 @@ PROTOTYPES = {
     "df_clear_volume": (_i, [Volume, _vp]),
     "df_compute_dists": (_i, [_vp, _sz, _i, _i, Intr, _vp, _sz, _vp]),
     "df_integrate": (_i, [Volume, _vp, _sz, _i, _i, Aff3f, Intr, _vp, _vp]),
+    "df_volume_activity_bytes": (_sz, [Volume]),
+    "df_integrate_tracked": (_i, [Volume, _vp, _sz, _i, _i, Aff3f, Intr, _vp, _vp, _vp]),
     "df_raycast_points": (_i, [Volume, Aff3f, C.POINTER(C.c_float), Intr, _i, _i, _f, _f, _vp, _sz, _vp, _sz, _vp]),
     "df_project_workspace_bytes": (_sz, [_i, _i]),
     "df_project_and_remove": (_i, [_vp, _sz, _i, _i, Intr, _vp, _sz, _i, _i, _vp, _vp]),
     "df_extract_workspace_bytes": (_sz, [Volume]),
     "df_extract_cloud": (_i, [Volume, Aff3f, _vp, _i, _vp, _vp, _vp]),
+    "df_extract_cloud_tracked": (_i, [Volume, Aff3f, _vp, _i, _vp, _vp, _vp, _vp]),
     "df_extract_normals": (_i, [Volume, _vp, _i, _vp, Aff3f, C.POINTER(C.c_float), _f, _vp, _vp]),
     "df_bilateral": (_i, [_vp, _sz, _i, _i, _vp, _sz, _i, _f, _f, _vp]),
     "df_truncate_depth": (_i, [_vp, _sz, _i, _i, _f, _vp]),

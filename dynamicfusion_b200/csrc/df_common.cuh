@@ -58,6 +58,9 @@ template <typename T> __device__ __forceinline__ T *row_ptr(T *base, size_t pitc
 
 static inline int div_up(int a, int b) { return (a + b - 1) / b; }
 
+// a voxel takes part in surface extraction iff W != 0 && F != 1.f (tsdf_volume.cu:548-633); 0x3c00 = half(1.0)
+__device__ __forceinline__ bool vox_active(uint32_t v) { return (v >> 16) != 0 && (v & 0xffffu) != 0x3c00u; }
+
 }  // namespace dfb
 
 #define DF_LAUNCH_CHECK()                                  \

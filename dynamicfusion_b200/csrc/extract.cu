@@ -6,11 +6,10 @@
 // an exclusive scan over block counts and an emit pass produce the points in ascending (z, y, x) voxel order, +x,+y,+z
 // edge within a voxel -- the same order the CPU oracle uses, so the result is comparable element by element.
 //
-// Work decomposition: the volume is one contiguous array; block b owns voxels [b*VOXELS_PER_BLOCK, ...) in memory
-// order, thread t owns VX consecutive voxels (one 16-byte load).  A thread whose voxels are all unobserved (W == 0) or
-// free space (F == 1) touches nothing else -- on real scenes that is >95 % of threads, so the counting pass streams the
-// volume once at HBM speed; only surface threads fetch the +x / +y / +z neighbours (L1/L2 hits: the neighbours are
-// another thread's own voxels).
+// Work decomposition: the volume is one contiguous array cut into blocks of EX_THREADS quads (1024 voxels when VX = 4), a
+// quad = VX consecutive voxels = one 16-byte load.  A quad whose voxels are all unobserved (W == 0) or free space (F == 1)
+// needs nothing else -- on real scenes that is >90 % of them; only surface quads fetch the +x / +y / +z neighbours (L1/L2
+// hits).  Kernels: see the comment above extract_count_kernel.
 #include "df_common.cuh"
 
 using namespace dfb;
@@ -26,24 +25,31 @@ struct ExtractParams {
     Aff pose;
     size_t nvox;
     int nblocks;
+    const unsigned char *activity;   // optional (dfusion.h, DF_ACTIVITY_VOXELS): blocks whose stretch of the volume is inactive are skipped
 };
 
-__device__ __forceinline__ bool vox_active(uint32_t v) { return (v >> 16) != 0 && (v & 0xffffu) != 0x3c00u; }   // W != 0 && F != 1.f
 __device__ __forceinline__ float vox_f(uint32_t v) { return half_bits_to_float((unsigned short)(v & 0xffffu)); }
 __device__ __forceinline__ bool sign_change(float F, float Fn) { return (F > 0 && Fn < 0) || (F < 0 && Fn > 0); }
 
 // Calls emit(point) for every zero crossing owned by this thread, in (voxel, axis) order.  tsdf_volume.cu:548-633.
-template <int VX, typename Emit>
-__device__ __forceinline__ void thread_crossings(const ExtractParams &p, size_t v0, Emit emit)
+// the thread's own VX voxels (one 16-byte load when VX = 4); zeros past the end of the volume
+template <int VX>
+__device__ __forceinline__ void load_quad(const ExtractParams &p, size_t v0, uint32_t (&own)[VX])
 {
+#pragma unroll
+    for (int j = 0; j < VX; ++j) own[j] = 0u;
     if (v0 >= p.nvox) return;
-    uint32_t own[VX];
     if (VX == 4) {
         const uint4 q = __ldg(reinterpret_cast<const uint4 *>(p.data + v0));
         own[0] = q.x; own[1 % VX] = q.y; own[2 % VX] = q.z; own[3 % VX] = q.w;
     } else {
         own[0] = __ldg(p.data + v0);
     }
+}
+
+template <int VX, typename Emit>
+__device__ __forceinline__ void thread_crossings(const ExtractParams &p, size_t v0, const uint32_t (&own)[VX], Emit emit)
+{
     bool any = false;
 #pragma unroll
     for (int j = 0; j < VX; ++j) any |= vox_active(own[j]);
@@ -98,6 +104,14 @@ __device__ __forceinline__ void thread_crossings(const ExtractParams &p, size_t 
     }
 }
 
+// Count / emit.  A block = EX_THREADS * EX_QPT quads (4096 voxels when VX = 4), a thread owns quads tid, tid + 256, ...: all of
+// its 16-byte loads are issued before any of them is used, and each load instruction of a warp is one contiguous 512-byte
+// request.  History (profiles/): one quad per thread meant 131,072 CTAs for 512^3 -- the emit pass, whose CTAs mostly return at
+// once, still took 0.17 ms: block scheduling, not memory, was the limit; one WARP per block (8 quads per lane, shuffle scans)
+// removed the scheduling cost but serialised the dependent neighbour fetches of the surface quads and was 4x slower.
+// With an activity map the quads of inactive stretches are not loaded at all.
+constexpr int EX_QPT = 4;
+
 __device__ __forceinline__ int block_exclusive_scan(int v, int *total)
 {
     __shared__ int warp_sums[EX_THREADS / 32];
@@ -127,12 +141,35 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *total)
 }
 
 template <int VX>
+__device__ __forceinline__ int quad_count(const ExtractParams &p, size_t v0, const uint32_t (&own)[VX])
+{
+    int n = 0;
+    thread_crossings<VX>(p, v0, own, [&](const float3) { ++n; });
+    return n;
+}
+
+template <int VX>
+__device__ __forceinline__ void load_block_quads(const ExtractParams &p, size_t q0, uint32_t (&own)[EX_QPT][VX])
+{
+#pragma unroll
+    for (int i = 0; i < EX_QPT; ++i) {
+        const size_t v0 = (q0 + (size_t)(i * EX_THREADS) + threadIdx.x) * VX;
+#pragma unroll
+        for (int j = 0; j < VX; ++j) own[i][j] = 0u;
+        if (p.activity && v0 < p.nvox && !p.activity[v0 / DF_ACTIVITY_VOXELS]) continue;    // cannot hold surface: not even loaded
+        load_quad<VX>(p, v0, own[i]);
+    }
+}
+
+template <int VX>
 __global__ void __launch_bounds__(EX_THREADS) extract_count_kernel(const ExtractParams p, int *block_counts)
 {
-    const size_t v0 = ((size_t)blockIdx.x * EX_THREADS + threadIdx.x) * VX;
+    const size_t q0 = (size_t)blockIdx.x * EX_THREADS * EX_QPT;
+    uint32_t own[EX_QPT][VX];
+    load_block_quads<VX>(p, q0, own);
     int n = 0;
-    thread_crossings<VX>(p, v0, [&](const float3) { ++n; });
-    // block sum (most blocks are all-zero: one ballot-based early path)
+#pragma unroll
+    for (int i = 0; i < EX_QPT; ++i) n += quad_count<VX>(p, (q0 + (size_t)(i * EX_THREADS) + threadIdx.x) * VX, own[i]);
     const int any = __syncthreads_or(n);
     if (!any) { if (threadIdx.x == 0) block_counts[blockIdx.x] = 0; return; }
     int total;
@@ -192,15 +229,23 @@ __global__ void __launch_bounds__(EX_THREADS) extract_emit_kernel(const ExtractP
                                                                   const int *super_off, float4 *out, int capacity)
 {
     if (block_counts[blockIdx.x] == 0) return;
-    const size_t v0 = ((size_t)blockIdx.x * EX_THREADS + threadIdx.x) * VX;
-    float3 pts[3 * VX];
-    int n = 0;
-    thread_crossings<VX>(p, v0, [&](const float3 q) { pts[n++] = q; });
-    const int local = block_exclusive_scan(n, nullptr);
-    const int base = super_off[blockIdx.x >> 10] + offsets[blockIdx.x] + local;
+    const size_t q0 = (size_t)blockIdx.x * EX_THREADS * EX_QPT;
+    uint32_t own[EX_QPT][VX];
+    load_block_quads<VX>(p, q0, own);
+    int run = super_off[blockIdx.x >> 10] + offsets[blockIdx.x];
 #pragma unroll
-    for (int i = 0; i < 3 * VX; ++i)
-        if (i < n && base + i < capacity) out[base + i] = make_float4(pts[i].x, pts[i].y, pts[i].z, 0.f);
+    for (int i = 0; i < EX_QPT; ++i) {                                // points leave in quad order i * EX_THREADS + tid
+        const size_t v0 = (q0 + (size_t)(i * EX_THREADS) + threadIdx.x) * VX;
+        const int c = quad_count<VX>(p, v0, own[i]);
+        int total;
+        int k = run + block_exclusive_scan(c, &total);
+        if (c)
+            thread_crossings<VX>(p, v0, own[i], [&](const float3 q) {
+                if (k < capacity) out[k] = make_float4(q.x, q.y, q.z, 0.f);
+                ++k;
+            });
+        run += total;
+    }
 }
 
 ExtractParams make_params(const df_volume &vol, const df_aff3f &pose, int vx)
@@ -211,7 +256,8 @@ ExtractParams make_params(const df_volume &vol, const df_aff3f &pose, int vx)
     p.vs = make_float3(vol.voxel_size[0], vol.voxel_size[1], vol.voxel_size[2]);
     p.pose = make_aff(pose);
     p.nvox = (size_t)vol.dims[0] * vol.dims[1] * vol.dims[2];
-    p.nblocks = (int)((p.nvox + (size_t)EX_THREADS * vx - 1) / ((size_t)EX_THREADS * vx));
+    p.nblocks = (int)((p.nvox + (size_t)EX_THREADS * EX_QPT * vx - 1) / ((size_t)EX_THREADS * EX_QPT * vx));
+    p.activity = nullptr;
     return p;
 }
 
@@ -228,8 +274,15 @@ extern "C" size_t df_extract_workspace_bytes(df_volume vol)
 
 extern "C" int df_extract_cloud(df_volume vol, df_aff3f pose, float *out_points, int capacity, int *count, void *workspace, void *stream)
 {
+    return df_extract_cloud_tracked(vol, pose, out_points, capacity, count, workspace, nullptr, stream);
+}
+
+extern "C" int df_extract_cloud_tracked(df_volume vol, df_aff3f pose, float *out_points, int capacity, int *count, void *workspace,
+                                        const unsigned char *activity, void *stream)
+{
     const int vx = pick_vx(vol);
-    const ExtractParams p = make_params(vol, pose, vx);
+    ExtractParams p = make_params(vol, pose, vx);
+    p.activity = activity;
     int *block_counts = (int *)workspace;
     int *offsets = block_counts + p.nblocks;
     cudaStream_t s = (cudaStream_t)stream;

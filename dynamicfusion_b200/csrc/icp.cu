@@ -110,11 +110,10 @@ __global__ void __launch_bounds__(256) icp_accumulate_kernel(const IcpParams p)
 // fixed-order reduction of the block partials into sums[27]
 __device__ void reduce_partials(const double *partials, int nblocks, double *sums_smem)
 {
-    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31, nwarps = (blockDim.x * blockDim.y) >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     for (int s = warp; s < 27; s += nwarps) {
         double v = 0.0;
-        for (int b = lane; b < nblocks; b += 32) v += __ldcg(partials + (size_t)b * 27 + s);   // written by other SMs in this launch
+        for (int b = lane; b < nblocks; b += 32) v += partials[(size_t)b * 27 + s];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (lane == 0) sums_smem[s] = v;
@@ -153,7 +152,7 @@ __device__ double det6_dev(const double *Ain)
 // solve).  *det receives det(A) = (prod L_jj)^2.
 __device__ __forceinline__ bool chol6_solve(const double (&A)[36], const double (&b)[6], double (&x)[6], double *det)
 {
-    double L[36], Linv[6];
+    double L[36];
     double dmax = 0.0;
 #pragma unroll
     for (int i = 0; i < 6; ++i) dmax = fmax(dmax, fabs(A[i * 6 + i]));
@@ -169,8 +168,7 @@ __device__ __forceinline__ bool chol6_solve(const double (&A)[36], const double 
         dprod *= d;
         L[j * 6 + j] = d;
         const double dinv = 1.0 / d;
-        Linv[j] = dinv;                                         // one division per pivot; the substitutions multiply (the tail is a
-#pragma unroll                                                  //  single dependent chain of software double divisions otherwise)
+#pragma unroll
         for (int i = j + 1; i < 6; ++i) {
             double s = A[i * 6 + j];
 #pragma unroll
@@ -184,14 +182,14 @@ __device__ __forceinline__ bool chol6_solve(const double (&A)[36], const double 
         double s = b[i];
 #pragma unroll
         for (int k = 0; k < i; ++k) s -= L[i * 6 + k] * y[k];
-        y[i] = s * Linv[i];
+        y[i] = s / L[i * 6 + i];
     }
 #pragma unroll
     for (int i = 5; i >= 0; --i) {
         double s = y[i];
 #pragma unroll
         for (int k = i + 1; k < 6; ++k) s -= L[k * 6 + i] * x[k];
-        x[i] = s * Linv[i];
+        x[i] = s / L[i * 6 + i];
     }
     *det = dprod * dprod;
     return ok;
@@ -234,11 +232,12 @@ __device__ void sym6_solve_dev(const double *Ain, const double *b, double *x)
 }
 
 // StreamHelper::get (projective_icp.cpp:43-62) + host step :195-209, on the device
-__device__ void icp_solve_tail(const double *partials, int nblocks, float *T, int *ok, double *sums)
+__global__ void __launch_bounds__(256) icp_solve_kernel(const double *partials, int nblocks, float *T, int *ok)
 {
+    __shared__ double sums[27];
     if (*ok == 0) return;
     reduce_partials(partials, nblocks, sums);
-    if (threadIdx.x != 0 || threadIdx.y != 0) return;
+    if (threadIdx.x != 0) return;
     double A[36], b[6];
     {
         int shift = 0;
@@ -280,12 +279,6 @@ __device__ void icp_solve_tail(const double *partials, int nblocks, float *T, in
     }
     for (int i = 0; i < 9; ++i) T[i] = Rn[i];
     for (int i = 0; i < 3; ++i) T[9 + i] = tn[i];
-}
-
-__global__ void __launch_bounds__(256) icp_solve_kernel(const double *partials, int nblocks, float *T, int *ok)
-{
-    __shared__ double sums[27];
-    icp_solve_tail(partials, nblocks, T, ok, sums);
 }
 
 __global__ void icp_init_kernel(float *T, int *ok)
@@ -347,8 +340,9 @@ extern "C" int df_icp_estimate(const float *const *vcurr, const float *const *nc
         p.min_cosine = cosf(angle_thres);
         p.T_val = Aff(); p.T_ptr = T_dev; p.ok_ptr = ok_dev;
         p.partials = scratch + 32;
-        // (fusing the solve into the accumulate kernel as a last-block tail was measured and dropped: the tail's 190 registers
-        //  become the whole kernel's allocation, occupancy falls to one block per SM and the stage got 25 % slower)
+        // (tried and dropped, round 1: running the solve as a last-block tail of the accumulate kernel -- the tail's 190 registers
+        //  become the whole kernel's allocation, occupancy falls to one block per SM and the stage got 25 % slower; replacing the
+        //  substitutions' divisions by reciprocal multiplies made the one-thread tail 2.4 us slower per iteration, not faster)
         for (int it = 0; it < iters[level]; ++it) {
             const int blocks = launch_accumulate(p, s);
             if (blocks < 0) return -blocks;

@@ -36,6 +36,7 @@ struct KinFu {
     float *icp_T = nullptr; int *icp_ok = nullptr; double *icp_scratch = nullptr;
     void *solve_ws = nullptr; size_t solve_ws_bytes = 0; double *solve_stats = nullptr;
     void *extract_ws = nullptr; void *project_ws = nullptr;
+    unsigned char *activity = nullptr; size_t activity_bytes = 0;   // dfusion.h DF_ACTIVITY_VOXELS: which stretches of the volume hold surface
     float *pinned = nullptr;             // 16 floats: T(12) + ok
     std::vector<float> poses;            // 12 floats per pose
     int frame_counter = 0, resets = 0, last_ok = 1, launches = 0;
@@ -118,6 +119,7 @@ int do_reset(KinFu &k)
     k.poses.clear();
     k.poses.resize(12);
     dfh_aff_identity(k.poses.data());
+    if (k.activity && cudaMemsetAsync(k.activity, 0, k.activity_bytes, k.stream) != cudaSuccess) return (int)cudaGetLastError();
     return df_clear_volume(vol_of(k), k.stream);
 }
 
@@ -172,7 +174,7 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_d
         ++k.launches;
         unsigned long long *counter = (p.flags & DF_KINFU_STAGE_TIMING) ? k.n_upd : nullptr;
         if (counter) cudaMemsetAsync(counter, 0, 8, s);
-        return df_integrate(vol, (const uint16_t *)dists.ptr, dists.pitch, p.cols, p.rows, to_aff(vol2cam), p.intr, counter, s);
+        return df_integrate_tracked(vol, (const uint16_t *)dists.ptr, dists.pitch, p.cols, p.rows, to_aff(vol2cam), p.intr, counter, k.activity, s);
     };
     auto raycast_to = [&](const float *cam_pose, Img &pts, Img &nrm) -> int {
         float inv[12], cam2vol[12], Rinv[9];
@@ -184,7 +186,7 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_d
                                  (float *)pts.ptr, pts.pitch, (float *)nrm.ptr, nrm.pitch, s);
     };
     auto extract = [&]() -> int {                                      // compute_points + compute_normals, tsdf_volume.cpp:313-325
-        int st = df_extract_cloud(vol, p.volume_pose, k.cloud, p.cloud_capacity, k.cloud_count, k.extract_ws, s);
+        int st = df_extract_cloud_tracked(vol, p.volume_pose, k.cloud, p.cloud_capacity, k.cloud_count, k.extract_ws, k.activity, s);
         if (st) return st;
         k.launches += 4;
         k.last_cloud = -1;
@@ -378,6 +380,8 @@ extern "C" void *df_kinfu_create(const df_kinfu_params *pp)
     ok = ok && cudaMalloc(&k->solve_ws, k->solve_ws_bytes) == cudaSuccess && cudaMalloc(&k->solve_stats, 64) == cudaSuccess;
     df_volume v = vol_of(*k);
     ok = ok && cudaMalloc(&k->extract_ws, df_extract_workspace_bytes(v)) == cudaSuccess;
+    k->activity_bytes = df_volume_activity_bytes(v);
+    ok = ok && cudaMalloc(&k->activity, k->activity_bytes) == cudaSuccess && cudaMemset(k->activity, 0, k->activity_bytes) == cudaSuccess;
     ok = ok && cudaMalloc(&k->project_ws, df_project_workspace_bytes(p.cols, p.rows)) == cudaSuccess;
     ok = ok && cudaMemset(k->project_ws, 0, df_project_workspace_bytes(p.cols, p.rows)) == cudaSuccess;
     ok = ok && cudaMemset(k->solve_stats, 0, 64) == cudaSuccess && cudaMemset(k->cloud_count, 0, 64) == cudaSuccess;
@@ -403,7 +407,7 @@ extern "C" void df_kinfu_destroy(void *h)
     cudaFree(k->canon.ptr); cudaFree(k->canon_nrm.ptr); cudaFree(k->canon_visible.ptr);
     cudaFree(k->cloud); cudaFree(k->cloud_nrm); cudaFree(k->cloud_count); cudaFree(k->nodes); cudaFree(k->node_grid);
     cudaFree(k->icp_T); cudaFree(k->icp_ok); cudaFree(k->icp_scratch); cudaFree(k->solve_ws); cudaFree(k->solve_stats);
-    cudaFree(k->extract_ws); cudaFree(k->project_ws); cudaFreeHost(k->pinned); cudaFree(k->n_upd);
+    cudaFree(k->extract_ws); cudaFree(k->project_ws); cudaFree(k->activity); cudaFreeHost(k->pinned); cudaFree(k->n_upd);
     for (int e = 0; e <= NSTAGES; ++e) cudaEventDestroy(k->ev[e]);
     delete k;
 }

@@ -161,25 +161,29 @@ __global__ void __launch_bounds__(256) solve_fill_kernel(SolveWs ws, int N)
 }
 
 // One block per node i: A_i* (sparse, via shared-memory hash), gb_i, diag_i.
-__global__ void __launch_bounds__(256) solve_rows_kernel(SolveWs ws, int M, int N, int quirk)
+// A node on the rim of the cloud can own 10^5 incidence entries while the median node owns 10^3: the kernel's duration is the
+// heaviest row's, so a row gets a full 1024-thread block (48 registers per thread).
+constexpr int ROWS_THREADS = 1024;
+
+__global__ void __launch_bounds__(ROWS_THREADS) solve_rows_kernel(SolveWs ws, int M, int N, int quirk)
 {
     __shared__ int keys[HCAP];
     __shared__ double vals[HCAP];
     __shared__ int list[HCAP];
     __shared__ int nlist;
-    __shared__ double red[3][8];
+    __shared__ double red[3][ROWS_THREADS / 32];
     const int i = blockIdx.x;
     const int tid = threadIdx.x;
-    for (int s = tid; s < HCAP; s += 256) { keys[s] = -1; vals[s] = 0.0; }
+    for (int s = tid; s < HCAP; s += ROWS_THREADS) { keys[s] = -1; vals[s] = 0.0; }
     if (tid == 0) nlist = 0;
     __syncthreads();
     const int beg = ws.off[i], end = ws.off[i + 1];
     const int lane = tid & 31;
     double g0 = 0.0, g1 = 0.0, g2 = 0.0;
     // Pixels that are far from the node cloud share one neighbour set, so a node on the rim of the cloud sees the SAME eight
-    // keys in (nearly) all of its incident entries: without aggregation 256 threads serialise on eight shared-memory words.
+    // keys in (nearly) all of its incident entries: without aggregation all threads serialise on eight shared-memory words.
     // Lanes of a warp holding the same key are summed first (match.any + shuffles) and only the group leader probes the hash.
-    for (int base = beg; base < end; base += 256) {
+    for (int base = beg; base < end; base += ROWS_THREADS) {
         const int e = base + tid;
         const bool valid = e < end;
         double wi = 0.0;
@@ -237,13 +241,13 @@ __global__ void __launch_bounds__(256) solve_rows_kernel(SolveWs ws, int M, int 
     for (int o = 16; o > 0; o >>= 1) { g0 += __shfl_xor_sync(0xffffffffu, g0, o); g1 += __shfl_xor_sync(0xffffffffu, g1, o); g2 += __shfl_xor_sync(0xffffffffu, g2, o); }
     if ((tid & 31) == 0) { red[0][tid >> 5] = g0; red[1][tid >> 5] = g1; red[2][tid >> 5] = g2; }
     __syncthreads();
-    for (int s = tid; s < HCAP; s += 256)
+    for (int s = tid; s < HCAP; s += ROWS_THREADS)
         if (keys[s] >= 0) list[atomicAdd(&nlist, 1)] = s;
     __syncthreads();
     const int nn = nlist;
     if (nn > ROWCAP && tid == 0) ws.flags[0] = 1;
     double dg = 0.0;
-    for (int a = tid; a < nn; a += 256) {
+    for (int a = tid; a < nn; a += ROWS_THREADS) {
         const int sa = list[a], ka = keys[sa];
         int rank = 0;
         for (int bq = 0; bq < nn; ++bq) rank += keys[list[bq]] < ka;
@@ -254,7 +258,7 @@ __global__ void __launch_bounds__(256) solve_rows_kernel(SolveWs ws, int M, int 
     if (tid == 0) {
         ws.rownnz[i] = min(nn, ROWCAP);
         double a = 0.0, b = 0.0, c = 0.0;
-        for (int q = 0; q < 8; ++q) { a += red[0][q]; b += red[1][q]; c += red[2][q]; }
+        for (int q = 0; q < ROWS_THREADS / 32; ++q) { a += red[0][q]; b += red[1][q]; c += red[2][q]; }
         ws.gb[i] = a; ws.gb[M + i] = b; ws.gb[2 * M + i] = c;
         if (end == beg && !(quirk && i == 0)) ws.diag[i] = 0.0;
     }
@@ -1493,7 +1497,7 @@ extern "C" int df_solve_data_term(float *nodes, int M, const void *node_grid, co
     DF_LAUNCH_CHECK();
     solve_fill_kernel<<<ws.prepare_blocks, 256, 0, s>>>(ws, N);
     DF_LAUNCH_CHECK();
-    solve_rows_kernel<<<M, 256, 0, s>>>(ws, M, N, flags & DF_SOLVE_REF_GRAPH_QUIRK);
+    solve_rows_kernel<<<M, ROWS_THREADS, 0, s>>>(ws, M, N, flags & DF_SOLVE_REF_GRAPH_QUIRK);
     DF_LAUNCH_CHECK();
     const size_t smem_budget = 200 * 1024;
     const LmSmemLayout L0 = lm_layout(M, 0);

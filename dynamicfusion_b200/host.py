@@ -105,8 +105,10 @@ def resizePointsNormals(points: torch.Tensor, normals: torch.Tensor):
 class TsdfVolume:
     """cuda::TsdfVolume (tsdf_volume.hpp:11-100, tsdf_volume.cpp).  Class defaults as tsdf_volume.cpp:7-14."""
 
-    def __init__(self, dims, device="cuda"):
+    def __init__(self, dims, device="cuda", track_activity=False):
         self.device = device
+        self.track_activity = track_activity      # dfusion.h DF_ACTIVITY_VOXELS: lets fetchCloud skip surface-free stretches
+        self.activity_ = None
         self.trunc_dist_ = 0.03
         self.max_weight_ = 128
         self.size_ = np.array([3.0, 3.0, 3.0], np.float32)
@@ -122,6 +124,8 @@ class TsdfVolume:
         self.dims_ = np.array(dims, np.int32)
         n = int(self.dims_[0]) * int(self.dims_[1]) * int(self.dims_[2])
         self.data_ = torch.empty(n, dtype=torch.int32, device=self.device)
+        if self.track_activity:
+            self.activity_ = torch.zeros(int(_lib().df_volume_activity_bytes(self._vol())), dtype=torch.uint8, device=self.device)
         self.setTruncDist(self.trunc_dist_)
         self.clear()
 
@@ -171,12 +175,15 @@ class TsdfVolume:
 
     def clear(self):
         capi.check(_lib().df_clear_volume(self._vol(), _stream()))
+        if self.activity_ is not None:
+            self.activity_.zero_()
 
     def integrate(self, dists: torch.Tensor, camera_pose, intr, n_updated: torch.Tensor | None = None):
         vol2cam = aff_mul(aff_inv(camera_pose), self.pose_)                           # tsdf_volume.cpp:112
         rows, cols = dists.shape
-        capi.check(_lib().df_integrate(self._vol(), dists.data_ptr(), cols * 2, cols, rows, capi.make_aff(*vol2cam),
-                                       capi.make_intr(*intr), n_updated.data_ptr() if n_updated is not None else None, _stream()))
+        capi.check(_lib().df_integrate_tracked(self._vol(), dists.data_ptr(), cols * 2, cols, rows, capi.make_aff(*vol2cam),
+                                               capi.make_intr(*intr), n_updated.data_ptr() if n_updated is not None else None,
+                                               self.activity_.data_ptr() if self.activity_ is not None else None, _stream()))
         return vol2cam
 
     def raycast(self, camera_pose, intr, cols: int, rows: int):
@@ -205,8 +212,9 @@ class TsdfVolume:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         out = torch.empty((capacity, 4), dtype=torch.float32, device=self.device)
         count = torch.zeros(1, dtype=torch.int32, device=self.device)
-        capi.check(_lib().df_extract_cloud(self._vol(), capi.make_aff(*self.pose_), out.data_ptr(), capacity, count.data_ptr(),
-                                           self._ws.data_ptr(), _stream()))
+        capi.check(_lib().df_extract_cloud_tracked(self._vol(), capi.make_aff(*self.pose_), out.data_ptr(), capacity, count.data_ptr(),
+                                                   self._ws.data_ptr(), self.activity_.data_ptr() if self.activity_ is not None else None,
+                                                   _stream()))
         return out, count
 
     def fetchNormals(self, cloud: torch.Tensor, n: int, count_dev: torch.Tensor | None = None):

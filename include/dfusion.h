@@ -58,6 +58,16 @@ int df_compute_dists(const uint16_t *depth, size_t depth_pitch, int cols, int ro
 int df_integrate(df_volume vol, const uint16_t *dists, size_t dists_pitch, int cols, int rows,
                  df_aff3f vol2cam, df_intr intr, unsigned long long *n_updated, void *stream);
 
+/* Activity map (optional accelerator for df_extract_cloud_tracked): one byte per DF_ACTIVITY_VOXELS consecutive voxels of the
+ * volume array, non-zero iff an integration stored a voxel with W != 0 && F != 1 there since the map was last zeroed.  Only such
+ * voxels can emit a zero crossing (tsdf_volume.cu:548-633), so extraction may skip every other stretch of the volume and still
+ * return exactly the full scan's points.  The caller zeroes the map whenever it clears the volume and must route EVERY
+ * integration of that volume through df_integrate_tracked. */
+#define DF_ACTIVITY_VOXELS 1024
+size_t df_volume_activity_bytes(df_volume vol);
+int df_integrate_tracked(df_volume vol, const uint16_t *dists, size_t dists_pitch, int cols, int rows,
+                         df_aff3f vol2cam, df_intr intr, unsigned long long *n_updated, unsigned char *activity, void *stream);
+
 /* device::raycast, points variant (internal.hpp:113-114, tsdf_volume.cu:341-405,459-474).
  * cam2vol = volume_pose^-1 * camera_pose, Rinv = cam2vol.R^-1 (tsdf_volume.cpp:157-174). */
 int df_raycast_points(df_volume vol, df_aff3f cam2vol, const float *Rinv_host9, df_intr intr, int cols, int rows,
@@ -78,6 +88,9 @@ int df_project_and_remove(uint16_t *dists, size_t dists_pitch, int cols, int row
 size_t df_extract_workspace_bytes(df_volume vol);
 int df_extract_cloud(df_volume vol, df_aff3f pose, float *out_points, int capacity, int *count,
                      void *workspace, void *stream);
+/* same, skipping the stretches of the volume whose activity byte is zero (activity == NULL: full scan) */
+int df_extract_cloud_tracked(df_volume vol, df_aff3f pose, float *out_points, int capacity, int *count, void *workspace,
+                             const unsigned char *activity, void *stream);
 
 /* device::extractNormals (internal.hpp:139, tsdf_volume.cu:714-795,817-831).  n_points may be given on the host
  * (count_dev == NULL) or read from device memory (count_dev != NULL, upper bound n_points). */

@@ -123,3 +123,63 @@ def test_project_and_remove(orc):
     assert np.array_equal(host.u16_from_device(d_dev), d_ref)
     assert np.array_equal(p_dev.cpu().numpy().view(np.uint32), p_ref.view(np.uint32))
     assert (d_ref == 0).sum() > (depth == 0).sum()
+
+
+def test_tracked_extraction_equals_full_scan(orc):
+    """df_integrate_tracked / df_extract_cloud_tracked: the activity map only lets extraction skip stretches of the volume
+    that cannot emit a zero crossing, so points AND their order are those of the full scan (and of the oracle)"""
+    dim = 128
+    vols = [_setup(dim, 1.0, None), None]
+    vols[1] = host.TsdfVolume((dim, dim, dim), track_activity=True)
+    v = vols[1]
+    v.setTruncDist(0.04); v.setMaxWeight(64); v.setSize((1.0, 1.0, 1.0)); v.setPose(synth.volume_pose(1.0)); v.clear()
+    for t in range(3):
+        depth = synth.umbrella_depth(t)
+        dists = host.computeDists(host.u16_to_device(depth), K)
+        pose = synth.camera_drift(4 * t)
+        pose = (pose[0].astype(np.float32), pose[1].astype(np.float32))
+        for vol in vols:
+            vol.integrate(dists, pose, K)
+    assert np.array_equal(vols[0].data_.cpu().numpy(), vols[1].data_.cpu().numpy())
+    act = vols[1].activity_.cpu().numpy()
+    assert 0 < np.count_nonzero(act) < 0.6 * act.size
+    clouds = []
+    for vol in vols:
+        pts, cnt = vol.fetchCloud(600000)
+        n = int(cnt.item())
+        clouds.append(pts[:n].cpu().numpy())
+    assert len(clouds[0]) > 5000
+    assert np.array_equal(clouds[0].view(np.uint32), clouds[1].view(np.uint32))
+    ref = orc.extract_cloud(vols[0].data_.cpu().numpy().view(np.uint32), vols[0].getDims(), vols[0].getVoxelSize(), vols[0].getTruncDist(),
+                            vols[0].getMaxWeight(), vols[0].pose_, 600000)
+    assert np.array_equal(clouds[1].view(np.uint32), ref.view(np.uint32))
+    # clearing resets the map
+    vols[1].clear()
+    assert int(vols[1].activity_.sum().item()) == 0 and int(vols[1].fetchCloud(1000)[1].item()) == 0
+
+
+def test_integrate_v2_variant_bit_exact_in_subprocess(orc):
+    """the alternative integrate kernel (DF_INTEGRATE_IMPL=2: approximate-reciprocal projection with exact fallback, sqrt only in
+    the band) is selected per process; it must store the same u32 voxels as the oracle"""
+    import os, subprocess, sys
+    script = (
+        "import numpy as np, torch\n"
+        "from dynamicfusion_b200 import host, synth\n"
+        "from oracle import orc\n"
+        "K = synth.DEFAULT_K; dim = 96\n"
+        "vol = host.TsdfVolume((dim, dim, dim)); vol.setTruncDist(0.04); vol.setMaxWeight(64); vol.setSize((1.0, 1.0, 1.0))\n"
+        "vol.setPose(synth.volume_pose(1.0)); vol.clear()\n"
+        "ref = np.zeros(dim ** 3, np.uint32)\n"
+        "for t in range(3):\n"
+        "    depth = synth.umbrella_depth(t)\n"
+        "    dists = host.computeDists(host.u16_to_device(depth), K)\n"
+        "    R, tr = synth.camera_drift(5 * t); pose = (R.astype(np.float32), tr.astype(np.float32))\n"
+        "    vol2cam = vol.integrate(dists, pose, K)\n"
+        "    orc.integrate(ref, vol.getDims(), vol.getVoxelSize(), vol.getTruncDist(), vol.getMaxWeight(), orc.compute_dists(depth, K), vol2cam, K)\n"
+        "got = vol.data_.cpu().numpy().view(np.uint32)\n"
+        "assert np.count_nonzero(ref) > 100000\n"
+        "raise SystemExit(0 if np.array_equal(got, ref) else 3)\n")
+    env = dict(os.environ, DF_INTEGRATE_IMPL="2")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", script], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
