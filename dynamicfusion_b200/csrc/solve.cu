@@ -957,10 +957,10 @@ struct Lm4Layout {
     size_t off_svec, off_val, off_col, total;
 };
 
-__host__ __device__ inline Lm4Layout lm4_layout(int M, int ent_cap)
+__host__ __device__ inline Lm4Layout lm4_layout(int M, int ent_cap, int ncta = LMC_CTAS)
 {
     Lm4Layout L;
-    L.rpc = (M + LMC_CTAS - 1) / LMC_CTAS;
+    L.rpc = (M + ncta - 1) / ncta;
     L.tpr = 1;
     while (L.tpr < 32 && L.tpr * 2 * L.rpc <= LM4_THREADS) L.tpr *= 2;
     L.ent_cap = ent_cap;
@@ -1200,17 +1200,18 @@ __device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uin
     asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr), "l"(__double_as_longlong(v)), "r"(remote_bar) : "memory");
 }
 
+template <int NCTA>
 struct Lm5Smem {
-    double wpart[LM4_THREADS / 32][8];
-    double red_in[2][LMC_CTAS][8];
+    double wpart[LM4_THREADS / 32][NCTA];
+    double red_in[2][NCTA][NCTA];
     unsigned long long bar_red[2];
     unsigned long long bar_pub;
 };
 
 struct Lm5Sync { int parity; uint32_t phase_red[2]; uint32_t phase_pub; };
 
-template <int NV>
-__device__ __forceinline__ void cluster_sum5(Lm5Smem &sm, Lm5Sync &sy, int cta, double (&v)[NV])
+template <int NCTA, int NV>
+__device__ __forceinline__ void cluster_sum5(Lm5Smem<NCTA> &sm, Lm5Sync &sy, int cta, double (&v)[NV])
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int par = sy.parity;
@@ -1224,14 +1225,14 @@ __device__ __forceinline__ void cluster_sum5(Lm5Smem &sm, Lm5Sync &sy, int cta, 
     __syncthreads();
     const uint32_t bar = smem_u32(&sm.bar_red[par]);
     if (warp == 0) {
-        const uint32_t rbar = mapa_u32(bar, (uint32_t)(lane & (LMC_CTAS - 1)));
+        const uint32_t rbar = mapa_u32(bar, (uint32_t)(lane & (NCTA - 1)));
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
             double t = lane < LM4_THREADS / 32 ? sm.wpart[lane][k] : 0.0;
             for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-            if (lane < LMC_CTAS) st_async_f64(mapa_u32(smem_u32(&sm.red_in[par][cta][k]), (uint32_t)lane), t, rbar);   // lane = destination CTA
+            if (lane < NCTA) st_async_f64(mapa_u32(smem_u32(&sm.red_in[par][cta][k]), (uint32_t)lane), t, rbar);   // lane = destination CTA
         }
-        if (lane == 0) mbar_arrive_expect(bar, (uint32_t)(LMC_CTAS * NV * 8));
+        if (lane == 0) mbar_arrive_expect(bar, (uint32_t)(NCTA * NV * 8));
     }
     mbar_wait(bar, sy.phase_red[par]);
     sy.phase_red[par] ^= 1u;
@@ -1239,19 +1240,22 @@ __device__ __forceinline__ void cluster_sum5(Lm5Smem &sm, Lm5Sync &sy, int cta, 
     for (int k = 0; k < NV; ++k) {
         double t = 0.0;
 #pragma unroll
-        for (int c = 0; c < LMC_CTAS; ++c) t += sm.red_in[par][c][k];
+        for (int c = 0; c < NCTA; ++c) t += sm.red_in[par][c][k];
         v[k] = t;
     }
     sy.parity = par ^ 1;
 }
 
-__global__ void __cluster_dims__(LMC_CTAS, 1, 1) __launch_bounds__(LM4_THREADS)
+// NCTA = CTAs per cluster (8, or 16 = the non-portable maximum: half the rows, hence half the shared-memory gather traffic of the
+// mat-vec, per SM); the cluster shape is a launch attribute.
+template <int NCTA>
+__global__ void __launch_bounds__(LM4_THREADS)
 solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_iters, int lin_iters, double *stats, int ent_cap)
 {
     cg::cluster_group cluster = cg::this_cluster();
-    __shared__ Lm5Smem sm;
+    __shared__ Lm5Smem<NCTA> sm;
     extern __shared__ __align__(16) unsigned char dyn[];
-    const Lm4Layout L = lm4_layout(M, ent_cap);
+    const Lm4Layout L = lm4_layout(M, ent_cap, NCTA);
     double *svec = reinterpret_cast<double *>(dyn + L.off_svec);          // full-length copy of the multiplied vector, [3 * node + axis]
     double *mval = reinterpret_cast<double *>(dyn + L.off_val);           // [entry][thread]
     unsigned short *mcol = reinterpret_cast<unsigned short *>(dyn + L.off_col);   // 3 * column
@@ -1295,7 +1299,7 @@ solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
     auto publish = [&](double a0, double a1, double a2) {
         if (owner) {
 #pragma unroll
-            for (int c = 0; c < LMC_CTAS; ++c) {
+            for (int c = 0; c < NCTA; ++c) {
                 if (!((need >> c) & 1u)) continue;
                 const uint32_t dst = mapa_u32(svec_addr + 24u * (uint32_t)n, (uint32_t)c), rb = mapa_u32(pub_bar, (uint32_t)c);
                 st_async_f64(dst, a0, rb); st_async_f64(dst + 8u, a1, rb); st_async_f64(dst + 16u, a2, rb);
@@ -1332,7 +1336,7 @@ solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
         const Quat t = dq_translation(Quat{a.w, b.x, b.y, b.z}, Quat{b.w, c.x, c.y, c.z});
         x0 = t.x; x1 = t.y; x2 = t.z;
     }
-    const int T = LMC_CTAS * LM4_THREADS, gt = cta * LM4_THREADS + tid;
+    const int T = NCTA * LM4_THREADS, gt = cta * LM4_THREADS + tid;
     double c0n[3] = {0.0, 0.0, 0.0};
     for (int i = gt; i < ws.prepare_blocks; i += T) { c0n[0] += ws.c0_partials[2 * i]; c0n[1] += ws.c0_partials[2 * i + 1]; }
     c0n[2] = (owner ? (double)nnz : 0.0);
@@ -1342,17 +1346,17 @@ solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
     }
     cluster.sync();                                            // every CTA is running, its barriers are initialised
     {   // how many rows will send to me: all-reduce of the per-destination row counts
-        double cnt[LMC_CTAS];
+        double cnt[NCTA];
 #pragma unroll
-        for (int c = 0; c < LMC_CTAS; ++c) cnt[c] = (owner && ((need >> c) & 1u)) ? 1.0 : 0.0;
-        cluster_sum5(sm, sy, cta, cnt);
+        for (int c = 0; c < NCTA; ++c) cnt[c] = (owner && ((need >> c) & 1u)) ? 1.0 : 0.0;
+        cluster_sum5<NCTA>(sm, sy, cta, cnt);
         double mine = 0.0;
 #pragma unroll
-        for (int c = 0; c < LMC_CTAS; ++c) if (c == cta) mine = cnt[c];
+        for (int c = 0; c < NCTA; ++c) if (c == cta) mine = cnt[c];
         pub_bytes = 24u * (uint32_t)mine;
     }
     publish(x0, x1, x2);
-    cluster_sum5(sm, sy, cta, c0n);
+    cluster_sum5<NCTA>(sm, sy, cta, c0n);
     const double nvalid = c0n[1], nnz_total = c0n[2];
     double Ap0, Ap1, Ap2;
     spmv(Ap0, Ap1, Ap2);
@@ -1362,7 +1366,7 @@ solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
         t0[0] += x1 * (0.5 * Ap1 - gb1);
         t0[0] += x2 * (0.5 * Ap2 - gb2);
     }
-    cluster_sum5(sm, sy, cta, t0);
+    cluster_sum5<NCTA>(sm, sy, cta, t0);
     double cost = c0n[0] + t0[0];
     const double cost0 = cost;
 
@@ -1381,7 +1385,7 @@ solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
             p0 = g0 * mi; p1 = g1 * mi; p2 = g2 * mi;
             rzv[0] += g0 * p0; rzv[0] += g1 * p1; rzv[0] += g2 * p2;
         }
-        cluster_sum5(sm, sy, cta, rzv);                        // completes only when every CTA has finished reading svec (x) ...
+        cluster_sum5<NCTA>(sm, sy, cta, rzv);                        // completes only when every CTA has finished reading svec (x) ...
         publish(p0, p1, p2);                                   // ... so p may overwrite it
         double rz = rzv[0];
         double Q0 = 0.0;
@@ -1392,7 +1396,7 @@ solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
                 Ap0 = Ap0 + cdn * p0; Ap1 = Ap1 + cdn * p1; Ap2 = Ap2 + cdn * p2;
                 pap[0] += p0 * Ap0; pap[0] += p1 * Ap1; pap[0] += p2 * Ap2;
             }
-            cluster_sum5(sm, sy, cta, pap);                    // every CTA finished reading svec (p)
+            cluster_sum5<NCTA>(sm, sy, cta, pap);                    // every CTA finished reading svec (p)
             if (!(pap[0] > 0.0)) break;
             const double alpha = rz / pap[0];
             double rq[2] = {0.0, 0.0};
@@ -1402,7 +1406,7 @@ solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
                 dl1 = dl1 + alpha * p1; r1 = r1 - alpha * Ap1; z1 = r1 * mi; rq[0] += r1 * z1; rq[1] += dl1 * (r1 + g1);
                 dl2 = dl2 + alpha * p2; r2 = r2 - alpha * Ap2; z2 = r2 * mi; rq[0] += r2 * z2; rq[1] += dl2 * (r2 + g2);
             }
-            cluster_sum5(sm, sy, cta, rq);
+            cluster_sum5<NCTA>(sm, sy, cta, rq);
             const double rz_new = rq[0], Q1 = -0.5 * rq[1];
             const double beta = rz_new / rz;
             if (owner) { p0 = z0 + beta * p0; p1 = z1 + beta * p1; p2 = z2 + beta * p2; }
@@ -1421,7 +1425,7 @@ solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
             c = cdn * dl1; mad[0] += dl1 * (g1 + r1 + c); mad[1] += dl1 * (g1 - r1 - c); mad[2] += dl1 * g1;
             c = cdn * dl2; mad[0] += dl2 * (g2 + r2 + c); mad[1] += dl2 * (g2 - r2 - c); mad[2] += dl2 * g2;
         }
-        cluster_sum5(sm, sy, cta, mad);
+        cluster_sum5<NCTA>(sm, sy, cta, mad);
         const double model = 0.5 * mad[0];
         const double new_cost = cost - mad[2] + 0.5 * mad[1];
         const double change = cost - new_cost;
@@ -1509,9 +1513,31 @@ extern "C" int df_solve_data_term(float *nodes, int M, const void *node_grid, co
         static bool attr4 = false;
         if (!attr4) { cudaFuncSetAttribute(solve_lm_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4_budget); attr4 = true; }
         if (solve_lm_impl() >= 5) {
+            // 16-CTA clusters (non-portable size) when the rows divide usefully; DF_SOLVE_LM_CTAS overrides
+            static int want = -1;
+            if (want < 0) { const char *e = getenv("DF_SOLVE_LM_CTAS"); want = e ? atoi(e) : 16; }
+            const int ncta = (want == 16 && M >= 256) ? 16 : 8;
+            const Lm4Layout Lb = lm4_layout(M, 0, ncta);
+            const size_t budget = ncta == 16 ? (size_t)216 * 1024 : smem4_budget;      // the 16-CTA variant has 6 KB of static shared memory
+            const int cap = (int)((budget - Lb.total - 16) / ((size_t)LM4_THREADS * 10));
+            const Lm4Layout Lc = lm4_layout(M, cap, ncta);
             static bool attr5 = false;
-            if (!attr5) { cudaFuncSetAttribute(solve_lm_v5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4_budget); attr5 = true; }
-            solve_lm_v5_kernel<<<LMC_CTAS, LM4_THREADS, L.total, s>>>(nodes, M, node_grid, ws, nonlinear_iters, linear_iters, stats_dev, ent_cap);
+            if (!attr5) {
+                cudaFuncSetAttribute(solve_lm_v5_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4_budget);
+                cudaFuncSetAttribute(solve_lm_v5_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+                cudaFuncSetAttribute(solve_lm_v5_kernel<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+                attr5 = true;
+            }
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(ncta); cfg.blockDim = dim3(LM4_THREADS); cfg.dynamicSmemBytes = Lc.total; cfg.stream = s;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = ncta; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            cudaError_t le;
+            if (ncta == 16) le = cudaLaunchKernelEx(&cfg, solve_lm_v5_kernel<16>, nodes, M, node_grid, ws, nonlinear_iters, linear_iters, stats_dev, cap);
+            else le = cudaLaunchKernelEx(&cfg, solve_lm_v5_kernel<8>, nodes, M, node_grid, ws, nonlinear_iters, linear_iters, stats_dev, cap);
+            if (le != cudaSuccess) return (int)le;
         } else
             solve_lm_v4_kernel<<<LMC_CTAS, LM4_THREADS, L.total, s>>>(nodes, M, node_grid, ws, nonlinear_iters, linear_iters, stats_dev, ent_cap);
     }
