@@ -3,13 +3,14 @@
 // set (node vertices are immutable after WarpField::init); one 1024-thread block, deterministic output: nodes are stored
 // cell by cell and, inside a cell, in ascending node index.
 #include "warp_common.cuh"
+#include <cstdlib>
 
 using namespace dfb;
 
 namespace {
 
 __global__ void __launch_bounds__(1024) build_node_grid_kernel(const float *__restrict__ nodes, int M, void *grid, int *cid_tmp, int *order, int *slot,
-                                                               float4 *bvh_box, float4 *bvh_leaf, int L)
+                                                               float4 *bvh_box, float4 *bvh_leaf, int L, float spacings_per_cell)
 {
     __shared__ float smin[3][32], smax[3][32];
     __shared__ NodeGridHeader h;
@@ -34,7 +35,7 @@ __global__ void __launch_bounds__(1024) build_node_grid_kernel(const float *__re
         const float ext = fmaxf(fmaxf(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
         // nodes sample a surface: ~sqrt(M) nodes along the longest extent; ~3 node spacings per cell, so that the 8th
         // neighbour (about 1.7 spacings away) is usually confirmed after the first shell (27 cells)
-        int res = (int)ceilf(sqrtf((float)M) / 3.0f);
+        int res = (int)ceilf(sqrtf((float)M) / spacings_per_cell);
         res = max(1, min(res, NODEGRID_MAX_RES));
         const float cell = ext > 0.f ? ext / (float)res * 1.0001f : 1.f;
         h.ox = lo[0]; h.oy = lo[1]; h.oz = lo[2]; h.cell = cell; h.inv_cell = 1.f / cell;
@@ -188,7 +189,9 @@ extern "C" int df_build_node_grid(const float *nodes, int M, void *grid, void *s
     const int L = bvh_leaves(M);
     float4 *bvh_box = want_order ? reinterpret_cast<float4 *>(tail - bvh_bytes(M)) : nullptr;      // 16-byte aligned: every block above is
     float4 *bvh_leaf = want_order ? bvh_box + 4 * (size_t)L : nullptr;
-    build_node_grid_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(nodes, M, grid, cid_tmp, order, slot, bvh_box, bvh_leaf, L);
+    static float spacings = 0.f;                              // node spacings per cell (default 3, see the kernel); DF_NODEGRID_SPACINGS overrides
+    if (spacings == 0.f) { const char *e = getenv("DF_NODEGRID_SPACINGS"); spacings = e ? (float)atof(e) : 3.0f; if (!(spacings >= 0.5f)) spacings = 3.0f; }
+    build_node_grid_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(nodes, M, grid, cid_tmp, order, slot, bvh_box, bvh_leaf, L, spacings);
     DF_LAUNCH_CHECK();
     return 0;
 }

@@ -64,19 +64,20 @@ size_t layout(SolveWs &ws, char *base, int M, int N)
     ws.cd = (double *)take((size_t)M * 8);
     ws.minv = (double *)take((size_t)M * 8);
     ws.prepare_blocks = (N + 255) / 256;
-    ws.c0_partials = (double *)take((size_t)ws.prepare_blocks * 2 * 8);
+    ws.c0_partials = (double *)take((size_t)ws.prepare_blocks * 8 * 2 * 8);   // one (0.5*|b|^2, count) pair per warp
     ws.vec = (double *)take((size_t)M * 3 * 8 * 7);
     ws.flags = (int *)take(64);
     return o;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) solve_prepare_kernel(const float *__restrict__ nodes, int M, const void *__restrict__ grid,
+constexpr int PREPARE_THREADS = 256;
+
+__global__ void __launch_bounds__(PREPARE_THREADS) solve_prepare_kernel(const float *__restrict__ nodes, int M, const void *__restrict__ grid,
                                                             const float *__restrict__ canon, const float *__restrict__ live, int N, int stride,
                                                             SolveWs ws)
 {
     __shared__ KnnSmem sm;
-    __shared__ double red[2][8];
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     float3 c = make_float3(0.f, 0.f, 0.f), l = c;
     bool valid = false, valid_c = false;       // valid_c: the vertex can be queried; valid: the row enters the solve
@@ -108,15 +109,13 @@ __global__ void __launch_bounds__(256) solve_prepare_kernel(const float *__restr
         const unsigned grp = __match_any_sync(0xffffffffu, n);
         if (n >= 0 && (int)(__ffs(grp) - 1) == (int)(threadIdx.x & 31)) atomicAdd(ws.cnt + n, __popc(grp));
     }
-    // deterministic per-block partials of 0.5*|b|^2 and of the valid-row count
+    // deterministic per-WARP partials of 0.5*|b|^2 and of the valid-row count (no block barrier: a warp whose queries are far
+    // from the node cloud takes several times longer than its neighbours, and nobody should wait for it)
     double vcount = valid ? 1.0 : 0.0;
     for (int o = 16; o > 0; o >>= 1) { half_b2 += __shfl_xor_sync(0xffffffffu, half_b2, o); vcount += __shfl_xor_sync(0xffffffffu, vcount, o); }
-    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = half_b2; red[1][threadIdx.x >> 5] = vcount; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double a = 0.0, bb = 0.0;
-        for (int i = 0; i < 8; ++i) { a += red[0][i]; bb += red[1][i]; }
-        ws.c0_partials[2 * blockIdx.x] = a; ws.c0_partials[2 * blockIdx.x + 1] = bb;
+    if ((threadIdx.x & 31) == 0) {
+        const int wid = blockIdx.x * (PREPARE_THREADS / 32) + (threadIdx.x >> 5);
+        ws.c0_partials[2 * wid] = half_b2; ws.c0_partials[2 * wid + 1] = vcount;
     }
 }
 
@@ -160,38 +159,110 @@ __global__ void __launch_bounds__(256) solve_fill_kernel(SolveWs ws, int N)
     }
 }
 
-// One block per node i: A_i* (sparse, via shared-memory hash), gb_i, diag_i.
-// A node on the rim of the cloud can own 10^5 incidence entries while the median node owns 10^3: the kernel's duration is the
-// heaviest row's, so a row gets a full 1024-thread block (48 registers per thread).
-constexpr int ROWS_THREADS = 1024;
+// One block per node i: A_i* (sparse), gb_i, diag_i.
+//
+// A typical row has ~725 incident entries x 8 contributions that all land on the ~30 distinct columns of the row (a rim node late
+// in a sequence: 10^5 entries).  History (profiles/): v1 = hash insert + shared-memory double atomicAdd per contribution
+// (contended compare-and-swap loops); v2 = equal keys combined inside the warp first (match.any + shuffles), 0.78 -> 0.54 ms on a
+// late frame; a fixed-point integer-atomic variant was 40 % slower AND wrong (weights span 60 orders of magnitude).  This one:
+//   pass 1  the column SET of the row: integer CAS inserts only (lanes holding the same key elect one leader with match.any);
+//           the occupied slots are ranked by key -> the row's sorted column list, written straight to the ELL arrays;
+//   pass 2  the values: every warp owns a private accumulator per column (ROWS_PRIV columns x 16 warps), a warp's lanes holding
+//           the same column are summed with shuffles and the leader adds to the warp's own slot -- no atomics at all;
+//           the per-warp slots are added in warp order at the end, so the row is bit-reproducible from run to run.
+// Rows with more than ROWS_PRIV columns take the atomic path for the values.
+constexpr int ROWS_THREADS = 512;
+constexpr int ROWS_WARPS = ROWS_THREADS / 32;
+constexpr int ROWS_PRIV = 128;
+
+__device__ __forceinline__ int rows_find_slot(const int *keys, int j)
+{
+    unsigned slot = ((unsigned)j * 2654435761u) & (HCAP - 1);
+    for (int probe = 0; probe < HCAP; ++probe) {
+        if (keys[slot] == j) return (int)slot;
+        slot = (slot + 1) & (HCAP - 1);
+    }
+    return 0;
+}
 
 __global__ void __launch_bounds__(ROWS_THREADS) solve_rows_kernel(SolveWs ws, int M, int N, int quirk)
 {
     __shared__ int keys[HCAP];
-    __shared__ double vals[HCAP];
+    __shared__ int slot_rank[HCAP];
     __shared__ int list[HCAP];
+    __shared__ double vals[HCAP];                       // only used by rows with more than ROWS_PRIV columns
+    __shared__ double priv[ROWS_WARPS][ROWS_PRIV];
     __shared__ int nlist;
-    __shared__ double red[3][ROWS_THREADS / 32];
+    __shared__ double red[3][ROWS_WARPS];
     const int i = blockIdx.x;
     const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
     for (int s = tid; s < HCAP; s += ROWS_THREADS) { keys[s] = -1; vals[s] = 0.0; }
+    for (int s = tid; s < ROWS_WARPS * ROWS_PRIV; s += ROWS_THREADS) (&priv[0][0])[s] = 0.0;
     if (tid == 0) nlist = 0;
     __syncthreads();
     const int beg = ws.off[i], end = ws.off[i + 1];
-    const int lane = tid & 31;
-    double g0 = 0.0, g1 = 0.0, g2 = 0.0;
-    // Pixels that are far from the node cloud share one neighbour set, so a node on the rim of the cloud sees the SAME eight
-    // keys in (nearly) all of its incident entries: without aggregation all threads serialise on eight shared-memory words.
-    // Lanes of a warp holding the same key are summed first (match.any + shuffles) and only the group leader probes the hash.
+    const bool quirk_row = quirk && i == 0 && N > 0 && ws.b[0].w != 0.f;
+
+    // ---- pass 1: which columns does the row have?
     for (int base = beg; base < end; base += ROWS_THREADS) {
         const int e = base + tid;
-        const bool valid = e < end;
+        int js[8];
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) js[kk] = -1;
+        if (e < end) {
+            const int v = ws.inc[e] >> 3;
+            const int4 ia = *reinterpret_cast<const int4 *>(ws.idx + (size_t)v * 8), ib = *reinterpret_cast<const int4 *>(ws.idx + (size_t)v * 8 + 4);
+            js[0] = ia.x; js[1] = ia.y; js[2] = ia.z; js[3] = ia.w; js[4] = ib.x; js[5] = ib.y; js[6] = ib.z; js[7] = ib.w;
+        }
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+            const int j = js[kk];
+            const unsigned grp = __match_any_sync(0xffffffffu, j);
+            if (j < 0 || lane != __ffs(grp) - 1) continue;
+            unsigned slot = ((unsigned)j * 2654435761u) & (HCAP - 1);
+            for (int probe = 0; probe < HCAP; ++probe) {
+                const int prev = atomicCAS(&keys[slot], -1, j);
+                if (prev == -1 || prev == j) break;
+                slot = (slot + 1) & (HCAP - 1);
+                if (probe == HCAP - 1) ws.flags[0] = 1;
+            }
+        }
+    }
+    if (quirk_row && tid == 0) {                          // CombinedSolver.h:70-79: N extra edges on (node 0, node 0)
+        unsigned slot = 0u;
+        for (int probe = 0; probe < HCAP; ++probe) {
+            const int prev = atomicCAS(&keys[slot], -1, 0);
+            if (prev == -1 || prev == 0) break;
+            slot = (slot + 1) & (HCAP - 1);
+        }
+    }
+    __syncthreads();
+    for (int s = tid; s < HCAP; s += ROWS_THREADS)
+        if (keys[s] >= 0) list[atomicAdd(&nlist, 1)] = s;
+    __syncthreads();
+    const int nn = nlist;
+    if (nn > ROWCAP && tid == 0) ws.flags[0] = 1;
+    for (int a = tid; a < nn; a += ROWS_THREADS) {        // rank by key = position in the sorted row
+        const int sa = list[a], ka = keys[sa];
+        int rank = 0;
+        for (int bq = 0; bq < nn; ++bq) rank += keys[list[bq]] < ka;
+        slot_rank[sa] = rank;
+        if (rank < ROWCAP) ws.col[(size_t)rank * M + i] = ka;
+    }
+    __syncthreads();
+    const bool use_priv = nn <= ROWS_PRIV;
+
+    // ---- pass 2: the values
+    double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+    for (int base = beg; base < end; base += ROWS_THREADS) {
+        const int e = base + tid;
         double wi = 0.0;
         int js[8];
         float wj[8];
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) { js[kk] = -1; wj[kk] = 0.f; }
-        if (valid) {
+        if (e < end) {
             const int entry = ws.inc[e];
             const int v = entry >> 3;
             wi = (double)ws.w[entry];
@@ -207,60 +278,53 @@ __global__ void __launch_bounds__(ROWS_THREADS) solve_rows_kernel(SolveWs ws, in
             const int j = js[kk];
             const double contrib = wi * (double)wj[kk];
             const unsigned grp = __match_any_sync(0xffffffffu, j);
-            if (j < 0) continue;
-            double sum = contrib;
-            if (grp == 0xffffffffu) {
-                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            } else if (grp & (grp - 1u)) {
-                sum = 0.0;
-                for (unsigned m = grp; m; m &= m - 1u) sum += __shfl_sync(grp, contrib, __ffs(m) - 1);
+            if (j >= 0) {
+                double sum = contrib;
+                if (grp == 0xffffffffu) {
+                    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                } else if (grp & (grp - 1u)) {
+                    sum = 0.0;
+                    for (unsigned m = grp; m; m &= m - 1u) sum += __shfl_sync(grp, contrib, __ffs(m) - 1);
+                }
+                if (lane == __ffs(grp) - 1) {
+                    const int slot = rows_find_slot(keys, j);
+                    if (use_priv) priv[warp][slot_rank[slot]] += sum;     // leaders of one match hold distinct columns: no conflict
+                    else atomicAdd(&vals[slot], sum);
+                }
             }
-            if (lane != __ffs(grp) - 1) continue;
-            unsigned slot = ((unsigned)j * 2654435761u) & (HCAP - 1);
-            for (int probe = 0; probe < HCAP; ++probe) {
-                const int prev = atomicCAS(&keys[slot], -1, j);
-                if (prev == -1 || prev == j) { atomicAdd(&vals[slot], sum); break; }
-                slot = (slot + 1) & (HCAP - 1);
-                if (probe == HCAP - 1) ws.flags[0] = 1;
-            }
+            __syncwarp();                                  // the next neighbour slot may hit a column another lane just updated
         }
     }
-    if (quirk && i == 0 && tid == 0 && N > 0 && ws.b[0].w != 0.f) {
-        // CombinedSolver.h:70-79: N extra edges (v = 0, n_k = node 0 for every k), weights W[0][k]
+    if (quirk_row && tid == 0) {
         double sw = 0.0;
         for (int k = 0; k < 8; ++k) sw += (double)ws.w[k];
         const float4 b = ws.b[0];
         g0 += (double)N * sw * (double)b.x; g1 += (double)N * sw * (double)b.y; g2 += (double)N * sw * (double)b.z;
-        unsigned slot = 0u;
-        for (int probe = 0; probe < HCAP; ++probe) {
-            const int prev = atomicCAS(&keys[slot], -1, 0);
-            if (prev == -1 || prev == 0) { atomicAdd(&vals[slot], (double)N * sw * sw); break; }
-            slot = (slot + 1) & (HCAP - 1);
-        }
+        const int slot = rows_find_slot(keys, 0);
+        if (use_priv) priv[0][slot_rank[slot]] += (double)N * sw * sw;
+        else atomicAdd(&vals[slot], (double)N * sw * sw);
     }
     for (int o = 16; o > 0; o >>= 1) { g0 += __shfl_xor_sync(0xffffffffu, g0, o); g1 += __shfl_xor_sync(0xffffffffu, g1, o); g2 += __shfl_xor_sync(0xffffffffu, g2, o); }
-    if ((tid & 31) == 0) { red[0][tid >> 5] = g0; red[1][tid >> 5] = g1; red[2][tid >> 5] = g2; }
+    if (lane == 0) { red[0][warp] = g0; red[1][warp] = g1; red[2][warp] = g2; }
     __syncthreads();
-    for (int s = tid; s < HCAP; s += ROWS_THREADS)
-        if (keys[s] >= 0) list[atomicAdd(&nlist, 1)] = s;
-    __syncthreads();
-    const int nn = nlist;
-    if (nn > ROWCAP && tid == 0) ws.flags[0] = 1;
-    double dg = 0.0;
     for (int a = tid; a < nn; a += ROWS_THREADS) {
-        const int sa = list[a], ka = keys[sa];
-        int rank = 0;
-        for (int bq = 0; bq < nn; ++bq) rank += keys[list[bq]] < ka;
-        if (rank < ROWCAP) { ws.col[(size_t)rank * M + i] = ka; ws.val[(size_t)rank * M + i] = vals[sa]; }
-        if (ka == i) dg = vals[sa];
-        if (ka == i) ws.diag[i] = dg;
+        const int sa = list[a], ka = keys[sa], rank = slot_rank[sa];
+        double total = 0.0;
+        if (use_priv) {
+#pragma unroll
+            for (int w = 0; w < ROWS_WARPS; ++w) total += priv[w][rank];
+        } else {
+            total = vals[sa];
+        }
+        if (rank < ROWCAP) ws.val[(size_t)rank * M + i] = total;
+        if (ka == i) ws.diag[i] = total;
     }
     if (tid == 0) {
         ws.rownnz[i] = min(nn, ROWCAP);
         double a = 0.0, b = 0.0, c = 0.0;
-        for (int q = 0; q < ROWS_THREADS / 32; ++q) { a += red[0][q]; b += red[1][q]; c += red[2][q]; }
+        for (int q = 0; q < ROWS_WARPS; ++q) { a += red[0][q]; b += red[1][q]; c += red[2][q]; }
         ws.gb[i] = a; ws.gb[M + i] = b; ws.gb[2 * M + i] = c;
-        if (end == beg && !(quirk && i == 0)) ws.diag[i] = 0.0;
+        if (end == beg && !quirk_row) ws.diag[i] = 0.0;
     }
 }
 
@@ -313,7 +377,7 @@ __global__ void __launch_bounds__(LM_THREADS) solve_lm_kernel(float *nodes, int 
     __syncthreads();
     // cost0 = 0.5|b|^2 - x.gb + 0.5 x^T A x
     double c0 = 0.0, nvalid = 0.0;
-    for (int i = tid; i < ws.prepare_blocks; i += LM_THREADS) { c0 += ws.c0_partials[2 * i]; nvalid += ws.c0_partials[2 * i + 1]; }
+    for (int i = tid; i < ws.prepare_blocks * (PREPARE_THREADS / 32); i += LM_THREADS) { c0 += ws.c0_partials[2 * i]; nvalid += ws.c0_partials[2 * i + 1]; }
     c0 = block_sum(c0, red);
     nvalid = block_sum(nvalid, red);
     spmv(ws, M, x, Ap);
@@ -546,7 +610,7 @@ solve_lm_cluster_kernel(float *nodes, int M, SolveWs ws, int nl_iters, int lin_i
             x[n] = t.x; x[M + n] = t.y; x[2 * M + n] = t.z;
         }
     double c0n[3] = {0.0, 0.0, 0.0};
-    for (int i = gt; i < ws.prepare_blocks; i += T) { c0n[0] += ws.c0_partials[2 * i]; c0n[1] += ws.c0_partials[2 * i + 1]; }
+    for (int i = gt; i < ws.prepare_blocks * (PREPARE_THREADS / 32); i += T) { c0n[0] += ws.c0_partials[2 * i]; c0n[1] += ws.c0_partials[2 * i + 1]; }
     for (int n = gt; n < M; n += T) c0n[2] += (double)ws.rownnz[n];
     cluster_sum(cluster, sm, parity, c0n);                     // also publishes x
     const double nvalid = c0n[1], nnz_total = c0n[2];
@@ -778,7 +842,7 @@ solve_lm_cluster_smem_kernel(float *nodes, int M, SolveWs ws, int nl_iters, int 
     }
     const int T = LMC_CTAS * LM3_THREADS, gt = cta * LM3_THREADS + tid;
     double c0n[3] = {0.0, 0.0, 0.0};
-    for (int i = gt; i < ws.prepare_blocks; i += T) { c0n[0] += ws.c0_partials[2 * i]; c0n[1] += ws.c0_partials[2 * i + 1]; }
+    for (int i = gt; i < ws.prepare_blocks * (PREPARE_THREADS / 32); i += T) { c0n[0] += ws.c0_partials[2 * i]; c0n[1] += ws.c0_partials[2 * i + 1]; }
     c0n[2] = (owner ? (double)nnz : 0.0);
     cluster.sync();                                            // every CTA is running: remote shared memory may be written
     publish(x);
@@ -1055,7 +1119,7 @@ solve_lm_v4_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
     }
     const int T = LMC_CTAS * LM4_THREADS, gt = cta * LM4_THREADS + tid;
     double c0n[3] = {0.0, 0.0, 0.0};
-    for (int i = gt; i < ws.prepare_blocks; i += T) { c0n[0] += ws.c0_partials[2 * i]; c0n[1] += ws.c0_partials[2 * i + 1]; }
+    for (int i = gt; i < ws.prepare_blocks * (PREPARE_THREADS / 32); i += T) { c0n[0] += ws.c0_partials[2 * i]; c0n[1] += ws.c0_partials[2 * i + 1]; }
     c0n[2] = (owner ? (double)nnz : 0.0);
     cluster.sync();                                            // every CTA is running: remote shared memory may be written
     publish(x0, x1, x2);
@@ -1338,7 +1402,7 @@ solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
     }
     const int T = NCTA * LM4_THREADS, gt = cta * LM4_THREADS + tid;
     double c0n[3] = {0.0, 0.0, 0.0};
-    for (int i = gt; i < ws.prepare_blocks; i += T) { c0n[0] += ws.c0_partials[2 * i]; c0n[1] += ws.c0_partials[2 * i + 1]; }
+    for (int i = gt; i < ws.prepare_blocks * (PREPARE_THREADS / 32); i += T) { c0n[0] += ws.c0_partials[2 * i]; c0n[1] += ws.c0_partials[2 * i + 1]; }
     c0n[2] = (owner ? (double)nnz : 0.0);
     if (tid == 0) {
         mbar_init(smem_u32(&sm.bar_red[0]), 1u); mbar_init(smem_u32(&sm.bar_red[1]), 1u); mbar_init(pub_bar, 1u);

@@ -158,16 +158,32 @@ __device__ __forceinline__ void knn8_grid(const void *__restrict__ grid, bool va
                 if (bound * bound > bd[7]) { done = true; break; }
             }
             if (r > KNN_SHELL_CAP) break;
+            // Cells of one grid row (fixed y, z) are consecutive in memory, and so are their nodes: a row that lies on the shell
+            // (|dz| == r or |dy| == r) is ONE contiguous run of nodes for the whole x-range, an interior row contributes only its two
+            // end cells.  Rows whose box is farther than the current 8th best (FLT_MAX until eight candidates are known) are skipped;
+            // the box is widened by 1e-4 cell and the bound taken 0.01 % low, so no node is lost to rounding.
+            const float slack = h.cell * 1e-4f;
             for (int z = cz - r; z <= cz + r; ++z) {
                 if (z < 0 || z >= h.gz) continue;
+                const float zlo = h.oz + (float)z * h.cell - slack, zhi = zlo + h.cell + 2.f * slack;
+                const float ez = fmaxf(fmaxf(zlo - qz, qz - zhi), 0.f);
+                if (ez * ez * 0.9999f > bd[7]) continue;
                 for (int y = cy - r; y <= cy + r; ++y) {
                     if (y < 0 || y >= h.gy) continue;
+                    const float ylo = h.oy + (float)y * h.cell - slack, yhi = ylo + h.cell + 2.f * slack;
+                    const float ey = fmaxf(fmaxf(ylo - qy, qy - yhi), 0.f);
+                    if ((ez * ez + ey * ey) * 0.9999f > bd[7]) continue;
                     const bool shell = (z == cz - r) || (z == cz + r) || (y == cy - r) || (y == cy + r);
-                    const int xstep = shell ? 1 : max(2 * r, 1);
-                    for (int x = cx - r; x <= cx + r; x += xstep) {
-                        if (x < 0 || x >= h.gx) continue;
-                        const int cid = x + h.gx * (y + h.gy * z);
-                        const int b = __ldg(cell_start + cid), e = __ldg(cell_start + cid + 1);
+                    const int row = h.gx * (y + h.gy * z);
+                    const int x0 = max(cx - r, 0), x1 = min(cx + r, h.gx - 1);
+                    // segment 0: the whole x-range (shell row) or the left end cell; segment 1: the right end cell of an interior row
+                    for (int seg = 0; seg < (shell || r == 0 ? 1 : 2); ++seg) {
+                        int xa, xb;
+                        if (shell || r == 0) { xa = x0; xb = x1; }
+                        else if (seg == 0) { xa = xb = cx - r; }
+                        else { xa = xb = cx + r; }
+                        if (xa < 0 || xb >= h.gx || xa > xb) continue;
+                        const int b = __ldg(cell_start + row + xa), e = __ldg(cell_start + row + xb + 1);
                         for (int it = b; it < e; ++it) {
                             const float4 nd = __ldg(sorted + it);
                             const float d0 = qx - nd.x, d1 = qy - nd.y, d2 = qz - nd.z;

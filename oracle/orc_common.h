@@ -13,11 +13,17 @@
  * (compile with -ffp-contract=off).
  *
  * PARITY STATUS: the reference's own .cu kernels cannot be compiled by CUDA 12.9 (texture
- * references were removed), and the reference has no tests/fixtures for integrate / raycast /
- * extract / ICP / imgproc.  Those stages are pinned by oracle/_ref (the reference's own kernel
- * SOURCE compiled for the host through a CUDA-on-CPU shim, see oracle/ref_shim/) where that
- * builds; otherwise "parity unpinned".  Quaternion / dual-quaternion / k-NN / warp-solve are
- * pinned by the golden vectors in the reference's tests/ (see tests/test_oracle_golden.py).
+ * references were removed) and the reference has no tests/fixtures for the TSDF / image / ICP
+ * stages.  They are pinned by RUNNING THE REFERENCE'S OWN KERNEL SOURCE on the host:
+ * oracle/_ref/libkfref.so = kfusion/src/cuda/{tsdf_volume,imgproc,proj_icp}.cu compiled with g++
+ * against the CUDA-on-CPU stand-in oracle/ref_shim/cudahost/.  This restatement is BIT-EXACT
+ * against it for integrate, raycast, extract_normals, project_and_remove (dists), compute_dists,
+ * bilateral, truncate, pyramid, points+normals, resize and the ICP correspondences / 27 sums
+ * (tests/test_oracle_vs_reference_kernels.py, digests in tests/golden/kfref_golden.json).
+ * The one stage still pinned only by this restatement + analytic scenes is the zero-crossing
+ * cloud extraction (the reference's extract_kernel is warp-synchronous: "parity unpinned").
+ * Quaternion / dual quaternion / DQB / k-NN are pinned by the reference's headers compiled as they
+ * lie (oracle/_ref/{dq_ref,knn_ref}); the warp solve by the reference's tests/warp_test.cpp.
  */
 #ifndef ORC_COMMON_H
 #define ORC_COMMON_H
