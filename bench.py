@@ -250,7 +250,7 @@ def main():
                 "ms_per_step": ms_e2e / K},
         "gpu_launches": int(info["launches"]) * K,
         "clocks": clocks,
-        "roofline": {"kernel": "integrate_kernel_v2<4>" if os.environ.get("DF_INTEGRATE_IMPL", "1") == "2" else "integrate_kernel<4>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"kernel": {"1": "integrate_kernel<4>", "2": "integrate_kernel_v2<4>"}.get(os.environ.get("DF_INTEGRATE_IMPL", "3"), "integrate_kernel_v3"), "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "voxels_written_per_launch": n_upd, "kernel_ms": integ_ms,
                      "dense_upper_bound_bytes": 8.0 * DIM ** 3 + 2.0 * COLS * ROWS},

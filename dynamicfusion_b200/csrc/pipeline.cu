@@ -36,6 +36,7 @@ struct KinFu {
     float *icp_T = nullptr; int *icp_ok = nullptr; double *icp_scratch = nullptr;
     void *solve_ws = nullptr; size_t solve_ws_bytes = 0; double *solve_stats = nullptr;
     void *extract_ws = nullptr; void *project_ws = nullptr;
+    void *integrate_ws = nullptr;
     unsigned char *activity = nullptr; size_t activity_bytes = 0;   // dfusion.h DF_ACTIVITY_VOXELS: which stretches of the volume hold surface
     float *pinned = nullptr;             // 16 floats: T(12) + ok
     std::vector<float> poses;            // 12 floats per pose
@@ -174,7 +175,7 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_d
         ++k.launches;
         unsigned long long *counter = (p.flags & DF_KINFU_STAGE_TIMING) ? k.n_upd : nullptr;
         if (counter) cudaMemsetAsync(counter, 0, 8, s);
-        return df_integrate_tracked(vol, (const uint16_t *)dists.ptr, dists.pitch, p.cols, p.rows, to_aff(vol2cam), p.intr, counter, k.activity, s);
+        return df_integrate_tracked(vol, (const uint16_t *)dists.ptr, dists.pitch, p.cols, p.rows, to_aff(vol2cam), p.intr, counter, k.activity, k.integrate_ws, s);
     };
     auto raycast_to = [&](const float *cam_pose, Img &pts, Img &nrm) -> int {
         float inv[12], cam2vol[12], Rinv[9];
@@ -380,6 +381,7 @@ extern "C" void *df_kinfu_create(const df_kinfu_params *pp)
     ok = ok && cudaMalloc(&k->solve_ws, k->solve_ws_bytes) == cudaSuccess && cudaMalloc(&k->solve_stats, 64) == cudaSuccess;
     df_volume v = vol_of(*k);
     ok = ok && cudaMalloc(&k->extract_ws, df_extract_workspace_bytes(v)) == cudaSuccess;
+    ok = ok && cudaMalloc(&k->integrate_ws, df_integrate_workspace_bytes(p.cols, p.rows)) == cudaSuccess;
     k->activity_bytes = df_volume_activity_bytes(v);
     ok = ok && cudaMalloc(&k->activity, k->activity_bytes) == cudaSuccess && cudaMemset(k->activity, 0, k->activity_bytes) == cudaSuccess;
     ok = ok && cudaMalloc(&k->project_ws, df_project_workspace_bytes(p.cols, p.rows)) == cudaSuccess;
@@ -407,7 +409,7 @@ extern "C" void df_kinfu_destroy(void *h)
     cudaFree(k->canon.ptr); cudaFree(k->canon_nrm.ptr); cudaFree(k->canon_visible.ptr);
     cudaFree(k->cloud); cudaFree(k->cloud_nrm); cudaFree(k->cloud_count); cudaFree(k->nodes); cudaFree(k->node_grid);
     cudaFree(k->icp_T); cudaFree(k->icp_ok); cudaFree(k->icp_scratch); cudaFree(k->solve_ws); cudaFree(k->solve_stats);
-    cudaFree(k->extract_ws); cudaFree(k->project_ws); cudaFree(k->activity); cudaFreeHost(k->pinned); cudaFree(k->n_upd);
+    cudaFree(k->extract_ws); cudaFree(k->project_ws); cudaFree(k->activity); cudaFree(k->integrate_ws); cudaFreeHost(k->pinned); cudaFree(k->n_upd);
     for (int e = 0; e <= NSTAGES; ++e) cudaEventDestroy(k->ev[e]);
     delete k;
 }

@@ -183,7 +183,7 @@ class TsdfVolume:
         rows, cols = dists.shape
         capi.check(_lib().df_integrate_tracked(self._vol(), dists.data_ptr(), cols * 2, cols, rows, capi.make_aff(*vol2cam),
                                                capi.make_intr(*intr), n_updated.data_ptr() if n_updated is not None else None,
-                                               self.activity_.data_ptr() if self.activity_ is not None else None, _stream()))
+                                               self.activity_.data_ptr() if self.activity_ is not None else None, None, _stream()))
         return vol2cam
 
     def raycast(self, camera_pose, intr, cols: int, rows: int):

@@ -65,8 +65,12 @@ int df_integrate(df_volume vol, const uint16_t *dists, size_t dists_pitch, int c
  * integration of that volume through df_integrate_tracked. */
 #define DF_ACTIVITY_VOXELS 1024
 size_t df_volume_activity_bytes(df_volume vol);
+/* workspace (optional, device memory, df_integrate_workspace_bytes(cols, rows) bytes): per-tile maximum ray length of the frame,
+ * used to skip the parts of the volume that lie behind the observed surface; NULL = allocated stream-ordered per call. */
+size_t df_integrate_workspace_bytes(int cols, int rows);
 int df_integrate_tracked(df_volume vol, const uint16_t *dists, size_t dists_pitch, int cols, int rows,
-                         df_aff3f vol2cam, df_intr intr, unsigned long long *n_updated, unsigned char *activity, void *stream);
+                         df_aff3f vol2cam, df_intr intr, unsigned long long *n_updated, unsigned char *activity, void *workspace,
+                         void *stream);
 
 /* device::raycast, points variant (internal.hpp:113-114, tsdf_volume.cu:341-405,459-474).
  * cam2vol = volume_pose^-1 * camera_pose, Rinv = cam2vol.R^-1 (tsdf_volume.cpp:157-174). */

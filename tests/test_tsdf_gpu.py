@@ -158,9 +158,11 @@ def test_tracked_extraction_equals_full_scan(orc):
     assert int(vols[1].activity_.sum().item()) == 0 and int(vols[1].fetchCloud(1000)[1].item()) == 0
 
 
-def test_integrate_v2_variant_bit_exact_in_subprocess(orc):
-    """the alternative integrate kernel (DF_INTEGRATE_IMPL=2: approximate-reciprocal projection with exact fallback, sqrt only in
-    the band) is selected per process; it must store the same u32 voxels as the oracle"""
+@pytest.mark.parametrize("impl", ["1", "2"])
+def test_integrate_alternative_kernels_bit_exact_in_subprocess(orc, impl):
+    """the integrate kernel is selected per process (DF_INTEGRATE_IMPL): 3 = default (v1 arithmetic + warp-level visibility culling,
+    covered by every other test), 1 = plain, 2 = approximate-reciprocal projection with exact fallback; all must store the same u32
+    voxels as the oracle"""
     import os, subprocess, sys
     script = (
         "import numpy as np, torch\n"
@@ -179,7 +181,7 @@ def test_integrate_v2_variant_bit_exact_in_subprocess(orc):
         "got = vol.data_.cpu().numpy().view(np.uint32)\n"
         "assert np.count_nonzero(ref) > 100000\n"
         "raise SystemExit(0 if np.array_equal(got, ref) else 3)\n")
-    env = dict(os.environ, DF_INTEGRATE_IMPL="2")
+    env = dict(os.environ, DF_INTEGRATE_IMPL=impl)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", script], cwd=root, env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
