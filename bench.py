@@ -54,10 +54,17 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -65,17 +72,28 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        # the sampler is started before the warm-up frames (nvidia-smi needs ~0.3 s to emit its first line); only the samples that
+        # arrived between mark_begin() and mark_end() -- i.e. while the timed frames were executing -- are reported.  A timed
+        # region shorter than the sampling period falls back to the samples within 0.25 s around it and says so.
+        inside = [r for (t, r) in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or t)]
+        note = None
+        if not inside and self.t0 is not None:
+            inside = [r for (t, r) in self.rows if self.t0 - 0.25 <= t <= (self.t1 or t) + 0.25]
+            note = "timed region shorter than the sampling period: samples within 0.25 s of it"
+        sm = [float(r[0]) for r in inside if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in inside if len(r) >= 6 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        reasons = sorted({n for r in inside if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        out = {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        if note:
+            out["note"] = note
+        return out
 
 
 def make_frames(n: int, seed: int):
@@ -185,19 +203,21 @@ def main():
 
     def timed(run_frame):
         """frame 0 + W warm-up frames untimed, then exactly K frames between barrier+sync, CUDA events on the launching stream"""
+        sampler = ClockSampler(local_rank)
+        sampler.start()
         k = kf.KinFu(params())
         ok = 0
         for t in range(1 + W):
             run_frame(k, t)
         barrier()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.mark_begin()
         e0.record()
         for t in range(1 + W, 1 + W + K):
             ok += run_frame(k, t)
         e1.record()
         barrier()
+        sampler.mark_end()
         clocks = sampler.stop()
         ms = e0.elapsed_time(e1)
         info = k.info()
