@@ -123,3 +123,32 @@ def test_c4_768_hd_depth_integrate_raycast(orc):
     m = ~np.isnan(rp[..., 0])
     np.testing.assert_allclose(gp[m], rp[m], rtol=1e-4, atol=1e-6)
     assert np.array_equal(gp.view(np.uint32), rp.view(np.uint32)) and np.array_equal(gn.view(np.uint32), rn.view(np.uint32))
+
+
+def test_c4_768_hd_full_loop_two_frames(orc):
+    """configs[3] through the whole frame loop (the largest sizes the path is specified for): 768^3 / 1.5 m volume, 1280x720 depth,
+    two frames against the oracle's loop -- first frame bit-exact, second frame (ICP + warp + solve + fusion) statistically"""
+    from oracle import orc_pipe
+    cols, rows = 1280, 720
+    K_hd = (K[0] * 2, K[1] * 2, 640.0, 360.0)
+    p = _params(768, 0, max_nodes=2048, cols=cols, rows=rows, K_=K_hd)
+    for i in range(3):
+        p.volume_size[i] = 1.5
+    p.volume_pose.t[0] = -0.75; p.volume_pose.t[1] = -0.75; p.volume_pose.t[2] = 0.5
+    gpu, cpu = kf.KinFu(p), orc_pipe.KinFu(orc_pipe.params_from(p))
+    d0 = synth.umbrella_depth(0, cols=cols, rows=rows, K=K_hd)
+    assert gpu(d0) is False and cpu(d0) is False
+    assert np.array_equal(gpu.buffer("volume"), cpu.buffer("volume"))
+    gi, ci = gpu.info(), cpu.info()
+    assert gi["nodes"] == ci["nodes"] >= 1000 and gi["cloud_points"] == ci["cloud_points"] > 500_000
+    d1 = synth.umbrella_depth(1, cols=cols, rows=rows, K=K_hd)
+    assert gpu(d1) is True and cpu(d1) is True
+    Rg, tg = gpu.getCameraPose(1)
+    Rc, tc = cpu.getCameraPose(1)
+    assert np.abs(Rg - Rc).max() < 2e-4 and np.abs(tg - tc).max() < 2e-4
+    fg, wg = _tsdf(gpu.buffer("volume"))
+    fc, wc = _tsdf(cpu.buffer("volume"))
+    assert np.mean(wg != wc) < 2e-2
+    sg, sc = gpu.buffer("solve_stats"), cpu.buffer("solve_stats")
+    assert abs(sg[3] - sc[3]) <= 0.01 * sc[3] and abs(sg[1] - sc[1]) <= 5e-2 * sc[1]
+    gpu.close(); cpu.close()
