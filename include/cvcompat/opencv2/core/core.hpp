@@ -56,6 +56,7 @@ namespace cv
         Vec(T a, T b, T c, T d) : Matx<T, cn, 1>(a, b, c, d) {}
         explicit Vec(const T *p) { for (int i = 0; i < cn; ++i) this->val[i] = p[i]; }
         Vec(const Matx<T, cn, 1> &o) : Matx<T, cn, 1>(o) {}
+        template <typename T2> explicit Vec(const Vec<T2, cn> &o) { for (int i = 0; i < cn; ++i) this->val[i] = (T)o.val[i]; }   // cv::Vec3d(Vec3f)
         static Vec all(T a) { Vec r; for (int i = 0; i < cn; ++i) r.val[i] = a; return r; }
         T &operator[](int i) { return this->val[i]; }
         const T &operator[](int i) const { return this->val[i]; }
@@ -191,6 +192,30 @@ namespace cv
         size_t elemSize() const { static const int sz[] = {1, 1, 2, 2, 4, 4, 8}; return (size_t)sz[type_ & 7] * (size_t)((type_ >> 3) + 1); }
         int type() const { return type_; }
         bool empty() const { return data == 0 || rows * cols == 0; }
+        // dst(i) = saturate(src(i) * alpha + beta) for the single-channel depth previews of demo.cpp (u8/u16/f32 -> u8/u16/f32)
+        void convertTo(Mat &dst, int rtype, double alpha = 1.0, double beta = 0.0) const
+        {
+            const int cn = (type_ >> 3) + 1;
+            Mat out(rows, cols, CV_MAKETYPE(rtype & 7, cn));
+            for (int r = 0; r < rows; ++r)
+                for (int c = 0; c < cols * cn; ++c) {
+                    double v = 0;
+                    switch (type_ & 7) {
+                        case CV_8U: v = ptr<unsigned char>(r)[c]; break;
+                        case CV_16U: v = ptr<unsigned short>(r)[c]; break;
+                        case CV_32F: v = ptr<float>(r)[c]; break;
+                        default: break;
+                    }
+                    v = v * alpha + beta;
+                    switch (rtype & 7) {
+                        case CV_8U: out.ptr<unsigned char>(r)[c] = (unsigned char)(v < 0 ? 0 : v > 255 ? 255 : (int)(v + 0.5)); break;
+                        case CV_16U: out.ptr<unsigned short>(r)[c] = (unsigned short)(v < 0 ? 0 : v > 65535 ? 65535 : (int)(v + 0.5)); break;
+                        case CV_32F: out.ptr<float>(r)[c] = (float)v; break;
+                        default: break;
+                    }
+                }
+            dst = out;
+        }
         template <typename T> T *ptr(int r = 0) { return (T *)(data + (size_t)r * step); }
         template <typename T> const T *ptr(int r = 0) const { return (const T *)(data + (size_t)r * step); }
         template <typename T> T &at(int i) { return rows == 1 ? ptr<T>(0)[i] : ptr<T>(i / cols)[i % cols]; }
