@@ -99,6 +99,30 @@ def build_cpp_program(src: Path, out: Path) -> Path:
     return out
 
 
+REF_DEMO_SRC = Path("/root/reference/apps/demo.cpp")
+REF_DEMO_BIN = ROOT / "tests" / "cpp" / "_build" / "ref_demo"
+
+
+def build_reference_demo(force: bool = False):
+    """The reference's OWN apps/demo.cpp, compiled from where it lies and UNCHANGED, against include/kfusion + the headless OpenCV
+    stand-ins (include/cvcompat) and linked with libkfusion.so / libdfusion.so -- the drop-in claim of INTEGRATION.md made literal.
+    Only possible where /root/reference exists; the binary (git-ignored) travels to the GPU box with the snapshot."""
+    if not REF_DEMO_SRC.exists():
+        return None
+    build_mirror()
+    REF_DEMO_BIN.parent.mkdir(parents=True, exist_ok=True)
+    deps = [REF_DEMO_SRC, MIRROR_LIB] + sorted((ROOT / "include").rglob("*.h*"))
+    if not force and REF_DEMO_BIN.exists() and all(d.stat().st_mtime <= REF_DEMO_BIN.stat().st_mtime for d in deps):
+        return REF_DEMO_BIN
+    gxx = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
+    cmd = [gxx, "-std=c++17", "-O1", "-w", *MIRROR_INC, "-o", str(REF_DEMO_BIN), str(REF_DEMO_SRC), "-L", str(HERE), "-lkfusion", "-ldfusion",
+           "-lz", "-Wl,-rpath," + str(HERE), "-Wl,-rpath,$ORIGIN/../../../dynamicfusion_b200"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building the reference's apps/demo.cpp failed:\n" + r.stdout)
+    return REF_DEMO_BIN
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
     if "--mirror" in sys.argv:

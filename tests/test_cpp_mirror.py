@@ -1,8 +1,12 @@
 """The C++ mirror of the reference's public API (include/kfusion/*.hpp + libkfusion.so): a demo.cpp-like program
 (tests/cpp/demo_like.cpp) must compile and link against it on the CPU box, and run green on the GPU."""
+import os
+import struct
 import subprocess
+import zlib
 from pathlib import Path
 
+import numpy as np
 import pytest
 
 ROOT = Path(__file__).resolve().parents[1]
@@ -31,3 +35,77 @@ def test_demo_like_program_runs():
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "all checks passed" in r.stdout
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# the reference's OWN apps/demo.cpp, unchanged (compiled from /root/reference where it lies; the binary travels to the GPU box)
+def write_png(path, arr):
+    """8-bit RGB (H, W, 3) or 16-bit grey (H, W) PNG, filter type 0, one IDAT"""
+    h, w = arr.shape[:2]
+    if arr.dtype == np.uint16:
+        ctype, depth, data, stride = 0, 16, arr.astype(">u2").tobytes(), w * 2
+    else:
+        ctype, depth, data, stride = 2, 8, np.ascontiguousarray(arr, np.uint8).tobytes(), w * 3
+    raw = b"".join(b"\x00" + data[y * stride:(y + 1) * stride] for y in range(h))
+
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xffffffff)
+    Path(path).write_bytes(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, 0))
+                           + chunk(b"IDAT", zlib.compress(raw, 1)) + chunk(b"IEND", b""))
+
+
+def test_headless_imread_reads_depth_and_colour_pngs(tmp_path):
+    from dynamicfusion_b200 import build
+    rng = np.random.default_rng(5)
+    depth = rng.integers(0, 6000, (48, 64), dtype=np.uint16)
+    color = rng.integers(0, 256, (48, 64, 3), dtype=np.uint8)
+    (tmp_path / "depth").mkdir()
+    write_png(tmp_path / "depth" / "000.png", depth)
+    write_png(tmp_path / "c.png", color)
+    exe = tmp_path / "imread_check"
+    cmd = ["/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++", "-std=c++17", "-O1", *build.MIRROR_INC, "-o", str(exe),
+           str(ROOT / "tests" / "cpp" / "imread_check.cpp"), "-lz"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe), str(tmp_path / "depth"), str(tmp_path / "c.png")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    v = [int(x) for x in out.stdout.split()]
+    disp = np.clip(np.floor(depth.astype(np.float64) * (255.0 / 4000) + 0.5), 0, 255)
+    assert v == [48, 64, 2, int(depth.sum(dtype=np.uint64)), 48, 64, 16, int(color[..., 2].sum()), int(color[..., 1].sum()), int(color[..., 0].sum()),
+                 int(disp.sum()), 1]
+
+
+def test_reference_demo_compiles_and_links_unchanged():
+    from dynamicfusion_b200 import build
+    if not build.REF_DEMO_SRC.exists():
+        pytest.skip("/root/reference is not mounted here")
+    exe = build.build_reference_demo(force=True)
+    assert exe.exists()
+    needed = subprocess.run(["readelf", "-d", str(exe)], capture_output=True, text=True).stdout
+    assert "libkfusion.so" in needed                          # the application binds to the mirror ...
+    mirror = subprocess.run(["readelf", "-d", str(ROOT / "dynamicfusion_b200" / "libkfusion.so")], capture_output=True, text=True).stdout
+    assert "libdfusion.so" in mirror                          # ... which binds to the C ABI
+    undefined = subprocess.run(["nm", "-DCu", str(exe)], capture_output=True, text=True).stdout
+    for sym in ("kfusion::KinFu::operator()", "kfusion::KinFuParams::default_params_dynamicfusion", "kfusion::KinFu::renderImage",
+                "kfusion::KinFu::getCameraPose", "kfusion::WarpField::getNodesAsMat", "kfusion::cuda::DeviceMemory2D::upload"):
+        assert sym in undefined, sym                          # the reference app's imports, resolved by libkfusion.so
+
+
+@pytest.mark.gpu
+def test_reference_demo_runs_headless_on_a_png_sequence(tmp_path):
+    """apps/demo.cpp <dir>: globs <dir>/depth and <dir>/color, uploads every depth frame, calls KinFu::operator(), renders and
+    'shows' the ray-cast view, follows the camera pose and fetches the warp nodes every frame (apps/demo.cpp:80-128)"""
+    from dynamicfusion_b200 import build, synth
+    exe = build.REF_DEMO_BIN
+    if not exe.exists():
+        pytest.skip("tests/cpp/_build/ref_demo was not built (needs /root/reference at build time)")
+    (tmp_path / "depth").mkdir(); (tmp_path / "color").mkdir()
+    for t in range(4):
+        write_png(tmp_path / "depth" / f"{t:04d}.png", synth.umbrella_depth(t))
+        write_png(tmp_path / "color" / f"{t:04d}.png", np.full((480, 640, 3), 40 * t, np.uint8))
+    env = dict(os.environ, DF_CVCOMPAT_VERBOSE="1")
+    r = subprocess.run([str(exe), str(tmp_path)], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stderr.count("imshow Scene 480x1280") == 3          # frames 1..3 have an image (frame 0 only initialises)
+    assert r.stderr.count("imshow Depth 480x640") == 4 and r.stderr.count("imshow Image 480x640") == 4
+    assert "Exception" not in r.stdout and "Bad alloc" not in r.stdout
