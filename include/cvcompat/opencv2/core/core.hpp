@@ -4,6 +4,7 @@
 // include directory BEFORE include/cvcompat and this file is never seen.  Written for this repo (not copied from OpenCV);
 // arithmetic follows OpenCV's definitions (float, left-to-right) so that host-side poses match df_hostmath.h.
 #pragma once
+#include <ostream>
 #include <cmath>
 #include <cstddef>
 #include <cstdio>
@@ -94,6 +95,13 @@ namespace cv
         const T id = T(1) / det;
         return Matx<T, 3, 3>(c00 * id, (c * h - b * i) * id, (b * f - c * e) * id, c01 * id, (a * i - c * g) * id, (c * d - a * f) * id,
                              c02 * id, (b * g - a * h) * id, (a * e - b * d) * id);
+    }
+
+    template <typename T, int m, int n> inline std::ostream &operator<<(std::ostream &os, const Matx<T, m, n> &v)
+    {
+        os << "[";
+        for (int i = 0; i < m * n; ++i) os << (i ? (i % n == 0 && n > 1 ? "; " : ", ") : "") << v.val[i];
+        return os << "]";
     }
 
     typedef Vec<float, 3> Vec3f;

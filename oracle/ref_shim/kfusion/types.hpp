@@ -29,6 +29,8 @@ namespace cv
     inline Vec3f operator*(const Vec3f& a, float s) { return Vec3f(a[0] * s, a[1] * s, a[2] * s); }
     inline Vec3f operator*(float s, const Vec3f& a) { return Vec3f(a[0] * s, a[1] * s, a[2] * s); }
     inline bool operator!=(const Vec3f& a, const Vec3f& b) { return a[0] != b[0] || a[1] != b[1] || a[2] != b[2]; }
+    inline bool operator==(const Vec3f& a, const Vec3f& b) { return !(a != b); }
+    inline std::ostream& operator<<(std::ostream& os, const Vec3f& v) { return os << "[" << v[0] << ", " << v[1] << ", " << v[2] << "]"; }
     inline Vec3f normalize(const Vec3f& v) { float n = std::sqrt(v.dot(v)); return Vec3f(v[0] / n, v[1] / n, v[2] / n); }
 
     // only named by Quaternion(const Vec3f& normal), which the pinned paths never instantiate
