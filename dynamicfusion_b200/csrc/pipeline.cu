@@ -172,7 +172,7 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_d
         float inv[12], vol2cam[12];
         dfh_aff_inv(cam_pose, inv);
         dfh_aff_mul(inv, vol_pose, vol2cam);                           // camera_pose.inv() * pose_, tsdf_volume.cpp:112
-        ++k.launches;
+        k.launches += df_integrate_launch_count(vol);
         unsigned long long *counter = (p.flags & DF_KINFU_STAGE_TIMING) ? k.n_upd : nullptr;
         if (counter) cudaMemsetAsync(counter, 0, 8, s);
         return df_integrate_tracked(vol, (const uint16_t *)dists.ptr, dists.pitch, p.cols, p.rows, to_aff(vol2cam), p.intr, counter, k.activity, k.integrate_ws, s);
@@ -266,7 +266,7 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_d
         CKD(df_solve_data_term(k.nodes, k.M, k.node_grid, (const float *)k.canon.ptr, (const float *)k.cur_pts[0].ptr, npix, 4,
                                p.solver_nonlinear_iters, p.solver_linear_iters,
                                (p.flags & DF_KINFU_REF_GRAPH_QUIRK) ? DF_SOLVE_REF_GRAPH_QUIRK : 0, k.solve_stats, k.solve_ws, s));   // :387
-        k.launches += 6;
+        k.launches += 5;                                               // prepare, scan, fill, rows, lm
         mark(k, 5);
         {
             // second warp (:389) queries exactly the vertices the solve just built its graph for (CombinedSolver.h:66-84):
