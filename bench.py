@@ -281,6 +281,16 @@ def main():
         dt, cinfo = run_cpu(frames[: 1 + 1 + steps_cpu], 1, steps_cpu)
         line["cpu_baseline"] = {"value": steps_cpu / dt, "unit": "frames/s", "cores": host_threads(), "kind": "port",
                                 "sample": f"{steps_cpu} timed frames (+1 init, +1 warm-up) of the same sequence through the CPU oracle (OpenMP)"}
+        # SURVEY 8d also asks for the single-thread figure (the reference's own warp / k-NN loops are serial): 2 frames, 1 OpenMP thread
+        try:
+            import ctypes
+            gomp = ctypes.CDLL("libgomp.so.1")
+            gomp.omp_set_num_threads(1)
+            dt1, _ = run_cpu(frames[:3], 0, 2)
+            gomp.omp_set_num_threads(host_threads())
+            line["cpu_baseline"]["single_thread_value"] = 2 / dt1
+        except Exception as e:                                                  # informational only
+            line["cpu_baseline"]["single_thread_value"] = None
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
