@@ -189,7 +189,7 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_d
     auto extract = [&]() -> int {                                      // compute_points + compute_normals, tsdf_volume.cpp:313-325
         int st = df_extract_cloud_tracked(vol, p.volume_pose, k.cloud, p.cloud_capacity, k.cloud_count, k.extract_ws, k.activity, s);
         if (st) return st;
-        k.launches += 4;
+        k.launches += 5;                                               // count, 2 scans, emit + the normals kernel below
         k.last_cloud = -1;
         return df_extract_normals(vol, k.cloud, p.cloud_capacity, k.cloud_count, p.volume_pose, Rinv_vol, p.gradient_delta_factor, k.cloud_nrm, s);
     };
