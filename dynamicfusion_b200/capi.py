@@ -69,6 +69,10 @@ PROTOTYPES = {
     "df_resize_points_normals": (_i, [_vp, _sz, _vp, _sz, _i, _i, _vp, _sz, _vp, _sz, _vp]),
     "df_render_image": (_i, [_vp, _sz, _vp, _sz, _i, _i, C.POINTER(C.c_float), _vp, _sz, _vp]),
     "df_render_tangent_colors": (_i, [_vp, _sz, _i, _i, _vp, _sz, _vp]),
+    "df_render_image_depth": (_i, [_vp, _sz, _vp, _sz, _i, _i, Intr, C.POINTER(C.c_float), _vp, _sz, _vp]),
+    "df_normals_mask_depth": (_i, [Intr, _vp, _sz, _i, _i, _vp, _sz, _vp]),
+    "df_cloud_to_depth": (_i, [_vp, _sz, _i, _i, _vp, _sz, _vp]),
+    "df_resize_depth_normals": (_i, [_vp, _sz, _vp, _sz, _i, _i, _vp, _sz, _vp, _sz, _vp]),
     "df_icp_accumulate": (_i, [_vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _i, _i, Intr, Aff3f, _f, _f, _vp, _vp]),
     "df_icp_estimate": (_i, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i),
                              C.POINTER(_sz), _i, C.POINTER(_i), Intr, _f, _f, _vp, _vp, _vp, _vp]),

@@ -204,12 +204,33 @@ void kfusion::cuda::renderTangentColors(const Normals& normals, Image& image)
     dfSafeCall(df_render_tangent_colors((const float *)normals.ptr(), normals.step(), normals.cols(), normals.rows(), image.ptr(), image.step(), 0));
     waitAllDefaultStream();
 }
-// USE_DEPTH-only entry points of the reference (internal.hpp:6 leaves USE_DEPTH undefined): not on the hot path
 static void not_built(const char *what) { kfusion::cuda::error(what, __FILE__, __LINE__); }
-void kfusion::cuda::computeNormalsAndMaskDepth(const Intr&, Depth&, Normals&) { not_built("computeNormalsAndMaskDepth: USE_DEPTH path is not part of the hot path"); }
-void kfusion::cuda::cloudToDepth(const Cloud&, Depth&) { not_built("cloudToDepth: unused by the reference's pipeline"); }
-void kfusion::cuda::resizeDepthNormals(const Depth&, const Normals&, Depth&, Normals&) { not_built("resizeDepthNormals: USE_DEPTH path is not part of the hot path"); }
-void kfusion::cuda::renderImage(const Depth&, const Normals&, const Intr&, const Vec3f&, Image&) { not_built("renderImage(depth): USE_DEPTH path is not part of the hot path"); }
+// USE_DEPTH-path entry points of the reference (internal.hpp:6 leaves USE_DEPTH undefined, so its own frame loop never calls them);
+// host wrappers as imgproc.cpp:52-60,98-103,112-121,152-164
+void kfusion::cuda::computeNormalsAndMaskDepth(const Intr& intr, Depth& depth, Normals& normals)
+{
+    normals.create(depth.rows(), depth.cols());
+    dfSafeCall(df_normals_mask_depth(to_df(intr), depth.ptr(), depth.step(), depth.cols(), depth.rows(), (float *)normals.ptr(), normals.step(), 0));
+}
+void kfusion::cuda::cloudToDepth(const Cloud& cloud, Depth& depth)
+{
+    depth.create(cloud.rows(), cloud.cols());
+    dfSafeCall(df_cloud_to_depth((const float *)cloud.ptr(), cloud.step(), cloud.cols(), cloud.rows(), depth.ptr(), depth.step(), 0));
+}
+void kfusion::cuda::resizeDepthNormals(const Depth& depth, const Normals& normals, Depth& depth_out, Normals& normals_out)
+{
+    depth_out.create(depth.rows() / 2, depth.cols() / 2);
+    normals_out.create(normals.rows() / 2, normals.cols() / 2);
+    dfSafeCall(df_resize_depth_normals(depth.ptr(), depth.step(), (const float *)normals.ptr(), normals.step(), depth.cols(), depth.rows(),
+                                       depth_out.ptr(), depth_out.step(), (float *)normals_out.ptr(), normals_out.step(), 0));
+}
+void kfusion::cuda::renderImage(const Depth& depth, const Normals& normals, const Intr& intr, const Vec3f& light_pose, Image& image)
+{
+    image.create(depth.rows(), depth.cols());
+    dfSafeCall(df_render_image_depth(depth.ptr(), depth.step(), (const float *)normals.ptr(), normals.step(), depth.cols(), depth.rows(), to_df(intr),
+                                     light_pose.val, image.ptr(), image.step(), 0));
+    waitAllDefaultStream();
+}
 
 // ------------------------------------------------------------------------------------------------------------------
 // ProjectiveICP: projective_icp.cpp:68-213
@@ -337,7 +358,16 @@ void TsdfVolume::integrate(const Dists& dists, const Affine3f& camera_pose, cons
                             to_df(vol2cam), to_df(intr), 0, 0));
     cudaSafeCall(cudaDeviceSynchronize());                                // the reference's launcher synchronises (tsdf_volume.cu:160)
 }
-void TsdfVolume::raycast(const Affine3f&, const Intr&, Depth&, Normals&) { not_built("raycast(depth): USE_DEPTH path is not part of the hot path"); }
+// depth variant (tsdf_volume.cu:273-339,441-456): the same march; on a hit the reference stores static_cast<ushort>(vertex.z * 1000) of the
+// camera-frame vertex and 0 elsewhere -- i.e. the points variant followed by cloud_to_depth's conversion (NaN -> 0)
+void TsdfVolume::raycast(const Affine3f& camera_pose, const Intr& intr, Depth& depth, Normals& normals)
+{
+    Cloud points;
+    points.create(depth.rows(), depth.cols());
+    raycast(camera_pose, intr, points, normals);
+    dfSafeCall(df_cloud_to_depth((const float *)points.ptr(), points.step(), points.cols(), points.rows(), depth.ptr(), depth.step(), 0));
+    cudaSafeCall(cudaDeviceSynchronize());
+}
 void TsdfVolume::raycast(const Affine3f& camera_pose, const Intr& intr, Cloud& points, Normals& normals)
 {
     Affine3f cam2vol = pose_.inv() * camera_pose;

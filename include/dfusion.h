@@ -125,6 +125,15 @@ int df_render_image(const float *points, size_t points_pitch, const float *norma
 int df_render_tangent_colors(const float *normals, size_t normals_pitch, int cols, int rows, void *image_bgra, size_t image_pitch,
                              void *stream);
 
+/* The reference's USE_DEPTH-path image operations (cuda/imgproc.hpp:15,21,23,31; imgproc.cu:145-200,277-303,307-366,420-537).  The
+ * default build of the reference does not take this path; they exist so that every function of its public header is served. */
+int df_render_image_depth(const uint16_t *depth, size_t depth_pitch, const float *normals, size_t normals_pitch, int cols, int rows,
+                          df_intr intr, const float *light_pose_host3, void *image_bgra, size_t image_pitch, void *stream);
+int df_normals_mask_depth(df_intr intr, uint16_t *depth, size_t depth_pitch, int cols, int rows, float *normals, size_t normals_pitch, void *stream);
+int df_cloud_to_depth(const float *cloud, size_t cloud_pitch, int cols, int rows, uint16_t *depth, size_t depth_pitch, void *stream);
+int df_resize_depth_normals(const uint16_t *dsrc, size_t dsrc_pitch, const float *nsrc, size_t nsrc_pitch, int src_cols, int src_rows,
+                            uint16_t *ddst, size_t ddst_pitch, float *ndst, size_t ndst_pitch, void *stream);
+
 /* ------------------------------------------------------------------ projective ICP -------------------------------------------------------- */
 /* ComputeIcpHelper::operator() points variant (internal.hpp:67-102, proj_icp.cu:80-108,350-394,448-467): one
  * data-association + 27-term reduction pass at one pyramid level.  scratch: device buffer of DF_ICP_SCRATCH_DOUBLES
