@@ -149,6 +149,8 @@ def build_reference_tests(force: bool = False) -> dict:
     jobs["mine_warp_test"] = [gxx, "-std=c++17", "-O1", "-w", "-I", str(REFCOMPAT), *MIRROR_INC, "-I", str(ROOT / "include" / "opt"),
                               str(REF_TESTS_DIR / "warp_test.cpp"), main_cpp, "-L", str(HERE), "-lkfusion", "-ldfusion",
                               "-Wl,-rpath," + str(HERE), "-Wl,-rpath,$ORIGIN/../../../dynamicfusion_b200"]
+    jobs["mine_ceres_warp_test"] = [gxx, "-std=c++17", "-O1", "-w", "-I", str(REFCOMPAT), *MIRROR_INC, str(REF_TESTS_DIR / "ceres_warp_test.cpp"), main_cpp,
+                                    "-L", str(HERE), "-lkfusion", "-ldfusion", "-Wl,-rpath," + str(HERE), "-Wl,-rpath,$ORIGIN/../../../dynamicfusion_b200"]
     built = {}
     for name, cmd in jobs.items():
         exe = out_dir / name
