@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--pipeline", action="store_true")
     ap.add_argument("--frames", type=int, default=12)
     ap.add_argument("--trace", action="store_true")
+    ap.add_argument("--hd", action="store_true", help="config C4: 1280x720 depth, volume edge 1.5 m (use with --dim 768)")
     a = ap.parse_args()
     os.environ["DF_INTEGRATE_IMPL"] = str(a.integrate_impl)
     if a.zchunk:
@@ -66,11 +67,14 @@ def main():
         k.close()
         print(json.dumps(out, indent=1))
         return
-    vol = host.TsdfVolume((dim, dim, dim))
-    vol.setTruncDist(0.04); vol.setMaxWeight(64); vol.setSize((1.0, 1.0, 1.0)); vol.setPose(synth.volume_pose(1.0))
+    cols, rows, size = (1280, 720, 1.5) if a.hd else (640, 480, 1.0)
+    if a.hd:
+        K = (K[0] * 2, K[1] * 2, 640.0, 360.0)
+    vol = host.TsdfVolume((dim, dim, dim), track_activity=True)
+    vol.setTruncDist(0.04); vol.setMaxWeight(64); vol.setSize((size, size, size)); vol.setPose(synth.volume_pose(size))
     vol.setRaycastStepFactor(0.75); vol.setGradientDeltaFactor(0.5); vol.clear()
     flush = torch.zeros(256 * 1024 * 1024 // 4, dtype=torch.int32, device="cuda")      # 256 MiB > 126 MB L2
-    d = host.u16_to_device(synth.umbrella_depth(0))
+    d = host.u16_to_device(synth.umbrella_depth(0, cols=cols, rows=rows, K=K))
     dists = host.computeDists(d, K)
     n_upd = torch.zeros(1, dtype=torch.int64, device="cuda")
     pose = host.identity_pose()
@@ -79,9 +83,9 @@ def main():
     nupd = int(n_upd.item())
     out["n_upd"] = nupd
     med, best = timeit(lambda: vol.integrate(dists, pose, K), flush=flush)
-    bytes_int = 8 * nupd + 2 * 640 * 480
+    bytes_int = 8 * nupd + 2 * cols * rows
     out["integrate_ms"] = med; out["integrate_best_ms"] = best; out["integrate_GBs"] = bytes_int / med / 1e6
-    med, best = timeit(lambda: vol.raycast(pose, K, 640, 480), flush=flush)
+    med, best = timeit(lambda: vol.raycast(pose, K, cols, rows), flush=flush)
     out["raycast_ms"] = med; out["raycast_best_ms"] = best
     cap = 4_000_000
     med, best = timeit(lambda: vol.fetchCloud(cap), flush=flush, iters=5)
@@ -90,6 +94,17 @@ def main():
     n = int(cnt.item()); out["cloud_points"] = n
     med, best = timeit(lambda: vol.fetchNormals(pts, n), flush=flush, iters=5)
     out["extract_normals_ms"] = med
+    # occupancy at 8^3-brick granularity (dense-equivalent vs occupied-brick bytes)
+    v = vol.data_.view(dim // 8, 8, dim // 8, 8, dim // 8, 8)
+    observed = ((v >> 16) & 0xffff) != 0
+    bricks_obs = int(observed.any(dim=5).any(dim=3).any(dim=1).sum().item())
+    surf = observed & ((v & 0xffff) != 0x3c00)
+    bricks_surf = int(surf.any(dim=5).any(dim=3).any(dim=1).sum().item())
+    out["dense_bytes"] = 4 * dim ** 3
+    out["bricks_total"] = (dim // 8) ** 3
+    out["bricks_observed"] = bricks_obs; out["observed_brick_bytes"] = bricks_obs * 2048
+    out["bricks_with_surface"] = bricks_surf; out["surface_brick_bytes"] = bricks_surf * 2048
+    out["activity_fraction"] = float((vol.activity_ != 0).float().mean().item())
     med, best = timeit(lambda: vol.clear(), flush=flush)
     out["clear_ms"] = med; out["clear_GBs"] = 4 * dim ** 3 / med / 1e6
     print(json.dumps(out, indent=1))
