@@ -22,6 +22,9 @@ struct IcpParams {
     const float4 *ncurr; size_t ncpitch;
     const float4 *vprev; size_t vppitch;
     const float4 *nprev; size_t nppitch;
+    const unsigned short *dcurr; size_t dcpitch;     // depth variant (USE_DEPTH, proj_icp.cu:47-78): u16 millimetres
+    const unsigned short *dprev; size_t dppitch;
+    float finvx, finvy;                              // 1/f of the level (setLevelIntr, projective_icp.cpp:22)
     int cols, rows;
     float fcols, frows;
     float fx, fy, cx, cy;
@@ -33,20 +36,37 @@ struct IcpParams {
     int tiles_x, tiles;
 };
 
-// find_coresp (points variant) proj_icp.cu:80-108 + row build :359-368
+// find_coresp proj_icp.cu:47-78 (DEPTH: the reference's compile-time USE_DEPTH alternative) / :80-108 (points) + row build :359-368
+template <bool DEPTH>
 __device__ __forceinline__ bool icp_row(const IcpParams &p, const Aff &T, int x, int y, float row[7])
 {
-    const float4 vc = __ldg(row_ptr(p.vcurr, p.vcpitch, y) + x);
-    float3 s = make_float3(vc.x, vc.y, vc.z);
-    if (isnan(s.x)) return false;
+    float3 s;
+    if (DEPTH) {
+        const int src_z = __ldg(row_ptr(p.dcurr, p.dcpitch, y) + x);
+        if (src_z == 0) return false;
+        const float z = src_z * 0.001f;
+        s = make_float3(z * ((float)x - p.cx) * p.finvx, z * ((float)y - p.cy) * p.finvy, z);    // reproj, proj_icp.cu:39-45
+    } else {
+        const float4 vc = __ldg(row_ptr(p.vcurr, p.vcpitch, y) + x);
+        s = make_float3(vc.x, vc.y, vc.z);
+        if (isnan(s.x)) return false;
+    }
     s = aff_mul(T, s);
     const float u = __fmaf_rn(p.fx, s.x / s.z, p.cx);
     const float v = __fmaf_rn(p.fy, s.y / s.z, p.cy);
     if (s.z <= 0 || u < 0 || v < 0 || u >= p.fcols || v >= p.frows) return false;
     if (!(u == u) || !(v == v)) return false;
-    const float4 dp = __ldg(row_ptr(p.vprev, p.vppitch, (int)v) + (int)u);     // point sampling of the previous maps
-    const float3 d = make_float3(dp.x, dp.y, dp.z);
-    if (isnan(d.x)) return false;
+    float3 d;
+    if (DEPTH) {
+        const int dst_z = __ldg(row_ptr(p.dprev, p.dppitch, (int)v) + (int)u);  // point sampling of the previous depth
+        if (dst_z == 0) return false;
+        const float z = dst_z * 0.001f;
+        d = make_float3(z * (u - p.cx) * p.finvx, z * (v - p.cy) * p.finvy, z);  // re-projected at the fractional coordinates
+    } else {
+        const float4 dp = __ldg(row_ptr(p.vprev, p.vppitch, (int)v) + (int)u);  // point sampling of the previous maps
+        d = make_float3(dp.x, dp.y, dp.z);
+        if (isnan(d.x)) return false;
+    }
     const float3 df = sub3(s, d);
     if (dot3(df, df) > p.dist2_thres) return false;
     const float4 nc = __ldg(row_ptr(p.ncurr, p.ncpitch, y) + x);
@@ -60,6 +80,7 @@ __device__ __forceinline__ bool icp_row(const IcpParams &p, const Aff &T, int x,
     return true;
 }
 
+template <bool DEPTH>
 __global__ void __launch_bounds__(256) icp_accumulate_kernel(const IcpParams p)
 {
     __shared__ double smem[8][27];
@@ -82,7 +103,7 @@ __global__ void __launch_bounds__(256) icp_accumulate_kernel(const IcpParams p)
             const int x = (tile % p.tiles_x) * 32 + threadIdx.x;
             const int y = (tile / p.tiles_x) * 8 + threadIdx.y;
             float row[7];
-            if (x < p.cols && y < p.rows && icp_row(p, T, x, y, row)) {
+            if (x < p.cols && y < p.rows && icp_row<DEPTH>(p, T, x, y, row)) {
                 int k = 0;
 #pragma unroll
                 for (int i = 0; i < 6; ++i)
@@ -292,7 +313,8 @@ int launch_accumulate(IcpParams &p, cudaStream_t s)
     p.tiles_x = div_up(p.cols, 32);
     p.tiles = p.tiles_x * div_up(p.rows, 8);
     const int blocks = p.tiles < 148 * 4 ? p.tiles : 148 * 4;
-    icp_accumulate_kernel<<<blocks, dim3(32, 8), 0, s>>>(p);
+    if (p.dcurr) icp_accumulate_kernel<true><<<blocks, dim3(32, 8), 0, s>>>(p);
+    else icp_accumulate_kernel<false><<<blocks, dim3(32, 8), 0, s>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return -(int)e;
     return blocks;
@@ -308,6 +330,7 @@ extern "C" int df_icp_accumulate(const float *vcurr, size_t vcurr_pitch, const f
     IcpParams p;
     p.vcurr = (const float4 *)vcurr; p.vcpitch = vcurr_pitch; p.ncurr = (const float4 *)ncurr; p.ncpitch = ncurr_pitch;
     p.vprev = (const float4 *)vprev; p.vppitch = vprev_pitch; p.nprev = (const float4 *)nprev; p.nppitch = nprev_pitch;
+    p.dcurr = p.dprev = nullptr; p.dcpitch = p.dppitch = 0; p.finvx = p.finvy = 0.f;
     p.cols = cols; p.rows = rows; p.fcols = (float)cols; p.frows = (float)rows;
     p.fx = intr_level.fx; p.fy = intr_level.fy; p.cx = intr_level.cx; p.cy = intr_level.cy;
     p.dist2_thres = dist2_thres; p.min_cosine = min_cosine;
@@ -320,22 +343,49 @@ extern "C" int df_icp_accumulate(const float *vcurr, size_t vcurr_pitch, const f
     return 0;
 }
 
-extern "C" int df_icp_estimate(const float *const *vcurr, const float *const *ncurr, const float *const *vprev, const float *const *nprev,
-                               const int *cols, const int *rows, const size_t *pitch, int levels, const int *iters,
-                               df_intr intr, float dist_thres, float angle_thres, float *T_dev, int *ok_dev, double *scratch,
-                               void *stream)
+extern "C" int df_icp_accumulate_depth(const unsigned short *dcurr, size_t dcurr_pitch, const float *ncurr, size_t ncurr_pitch,
+                                       const unsigned short *dprev, size_t dprev_pitch, const float *nprev, size_t nprev_pitch,
+                                       int cols, int rows, df_intr intr_level, df_aff3f T, float dist2_thres, float min_cosine,
+                                       double *scratch, void *stream)
 {
-    cudaStream_t s = (cudaStream_t)stream;
+    if (!dcurr || !dprev) return (int)cudaErrorInvalidValue;
+    IcpParams p;
+    p.vcurr = p.vprev = nullptr; p.vcpitch = p.vppitch = 0;
+    p.ncurr = (const float4 *)ncurr; p.ncpitch = ncurr_pitch; p.nprev = (const float4 *)nprev; p.nppitch = nprev_pitch;
+    p.dcurr = dcurr; p.dcpitch = dcurr_pitch; p.dprev = dprev; p.dppitch = dprev_pitch;
+    p.cols = cols; p.rows = rows; p.fcols = (float)cols; p.frows = (float)rows;
+    p.fx = intr_level.fx; p.fy = intr_level.fy; p.cx = intr_level.cx; p.cy = intr_level.cy;
+    p.finvx = 1.f / p.fx; p.finvy = 1.f / p.fy;
+    p.dist2_thres = dist2_thres; p.min_cosine = min_cosine;
+    p.T_val = make_aff(T); p.T_ptr = nullptr; p.ok_ptr = nullptr;
+    p.partials = scratch + 32;
+    const int blocks = launch_accumulate(p, (cudaStream_t)stream);
+    if (blocks < 0) return -blocks;
+    icp_reduce_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(p.partials, blocks, scratch);
+    DF_LAUNCH_CHECK();
+    return 0;
+}
+
+namespace {
+// the coarse-to-fine loop of both estimateTransform overloads (projective_icp.cpp:126-167 depth, :169-213 points)
+int icp_estimate_impl(const float *const *vcurr, const unsigned short *const *dcurr, const float *const *ncurr, const float *const *vprev,
+                      const unsigned short *const *dprev, const float *const *nprev, const int *cols, const int *rows, const size_t *pitch,
+                      const size_t *dpitch, int levels, const int *iters, df_intr intr, float dist_thres, float angle_thres, float *T_dev,
+                      int *ok_dev, double *scratch, cudaStream_t s)
+{
     icp_init_kernel<<<1, 32, 0, s>>>(T_dev, ok_dev);        // affine = Identity, projective_icp.cpp:175
     DF_LAUNCH_CHECK();
     for (int level = levels - 1; level >= 0; --level) {
         const int div = 1 << level;                          // setLevelIntr, projective_icp.cpp:17-23
         IcpParams p;
-        p.vcurr = (const float4 *)vcurr[level]; p.ncurr = (const float4 *)ncurr[level];
-        p.vprev = (const float4 *)vprev[level]; p.nprev = (const float4 *)nprev[level];
+        p.vcurr = p.vprev = nullptr; p.dcurr = p.dprev = nullptr; p.dcpitch = p.dppitch = 0;
+        if (dcurr) { p.dcurr = dcurr[level]; p.dprev = dprev[level]; p.dcpitch = p.dppitch = dpitch[level]; }
+        else { p.vcurr = (const float4 *)vcurr[level]; p.vprev = (const float4 *)vprev[level]; }
+        p.ncurr = (const float4 *)ncurr[level]; p.nprev = (const float4 *)nprev[level];
         p.vcpitch = p.ncpitch = p.vppitch = p.nppitch = pitch[level];
         p.cols = cols[level]; p.rows = rows[level]; p.fcols = (float)cols[level]; p.frows = (float)rows[level];
         p.fx = intr.fx / div; p.fy = intr.fy / div; p.cx = intr.cx / div; p.cy = intr.cy / div;
+        p.finvx = 1.f / p.fx; p.finvy = 1.f / p.fy;
         p.dist2_thres = dist_thres * dist_thres;             // ComputeIcpHelper ctor, projective_icp.cpp:11-15
         p.min_cosine = cosf(angle_thres);
         p.T_val = Aff(); p.T_ptr = T_dev; p.ok_ptr = ok_dev;
@@ -351,4 +401,24 @@ extern "C" int df_icp_estimate(const float *const *vcurr, const float *const *nc
         }
     }
     return 0;
+}
+}  // namespace
+
+extern "C" int df_icp_estimate(const float *const *vcurr, const float *const *ncurr, const float *const *vprev, const float *const *nprev,
+                               const int *cols, const int *rows, const size_t *pitch, int levels, const int *iters,
+                               df_intr intr, float dist_thres, float angle_thres, float *T_dev, int *ok_dev, double *scratch,
+                               void *stream)
+{
+    return icp_estimate_impl(vcurr, nullptr, ncurr, vprev, nullptr, nprev, cols, rows, pitch, nullptr, levels, iters, intr, dist_thres,
+                             angle_thres, T_dev, ok_dev, scratch, (cudaStream_t)stream);
+}
+
+extern "C" int df_icp_estimate_depth(const unsigned short *const *dcurr, const float *const *ncurr, const unsigned short *const *dprev,
+                                     const float *const *nprev, const int *cols, const int *rows, const size_t *depth_pitch,
+                                     const size_t *normals_pitch, int levels, const int *iters, df_intr intr, float dist_thres,
+                                     float angle_thres, float *T_dev, int *ok_dev, double *scratch, void *stream)
+{
+    if (!dcurr || !dprev) return (int)cudaErrorInvalidValue;
+    return icp_estimate_impl(nullptr, dcurr, ncurr, nullptr, dprev, nprev, cols, rows, normals_pitch, depth_pitch, levels, iters, intr,
+                             dist_thres, angle_thres, T_dev, ok_dev, scratch, (cudaStream_t)stream);
 }

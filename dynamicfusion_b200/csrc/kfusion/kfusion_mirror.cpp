@@ -204,7 +204,6 @@ void kfusion::cuda::renderTangentColors(const Normals& normals, Image& image)
     dfSafeCall(df_render_tangent_colors((const float *)normals.ptr(), normals.step(), normals.cols(), normals.rows(), image.ptr(), image.step(), 0));
     waitAllDefaultStream();
 }
-static void not_built(const char *what) { kfusion::cuda::error(what, __FILE__, __LINE__); }
 // USE_DEPTH-path entry points of the reference (internal.hpp:6 leaves USE_DEPTH undefined, so its own frame loop never calls them);
 // host wrappers as imgproc.cpp:52-60,98-103,112-121,152-164
 void kfusion::cuda::computeNormalsAndMaskDepth(const Intr& intr, Depth& depth, Normals& normals)
@@ -267,8 +266,28 @@ int ProjectiveICP::getUsedLevelsNum() const
     return i + 1;
 }
 bool ProjectiveICP::estimateTransform(Affine3f&, const Intr&, const Frame&, const Frame&) { CV_Assert(!"Not implemented"); return false; }
-bool ProjectiveICP::estimateTransform(Affine3f&, const Intr&, const DepthPyr&, const NormalsPyr, const DepthPyr, const NormalsPyr)
-{ not_built("estimateTransform(depth pyramids): USE_DEPTH path is not part of the hot path"); return false; }
+bool ProjectiveICP::estimateTransform(Affine3f& affine, const Intr& intr, const DepthPyr& dcurr, const NormalsPyr ncurr, const DepthPyr dprev, const NormalsPyr nprev)
+{
+    // the reference's compile-time USE_DEPTH alternative (projective_icp.cpp:126-167); always available here
+    const int LEVELS = getUsedLevelsNum();
+    const unsigned short *dc[MAX_PYRAMID_LEVELS], *dp[MAX_PYRAMID_LEVELS];
+    const float *nc[MAX_PYRAMID_LEVELS], *np[MAX_PYRAMID_LEVELS];
+    int cols[MAX_PYRAMID_LEVELS], rows[MAX_PYRAMID_LEVELS]; size_t dpitch[MAX_PYRAMID_LEVELS], npitch[MAX_PYRAMID_LEVELS];
+    for (int i = 0; i < LEVELS; ++i) {
+        dc[i] = (const unsigned short *)dcurr[i].ptr(); dp[i] = (const unsigned short *)dprev[i].ptr();
+        nc[i] = (const float *)ncurr[i].ptr(); np[i] = (const float *)nprev[i].ptr();
+        cols[i] = dcurr[i].cols(); rows[i] = dcurr[i].rows(); dpitch[i] = dcurr[i].step(); npitch[i] = ncurr[i].step();
+        CV_Assert(dprev[i].step() == dpitch[i] && nprev[i].step() == npitch[i]);
+    }
+    StreamHelper& sh = *shelp_;
+    dfSafeCall(df_icp_estimate_depth(dc, nc, dp, np, cols, rows, dpitch, npitch, LEVELS, &iters_[0], to_df(intr), dist_thres_, angle_thres_, sh.T_dev, sh.ok_dev, sh.scratch, 0));
+    cudaSafeCall(cudaMemcpy(sh.pinned, sh.T_dev, 48, cudaMemcpyDeviceToHost));
+    cudaSafeCall(cudaMemcpy(sh.pinned + 12, sh.ok_dev, 4, cudaMemcpyDeviceToHost));
+    int ok; memcpy(&ok, sh.pinned + 12, 4);
+    if (!ok) return false;
+    affine = from12(sh.pinned);
+    return true;
+}
 bool ProjectiveICP::estimateTransform(Affine3f& affine, const Intr& intr, const PointsPyr& vcurr, const NormalsPyr ncurr, const PointsPyr vprev, const NormalsPyr nprev)
 {
     const int LEVELS = getUsedLevelsNum();

@@ -278,6 +278,32 @@ class ProjectiveICP:
         return bool(self._ok.item()), (T[:9].reshape(3, 3).copy(), T[9:].copy())
 
 
+    def accumulateDepth(self, dcurr, ncurr, dprev, nprev, intr_level, T):
+        """the reference's USE_DEPTH alternative of the association pass: u16 (rows, cols) depth maps in place of the vertex maps"""
+        rows, cols = dcurr.shape[:2]
+        out = self._scratch
+        capi.check(_lib().df_icp_accumulate_depth(dcurr.data_ptr(), cols * 2, ncurr.data_ptr(), cols * 16, dprev.data_ptr(), cols * 2,
+                                                  nprev.data_ptr(), cols * 16, cols, rows, capi.make_intr(*intr_level), capi.make_aff(*T),
+                                                  self.dist_thres_ * self.dist_thres_, math.cos(self.angle_thres_), out.data_ptr(),
+                                                  _stream()))
+        return out[:27].clone()
+
+    def estimateTransformDepth(self, intr, dcurr, ncurr, dprev, nprev):
+        """estimateTransform(affine, intr, DepthPyr, NormalsPyr, DepthPyr, NormalsPyr) (projective_icp.hpp:38)"""
+        L = self.getUsedLevelsNum()
+        vp = lambda xs: (C.c_void_p * L)(*[x.data_ptr() for x in xs[:L]])
+        cols = (C.c_int * L)(*[x.shape[1] for x in dcurr[:L]])
+        rows = (C.c_int * L)(*[x.shape[0] for x in dcurr[:L]])
+        dpitch = (C.c_size_t * L)(*[x.shape[1] * 2 for x in dcurr[:L]])
+        npitch = (C.c_size_t * L)(*[x.shape[1] * 16 for x in dcurr[:L]])
+        it = (C.c_int * L)(*self.iters_[:L])
+        capi.check(_lib().df_icp_estimate_depth(vp(dcurr), vp(ncurr), vp(dprev), vp(nprev), cols, rows, dpitch, npitch, L, it,
+                                                capi.make_intr(*intr), self.dist_thres_, self.angle_thres_, self._T.data_ptr(),
+                                                self._ok.data_ptr(), self._scratch.data_ptr(), _stream()))
+        T = self._T.cpu().numpy()
+        return bool(self._ok.item()), (T[:9].reshape(3, 3).copy(), T[9:].copy())
+
+
 # ------------------------------------------------------------------ WarpField ----------------------------------------------------------------
 NODE_STRIDE = 12
 KNN_NEIGHBOURS = 8

@@ -156,6 +156,22 @@ int df_icp_estimate(const float *const *vcurr, const float *const *ncurr, const 
                     df_intr intr, float dist_thres, float angle_thres, float *T_dev, int *ok_dev, double *scratch,
                     void *stream);
 
+/* The reference's compile-time USE_DEPTH alternative (internal.hpp:6; ComputeIcpHelper::find_coresp proj_icp.cu:47-78,
+ * ComputeIcpHelper::operator()(const Depth&, ...) proj_icp.cu:396-418): the current depth map (u16 millimetres) is
+ * re-projected per pixel, the previous depth map is point-sampled at the projection and re-projected at the fractional
+ * coordinates; normal maps as above.  Same scratch / sums layout as df_icp_accumulate. */
+int df_icp_accumulate_depth(const unsigned short *dcurr, size_t dcurr_pitch, const float *ncurr, size_t ncurr_pitch,
+                            const unsigned short *dprev, size_t dprev_pitch, const float *nprev, size_t nprev_pitch,
+                            int cols, int rows, df_intr intr_level, df_aff3f T, float dist2_thres, float min_cosine,
+                            double *scratch, void *stream);
+
+/* ProjectiveICP::estimateTransform, depth-pyramid overload (projective_icp.hpp:38, projective_icp.cpp:126-167), device
+ * resident like df_icp_estimate. */
+int df_icp_estimate_depth(const unsigned short *const *dcurr, const float *const *ncurr, const unsigned short *const *dprev,
+                          const float *const *nprev, const int *cols, const int *rows, const size_t *depth_pitch,
+                          const size_t *normals_pitch, int levels, const int *iters, df_intr intr, float dist_thres,
+                          float angle_thres, float *T_dev, int *ok_dev, double *scratch, void *stream);
+
 /* ------------------------------------------------------------------ warp field ------------------------------------------------------------ */
 /* deformation_node (warp_field.hpp:35-40) as 12 floats: vertex[3], rotation quat (w,x,y,z), dual/translation quat
  * (w,x,y,z) = 0.5*t*r (dual_quaternion.hpp:59-63), weight. */

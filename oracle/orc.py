@@ -43,6 +43,7 @@ def load() -> C.CDLL:
         _lib.orc_integrate.restype = C.c_longlong
         _lib.orc_extract_cloud.restype = C.c_longlong
         _lib.orc_icp_accumulate.restype = C.c_longlong
+        _lib.orc_icp_accumulate_depth.restype = C.c_longlong
         _lib.orc_float2half_rn.restype = C.c_uint16
         _lib.orc_float2half_rn.argtypes = [C.c_float]
         _lib.orc_half2float.restype = C.c_float
@@ -73,6 +74,20 @@ def load_ref() -> C.CDLL:
     return _ref_lib
 
 
+# libkfref_usedepth.so = proj_icp.cu compiled with the reference's compile-time USE_DEPTH alternative (internal.hpp:6); it defines the
+# same C++ symbols as libkfref.so, hence a library of its own (both are loaded RTLD_LOCAL)
+REF_DEPTH_LIB = HERE / "_ref" / "libkfref_usedepth.so"
+_ref_depth_lib = None
+
+
+def load_ref_usedepth() -> C.CDLL:
+    global _ref_depth_lib
+    if _ref_depth_lib is None:
+        _ref_depth_lib = C.CDLL(str(REF_DEPTH_LIB))
+        _ref_depth_lib.kfref_icp_accumulate_depth.restype = C.c_longlong
+    return _ref_depth_lib
+
+
 class reference:
     """context manager: route the wrappers below to the reference's own kernels (libkfref.so)"""
 
@@ -89,6 +104,8 @@ class reference:
 
 
 def _fn(name: str):
+    if _use_ref and name == "icp_accumulate_depth":
+        return load_ref_usedepth().kfref_icp_accumulate_depth
     if _use_ref:
         return getattr(load_ref(), "kfref_" + name)
     return getattr(load(), "orc_" + name)
@@ -222,6 +239,33 @@ def icp_accumulate(vcurr, ncurr, vprev, nprev, K_level, T, dist2, min_cos):
                                   _p(nprev), C.c_size_t(cols * 16), cols, rows, intr(*K_level), aff(*T), C.c_float(dist2),
                                   C.c_float(min_cos), _p(out))
     return out, int(n)
+
+
+def icp_accumulate_depth(dcurr, ncurr, dprev, nprev, K_level, T, dist2, min_cos):
+    """USE_DEPTH variant: u16 millimetre depth maps in place of the vertex maps"""
+    rows, cols = dcurr.shape[:2]
+    dcurr, dprev = np.ascontiguousarray(dcurr, np.uint16), np.ascontiguousarray(dprev, np.uint16)
+    out = np.zeros(27, np.float64)
+    n = _fn("icp_accumulate_depth")(_p(dcurr), C.c_size_t(cols * 2), _p(ncurr), C.c_size_t(cols * 16), _p(dprev), C.c_size_t(cols * 2),
+                                        _p(nprev), C.c_size_t(cols * 16), cols, rows, intr(*K_level), aff(*T), C.c_float(dist2),
+                                        C.c_float(min_cos), _p(out))
+    return out, int(n)
+
+
+def icp_estimate_depth(dcurr, ncurr, dprev, nprev, iters, K, dist_thres, angle_thres):
+    L = len(dcurr)
+    dcurr = [np.ascontiguousarray(x, np.uint16) for x in dcurr]
+    dprev = [np.ascontiguousarray(x, np.uint16) for x in dprev]
+    arr = lambda xs: (C.c_void_p * L)(*[x.ctypes.data for x in xs])
+    cols = (C.c_int * L)(*[x.shape[1] for x in dcurr])
+    rows = (C.c_int * L)(*[x.shape[0] for x in dcurr])
+    dpitch = (C.c_size_t * L)(*[x.shape[1] * 2 for x in dcurr])
+    npitch = (C.c_size_t * L)(*[x.shape[1] * 16 for x in dcurr])
+    it = (C.c_int * L)(*iters[:L])
+    a = Aff3f()
+    ok = load().orc_icp_estimate_depth(arr(dcurr), arr(ncurr), arr(dprev), arr(nprev), cols, rows, dpitch, npitch, L, it, intr(*K),
+                                       C.c_float(dist_thres), C.c_float(angle_thres), C.byref(a))
+    return bool(ok), (np.array(list(a.R), np.float32).reshape(3, 3), np.array(list(a.t), np.float32))
 
 
 def icp_solve_update(sums27, T):

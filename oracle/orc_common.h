@@ -118,6 +118,12 @@ void orc_resize_points_normals(const float *vsrc, size_t vspitch, const float *n
 long long orc_icp_accumulate(const float *vcurr, size_t vcpitch, const float *ncurr, size_t ncpitch, const float *vprev, size_t vppitch,
                              const float *nprev, size_t nppitch, int cols, int rows, orc_intr intr_level, orc_aff3f T,
                              float dist2_thres, float min_cosine, double *out27);
+long long orc_icp_accumulate_depth(const unsigned short *dcurr, size_t dcpitch, const float *ncurr, size_t ncpitch, const unsigned short *dprev,
+                                   size_t dppitch, const float *nprev, size_t nppitch, int cols, int rows, orc_intr k, orc_aff3f T,
+                                   float dist2_thres, float min_cosine, double *out27);
+int orc_icp_estimate_depth(const unsigned short *const *dcurr, const float *const *ncurr, const unsigned short *const *dprev,
+                           const float *const *nprev, const int *cols, const int *rows, const size_t *dpitch, const size_t *npitch,
+                           int levels, const int *iters, orc_intr intr, float dist_thres, float angle_thres, orc_aff3f *T_out);
 int orc_icp_solve_update(const double *sums27, orc_aff3f *T);
 int orc_icp_estimate(const float *const *vcurr, const float *const *ncurr, const float *const *vprev, const float *const *nprev,
                      const int *cols, const int *rows, const size_t *pitch, int levels, const int *iters, orc_intr intr,

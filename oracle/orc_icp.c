@@ -52,6 +52,55 @@ long long orc_icp_accumulate(const float *vcurr, size_t vcpitch, const float *nc
     return inliers;
 }
 
+/* ComputeIcpHelper::find_coresp, USE_DEPTH variant (proj_icp.cu:47-78; compiled in when internal.hpp:6 defines USE_DEPTH):
+ * the source point is the current depth pixel (u16 millimetres) re-projected with finv = 1/f (reproj, proj_icp.cu:39-45), the
+ * destination is the previous depth map point-sampled at the projection (texture<ushort> dprev_tex, cudaFilterModePoint) and
+ * re-projected at the fractional coordinates; normals as in the points variant.  Row build and sums as above. */
+long long orc_icp_accumulate_depth(const unsigned short *dcurr, size_t dcpitch, const float *ncurr, size_t ncpitch, const unsigned short *dprev,
+                                   size_t dppitch, const float *nprev, size_t nppitch, int cols, int rows, orc_intr k, orc_aff3f T,
+                                   float dist2_thres, float min_cosine, double *out27)
+{
+    double acc[27];
+    for (int i = 0; i < 27; ++i) acc[i] = 0.0;
+    long long inliers = 0;
+    const float finvx = 1.f / k.fx, finvy = 1.f / k.fy;              /* setLevelIntr, projective_icp.cpp:22 */
+    for (int y = 0; y < rows; ++y)
+        for (int x = 0; x < cols; ++x) {
+            const int src_z = ((const unsigned short *)((const char *)dcurr + (size_t)y * dcpitch))[x];
+            if (src_z == 0) continue;
+            const float zs = src_z * 0.001f;
+            orc_f3 s = f3(zs * ((float)x - k.cx) * finvx, zs * ((float)y - k.cy) * finvy, zs);
+            s = orc_aff_mul(&T, s);
+            float u = fmaf(k.fx, s.x / s.z, k.cx);
+            float v = fmaf(k.fy, s.y / s.z, k.cy);
+            if (s.z <= 0 || u < 0 || v < 0 || u >= (float)cols || v >= (float)rows) continue;
+            if (!(u == u) || !(v == v)) continue;
+            const int dst_z = ((const unsigned short *)((const char *)dprev + (size_t)(int)v * dppitch))[(int)u];
+            if (dst_z == 0) continue;
+            const float zd = dst_z * 0.001f;
+            orc_f3 d = f3(zd * (u - k.cx) * finvx, zd * (v - k.cy) * finvy, zd);
+            orc_f3 df = orc_sub(s, d);
+            float dist2 = orc_dot(df, df);
+            if (dist2 > dist2_thres) continue;
+            const float *nc = orc_row_f4(ncurr, ncpitch, y) + 4 * x;
+            orc_f3 ns = orc_mat_mul(T.R, f3(nc[0], nc[1], nc[2]));
+            const float *np = orc_row_f4(nprev, nppitch, (int)v) + 4 * (int)u;
+            orc_f3 nd = f3(np[0], np[1], np[2]);
+            float cosine = fabsf(orc_dot(ns, nd));
+            if (!(cosine >= min_cosine)) { if (cosine < min_cosine) continue; }   /* NaN cosine passes, as in the reference */
+            float row[7];
+            orc_f3 c = orc_cross(s, nd);
+            row[0] = c.x; row[1] = c.y; row[2] = c.z; row[3] = nd.x; row[4] = nd.y; row[5] = nd.z;
+            row[6] = orc_dot(nd, orc_sub(d, s));
+            int shift = 0;
+            for (int i = 0; i < 6; ++i)
+                for (int j = i; j < 7; ++j) acc[shift++] += (double)(row[i] * row[j]);
+            ++inliers;
+        }
+    for (int i = 0; i < 27; ++i) out27[i] = acc[i];
+    return inliers;
+}
+
 static double det6(const double *Ain)
 {
     double A[36];
@@ -180,6 +229,30 @@ int orc_icp_estimate(const float *const *vcurr, const float *const *ncurr, const
             double sums[27];
             orc_icp_accumulate(vcurr[level], pitch[level], ncurr[level], pitch[level], vprev[level], pitch[level],
                                nprev[level], pitch[level], cols[level], rows[level], k, T, dist2, min_cosine, sums);
+            if (!orc_icp_solve_update(sums, &T)) return 0;
+        }
+    }
+    *T_out = T;
+    return 1;
+}
+
+/* ProjectiveICP::estimateTransform, depth variant (projective_icp.cpp:126-167): same loop over depth pyramids */
+int orc_icp_estimate_depth(const unsigned short *const *dcurr, const float *const *ncurr, const unsigned short *const *dprev,
+                           const float *const *nprev, const int *cols, const int *rows, const size_t *dpitch, const size_t *npitch,
+                           int levels, const int *iters, orc_intr intr, float dist_thres, float angle_thres, orc_aff3f *T_out)
+{
+    orc_aff3f T;
+    for (int i = 0; i < 9; ++i) T.R[i] = (i % 4 == 0) ? 1.f : 0.f;
+    T.t[0] = T.t[1] = T.t[2] = 0.f;
+    const float min_cosine = cosf(angle_thres);
+    const float dist2 = dist_thres * dist_thres;
+    for (int level = levels - 1; level >= 0; --level) {
+        int div = 1 << level;
+        orc_intr k = {intr.fx / div, intr.fy / div, intr.cx / div, intr.cy / div};
+        for (int it = 0; it < iters[level]; ++it) {
+            double sums[27];
+            orc_icp_accumulate_depth(dcurr[level], dpitch[level], ncurr[level], npitch[level], dprev[level], dpitch[level],
+                                     nprev[level], npitch[level], cols[level], rows[level], k, T, dist2, min_cosine, sums);
             if (!orc_icp_solve_update(sums, &T)) return 0;
         }
     }

@@ -4,6 +4,7 @@
 // reference's tests use (WarpField::init / warp, WarpFieldOptimiser, Quaternion, DualQuaternion).
 // Build: see tests/test_cpp_mirror.py.  Needs a GPU to RUN (exit code 0 = all checks passed).
 #include <kfusion/kinfu.hpp>
+#include <kfusion/cuda/imgproc.hpp>
 #include <cmath>
 #include <cstdio>
 #include <vector>
@@ -96,6 +97,36 @@ int main()
     CHECK(dynamic_fusion.tsdf().getDims()[0] == 128 && dynamic_fusion.icp().getUsedLevelsNum() == 3);
     dynamic_fusion.tsdf().compute_points();
     CHECK(dynamic_fusion.tsdf().get_cloud_host().cols > 1000);
+    // --- the USE_DEPTH branch of the frame loop (kinfu.cpp:226-243,271-272), driven through the public component API --------------
+    {
+        const int LEVELS = 3;
+        cuda::Frame curr, prev;
+        for (int f = 0; f < 2; ++f) {
+            cuda::Frame& fr = f ? curr : prev;
+            fr.depth_pyr.resize(LEVELS); fr.normals_pyr.resize(LEVELS);
+            std::vector<unsigned short> depth = make_depth(params.cols, params.rows, params.intr, 0.004f * f);
+            cuda::Depth raw;
+            raw.upload(&depth[0], params.cols * sizeof(unsigned short), params.rows, params.cols);
+            cuda::depthBilateralFilter(raw, fr.depth_pyr[0], params.bilateral_kernel_size, params.bilateral_sigma_spatial, params.bilateral_sigma_depth);
+            cuda::depthTruncation(fr.depth_pyr[0], params.icp_truncate_depth_dist);
+            for (int i = 1; i < LEVELS; ++i) cuda::depthBuildPyramid(fr.depth_pyr[i - 1], fr.depth_pyr[i], params.bilateral_sigma_depth);
+            for (int i = 0; i < LEVELS; ++i) cuda::computeNormalsAndMaskDepth(params.intr(i), fr.depth_pyr[i], fr.normals_pyr[i]);
+        }
+        cuda::waitAllDefaultStream();
+        cuda::ProjectiveICP icp;
+        icp.setDistThreshold(params.icp_dist_thres);
+        icp.setAngleThreshold(params.icp_angle_thres);
+        icp.setIterationsNum(params.icp_iter_num);
+        Affine3f affine;
+        bool ok = icp.estimateTransform(affine, params.intr, prev.depth_pyr, prev.normals_pyr, prev.depth_pyr, prev.normals_pyr);
+        CHECK(ok);
+        for (int i = 0; i < 3; ++i) CHECK(std::fabs(affine.matrix(i, i) - 1.f) < 1e-4f && std::fabs(affine.matrix(i, 3)) < 1e-4f);   // a frame against itself
+        ok = icp.estimateTransform(affine, params.intr, curr.depth_pyr, curr.normals_pyr, prev.depth_pyr, prev.normals_pyr);
+        CHECK(ok);
+        // the sphere moved +4 mm in x in front of a fixed wall: a small, finite curr -> prev motion
+        CHECK(std::fabs(affine.matrix(0, 0) - 1.f) < 0.01f && std::fabs(affine.matrix(0, 3)) < 0.01f && std::fabs(affine.matrix(2, 3)) < 0.01f);
+        CHECK(affine.matrix(0, 3) != 0.f);
+    }
     std::printf(fails ? "demo_like: %d check(s) FAILED\n" : "demo_like: all checks passed\n", fails);
     return fails ? 1 : 0;
 }

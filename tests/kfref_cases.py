@@ -93,6 +93,13 @@ def imgproc_icp_case(orc, ref):
             Kl = tuple(k / (1 << lvl) for k in K)
             sums, inl = orc.icp_accumulate(b[lvl][0], b[lvl][1], a[lvl][0], a[lvl][1], Kl, T, 0.1 * 0.1, math.cos(30 * 0.017453293))
             out[f"icp_sums_l{lvl}"], out[f"icp_inliers_l{lvl}"] = sums, np.array([inl], np.int64)
+            # the reference's compile-time USE_DEPTH alternative: depth pyramids masked where the normal is invalid (what
+            # computeNormalsAndMaskDepth leaves, kinfu.cpp:241-243) in place of the vertex maps
+            dc, dp = db[lvl].copy(), da[lvl].copy()
+            dc[np.isnan(b[lvl][1][..., 0])] = 0
+            dp[np.isnan(a[lvl][1][..., 0])] = 0
+            sums, inl = orc.icp_accumulate_depth(dc, b[lvl][1], dp, a[lvl][1], Kl, T, 0.1 * 0.1, math.cos(30 * 0.017453293))
+            out[f"icp_depth_sums_l{lvl}"], out[f"icp_depth_inliers_l{lvl}"] = sums, np.array([inl], np.int64)
     return out
 
 

@@ -2,7 +2,7 @@
 
 oracle/ref_shim compiles the reference's kfusion/src/cuda/{tsdf_volume,imgproc,proj_icp}.cu for the host (a CUDA-on-CPU
 emulation of the handful of runtime/texture/intrinsic calls they make, oracle/ref_shim/cudahost/cuda_runtime.h) into
-oracle/_ref/libkfref.so.  Bar: BIT-EXACT on every output (u32 voxels, u16 images, f32 vertex/normal maps, f64 ICP sums).
+oracle/_ref/libkfref.so (and proj_icp.cu once more with the reference's compile-time USE_DEPTH switch into libkfref_usedepth.so).  Bar: BIT-EXACT on every output (u32 voxels, u16 images, f32 vertex/normal maps, f64 ICP sums).
 
   * test_oracle_matches_reference_digests runs everywhere: oracle outputs vs the committed SHA-256 digests of the
     reference's outputs (tests/golden/kfref_golden.json, written by tests/golden/make_kfref_golden.py);
@@ -38,7 +38,7 @@ def test_oracle_matches_reference_digests(oracle_outputs):
             continue                                             # see kfref_cases.RACY; compared element-wise below
         assert kfref_cases.digest(arr) == g["sha256"], f"{name}: oracle output differs from the reference's"
         checked += 1
-    assert checked >= 29
+    assert checked >= 35
 
 
 def test_scenes_are_meaningful(oracle_outputs):

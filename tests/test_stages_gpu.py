@@ -86,6 +86,53 @@ def test_icp_accumulate_and_estimate(orc):
     assert np.array_equal(R, R2) and np.array_equal(t, t2)
 
 
+def _depth_pyramids(orc, depth):
+    """depth pyramid + normals, depth masked where the normal is invalid (computeNormalsAndMaskDepth, kinfu.cpp:241-243)"""
+    d0 = orc.bilateral(depth, 7, 4.5, 0.04)
+    ds = [d0]
+    for _ in range(2):
+        ds.append(orc.pyr_down(ds[-1], 0.04))
+    out = []
+    for i, d in enumerate(ds):
+        n = orc.points_normals(tuple(k / (1 << i) for k in K), d)[1]
+        d = d.copy()
+        d[np.isnan(n[..., 0])] = 0
+        out.append((d, n))
+    return out
+
+
+def test_icp_depth_variant_accumulate_and_estimate(orc):
+    """the reference's compile-time USE_DEPTH alternative (proj_icp.cu:47-78, projective_icp.cpp:126-167) vs the oracle, whose
+    restatement is pinned bit-exactly to the reference's own USE_DEPTH build (tests/test_oracle_vs_reference_kernels.py)"""
+    a = _depth_pyramids(orc, synth.umbrella_depth(0))
+    b = _depth_pyramids(orc, synth.umbrella_depth(3, shape_t=0))
+    icp = host.ProjectiveICP()
+    icp.setDistThreshold(0.1); icp.setAngleThreshold(30 * 0.017453293); icp.setIterationsNum([10, 5, 4, 0])
+    dev = lambda x: host.u16_to_device(x) if x.dtype == np.uint16 else torch.from_numpy(x).cuda()
+    T = (np.eye(3, dtype=np.float32), np.array([0.002, -0.001, 0.0], np.float32))
+    for lvl in range(3):
+        Kl = tuple(k / (1 << lvl) for k in K)
+        got = icp.accumulateDepth(dev(b[lvl][0]), dev(b[lvl][1]), dev(a[lvl][0]), dev(a[lvl][1]), Kl, T).cpu().numpy()
+        ref, inl = orc.icp_accumulate_depth(b[lvl][0], b[lvl][1], a[lvl][0], a[lvl][1], Kl, T, 0.1 * 0.1, math.cos(30 * 0.017453293))
+        assert inl > 1000
+        scale = np.abs(ref).max()
+        assert np.abs(got - ref).max() <= 1e-5 * scale, (lvl, got - ref)
+        pts, _ = orc.icp_accumulate(*[orc.points_normals(Kl, x[0])[i] for x, i in ((b[lvl], 0), (b[lvl], 1), (a[lvl], 0), (a[lvl], 1))],
+                                    Kl, T, 0.1 * 0.1, math.cos(30 * 0.017453293))
+        assert np.abs(pts[26] - ref[26]) > 1e-3 * abs(ref[26])       # not the points variant: the b column differs
+    args = ([dev(x[0]) for x in b], [dev(x[1]) for x in b], [dev(x[0]) for x in a], [dev(x[1]) for x in a])
+    ok, (R, t) = icp.estimateTransformDepth(K, *args)
+    ok_r, (Rr, tr) = orc.icp_estimate_depth([x[0] for x in b], [x[1] for x in b], [x[0] for x in a], [x[1] for x in a], [10, 5, 4], K, 0.1,
+                                            np.float32(30 * 0.017453293))
+    assert ok and ok_r
+    assert np.abs(R - Rr).max() < 1e-5 and np.abs(t - tr).max() < 1e-5
+    ok2, (R2, t2) = icp.estimateTransformDepth(K, *args)
+    assert np.array_equal(R, R2) and np.array_equal(t, t2)
+    blank = [(np.zeros_like(x[0]), x[1]) for x in b]
+    ok3, _ = icp.estimateTransformDepth(K, [dev(x[0]) for x in blank], [dev(x[1]) for x in blank], args[2], args[3])
+    assert ok3 is False
+
+
 def test_icp_degenerate_returns_false(orc):
     a = _pyramids(orc, synth.umbrella_depth(0))
     blank = _pyramids(orc, np.zeros((480, 640), np.uint16))
