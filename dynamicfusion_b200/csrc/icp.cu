@@ -4,8 +4,8 @@
 // floats, stream sync, cv::determinant, cv::solve(DECOMP_SVD), Rodrigues, H2D of the pose = 19 round trips a frame).
 //
 // Per iteration two launches, no host involvement:
-//   icp_accumulate_kernel  persistent tiles; each thread forms its 7-vector row and keeps the 27 products in registers
-//                          across its tiles (float products as the reference, proj_icp.cu:137-345), then one
+//   icp_accumulate_kernel  at most one block per SM; each thread forms its 7-vector rows and keeps the 27 products in registers
+//                          across its pixels (float products as the reference, proj_icp.cu:137-345), then one
 //                          double-precision warp-shuffle reduction and one partial row per block (deterministic order);
 //   icp_solve_kernel       one block: fixed-order sum of the partials, 6x6 solve, Rodrigues, T <- Tinc * T in place.
 #include "df_common.cuh"
@@ -15,7 +15,6 @@ using namespace dfb;
 
 namespace {
 
-constexpr int ICP_MAX_BLOCKS = 1024;
 
 struct IcpParams {
     const float4 *vcurr; size_t vcpitch;
@@ -33,7 +32,6 @@ struct IcpParams {
     const float *T_ptr;       // when non-null: 12 floats (R row-major, t) in device memory
     const int *ok_ptr;        // when non-null and *ok_ptr == 0 the iteration is skipped
     double *partials;         // [gridDim.x][27]
-    int tiles_x, tiles;
 };
 
 // find_coresp proj_icp.cu:47-78 (DEPTH: the reference's compile-time USE_DEPTH alternative) / :80-108 (points) + row build :359-368
@@ -80,35 +78,45 @@ __device__ __forceinline__ bool icp_row(const IcpParams &p, const Aff &T, int x,
     return true;
 }
 
-template <bool DEPTH>
-__global__ void __launch_bounds__(256) icp_accumulate_kernel(const IcpParams p)
+// One row of partials per block and at most ICP_MAX_PARTIAL_BLOCKS (= one per SM) blocks: the solve tail's fixed-order sum over the
+// rows is a chain of L2 round trips, so the row count is what its latency scales with (592 rows of 256-thread blocks cost the
+// 19 solves of a frame ~0.13 ms more than 148 rows of 768-thread blocks).  Pixels are dealt to threads linearly (coalesced
+// along x, balanced to one pixel per warp whatever the image size).
+template <bool DEPTH, int NT>
+__global__ void __launch_bounds__(NT) icp_accumulate_kernel(const IcpParams p)
 {
-    __shared__ double smem[8][27];
-    const int tid = threadIdx.y * 32 + threadIdx.x;
+    constexpr int NW = NT / 32;
+    __shared__ double smem[NW][27];
+    const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     float acc[27];
 #pragma unroll
     for (int i = 0; i < 27; ++i) acc[i] = 0.f;
 
-    const bool active = p.ok_ptr ? (*p.ok_ptr != 0) : true;
+    // pose and gate written by the previous solve: both loads are issued before either is consumed
+    Aff T = p.T_val;
+    int active = 1;
+    if (p.T_ptr) {
+        float t[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) t[i] = p.T_ptr[i];
+        active = *p.ok_ptr;
+        T.r0 = make_float3(t[0], t[1], t[2]);
+        T.r1 = make_float3(t[3], t[4], t[5]);
+        T.r2 = make_float3(t[6], t[7], t[8]);
+        T.t = make_float3(t[9], t[10], t[11]);
+    }
     if (active) {
-        Aff T = p.T_val;
-        if (p.T_ptr) {
-            T.r0 = make_float3(p.T_ptr[0], p.T_ptr[1], p.T_ptr[2]);
-            T.r1 = make_float3(p.T_ptr[3], p.T_ptr[4], p.T_ptr[5]);
-            T.r2 = make_float3(p.T_ptr[6], p.T_ptr[7], p.T_ptr[8]);
-            T.t = make_float3(p.T_ptr[9], p.T_ptr[10], p.T_ptr[11]);
-        }
-        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-            const int x = (tile % p.tiles_x) * 32 + threadIdx.x;
-            const int y = (tile / p.tiles_x) * 8 + threadIdx.y;
+        const int npix = p.cols * p.rows;
+        for (int i = blockIdx.x * NT + tid; i < npix; i += gridDim.x * NT) {
+            const int y = i / p.cols, x = i - y * p.cols;
             float row[7];
-            if (x < p.cols && y < p.rows && icp_row<DEPTH>(p, T, x, y, row)) {
+            if (icp_row<DEPTH>(p, T, x, y, row)) {
                 int k = 0;
 #pragma unroll
-                for (int i = 0; i < 6; ++i)
+                for (int a = 0; a < 6; ++a)
 #pragma unroll
-                    for (int j = i; j < 7; ++j) acc[k++] += row[i] * row[j];
+                    for (int j = a; j < 7; ++j) acc[k++] += row[a] * row[j];
             }
         }
     }
@@ -123,21 +131,44 @@ __global__ void __launch_bounds__(256) icp_accumulate_kernel(const IcpParams p)
     if (tid < 27) {
         double v = 0.0;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) v += smem[w][tid];
+        for (int w = 0; w < NW; ++w) v += smem[w][tid];
         p.partials[(size_t)blockIdx.x * 27 + tid] = v;
     }
 }
 
-// fixed-order reduction of the block partials into sums[27]
-__device__ void reduce_partials(const double *partials, int nblocks, double *sums_smem)
+// fixed-order reduction of the block partials into sums[27].  The rows are first staged in shared memory with cp.async (every
+// thread's copies are in flight together: ONE L2 round trip for the whole table; a register-accumulating loop was serialised by
+// the compiler into one round trip per load), then each warp sums its columns s = warp, warp + nwarps, ... lane-strided.
+constexpr int RED_ROWS = 160;                               // rows staged per pass (>= ICP_MAX_PARTIAL_BLOCKS)
+__device__ void reduce_partials(const double *partials, int nblocks, double *sums_smem, double *stage)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    for (int s = warp; s < 27; s += nwarps) {
-        double v = 0.0;
-        for (int b = lane; b < nblocks; b += 32) v += partials[(size_t)b * 27 + s];
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int base = 0; base < nblocks; base += RED_ROWS) {
+        const int rows = nblocks - base < RED_ROWS ? nblocks - base : RED_ROWS;
+        const int chunks = (rows * 27 + 1) >> 1;            // 16-byte chunks (an odd tail reads one double of slack)
+        const double *src = partials + (size_t)base * 27;
+        for (int c = threadIdx.x; c < chunks; c += blockDim.x) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(stage + 2 * c);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + 2 * c) : "memory");
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) sums_smem[s] = v;
+        for (int q = 0; q < 4; ++q) {
+            const int s = warp + q * nwarps;
+            if (s < 27)
+                for (int b = lane; b < rows; b += 32) v[q] += stage[b * 27 + s];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        double t = v[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        const int s = warp + q * nwarps;
+        if (lane == 0 && s < 27) sums_smem[s] = t;
     }
     __syncthreads();
 }
@@ -145,7 +176,8 @@ __device__ void reduce_partials(const double *partials, int nblocks, double *sum
 __global__ void __launch_bounds__(256) icp_reduce_kernel(const double *partials, int nblocks, double *out27)
 {
     __shared__ double sums[27];
-    reduce_partials(partials, nblocks, sums);
+    __shared__ __align__(16) double stage[RED_ROWS * 27];
+    reduce_partials(partials, nblocks, sums, stage);
     if (threadIdx.x < 27) out27[threadIdx.x] = sums[threadIdx.x];
 }
 
@@ -256,8 +288,12 @@ __device__ void sym6_solve_dev(const double *Ain, const double *b, double *x)
 __global__ void __launch_bounds__(256) icp_solve_kernel(const double *partials, int nblocks, float *T, int *ok)
 {
     __shared__ double sums[27];
+    __shared__ __align__(16) double stage[RED_ROWS * 27];
+    float Tin[12];                                                       // loaded up front: in flight with the partials
+#pragma unroll
+    for (int i = 0; i < 12; ++i) Tin[i] = T[i];
     if (*ok == 0) return;
-    reduce_partials(partials, nblocks, sums);
+    reduce_partials(partials, nblocks, sums, stage);
     if (threadIdx.x != 0) return;
     double A[36], b[6];
     {
@@ -295,8 +331,8 @@ __global__ void __launch_bounds__(256) icp_solve_kernel(const double *partials, 
     float Rn[9], tn[3];
     for (int i = 0; i < 3; ++i) {
         for (int j = 0; j < 3; ++j)
-            Rn[i * 3 + j] = Rinc[i * 3 + 0] * T[0 * 3 + j] + Rinc[i * 3 + 1] * T[1 * 3 + j] + Rinc[i * 3 + 2] * T[2 * 3 + j];
-        tn[i] = Rinc[i * 3 + 0] * T[9] + Rinc[i * 3 + 1] * T[10] + Rinc[i * 3 + 2] * T[11] + rf[3 + i];
+            Rn[i * 3 + j] = Rinc[i * 3 + 0] * Tin[0 * 3 + j] + Rinc[i * 3 + 1] * Tin[1 * 3 + j] + Rinc[i * 3 + 2] * Tin[2 * 3 + j];
+        tn[i] = Rinc[i * 3 + 0] * Tin[9] + Rinc[i * 3 + 1] * Tin[10] + Rinc[i * 3 + 2] * Tin[11] + rf[3 + i];
     }
     for (int i = 0; i < 9; ++i) T[i] = Rn[i];
     for (int i = 0; i < 3; ++i) T[9 + i] = tn[i];
@@ -308,13 +344,27 @@ __global__ void icp_init_kernel(float *T, int *ok)
     if (threadIdx.x == 0) *ok = 1;
 }
 
+constexpr int ICP_MAX_PARTIAL_BLOCKS = 148;
+
+template <int NT>
+void launch_accumulate_nt(const IcpParams &p, int blocks, cudaStream_t s)
+{
+    if (p.dcurr) icp_accumulate_kernel<true, NT><<<blocks, NT, 0, s>>>(p);
+    else icp_accumulate_kernel<false, NT><<<blocks, NT, 0, s>>>(p);
+}
+
 int launch_accumulate(IcpParams &p, cudaStream_t s)
 {
-    p.tiles_x = div_up(p.cols, 32);
-    p.tiles = p.tiles_x * div_up(p.rows, 8);
-    const int blocks = p.tiles < 148 * 4 ? p.tiles : 148 * 4;
-    if (p.dcurr) icp_accumulate_kernel<true><<<blocks, dim3(32, 8), 0, s>>>(p);
-    else icp_accumulate_kernel<false><<<blocks, dim3(32, 8), 0, s>>>(p);
+    const int npix = p.cols * p.rows;
+    int blocks;
+    if (npix >= ICP_MAX_PARTIAL_BLOCKS * 768) {         // 768 threads x 80 registers = one full-register-file block per SM
+        blocks = ICP_MAX_PARTIAL_BLOCKS;
+        launch_accumulate_nt<768>(p, blocks, s);
+    } else {
+        blocks = div_up(npix, 256) < ICP_MAX_PARTIAL_BLOCKS ? div_up(npix, 256) : ICP_MAX_PARTIAL_BLOCKS;
+        if (blocks < 1) blocks = 1;
+        launch_accumulate_nt<256>(p, blocks, s);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return -(int)e;
     return blocks;
@@ -327,6 +377,7 @@ extern "C" int df_icp_accumulate(const float *vcurr, size_t vcurr_pitch, const f
                                  int cols, int rows, df_intr intr_level, df_aff3f T, float dist2_thres, float min_cosine,
                                  double *scratch, void *stream)
 {
+    if ((size_t)scratch & 15) return (int)cudaErrorMisalignedAddress;
     IcpParams p;
     p.vcurr = (const float4 *)vcurr; p.vcpitch = vcurr_pitch; p.ncurr = (const float4 *)ncurr; p.ncpitch = ncurr_pitch;
     p.vprev = (const float4 *)vprev; p.vppitch = vprev_pitch; p.nprev = (const float4 *)nprev; p.nppitch = nprev_pitch;
@@ -349,6 +400,7 @@ extern "C" int df_icp_accumulate_depth(const unsigned short *dcurr, size_t dcurr
                                        double *scratch, void *stream)
 {
     if (!dcurr || !dprev) return (int)cudaErrorInvalidValue;
+    if ((size_t)scratch & 15) return (int)cudaErrorMisalignedAddress;
     IcpParams p;
     p.vcurr = p.vprev = nullptr; p.vcpitch = p.vppitch = 0;
     p.ncurr = (const float4 *)ncurr; p.ncpitch = ncurr_pitch; p.nprev = (const float4 *)nprev; p.nppitch = nprev_pitch;
@@ -373,6 +425,7 @@ int icp_estimate_impl(const float *const *vcurr, const unsigned short *const *dc
                       const size_t *dpitch, int levels, const int *iters, df_intr intr, float dist_thres, float angle_thres, float *T_dev,
                       int *ok_dev, double *scratch, cudaStream_t s)
 {
+    if ((size_t)scratch & 15) return (int)cudaErrorMisalignedAddress;
     icp_init_kernel<<<1, 32, 0, s>>>(T_dev, ok_dev);        // affine = Identity, projective_icp.cpp:175
     DF_LAUNCH_CHECK();
     for (int level = levels - 1; level >= 0; --level) {

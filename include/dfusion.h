@@ -136,8 +136,8 @@ int df_resize_depth_normals(const uint16_t *dsrc, size_t dsrc_pitch, const float
 
 /* ------------------------------------------------------------------ projective ICP -------------------------------------------------------- */
 /* ComputeIcpHelper::operator() points variant (internal.hpp:67-102, proj_icp.cu:80-108,350-394,448-467): one
- * data-association + 27-term reduction pass at one pyramid level.  scratch: device buffer of DF_ICP_SCRATCH_DOUBLES
- * doubles; on completion scratch[0..26] hold the 27 sums, order (i, j>=i) for i = 0..5, j = 0..6 (the rest holds the
+ * data-association + 27-term reduction pass at one pyramid level.  scratch: 16-byte aligned device buffer of
+ * DF_ICP_SCRATCH_DOUBLES doubles; on completion scratch[0..26] hold the 27 sums, order (i, j>=i) for i = 0..5, j = 0..6 (the rest holds the
  * per-block partials, summed in a fixed order: results are run-to-run deterministic).  intr_level are the level's
  * intrinsics (setLevelIntr, projective_icp.cpp:17-23). */
 #define DF_ICP_SCRATCH_DOUBLES (32 + 27 * 1024)
