@@ -61,7 +61,31 @@ static inline int div_up(int a, int b) { return (a + b - 1) / b; }
 // a voxel takes part in surface extraction iff W != 0 && F != 1.f (tsdf_volume.cu:548-633); 0x3c00 = half(1.0)
 __device__ __forceinline__ bool vox_active(uint32_t v) { return (v >> 16) != 0 && (v & 0xffffu) != 0x3c00u; }
 
+// Programmatic dependent launch (sm_90+): a kernel launched through launch_pdl may be scheduled while its predecessor in the
+// stream is still draining; it must execute pdl_wait() before it touches anything the predecessor wrote (or overwrites anything
+// the predecessor reads).  Every kernel of a chain calls pdl_wait() first and pdl_trigger() right after, so the data flow stays
+// fully serialised and only the launch latency of the successor is hidden.  Both are no-ops in a normal launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+int pdl_enabled();          // DF_PDL (default 1), read once (df_common.cu)
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled();
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 }  // namespace dfb
+
+// first statement of every kernel launched through launch_pdl
+#define DF_PDL_ENTRY() do { dfb::pdl_wait(); dfb::pdl_trigger(); } while (0)
 
 #define DF_LAUNCH_CHECK()                                  \
     do {                                                   \

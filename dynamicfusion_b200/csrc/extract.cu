@@ -164,6 +164,7 @@ __device__ __forceinline__ void load_block_quads(const ExtractParams &p, size_t 
 template <int VX>
 __global__ void __launch_bounds__(EX_THREADS) extract_count_kernel(const ExtractParams p, int *block_counts)
 {
+    DF_PDL_ENTRY();
     const size_t q0 = (size_t)blockIdx.x * EX_THREADS * EX_QPT;
     uint32_t own[EX_QPT][VX];
     load_block_quads<VX>(p, q0, own);
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(EX_THREADS) extract_count_kernel(const Extract
 // over the <= 1024 super totals.  (A single-block serial-chunk scan of the 131,072 counts of a 512^3 volume took 0.26 ms.)
 __global__ void __launch_bounds__(1024) extract_scan_local_kernel(const int *counts, int *offsets, int n, int *super_tot)
 {
+    DF_PDL_ENTRY();
     __shared__ int wsum[32];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int i = blockIdx.x * 1024 + t;
@@ -204,6 +206,7 @@ __global__ void __launch_bounds__(1024) extract_scan_local_kernel(const int *cou
 
 __global__ void __launch_bounds__(1024) extract_scan_super_kernel(const int *super_tot, int nsuper, int *super_off, int capacity, int *count_out)
 {
+    DF_PDL_ENTRY();
     __shared__ int wsum[32];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int c = t < nsuper ? super_tot[t] : 0;
@@ -228,6 +231,7 @@ template <int VX>
 __global__ void __launch_bounds__(EX_THREADS) extract_emit_kernel(const ExtractParams p, const int *block_counts, const int *offsets,
                                                                   const int *super_off, float4 *out, int capacity)
 {
+    DF_PDL_ENTRY();
     if (block_counts[blockIdx.x] == 0) return;
     const size_t q0 = (size_t)blockIdx.x * EX_THREADS * EX_QPT;
     uint32_t own[EX_QPT][VX];
@@ -286,18 +290,18 @@ extern "C" int df_extract_cloud_tracked(df_volume vol, df_aff3f pose, float *out
     int *block_counts = (int *)workspace;
     int *offsets = block_counts + p.nblocks;
     cudaStream_t s = (cudaStream_t)stream;
-    if (vx == 4) extract_count_kernel<4><<<p.nblocks, EX_THREADS, 0, s>>>(p, block_counts);
-    else extract_count_kernel<1><<<p.nblocks, EX_THREADS, 0, s>>>(p, block_counts);
+    if (vx == 4) launch_pdl(extract_count_kernel<4>, dim3(p.nblocks), dim3(EX_THREADS), 0, s, p, block_counts);
+    else launch_pdl(extract_count_kernel<1>, dim3(p.nblocks), dim3(EX_THREADS), 0, s, p, block_counts);
     DF_LAUNCH_CHECK();
     const int nsuper = (p.nblocks + 1023) / 1024;
     if (nsuper > 1024) return (int)cudaErrorInvalidValue;               // > 2^20 blocks (volume > 1024^3 voxels)
     int *super_tot = offsets + p.nblocks, *super_off = super_tot + 1024;
-    extract_scan_local_kernel<<<nsuper, 1024, 0, s>>>(block_counts, offsets, p.nblocks, super_tot);
+    launch_pdl(extract_scan_local_kernel, dim3(nsuper), dim3(1024), 0, s, block_counts, offsets, p.nblocks, super_tot);
     DF_LAUNCH_CHECK();
-    extract_scan_super_kernel<<<1, 1024, 0, s>>>(super_tot, nsuper, super_off, capacity, count);
+    launch_pdl(extract_scan_super_kernel, dim3(1), dim3(1024), 0, s, super_tot, nsuper, super_off, capacity, count);
     DF_LAUNCH_CHECK();
-    if (vx == 4) extract_emit_kernel<4><<<p.nblocks, EX_THREADS, 0, s>>>(p, block_counts, offsets, super_off, (float4 *)out_points, capacity);
-    else extract_emit_kernel<1><<<p.nblocks, EX_THREADS, 0, s>>>(p, block_counts, offsets, super_off, (float4 *)out_points, capacity);
+    if (vx == 4) launch_pdl(extract_emit_kernel<4>, dim3(p.nblocks), dim3(EX_THREADS), 0, s, p, block_counts, offsets, super_off, (float4 *)out_points, capacity);
+    else launch_pdl(extract_emit_kernel<1>, dim3(p.nblocks), dim3(EX_THREADS), 0, s, p, block_counts, offsets, super_off, (float4 *)out_points, capacity);
     DF_LAUNCH_CHECK();
     return 0;
 }
@@ -346,6 +350,7 @@ __device__ __forceinline__ float en_interpolate(const NormalsParams &p, const fl
 
 __global__ void __launch_bounds__(256) extract_normals_kernel(const NormalsParams p)
 {
+    DF_PDL_ENTRY();
     const int n = p.count_dev ? min(*p.count_dev, p.n) : p.n;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
         const float nanv = qnan();
@@ -384,7 +389,7 @@ extern "C" int df_extract_normals(df_volume vol, const float *points, int n_poin
     p.Rinv = make_mat3(Rinv_host9);
     p.points = (const float4 *)points; p.n = n_points; p.count_dev = count_dev; p.out = (float4 *)out_normals;
     const int blocks = count_dev ? 148 * 8 : div_up(n_points, 256);
-    extract_normals_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    launch_pdl(extract_normals_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, p);
     DF_LAUNCH_CHECK();
     return 0;
 }

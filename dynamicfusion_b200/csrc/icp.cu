@@ -10,8 +10,16 @@
 //   icp_solve_kernel       one block: fixed-order sum of the partials, 6x6 solve, Rodrigues, T <- Tinc * T in place.
 #include "df_common.cuh"
 #include <float.h>
+#include <stdlib.h>
 
 using namespace dfb;
+
+int dfb::pdl_enabled()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("DF_PDL"); v = e ? (atoi(e) != 0) : 1; }
+    return v;
+}
 
 namespace {
 
@@ -38,6 +46,9 @@ struct IcpParams {
 template <bool DEPTH>
 __device__ __forceinline__ bool icp_row(const IcpParams &p, const Aff &T, int x, int y, float row[7])
 {
+    // the loads of one pixel go out in two batches (current maps at (x, y), previous maps at the projection) instead of one
+    // dependent round trip per test: the order of the reference's tests is kept, only the fetches are hoisted
+    const float4 nc = __ldg(row_ptr(p.ncurr, p.ncpitch, y) + x);
     float3 s;
     if (DEPTH) {
         const int src_z = __ldg(row_ptr(p.dcurr, p.dcpitch, y) + x);
@@ -54,22 +65,21 @@ __device__ __forceinline__ bool icp_row(const IcpParams &p, const Aff &T, int x,
     const float v = __fmaf_rn(p.fy, s.y / s.z, p.cy);
     if (s.z <= 0 || u < 0 || v < 0 || u >= p.fcols || v >= p.frows) return false;
     if (!(u == u) || !(v == v)) return false;
+    const float4 np = __ldg(row_ptr(p.nprev, p.nppitch, (int)v) + (int)u);     // point sampling of the previous maps
     float3 d;
     if (DEPTH) {
-        const int dst_z = __ldg(row_ptr(p.dprev, p.dppitch, (int)v) + (int)u);  // point sampling of the previous depth
+        const int dst_z = __ldg(row_ptr(p.dprev, p.dppitch, (int)v) + (int)u);
         if (dst_z == 0) return false;
         const float z = dst_z * 0.001f;
         d = make_float3(z * (u - p.cx) * p.finvx, z * (v - p.cy) * p.finvy, z);  // re-projected at the fractional coordinates
     } else {
-        const float4 dp = __ldg(row_ptr(p.vprev, p.vppitch, (int)v) + (int)u);  // point sampling of the previous maps
+        const float4 dp = __ldg(row_ptr(p.vprev, p.vppitch, (int)v) + (int)u);
         d = make_float3(dp.x, dp.y, dp.z);
         if (isnan(d.x)) return false;
     }
     const float3 df = sub3(s, d);
     if (dot3(df, df) > p.dist2_thres) return false;
-    const float4 nc = __ldg(row_ptr(p.ncurr, p.ncpitch, y) + x);
     const float3 ns = mat_mul(T.r0, T.r1, T.r2, make_float3(nc.x, nc.y, nc.z));
-    const float4 np = __ldg(row_ptr(p.nprev, p.nppitch, (int)v) + (int)u);
     const float3 nd = make_float3(np.x, np.y, np.z);
     if (fabsf(dot3(ns, nd)) < p.min_cosine) return false;
     const float3 c = cross3(s, nd);
@@ -92,6 +102,8 @@ __global__ void __launch_bounds__(NT) icp_accumulate_kernel(const IcpParams p)
     float acc[27];
 #pragma unroll
     for (int i = 0; i < 27; ++i) acc[i] = 0.f;
+    pdl_wait();
+    pdl_trigger();
 
     // pose and gate written by the previous solve: both loads are issued before either is consumed
     Aff T = p.T_val;
@@ -289,6 +301,8 @@ __global__ void __launch_bounds__(256) icp_solve_kernel(const double *partials, 
 {
     __shared__ double sums[27];
     __shared__ __align__(16) double stage[RED_ROWS * 27];
+    pdl_wait();
+    pdl_trigger();
     float Tin[12];                                                       // loaded up front: in flight with the partials
 #pragma unroll
     for (int i = 0; i < 12; ++i) Tin[i] = T[i];
@@ -349,8 +363,8 @@ constexpr int ICP_MAX_PARTIAL_BLOCKS = 148;
 template <int NT>
 void launch_accumulate_nt(const IcpParams &p, int blocks, cudaStream_t s)
 {
-    if (p.dcurr) icp_accumulate_kernel<true, NT><<<blocks, NT, 0, s>>>(p);
-    else icp_accumulate_kernel<false, NT><<<blocks, NT, 0, s>>>(p);
+    if (p.dcurr) launch_pdl(icp_accumulate_kernel<true, NT>, dim3(blocks), dim3(NT), 0, s, p);
+    else launch_pdl(icp_accumulate_kernel<false, NT>, dim3(blocks), dim3(NT), 0, s, p);
 }
 
 int launch_accumulate(IcpParams &p, cudaStream_t s)
@@ -449,7 +463,7 @@ int icp_estimate_impl(const float *const *vcurr, const unsigned short *const *dc
         for (int it = 0; it < iters[level]; ++it) {
             const int blocks = launch_accumulate(p, s);
             if (blocks < 0) return -blocks;
-            icp_solve_kernel<<<1, 256, 0, s>>>(p.partials, blocks, T_dev, ok_dev);
+            launch_pdl(icp_solve_kernel, dim3(1), dim3(256), 0, s, (const double *)p.partials, blocks, T_dev, ok_dev);
             DF_LAUNCH_CHECK();
         }
     }

@@ -11,6 +11,7 @@ __global__ void __launch_bounds__(256) compute_dists_kernel(const unsigned short
                                                             float finvx, float finvy, float cx, float cy,
                                                             unsigned short *dists, size_t pitch)
 {
+    DF_PDL_ENTRY();
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= cols || y >= rows) return;
@@ -24,7 +25,7 @@ extern "C" int df_compute_dists(const uint16_t *depth, size_t depth_pitch, int c
                                 uint16_t *dists, size_t dists_pitch, void *stream)
 {
     dim3 block(32, 8), grid(div_up(cols, 32), div_up(rows, 8));
-    compute_dists_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(depth, depth_pitch, cols, rows, 1.f / intr.fx, 1.f / intr.fy,
+    launch_pdl(compute_dists_kernel, dim3(grid), dim3(block), 0, (cudaStream_t)stream, depth, depth_pitch, cols, rows, 1.f / intr.fx, 1.f / intr.fy,
                                                                    intr.cx, intr.cy, dists, dists_pitch);
     DF_LAUNCH_CHECK();
     return 0;
@@ -34,6 +35,7 @@ extern "C" int df_compute_dists(const uint16_t *depth, size_t depth_pitch, int c
 __global__ void __launch_bounds__(256) bilateral_kernel(const unsigned short *src, size_t spitch, int cols, int rows,
                                                         unsigned short *dst, size_t dpitch, int ksz, float ss, float sd)
 {
+    DF_PDL_ENTRY();
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= cols || y >= rows) return;
@@ -60,7 +62,7 @@ extern "C" int df_bilateral(const uint16_t *src, size_t src_pitch, int cols, int
 {
     sigma_depth *= 1000;   // imgproc.cu:47
     dim3 block(32, 8), grid(div_up(cols, 32), div_up(rows, 8));
-    bilateral_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, src_pitch, cols, rows, dst, dst_pitch, kernel_size,
+    launch_pdl(bilateral_kernel, dim3(grid), dim3(block), 0, (cudaStream_t)stream, src, src_pitch, cols, rows, dst, dst_pitch, kernel_size,
                                                                0.5f / (sigma_spatial * sigma_spatial), 0.5f / (sigma_depth * sigma_depth));
     DF_LAUNCH_CHECK();
     return 0;
@@ -69,6 +71,7 @@ extern "C" int df_bilateral(const uint16_t *src, size_t src_pitch, int cols, int
 // truncate_depth_kernel, imgproc.cu:66-75
 __global__ void __launch_bounds__(256) truncate_depth_kernel(unsigned short *depth, size_t pitch, int cols, int rows, unsigned short max_dist)
 {
+    DF_PDL_ENTRY();
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x < cols && y < rows) {
@@ -80,7 +83,7 @@ __global__ void __launch_bounds__(256) truncate_depth_kernel(unsigned short *dep
 extern "C" int df_truncate_depth(uint16_t *depth, size_t pitch, int cols, int rows, float max_dist, void *stream)
 {
     dim3 block(32, 8), grid(div_up(cols, 32), div_up(rows, 8));
-    truncate_depth_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(depth, pitch, cols, rows, (unsigned short)(max_dist * 1000.f));
+    launch_pdl(truncate_depth_kernel, dim3(grid), dim3(block), 0, (cudaStream_t)stream, depth, pitch, cols, rows, (unsigned short)(max_dist * 1000.f));
     DF_LAUNCH_CHECK();
     return 0;
 }
@@ -89,6 +92,7 @@ extern "C" int df_truncate_depth(uint16_t *depth, size_t pitch, int cols, int ro
 __global__ void __launch_bounds__(256) pyramid_kernel(const unsigned short *src, size_t spitch, int scols, int srows,
                                                       unsigned short *dst, size_t dpitch, int dcols, int drows, float thr)
 {
+    DF_PDL_ENTRY();
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= dcols || y >= drows) return;
@@ -113,7 +117,7 @@ extern "C" int df_pyr_down(const uint16_t *src, size_t src_pitch, int src_cols, 
     sigma_depth *= 1000;   // imgproc.cu:127
     const int dcols = src_cols / 2, drows = src_rows / 2;
     dim3 block(32, 8), grid(div_up(dcols, 32), div_up(drows, 8));
-    pyramid_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, src_pitch, src_cols, src_rows, dst, dst_pitch, dcols, drows, sigma_depth * 3);
+    launch_pdl(pyramid_kernel, dim3(grid), dim3(block), 0, (cudaStream_t)stream, src, src_pitch, src_cols, src_rows, dst, dst_pitch, dcols, drows, sigma_depth * 3);
     DF_LAUNCH_CHECK();
     return 0;
 }
@@ -126,6 +130,7 @@ __global__ void __launch_bounds__(256) points_normals_kernel(float finvx, float 
                                                              const unsigned short *depth, size_t dpitch, int cols, int rows,
                                                              float4 *points, size_t ppitch, float4 *normals, size_t npitch)
 {
+    DF_PDL_ENTRY();
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= cols || y >= rows) return;
@@ -152,7 +157,7 @@ extern "C" int df_points_normals(df_intr intr, const uint16_t *depth, size_t dep
                                  float *points, size_t points_pitch, float *normals, size_t normals_pitch, void *stream)
 {
     dim3 block(32, 8), grid(div_up(cols, 32), div_up(rows, 8));
-    points_normals_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(1.f / intr.fx, 1.f / intr.fy, intr.cx, intr.cy, depth, depth_pitch,
+    launch_pdl(points_normals_kernel, dim3(grid), dim3(block), 0, (cudaStream_t)stream, 1.f / intr.fx, 1.f / intr.fy, intr.cx, intr.cy, depth, depth_pitch,
                                                                     cols, rows, (float4 *)points, points_pitch, (float4 *)normals, normals_pitch);
     DF_LAUNCH_CHECK();
     return 0;
@@ -162,6 +167,7 @@ extern "C" int df_points_normals(df_intr intr, const uint16_t *depth, size_t dep
 __global__ void __launch_bounds__(256) resize_points_normals_kernel(const float4 *vsrc, size_t vspitch, const float4 *nsrc, size_t nspitch,
                                                                     float4 *vdst, size_t vdpitch, float4 *ndst, size_t ndpitch, int dcols, int drows)
 {
+    DF_PDL_ENTRY();
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= dcols || y >= drows) return;
@@ -188,7 +194,7 @@ extern "C" int df_resize_points_normals(const float *vsrc, size_t vsrc_pitch, co
 {
     const int dcols = src_cols / 2, drows = src_rows / 2;
     dim3 block(32, 8), grid(div_up(dcols, 32), div_up(drows, 8));
-    resize_points_normals_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const float4 *)vsrc, vsrc_pitch, (const float4 *)nsrc, nsrc_pitch,
+    launch_pdl(resize_points_normals_kernel, dim3(grid), dim3(block), 0, (cudaStream_t)stream, (const float4 *)vsrc, vsrc_pitch, (const float4 *)nsrc, nsrc_pitch,
                                                                            (float4 *)vdst, vdst_pitch, (float4 *)ndst, ndst_pitch, dcols, drows);
     DF_LAUNCH_CHECK();
     return 0;

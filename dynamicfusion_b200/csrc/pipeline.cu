@@ -81,6 +81,7 @@ df_aff3f to_aff(const float *a12) { df_aff3f a; memcpy(a.R, a12, 36); memcpy(a.t
 // NaN pixels stay NaN.  Also writes the `canonical_visible` copy (kinfu.cpp:383).
 __global__ void __launch_bounds__(256) to_canonical_kernel(const float4 *src, Aff inv_pose, float4 *dst, float4 *dst_copy, int n)
 {
+    DF_PDL_ENTRY();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 v = src[i];
@@ -255,7 +256,7 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_d
         CKD(raycast_to(cam_pose, k.canon_visible, k.canon_nrm));       // tsdf().raycast(camera_pose, ...), :351 (camera frame)
         float inv_pose[12];
         dfh_aff_inv(cam_pose, inv_pose);
-        to_canonical_kernel<<<div_up(npix, 256), 256, 0, s>>>((const float4 *)k.canon_visible.ptr, make_aff(to_aff(inv_pose)),
+        launch_pdl(to_canonical_kernel, dim3(div_up(npix, 256)), dim3(256), 0, s, (const float4 *)k.canon_visible.ptr, make_aff(to_aff(inv_pose)),
                                                                (float4 *)k.canon.ptr, (float4 *)k.canon_visible.ptr, npix);
         ++k.launches;
         mark(k, 3);

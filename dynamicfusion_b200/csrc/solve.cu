@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(PREPARE_THREADS) solve_prepare_kernel(const fl
                                                             const float *__restrict__ canon, const float *__restrict__ live, int N, int stride,
                                                             SolveWs ws)
 {
+    DF_PDL_ENTRY();
     __shared__ KnnSmem sm;
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     float3 c = make_float3(0.f, 0.f, 0.f), l = c;
@@ -121,6 +122,7 @@ __global__ void __launch_bounds__(PREPARE_THREADS) solve_prepare_kernel(const fl
 
 __global__ void __launch_bounds__(1024) solve_scan_kernel(SolveWs ws, int M)
 {
+    DF_PDL_ENTRY();
     __shared__ int partial[1024];
     const int t = threadIdx.x;
     const int per = (M + 1023) / 1024;
@@ -143,6 +145,7 @@ __global__ void __launch_bounds__(1024) solve_scan_kernel(SolveWs ws, int M)
 
 __global__ void __launch_bounds__(256) solve_fill_kernel(SolveWs ws, int N)
 {
+    DF_PDL_ENTRY();
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -187,6 +190,7 @@ __device__ __forceinline__ int rows_find_slot(const int *keys, int j)
 
 __global__ void __launch_bounds__(ROWS_THREADS) solve_rows_kernel(SolveWs ws, int M, int N, int quirk)
 {
+    DF_PDL_ENTRY();
     __shared__ int keys[HCAP];
     __shared__ int slot_rank[HCAP];
     __shared__ int list[HCAP];
@@ -1316,6 +1320,7 @@ template <int NCTA>
 __global__ void __launch_bounds__(LM4_THREADS)
 solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_iters, int lin_iters, double *stats, int ent_cap)
 {
+    DF_PDL_ENTRY();
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ Lm5Smem<NCTA> sm;
     extern __shared__ __align__(16) unsigned char dyn[];
@@ -1559,13 +1564,13 @@ extern "C" int df_solve_data_term(float *nodes, int M, const void *node_grid, co
     layout(ws, base, M, N);
     cudaError_t e = cudaMemsetAsync(ws.cnt, 0, (size_t)(M + 1) * 4, s);
     if (e != cudaSuccess) return (int)e;
-    solve_prepare_kernel<<<ws.prepare_blocks, 256, 0, s>>>(nodes, M, node_grid, canon, live, N, stride, ws);
+    launch_pdl(solve_prepare_kernel, dim3(ws.prepare_blocks), dim3(256), 0, s, nodes, M, node_grid, canon, live, N, stride, ws);
     DF_LAUNCH_CHECK();
-    solve_scan_kernel<<<1, 1024, 0, s>>>(ws, M);
+    launch_pdl(solve_scan_kernel, dim3(1), dim3(1024), 0, s, ws, M);
     DF_LAUNCH_CHECK();
-    solve_fill_kernel<<<ws.prepare_blocks, 256, 0, s>>>(ws, N);
+    launch_pdl(solve_fill_kernel, dim3(ws.prepare_blocks), dim3(256), 0, s, ws, N);
     DF_LAUNCH_CHECK();
-    solve_rows_kernel<<<M, ROWS_THREADS, 0, s>>>(ws, M, N, flags & DF_SOLVE_REF_GRAPH_QUIRK);
+    launch_pdl(solve_rows_kernel, dim3(M), dim3(ROWS_THREADS), 0, s, ws, M, N, flags & DF_SOLVE_REF_GRAPH_QUIRK);
     DF_LAUNCH_CHECK();
     const size_t smem_budget = 200 * 1024;
     const LmSmemLayout L0 = lm_layout(M, 0);
@@ -1594,10 +1599,12 @@ extern "C" int df_solve_data_term(float *nodes, int M, const void *node_grid, co
             }
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(ncta); cfg.blockDim = dim3(LM4_THREADS); cfg.dynamicSmemBytes = Lc.total; cfg.stream = s;
-            cudaLaunchAttribute at[1];
+            cudaLaunchAttribute at[2];
             at[0].id = cudaLaunchAttributeClusterDimension;
             at[0].val.clusterDim.x = ncta; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            cfg.attrs = at; cfg.numAttrs = 1;
+            at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[1].val.programmaticStreamSerializationAllowed = pdl_enabled();
+            cfg.attrs = at; cfg.numAttrs = 2;
             cudaError_t le;
             if (ncta == 16) le = cudaLaunchKernelEx(&cfg, solve_lm_v5_kernel<16>, nodes, M, node_grid, ws, nonlinear_iters, linear_iters, stats_dev, cap);
             else le = cudaLaunchKernelEx(&cfg, solve_lm_v5_kernel<8>, nodes, M, node_grid, ws, nonlinear_iters, linear_iters, stats_dev, cap);

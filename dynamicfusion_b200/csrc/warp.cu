@@ -13,6 +13,7 @@ __global__ void __launch_bounds__(256) knn8_kernel(const float *__restrict__ nod
                                                    const float *__restrict__ queries, int N,
                                                    int qstride, int *__restrict__ idx, float *__restrict__ d2)
 {
+    DF_PDL_ENTRY();
     __shared__ KnnSmem sm;
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     float qx = 0.f, qy = 0.f, qz = 0.f;
@@ -53,6 +54,7 @@ __device__ __forceinline__ float3 aff_apply_cv(const Aff &a, const float3 v)
 template <bool kReuse>
 __global__ void __launch_bounds__(256) warp_kernel(const WarpParams p)
 {
+    DF_PDL_ENTRY();
     __shared__ KnnSmem sm;
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     float3 pt = make_float3(0.f, 0.f, 0.f), nr = pt;
@@ -114,7 +116,7 @@ extern "C" int df_knn8(const float *nodes, int M, const void *node_grid, const f
                        void *stream)
 {
     if (N <= 0) return 0;
-    knn8_kernel<<<div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(nodes, M, node_grid, queries, N, qstride, idx, d2);
+    launch_pdl(knn8_kernel, dim3(div_up(N, 256)), dim3(256), 0, (cudaStream_t)stream, nodes, M, node_grid, queries, N, qstride, idx, d2);
     DF_LAUNCH_CHECK();
     return 0;
 }
@@ -128,8 +130,8 @@ extern "C" int df_warp(const float *nodes, int M, const void *node_grid, float *
     WarpParams p;
     p.nodes = nodes; p.M = M; p.grid = node_grid; p.points = points; p.normals = normals; p.N = N; p.stride = stride;
     p.w2l = make_aff(warp_to_live); p.flags = flags; p.idx = idx; p.w = w;
-    if (flags & DF_WARP_REUSE_KNN) warp_kernel<true><<<div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(p);
-    else warp_kernel<false><<<div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    if (flags & DF_WARP_REUSE_KNN) launch_pdl(warp_kernel<true>, dim3(div_up(N, 256)), dim3(256), 0, (cudaStream_t)stream, p);
+    else launch_pdl(warp_kernel<false>, dim3(div_up(N, 256)), dim3(256), 0, (cudaStream_t)stream, p);
     DF_LAUNCH_CHECK();
     return 0;
 }

@@ -108,7 +108,7 @@ int main()
             cuda::Depth raw;
             raw.upload(&depth[0], params.cols * sizeof(unsigned short), params.rows, params.cols);
             cuda::depthBilateralFilter(raw, fr.depth_pyr[0], params.bilateral_kernel_size, params.bilateral_sigma_spatial, params.bilateral_sigma_depth);
-            cuda::depthTruncation(fr.depth_pyr[0], params.icp_truncate_depth_dist);
+            if (params.icp_truncate_depth_dist > 0) cuda::depthTruncation(fr.depth_pyr[0], params.icp_truncate_depth_dist);   // disabled by default (kinfu.cpp:33,229)
             for (int i = 1; i < LEVELS; ++i) cuda::depthBuildPyramid(fr.depth_pyr[i - 1], fr.depth_pyr[i], params.bilateral_sigma_depth);
             for (int i = 0; i < LEVELS; ++i) cuda::computeNormalsAndMaskDepth(params.intr(i), fr.depth_pyr[i], fr.normals_pyr[i]);
         }
