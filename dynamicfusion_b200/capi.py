@@ -39,7 +39,8 @@ class KinfuParams(C.Structure):
                 ("raycast_step_factor", C.c_float), ("gradient_delta_factor", C.c_float),
                 ("light_pose", C.c_float * 3),
                 ("solver_nonlinear_iters", C.c_int), ("solver_linear_iters", C.c_int),
-                ("max_nodes", C.c_int), ("node_step", C.c_int), ("cloud_capacity", C.c_int), ("flags", C.c_int)]
+                ("max_nodes", C.c_int), ("node_step", C.c_int), ("cloud_capacity", C.c_int), ("flags", C.c_int),
+                ("fusion_weight_scale", C.c_float)]
 
 
 _vp, _sz, _i, _f = C.c_void_p, C.c_size_t, C.c_int, C.c_float
@@ -83,6 +84,9 @@ PROTOTYPES = {
     "df_node_grid_bytes": (_sz, [_i]),
     "df_build_node_grid": (_i, [_vp, _i, _vp, _vp]),
     "df_warp": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, Aff3f, _i, _vp, _vp, _vp]),
+    "df_integrate_warped_workspace_bytes": (_sz, [_i, _i]),
+    "df_integrate_warped_launch_count": (_i, []),
+    "df_integrate_warped": (_i, [Volume, _vp, _sz, _i, _i, Aff3f, Aff3f, Intr, _vp, _i, _vp, _f, _vp, _vp, _vp, _vp]),
     "df_solve_workspace_bytes": (_sz, [_i, _i]),
     "df_solve_knn_buffers": (_i, [_vp, _i, _i, C.POINTER(_vp), C.POINTER(_vp)]),
     "df_solve_data_term": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),

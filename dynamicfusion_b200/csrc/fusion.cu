@@ -1,0 +1,351 @@
+// fusion.cu -- per-voxel warped TSDF integration on sm_100a: k-NN + node weights + dual-quaternion blend +
+// projective signed distance + weighted running average fused into one kernel over the voxels that can be updated.
+//
+// The reference stops short of this step: TsdfVolume::surface_fusion (kfusion/src/tsdf_volume.cpp:228-254) evaluates psdf() for the
+// warped ray-cast points, runs the RIGID integrate and leaves the per-entry update commented out (:248-251).  The update built here
+// is the one that code was written towards (DynamicFusion eq. 4-5), assembled only from operations the reference defines, in the
+// reference's operation order (each cited below); the CPU restatement it is tested against is oracle/orc_fusion.c.
+//
+//   x_c = pose_vol * (x*vs, y*vs, z*vs)            TsdfIntegrator's voxel position (tsdf_volume.cu:62-64), Aff3f * float3 (device.hpp:71-74)
+//   8-NN of x_c, weights, DQB, transform           WarpField::KNN / weighting / DQB / warp (warp_field.cpp:180-251)
+//   x_t = world2cam * x_w                          cv::Affine3f * Vec3f (the last step of WarpField::warp)
+//   rho = depth(floor v, floor u) * 0.001 - x_t.z  TsdfVolume::psdf (tsdf_volume.cpp:266-292) with Projector (device.hpp:32-38)
+//   if rho > -trunc:  tsdf = min(1, rho / trunc);  w = mean node distance (TsdfVolume::weighting, :300-306) quantised to the u16 weight;
+//                     F' = (F*W + tsdf*w) / (W + w), W' = min(W + w, max_weight)          (:248-251 in the arithmetic of tsdf_volume.cu:97-103)
+//
+// Cost model.  Unlike the rigid rule, a voxel's pixel is only known after its warp, i.e. after an exact 8-NN search and a blend with
+// eight double-precision exponentials (~2 k instructions): the kernel is instruction-bound by three orders of magnitude over its
+// 8 bytes of volume traffic per written voxel, so the design levers are (i) not searching for voxels that cannot be updated and
+// (ii) making the search cheap:
+//   (i)  a warp owns an 8 x 4 voxel footprint; before every run of FUS_SUB slices it tests the sub-brick GROWN BY THE LARGEST
+//        DISPLACEMENT THE FIELD CAN PRODUCE against the frustum and against the per-tile depth maxima (three levels: 16-pixel tiles,
+//        64-pixel tiles, whole image).  The bound: weights are exp(-d^2/2s^2) <= 1 and are not normalised (warp_field.cpp:203-217), so
+//        |x_w - x_c| <= 8 max_i |t_i| when every node rotation is the identity (true for everything the translation-only solve
+//        produces); one small kernel per call reduces it over the node table and reports +inf (no culling) if any node is rotated.
+//   (ii) consecutive voxels of a z-column have almost the same neighbours: the largest distance from the new voxel to the previous
+//        voxel's eight neighbours bounds its 8th-nearest distance, and a BVH descent with that bound (knn8_bvh_bounded) touches one or
+//        two leaves instead of walking grid shells.  Results are ranked by (distance, index) on every path: identical to the exhaustive scan.
+#include "warp_common.cuh"
+#include <cmath>
+#include <cstdlib>
+
+using namespace dfb;
+
+namespace {
+
+constexpr int FUS_SUB = 8;          // slices per visibility test
+constexpr int FUS_TILE = 16;        // fine depth tiles (pixels)
+constexpr int FUS_COARSE = 4;       // coarse tile = FUS_COARSE x FUS_COARSE fine tiles
+
+struct FusionParams {
+    uint32_t *data;
+    int Dx, Dy, Dz;
+    float vsx, vsy, vsz;
+    float trunc, trunc_inv;
+    int max_weight;
+    const unsigned short *depth;
+    size_t pitch;
+    int cols, rows;
+    float fcols, frows;
+    Aff vol2world, world2cam, vol2cam;     // vol2cam = world2cam o vol2world: used by the visibility test only
+    float fx, fy, cx, cy;
+    const float *nodes; int M; const void *grid;
+    float weight_scale;
+    int cull;                              // 0: the two poses are not rigid -> no visibility test
+    const float *ws;                       // [0] displacement bound, [1] global depth maximum, [16..] fine tile maxima, then coarse
+    int tiles_x, tiles_y, ctiles_x, ctiles_y;
+    int zchunk;
+    unsigned long long *counters;          // [0] voxels written, [1] voxels warped
+    unsigned char *activity;
+};
+
+// metric depth maxima per FUS_TILE x FUS_TILE pixel tile
+__global__ void __launch_bounds__(256) depth_tile_max_kernel(const unsigned short *__restrict__ depth, size_t pitch, int cols, int rows, float *tile_max, int tiles_x)
+{
+    DF_PDL_ENTRY();
+    const int tx = blockIdx.x, ty = blockIdx.y;
+    const int x = tx * FUS_TILE + (threadIdx.x & (FUS_TILE - 1)), y = ty * FUS_TILE + (threadIdx.x / FUS_TILE);
+    float v = 0.f;
+    if (x < cols && y < rows) v = (float)__ldg(row_ptr(depth, pitch, y) + x) * 0.001f;
+    __shared__ float wm[8];
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m = wm[0];
+        for (int i = 1; i < 8; ++i) m = fmaxf(m, wm[i]);
+        tile_max[ty * tiles_x + tx] = m;
+    }
+}
+
+// block 0: coarse tile maxima + global maximum from the fine ones; block 1: displacement bound of the node table
+__global__ void __launch_bounds__(256) fusion_prepare_kernel(float *ws, int tiles_x, int tiles_y, int ctiles_x, int ctiles_y, const float *__restrict__ nodes, int M)
+{
+    DF_PDL_ENTRY();
+    __shared__ float red[256];
+    __shared__ int flag;
+    const int t = threadIdx.x;
+    float *fine = ws + 16, *coarse = fine + tiles_x * tiles_y;
+    if (blockIdx.x == 0) {
+        float g = 0.f;
+        for (int c = t; c < ctiles_x * ctiles_y; c += 256) {
+            const int cx = c % ctiles_x, cy = c / ctiles_x;
+            float m = 0.f;
+            for (int j = 0; j < FUS_COARSE; ++j)
+                for (int i = 0; i < FUS_COARSE; ++i) {
+                    const int fx = cx * FUS_COARSE + i, fy = cy * FUS_COARSE + j;
+                    if (fx < tiles_x && fy < tiles_y) m = fmaxf(m, fine[fy * tiles_x + fx]);
+                }
+            coarse[c] = m;
+            g = fmaxf(g, m);
+        }
+        red[t] = g;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) { if (t < o) red[t] = fmaxf(red[t], red[t + o]); __syncthreads(); }
+        if (t == 0) ws[1] = red[0];
+    } else {
+        if (t == 0) flag = 0;
+        __syncthreads();
+        float tmax = 0.f;
+        bool rotated = false;
+        for (int i = t; i < M; i += 256) {
+            const float4 *n4 = reinterpret_cast<const float4 *>(nodes + (size_t)i * DF_NODE_STRIDE);
+            const float4 a = __ldg(n4), b = __ldg(n4 + 1), c = __ldg(n4 + 2);
+            const Quat rot = {a.w, b.x, b.y, b.z};
+            const Quat dual = {b.w, c.x, c.y, c.z};
+            if (!(rot.w == 1.f && rot.x == 0.f && rot.y == 0.f && rot.z == 0.f)) rotated = true;
+            const Quat tr = dq_translation(rot, dual);
+            const float len = sqrtf(tr.x * tr.x + tr.y * tr.y + tr.z * tr.z);
+            tmax = fmaxf(tmax, len);
+            if (!(len == len)) rotated = true;              // NaN translation: no bound
+        }
+        if (rotated) atomicOr(&flag, 1);
+        red[t] = tmax;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) { if (t < o) red[t] = fmaxf(red[t], red[t + o]); __syncthreads(); }
+        if (t == 0) ws[0] = flag ? __int_as_float(0x7f800000) : 8.f * red[0] * 1.0001f + 1e-6f;
+    }
+}
+
+// true when no voxel with x in [xa, xb], y in [ya, yb], z in [za, zb] can be updated whatever the field does to it within `delta`:
+// the sub-brick, grown by one voxel and by delta along every volume axis (this contains its Minkowski sum with the delta-ball), is
+// convex, so half-space tests on its eight corners decide the frustum; every point of it is at least zmin deep, so
+// rho = Dp - z <= max depth of the tiles it can project to - zmin.
+__device__ __forceinline__ bool fusion_run_invisible(const FusionParams &p, int lane, float delta, int xa, int xb, int ya, int yb, int za, int zb)
+{
+    const int k = lane & 7;
+    const float3 c = make_float3((k & 1) ? (float)(xb + 1) * p.vsx + delta : (float)(xa - 1) * p.vsx - delta,
+                                 (k & 2) ? (float)(yb + 1) * p.vsy + delta : (float)(ya - 1) * p.vsy - delta,
+                                 (k & 4) ? (float)(zb + 1) * p.vsz + delta : (float)(za - 1) * p.vsz - delta);
+    const float3 pc = aff_mul(p.vol2cam, c);
+    const unsigned full = 0xffffffffu;
+    if (__all_sync(full, pc.z < -1e-3f)) return true;             // x_t.z <= 0 for every voxel
+    if (__any_sync(full, !(pc.z > 1e-2f))) return false;          // straddles the camera plane: no projective reasoning
+    const float u = p.fx * (pc.x / pc.z) + p.cx, v = p.fy * (pc.y / pc.z) + p.cy;
+    if (__all_sync(full, u < -1.f) || __all_sync(full, v < -1.f) || __all_sync(full, u > p.fcols + 1.f) || __all_sync(full, v > p.frows + 1.f)) return true;
+    float umin = u, umax = u, vmin = v, vmax = v, zmin = pc.z;
+    for (int o = 4; o > 0; o >>= 1) {
+        umin = fminf(umin, __shfl_xor_sync(full, umin, o)); umax = fmaxf(umax, __shfl_xor_sync(full, umax, o));
+        vmin = fminf(vmin, __shfl_xor_sync(full, vmin, o)); vmax = fmaxf(vmax, __shfl_xor_sync(full, vmax, o));
+        zmin = fminf(zmin, __shfl_xor_sync(full, zmin, o));
+    }
+    const int px0 = max(0, (int)floorf(umin - 1.f)), px1 = min(p.cols - 1, (int)floorf(umax + 1.f));
+    const int py0 = max(0, (int)floorf(vmin - 1.f)), py1 = min(p.rows - 1, (int)floorf(vmax + 1.f));
+    if (px1 < px0 || py1 < py0) return true;                      // projects entirely off the image
+    float m;
+    {
+        const float *fine = p.ws + 16;
+        int tx0 = px0 / FUS_TILE, tx1 = px1 / FUS_TILE, ty0 = py0 / FUS_TILE, ty1 = py1 / FUS_TILE, stride = p.tiles_x;
+        const float *tiles = fine;
+        int nx = tx1 - tx0 + 1, nt = nx * (ty1 - ty0 + 1);
+        if (nt > 32) {                                             // too many fine tiles: 64-pixel tiles
+            tiles = fine + p.tiles_x * p.tiles_y; stride = p.ctiles_x;
+            tx0 /= FUS_COARSE; tx1 /= FUS_COARSE; ty0 /= FUS_COARSE; ty1 /= FUS_COARSE;
+            nx = tx1 - tx0 + 1; nt = nx * (ty1 - ty0 + 1);
+        }
+        if (nt > 32) m = __ldg(p.ws + 1);                          // whole image
+        else {
+            m = 0.f;
+            if (lane < nt) m = __ldg(tiles + (ty0 + lane / nx) * stride + tx0 + lane % nx);
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(full, m, o));
+        }
+    }
+    return zmin - 1e-3f > m + p.trunc;                             // rho < -trunc (or no depth at all) for every voxel of the run
+}
+
+// TsdfVolume::weighting (tsdf_volume.cpp:300-306) quantised to the volume's u16 weight
+__device__ __forceinline__ int fusion_sample_weight(const FusionParams &p, const int (&bi)[8], const float (&bd)[8])
+{
+    if (!(p.weight_scale > 0)) return 1;
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) if (bi[k] >= 0) sum += sqrtf(bd[k]);
+    const float w = sum / 8;
+    const float s = rintf(w * p.weight_scale);
+    return s < 1.f ? 1 : (s > (float)p.max_weight ? p.max_weight : (int)s);
+}
+
+__global__ void __launch_bounds__(256) integrate_warped_kernel(const FusionParams p)
+{
+    DF_PDL_ENTRY();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int xw = blockIdx.x * 32 + (warp & 3) * 8, yw = blockIdx.y * 8 + (warp >> 2) * 4;       // the warp's 8 x 4 voxel footprint
+    const int x = xw + (lane & 7), y = yw + (lane >> 3);
+    const bool inb = x < p.Dx && y < p.Dy;
+    const int z0 = blockIdx.z * p.zchunk, z1 = min(p.Dz, z0 + p.zchunk);
+    const float delta = p.cull ? __ldg(p.ws) : __int_as_float(0x7f800000);
+    const bool can_cull = delta < 3.0e38f;
+
+    const NodeGridHeader h = *reinterpret_cast<const NodeGridHeader *>(p.grid);
+    const bool has_bvh = h.pad[2] != 0;
+    const float4 *bvh_box = reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(p.grid) + h.pad[2]);
+    const float4 *bvh_leaf = reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(p.grid) + h.pad[3]);
+
+    int prev[8];
+    bool have_prev = false;
+    unsigned int n_upd = 0, n_warp = 0;
+    const size_t slice = (size_t)p.Dx * p.Dy;
+    for (int za = z0; za < z1; za += FUS_SUB) {
+        const int zb = min(z1, za + FUS_SUB);
+        if (can_cull && fusion_run_invisible(p, lane, delta, xw, min(xw + 7, p.Dx - 1), yw, min(yw + 3, p.Dy - 1), za, zb - 1)) continue;
+        if (!inb) continue;
+        uint32_t *vptr = p.data + x + (size_t)p.Dx * y + slice * za;
+        for (int z = za; z < zb; ++z, vptr += slice) {
+            const float3 xc = aff_mul(p.vol2world, make_float3((float)x * p.vsx, (float)y * p.vsy, (float)z * p.vsz));
+            int bi[8]; float bd[8];
+            if (has_bvh) {
+                float limit = 3.402823466e+38f;
+                if (have_prev) {
+                    limit = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float *v = p.nodes + (size_t)prev[k] * DF_NODE_STRIDE;
+                        const float d0 = xc.x - __ldg(v), d1 = xc.y - __ldg(v + 1), d2 = xc.z - __ldg(v + 2);
+                        limit = fmaxf(limit, d0 * d0 + d1 * d1 + d2 * d2);
+                    }
+                    if (!(limit == limit)) limit = 3.402823466e+38f;
+                }
+                knn8_bvh_bounded(bvh_box, bvh_leaf, h.pad[4], xc.x, xc.y, xc.z, limit, bi, bd);
+            } else {
+                knn8_grid(p.grid, true, xc.x, xc.y, xc.z, bi, bd);
+            }
+            have_prev = bi[7] >= 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) prev[k] = bi[k];
+            ++n_warp;
+
+            const Dqb d = dqb_blend<false>(p.nodes, bi, bd, nullptr);
+            const float3 xwp = dq_transform(d, xc);
+            const float tx = p.world2cam.r0.x * xwp.x + p.world2cam.r0.y * xwp.y + p.world2cam.r0.z * xwp.z + p.world2cam.t.x;
+            const float ty = p.world2cam.r1.x * xwp.x + p.world2cam.r1.y * xwp.y + p.world2cam.r1.z * xwp.z + p.world2cam.t.y;
+            const float tz = p.world2cam.r2.x * xwp.x + p.world2cam.r2.y * xwp.y + p.world2cam.r2.z * xwp.z + p.world2cam.t.z;
+            if (!(tz > 0)) continue;
+            const float u = __fmaf_rn(p.fx, tx / tz, p.cx), v = __fmaf_rn(p.fy, ty / tz, p.cy);
+            if (!(u >= 0 && v >= 0 && u < p.fcols && v < p.frows)) continue;
+            const unsigned short mm = __ldg(row_ptr(p.depth, p.pitch, (int)v) + (int)u);
+            if (mm == 0) continue;
+            const float rho = (float)mm * 0.001f - tz;
+            if (!(rho > -p.trunc)) continue;
+            const float tsdf = fminf(1.f, rho * p.trunc_inv);
+            const int wq = fusion_sample_weight(p, bi, bd);
+            const uint32_t packed = *vptr;
+            const int weight_prev = (int)(packed >> 16);
+            const float tsdf_prev = half_bits_to_float((unsigned short)(packed & 0xffffu));
+            const float tsdf_new = __fmaf_rn(tsdf_prev, (float)weight_prev, tsdf * (float)wq) / (float)(weight_prev + wq);
+            const int weight_new = min(weight_prev + wq, p.max_weight);
+            const uint32_t val = (uint32_t)float_to_half_bits(tsdf_new) | ((uint32_t)weight_new << 16);
+            *vptr = val;
+            if (p.activity && vox_active(val)) p.activity[(size_t)(vptr - p.data) / DF_ACTIVITY_VOXELS] = 1;
+            ++n_upd;
+        }
+    }
+    if (p.counters) {
+        __syncwarp();
+        for (int o = 16; o > 0; o >>= 1) { n_upd += __shfl_xor_sync(0xffffffffu, n_upd, o); n_warp += __shfl_xor_sync(0xffffffffu, n_warp, o); }
+        if (lane == 0) {
+            if (n_upd) atomicAdd(p.counters, (unsigned long long)n_upd);
+            if (n_warp) atomicAdd(p.counters + 1, (unsigned long long)n_warp);
+        }
+    }
+}
+
+// |R^T R - I|_max: how far a pose's linear part is from a rotation
+double orthonormal_defect(const df_aff3f &a)
+{
+    double worst = 0.0;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < 3; ++k) s += (double)a.R[3 * k + i] * (double)a.R[3 * k + j];
+            worst = fmax(worst, fabs(s - (i == j ? 1.0 : 0.0)));
+        }
+    return worst;
+}
+
+}  // namespace
+
+extern "C" size_t df_integrate_warped_workspace_bytes(int cols, int rows)
+{
+    const int tx = div_up(cols, FUS_TILE), ty = div_up(rows, FUS_TILE);
+    return (size_t)(16 + tx * ty + div_up(tx, FUS_COARSE) * div_up(ty, FUS_COARSE)) * sizeof(float) + 64;
+}
+
+extern "C" int df_integrate_warped_launch_count(void) { return 3; }
+
+extern "C" int df_integrate_warped(df_volume vol, const uint16_t *depth, size_t depth_pitch, int cols, int rows, df_aff3f vol2world,
+                                   df_aff3f world2cam, df_intr intr, const float *nodes, int M, const void *node_grid, float weight_scale,
+                                   unsigned long long *counters, unsigned char *activity, void *workspace, void *stream)
+{
+    if (!node_grid || !nodes || M <= 0 || !vol.data || !depth) return (int)cudaErrorInvalidValue;
+    cudaStream_t s = (cudaStream_t)stream;
+    FusionParams p;
+    p.data = vol.data;
+    p.Dx = vol.dims[0]; p.Dy = vol.dims[1]; p.Dz = vol.dims[2];
+    p.vsx = vol.voxel_size[0]; p.vsy = vol.voxel_size[1]; p.vsz = vol.voxel_size[2];
+    p.trunc = vol.trunc_dist; p.trunc_inv = 1.f / vol.trunc_dist;
+    p.max_weight = vol.max_weight;
+    p.depth = depth; p.pitch = depth_pitch; p.cols = cols; p.rows = rows; p.fcols = (float)cols; p.frows = (float)rows;
+    p.vol2world = make_aff(vol2world); p.world2cam = make_aff(world2cam);
+    df_aff3f v2c;                                   // composed in double: only the (conservative) visibility test uses it
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) {
+            double a = 0.0;
+            for (int k = 0; k < 3; ++k) a += (double)world2cam.R[3 * i + k] * (double)vol2world.R[3 * k + j];
+            v2c.R[3 * i + j] = (float)a;
+        }
+        double t = world2cam.t[i];
+        for (int k = 0; k < 3; ++k) t += (double)world2cam.R[3 * i + k] * (double)vol2world.t[k];
+        v2c.t[i] = (float)t;
+    }
+    p.vol2cam = make_aff(v2c);
+    p.cull = orthonormal_defect(vol2world) < 1e-3 && orthonormal_defect(world2cam) < 1e-3;
+    {
+        const char *e = getenv("DF_FUSION_CULL");
+        if (e && atoi(e) == 0) p.cull = 0;
+    }
+    p.fx = intr.fx; p.fy = intr.fy; p.cx = intr.cx; p.cy = intr.cy;
+    p.nodes = nodes; p.M = M; p.grid = node_grid;
+    p.weight_scale = weight_scale;
+    p.counters = counters; p.activity = activity;
+    p.tiles_x = div_up(cols, FUS_TILE); p.tiles_y = div_up(rows, FUS_TILE);
+    p.ctiles_x = div_up(p.tiles_x, FUS_COARSE); p.ctiles_y = div_up(p.tiles_y, FUS_COARSE);
+    p.zchunk = vol.dims[2] >= 64 ? 32 : vol.dims[2];
+    {
+        const char *e = getenv("DF_FUSION_ZCHUNK");
+        if (e && atoi(e) > 0) p.zchunk = atoi(e);
+    }
+    float *ws = (float *)workspace;
+    const bool own = ws == nullptr;
+    if (own) {
+        const cudaError_t e = cudaMallocAsync((void **)&ws, df_integrate_warped_workspace_bytes(cols, rows), s);
+        if (e != cudaSuccess) return (int)e;
+    }
+    p.ws = ws;
+    launch_pdl(depth_tile_max_kernel, dim3(p.tiles_x, p.tiles_y), dim3(256), 0, s, depth, depth_pitch, cols, rows, ws + 16, p.tiles_x);
+    launch_pdl(fusion_prepare_kernel, dim3(2), dim3(256), 0, s, ws, p.tiles_x, p.tiles_y, p.ctiles_x, p.ctiles_y, nodes, M);
+    dim3 grid(div_up(vol.dims[0], 32), div_up(vol.dims[1], 8), div_up(vol.dims[2], p.zchunk));
+    launch_pdl(integrate_warped_kernel, grid, dim3(256), 0, s, p);
+    if (own) cudaFreeAsync(ws, s);
+    DF_LAUNCH_CHECK();
+    return 0;
+}

@@ -37,6 +37,7 @@ struct KinFu {
     void *solve_ws = nullptr; size_t solve_ws_bytes = 0; double *solve_stats = nullptr;
     void *extract_ws = nullptr; void *project_ws = nullptr;
     void *integrate_ws = nullptr;
+    void *fusion_ws = nullptr;             // df_integrate_warped workspace (DF_KINFU_WARPED_INTEGRATE)
     unsigned char *activity = nullptr; size_t activity_bytes = 0;   // dfusion.h DF_ACTIVITY_VOXELS: which stretches of the volume hold surface
     float *pinned = nullptr;             // 16 floats: T(12) + ok
     std::vector<float> poses;            // 12 floats per pose
@@ -278,6 +279,19 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_d
         }
         ++k.launches;
         mark(k, 6);
+        if (p.flags & DF_KINFU_WARPED_INTEGRATE) {
+            // the update surface_fusion was written towards (tsdf_volume.cpp:240-252) -- every voxel is carried through
+            // the field solved above and fused against the (bilateral-filtered) frame; no pixel is removed, no rigid integrate.
+            mark(k, 7);
+            unsigned long long *counter = (p.flags & DF_KINFU_STAGE_TIMING) ? k.n_upd : nullptr;
+            if (counter) cudaMemsetAsync(counter, 0, 16, s);
+            CKD(df_integrate_warped(vol, (const uint16_t *)k.cur_depth[0].ptr, k.cur_depth[0].pitch, p.cols, p.rows, p.volume_pose, to_aff(inv_pose),
+                                    p.intr, k.nodes, k.M, k.node_grid, p.fusion_weight_scale, counter, k.activity, k.fusion_ws, s));
+            k.launches += df_integrate_warped_launch_count();
+            mark(k, 8);
+            CKD(extract());
+            mark(k, 9);
+        } else {
         // surface_fusion (tsdf_volume.cpp:228-255): psdf projects the warped vertices into the (bilateral-filtered) depth,
         // zeroes the pixels they explain, then the ordinary rigid integrate runs on what is left.
         CKD(df_project_and_remove((uint16_t *)k.cur_depth[0].ptr, k.cur_depth[0].pitch, p.cols, p.rows, p.intr,
@@ -291,6 +305,7 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_d
         mark(k, 8);
         CKD(extract());                                                // compute_points / compute_normals, :398-399
         mark(k, 9);
+        }
     } else {
         // plain KinFu (Nerei) loop: integrate the frame rigidly
         mark(k, 3); mark(k, 4); mark(k, 5); mark(k, 6); mark(k, 7);
@@ -353,6 +368,12 @@ extern "C" void *df_kinfu_create(const df_kinfu_params *pp)
     }
     KinFu *k = new KinFu();
     k->p = *pp;
+    {
+        const char *e = getenv("DF_KINFU_WARPED_INTEGRATE");
+        if (e && atoi(e) != 0) k->p.flags |= DF_KINFU_WARPED_INTEGRATE;
+        const char *w = getenv("DF_FUSION_WEIGHT_SCALE");
+        if (w) k->p.fusion_weight_scale = (float)atof(w);
+    }
     const df_kinfu_params &p = k->p;
     int i = MAX_LEVELS - 1;                                           // getUsedLevelsNum, projective_icp.cpp:110-115
     for (; i >= 0 && !p.icp_iter_num[i]; --i) {}
@@ -383,6 +404,7 @@ extern "C" void *df_kinfu_create(const df_kinfu_params *pp)
     df_volume v = vol_of(*k);
     ok = ok && cudaMalloc(&k->extract_ws, df_extract_workspace_bytes(v)) == cudaSuccess;
     ok = ok && cudaMalloc(&k->integrate_ws, df_integrate_workspace_bytes(p.cols, p.rows)) == cudaSuccess;
+    ok = ok && cudaMalloc(&k->fusion_ws, df_integrate_warped_workspace_bytes(p.cols, p.rows)) == cudaSuccess;
     k->activity_bytes = df_volume_activity_bytes(v);
     ok = ok && cudaMalloc(&k->activity, k->activity_bytes) == cudaSuccess && cudaMemset(k->activity, 0, k->activity_bytes) == cudaSuccess;
     ok = ok && cudaMalloc(&k->project_ws, df_project_workspace_bytes(p.cols, p.rows)) == cudaSuccess;
@@ -410,7 +432,7 @@ extern "C" void df_kinfu_destroy(void *h)
     cudaFree(k->canon.ptr); cudaFree(k->canon_nrm.ptr); cudaFree(k->canon_visible.ptr);
     cudaFree(k->cloud); cudaFree(k->cloud_nrm); cudaFree(k->cloud_count); cudaFree(k->nodes); cudaFree(k->node_grid);
     cudaFree(k->icp_T); cudaFree(k->icp_ok); cudaFree(k->icp_scratch); cudaFree(k->solve_ws); cudaFree(k->solve_stats);
-    cudaFree(k->extract_ws); cudaFree(k->project_ws); cudaFree(k->activity); cudaFree(k->integrate_ws); cudaFreeHost(k->pinned); cudaFree(k->n_upd);
+    cudaFree(k->extract_ws); cudaFree(k->project_ws); cudaFree(k->activity); cudaFree(k->integrate_ws); cudaFree(k->fusion_ws); cudaFreeHost(k->pinned); cudaFree(k->n_upd);
     for (int e = 0; e <= NSTAGES; ++e) cudaEventDestroy(k->ev[e]);
     delete k;
 }
@@ -490,12 +512,13 @@ extern "C" int df_kinfu_get_info(void *h, long long *info, int n)
     double st[8] = {0};
     cudaMemcpyAsync(st, k->solve_stats, sizeof st, cudaMemcpyDeviceToHost, k->stream);
     cudaStreamSynchronize(k->stream);
-    unsigned long long nu = 0;
-    cudaMemcpyAsync(&nu, k->n_upd, 8, cudaMemcpyDeviceToHost, k->stream);
+    unsigned long long nu2[2] = {0, 0};
+    cudaMemcpyAsync(nu2, k->n_upd, 16, cudaMemcpyDeviceToHost, k->stream);
     cudaStreamSynchronize(k->stream);
-    const long long vals[10] = {k->frame_counter, k->M, k->last_cloud, (long long)(k->poses.size() / 12), k->last_ok, k->launches, k->resets,
-                                (long long)st[2], (long long)nu, (long long)st[4]};
-    for (int i = 0; i < n && i < 10; ++i) info[i] = vals[i];
+    const unsigned long long nu = nu2[0];
+    const long long vals[11] = {k->frame_counter, k->M, k->last_cloud, (long long)(k->poses.size() / 12), k->last_ok, k->launches, k->resets,
+                                (long long)st[2], (long long)nu, (long long)st[4], (long long)nu2[1]};
+    for (int i = 0; i < n && i < 11; ++i) info[i] = vals[i];
     return 0;
 }
 

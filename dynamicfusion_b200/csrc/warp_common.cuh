@@ -137,6 +137,49 @@ __device__ __forceinline__ void knn8_bvh(const float4 *__restrict__ box, const f
     }
 }
 
+// knn8_bvh with a caller-supplied upper bound on the 8th-nearest distance (e.g. the largest distance from the query to ANY eight
+// distinct nodes, such as the neighbours of an adjacent query): the set starts empty, candidates farther than `limit` are dropped
+// before the insertion and subtrees farther than min(limit, current 8th best) are not entered.  The true eight nearest all lie
+// within `limit` (distances are formed by the same float operations everywhere, so a node that defined the bound is found again
+// with exactly that distance) and ranking is by (distance, index): the result equals knn8_bvh's / the exhaustive scan's.
+__device__ __forceinline__ void knn8_bvh_bounded(const float4 *__restrict__ box, const float4 *__restrict__ leaf, int L, float qx, float qy, float qz,
+                                                 float limit, int (&bi)[8], float (&bd)[8])
+{
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { bi[i] = 0x7fffffff; bd[i] = 3.402823466e+38f; }
+    int stack_i[24];
+    float stack_d[24];
+    int sp = 0;
+    stack_i[sp] = 0; stack_d[sp] = 0.f; ++sp;
+    while (sp > 0) {
+        --sp;
+        const int i = stack_i[sp];
+        const float cut = fminf(bd[7], limit);
+        if (stack_d[sp] > cut) continue;
+        if (i >= L - 1) {
+            const float4 *e = leaf + (size_t)(i - (L - 1)) * NODEGRID_BVH_LEAF;
+#pragma unroll
+            for (int k = 0; k < NODEGRID_BVH_LEAF; ++k) {
+                const float4 nd = __ldg(e + k);
+                const float d0 = qx - nd.x, d1 = qy - nd.y, d2 = qz - nd.z;
+                const float dist = d0 * d0 + d1 * d1 + d2 * d2;
+                if (dist <= limit) knn8_insert_lex(bi, bd, dist, __float_as_int(nd.w));       // padding has distance inf
+            }
+        } else {
+            const int a = 2 * i + 1, b = a + 1;
+            const float da = bvh_box_dist2(__ldg(box + 2 * a), __ldg(box + 2 * a + 1), qx, qy, qz);
+            const float db = bvh_box_dist2(__ldg(box + 2 * b), __ldg(box + 2 * b + 1), qx, qy, qz);
+            const bool a_first = da <= db;
+            const int far_i = a_first ? b : a, near_i = a_first ? a : b;
+            const float far_d = a_first ? db : da, near_d = a_first ? da : db;
+            if (far_d <= cut) { stack_i[sp] = far_i; stack_d[sp] = far_d; ++sp; }
+            if (near_d <= cut) { stack_i[sp] = near_i; stack_d[sp] = near_d; ++sp; }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) if (bi[i] == 0x7fffffff) bi[i] = -1;
+}
+
 __device__ __forceinline__ void knn8_grid(const void *__restrict__ grid, bool valid, float qx, float qy, float qz, int (&bi)[8], float (&bd)[8])
 {
 #pragma unroll

@@ -186,6 +186,22 @@ class TsdfVolume:
                                                self.activity_.data_ptr() if self.activity_ is not None else None, None, _stream()))
         return vol2cam
 
+    def integrate_warped(self, depth: torch.Tensor, camera_pose, intr, warp_field, weight_scale: float = 0.0,
+                         counters: torch.Tensor | None = None):
+        """Per-voxel warped integration (dfusion.h df_integrate_warped; SURVEY 8f(1)): what TsdfVolume::surface_fusion
+        (tsdf_volume.cpp:228-254) was written towards.  depth = the u16 millimetre frame; the field's warp_to_live is applied
+        before the camera transform, as WarpField::warp does."""
+        world2cam = aff_mul(aff_inv(camera_pose), warp_field.warp_to_live_)
+        rows, cols = depth.shape
+        if warp_field.grid_ is None:
+            raise RuntimeError("integrate_warped needs the node grid (WarpField(use_grid=True) + buildKDTree)")
+        capi.check(_lib().df_integrate_warped(self._vol(), depth.data_ptr(), cols * 2, cols, rows, capi.make_aff(*self.pose_),
+                                              capi.make_aff(*world2cam), capi.make_intr(*intr), warp_field.nodes_.data_ptr(),
+                                              warp_field.nodes_.shape[0], warp_field.grid_.data_ptr(), float(weight_scale),
+                                              counters.data_ptr() if counters is not None else None,
+                                              self.activity_.data_ptr() if self.activity_ is not None else None, None, _stream()))
+        return world2cam
+
     def raycast(self, camera_pose, intr, cols: int, rows: int):
         cam2vol = aff_mul(aff_inv(self.pose_), camera_pose)                           # tsdf_volume.cpp:162
         Rinv = np.linalg.inv(cam2vol[0].astype(np.float64)).astype(np.float32)

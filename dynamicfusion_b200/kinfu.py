@@ -17,6 +17,7 @@ STAGES = ["preprocess", "icp", "raycast_canonical", "warp1", "solve", "warp2", "
 RIGID_ONLY = 1
 STAGE_TIMING = 2
 REF_GRAPH_QUIRK = 4
+WARPED_INTEGRATE = 8      # DF_KINFU_WARPED_INTEGRATE: per-voxel warped fusion instead of the rigid fallback
 
 
 class KinFuParams:
@@ -91,9 +92,10 @@ class KinFu:
         return a[:9].reshape(3, 3), a[9:]
 
     def info(self) -> dict:
-        v = (C.c_longlong * 10)()
-        self.lib.df_kinfu_get_info(self.h, v, 10)
-        keys = ["frame_counter", "nodes", "cloud_points", "poses", "icp_ok", "launches", "resets", "lm_iters", "n_updated", "pcg_iters"]
+        v = (C.c_longlong * 11)()
+        self.lib.df_kinfu_get_info(self.h, v, 11)
+        keys = ["frame_counter", "nodes", "cloud_points", "poses", "icp_ok", "launches", "resets", "lm_iters", "n_updated", "pcg_iters",
+                "n_warped"]
         return dict(zip(keys, [int(x) for x in v]))
 
     def stage_ms(self) -> dict:

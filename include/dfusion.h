@@ -198,6 +198,21 @@ int df_build_node_grid(const float *nodes, int M, void *node_grid, void *stream)
 int df_warp(const float *nodes, int M, const void *node_grid, float *points, float *normals, int N, int stride, df_aff3f warp_to_live,
             int flags, int32_t *idx_out, float *w_out, void *stream);
 
+/* Per-voxel warped integration: the update TsdfVolume::surface_fusion (tsdf_volume.hpp:76-79,
+ * tsdf_volume.cpp:228-254) was written towards and left commented out (:248-251) -- DynamicFusion eq. 4-5.  For every voxel:
+ *   x_c = vol2world * (x*vs, y*vs, z*vs);  x_t = world2cam * DQB(8-NN of x_c).transform(x_c)   (WarpField::warp, warp_field.cpp:180-251)
+ *   rho = depth_mm(floor v, floor u) * 0.001 - x_t.z                                            (TsdfVolume::psdf, tsdf_volume.cpp:266-292)
+ *   if rho > -trunc:  tsdf = min(1, rho/trunc);  w = clamp(rint(weight_scale * mean node distance), 1, max_weight)  (TsdfVolume::weighting,
+ *   :300-306; weight_scale <= 0 -> w = 1);  F' = (F*W + tsdf*w)/(W + w);  W' = min(W + w, max_weight).
+ * depth: the frame's u16 millimetre image (not the ray lengths df_integrate takes); nodes / node_grid: the warp field (node_grid is
+ * required).  counters (optional, device, 2 x u64): [0] += voxels written, [1] += voxels warped (k-NN + blend evaluated).
+ * activity: as df_integrate_tracked.  workspace (optional, device): df_integrate_warped_workspace_bytes(cols, rows) bytes. */
+size_t df_integrate_warped_workspace_bytes(int cols, int rows);
+int df_integrate_warped_launch_count(void);
+int df_integrate_warped(df_volume vol, const uint16_t *depth, size_t depth_pitch, int cols, int rows, df_aff3f vol2world,
+                        df_aff3f world2cam, df_intr intr, const float *nodes, int M, const void *node_grid, float weight_scale,
+                        unsigned long long *counters, unsigned char *activity, void *workspace, void *stream);
+
 /* WarpFieldOptimiser::optimiseWarpData (warp_field_optimiser.hpp:14-17) -> CombinedSolver (CombinedSolver.h:25-110)
  * -> Opt LM/PCG on kfusion/solvers/dynamicfusion.t: translation-only data term solved on the device; node
  * translations are updated in place (encodeTranslation, CombinedSolver.h:189-197).
@@ -235,11 +250,16 @@ typedef struct df_kinfu_params {
     int node_step;        /* every node_step-th extracted point becomes a node: 50 (warp_field.cpp:49) */
     int cloud_capacity;   /* extracted-cloud buffer, points: 256^3 in the reference (tsdf_volume.cpp:184) */
     int flags;            /* DF_KINFU_* */
+    float fusion_weight_scale;   /* DF_KINFU_WARPED_INTEGRATE: weight_scale of df_integrate_warped (0 = every sample weighs 1) */
 } df_kinfu_params;
 
 #define DF_KINFU_RIGID_ONLY 1      /* skip warp + solve (plain KinFu loop: config 1) */
 #define DF_KINFU_STAGE_TIMING 2    /* record CUDA events per stage (df_kinfu_get_stage_ms) */
 #define DF_KINFU_REF_GRAPH_QUIRK 4 /* forward DF_SOLVE_REF_GRAPH_QUIRK to the solve */
+#define DF_KINFU_WARPED_INTEGRATE 8 /* the fusion step of KinFu::dynamicfusion integrates the frame through the warp field, voxel by
+                                      voxel (df_integrate_warped), instead of project_and_remove + the rigid integrate the reference falls back to
+                                      (tsdf_volume.cpp:234-238).  Also switched on by the environment variable DF_KINFU_WARPED_INTEGRATE=1, so that an
+                                      unchanged apps/demo.cpp can run it; DF_FUSION_WEIGHT_SCALE sets fusion_weight_scale the same way. */
 
 /* which = 0: KinFuParams::default_params_dynamicfusion (kinfu.cpp:14-49); 1: default_params (kinfu.cpp:55-89) */
 void df_kinfu_default_params(df_kinfu_params *p, int which);
@@ -261,7 +281,8 @@ int df_kinfu_dynamicfusion(void *kinfu, uint16_t *depth_dev, size_t depth_pitch,
 int df_kinfu_get_pose(void *kinfu, int time, float *pose12_host);
 /* info[0] frame counter, [1] warp nodes M, [2] extracted cloud points, [3] poses stored, [4] last ICP ok,
  * [5] kernels launched in the last frame, [6] resets so far, [7] solver LM iterations (last frame),
- * [8] voxels written by the last integrate (DF_KINFU_STAGE_TIMING only), [9] solver PCG iterations (last frame) */
+ * [8] voxels written by the last integrate (DF_KINFU_STAGE_TIMING only), [9] solver PCG iterations (last frame),
+ * [10] voxels carried through the warp field by the last df_integrate_warped (DF_KINFU_WARPED_INTEGRATE + STAGE_TIMING) */
 int df_kinfu_get_info(void *kinfu, long long *info_host, int n);
 /* device buffers of the current state: 0 volume(u32), 1 dists, 2 curr depth L0, 3 curr points L0, 4 curr normals L0,
  * 5 prev points L0, 6 prev normals L0, 7 canonical (after 2nd warp), 8 canonical normals, 9 extracted cloud,

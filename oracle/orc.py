@@ -42,6 +42,7 @@ def load() -> C.CDLL:
         _lib = C.CDLL(str(LIB))
         _lib.orc_integrate.restype = C.c_longlong
         _lib.orc_extract_cloud.restype = C.c_longlong
+        _lib.orc_integrate_warped.restype = C.c_longlong
         _lib.orc_icp_accumulate.restype = C.c_longlong
         _lib.orc_icp_accumulate_depth.restype = C.c_longlong
         _lib.orc_float2half_rn.restype = C.c_uint16
@@ -164,6 +165,14 @@ def integrate(vol_data, dims, vs, trunc, mw, dists, vol2cam, K) -> int:
     rows, cols = dists.shape
     return int(_fn("integrate")(volume(vol_data, dims, vs, trunc, mw), _p(dists), C.c_size_t(cols * 2), cols, rows,
                                     aff(*vol2cam), intr(*K)))
+
+
+def integrate_warped(vol_data, dims, vs, trunc, mw, depth, vol2world, world2cam, K, nodes, weight_scale) -> int:
+    """per-voxel warped integration (orc_fusion.c); depth = u16 millimetres"""
+    rows, cols = depth.shape
+    nodes = np.ascontiguousarray(nodes, np.float32)
+    return int(load().orc_integrate_warped(volume(vol_data, dims, vs, trunc, mw), _p(depth), C.c_size_t(cols * 2), cols, rows,
+                                           aff(*vol2world), aff(*world2cam), intr(*K), _p(nodes), len(nodes), C.c_float(weight_scale)))
 
 
 def raycast_points(vol_data, dims, vs, trunc, mw, cam2vol, Rinv, K, cols, rows, step_factor, delta_factor):

@@ -142,6 +142,10 @@ void orc_quat_encode_rotation(float theta, float x, float y, float z, float *q);
 void orc_quat_rotate_sandwich(const float *q, float *v3);
 void orc_node_encode_translation(float *node, float x, float y, float z);
 
+/* per-voxel warped integration (orc_fusion.c) */
+long long orc_integrate_warped(orc_volume vol, const uint16_t *depth, size_t pitch, int cols, int rows, orc_aff3f vol2world,
+                               orc_aff3f world2cam, orc_intr intr, const float *nodes, int M, float weight_scale);
+
 /* data-term solve */
 int orc_solve_data_term(float *nodes, int M, const float *canon, const float *live, long long N, int stride, int flags, int max_lm, double *stats);
 

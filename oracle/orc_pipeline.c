@@ -29,6 +29,7 @@ typedef struct {
     float light_pose[3];
     int solver_nonlinear_iters, solver_linear_iters;
     int max_nodes, node_step, cloud_capacity, flags;
+    float fusion_weight_scale;
 } orc_kinfu_params;     /* identical layout to df_kinfu_params (include/dfusion.h) */
 
 typedef struct {
@@ -257,11 +258,19 @@ int orc_kinfu_process(orc_kinfu *k, const uint16_t *depth, size_t pitch)
         double t5 = now_s(); k->stage_s[4] = t5 - t4;
         warp_all(k, k->canon, k->canon_nrm, npix);
         double t6 = now_s(); k->stage_s[5] = t6 - t5;
+        double t7, t8;
+        if (p->flags & 8) {          /* DF_KINFU_WARPED_INTEGRATE: per-voxel warped fusion (orc_fusion.c), no pixel removal, no rigid integrate */
+            t7 = now_s(); k->stage_s[6] = t7 - t6;
+            orc_integrate_warped(vol_of(k), k->cur_depth[0], p2, p->cols, p->rows, p->volume_pose, to_aff(inv_pose), p->intr, k->nodes, k->M,
+                                 p->fusion_weight_scale);
+            t8 = now_s(); k->stage_s[7] = t8 - t7;
+        } else {
         orc_project_and_remove(k->cur_depth[0], p2, p->cols, p->rows, p->intr, k->canon, (size_t)p->cols * 16, p->cols, p->rows);
-        double t7 = now_s(); k->stage_s[6] = t7 - t6;
+        t7 = now_s(); k->stage_s[6] = t7 - t6;
         orc_compute_dists(k->cur_depth[0], p2, p->cols, p->rows, p->intr, k->dists, p2);
         integrate_with(k, k->dists, cam_pose);
-        double t8 = now_s(); k->stage_s[7] = t8 - t7;
+        t8 = now_s(); k->stage_s[7] = t8 - t7;
+        }
         extract(k);
         double t9 = now_s(); k->stage_s[8] = t9 - t8;
         t2 = t9;
