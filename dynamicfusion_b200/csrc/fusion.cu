@@ -214,8 +214,9 @@ __global__ void __launch_bounds__(256) integrate_warped_kernel(const FusionParam
             const float3 xc = aff_mul(p.vol2world, make_float3((float)x * p.vsx, (float)y * p.vsy, (float)z * p.vsz));
             int bi[8]; float bd[8];
             if (has_bvh) {
-                float limit = 3.402823466e+38f;
-                if (have_prev) {
+                float limit;
+                if (!have_prev) limit = knn8_bvh_greedy_bound(bvh_box, bvh_leaf, h.pad[4], xc.x, xc.y, xc.z);
+                else {
                     limit = 0.f;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {

@@ -460,6 +460,16 @@ void TsdfVolume::surface_fusion(const WarpField&, std::vector<Vec3f> warped, std
     integrate(dists, camera_pose, intr);
 }
 
+void TsdfVolume::integrate(const Depth& depth, const WarpField& warp_field, const Affine3f& camera_pose, const Intr& intr, float weight_scale)
+{
+    warp_field.uploadNodes();
+    const Affine3f world2cam = camera_pose.inv() * warp_field.getWarpToLive();       // WarpField::warp applies warp_to_live_ last (warp_field.cpp:191)
+    dfSafeCall(df_integrate_warped(vol_of(data_, dims_, getVoxelSize(), trunc_dist_, max_weight_), depth.ptr(), depth.step(), depth.cols(), depth.rows(),
+                                   to_df(pose_), to_df(world2cam), to_df(intr), warp_field.deviceNodes(), warp_field.deviceNodeCount(), warp_field.deviceGrid(),
+                                   weight_scale, 0, 0, 0, 0));
+    cudaSafeCall(cudaDeviceSynchronize());                                           // as device::integrate does (tsdf_volume.cu:160)
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // WarpField: warp_field.cpp
 struct WarpField::Impl

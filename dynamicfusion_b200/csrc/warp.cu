@@ -110,6 +110,90 @@ __global__ void __launch_bounds__(256) warp_kernel(const WarpParams p)
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// DF_WARP_REF_NORMAL_INDEX: the reference's normal cursor (warp_field.cpp:182-194).  `i` advances only after a point has been
+// warped, and a point is skipped when ITS x is NaN or when normals[i] is NaN -- so the j-th non-NaN point is paired with normal j, and
+// once the cursor reaches the first NaN normal (index c) it never moves again: points of rank >= c are left untouched.  In parallel:
+// c = the smallest index of a NaN normal (one atomicMin), rank = exclusive count of non-NaN points (block counts -> one-block scan ->
+// ballot ranks inside the warp kernel).  Every rank is unique, so no two threads touch the same normal.
+__global__ void __launch_bounds__(256) warp_cursor_count_kernel(const float *__restrict__ points, const float *__restrict__ normals, int N, int stride,
+                                                                int *block_count, int *first_nan_normal)
+{
+    DF_PDL_ENTRY();
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = q < N && !isnan(points[(size_t)q * stride]);
+    const int n = __syncthreads_count(valid);
+    if (threadIdx.x == 0) block_count[blockIdx.x] = n;
+    if (q < N && isnan(normals[(size_t)q * stride])) atomicMin(first_nan_normal, q);
+}
+
+__global__ void __launch_bounds__(1024) warp_cursor_scan_kernel(int *block_count, int nblocks)
+{
+    DF_PDL_ENTRY();
+    __shared__ int sm[1024];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nblocks; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < nblocks ? block_count[i] : 0;
+        sm[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            const int t = threadIdx.x >= o ? sm[threadIdx.x - o] : 0;
+            __syncthreads();
+            sm[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (i < nblocks) block_count[i] = carry + sm[threadIdx.x] - v;        // exclusive
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += sm[1023];
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) warp_cursor_kernel(const WarpParams p, const int *__restrict__ block_offset, const int *__restrict__ first_nan_normal)
+{
+    DF_PDL_ENTRY();
+    __shared__ KnnSmem sm;
+    __shared__ int warp_count[8];
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    float3 pt = make_float3(0.f, 0.f, 0.f);
+    bool valid = false;
+    if (q < p.N) {
+        const float *pp = p.points + (size_t)q * p.stride;
+        pt = make_float3(pp[0], pp[1], pp[2]);
+        valid = !isnan(pt.x);
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, valid);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) warp_count[w] = __popc(ballot);
+    __syncthreads();
+    int rank = block_offset[blockIdx.x] + __popc(ballot & ((1u << lane) - 1u));
+    for (int i = 0; i < w; ++i) rank += warp_count[i];
+    valid = valid && rank < *first_nan_normal;
+    int bi[8]; float bd[8];
+    if (p.grid) knn8_grid(p.grid, valid, pt.x, pt.y, pt.z, bi, bd);
+    else knn8_scan(p.nodes, p.M, valid, pt.x, pt.y, pt.z, sm, bi, bd);
+    if (!valid) return;
+    float *np = p.normals + (size_t)rank * p.stride;
+    const float3 nr = make_float3(np[0], np[1], np[2]);
+    const Dqb d = dqb_blend<false>(p.nodes, bi, bd, nullptr);
+    const float3 wp = aff_apply_cv(p.w2l, dq_transform(d, pt));
+    float3 wn;
+    if (p.flags & DF_WARP_NORMAL_ROTATE_ONLY) {
+        const float3 r = qrotate(d.rot, nr);
+        wn = make_float3(p.w2l.r0.x * r.x + p.w2l.r0.y * r.y + p.w2l.r0.z * r.z,
+                         p.w2l.r1.x * r.x + p.w2l.r1.y * r.y + p.w2l.r1.z * r.z,
+                         p.w2l.r2.x * r.x + p.w2l.r2.y * r.y + p.w2l.r2.z * r.z);
+    } else {
+        wn = aff_apply_cv(p.w2l, dq_transform(d, nr));
+    }
+    float *pp = p.points + (size_t)q * p.stride;
+    pp[0] = wp.x; pp[1] = wp.y; pp[2] = wp.z;
+    np[0] = wn.x; np[1] = wn.y; np[2] = wn.z;
+}
+
 }  // namespace
 
 extern "C" int df_knn8(const float *nodes, int M, const void *node_grid, const float *queries, int N, int qstride, int32_t *idx, float *d2,
@@ -125,7 +209,26 @@ extern "C" int df_warp(const float *nodes, int M, const void *node_grid, float *
                        df_aff3f warp_to_live, int flags, int32_t *idx, float *w, void *stream)
 {
     if (N <= 0) return 0;
-    if (flags & DF_WARP_REF_NORMAL_INDEX) return (int)cudaErrorNotSupported;   // reference normal-cursor quirk: not built yet
+    if (flags & DF_WARP_REF_NORMAL_INDEX) {
+        // the reference's normal cursor (warp_field.cpp:182-194); neighbour output / re-use is not offered on this path
+        if ((flags & DF_WARP_REUSE_KNN) || idx || w) return (int)cudaErrorNotSupported;
+        cudaStream_t s = (cudaStream_t)stream;
+        const int nblocks = div_up(N, 256);
+        int *scratch = nullptr;
+        cudaError_t e = cudaMallocAsync((void **)&scratch, (size_t)(nblocks + 1) * sizeof(int), s);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaMemcpyAsync(scratch + nblocks, &N, sizeof(int), cudaMemcpyHostToDevice, s);      // first NaN normal: N = none (pageable source: copied before return)
+        if (e != cudaSuccess) { cudaFreeAsync(scratch, s); return (int)e; }
+        WarpParams p;
+        p.nodes = nodes; p.M = M; p.grid = node_grid; p.points = points; p.normals = normals; p.N = N; p.stride = stride;
+        p.w2l = make_aff(warp_to_live); p.flags = flags; p.idx = nullptr; p.w = nullptr;
+        launch_pdl(warp_cursor_count_kernel, dim3(nblocks), dim3(256), 0, s, (const float *)points, (const float *)normals, N, stride, scratch, scratch + nblocks);
+        launch_pdl(warp_cursor_scan_kernel, dim3(1), dim3(1024), 0, s, scratch, nblocks);
+        launch_pdl(warp_cursor_kernel, dim3(nblocks), dim3(256), 0, s, p, (const int *)scratch, (const int *)(scratch + nblocks));
+        cudaFreeAsync(scratch, s);
+        DF_LAUNCH_CHECK();
+        return 0;
+    }
     if ((flags & DF_WARP_REUSE_KNN) && (!idx || !w)) return (int)cudaErrorInvalidValue;
     WarpParams p;
     p.nodes = nodes; p.M = M; p.grid = node_grid; p.points = points; p.normals = normals; p.N = N; p.stride = stride;

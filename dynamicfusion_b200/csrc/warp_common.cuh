@@ -180,6 +180,29 @@ __device__ __forceinline__ void knn8_bvh_bounded(const float4 *__restrict__ box,
     for (int i = 0; i < 8; ++i) if (bi[i] == 0x7fffffff) bi[i] = -1;
 }
 
+// A cheap upper bound on the 8th-nearest distance for knn8_bvh_bounded when no neighbouring result is at hand: descend to the leaf
+// whose boxes are nearest at every level (no backtracking) and take the largest distance to its eight nodes.  Any eight distinct
+// nodes bound the 8th-nearest distance; a padded leaf (fewer than eight nodes) yields FLT_MAX, i.e. an unbounded search.
+__device__ __forceinline__ float knn8_bvh_greedy_bound(const float4 *__restrict__ box, const float4 *__restrict__ leaf, int L, float qx, float qy, float qz)
+{
+    int i = 0;
+    while (i < L - 1) {
+        const int a = 2 * i + 1, b = a + 1;
+        const float da = bvh_box_dist2(__ldg(box + 2 * a), __ldg(box + 2 * a + 1), qx, qy, qz);
+        const float db = bvh_box_dist2(__ldg(box + 2 * b), __ldg(box + 2 * b + 1), qx, qy, qz);
+        i = da <= db ? a : b;
+    }
+    const float4 *e = leaf + (size_t)(i - (L - 1)) * NODEGRID_BVH_LEAF;
+    float limit = 0.f;
+#pragma unroll
+    for (int k = 0; k < NODEGRID_BVH_LEAF; ++k) {
+        const float4 nd = __ldg(e + k);
+        const float d0 = qx - nd.x, d1 = qy - nd.y, d2 = qz - nd.z;
+        limit = fmaxf(limit, d0 * d0 + d1 * d1 + d2 * d2);
+    }
+    return limit < 3.402823466e+38f ? limit : 3.402823466e+38f;      // inf (padding) or NaN -> unbounded
+}
+
 __device__ __forceinline__ void knn8_grid(const void *__restrict__ grid, bool valid, float qx, float qy, float qz, int (&bi)[8], float (&bd)[8])
 {
 #pragma unroll

@@ -46,6 +46,9 @@ namespace kfusion
             virtual void clear();
             virtual void applyAffine(const Affine3f& affine);
             virtual void integrate(const Dists& dists, const Affine3f& camera_pose, const Intr& intr);
+            // not in the reference: the per-voxel warped fusion surface_fusion() was written towards and left commented out
+            // (tsdf_volume.cpp:240-252) -> df_integrate_warped.  depth = the u16 millimetre frame.
+            virtual void integrate(const Depth& depth, const WarpField& warp_field, const Affine3f& camera_pose, const Intr& intr, float weight_scale = 0.f);
             virtual void raycast(const Affine3f& camera_pose, const Intr& intr, Depth& depth, Normals& normals);   // USE_DEPTH path: aborts
             virtual void raycast(const Affine3f& camera_pose, const Intr& intr, Cloud& points, Normals& normals);
 

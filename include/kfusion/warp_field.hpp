@@ -53,6 +53,7 @@ namespace kfusion
         float *deviceNodes() const;
         void *deviceGrid() const;
         int deviceNodeCount() const;
+        const Affine3f& getWarpToLive() const { return warp_to_live_; }
         void adoptDeviceNodes(float *nodes_dev, void *grid_dev, int M);   // KinFu: share the pipeline's table
     private:
         std::vector<deformation_node>* nodes_;

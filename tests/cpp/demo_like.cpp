@@ -129,6 +129,40 @@ int main()
         CHECK(std::fabs(affine.matrix(0, 0) - 1.f) < 0.01f && std::fabs(affine.matrix(0, 3)) < 0.01f && std::fabs(affine.matrix(2, 3)) < 0.01f);
         CHECK(affine.matrix(0, 3) != 0.f);
     }
+    // --- per-voxel warped fusion (TsdfVolume::integrate(depth, warp_field, ...), not in the reference) ---------------------
+    {
+        cuda::TsdfVolume vol(Vec3i(64, 64, 64));
+        vol.setSize(Vec3f(1.f, 1.f, 1.f));
+        vol.setTruncDist(0.04f);
+        vol.setMaxWeight(64);
+        vol.setPose(Affine3f().translate(Vec3f(-0.5f, -0.5f, 0.5f)));
+        vol.clear();
+        std::vector<unsigned short> depth = make_depth(params.cols, params.rows, params.intr, 0.f);
+        cuda::Depth d;
+        d.upload(&depth[0], params.cols * sizeof(unsigned short), params.rows, params.cols);
+        // rigid first frame -> cloud -> nodes, as KinFu::operator() does (kinfu.cpp:245-264)
+        cuda::Dists dists;
+        cuda::computeDists(d, dists, params.intr);
+        vol.integrate(dists, Affine3f(), params.intr);
+        vol.compute_points();
+        cv::Mat cloud = vol.get_cloud_host();
+        CHECK(cloud.cols > 1000);
+        WarpField field;
+        field.init(cloud);
+        const int M = (int)field.getNodes()->size();
+        CHECK(M >= 8);
+        // push every node 2 mm towards the camera and fuse the same frame through the field
+        for (int i = 0; i < M; ++i) field.getNodes()->at(i).transform.encodeTranslation(0.f, 0.f, -0.002f / 8);
+        vol.integrate(d, field, Affine3f(), params.intr, 100.f);
+        vol.compute_points();
+        CHECK(vol.get_cloud_host().cols > 1000);
+        // every voxel the rigid frame wrote and the warped frame saw again now carries more than one unit of weight
+        std::vector<unsigned int> host((size_t)64 * 64 * 64);
+        vol.data().download(&host[0]);
+        int heavier = 0, seen = 0;
+        for (size_t i = 0; i < host.size(); ++i) { seen += (host[i] >> 16) != 0; heavier += (host[i] >> 16) > 1; }
+        CHECK(seen > 10000 && heavier > seen / 2);
+    }
     std::printf(fails ? "demo_like: %d check(s) FAILED\n" : "demo_like: all checks passed\n", fails);
     return fails ? 1 : 0;
 }

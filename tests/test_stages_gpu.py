@@ -199,6 +199,44 @@ def test_knn_and_warp(orc, M, N):
     assert np.array_equal(p_dev.cpu().numpy()[skipped].view(np.uint32), pts[skipped].view(np.uint32)), "skipped points untouched"
 
 
+@pytest.mark.parametrize("first_nan_normal", [None, 700, 0])
+def test_warp_reference_normal_cursor(orc, first_nan_normal):
+    """DF_WARP_REF_NORMAL_INDEX: the reference's cursor (warp_field.cpp:182-194) pairs the j-th non-NaN point with normal j and stalls
+    for good at the first NaN normal -- with a NaN normal at index 0 (a ray-cast miss at pixel 0) it warps nothing at all"""
+    import ctypes as C
+    rng = np.random.default_rng(7)
+    M, N = 300, 3000
+    nodes = _random_nodes(rng, M)
+    for m in range(M):
+        t = rng.normal(scale=0.02, size=3).astype(np.float32)
+        orc.load().orc_node_encode_translation(C.c_void_p(nodes[m].ctypes.data), C.c_float(t[0]), C.c_float(t[1]), C.c_float(t[2]))
+    pts = rng.uniform(-0.35, 0.35, (N, 4)).astype(np.float32)
+    pts[:, 3] = 0
+    nrm = rng.normal(size=(N, 4)).astype(np.float32)
+    pts[::7, 0] = np.nan
+    pts[100:400, 0] = np.nan                              # whole blocks of invalid points
+    if first_nan_normal is not None:
+        nrm[first_nan_normal, 0] = np.nan
+    wf = host.WarpField()
+    wf.setNodes(torch.from_numpy(nodes).cuda())
+    p_dev, n_dev = torch.from_numpy(pts).cuda(), torch.from_numpy(nrm).cuda()
+    wf.warp(p_dev, n_dev, flags=1)
+    p_ref, n_ref = pts.copy(), nrm.copy()
+    orc.warp(nodes, p_ref, n_ref, flags=1)
+    gp, gn = p_dev.cpu().numpy(), n_dev.cpu().numpy()
+    touched_ref = np.any(p_ref.view(np.uint32) != pts.view(np.uint32), axis=1)
+    touched_gpu = np.any(gp.view(np.uint32) != pts.view(np.uint32), axis=1)
+    assert np.array_equal(touched_ref, touched_gpu)
+    valid = int((~np.isnan(pts[:, 0])).sum())
+    want = valid if first_nan_normal is None else min(valid, first_nan_normal)
+    assert int(touched_ref.sum()) == want
+    assert np.array_equal(np.isnan(gp), np.isnan(p_ref)) and np.array_equal(np.isnan(gn), np.isnan(n_ref))
+    m = ~np.isnan(p_ref[:, 0])
+    np.testing.assert_allclose(gp[m], p_ref[m], rtol=1e-4, atol=1e-6)
+    mn = ~np.isnan(n_ref[:, 0])
+    np.testing.assert_allclose(gn[mn], n_ref[mn], rtol=1e-4, atol=1e-6)
+
+
 CUBE = [(1, 1, 1), (1, 1, -1), (1, -1, 1), (1, -1, -1), (-1, 1, 1), (-1, 1, -1), (-1, -1, 1), (-1, -1, -1)]
 
 

@@ -19,6 +19,8 @@ def main():
     ap.add_argument("--pipeline", action="store_true")
     ap.add_argument("--frames", type=int, default=12)
     ap.add_argument("--trace", action="store_true")
+    ap.add_argument("--warped", action="store_true", help="with --pipeline: DF_KINFU_WARPED_INTEGRATE (per-voxel warped fusion, SURVEY 8f(1))")
+    ap.add_argument("--weight-scale", type=float, default=100.0)
     ap.add_argument("--hd", action="store_true", help="config C4: 1280x720 depth, volume edge 1.5 m (use with --dim 768)")
     a = ap.parse_args()
     os.environ["DF_INTEGRATE_IMPL"] = str(a.integrate_impl)
@@ -46,7 +48,8 @@ def main():
     if a.pipeline:
         p = kf.KinFuParams.default_params_dynamicfusion()
         kf.KinFuParams.set_volume(p, dim, 1.0)
-        p.max_nodes = 2048; p.cloud_capacity = 4_000_000; p.flags = kf.STAGE_TIMING
+        p.max_nodes = 2048; p.cloud_capacity = 4_000_000; p.flags = kf.STAGE_TIMING | (kf.WARPED_INTEGRATE if a.warped else 0)
+        p.fusion_weight_scale = a.weight_scale
         k = kf.KinFu(p)
         acc, n = {}, 0
         for t in range(a.frames):
@@ -54,7 +57,7 @@ def main():
             k(d)
             if a.trace and (t < 6 or t % 5 == 0):
                 i, sm = k.info(), k.stage_ms()
-                print(f"frame {t:3d} lm {i['lm_iters']} pcg {i['pcg_iters']:4d} cloud {i['cloud_points']:7d} n_upd {i['n_updated']:9d} "
+                print(f"frame {t:3d} lm {i['lm_iters']} pcg {i['pcg_iters']:4d} cloud {i['cloud_points']:7d} n_upd {i['n_updated']:9d} n_warped {i['n_warped']:9d} "
                       f"solve {sm['solve']:.3f} icp {sm['icp']:.3f} integ {sm['integrate']:.3f} extract {sm['extract']:.3f} total {sum(sm.values()):.3f}", flush=True)
             if t >= 3:
                 for name, v in k.stage_ms().items():
