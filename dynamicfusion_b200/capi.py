@@ -84,7 +84,7 @@ PROTOTYPES = {
     "df_node_grid_bytes": (_sz, [_i]),
     "df_build_node_grid": (_i, [_vp, _i, _vp, _vp]),
     "df_warp": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, Aff3f, _i, _vp, _vp, _vp]),
-    "df_integrate_warped_workspace_bytes": (_sz, [_i, _i]),
+    "df_integrate_warped_workspace_bytes": (_sz, [_i, _i, _i]),
     "df_integrate_warped_launch_count": (_i, []),
     "df_integrate_warped": (_i, [Volume, _vp, _sz, _i, _i, Aff3f, Aff3f, Intr, _vp, _i, _vp, _f, _vp, _vp, _vp, _vp]),
     "df_solve_workspace_bytes": (_sz, [_i, _i]),

@@ -50,6 +50,7 @@ struct FusionParams {
     Aff vol2world, world2cam, vol2cam;     // vol2cam = world2cam o vol2world: used by the visibility test only
     float fx, fy, cx, cy;
     const float *nodes; int M; const void *grid;
+    const float4 *node_rec;                // per node: rotation quaternion, translation quaternion (fusion_prepare_kernel)
     float weight_scale;
     int cull;                              // 0: the two poses are not rigid -> no visibility test
     const float *ws;                       // [0] displacement bound, [1] global depth maximum, [16..] fine tile maxima, then coarse
@@ -78,8 +79,10 @@ __global__ void __launch_bounds__(256) depth_tile_max_kernel(const unsigned shor
     }
 }
 
-// block 0: coarse tile maxima + global maximum from the fine ones; block 1: displacement bound of the node table
-__global__ void __launch_bounds__(256) fusion_prepare_kernel(float *ws, int tiles_x, int tiles_y, int ctiles_x, int ctiles_y, const float *__restrict__ nodes, int M)
+// block 0: coarse tile maxima + global maximum from the fine ones; block 1: displacement bound of the node table and the per-node
+// (rotation, translation) records -- DualQuaternion::getTranslation (dual_quaternion.hpp:120-125) depends on the node alone
+__global__ void __launch_bounds__(256) fusion_prepare_kernel(float *ws, int tiles_x, int tiles_y, int ctiles_x, int ctiles_y, const float *__restrict__ nodes, int M,
+                                                             float4 *node_rec)
 {
     DF_PDL_ENTRY();
     __shared__ float red[256];
@@ -115,6 +118,8 @@ __global__ void __launch_bounds__(256) fusion_prepare_kernel(float *ws, int tile
             const Quat dual = {b.w, c.x, c.y, c.z};
             if (!(rot.w == 1.f && rot.x == 0.f && rot.y == 0.f && rot.z == 0.f)) rotated = true;
             const Quat tr = dq_translation(rot, dual);
+            node_rec[2 * i] = make_float4(rot.w, rot.x, rot.y, rot.z);      // the blend needs only these two per neighbour: 8 normalisations
+            node_rec[2 * i + 1] = make_float4(tr.w, tr.x, tr.y, tr.z);      // and quaternion products per voxel leave the inner loop
             const float len = sqrtf(tr.x * tr.x + tr.y * tr.y + tr.z * tr.z);
             tmax = fmaxf(tmax, len);
             if (!(len == len)) rotated = true;              // NaN translation: no bound
@@ -171,6 +176,26 @@ __device__ __forceinline__ bool fusion_run_invisible(const FusionParams &p, int 
         }
     }
     return zmin - 1e-3f > m + p.trunc;                             // rho < -trunc (or no depth at all) for every voxel of the run
+}
+
+// WarpField::DQB (warp_field.cpp:203-217) as dqb_blend() computes it, with every node's getTranslation() read from the records
+// instead of being re-derived per voxel: same float values, same accumulation order, same result bit for bit
+__device__ __forceinline__ Dqb fusion_blend(const FusionParams &p, const int (&bi)[8], const float (&bd)[8])
+{
+    Quat tsum = {0.f, 0.f, 0.f, 0.f}, rsum = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (bi[i] >= 0) {
+            const float4 r = __ldg(p.node_rec + 2 * bi[i]), t = __ldg(p.node_rec + 2 * bi[i] + 1);
+            const float w = node_weighting(bd[i], __ldg(p.nodes + (size_t)bi[i] * DF_NODE_STRIDE + 11));
+            tsum.w = tsum.w + w * t.x; tsum.x = tsum.x + w * t.y; tsum.y = tsum.y + w * t.z; tsum.z = tsum.z + w * t.w;
+            rsum.w = rsum.w + w * r.x; rsum.x = rsum.x + w * r.y; rsum.y = rsum.y + w * r.z; rsum.z = rsum.z + w * r.w;
+        }
+    }
+    Dqb d;
+    d.rot = qnormalize(rsum);
+    d.dual = qmul(qhalf(tsum), d.rot);
+    return d;
 }
 
 // TsdfVolume::weighting (tsdf_volume.cpp:300-306) quantised to the volume's u16 weight
@@ -235,7 +260,7 @@ __global__ void __launch_bounds__(256) integrate_warped_kernel(const FusionParam
             for (int k = 0; k < 8; ++k) prev[k] = bi[k];
             ++n_warp;
 
-            const Dqb d = dqb_blend<false>(p.nodes, bi, bd, nullptr);
+            const Dqb d = fusion_blend(p, bi, bd);
             const float3 xwp = dq_transform(d, xc);
             const float tx = p.world2cam.r0.x * xwp.x + p.world2cam.r0.y * xwp.y + p.world2cam.r0.z * xwp.z + p.world2cam.t.x;
             const float ty = p.world2cam.r1.x * xwp.x + p.world2cam.r1.y * xwp.y + p.world2cam.r1.z * xwp.z + p.world2cam.t.y;
@@ -285,10 +310,15 @@ double orthonormal_defect(const df_aff3f &a)
 
 }  // namespace
 
-extern "C" size_t df_integrate_warped_workspace_bytes(int cols, int rows)
+static size_t fusion_rec_offset_floats(int cols, int rows)
 {
     const int tx = div_up(cols, FUS_TILE), ty = div_up(rows, FUS_TILE);
-    return (size_t)(16 + tx * ty + div_up(tx, FUS_COARSE) * div_up(ty, FUS_COARSE)) * sizeof(float) + 64;
+    return ((size_t)(16 + tx * ty + div_up(tx, FUS_COARSE) * div_up(ty, FUS_COARSE)) + 3) & ~(size_t)3;      // 16-byte aligned
+}
+
+extern "C" size_t df_integrate_warped_workspace_bytes(int cols, int rows, int M)
+{
+    return (fusion_rec_offset_floats(cols, rows) + (size_t)8 * (M > 0 ? M : 0)) * sizeof(float) + 64;
 }
 
 extern "C" int df_integrate_warped_launch_count(void) { return 3; }
@@ -338,12 +368,14 @@ extern "C" int df_integrate_warped(df_volume vol, const uint16_t *depth, size_t 
     float *ws = (float *)workspace;
     const bool own = ws == nullptr;
     if (own) {
-        const cudaError_t e = cudaMallocAsync((void **)&ws, df_integrate_warped_workspace_bytes(cols, rows), s);
+        const cudaError_t e = cudaMallocAsync((void **)&ws, df_integrate_warped_workspace_bytes(cols, rows, M), s);
         if (e != cudaSuccess) return (int)e;
     }
     p.ws = ws;
+    float4 *rec = reinterpret_cast<float4 *>(ws + fusion_rec_offset_floats(cols, rows));
+    p.node_rec = rec;
     launch_pdl(depth_tile_max_kernel, dim3(p.tiles_x, p.tiles_y), dim3(256), 0, s, depth, depth_pitch, cols, rows, ws + 16, p.tiles_x);
-    launch_pdl(fusion_prepare_kernel, dim3(2), dim3(256), 0, s, ws, p.tiles_x, p.tiles_y, p.ctiles_x, p.ctiles_y, nodes, M);
+    launch_pdl(fusion_prepare_kernel, dim3(2), dim3(256), 0, s, ws, p.tiles_x, p.tiles_y, p.ctiles_x, p.ctiles_y, nodes, M, rec);
     dim3 grid(div_up(vol.dims[0], 32), div_up(vol.dims[1], 8), div_up(vol.dims[2], p.zchunk));
     launch_pdl(integrate_warped_kernel, grid, dim3(256), 0, s, p);
     if (own) cudaFreeAsync(ws, s);

@@ -404,7 +404,7 @@ extern "C" void *df_kinfu_create(const df_kinfu_params *pp)
     df_volume v = vol_of(*k);
     ok = ok && cudaMalloc(&k->extract_ws, df_extract_workspace_bytes(v)) == cudaSuccess;
     ok = ok && cudaMalloc(&k->integrate_ws, df_integrate_workspace_bytes(p.cols, p.rows)) == cudaSuccess;
-    ok = ok && cudaMalloc(&k->fusion_ws, df_integrate_warped_workspace_bytes(p.cols, p.rows)) == cudaSuccess;
+    ok = ok && cudaMalloc(&k->fusion_ws, df_integrate_warped_workspace_bytes(p.cols, p.rows, maxM)) == cudaSuccess;
     k->activity_bytes = df_volume_activity_bytes(v);
     ok = ok && cudaMalloc(&k->activity, k->activity_bytes) == cudaSuccess && cudaMemset(k->activity, 0, k->activity_bytes) == cudaSuccess;
     ok = ok && cudaMalloc(&k->project_ws, df_project_workspace_bytes(p.cols, p.rows)) == cudaSuccess;

@@ -206,8 +206,9 @@ int df_warp(const float *nodes, int M, const void *node_grid, float *points, flo
  *   :300-306; weight_scale <= 0 -> w = 1);  F' = (F*W + tsdf*w)/(W + w);  W' = min(W + w, max_weight).
  * depth: the frame's u16 millimetre image (not the ray lengths df_integrate takes); nodes / node_grid: the warp field (node_grid is
  * required).  counters (optional, device, 2 x u64): [0] += voxels written, [1] += voxels warped (k-NN + blend evaluated).
- * activity: as df_integrate_tracked.  workspace (optional, device): df_integrate_warped_workspace_bytes(cols, rows) bytes. */
-size_t df_integrate_warped_workspace_bytes(int cols, int rows);
+ * activity: as df_integrate_tracked.  workspace (optional, device): df_integrate_warped_workspace_bytes(cols, rows, M) bytes
+ * (M = the largest node count it will be used with). */
+size_t df_integrate_warped_workspace_bytes(int cols, int rows, int M);
 int df_integrate_warped_launch_count(void);
 int df_integrate_warped(df_volume vol, const uint16_t *depth, size_t depth_pitch, int cols, int rows, df_aff3f vol2world,
                         df_aff3f world2cam, df_intr intr, const float *nodes, int M, const void *node_grid, float weight_scale,
