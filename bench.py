@@ -163,6 +163,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--roofline-frames", type=int, default=12)
+    ap.add_argument("--no-warped", action="store_true", help="skip the short pass through the per-voxel warped fusion variant (SURVEY 8f(1))")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -276,6 +277,36 @@ def main():
                      "dense_upper_bound_bytes": 8.0 * DIM ** 3 + 2.0 * COLS * ROWS},
         "stage_ms": stage_ms,
     }
+    if rank == 0 and world == 1 and not args.no_warped:
+        # SURVEY 8f(1), reported beside the headline (never part of it): the same sequence with the fusion step of every frame done by
+        # df_integrate_warped (DF_KINFU_WARPED_INTEGRATE) instead of the reference's rigid fallback.  Short separate pass.
+        try:
+            p = params(kf.STAGE_TIMING | kf.WARPED_INTEGRATE)
+            p.fusion_weight_scale = 100.0
+            kw = kf.KinFu(p)
+            nw = min(nframes, 3 + 8)
+            acc, n_upd_w, n_warped, cnt = {}, 0, 0, 0
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for t in range(nw):
+                if t == 3:
+                    torch.cuda.synchronize()
+                    e0.record()
+                kw.lib.df_kinfu_process_device(kw.h, frames_dev[t].data_ptr(), pitch)
+                if t >= 3:
+                    for name, v in kw.stage_ms().items():
+                        acc[name] = acc.get(name, 0.0) + v
+                    i = kw.info()
+                    n_upd_w += i["n_updated"]; n_warped += i["n_warped"]; cnt += 1
+            e1.record()
+            torch.cuda.synchronize()
+            kw.close()
+            line["warped_fusion"] = {"what": "same workload, fusion step = per-voxel warped integration (df_integrate_warped, weight_scale 100)",
+                                     "frames": cnt, "ms_per_frame_incl_stage_readback": e0.elapsed_time(e1) / max(cnt, 1),
+                                     "stage_ms": {n: v / max(cnt, 1) for n, v in acc.items()},
+                                     "voxels_warped_per_frame": n_warped / max(cnt, 1), "voxels_written_per_frame": n_upd_w / max(cnt, 1),
+                                     "volume_voxels": DIM ** 3}
+        except Exception as e:                                                  # informational only: never lose the headline line
+            line["warped_fusion"] = {"error": repr(e)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         steps_cpu = 12
         dt, cinfo = run_cpu(frames[: 1 + 1 + steps_cpu], 1, steps_cpu)

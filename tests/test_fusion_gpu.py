@@ -108,6 +108,32 @@ def test_integrate_warped_matches_oracle(orc, dim, M, t_scale, weight_scale, pos
     assert np.all(act[active_vox // 1024] == 1)
 
 
+def test_integrate_warped_ragged_dims_and_empty_frame(orc):
+    """dims that are not multiples of the 32 x 8 block footprint (edge warps carry idle lanes through the warp-wide visibility test),
+    anisotropic voxels; an all-zero depth frame writes nothing"""
+    dims, size = (40, 28, 36), 1.0
+    depth = synth.sphere_wall_depth(seed=4)
+    nodes = _surface_nodes(orc, 150, seed=3, t_scale=0.002)
+    vol = host.TsdfVolume(dims, track_activity=True)
+    vol.setTruncDist(0.08); vol.setMaxWeight(MAXW); vol.setSize((size, size, size)); vol.setPose(synth.volume_pose(size)); vol.clear()
+    wf = host.WarpField()
+    wf.setNodes(torch.from_numpy(nodes).cuda())
+    counters = torch.zeros(2, dtype=torch.int64, device="cuda")
+    vol.integrate_warped(host.u16_to_device(np.zeros_like(depth)), _tilted_pose(), K, wf, 100.0, counters)
+    torch.cuda.synchronize()
+    assert int(counters[0].item()) == 0 and int(vol.data_.abs().sum().item()) == 0
+    counters.zero_()
+    world2cam = vol.integrate_warped(host.u16_to_device(depth), _tilted_pose(), K, wf, 100.0, counters)
+    ref = np.zeros(dims[0] * dims[1] * dims[2], np.uint32)
+    n_ref = orc.integrate_warped(ref, vol.getDims(), vol.getVoxelSize(), vol.getTruncDist(), vol.getMaxWeight(), depth, vol.getPose(), world2cam, K,
+                                 nodes, 100.0)
+    torch.cuda.synchronize()
+    got = vol.data_.cpu().numpy().view(np.uint32)
+    mism = int(np.count_nonzero(got != ref))
+    print(f"ragged {dims}: {int(counters[0].item())} written (oracle {n_ref}), {mism} differ")
+    assert n_ref > 500 and mism <= 2 and abs(int(counters[0].item()) - n_ref) <= 2
+
+
 def test_integrate_warped_rotated_nodes_disable_culling_and_still_match(orc):
     """any rotated node makes the displacement bound infinite: every voxel is warped, the result still equals the oracle's"""
     dim = 64
