@@ -40,7 +40,7 @@ class KinfuParams(C.Structure):
                 ("light_pose", C.c_float * 3),
                 ("solver_nonlinear_iters", C.c_int), ("solver_linear_iters", C.c_int),
                 ("max_nodes", C.c_int), ("node_step", C.c_int), ("cloud_capacity", C.c_int), ("flags", C.c_int),
-                ("fusion_weight_scale", C.c_float)]
+                ("fusion_weight_scale", C.c_float), ("extend_radius", C.c_float)]
 
 
 _vp, _sz, _i, _f = C.c_void_p, C.c_size_t, C.c_int, C.c_float
@@ -83,6 +83,8 @@ PROTOTYPES = {
     "df_knn8": (_i, [_vp, _i, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "df_node_grid_bytes": (_sz, [_i]),
     "df_build_node_grid": (_i, [_vp, _i, _vp, _vp]),
+    "df_extend_field_workspace_bytes": (_sz, [_i]),
+    "df_extend_field": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp, _i, _f, _i, _vp, _vp, _vp]),
     "df_warp": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, Aff3f, _i, _vp, _vp, _vp]),
     "df_integrate_warped_workspace_bytes": (_sz, [_i, _i, _i]),
     "df_integrate_warped_launch_count": (_i, []),

@@ -37,6 +37,7 @@ struct KinFu {
     void *solve_ws = nullptr; size_t solve_ws_bytes = 0; double *solve_stats = nullptr;
     void *extract_ws = nullptr; void *project_ws = nullptr;
     void *integrate_ws = nullptr;
+    void *extend_ws = nullptr; int *M_dev = nullptr;   // df_extend_field workspace / new node count (DF_KINFU_EXTEND_FIELD)
     void *fusion_ws = nullptr;             // df_integrate_warped workspace (DF_KINFU_WARPED_INTEGRATE)
     unsigned char *activity = nullptr; size_t activity_bytes = 0;   // dfusion.h DF_ACTIVITY_VOXELS: which stretches of the volume hold surface
     float *pinned = nullptr;             // 16 floats: T(12) + ok
@@ -196,6 +197,25 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_d
         return df_extract_normals(vol, k.cloud, p.cloud_capacity, k.cloud_count, p.volume_pose, Rinv_vol, p.gradient_delta_factor, k.cloud_nrm, s);
     };
 
+    auto extend = [&]() -> int {                                       // SURVEY 8f(3) / Report.md step 4, DF_KINFU_EXTEND_FIELD
+        if (!(p.flags & DF_KINFU_EXTEND_FIELD) || k.M <= 0) return 0;
+        const int maxM = p.max_nodes > 0 ? p.max_nodes : (p.cloud_capacity + 49) / 50;
+        if (k.M >= maxM) return 0;
+        int st = df_extend_field(k.nodes, k.M, maxM, k.node_grid, k.cloud, p.cloud_capacity, k.cloud_count, 4,
+                                 p.extend_radius > 0 ? p.extend_radius : 0.03f, p.node_step > 0 ? p.node_step : 50, k.M_dev, k.extend_ws, s);
+        if (st) return st;
+        k.launches += 3;
+        int Mn = k.M;
+        if (cudaMemcpyAsync(&Mn, k.M_dev, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess) return (int)cudaGetLastError();
+        if (cudaStreamSynchronize(s) != cudaSuccess) return (int)cudaGetLastError();
+        if (Mn != k.M) {
+            k.M = Mn;
+            st = df_build_node_grid(k.nodes, k.M, k.node_grid, s);     // buildKDTree() after the node set changed
+            ++k.launches;
+        }
+        return st;
+    };
+
     // ---- first frame, kinfu.cpp:245-264 ----------------------------------------------------------------------------
     if (!only_df && k.frame_counter == 0) {
         CKD(integrate_with(k.dists, &k.poses[k.poses.size() - 12]));
@@ -290,6 +310,7 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_d
             k.launches += df_integrate_warped_launch_count();
             mark(k, 8);
             CKD(extract());
+            CKD(extend());
             mark(k, 9);
         } else {
         // surface_fusion (tsdf_volume.cpp:228-255): psdf projects the warped vertices into the (bilateral-filtered) depth,
@@ -304,6 +325,7 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_d
         CKD(integrate_with(k.dists, cam_pose));
         mark(k, 8);
         CKD(extract());                                                // compute_points / compute_normals, :398-399
+        CKD(extend());
         mark(k, 9);
         }
     } else {
@@ -371,6 +393,10 @@ extern "C" void *df_kinfu_create(const df_kinfu_params *pp)
     {
         const char *e = getenv("DF_KINFU_WARPED_INTEGRATE");
         if (e && atoi(e) != 0) k->p.flags |= DF_KINFU_WARPED_INTEGRATE;
+        const char *x = getenv("DF_KINFU_EXTEND_FIELD");
+        if (x && atoi(x) != 0) k->p.flags |= DF_KINFU_EXTEND_FIELD;
+        const char *xr = getenv("DF_EXTEND_RADIUS");
+        if (xr) k->p.extend_radius = (float)atof(xr);
         const char *w = getenv("DF_FUSION_WEIGHT_SCALE");
         if (w) k->p.fusion_weight_scale = (float)atof(w);
     }
@@ -404,6 +430,7 @@ extern "C" void *df_kinfu_create(const df_kinfu_params *pp)
     df_volume v = vol_of(*k);
     ok = ok && cudaMalloc(&k->extract_ws, df_extract_workspace_bytes(v)) == cudaSuccess;
     ok = ok && cudaMalloc(&k->integrate_ws, df_integrate_workspace_bytes(p.cols, p.rows)) == cudaSuccess;
+    ok = ok && cudaMalloc(&k->extend_ws, df_extend_field_workspace_bytes(p.cloud_capacity)) == cudaSuccess && cudaMalloc((void **)&k->M_dev, 64) == cudaSuccess;
     ok = ok && cudaMalloc(&k->fusion_ws, df_integrate_warped_workspace_bytes(p.cols, p.rows, maxM)) == cudaSuccess;
     k->activity_bytes = df_volume_activity_bytes(v);
     ok = ok && cudaMalloc(&k->activity, k->activity_bytes) == cudaSuccess && cudaMemset(k->activity, 0, k->activity_bytes) == cudaSuccess;
@@ -432,7 +459,7 @@ extern "C" void df_kinfu_destroy(void *h)
     cudaFree(k->canon.ptr); cudaFree(k->canon_nrm.ptr); cudaFree(k->canon_visible.ptr);
     cudaFree(k->cloud); cudaFree(k->cloud_nrm); cudaFree(k->cloud_count); cudaFree(k->nodes); cudaFree(k->node_grid);
     cudaFree(k->icp_T); cudaFree(k->icp_ok); cudaFree(k->icp_scratch); cudaFree(k->solve_ws); cudaFree(k->solve_stats);
-    cudaFree(k->extract_ws); cudaFree(k->project_ws); cudaFree(k->activity); cudaFree(k->integrate_ws); cudaFree(k->fusion_ws); cudaFreeHost(k->pinned); cudaFree(k->n_upd);
+    cudaFree(k->extract_ws); cudaFree(k->project_ws); cudaFree(k->activity); cudaFree(k->integrate_ws); cudaFree(k->fusion_ws); cudaFree(k->extend_ws); cudaFree(k->M_dev); cudaFreeHost(k->pinned); cudaFree(k->n_upd);
     for (int e = 0; e <= NSTAGES; ++e) cudaEventDestroy(k->ev[e]);
     delete k;
 }

@@ -390,6 +390,23 @@ class WarpField:
                                   w.data_ptr() if want_knn else None, _stream()))
         return idx, w
 
+    def extend(self, cloud: torch.Tensor, radius: float, step: int = 50, max_nodes: int = 4096, count_dev: torch.Tensor | None = None) -> int:
+        """Extending the warp field (dfusion.h df_extend_field; SURVEY 8f(3), Report.md step 4): append a node for every step-th point of
+        the canonical cloud whose nearest node is farther than `radius`; rebuilds the node grid when nodes were added.  Returns the count."""
+        M = self.nodes_.shape[0]
+        cap, stride = cloud.shape
+        table = torch.zeros((max_nodes, NODE_STRIDE), dtype=torch.float32, device=self.device)
+        table[:M] = self.nodes_
+        ws = torch.empty(_lib().df_extend_field_workspace_bytes(cap), dtype=torch.uint8, device=self.device)
+        m_out = torch.zeros(1, dtype=torch.int32, device=self.device)
+        capi.check(_lib().df_extend_field(table.data_ptr(), M, max_nodes, self._grid(), cloud.data_ptr(), cap,
+                                          count_dev.data_ptr() if count_dev is not None else None, stride, float(radius), int(step),
+                                          m_out.data_ptr(), ws.data_ptr(), _stream()))
+        Mn = int(m_out.item())
+        if Mn != M:
+            self.setNodes(table[:Mn].clone())
+        return Mn
+
     def optimiseWarpData(self, canonical: torch.Tensor, live: torch.Tensor, nonlinear_iters=5, linear_iters=100, flags=0):
         """WarpFieldOptimiser::optimiseWarpData (warp_field_optimiser.cpp:7-16) -> device LM/PCG"""
         N, stride = canonical.shape

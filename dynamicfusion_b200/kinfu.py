@@ -17,6 +17,7 @@ STAGES = ["preprocess", "icp", "raycast_canonical", "warp1", "solve", "warp2", "
 RIGID_ONLY = 1
 STAGE_TIMING = 2
 REF_GRAPH_QUIRK = 4
+EXTEND_FIELD = 16         # DF_KINFU_EXTEND_FIELD: grow the warp field over unsupported canonical surface
 WARPED_INTEGRATE = 8      # DF_KINFU_WARPED_INTEGRATE: per-voxel warped fusion instead of the rigid fallback
 
 

@@ -189,6 +189,17 @@ int df_knn8(const float *nodes, int M, const void *node_grid, const float *queri
 size_t df_node_grid_bytes(int M);
 int df_build_node_grid(const float *nodes, int M, void *node_grid, void *stream);
 
+/* Extending the warp field (Report.md "4. Extending the warp field - stubbed out functionality"): nodes are appended for
+ * the points of the extracted canonical cloud that the field does not support.  A point is unsupported when its nearest node (of the M
+ * nodes present on entry) is farther than `radius`; every step-th unsupported point, in cloud order (the subsampling rule of
+ * WarpField::init, warp_field.cpp:49-60), becomes a node as init makes them (identity DualQuaternion(), weight 3, :68-80), appended to
+ * `nodes` (capacity max_nodes) until it is full.  cloud: float[capacity][stride], count_dev (optional, device) = valid points;
+ * M_out_dev (device int) receives the new node count -- rebuild the node grid (df_build_node_grid) when it differs from M.
+ * workspace: df_extend_field_workspace_bytes(capacity) bytes. */
+size_t df_extend_field_workspace_bytes(int capacity);
+int df_extend_field(float *nodes, int M, int max_nodes, const void *node_grid, const float *cloud, int capacity, const int *count_dev,
+                    int stride, float radius, int step, int *M_out_dev, void *workspace, void *stream);
+
 /* WarpField::warp (warp_field.hpp:62, warp_field.cpp:180-195): k-NN + weights + DQB + transform of points and
  * normals in place (stride in floats, 3 or 4).  flags: bit0 = reference normal cursor (advance only on valid points),
  * bit1 = rotate normals only (extension).  idx_out / w_out (optional, N*8) receive the neighbours and weights. */
@@ -252,6 +263,7 @@ typedef struct df_kinfu_params {
     int cloud_capacity;   /* extracted-cloud buffer, points: 256^3 in the reference (tsdf_volume.cpp:184) */
     int flags;            /* DF_KINFU_* */
     float fusion_weight_scale;   /* DF_KINFU_WARPED_INTEGRATE: weight_scale of df_integrate_warped (0 = every sample weighs 1) */
+    float extend_radius;         /* DF_KINFU_EXTEND_FIELD: support radius of df_extend_field in metres (<= 0: 0.03) */
 } df_kinfu_params;
 
 #define DF_KINFU_RIGID_ONLY 1      /* skip warp + solve (plain KinFu loop: config 1) */
@@ -261,6 +273,10 @@ typedef struct df_kinfu_params {
                                       voxel (df_integrate_warped), instead of project_and_remove + the rigid integrate the reference falls back to
                                       (tsdf_volume.cpp:234-238).  Also switched on by the environment variable DF_KINFU_WARPED_INTEGRATE=1, so that an
                                       unchanged apps/demo.cpp can run it; DF_FUSION_WEIGHT_SCALE sets fusion_weight_scale the same way. */
+
+#define DF_KINFU_EXTEND_FIELD 16    /* after every extraction the warp field is extended (df_extend_field, radius = extend_radius, step = node_step,
+                                      up to max_nodes) and the node grid rebuilt; costs one 4-byte read-back per frame.  Environment: DF_KINFU_EXTEND_FIELD=1,
+                                      DF_EXTEND_RADIUS. */
 
 /* which = 0: KinFuParams::default_params_dynamicfusion (kinfu.cpp:14-49); 1: default_params (kinfu.cpp:55-89) */
 void df_kinfu_default_params(df_kinfu_params *p, int which);

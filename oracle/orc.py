@@ -175,6 +175,17 @@ def integrate_warped(vol_data, dims, vs, trunc, mw, depth, vol2world, world2cam,
                                            aff(*vol2world), aff(*world2cam), intr(*K), _p(nodes), len(nodes), C.c_float(weight_scale)))
 
 
+def extend_field(nodes, cloud, radius, step, max_nodes) -> np.ndarray:
+    """orc_extend_field (orc_fusion.c): returns the extended node table"""
+    nodes = np.ascontiguousarray(nodes, np.float32)
+    M = len(nodes)
+    buf = np.zeros((max_nodes, NODE_STRIDE), np.float32)
+    buf[:M] = nodes
+    c = np.ascontiguousarray(cloud, np.float32)
+    Mn = load().orc_extend_field(_p(buf), M, max_nodes, _p(c), C.c_longlong(len(c)), c.shape[1], C.c_float(radius), step)
+    return buf[:Mn].copy()
+
+
 def raycast_points(vol_data, dims, vs, trunc, mw, cam2vol, Rinv, K, cols, rows, step_factor, delta_factor):
     pts = np.empty((rows, cols, 4), np.float32)
     nrm = np.empty((rows, cols, 4), np.float32)

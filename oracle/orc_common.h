@@ -146,6 +146,8 @@ void orc_node_encode_translation(float *node, float x, float y, float z);
 long long orc_integrate_warped(orc_volume vol, const uint16_t *depth, size_t pitch, int cols, int rows, orc_aff3f vol2world,
                                orc_aff3f world2cam, orc_intr intr, const float *nodes, int M, float weight_scale);
 
+int orc_extend_field(float *nodes, int M, int max_nodes, const float *cloud, long long n_points, int stride, float radius, int step);
+
 /* data-term solve */
 int orc_solve_data_term(float *nodes, int M, const float *canon, const float *live, long long N, int stride, int flags, int max_lm, double *stats);
 

@@ -89,3 +89,39 @@ long long orc_integrate_warped(orc_volume vol, const uint16_t *depth, size_t pit
     free(q); free(idx); free(d2);
     return n_upd;
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Extending the warp field, SURVEY.md 8f(3).  PARITY UNPINNED BY THE REFERENCE: Report.md ("4. Extending the warp field - stubbed out
+ * functionality") describes the step, the code base has none.  Restated from the pieces the reference does define:
+ *   - a point of the extracted canonical cloud is UNSUPPORTED when its nearest node (WarpField::KNN, warp_field.cpp:247-251: squared
+ *     distance d0*d0 + d1*d1 + d2*d2 in float) is farther than `radius` (d^2 > radius*radius); NaN points are skipped;
+ *   - the unsupported points are subsampled as WarpField::init subsamples the first cloud (every step-th, starting with the first:
+ *     warp_field.cpp:49-60), in cloud order;
+ *   - each becomes a node as init makes them (:68-80): vertex = the point, identity DualQuaternion() (rotation (1,0,0,0), dual (1,0,0,0)),
+ *     weight 3; appended after the M existing nodes until max_nodes.
+ * Support is judged against the M nodes present on entry only.  Returns the new node count. */
+int orc_extend_field(float *nodes, int M, int max_nodes, const float *cloud, long long n_points, int stride, float radius, int step)
+{
+    if (M <= 0 || n_points <= 0 || step <= 0) return M;
+    int32_t *idx = (int32_t *)malloc((size_t)n_points * 8 * sizeof(int32_t));
+    float *d2 = (float *)malloc((size_t)n_points * 8 * sizeof(float));
+    orc_knn8_fast(nodes, M, cloud, n_points, stride, idx, d2);
+    const float r2 = radius * radius;
+    long long rank = 0;
+    int Mn = M;
+    for (long long i = 0; i < n_points; ++i) {
+        const float *p = cloud + (size_t)i * stride;
+        if (p[0] != p[0] || p[1] != p[1] || p[2] != p[2]) continue;
+        if (!(d2[i * 8] > r2)) continue;
+        if (rank % step == 0 && M + rank / step < max_nodes) {
+            float *n = nodes + (size_t)(M + rank / step) * ORC_NODE_STRIDE;
+            memset(n, 0, ORC_NODE_STRIDE * sizeof(float));
+            n[0] = p[0]; n[1] = p[1]; n[2] = p[2];
+            n[3] = 1.f; n[7] = 1.f; n[11] = 3.f;
+            Mn = (int)(M + rank / step) + 1;
+        }
+        ++rank;
+    }
+    free(idx); free(d2);
+    return Mn;
+}

@@ -21,7 +21,7 @@ class KinfuParams(C.Structure):
                 ("light_pose", C.c_float * 3),
                 ("solver_nonlinear_iters", C.c_int), ("solver_linear_iters", C.c_int),
                 ("max_nodes", C.c_int), ("node_step", C.c_int), ("cloud_capacity", C.c_int), ("flags", C.c_int),
-                ("fusion_weight_scale", C.c_float)]
+                ("fusion_weight_scale", C.c_float), ("extend_radius", C.c_float)]
 
 
 def params_from(product_params) -> KinfuParams:

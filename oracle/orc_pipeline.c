@@ -30,6 +30,7 @@ typedef struct {
     int solver_nonlinear_iters, solver_linear_iters;
     int max_nodes, node_step, cloud_capacity, flags;
     float fusion_weight_scale;
+    float extend_radius;
 } orc_kinfu_params;     /* identical layout to df_kinfu_params (include/dfusion.h) */
 
 typedef struct {
@@ -272,6 +273,11 @@ int orc_kinfu_process(orc_kinfu *k, const uint16_t *depth, size_t pitch)
         t8 = now_s(); k->stage_s[7] = t8 - t7;
         }
         extract(k);
+        if ((p->flags & 16) && k->M > 0) {     /* DF_KINFU_EXTEND_FIELD: grow the field over unsupported canonical surface (orc_fusion.c) */
+            const int maxM = p->max_nodes > 0 ? p->max_nodes : (p->cloud_capacity + 49) / 50;
+            k->M = orc_extend_field(k->nodes, k->M, maxM, k->cloud, k->cloud_count, 4, p->extend_radius > 0 ? p->extend_radius : 0.03f,
+                                    p->node_step > 0 ? p->node_step : 50);
+        }
         double t9 = now_s(); k->stage_s[8] = t9 - t8;
         t2 = t9;
     } else {

@@ -245,3 +245,44 @@ def test_pipeline_with_warped_integration_tracks_the_oracle_pipeline(orc):
     finally:
         gpu.close()
         cpu.close()
+
+
+def test_pipeline_extends_the_field_like_the_oracle_pipeline(orc):
+    """DF_KINFU_EXTEND_FIELD through the frame loop against the oracle's loop with the same flag (64^3, 5 frames): the field grows every
+    frame; node counts agree within a few nodes (the two clouds differ by a handful of points, see tests/test_pipeline_gpu.py) and the
+    nodes both sides added on the first extension are the same points"""
+    from dynamicfusion_b200 import kinfu
+    from oracle import orc_pipe
+    p = kinfu.KinFuParams.default_params_dynamicfusion()
+    kinfu.KinFuParams.set_volume(p, 64, 1.0)
+    p.max_nodes = 4096
+    p.cloud_capacity = 400000
+    p.flags = kinfu.EXTEND_FIELD
+    p.extend_radius = 0.05
+    gpu = kinfu.KinFu(p)
+    cpu = orc_pipe.KinFu(orc_pipe.params_from(p))
+    try:
+        counts = []
+        for t in range(5):
+            depth = synth.umbrella_depth(t)
+            assert gpu(depth) == cpu(depth) == (t > 0)
+            counts.append((gpu.info()["nodes"], cpu.info()["nodes"]))
+        print("nodes per frame (gpu, oracle):", counts)
+        assert counts[0][0] == counts[0][1] >= 8
+        for (g0, c0), (g1, c1) in zip(counts, counts[1:]):
+            assert g1 >= g0 and c1 >= c0
+        assert counts[-1][0] > counts[0][0] + 20
+        for g, c in counts:
+            assert abs(g - c) <= max(3, 0.05 * c)
+        ng, nc = gpu.buffer("nodes")[: counts[-1][0]], cpu.buffer("nodes")
+        M0 = counts[0][0]
+        assert np.array_equal(ng[:M0, :3], nc[:M0, :3])
+        # appended nodes: identity transform, weight 3; most of frame 1's additions coincide exactly
+        assert np.all(ng[M0:, 3] == 1) and np.all(ng[M0:, 7] == 1) and np.all(ng[M0:, 11] == 3) and np.all(ng[M0:, 4:7] == 0)
+        first = min(counts[1])
+        same = sum(np.array_equal(ng[i, :3], nc[i, :3]) for i in range(M0, first))
+        print(f"first extension: {same} of {first - M0} appended nodes identical")
+        assert same >= 0.5 * (first - M0)
+    finally:
+        gpu.close()
+        cpu.close()

@@ -237,6 +237,29 @@ def test_warp_reference_normal_cursor(orc, first_nan_normal):
     np.testing.assert_allclose(gn[mn], n_ref[mn], rtol=1e-4, atol=1e-6)
 
 
+@pytest.mark.parametrize("use_grid,max_nodes", [(True, 4096), (False, 4096), (True, 330)])
+def test_extend_field_matches_oracle(orc, use_grid, max_nodes):
+    """df_extend_field: same appended nodes, bit for bit, as the oracle's sequential restatement -- the support test is
+    the exact nearest-node distance and the subsampling follows cloud order"""
+    rng = np.random.default_rng(11)
+    M, P, cap = 300, 20000, 24000
+    nodes = _random_nodes(rng, M)
+    nodes[:, :3] *= 0.5                                    # nodes cover the centre of the cloud only
+    cloud = np.zeros((cap, 4), np.float32)
+    cloud[:, :3] = rng.uniform(-0.45, 0.45, (cap, 3))
+    cloud[::19, 1] = np.nan
+    want = orc.extend_field(nodes, cloud[:P], 0.06, 50, max_nodes)
+    wf = host.WarpField(use_grid=use_grid)
+    wf.setNodes(torch.from_numpy(nodes).cuda())
+    count = torch.tensor([P], dtype=torch.int32, device="cuda")
+    Mn = wf.extend(torch.from_numpy(cloud).cuda(), 0.06, 50, max_nodes, count)
+    got = wf.getNodes().cpu().numpy()
+    assert Mn == len(want) == len(got) and (Mn > M + 20 if max_nodes > 1000 else Mn == max_nodes)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    # nothing to add when every point is supported
+    assert wf.extend(torch.from_numpy(cloud).cuda(), 10.0, 50, max_nodes + 10, count) == Mn
+
+
 CUBE = [(1, 1, 1), (1, 1, -1), (1, -1, 1), (1, -1, -1), (-1, 1, 1), (-1, 1, -1), (-1, -1, 1), (-1, -1, -1)]
 
 
