@@ -277,8 +277,9 @@ def test_pipeline_extends_the_field_like_the_oracle_pipeline(orc):
         ng, nc = gpu.buffer("nodes")[: counts[-1][0]], cpu.buffer("nodes")
         M0 = counts[0][0]
         assert np.array_equal(ng[:M0, :3], nc[:M0, :3])
-        # appended nodes: identity transform, weight 3; most of frame 1's additions coincide exactly
-        assert np.all(ng[M0:, 3] == 1) and np.all(ng[M0:, 7] == 1) and np.all(ng[M0:, 11] == 3) and np.all(ng[M0:, 4:7] == 0)
+        # appended nodes: identity rotation, weight 3 (their translations have been through the later solves); most of frame 1's
+        # additions coincide exactly
+        assert np.all(ng[M0:, 3] == 1) and np.all(ng[M0:, 11] == 3) and np.all(ng[M0:, 4:7] == 0)
         first = min(counts[1])
         same = sum(np.array_equal(ng[i, :3], nc[i, :3]) for i in range(M0, first))
         print(f"first extension: {same} of {first - M0} appended nodes identical")
