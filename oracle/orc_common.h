@@ -24,6 +24,8 @@
  * cloud extraction (the reference's extract_kernel is warp-synchronous: "parity unpinned").
  * Quaternion / dual quaternion / DQB / k-NN are pinned by the reference's headers compiled as they
  * lie (oracle/_ref/{dq_ref,knn_ref}); the warp solve by the reference's tests/warp_test.cpp.
+ * orc_fusion.c (per-voxel warped integration, field extension: SURVEY 8f(1), 8f(3)) restates steps the reference describes but
+ * never wrote -- PARITY UNPINNED there by construction; see that file's header.
  */
 #ifndef ORC_COMMON_H
 #define ORC_COMMON_H
