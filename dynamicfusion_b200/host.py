@@ -101,6 +101,30 @@ def resizePointsNormals(points: torch.Tensor, normals: torch.Tensor):
     return vd, nd
 
 
+def save_ply(path, points, normals=None) -> int:
+    """Export of the extracted canonical cloud (Report.md "Export the reconstructions to .ply"): the Python twin of
+    kfusion::writePly (include/kfusion/io/ply.hpp) -- binary little-endian PLY, float x y z [nx ny nz]; points with a NaN coordinate
+    are skipped, NaN normals written as 0.  points / normals: host or device arrays of shape [N, >=3]."""
+    pts = points.detach().cpu().numpy() if isinstance(points, torch.Tensor) else np.asarray(points)
+    pts = np.asarray(pts, np.float32)[:, :3]
+    keep = ~np.isnan(pts).any(1)
+    cols = [pts[keep]]
+    if normals is not None:
+        nrm = normals.detach().cpu().numpy() if isinstance(normals, torch.Tensor) else np.asarray(normals)
+        nrm = np.asarray(nrm, np.float32)[:, :3][keep].copy()
+        nrm[np.isnan(nrm).any(1)] = 0.0
+        cols.append(nrm)
+    data = np.ascontiguousarray(np.concatenate(cols, 1), "<f4")
+    with open(path, "wb") as f:
+        f.write(b"ply\nformat binary_little_endian 1.0\ncomment dynamicfusion canonical cloud\n")
+        f.write(f"element vertex {len(data)}\nproperty float x\nproperty float y\nproperty float z\n".encode())
+        if normals is not None:
+            f.write(b"property float nx\nproperty float ny\nproperty float nz\n")
+        f.write(b"end_header\n")
+        f.write(data.tobytes())
+    return len(data)
+
+
 # ------------------------------------------------------------------ TsdfVolume ---------------------------------------------------------------
 class TsdfVolume:
     """cuda::TsdfVolume (tsdf_volume.hpp:11-100, tsdf_volume.cpp).  Class defaults as tsdf_volume.cpp:7-14."""

@@ -109,3 +109,43 @@ def test_reference_demo_runs_headless_on_a_png_sequence(tmp_path):
     assert r.stderr.count("imshow Scene 480x1280") == 3          # frames 1..3 have an image (frame 0 only initialises)
     assert r.stderr.count("imshow Depth 480x640") == 4 and r.stderr.count("imshow Image 480x640") == 4
     assert "Exception" not in r.stdout and "Bad alloc" not in r.stdout
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# PLY export of the canonical cloud: the header-only C++ writer and its Python twin produce the same bytes
+def _read_ply(path):
+    raw = Path(path).read_bytes()
+    head, body = raw.split(b"end_header\n", 1)
+    lines = head.decode().splitlines()
+    n = int([l for l in lines if l.startswith("element vertex")][0].split()[-1])
+    props = [l.split()[-1] for l in lines if l.startswith("property float")]
+    return np.frombuffer(body, "<f4").reshape(n, len(props)), props
+
+
+def test_ply_export_cpp_and_python_agree(tmp_path):
+    from dynamicfusion_b200 import build
+    exe = tmp_path / "ply_check"
+    cmd = ["/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++", "-std=c++17", "-O1", *build.MIRROR_INC, "-o", str(exe),
+           str(ROOT / "tests" / "cpp" / "ply_check.cpp")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe), str(tmp_path)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.split() == ["6", "6", "-1"], out.stdout + out.stderr
+    data, props = _read_ply(tmp_path / "with_normals.ply")
+    assert props == ["x", "y", "z", "nx", "ny", "nz"] and data.shape == (6, 6)
+    idx = np.array([0, 1, 2, 4, 5, 6], np.float32)
+    assert np.array_equal(data[:, 0], 0.5 * idx) and np.array_equal(data[:, 1], -idx) and np.array_equal(data[:, 2], 2 + idx)
+    assert np.array_equal(data[:, 5], [1, 1, 1, 1, 0, 1])                       # the NaN normal became 0 0 0
+    pts_only, props2 = _read_ply(tmp_path / "points_only.ply")
+    assert props2 == ["x", "y", "z"] and np.array_equal(pts_only, data[:, :3])
+    # the Python twin writes the same file byte for byte
+    pytest.importorskip("torch")
+    from dynamicfusion_b200 import host
+    cloud = np.zeros((7, 4), np.float32)
+    cloud[:, 0], cloud[:, 1], cloud[:, 2] = 0.5 * np.arange(7), np.float32(-1.0) * np.arange(7, dtype=np.float32), 2 + np.arange(7)   # -1.f * 0 = -0.f
+    cloud[3, 0] = np.nan
+    nrm = np.zeros((7, 4), np.float32)
+    nrm[:, 2] = 1
+    nrm[5, 1] = np.nan
+    assert host.save_ply(tmp_path / "py.ply", cloud, nrm) == 6
+    assert (tmp_path / "py.ply").read_bytes() == (tmp_path / "with_normals.ply").read_bytes()

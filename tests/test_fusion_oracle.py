@@ -127,3 +127,38 @@ def test_weighted_average_saturates_at_max_weight(orc):
         orc.integrate_warped(vol, (DIM,) * 3, VS, TRUNC, 40, _plane_depth(800), POSE_VOL, IDENT, K, nodes, 100.0)
     w = vol >> 16
     assert w.max() == 40 and np.all(w <= 40)
+
+
+# ------------------------------------------------------------------ extending the warp field (orc_extend_field) ----------------
+def _brute_unsupported(nodes, cloud, radius):
+    d2 = ((cloud[:, None, :3].astype(np.float32) - nodes[None, :, :3]) ** 2)
+    d2 = (d2[..., 0] + d2[..., 1]) + d2[..., 2]                      # the reference's float evaluation order
+    valid = ~np.isnan(cloud[:, :3]).any(1)
+    return valid & (d2.min(1) > np.float32(radius) * np.float32(radius))
+
+
+def test_extend_field_appends_every_step_th_unsupported_point(orc):
+    rng = np.random.default_rng(5)
+    nodes = orc.make_nodes(rng.uniform(-0.1, 0.1, (120, 3)))
+    cloud = np.zeros((6000, 4), np.float32)
+    cloud[:, :3] = rng.uniform(-0.3, 0.3, (6000, 3))
+    cloud[::13, 2] = np.nan
+    out = orc.extend_field(nodes, cloud, 0.05, 50, 4096)
+    uns = np.flatnonzero(_brute_unsupported(nodes, cloud, 0.05))
+    picked = uns[::50]
+    assert len(out) == len(nodes) + len(picked)
+    assert np.array_equal(out[: len(nodes)], nodes)
+    assert np.array_equal(out[len(nodes):, :3], cloud[picked, :3])
+    new = out[len(nodes):]
+    assert np.all(new[:, 3] == 1) and np.all(new[:, 4:7] == 0) and np.all(new[:, 7] == 1) and np.all(new[:, 8:11] == 0) and np.all(new[:, 11] == 3)
+
+
+def test_extend_field_respects_capacity_and_support(orc):
+    rng = np.random.default_rng(6)
+    nodes = orc.make_nodes(rng.uniform(-0.1, 0.1, (100, 3)))
+    cloud = np.zeros((5000, 4), np.float32)
+    cloud[:, :3] = rng.uniform(-0.3, 0.3, (5000, 3))
+    assert len(orc.extend_field(nodes, cloud, 0.05, 50, 110)) == 110            # full table
+    assert len(orc.extend_field(nodes, cloud, 10.0, 50, 4096)) == 100           # everything supported
+    grown = orc.extend_field(nodes, cloud, 0.05, 1, 100000)                     # step 1: every unsupported point becomes a node ...
+    assert len(orc.extend_field(grown, cloud, 0.05, 1, 100000)) == len(grown)   # ... after which the cloud is fully supported (idempotent)
