@@ -653,6 +653,32 @@ const cv::Mat WarpField::getNodesAsMat() const
     }
     return matrix;
 }
+int WarpField::extend(const cv::Mat& cloud, float radius, int step, int max_nodes)
+{
+    uploadNodes();
+    Impl& I = *impl_;
+    const int M = I.M, P = cloud.cols * cloud.rows;
+    if (M <= 0 || P <= 0 || max_nodes <= M || !I.owns) return M;       // (KinFu's own table is extended by DF_KINFU_EXTEND_FIELD)
+    DeviceMemory table((size_t)max_nodes * DF_NODE_STRIDE * 4), pts((size_t)P * 16), ws(df_extend_field_workspace_bytes(P)), m_out(64);
+    cudaSafeCall(cudaMemcpy(table.ptr<void>(), I.nodes_dev, (size_t)M * DF_NODE_STRIDE * 4, cudaMemcpyDeviceToDevice));
+    cudaSafeCall(cudaMemcpy(pts.ptr<void>(), cloud.ptr<float>(), (size_t)P * 16, cudaMemcpyHostToDevice));
+    dfSafeCall(df_extend_field(table.ptr<float>(), M, max_nodes, I.grid_dev, pts.ptr<float>(), P, 0, 4, radius, step, m_out.ptr<int>(), ws.ptr<void>(), 0));
+    int Mn = M;
+    cudaSafeCall(cudaMemcpy(&Mn, m_out.ptr<void>(), sizeof(int), cudaMemcpyDeviceToHost));
+    if (Mn > M) {
+        std::vector<float> added((size_t)(Mn - M) * DF_NODE_STRIDE);
+        cudaSafeCall(cudaMemcpy(&added[0], table.ptr<float>() + (size_t)M * DF_NODE_STRIDE, added.size() * 4, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < Mn - M; ++i) {
+            deformation_node n;
+            n.transform = utils::DualQuaternion<float>();
+            n.vertex = Vec3f(added[(size_t)i * DF_NODE_STRIDE], added[(size_t)i * DF_NODE_STRIDE + 1], added[(size_t)i * DF_NODE_STRIDE + 2]);
+            n.weight = added[(size_t)i * DF_NODE_STRIDE + 11];
+            nodes_->push_back(n);
+        }
+        buildKDTree();
+    }
+    return Mn;
+}
 void WarpField::clear() {}
 void WarpField::setWarpToLive(const Affine3f &pose) { warp_to_live_ = pose; }
 std::vector<float>* WarpField::getDistSquared() const { return &impl_->out_dist_sqr_; }

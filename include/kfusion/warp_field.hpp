@@ -47,6 +47,11 @@ namespace kfusion
         std::vector<size_t>* getRetIndex() const;
         void buildKDTree();
 
+        // not in the reference ("Extending the warp field - stubbed out functionality", Report.md): append a node, made as init()
+        // makes them, for every step-th point of the canonical cloud (1 x N CV_32FC4, e.g. TsdfVolume::get_cloud_host()) whose nearest
+        // node is farther than radius -> df_extend_field.  Returns the new node count.
+        int extend(const cv::Mat& canonical_cloud, float radius, int step = 50, int max_nodes = 4096);
+
         // device side (not in the reference): used by KinFu / WarpFieldOptimiser
         void uploadNodes() const;                    // host vector -> device table (+ node grid when vertices changed)
         void downloadTranslations();                 // device table -> host vector (after the solve)

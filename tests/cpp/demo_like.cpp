@@ -151,8 +151,14 @@ int main()
         field.init(cloud);
         const int M = (int)field.getNodes()->size();
         CHECK(M >= 8);
+        // the field was seeded from every 50th point: with a 2 cm support radius most of the cloud is unsupported, and extending adds nodes
+        // until a second pass finds (almost) nothing left to add
+        const int M1 = field.extend(cloud, 0.02f, 5, 4096);
+        CHECK(M1 > M && M1 == (int)field.getNodes()->size());
+        const int M2 = field.extend(cloud, 0.02f, 5, 4096);
+        CHECK(M2 >= M1 && M2 - M1 < M1 - M);
         // push every node 2 mm towards the camera and fuse the same frame through the field
-        for (int i = 0; i < M; ++i) field.getNodes()->at(i).transform.encodeTranslation(0.f, 0.f, -0.002f / 8);
+        for (int i = 0; i < (int)field.getNodes()->size(); ++i) field.getNodes()->at(i).transform.encodeTranslation(0.f, 0.f, -0.002f / 8);
         vol.integrate(d, field, Affine3f(), params.intr, 100.f);
         vol.compute_points();
         CHECK(vol.get_cloud_host().cols > 1000);
