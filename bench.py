@@ -243,6 +243,27 @@ def main():
                 stage_acc[name] = stage_acc.get(name, 0.0) + v
             nupd_acc += k.info()["n_updated"]
             nroof += 1
+    # ray-cast roofline (the metric names integrate + ray-cast): re-run the frame's last ray-cast on the final volume with the counting
+    # instantiation of the kernel (df_raycast_points_stats) to get U = unique voxels read; its time is the stage's CUDA-event time
+    raycast_info = None
+    try:
+        import ctypes as C
+        from dynamicfusion_b200 import capi, host
+        ptr, pitch_, c_, r_ = C.c_void_p(), C.c_size_t(), C.c_int(), C.c_int()
+        capi.check(k.lib.df_kinfu_get_buffer(k.h, kf.BUF["volume"], C.byref(ptr), C.byref(pitch_), C.byref(c_), C.byref(r_)))
+        view = host.TsdfVolume.__new__(host.TsdfVolume)
+        view.device, view.activity_, view._ws, view._proj_ws = device, None, None, None
+        view.dims_ = np.array([DIM] * 3, np.int32)
+        view.size_ = np.array([SIZE] * 3, np.float32)
+        view.trunc_dist_ = max(0.04, 2.1 * SIZE / DIM)
+        view.max_weight_ = 64
+        view.pose_ = (np.eye(3, dtype=np.float32), np.array([-SIZE / 2, -SIZE / 2, 0.5], np.float32))
+        view.raycast_step_factor_, view.gradient_delta_factor_ = 0.75, 0.5
+        view._vol = lambda: capi.make_volume(ptr.value, view.dims_, view.getVoxelSize(), view.trunc_dist_, view.max_weight_)
+        st = view.raycast_stats(k.getCameraPose(), (570.342, 570.342, 320.0, 240.0), COLS, ROWS)
+        raycast_info = {kk: st[kk] for kk in ("unique_voxels", "hit_rays", "march_samples", "algorithmic_bytes")}
+    except Exception as e:                                                      # informational: never lose the headline line
+        raycast_info = {"error": repr(e)}
     k.close()
     stage_ms = {n: v / max(nroof, 1) for n, v in stage_acc.items()}
     n_upd = nupd_acc / max(nroof, 1)
@@ -277,6 +298,18 @@ def main():
                      "dense_upper_bound_bytes": 8.0 * DIM ** 3 + 2.0 * COLS * ROWS},
         "stage_ms": stage_ms,
     }
+    if raycast_info and "error" not in raycast_info:
+        rc_ms = stage_ms.get("raycast_prev", float("nan"))
+        rc_ach = raycast_info["algorithmic_bytes"] / (rc_ms * 1e-3) / 1e9 if rc_ms and rc_ms > 0 else float("nan")
+        line["roofline_raycast"] = {"kernel": "raycast_points_kernel", "bound": "hbm", "achieved": rc_ach, "peak": peak, "unit": "GB/s",
+                                    "frac": rc_ach / peak if peak else None, "traffic": None, "kernel_ms": rc_ms,
+                                    "algorithmic_bytes_per_launch": raycast_info["algorithmic_bytes"], "unique_voxels_read": raycast_info["unique_voxels"],
+                                    "hit_rays": raycast_info["hit_rays"], "march_samples": raycast_info["march_samples"],
+                                    "uncached_upper_bound_bytes": 4 * (raycast_info["march_samples"] + 64 * raycast_info["hit_rays"]) + 32 * COLS * ROWS,
+                                    "note": "U counted by the counting instantiation of the same kernel on the last frame's volume and pose; kernel_ms = "
+                                            "the stage's CUDA-event time averaged over the roofline frames"}
+    elif raycast_info:
+        line["roofline_raycast"] = raycast_info
     if rank == 0 and world == 1 and not args.no_warped:
         # SURVEY 8f(1), reported beside the headline (never part of it): the same sequence with the fusion step of every frame done by
         # df_integrate_warped (DF_KINFU_WARPED_INTEGRATE) instead of the reference's rigid fallback.  Short separate pass.

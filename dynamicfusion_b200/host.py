@@ -125,6 +125,15 @@ def save_ply(path, points, normals=None) -> int:
     return len(data)
 
 
+def _popcount32(t: torch.Tensor) -> torch.Tensor:
+    """per-element population count of an int32 tensor (bit tricks on int64 to stay clear of the sign bit)"""
+    v = t.to(torch.int64) & 0xffffffff
+    v = v - ((v >> 1) & 0x55555555)
+    v = (v & 0x33333333) + ((v >> 2) & 0x33333333)
+    v = (v + (v >> 4)) & 0x0f0f0f0f
+    return (v * 0x01010101 >> 24) & 0xff
+
+
 # ------------------------------------------------------------------ TsdfVolume ---------------------------------------------------------------
 class TsdfVolume:
     """cuda::TsdfVolume (tsdf_volume.hpp:11-100, tsdf_volume.cpp).  Class defaults as tsdf_volume.cpp:7-14."""
@@ -235,6 +244,23 @@ class TsdfVolume:
                                             self.raycast_step_factor_, self.gradient_delta_factor_, pts.data_ptr(), cols * 16,
                                             nrm.data_ptr(), cols * 16, _stream()))
         return pts, nrm, (cam2vol, Rinv)
+
+    def raycast_stats(self, camera_pose, intr, cols: int, rows: int) -> dict:
+        """df_raycast_points_stats: the ray-cast kernel instantiated with counters (measurement only).  Returns the unique voxels the
+        launch reads (U of SURVEY 8d), the rays that produced a vertex, the march samples, and the algorithmic bytes 4*U + 32*cols*rows."""
+        cam2vol = aff_mul(aff_inv(self.pose_), camera_pose)
+        Rinv = np.linalg.inv(cam2vol[0].astype(np.float64)).astype(np.float32)
+        pts = torch.empty((rows, cols, 4), dtype=torch.float32, device=self.device)
+        nrm = torch.empty_like(pts)
+        touched = torch.zeros(int(_lib().df_raycast_touched_bytes(self._vol())) // 4, dtype=torch.int32, device=self.device)
+        stats = torch.zeros(2, dtype=torch.int64, device=self.device)
+        capi.check(_lib().df_raycast_points_stats(self._vol(), capi.make_aff(*cam2vol), capi.f9(Rinv), capi.make_intr(*intr), cols, rows,
+                                                  self.raycast_step_factor_, self.gradient_delta_factor_, pts.data_ptr(), cols * 16,
+                                                  nrm.data_ptr(), cols * 16, touched.data_ptr(), stats.data_ptr(), _stream()))
+        unique = int(_popcount32(touched).sum().item())
+        hits, samples = (int(v) for v in stats.cpu().numpy())
+        return {"unique_voxels": unique, "hit_rays": hits, "march_samples": samples, "algorithmic_bytes": 4 * unique + 32 * cols * rows,
+                "points": pts, "normals": nrm}
 
     def project_and_remove(self, dists: torch.Tensor, intr, points: torch.Tensor):
         rows, cols = dists.shape

@@ -79,6 +79,15 @@ int df_raycast_points(df_volume vol, df_aff3f cam2vol, const float *Rinv_host9, 
                       float step_factor, float delta_factor,
                       float *points, size_t points_pitch, float *normals, size_t normals_pitch, void *stream);
 
+/* Measurement variant of df_raycast_points (bench.py's ray-cast roofline; never on the frame path): the same kernel instantiated with
+ * counters.  touched: df_raycast_touched_bytes(vol) bytes, zeroed by the caller, one bit per voxel the launch reads (its popcount is U of
+ * algorithmic bytes = 4*U + 32*cols*rows); stats (device, 2 x u64, zeroed by the caller): [0] rays that produced a vertex,
+ * [1] march samples fetched after the entry sample. */
+size_t df_raycast_touched_bytes(df_volume vol);
+int df_raycast_points_stats(df_volume vol, df_aff3f cam2vol, const float *Rinv_host9, df_intr intr, int cols, int rows,
+                            float step_factor, float delta_factor, float *points, size_t points_pitch,
+                            float *normals, size_t normals_pitch, unsigned int *touched, unsigned long long *stats, void *stream);
+
 /* device::project_and_remove (internal.hpp:108-109, tsdf_volume.cu:114-137,164-177): `dists` is sampled as fp16 and
  * the pixels the vertices land on are zeroed; vertices become (u*Dp, v*Dp, Dp, 0) or NaN when off-image.
  * Deterministic (the reference races the scatter with the sampling): samples always see the original image.
