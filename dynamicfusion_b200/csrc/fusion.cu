@@ -22,9 +22,9 @@
 //        64-pixel tiles, whole image).  The bound: weights are exp(-d^2/2s^2) <= 1 and are not normalised (warp_field.cpp:203-217), so
 //        |x_w - x_c| <= 8 max_i |t_i| when every node rotation is the identity (true for everything the translation-only solve
 //        produces); one small kernel per call reduces it over the node table and reports +inf (no culling) if any node is rotated.
-//   (ii) consecutive voxels of a z-column have almost the same neighbours: the largest distance from the new voxel to the previous
-//        voxel's eight neighbours bounds its 8th-nearest distance, and a BVH descent with that bound (knn8_bvh_bounded) touches one or
-//        two leaves instead of walking grid shells.  Results are ranked by (distance, index) on every path: identical to the exhaustive scan.
+//   (ii) consecutive voxels of a z-column have almost the same neighbours: the previous voxel's eight neighbours, re-measured from the new
+//        voxel, seed the branch-and-bound (knn8_bvh_seeded) so that it prunes with a near-final bound from the first box on and inserts only
+//        the few nodes that actually changed.  Results are ranked by (distance, index) on every path: identical to the exhaustive scan.
 #include "warp_common.cuh"
 #include <cmath>
 #include <cstdlib>
@@ -239,19 +239,22 @@ __global__ void __launch_bounds__(256) integrate_warped_kernel(const FusionParam
             const float3 xc = aff_mul(p.vol2world, make_float3((float)x * p.vsx, (float)y * p.vsy, (float)z * p.vsz));
             int bi[8]; float bd[8];
             if (has_bvh) {
-                float limit;
-                if (!have_prev) limit = knn8_bvh_greedy_bound(bvh_box, bvh_leaf, h.pad[4], xc.x, xc.y, xc.z);
-                else {
-                    limit = 0.f;
+                bool seeded = false;
+                if (have_prev) {                                   // the previous voxel's neighbours at this voxel's position
+                    seeded = true;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         const float *v = p.nodes + (size_t)prev[k] * DF_NODE_STRIDE;
                         const float d0 = xc.x - __ldg(v), d1 = xc.y - __ldg(v + 1), d2 = xc.z - __ldg(v + 2);
-                        limit = fmaxf(limit, d0 * d0 + d1 * d1 + d2 * d2);
+                        bi[k] = prev[k];
+                        bd[k] = d0 * d0 + d1 * d1 + d2 * d2;
+                        seeded = seeded && bd[k] == bd[k];
                     }
-                    if (!(limit == limit)) limit = 3.402823466e+38f;
+                } else {
+                    seeded = knn8_bvh_greedy_seed(bvh_box, bvh_leaf, h.pad[4], xc.x, xc.y, xc.z, bi, bd);
                 }
-                knn8_bvh_bounded(bvh_box, bvh_leaf, h.pad[4], xc.x, xc.y, xc.z, limit, bi, bd);
+                if (seeded) knn8_bvh_seeded(bvh_box, bvh_leaf, h.pad[4], xc.x, xc.y, xc.z, bi, bd);
+                else knn8_bvh_bounded(bvh_box, bvh_leaf, h.pad[4], xc.x, xc.y, xc.z, 3.402823466e+38f, bi, bd);
             } else {
                 knn8_grid(p.grid, true, xc.x, xc.y, xc.z, bi, bd);
             }

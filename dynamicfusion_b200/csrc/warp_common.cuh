@@ -180,6 +180,88 @@ __device__ __forceinline__ void knn8_bvh_bounded(const float4 *__restrict__ box,
     for (int i = 0; i < 8; ++i) if (bi[i] == 0x7fffffff) bi[i] = -1;
 }
 
+// knn8_bvh started from eight KNOWN nodes instead of an empty set: on entry bi[] holds eight distinct valid node indices and bd[] their
+// squared distances to the query, in any order (e.g. the neighbours of an adjacent query).  They are sorted by (distance, index) with a
+// 19-comparator network and the branch-and-bound then runs with the 8th of them as its bound from the first box on; a candidate that would
+// enter the set is first checked against the eight indices held (a seed node met again in its leaf).  Same result as knn8_bvh: the final
+// set is the (distance, index)-smallest eight of all nodes.  ncu on the first version of the warped-fusion kernel (search from an empty
+// set with a distance limit): 24 % of all instructions were insertions -- far from the node cloud ~30 nodes are nearly equidistant and each
+// query re-inserted ~18 of them -- with 15 of 32 lanes active (profiles/r01_fusion_v1_*).
+__device__ __forceinline__ void knn8_cswap_lex(float &da, int &ia, float &db, int &ib)
+{
+    if (db < da || (db == da && ib < ia)) { const float td = da; da = db; db = td; const int ti = ia; ia = ib; ib = ti; }
+}
+
+__device__ __forceinline__ void knn8_bvh_seeded(const float4 *__restrict__ box, const float4 *__restrict__ leaf, int L, float qx, float qy, float qz,
+                                                int (&bi)[8], float (&bd)[8])
+{
+#define DF_CS(a, b) knn8_cswap_lex(bd[a], bi[a], bd[b], bi[b])
+    DF_CS(0, 1); DF_CS(2, 3); DF_CS(4, 5); DF_CS(6, 7);
+    DF_CS(0, 2); DF_CS(1, 3); DF_CS(4, 6); DF_CS(5, 7);
+    DF_CS(1, 2); DF_CS(5, 6);
+    DF_CS(0, 4); DF_CS(1, 5); DF_CS(2, 6); DF_CS(3, 7);
+    DF_CS(2, 4); DF_CS(3, 5);
+    DF_CS(1, 2); DF_CS(3, 4); DF_CS(5, 6);
+#undef DF_CS
+    int stack_i[24];
+    float stack_d[24];
+    int sp = 0;
+    stack_i[sp] = 0; stack_d[sp] = 0.f; ++sp;
+    while (sp > 0) {
+        --sp;
+        const int i = stack_i[sp];
+        if (stack_d[sp] > bd[7]) continue;                       // strict: an equal distance may still win on the index
+        if (i >= L - 1) {
+            const float4 *e = leaf + (size_t)(i - (L - 1)) * NODEGRID_BVH_LEAF;
+#pragma unroll
+            for (int k = 0; k < NODEGRID_BVH_LEAF; ++k) {
+                const float4 nd = __ldg(e + k);
+                const float d0 = qx - nd.x, d1 = qy - nd.y, d2 = qz - nd.z;
+                const float dist = d0 * d0 + d1 * d1 + d2 * d2;
+                const int idx = __float_as_int(nd.w);
+                if (dist < bd[7] || (dist == bd[7] && idx < bi[7])) {
+                    const bool held = idx == bi[0] || idx == bi[1] || idx == bi[2] || idx == bi[3] || idx == bi[4] || idx == bi[5] || idx == bi[6];
+                    if (!held) knn8_insert_lex(bi, bd, dist, idx);
+                }
+            }
+        } else {
+            const int a = 2 * i + 1, b = a + 1;
+            const float da = bvh_box_dist2(__ldg(box + 2 * a), __ldg(box + 2 * a + 1), qx, qy, qz);
+            const float db = bvh_box_dist2(__ldg(box + 2 * b), __ldg(box + 2 * b + 1), qx, qy, qz);
+            const bool a_first = da <= db;
+            const int far_i = a_first ? b : a, near_i = a_first ? a : b;
+            const float far_d = a_first ? db : da, near_d = a_first ? da : db;
+            if (far_d <= bd[7]) { stack_i[sp] = far_i; stack_d[sp] = far_d; ++sp; }
+            if (near_d <= bd[7]) { stack_i[sp] = near_i; stack_d[sp] = near_d; ++sp; }
+        }
+    }
+}
+
+// The eight entries of the leaf a greedy descent reaches (nearer child at every level, no backtracking), with their squared distances:
+// a seed for knn8_bvh_seeded when no neighbouring result is at hand.  false when that leaf is padded (fewer than eight nodes).
+__device__ __forceinline__ bool knn8_bvh_greedy_seed(const float4 *__restrict__ box, const float4 *__restrict__ leaf, int L, float qx, float qy, float qz,
+                                                     int (&bi)[8], float (&bd)[8])
+{
+    int i = 0;
+    while (i < L - 1) {
+        const int a = 2 * i + 1, b = a + 1;
+        const float da = bvh_box_dist2(__ldg(box + 2 * a), __ldg(box + 2 * a + 1), qx, qy, qz);
+        const float db = bvh_box_dist2(__ldg(box + 2 * b), __ldg(box + 2 * b + 1), qx, qy, qz);
+        i = da <= db ? a : b;
+    }
+    const float4 *e = leaf + (size_t)(i - (L - 1)) * NODEGRID_BVH_LEAF;
+    bool full = true;
+#pragma unroll
+    for (int k = 0; k < NODEGRID_BVH_LEAF; ++k) {
+        const float4 nd = __ldg(e + k);
+        const float d0 = qx - nd.x, d1 = qy - nd.y, d2 = qz - nd.z;
+        bd[k] = d0 * d0 + d1 * d1 + d2 * d2;
+        bi[k] = __float_as_int(nd.w);
+        full = full && bd[k] < 3.402823466e+38f;                 // padding: distance inf, index INT_MAX
+    }
+    return full;
+}
+
 // A cheap upper bound on the 8th-nearest distance for knn8_bvh_bounded when no neighbouring result is at hand: descend to the leaf
 // whose boxes are nearest at every level (no backtracking) and take the largest distance to its eight nodes.  Any eight distinct
 // nodes bound the 8th-nearest distance; a padded leaf (fewer than eight nodes) yields FLT_MAX, i.e. an unbounded search.
