@@ -50,10 +50,10 @@ struct FusionParams {
     Aff vol2world, world2cam, vol2cam;     // vol2cam = world2cam o vol2world: used by the visibility test only
     float fx, fy, cx, cy;
     const float *nodes; int M; const void *grid;
-    const float4 *node_rec;                // per node: rotation quaternion, translation quaternion (fusion_prepare_kernel)
+    const float4 *node_rec;                // per node: rotation quaternion, translation quaternion, (vertex, weight) (fusion_prepare_kernel)
     float weight_scale;
     int cull;                              // 0: the two poses are not rigid -> no visibility test
-    const float *ws;                       // [0] displacement bound, [1] global depth maximum, [16..] fine tile maxima, then coarse
+    const float *ws;                       // [0] displacement bound, [1] global depth maximum, [2] 1 = every node rotation is the identity, [16..] fine tile maxima, then coarse
     int tiles_x, tiles_y, ctiles_x, ctiles_y;
     int zchunk;
     unsigned long long *counters;          // [0] voxels written, [1] voxels warped
@@ -118,8 +118,9 @@ __global__ void __launch_bounds__(256) fusion_prepare_kernel(float *ws, int tile
             const Quat dual = {b.w, c.x, c.y, c.z};
             if (!(rot.w == 1.f && rot.x == 0.f && rot.y == 0.f && rot.z == 0.f)) rotated = true;
             const Quat tr = dq_translation(rot, dual);
-            node_rec[2 * i] = make_float4(rot.w, rot.x, rot.y, rot.z);      // the blend needs only these two per neighbour: 8 normalisations
-            node_rec[2 * i + 1] = make_float4(tr.w, tr.x, tr.y, tr.z);      // and quaternion products per voxel leave the inner loop
+            node_rec[3 * i] = make_float4(rot.w, rot.x, rot.y, rot.z);      // the blend needs only these per neighbour: 8 normalisations
+            node_rec[3 * i + 1] = make_float4(tr.w, tr.x, tr.y, tr.z);      // and quaternion products per voxel leave the inner loop
+            node_rec[3 * i + 2] = make_float4(a.x, a.y, a.z, c.w);          // vertex + weight in one 16-byte load
             const float len = sqrtf(tr.x * tr.x + tr.y * tr.y + tr.z * tr.z);
             tmax = fmaxf(tmax, len);
             if (!(len == len)) rotated = true;              // NaN translation: no bound
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(256) fusion_prepare_kernel(float *ws, int tile
         red[t] = tmax;
         __syncthreads();
         for (int o = 128; o > 0; o >>= 1) { if (t < o) red[t] = fmaxf(red[t], red[t + o]); __syncthreads(); }
-        if (t == 0) ws[0] = flag ? __int_as_float(0x7f800000) : 8.f * red[0] * 1.0001f + 1e-6f;
+        if (t == 0) { ws[0] = flag ? __int_as_float(0x7f800000) : 8.f * red[0] * 1.0001f + 1e-6f; ws[2] = flag ? 0.f : 1.f; }
     }
 }
 
@@ -178,24 +179,37 @@ __device__ __forceinline__ bool fusion_run_invisible(const FusionParams &p, int 
     return zmin - 1e-3f > m + p.trunc;                             // rho < -trunc (or no depth at all) for every voxel of the run
 }
 
-// WarpField::DQB (warp_field.cpp:203-217) as dqb_blend() computes it, with every node's getTranslation() read from the records
-// instead of being re-derived per voxel: same float values, same accumulation order, same result bit for bit
-__device__ __forceinline__ Dqb fusion_blend(const FusionParams &p, const int (&bi)[8], const float (&bd)[8])
+// WarpField::DQB (warp_field.cpp:203-217) + DualQuaternion::transform (dual_quaternion.hpp:204-210) of the voxel position, as
+// dqb_blend() / dq_transform() compute them, with every node's getTranslation() read from the records instead of being re-derived per
+// voxel: same float values, same accumulation order, same result bit for bit.
+//
+// kIdentity (every node rotation is exactly (1,0,0,0): fusion_prepare_kernel checked it): the rotation sum is (W,0,0,0) with W > 0, and
+// then every later step is the identity in IEEE arithmetic -- sqrtf(W*W) == W, (float)((1.0/W)*W) == 1.f, a quaternion product with
+// (1,0,0,0) returns its other operand (x*1 == x, x +- 0 == x), halving and doubling are exact, and rotate() adds a cross product with the
+// zero vector -- so DQB(x).transform(x) == x + (sum_i w_i t_i).xyz bit for bit, and the normalisations (three double divisions), the two
+// quaternion products and the rotation are not executed.  (Only the sign of an exactly-zero component can differ, which no later
+// operation distinguishes.)  The parity tests compare this path with the oracle's unabridged arithmetic voxel for voxel.
+template <bool kIdentity>
+__device__ __forceinline__ float3 fusion_warp_point(const FusionParams &p, const int (&bi)[8], const float (&bd)[8], const float3 xc)
 {
     Quat tsum = {0.f, 0.f, 0.f, 0.f}, rsum = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         if (bi[i] >= 0) {
-            const float4 r = __ldg(p.node_rec + 2 * bi[i]), t = __ldg(p.node_rec + 2 * bi[i] + 1);
-            const float w = node_weighting(bd[i], __ldg(p.nodes + (size_t)bi[i] * DF_NODE_STRIDE + 11));
+            const float4 t = __ldg(p.node_rec + 3 * bi[i] + 1), pw = __ldg(p.node_rec + 3 * bi[i] + 2);
+            const float w = node_weighting(bd[i], pw.w);
             tsum.w = tsum.w + w * t.x; tsum.x = tsum.x + w * t.y; tsum.y = tsum.y + w * t.z; tsum.z = tsum.z + w * t.w;
-            rsum.w = rsum.w + w * r.x; rsum.x = rsum.x + w * r.y; rsum.y = rsum.y + w * r.z; rsum.z = rsum.z + w * r.w;
+            if (!kIdentity) {
+                const float4 r = __ldg(p.node_rec + 3 * bi[i]);
+                rsum.w = rsum.w + w * r.x; rsum.x = rsum.x + w * r.y; rsum.y = rsum.y + w * r.z; rsum.z = rsum.z + w * r.w;
+            }
         }
     }
+    if (kIdentity) return make_float3(xc.x + tsum.x, xc.y + tsum.y, xc.z + tsum.z);
     Dqb d;
     d.rot = qnormalize(rsum);
     d.dual = qmul(qhalf(tsum), d.rot);
-    return d;
+    return dq_transform(d, xc);
 }
 
 // TsdfVolume::weighting (tsdf_volume.cpp:300-306) quantised to the volume's u16 weight
@@ -210,9 +224,9 @@ __device__ __forceinline__ int fusion_sample_weight(const FusionParams &p, const
     return s < 1.f ? 1 : (s > (float)p.max_weight ? p.max_weight : (int)s);
 }
 
-__global__ void __launch_bounds__(256) integrate_warped_kernel(const FusionParams p)
+template <bool kIdentity>
+__device__ __forceinline__ void integrate_warped_body(const FusionParams &p)
 {
-    DF_PDL_ENTRY();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int xw = blockIdx.x * 32 + (warp & 3) * 8, yw = blockIdx.y * 8 + (warp >> 2) * 4;       // the warp's 8 x 4 voxel footprint
     const int x = xw + (lane & 7), y = yw + (lane >> 3);
@@ -244,8 +258,8 @@ __global__ void __launch_bounds__(256) integrate_warped_kernel(const FusionParam
                     seeded = true;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        const float *v = p.nodes + (size_t)prev[k] * DF_NODE_STRIDE;
-                        const float d0 = xc.x - __ldg(v), d1 = xc.y - __ldg(v + 1), d2 = xc.z - __ldg(v + 2);
+                        const float4 v = __ldg(p.node_rec + 3 * prev[k] + 2);
+                        const float d0 = xc.x - v.x, d1 = xc.y - v.y, d2 = xc.z - v.z;
                         bi[k] = prev[k];
                         bd[k] = d0 * d0 + d1 * d1 + d2 * d2;
                         seeded = seeded && bd[k] == bd[k];
@@ -263,8 +277,7 @@ __global__ void __launch_bounds__(256) integrate_warped_kernel(const FusionParam
             for (int k = 0; k < 8; ++k) prev[k] = bi[k];
             ++n_warp;
 
-            const Dqb d = fusion_blend(p, bi, bd);
-            const float3 xwp = dq_transform(d, xc);
+            const float3 xwp = fusion_warp_point<kIdentity>(p, bi, bd, xc);
             const float tx = p.world2cam.r0.x * xwp.x + p.world2cam.r0.y * xwp.y + p.world2cam.r0.z * xwp.z + p.world2cam.t.x;
             const float ty = p.world2cam.r1.x * xwp.x + p.world2cam.r1.y * xwp.y + p.world2cam.r1.z * xwp.z + p.world2cam.t.y;
             const float tz = p.world2cam.r2.x * xwp.x + p.world2cam.r2.y * xwp.y + p.world2cam.r2.z * xwp.z + p.world2cam.t.z;
@@ -298,6 +311,17 @@ __global__ void __launch_bounds__(256) integrate_warped_kernel(const FusionParam
     }
 }
 
+// Two instantiations are launched back to back and the one whose kIdentity does not match the node table returns at once (the flag is a
+// device-side result of fusion_prepare_kernel; reading it on the host would stall the frame loop): each path keeps its own register
+// allocation.  kMinBlocks = 3 (no spills) or 4 (64 registers, one more block per SM): DF_FUSION_MIN_BLOCKS.
+template <bool kIdentity, int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks) integrate_warped_kernel(const FusionParams p)
+{
+    DF_PDL_ENTRY();
+    if ((__ldg(p.ws + 2) != 0.f) != kIdentity) return;
+    integrate_warped_body<kIdentity>(p);
+}
+
 // |R^T R - I|_max: how far a pose's linear part is from a rotation
 double orthonormal_defect(const df_aff3f &a)
 {
@@ -321,10 +345,10 @@ static size_t fusion_rec_offset_floats(int cols, int rows)
 
 extern "C" size_t df_integrate_warped_workspace_bytes(int cols, int rows, int M)
 {
-    return (fusion_rec_offset_floats(cols, rows) + (size_t)8 * (M > 0 ? M : 0)) * sizeof(float) + 64;
+    return (fusion_rec_offset_floats(cols, rows) + (size_t)12 * (M > 0 ? M : 0)) * sizeof(float) + 64;
 }
 
-extern "C" int df_integrate_warped_launch_count(void) { return 3; }
+extern "C" int df_integrate_warped_launch_count(void) { return 4; }
 
 extern "C" int df_integrate_warped(df_volume vol, const uint16_t *depth, size_t depth_pitch, int cols, int rows, df_aff3f vol2world,
                                    df_aff3f world2cam, df_intr intr, const float *nodes, int M, const void *node_grid, float weight_scale,
@@ -380,7 +404,15 @@ extern "C" int df_integrate_warped(df_volume vol, const uint16_t *depth, size_t 
     launch_pdl(depth_tile_max_kernel, dim3(p.tiles_x, p.tiles_y), dim3(256), 0, s, depth, depth_pitch, cols, rows, ws + 16, p.tiles_x);
     launch_pdl(fusion_prepare_kernel, dim3(2), dim3(256), 0, s, ws, p.tiles_x, p.tiles_y, p.ctiles_x, p.ctiles_y, nodes, M, rec);
     dim3 grid(div_up(vol.dims[0], 32), div_up(vol.dims[1], 8), div_up(vol.dims[2], p.zchunk));
-    launch_pdl(integrate_warped_kernel, grid, dim3(256), 0, s, p);
+    static int min_blocks = -1;
+    if (min_blocks < 0) { const char *e = getenv("DF_FUSION_MIN_BLOCKS"); min_blocks = e ? atoi(e) : 3; }
+    if (min_blocks == 4) {
+        launch_pdl(integrate_warped_kernel<true, 4>, grid, dim3(256), 0, s, p);
+        launch_pdl(integrate_warped_kernel<false, 4>, grid, dim3(256), 0, s, p);
+    } else {
+        launch_pdl(integrate_warped_kernel<true, 3>, grid, dim3(256), 0, s, p);
+        launch_pdl(integrate_warped_kernel<false, 3>, grid, dim3(256), 0, s, p);
+    }
     if (own) cudaFreeAsync(ws, s);
     DF_LAUNCH_CHECK();
     return 0;
