@@ -313,7 +313,8 @@ __device__ __forceinline__ void integrate_warped_body(const FusionParams &p)
 
 // Two instantiations are launched back to back and the one whose kIdentity does not match the node table returns at once (the flag is a
 // device-side result of fusion_prepare_kernel; reading it on the host would stall the frame loop): each path keeps its own register
-// allocation.  kMinBlocks = 3, 4 (default: 64 registers, a few dozen bytes of spills, 34.8 vs 38.3 ms at 512^3) or 5: DF_FUSION_MIN_BLOCKS.
+// allocation.  kMinBlocks = 4 (default: 64 registers, a few dozen bytes of spills) or 3: 34.8 vs 38.3 ms at 512^3; 5 blocks (48 registers, 600 bytes
+// of spills) ran at 57 ms (profiles/r01_call63_*, r01_call64_*).  DF_FUSION_MIN_BLOCKS selects 3.
 template <bool kIdentity, int kMinBlocks>
 __global__ void __launch_bounds__(256, kMinBlocks) integrate_warped_kernel(const FusionParams p)
 {
@@ -405,11 +406,8 @@ extern "C" int df_integrate_warped(df_volume vol, const uint16_t *depth, size_t 
     launch_pdl(fusion_prepare_kernel, dim3(2), dim3(256), 0, s, ws, p.tiles_x, p.tiles_y, p.ctiles_x, p.ctiles_y, nodes, M, rec);
     dim3 grid(div_up(vol.dims[0], 32), div_up(vol.dims[1], 8), div_up(vol.dims[2], p.zchunk));
     static int min_blocks = -1;
-    if (min_blocks < 0) { const char *e = getenv("DF_FUSION_MIN_BLOCKS"); min_blocks = e ? atoi(e) : 4; }
-    if (min_blocks == 5) {
-        launch_pdl(integrate_warped_kernel<true, 5>, grid, dim3(256), 0, s, p);
-        launch_pdl(integrate_warped_kernel<false, 5>, grid, dim3(256), 0, s, p);
-    } else if (min_blocks == 4) {
+    if (min_blocks < 0) { const char *e = getenv("DF_FUSION_MIN_BLOCKS"); min_blocks = e ? atoi(e) : 4; if (min_blocks != 3) min_blocks = 4; }
+    if (min_blocks == 4) {
         launch_pdl(integrate_warped_kernel<true, 4>, grid, dim3(256), 0, s, p);
         launch_pdl(integrate_warped_kernel<false, 4>, grid, dim3(256), 0, s, p);
     } else {
