@@ -116,15 +116,60 @@ __global__ void __launch_bounds__(1024) build_node_grid_kernel(const float *__re
             hg->pad[0] = (int)(reinterpret_cast<char *>(order) - reinterpret_cast<char *>(grid));
             hg->pad[1] = (int)(reinterpret_cast<char *>(slot) - reinterpret_cast<char *>(grid));
         }
-        // 6. bounding-volume hierarchy over the Morton order for queries that lie far from every node (warp_common.cuh,
-        //    knn8_bvh): leaves = NODEGRID_BVH_LEAF consecutive nodes, implicit complete binary tree of L leaves, boxes bottom-up.
+        // 6. bounding-volume hierarchy for queries that lie far from every node and for the per-voxel searches of fusion.cu (warp_common.cuh,
+        //    knn8_bvh / knn8_bvh_seeded): leaves = NODEGRID_BVH_LEAF nodes, implicit complete binary tree of L leaves, boxes bottom-up.
+        //    Leaf membership = a k-d median split: the entries of every segment (the whole array, then halves, quarters, ... down to 16)
+        //    are sorted along the segment's widest axis and the segment is cut in the middle, so a leaf is a compact patch of eight nodes.
+        //    (The first version cut the Morton order into runs of eight: ncu on the fusion kernel showed ~10 leaves entered per query,
+        //    52 % of its instructions in leaf-entry and box tests -- Z-curve jumps make long, overlapping leaf boxes.)  Segments are aligned
+        //    power-of-two blocks, so one bitonic network run up to block size S sorts all of them at once; ties break on the node index.
+        //    The search result never depends on this order (boxes are built from whatever the leaves hold; ranking is by (distance, index)).
         if (bvh_box) {
             __syncthreads();
             const float inf = __int_as_float(0x7f800000);
-            for (int sidx = t; sidx < L * NODEGRID_BVH_LEAF; sidx += 1024) {
+            const int Mpad = L * NODEGRID_BVH_LEAF;
+            for (int sidx = t; sidx < Mpad; sidx += 1024) {
                 float4 e = make_float4(inf, inf, inf, __int_as_float(0x7fffffff));
-                if (sidx < M) { const int i = order[sidx]; const float *v = nodes + (size_t)i * DF_NODE_STRIDE; e = make_float4(v[0], v[1], v[2], __int_as_float(i)); }
+                if (sidx < M) { const float *v = nodes + (size_t)sidx * DF_NODE_STRIDE; e = make_float4(v[0], v[1], v[2], __int_as_float(sidx)); }
                 bvh_leaf[sidx] = e;
+            }
+            for (int S = Mpad; S >= 2 * NODEGRID_BVH_LEAF; S >>= 1) {
+                __syncthreads();
+                // widest axis of every segment (one warp per segment; padding entries are skipped); partial[] holds the axes
+                const int nseg = Mpad / S;
+                for (int seg = warp; seg < nseg; seg += 32) {
+                    float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+                    for (int k = lane; k < S; k += 32) {
+                        const float4 e = bvh_leaf[seg * S + k];
+                        if (__float_as_int(e.w) == 0x7fffffff) continue;
+                        lo[0] = fminf(lo[0], e.x); hi[0] = fmaxf(hi[0], e.x);
+                        lo[1] = fminf(lo[1], e.y); hi[1] = fmaxf(hi[1], e.y);
+                        lo[2] = fminf(lo[2], e.z); hi[2] = fmaxf(hi[2], e.z);
+                    }
+                    for (int c = 0; c < 3; ++c)
+                        for (int o = 16; o > 0; o >>= 1) { lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o)); hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o)); }
+                    if (lane == 0) {
+                        const float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];      // NaN (empty segment: inf - inf) compares false: axis 0
+                        partial[seg] = (ey > ex && ey >= ez) ? 1 : ((ez > ex && ez > ey) ? 2 : 0);
+                    }
+                }
+                __syncthreads();
+                for (int k = 2; k <= S; k <<= 1)
+                    for (int j = k >> 1; j > 0; j >>= 1) {
+                        for (int i = t; i < Mpad; i += 1024) {
+                            const int partner = i ^ j;
+                            if (partner > i) {
+                                const int axis = partial[i / S];
+                                const bool up = (k == S) || ((i & k) == 0);           // every segment ends ascending
+                                const float4 a = bvh_leaf[i], b = bvh_leaf[partner];
+                                const float ka = axis == 0 ? a.x : (axis == 1 ? a.y : a.z), kb = axis == 0 ? b.x : (axis == 1 ? b.y : b.z);
+                                const int ia = __float_as_int(a.w), ib = __float_as_int(b.w);
+                                const bool a_after_b = ka > kb || (ka == kb && ia > ib);      // padding: key inf, index INT_MAX -> sorts last
+                                if (a_after_b == up) { bvh_leaf[i] = b; bvh_leaf[partner] = a; }
+                            }
+                        }
+                        __syncthreads();
+                    }
             }
             __syncthreads();
             for (int l = t; l < L; l += 1024) {
