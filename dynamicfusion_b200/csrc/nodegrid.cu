@@ -10,7 +10,7 @@ using namespace dfb;
 namespace {
 
 __global__ void __launch_bounds__(1024) build_node_grid_kernel(const float *__restrict__ nodes, int M, void *grid, int *cid_tmp, int *order, int *slot,
-                                                               float4 *bvh_box, float4 *bvh_leaf, int L, float spacings_per_cell)
+                                                               float4 *bvh_box, float4 *bvh_leaf, int L, float spacings_per_cell, int kd_leaves)
 {
     __shared__ float smin[3][32], smax[3][32];
     __shared__ NodeGridHeader h;
@@ -130,10 +130,10 @@ __global__ void __launch_bounds__(1024) build_node_grid_kernel(const float *__re
             const int Mpad = L * NODEGRID_BVH_LEAF;
             for (int sidx = t; sidx < Mpad; sidx += 1024) {
                 float4 e = make_float4(inf, inf, inf, __int_as_float(0x7fffffff));
-                if (sidx < M) { const float *v = nodes + (size_t)sidx * DF_NODE_STRIDE; e = make_float4(v[0], v[1], v[2], __int_as_float(sidx)); }
+                if (sidx < M) { const int i = kd_leaves ? sidx : order[sidx]; const float *v = nodes + (size_t)i * DF_NODE_STRIDE; e = make_float4(v[0], v[1], v[2], __int_as_float(i)); }
                 bvh_leaf[sidx] = e;
             }
-            for (int S = Mpad; S >= 2 * NODEGRID_BVH_LEAF; S >>= 1) {
+            for (int S = kd_leaves ? Mpad : 0; S >= 2 * NODEGRID_BVH_LEAF; S >>= 1) {       // kd_leaves == 0: runs of the Morton order (first version)
                 __syncthreads();
                 // widest axis of every segment (one warp per segment; padding entries are skipped); partial[] holds the axes
                 const int nseg = Mpad / S;
@@ -236,7 +236,9 @@ extern "C" int df_build_node_grid(const float *nodes, int M, void *grid, void *s
     float4 *bvh_leaf = want_order ? bvh_box + 4 * (size_t)L : nullptr;
     static float spacings = 0.f;                              // node spacings per cell (default 3, see the kernel); DF_NODEGRID_SPACINGS overrides
     if (spacings == 0.f) { const char *e = getenv("DF_NODEGRID_SPACINGS"); spacings = e ? (float)atof(e) : 3.0f; if (!(spacings >= 0.5f)) spacings = 3.0f; }
-    build_node_grid_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(nodes, M, grid, cid_tmp, order, slot, bvh_box, bvh_leaf, L, spacings);
+    static int kd_leaves = -1;                                // BVH leaf membership: 1 = k-d median split, 0 = runs of the Morton order; DF_BVH_KD
+    if (kd_leaves < 0) { const char *e = getenv("DF_BVH_KD"); kd_leaves = e ? (atoi(e) != 0) : 0; }
+    build_node_grid_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(nodes, M, grid, cid_tmp, order, slot, bvh_box, bvh_leaf, L, spacings, kd_leaves);
     DF_LAUNCH_CHECK();
     return 0;
 }
