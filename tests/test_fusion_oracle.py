@@ -162,3 +162,16 @@ def test_extend_field_respects_capacity_and_support(orc):
     assert len(orc.extend_field(nodes, cloud, 10.0, 50, 4096)) == 100           # everything supported
     grown = orc.extend_field(nodes, cloud, 0.05, 1, 100000)                     # step 1: every unsupported point becomes a node ...
     assert len(orc.extend_field(grown, cloud, 0.05, 1, 100000)) == len(grown)   # ... after which the cloud is fully supported (idempotent)
+
+
+def test_oracle_outputs_match_committed_digests(orc):
+    """tests/golden/fusion_golden.json (made by tests/golden/make_fusion_golden.py): the restatement the GPU kernels are compared with
+    must not drift"""
+    import importlib.util
+    import json
+    from pathlib import Path
+    here = Path(__file__).resolve().parent / "golden"
+    spec = importlib.util.spec_from_file_location("make_fusion_golden", here / "make_fusion_golden.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.cases() == json.loads((here / "fusion_golden.json").read_text())
