@@ -758,6 +758,8 @@ static df_kinfu_params params_to(const KinFuParams& p)
     for (int i = 0; i < 4; ++i) d.icp_iter_num[i] = i < (int)p.icp_iter_num.size() ? p.icp_iter_num[i] : 0;
     d.tsdf_min_camera_movement = p.tsdf_min_camera_movement; d.tsdf_trunc_dist = p.tsdf_trunc_dist; d.tsdf_max_weight = p.tsdf_max_weight;
     d.raycast_step_factor = p.raycast_step_factor; d.gradient_delta_factor = p.gradient_delta_factor;
+    d.flags |= p.dfusion_flags & (DF_KINFU_WARPED_INTEGRATE | DF_KINFU_EXTEND_FIELD);
+    d.fusion_weight_scale = p.fusion_weight_scale; d.extend_radius = p.extend_radius;
     return d;
 }
 KinFuParams KinFuParams::default_params_dynamicfusion() { df_kinfu_params d; df_kinfu_default_params(&d, 0); return params_from(d); }

@@ -38,6 +38,12 @@ namespace kfusion
         float raycast_step_factor;   // in voxel sizes
         float gradient_delta_factor; // in voxel sizes
         Vec3f light_pose; //meters
+
+        // not in the reference: opt-in extensions of the fusion step, forwarded to df_kinfu_params; the defaults keep the
+        // reference's behaviour.  (The same switches exist as environment variables for an unchanged apps/demo.cpp, dfusion.h.)
+        int dfusion_flags = 0;             // DF_KINFU_WARPED_INTEGRATE (8) | DF_KINFU_EXTEND_FIELD (16)
+        float fusion_weight_scale = 0.f;   // df_integrate_warped's weight quantisation (0: every sample weighs 1)
+        float extend_radius = 0.f;         // df_extend_field's support radius in metres (0: 0.03)
     };
 
     class KF_EXPORTS KinFu
