@@ -18,9 +18,16 @@ references, OpenCV/Opt/Terra/Ceres are absent -- see DESIGN.md) with all host th
 """
 from __future__ import annotations
 
+import os
+# OpenMP (the CPU oracle of the cpu_baseline / --impl reference legs): idle workers sleep instead of spinning -- on a box whose
+# cgroup CPU quota is smaller than the visible CPU count, spinning workers burn the quota and the run thrashes (round 1:
+# 0.08 frames/s on 128 threads vs 0.36 on ONE).  Must be in the environment before libgomp is loaded.
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+os.environ.setdefault("OMP_PROC_BIND", "false")
+os.environ.setdefault("OMP_DYNAMIC", "false")
+
 import argparse
 import json
-import os
 import statistics
 import subprocess
 import sys
@@ -64,7 +71,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "10"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -96,6 +103,44 @@ class ClockSampler:
         return out
 
 
+def dram_traffic_probe(frames: int, timeout_s: float = 240.0):
+    """DRAM bytes per launch of the integrate and ray-cast kernels, measured NOW on this GPU: one extra process runs the same sequence
+    (tools/traffic_probe.py) under `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` restricted to those kernels; the launches of
+    the last three frames are averaged.  Returns {kernel_name: {"read": B, "write": B, "launches": n}} or {"error": ...}."""
+    import csv
+    import shutil
+    import tempfile
+    ncu = shutil.which("ncu") or ("/usr/local/cuda/bin/ncu" if Path("/usr/local/cuda/bin/ncu").exists() else None)
+    if not ncu:
+        return {"error": "ncu not found"}
+    with tempfile.TemporaryDirectory() as td:
+        log = Path(td) / "traffic.csv"
+        cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "--print-units", "base", "--csv",
+               "--kernel-name", "regex:integrate_kernel|raycast_points_kernel", "--log-file", str(log),
+               sys.executable, str(ROOT / "tools" / "traffic_probe.py"), "--frames", str(frames), "--dim", str(DIM), "--max-nodes", str(MAX_NODES)]
+        try:
+            r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout_s, cwd=str(ROOT))
+        except Exception as e:
+            return {"error": repr(e)}
+        if r.returncode != 0 or not log.exists():
+            return {"error": f"ncu rc {r.returncode}: {r.stdout[-300:]}"}
+        rows = [l for l in log.read_text().splitlines() if l.startswith('"')]
+        per = {}                                                 # (id, kernel) -> {metric: value}
+        for rec in csv.DictReader(rows):
+            try:
+                key = (int(rec["ID"]), rec["Kernel Name"].split("(")[0].split("<")[0].strip())
+                per.setdefault(key, {})[rec["Metric Name"]] = float(rec["Metric Value"].replace(",", ""))
+            except Exception:
+                continue
+        out = {}
+        for name in sorted({k[1] for k in per}):
+            launches = [per[k] for k in sorted(per) if k[1] == name]
+            tail = launches[-(3 if "integrate" in name else 6):]  # last three frames: 1 integrate, 2 ray-casts per frame
+            out[name] = {"read": sum(x.get("dram__bytes_read.sum", 0.0) for x in tail) / len(tail),
+                         "write": sum(x.get("dram__bytes_write.sum", 0.0) for x in tail) / len(tail), "launches": len(launches)}
+        return out or {"error": "no matching kernel in the ncu log"}
+
+
 def make_frames(n: int, seed: int):
     from dynamicfusion_b200 import synth
     return np.stack([synth.umbrella_depth(t, seed=seed) for t in range(n)])
@@ -109,47 +154,186 @@ def cpu_params():
     return p
 
 
-def run_cpu(frames: np.ndarray, warm: int, steps: int):
-    """the oracle's restated per-frame loop on the host cores; frame 0 initialises, then `warm` untimed, `steps` timed"""
+def run_cpu(frames: np.ndarray, lead: int, steps: int, calibrate=None):
+    """the oracle's restated per-frame loop on the host cores; frame 0 initialises, then `lead` untimed frames (lead-in + warm-up),
+    then `steps` timed.  calibrate: optional list of OpenMP thread counts tried on the first untimed frames (one each); the fastest is
+    kept for the rest of the run.  Returns (seconds, info, per-frame seconds, threads used, calibration record)."""
     from oracle import orc, orc_pipe
     orc.build()
     k = orc_pipe.KinFu(cpu_params())
     k(frames[0])
-    for t in range(1, 1 + warm):
-        k(frames[t])
+    calib, used = {}, None
+    cands = list(calibrate or [])
+    if cands:
+        set_omp_threads(cands[0])
+    preroll = 1 if lead > len(cands) else 0        # frame 1 pays first-touch page faults: keep it out of the calibration when there is room
+    for t in range(1, 1 + lead):
+        if cands and t > preroll:
+            c = cands.pop(0)
+            set_omp_threads(c)
+            t0 = time.perf_counter()
+            k(frames[t])
+            calib[c] = time.perf_counter() - t0
+            if not cands:
+                used = min(calib, key=calib.get)
+                set_omp_threads(used)
+        else:
+            k(frames[t])
+    per = []
     t0 = time.perf_counter()
-    for t in range(1 + warm, 1 + warm + steps):
+    for t in range(1 + lead, 1 + lead + steps):
+        t1 = time.perf_counter()
         k(frames[t])
+        per.append(time.perf_counter() - t1)
     dt = time.perf_counter() - t0
     info = k.info()
     k.close()
-    return dt, info
+    return dt, info, per, used, calib
+
+
+_gomp = None
+
+
+def set_omp_threads(n: int):
+    """omp_set_num_threads on the libgomp the oracle links (also overrides torchrun's OMP_NUM_THREADS=1); per calling thread"""
+    global _gomp
+    import ctypes
+    if _gomp is None:
+        _gomp = ctypes.CDLL("libgomp.so.1")
+    _gomp.omp_set_num_threads(int(max(1, n)))
+
+
+def host_cpus():
+    """(CPUs in the affinity mask, cgroup CPU quota in cores or None): the quota, not the mask, is what the process can use"""
+    try:
+        aff = len(os.sched_getaffinity(0))
+    except Exception:
+        aff = os.cpu_count() or 1
+    quota = None
+    try:                                            # cgroup v2
+        q, per = Path("/sys/fs/cgroup/cpu.max").read_text().split()[:2]
+        if q != "max":
+            quota = float(q) / float(per)
+    except Exception:
+        pass
+    if quota is None:
+        try:                                        # cgroup v1
+            q = int(Path("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read_text())
+            per = int(Path("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read_text())
+            if q > 0 and per > 0:
+                quota = q / per
+        except Exception:
+            pass
+    return aff, quota
 
 
 def host_threads():
-    try:
-        return len(os.sched_getaffinity(0))
-    except Exception:
-        return os.cpu_count() or 1
+    """threads the CPU legs start from: the cgroup quota capped by the affinity mask (then refined by calibration)"""
+    aff, quota = host_cpus()
+    n = aff if quota is None else max(1, min(aff, int(quota + 0.999)))
+    return n
+
+
+def thread_candidates():
+    """thread counts tried on the first untimed frames: quota/affinity-derived count, then halves -- a box that lies about its CPUs
+    (affinity 128, real share far smaller) shows up as the smaller counts being FASTER, and the fastest is used"""
+    n = host_threads()
+    c = [n]
+    while c[-1] > 4 and len(c) < 4:
+        c.append(max(4, c[-1] // 2))
+    return c
+
+
+def frame_stats_ms(per_s):
+    v = sorted(1000.0 * x for x in per_s)
+    return {"min": v[0], "median": v[len(v) // 2], "max": v[-1]} if v else None
+
+
+def bench_config(world: int, first: int, K: int):
+    """the SAME dict in both arms (the driver compares them): workload + the timed window, nothing measured"""
+    return {"workload": WORKLOAD, "node_cap": MAX_NODES, "knn": 8, "solver": "LM 5 x PCG 100 (early-out)", "sequences": world,
+            "parallelism": f"{world} independent sequences" if world > 1 else "single sequence",
+            "timed_frames": [first, first + K],
+            "l2": "working set (512 MiB volume, re-read every frame) exceeds the 126 MB L2; no explicit flush"}
 
 
 def reference_arm(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path = the oracle port (the reference itself cannot be built here,
+    DESIGN.md 5) on the box's host cores.  Same frames, same timed window, same --steps/--warmup as the GPU arm.  At N > 1 rank 0 runs
+    N sequences concurrently (seeds 0..N-1, the host threads split between them), so that `value` counts the same N*K frames as
+    the GPU arm's."""
     if rank != 0:
         return
-    budget_s = 150.0
-    est = 1.3                                   # s/frame measured on 8 vCPUs; re-estimated from the first timed frame below
-    steps = max(1, min(args.steps, int(budget_s / est)))
-    warm = min(args.warmup, 2)
-    frames = make_frames(1 + warm + steps, 0)
-    dt, info = run_cpu(frames, warm, steps)
-    fps = steps / dt
-    cores = host_threads()
-    sample = f"{steps} timed frames (+1 init, +{warm} warm-up) of the same 512^3 workload, OpenMP on {cores} threads"
-    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
-            "ms_per_step": 1000.0 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f16/u16 volume)",
-            "data": "synthetic", "config": {"workload": WORKLOAD, "nodes": info["nodes"], "note": "CPU restatement (oracle port): the reference's own "
-                                            "CUDA/Opt/OpenCV build is not possible in this image"},
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+    K, W = args.steps, args.warmup
+    first = max(args.frames_from, 1 + W)
+    lead = first - 1
+    aff, quota = host_cpus()
+    cands = thread_candidates()
+    if lead < len(cands):
+        cands = cands[:max(lead, 1)]
+    t_wall0 = time.perf_counter()
+    passes = []
+    if world == 1:
+        frames = make_frames(1 + lead + K, 0)
+        dt, info, per, used, calib = run_cpu(frames, lead, K, calibrate=cands)
+        passes.append((dt, per))
+        # second pass of the same frames (best + spread) if the first left room in the few-minutes budget
+        if time.perf_counter() - t_wall0 < 100.0:
+            dt2, info, per2, _, _ = run_cpu(frames, lead, K, calibrate=[used])
+            passes.append((dt2, per2))
+        nseq = 1
+    else:
+        # N concurrent sequences: calibrate the total thread count on sequence 0's first frames, then one host thread per sequence
+        import threading as th
+        frames0 = make_frames(1 + len(cands), 0)
+        _, _, _, used_total, calib = run_cpu(frames0, len(cands), 0, calibrate=cands)
+        per_seq = max(1, used_total // world)
+        results = [None] * world
+
+        def one(i):
+            set_omp_threads(per_seq)
+            fr = make_frames(1 + lead + K, i)
+            results[i] = (fr,)
+        ts = [th.Thread(target=one, args=(i,)) for i in range(world)]
+        [t.start() for t in ts]; [t.join() for t in ts]
+        start = th.Barrier(world)
+
+        def run(i):
+            set_omp_threads(per_seq)
+            from oracle import orc_pipe
+            k = orc_pipe.KinFu(cpu_params())
+            fr = results[i][0]
+            for t in range(0, 1 + lead):
+                k(fr[t])
+            start.wait()
+            t0 = time.perf_counter()
+            per = []
+            for t in range(1 + lead, 1 + lead + K):
+                t1 = time.perf_counter(); k(fr[t]); per.append(time.perf_counter() - t1)
+            results[i] = (time.perf_counter() - t0, per, k.info())
+            k.close()
+        ts = [th.Thread(target=run, args=(i,)) for i in range(world)]
+        [t.start() for t in ts]; [t.join() for t in ts]
+        dt = max(r[0] for r in results)
+        per = [x for r in results for x in r[1]]
+        info = results[0][2]
+        passes.append((dt, per))
+        used, nseq = per_seq, world
+    best_dt, best_per = min(passes, key=lambda q: q[0])
+    fps = nseq * K / best_dt
+    all_fps = [nseq * K / q[0] for q in passes]
+    spread = (max(all_fps) - min(all_fps)) / max(all_fps) if len(all_fps) > 1 else None
+    sample = (f"{K} timed frames per sequence x {nseq} sequence(s) (+1 init, +{lead} untimed incl. {W} warm-up) of the same 512^3 workload, "
+              f"OpenMP {used} threads per sequence, best of {len(passes)} pass(es)")
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
+            "ms_per_step": 1000.0 * best_dt / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f16/u16 volume)",
+            "data": "synthetic", "config": bench_config(world, first, K),
+            "note": "CPU restatement (oracle port, OpenMP): the reference's own CUDA/Opt/OpenCV build is not possible in this image (DESIGN.md 5)",
+            "run_info": {"nodes": info["nodes"], "cloud_points": info["cloud_points"]},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": used * nseq, "kind": "port", "sample": sample,
+                             "affinity_cpus": aff, "cgroup_quota_cpus": quota, "thread_calibration_s_per_frame": {str(c): v for c, v in calib.items()},
+                             "passes_fps": all_fps, "spread": spread, "per_sequence_fps": fps / nseq},
+            "frame_ms": frame_stats_ms(best_per),
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -164,6 +348,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--roofline-frames", type=int, default=12)
     ap.add_argument("--no-warped", action="store_true", help="skip the short pass through the per-voxel warped fusion variant (SURVEY 8f(1))")
+    ap.add_argument("--frames-from", type=int, default=10, help="first TIMED frame of the sequence (SURVEY 8d: steady state = frames 10-99): frame 0 "
+                    "initialises, frames 1..F-1 are untimed (the last W of them are the warm-up steps), frames F..F+K-1 are timed")
+    ap.add_argument("--no-traffic-probe", action="store_true", help="do not run the one-launch ncu pass that measures the integrate / ray-cast DRAM bytes")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -188,7 +375,8 @@ def main():
         distrib.barrier(device)
 
     K, W = args.steps, args.warmup
-    nframes = 1 + W + K
+    first = max(args.frames_from, 1 + W)                              # first timed frame; frames 1..first-1 untimed (lead-in + W warm-up)
+    nframes = first + K
     frames = make_frames(nframes, seed=distrib.sequence_seed(rank))   # independent sequence per rank (config 5)
     frames_i16 = torch.from_numpy(frames.view(np.int16))
     frames_dev = frames_i16.cuda()
@@ -203,42 +391,45 @@ def main():
         return p
 
     def timed(run_frame):
-        """frame 0 + W warm-up frames untimed, then exactly K frames between barrier+sync, CUDA events on the launching stream"""
+        """frame 0 + the untimed frames 1..first-1 (the last W = warm-up), then exactly K frames between barrier+sync, CUDA events on the
+        launching stream (one event per frame: the whole-region time is ev[0] -> ev[K], the per-frame spread comes for free)"""
         sampler = ClockSampler(local_rank)
         sampler.start()
         k = kf.KinFu(params())
         ok = 0
-        for t in range(1 + W):
+        for t in range(first):
             run_frame(k, t)
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
         sampler.mark_begin()
-        e0.record()
-        for t in range(1 + W, 1 + W + K):
+        ev[0].record()
+        for i, t in enumerate(range(first, first + K)):
             ok += run_frame(k, t)
-        e1.record()
+            ev[i + 1].record()
         barrier()
         sampler.mark_end()
         clocks = sampler.stop()
-        ms = e0.elapsed_time(e1)
+        ms = ev[0].elapsed_time(ev[K])
+        per = [ev[i].elapsed_time(ev[i + 1]) * 1e-3 for i in range(K)]
         info = k.info()
+        digest = k.state_digest() if hasattr(k, "state_digest") else None
         k.close()
         ms, _total, ok = distrib.aggregate(ms, ok, device)       # max time over ranks; ok = fewest fused frames on any rank
-        return ms, ok, info, clocks
+        return ms, ok, info, clocks, per, digest
 
     pitch = COLS * 2
     # value: inputs already resident in HBM
-    ms_dev, ok_dev, info, clocks = timed(lambda k, t: k.lib.df_kinfu_process_device(k.h, frames_dev[t].data_ptr(), pitch))
+    ms_dev, ok_dev, info, clocks, per_dev, digest_dev = timed(lambda k, t: k.lib.df_kinfu_process_device(k.h, frames_dev[t].data_ptr(), pitch))
     # e2e: the reference-facing call with HOST buffers (pinned), H2D + D2H inside the timed region
-    ms_e2e, ok_e2e, _, clocks_e2e = timed(lambda k, t: k.lib.df_kinfu_process_host(k.h, frames_pinned[t].data_ptr(), pitch))
+    ms_e2e, ok_e2e, _, clocks_e2e, per_e2e, digest_e2e = timed(lambda k, t: k.lib.df_kinfu_process_host(k.h, frames_pinned[t].data_ptr(), pitch))
     assert ok_dev == K and ok_e2e == K, f"tracking was lost during the timed region ({ok_dev}/{ok_e2e} of {K} frames fused)"
 
     # roofline of the dominant kernel (integrate): per-stage CUDA events + voxels written, on a separate short pass
     k = kf.KinFu(params(kf.STAGE_TIMING))
     stage_acc, nupd_acc, nroof = {}, 0, 0
-    for t in range(min(nframes, 3 + args.roofline_frames)):
+    for t in range(min(nframes, first + args.roofline_frames)):          # the stage times are those of the timed window's frames
         k.lib.df_kinfu_process_device(k.h, frames_dev[t].data_ptr(), pitch)
-        if t >= 3:
+        if t >= first:
             for name, v in k.stage_ms().items():
                 stage_acc[name] = stage_acc.get(name, 0.0) + v
             nupd_acc += k.info()["n_updated"]
@@ -271,13 +462,24 @@ def main():
     alg_bytes = 8.0 * n_upd + 2.0 * COLS * ROWS                # 4 B read + 4 B write per updated voxel + the fp16 dists image
     integ_ms = stage_ms.get("integrate", float("nan"))
     achieved = alg_bytes / (integ_ms * 1e-3) / 1e9 if integ_ms and integ_ms > 0 else float("nan")
-    traffic = None
-    tf = ROOT / "profiles" / "integrate_traffic.json"
-    if tf.exists():
-        try:
-            traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
+    # DRAM traffic of the two kernels, measured in THIS run (one ncu pass over the same sequence, rank 0 at N = 1); the committed
+    # capture (profiles/integrate_traffic.json) is only the fallback when ncu is unavailable
+    traffic, traffic_rc, traffic_src, probe = None, None, None, None
+    if rank == 0 and world == 1 and not args.no_traffic_probe:
+        probe = dram_traffic_probe(min(nframes, first + 3))
+        for name, v in probe.items():
+            if isinstance(v, dict) and "integrate" in name:
+                traffic, traffic_src = v["read"] + v["write"], f"live ncu pass ({name}, dram__bytes_read.sum + dram__bytes_write.sum, mean of the last 3 launches)"
+            if isinstance(v, dict) and "raycast" in name:
+                traffic_rc = v["read"] + v["write"]
+    if traffic is None:
+        tf = ROOT / "profiles" / "integrate_traffic.json"
+        if tf.exists():
+            try:
+                traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
+                traffic_src = "committed capture profiles/integrate_traffic.json (live probe unavailable: %s)" % ((probe or {}).get("error", "not run"))
+            except Exception:
+                traffic = None
 
     total_frames = K * world
     fps = total_frames / (ms_dev * 1e-3)
@@ -285,15 +487,16 @@ def main():
     line = {
         "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_dev / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f16/u16 volume)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "nodes": info["nodes"], "cloud_points": info["cloud_points"], "knn": 8,
-                   "solver": "LM 5 x PCG 100 (early-out)", "sequences": world, "parallelism": f"{world} independent sequences" if world > 1 else "single sequence",
-                   "l2": "working set (512 MiB volume, re-read every frame) exceeds the 126 MB L2; no explicit flush"},
+        "config": bench_config(world, first, K),
+        "run_info": {"nodes": info["nodes"], "cloud_points": info["cloud_points"]},
+        "frame_ms": frame_stats_ms(per_dev),
         "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": COLS * ROWS * 2, "d2h_bytes_per_step": 52,
-                "ms_per_step": ms_e2e / K},
+                "ms_per_step": ms_e2e / K, "frame_ms": frame_stats_ms(per_e2e)},
         "gpu_launches": int(info["launches"]) * K,
         "clocks": clocks,
         "roofline": {"kernel": {"1": "integrate_kernel<4>", "2": "integrate_kernel_v2<4>"}.get(os.environ.get("DF_INTEGRATE_IMPL", "3"), "integrate_kernel_v3"), "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
+                     "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
+                     "traffic_over_algorithmic": (traffic / alg_bytes) if (traffic and alg_bytes) else None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "voxels_written_per_launch": n_upd, "kernel_ms": integ_ms,
                      "dense_upper_bound_bytes": 8.0 * DIM ** 3 + 2.0 * COLS * ROWS},
         "stage_ms": stage_ms,
@@ -302,7 +505,7 @@ def main():
         rc_ms = stage_ms.get("raycast_prev", float("nan"))
         rc_ach = raycast_info["algorithmic_bytes"] / (rc_ms * 1e-3) / 1e9 if rc_ms and rc_ms > 0 else float("nan")
         line["roofline_raycast"] = {"kernel": "raycast_points_kernel", "bound": "hbm", "achieved": rc_ach, "peak": peak, "unit": "GB/s",
-                                    "frac": rc_ach / peak if peak else None, "traffic": None, "kernel_ms": rc_ms,
+                                    "frac": rc_ach / peak if peak else None, "traffic": traffic_rc, "kernel_ms": rc_ms,
                                     "algorithmic_bytes_per_launch": raycast_info["algorithmic_bytes"], "unique_voxels_read": raycast_info["unique_voxels"],
                                     "hit_rays": raycast_info["hit_rays"], "march_samples": raycast_info["march_samples"],
                                     "uncached_upper_bound_bytes": 4 * (raycast_info["march_samples"] + 64 * raycast_info["hit_rays"]) + 32 * COLS * ROWS,
@@ -340,18 +543,48 @@ def main():
                                      "volume_voxels": DIM ** 3}
         except Exception as e:                                                  # informational only: never lose the headline line
             line["warped_fusion"] = {"error": repr(e)}
+    # ---- multi-GPU correctness record: every rank's end state (volume checksum, node-table checksum, cloud points, pose-chain
+    # hash) is all-gathered; rank 0 then re-runs every other rank's sequence on ITS GPU and requires bit-identical digests -- the proof
+    # that ranks 1..N-1 fused the right volumes, not just that they were busy.  Also at N = 1: device-resident and host-buffer runs agree.
+    check = {"device_vs_host_path_identical": digest_dev == digest_e2e if digest_dev is not None else None}
+    if world > 1 and digest_dev is not None:
+        mine = torch.tensor([d - (1 << 64) if d >= (1 << 63) else d for d in digest_dev] + [ok_dev], dtype=torch.int64, device=device)
+        allv = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine)
+        if rank == 0:
+            got = [[int(x) & ((1 << 64) - 1) for x in v[:4].tolist()] for v in allv]
+            mism = []
+            for r in range(1, world):
+                fr = torch.from_numpy(make_frames(nframes, seed=distrib.sequence_seed(r)).view(np.int16)).cuda()
+                kr = kf.KinFu(params())
+                for t in range(nframes):
+                    kr.lib.df_kinfu_process_device(kr.h, fr[t].data_ptr(), pitch)
+                want = kr.state_digest()
+                kr.close()
+                del fr
+                if want != got[r]:
+                    mism.append(r)
+            check.update({"ranks": world, "rank_digests": [[f"{x:016x}" for x in g] for g in got], "ranks_recomputed_on_gpu0": world - 1,
+                          "mismatching_ranks": mism, "all_ranks_match_single_gpu_run": not mism})
+            assert not mism, f"ranks {mism} ended in a state that differs from a single-GPU run of the same sequence"
+        barrier()
+    line["state_check"] = check
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        steps_cpu = 12
-        dt, cinfo = run_cpu(frames[: 1 + 1 + steps_cpu], 1, steps_cpu)
-        line["cpu_baseline"] = {"value": steps_cpu / dt, "unit": "frames/s", "cores": host_threads(), "kind": "port",
-                                "sample": f"{steps_cpu} timed frames (+1 init, +1 warm-up) of the same sequence through the CPU oracle (OpenMP)"}
+        # bounded sample: 1 init + the calibration frames + 10 timed frames of the same sequence (about 15-25 s of CPU work)
+        steps_cpu = min(10, K)
+        cands = thread_candidates()
+        aff, quota = host_cpus()
+        dt, cinfo, per_cpu, used, calib = run_cpu(frames[: 1 + len(cands) + steps_cpu], len(cands), steps_cpu, calibrate=cands)
+        line["cpu_baseline"] = {"value": steps_cpu / dt, "unit": "frames/s", "cores": used, "kind": "port",
+                                "sample": f"{steps_cpu} timed frames (+1 init, +{len(cands)} untimed thread-count calibration frames) of the same sequence "
+                                          f"through the CPU oracle (OpenMP, {used} threads)",
+                                "affinity_cpus": aff, "cgroup_quota_cpus": quota,
+                                "thread_calibration_s_per_frame": {str(c): v for c, v in calib.items()}, "frame_ms": frame_stats_ms(per_cpu)}
         # SURVEY 8d also asks for the single-thread figure (the reference's own warp / k-NN loops are serial): 2 frames, 1 OpenMP thread
         try:
-            import ctypes
-            gomp = ctypes.CDLL("libgomp.so.1")
-            gomp.omp_set_num_threads(1)
-            dt1, _ = run_cpu(frames[:3], 0, 2)
-            gomp.omp_set_num_threads(host_threads())
+            set_omp_threads(1)
+            dt1 = run_cpu(frames[:3], 0, 2)[0]
+            set_omp_threads(used)
             line["cpu_baseline"]["single_thread_value"] = 2 / dt1
         except Exception as e:                                                  # informational only
             line["cpu_baseline"]["single_thread_value"] = None

@@ -90,6 +90,7 @@ def build_mirror(force: bool = False) -> Path:
 def build_cpp_program(src: Path, out: Path) -> Path:
     """compile + link a C++ program against the mirror (used by tests/test_cpp_mirror.py)"""
     build_mirror()
+    out.parent.mkdir(parents=True, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-std=c++17", "-O1", *MIRROR_INC, "-o", str(out), str(src), "-L", str(HERE), "-lkfusion", "-ldfusion",
            "-Xlinker", "-rpath", "-Xlinker", str(HERE)]

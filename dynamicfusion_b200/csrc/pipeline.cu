@@ -110,6 +110,21 @@ __global__ void __launch_bounds__(256) init_nodes_kernel(const float4 *cloud, in
     n[11] = 3.f;
 }
 
+// order-independent 64-bit checksum of a u32 array: sum over i of mix(i, a[i]) (splitmix64 finaliser); one u64 atomicAdd per block
+__global__ void __launch_bounds__(256) digest_kernel(const uint32_t *__restrict__ a, size_t n, unsigned long long *out)
+{
+    unsigned long long acc = 0ull;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        unsigned long long z = ((unsigned long long)a[i] << 32) ^ (unsigned long long)i;
+        z += 0x9e3779b97f4a7c15ull;
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+        z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+        acc += z ^ (z >> 31);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
 void mark(KinFu &k, int stage)
 {
     if (k.p.flags & DF_KINFU_STAGE_TIMING) cudaEventRecord(k.ev[stage], k.stream);
@@ -585,6 +600,26 @@ extern "C" int df_kinfu_read_buffer(void *h, int which, void *dst_host, size_t b
     if (e != cudaSuccess) return (int)e;
     e = cudaMemcpy(dst_host, ptr, bytes < have ? bytes : have, cudaMemcpyDeviceToHost);
     return (int)e;
+}
+
+extern "C" int df_kinfu_state_digest(void *h, unsigned long long *out4_host)
+{
+    KinFu *k = (KinFu *)h;
+    unsigned long long *d = nullptr;
+    if (cudaMalloc((void **)&d, 32) != cudaSuccess) return (int)cudaGetLastError();
+    cudaMemsetAsync(d, 0, 32, k->stream);
+    const size_t nvox = (size_t)k->p.volume_dims[0] * k->p.volume_dims[1] * k->p.volume_dims[2];
+    digest_kernel<<<148 * 8, 256, 0, k->stream>>>(k->volume, nvox, d);
+    if (k->M > 0) digest_kernel<<<8, 256, 0, k->stream>>>((const uint32_t *)k->nodes, (size_t)k->M * DF_NODE_STRIDE, d + 1);
+    cudaMemcpyAsync(d + 2, k->cloud_count, sizeof(int), cudaMemcpyDeviceToDevice, k->stream);
+    cudaError_t e = cudaMemcpyAsync(out4_host, d, 32, cudaMemcpyDeviceToHost, k->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(k->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return (int)e;
+    unsigned long long ph = 0x243f6a8885a308d3ull;                      // camera poses so far, bit pattern by bit pattern
+    for (float f : k->poses) { uint32_t u; memcpy(&u, &f, 4); ph = (ph ^ u) * 0x100000001b3ull; }
+    out4_host[3] = ph;
+    return 0;
 }
 
 extern "C" int df_kinfu_get_stage_ms(void *h, float *ms, int n)

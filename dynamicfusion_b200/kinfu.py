@@ -99,6 +99,12 @@ class KinFu:
                 "n_warped"]
         return dict(zip(keys, [int(x) for x in v]))
 
+    def state_digest(self) -> list:
+        """df_kinfu_state_digest: [volume checksum, node-table checksum, cloud points, pose-chain hash] (u64 each)"""
+        v = (C.c_ulonglong * 4)()
+        capi.check(self.lib.df_kinfu_state_digest(self.h, v))
+        return [int(x) for x in v]
+
     def stage_ms(self) -> dict:
         v = (C.c_float * 10)()
         n = self.lib.df_kinfu_get_stage_ms(self.h, v, 10)

@@ -316,6 +316,10 @@ int df_kinfu_get_info(void *kinfu, long long *info_host, int n);
 int df_kinfu_get_buffer(void *kinfu, int which, void **ptr, size_t *pitch, int *cols, int *rows);
 /* synchronous device-to-host copy of one of those buffers (diagnostics / tests), at most `bytes` bytes */
 int df_kinfu_read_buffer(void *kinfu, int which, void *dst_host, size_t bytes);
+/* digest of the current state (multi-GPU correctness record, SURVEY 8e: ranks exchange it and rank 0 compares every rank's with a
+ * single-GPU run of the same sequence): out4_host[0] order-independent 64-bit checksum of the packed volume, [1] the same over the node
+ * table, [2] extracted cloud points, [3] FNV-style hash of every camera pose so far (bit patterns).  Synchronous. */
+int df_kinfu_state_digest(void *kinfu, unsigned long long *out4_host);
 /* per-stage milliseconds of the last frame (DF_KINFU_STAGE_TIMING): preprocess, icp, raycast_canonical, warp1, solve,
  * warp2, project_remove, integrate, extract, raycast_prev; returns the number written */
 int df_kinfu_get_stage_ms(void *kinfu, float *ms_host, int n);

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 ROOT = Path(__file__).resolve().parents[1]
-EXE = ROOT / "tests" / "cpp" / "demo_like"
+EXE = ROOT / "tests" / "cpp" / "_build" / "demo_like"
 
 
 def _build():
