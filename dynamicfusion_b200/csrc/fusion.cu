@@ -379,7 +379,7 @@ extern "C" int df_integrate_warped(df_volume vol, const uint16_t *depth, size_t 
     p.vol2cam = make_aff(v2c);
     p.cull = orthonormal_defect(vol2world) < 1e-3 && orthonormal_defect(world2cam) < 1e-3;
     {
-        const char *e = getenv("DF_FUSION_CULL");
+        static const char *const e = getenv("DF_FUSION_CULL");
         if (e && atoi(e) == 0) p.cull = 0;
     }
     p.fx = intr.fx; p.fy = intr.fy; p.cx = intr.cx; p.cy = intr.cy;
@@ -390,7 +390,7 @@ extern "C" int df_integrate_warped(df_volume vol, const uint16_t *depth, size_t 
     p.ctiles_x = div_up(p.tiles_x, FUS_COARSE); p.ctiles_y = div_up(p.tiles_y, FUS_COARSE);
     p.zchunk = vol.dims[2] >= 64 ? 32 : vol.dims[2];
     {
-        const char *e = getenv("DF_FUSION_ZCHUNK");
+        static const char *const e = getenv("DF_FUSION_ZCHUNK");
         if (e && atoi(e) > 0) p.zchunk = atoi(e);
     }
     float *ws = (float *)workspace;
@@ -405,8 +405,7 @@ extern "C" int df_integrate_warped(df_volume vol, const uint16_t *depth, size_t 
     launch_pdl(depth_tile_max_kernel, dim3(p.tiles_x, p.tiles_y), dim3(256), 0, s, depth, depth_pitch, cols, rows, ws + 16, p.tiles_x);
     launch_pdl(fusion_prepare_kernel, dim3(2), dim3(256), 0, s, ws, p.tiles_x, p.tiles_y, p.ctiles_x, p.ctiles_y, nodes, M, rec);
     dim3 grid(div_up(vol.dims[0], 32), div_up(vol.dims[1], 8), div_up(vol.dims[2], p.zchunk));
-    static int min_blocks = -1;
-    if (min_blocks < 0) { const char *e = getenv("DF_FUSION_MIN_BLOCKS"); min_blocks = e ? atoi(e) : 4; if (min_blocks != 3) min_blocks = 4; }
+    static const int min_blocks = [] { const char *e = getenv("DF_FUSION_MIN_BLOCKS"); return (e && atoi(e) == 3) ? 3 : 4; }();
     if (min_blocks == 4) {
         launch_pdl(integrate_warped_kernel<true, 4>, grid, dim3(256), 0, s, p);
         launch_pdl(integrate_warped_kernel<false, 4>, grid, dim3(256), 0, s, p);

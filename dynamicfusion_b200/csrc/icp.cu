@@ -16,8 +16,7 @@ using namespace dfb;
 
 int dfb::pdl_enabled()
 {
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("DF_PDL"); v = e ? (atoi(e) != 0) : 1; }
+    static const int v = [] { const char *e = getenv("DF_PDL"); return e ? (int)(atoi(e) != 0) : 1; }();   // thread-safe one-time read
     return v;
 }
 

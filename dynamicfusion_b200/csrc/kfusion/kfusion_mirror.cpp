@@ -344,10 +344,26 @@ void TsdfVolume::setTruncDist(float distance)
     float max_coeff = std::max<float>(std::max<float>(vsz[0], vsz[1]), vsz[2]);
     trunc_dist_ = std::max(distance, 2.1f * max_coeff);
 }
-cv::Mat TsdfVolume::get_cloud_host() const { return *cloud_host_; }
-cv::Mat TsdfVolume::get_normal_host() const { return *normal_host_; }
-cv::Mat* TsdfVolume::get_cloud_host_ptr() const { return cloud_host_; }
-cv::Mat* TsdfVolume::get_normal_host_ptr() const { return normal_host_; }
+// KinFu's view: the frame loop extracted cloud + normals on the device (buffers 9 / 10); the reference's per-frame downloads
+// (compute_points / compute_normals, kinfu.cpp:249-250,398-399) happen here, on first use after a frame
+void TsdfVolume::refresh_host_clouds() const
+{
+    if (!pipeline_ || !host_clouds_stale_) return;
+    host_clouds_stale_ = false;
+    long long info[3];
+    df_kinfu_get_info(pipeline_, info, 3);
+    const int n = (int)info[2];
+    *cloud_host_ = cv::Mat(1, n, CV_32FC4);
+    *normal_host_ = cv::Mat(1, n, CV_32FC4);
+    if (n > 0) {
+        dfSafeCall(df_kinfu_read_buffer(pipeline_, 9, cloud_host_->ptr<Point>(), (size_t)n * sizeof(Point)));
+        dfSafeCall(df_kinfu_read_buffer(pipeline_, 10, normal_host_->ptr<Normal>(), (size_t)n * sizeof(Normal)));
+    }
+}
+cv::Mat TsdfVolume::get_cloud_host() const { refresh_host_clouds(); return *cloud_host_; }
+cv::Mat TsdfVolume::get_normal_host() const { refresh_host_clouds(); return *normal_host_; }
+cv::Mat* TsdfVolume::get_cloud_host_ptr() const { refresh_host_clouds(); return cloud_host_; }
+cv::Mat* TsdfVolume::get_normal_host_ptr() const { refresh_host_clouds(); return normal_host_; }
 int TsdfVolume::getMaxWeight() const { return (int)max_weight_; }
 void TsdfVolume::setMaxWeight(int weight) { max_weight_ = (float)weight; }
 Affine3f TsdfVolume::getPose() const { return pose_; }
@@ -373,8 +389,9 @@ void TsdfVolume::clear()
 void TsdfVolume::integrate(const Dists& dists, const Affine3f& camera_pose, const Intr& intr)
 {
     Affine3f vol2cam = camera_pose.inv() * pose_;
-    dfSafeCall(df_integrate(vol_of(data_, dims_, getVoxelSize(), trunc_dist_, max_weight_), dists.ptr(), dists.step(), dists.cols(), dists.rows(),
-                            to_df(vol2cam), to_df(intr), 0, 0));
+    // activity_ != 0: this is KinFu's view of the frame loop's volume, whose extraction trusts the activity map (dfusion.h)
+    dfSafeCall(df_integrate_tracked(vol_of(data_, dims_, getVoxelSize(), trunc_dist_, max_weight_), dists.ptr(), dists.step(), dists.cols(), dists.rows(),
+                                    to_df(vol2cam), to_df(intr), 0, activity_, 0, 0));
     cudaSafeCall(cudaDeviceSynchronize());                                // the reference's launcher synchronises (tsdf_volume.cu:160)
 }
 // depth variant (tsdf_volume.cu:273-339,441-456): the same march; on a hit the reference stores static_cast<ushort>(vertex.z * 1000) of the
@@ -466,7 +483,7 @@ void TsdfVolume::integrate(const Depth& depth, const WarpField& warp_field, cons
     const Affine3f world2cam = camera_pose.inv() * warp_field.getWarpToLive();       // WarpField::warp applies warp_to_live_ last (warp_field.cpp:191)
     dfSafeCall(df_integrate_warped(vol_of(data_, dims_, getVoxelSize(), trunc_dist_, max_weight_), depth.ptr(), depth.step(), depth.cols(), depth.rows(),
                                    to_df(pose_), to_df(world2cam), to_df(intr), warp_field.deviceNodes(), warp_field.deviceNodeCount(), warp_field.deviceGrid(),
-                                   weight_scale, 0, 0, 0, 0));
+                                   weight_scale, 0, activity_, 0, 0));
     cudaSafeCall(cudaDeviceSynchronize());                                           // as device::integrate does (tsdf_volume.cu:160)
 }
 
@@ -679,7 +696,16 @@ int WarpField::extend(const cv::Mat& cloud, float radius, int step, int max_node
     }
     return Mn;
 }
-void WarpField::clear() {}
+void WarpField::clear()
+{
+    // the reference's clear() is an empty stub (warp_field.cpp:298-301); here it really drops the field, so that a tracking-loss
+    // reset cannot leave a stale field behind (KinFu::reset calls it, kinfu.cpp:206)
+    nodes_->clear();
+    Impl& I = *impl_;
+    if (I.owns) { cudaFree(I.nodes_dev); cudaFree(I.grid_dev); }
+    I.nodes_dev = 0; I.grid_dev = 0; I.M = 0; I.cap = 0; I.owns = true;
+    I.host12.clear();
+}
 void WarpField::setWarpToLive(const Affine3f &pose) { warp_to_live_ = pose; }
 std::vector<float>* WarpField::getDistSquared() const { return &impl_->out_dist_sqr_; }
 std::vector<size_t>* WarpField::getRetIndex() const { return &impl_->ret_index_; }
@@ -716,6 +742,8 @@ void CombinedSolver::solveAll()
     double st[8];
     cudaSafeCall(cudaMemcpy(st, impl_->stats.ptr<void>(), 64, cudaMemcpyDeviceToHost));
     last_cost_ = st[1];
+    if (st[5] != 0.0)
+        std::cerr << "CombinedSolver: a normal-matrix row exceeded the row capacity of df_solve_data_term; the warp field was left unchanged" << std::endl;
     m_warp->downloadTranslations();                                           // copyResultToCPUFromFloat3, CombinedSolver.h:189-197
 }
 WarpFieldOptimiser::WarpFieldOptimiser(WarpField *warp, CombinedSolver *solver) : warp_(warp), solver_(solver) {}
@@ -793,6 +821,8 @@ KinFu::KinFu(const KinFuParams& params) : frame_counter_(0), params_(params), ha
     volume_->setPose(params_.volume_pose);
     volume_->setRaycastStepFactor(params_.raycast_step_factor);
     volume_->setGradientDeltaFactor(params_.gradient_delta_factor);
+    volume_->activity_ = (unsigned char *)buffer_of(handle_, 14);      // the view's integrations stay visible to the loop's extraction
+    volume_->pipeline_ = handle_;
     warp_ = cv::Ptr<WarpField>(new WarpField());
     icp_ = cv::Ptr<cuda::ProjectiveICP>(new cuda::ProjectiveICP());
     icp_->setDistThreshold(params_.icp_dist_thres);
@@ -846,8 +876,13 @@ bool KinFu::operator()(const cuda::Depth& depth, const cuda::Image& /*image*/)
     long long info[10];
     df_kinfu_get_info(handle_, info, 10);
     frame_counter_ = (int)info[0];
+    // the pose chain only grows by one per frame (or restarts after a reset): copy what is new
+    const size_t have = (size_t)info[3] >= poses_.size() && info[6] == resets_seen_ ? poses_.size() : 0;
+    resets_seen_ = info[6];
     poses_.resize((size_t)info[3]);
-    for (size_t i = 0; i < poses_.size(); ++i) { float p[12]; df_kinfu_get_pose(handle_, (int)i, p); poses_[i] = from12(p); }
+    for (size_t i = have ? have - 1 : 0; i < poses_.size(); ++i) { float p[12]; df_kinfu_get_pose(handle_, (int)i, p); poses_[i] = from12(p); }
+    volume_->host_clouds_stale_ = true;                                // get_cloud_host() / get_normal_host() fetch the frame's extraction on demand
+    if (info[1] == 0 && warp_->deviceNodeCount() != 0) warp_->clear();  // the loop dropped its field (tracking-loss reset)
     if (info[1] > 0 && warp_->deviceNodeCount() != (int)info[1]) {       // nodes were (re)initialised on the device: adopt them
         size_t pitch; int cols, rows;
         float *nodes = (float *)buffer_of(handle_, 11, &pitch, &cols, &rows);

@@ -234,10 +234,10 @@ extern "C" int df_build_node_grid(const float *nodes, int M, void *grid, void *s
     const int L = bvh_leaves(M);
     float4 *bvh_box = want_order ? reinterpret_cast<float4 *>(tail - bvh_bytes(M)) : nullptr;      // 16-byte aligned: every block above is
     float4 *bvh_leaf = want_order ? bvh_box + 4 * (size_t)L : nullptr;
-    static float spacings = 0.f;                              // node spacings per cell (default 3, see the kernel); DF_NODEGRID_SPACINGS overrides
-    if (spacings == 0.f) { const char *e = getenv("DF_NODEGRID_SPACINGS"); spacings = e ? (float)atof(e) : 3.0f; if (!(spacings >= 0.5f)) spacings = 3.0f; }
-    static int kd_leaves = -1;                                // BVH leaf membership: 1 = k-d median split (default), 0 = runs of the Morton order (first version); DF_BVH_KD
-    if (kd_leaves < 0) { const char *e = getenv("DF_BVH_KD"); kd_leaves = e ? (atoi(e) != 0) : 1; }
+    // node spacings per cell (default 3, see the kernel); DF_NODEGRID_SPACINGS overrides
+    static const float spacings = [] { const char *e = getenv("DF_NODEGRID_SPACINGS"); const float v = e ? (float)atof(e) : 3.0f; return v >= 0.5f ? v : 3.0f; }();
+    // BVH leaf membership: 1 = k-d median split (default), 0 = runs of the Morton order (first version); DF_BVH_KD
+    static const int kd_leaves = [] { const char *e = getenv("DF_BVH_KD"); return e ? (int)(atoi(e) != 0) : 1; }();
     build_node_grid_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(nodes, M, grid, cid_tmp, order, slot, bvh_box, bvh_leaf, L, spacings, kd_leaves);
     DF_LAUNCH_CHECK();
     return 0;

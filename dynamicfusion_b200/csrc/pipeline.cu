@@ -43,6 +43,7 @@ struct KinFu {
     float *pinned = nullptr;             // 16 floats: T(12) + ok
     std::vector<float> poses;            // 12 floats per pose
     int frame_counter = 0, resets = 0, last_ok = 1, launches = 0;
+    long long solve_overflows = 0;       // frames whose solve was skipped because a normal-matrix row overflowed (solve.cu ROWCAP); info[11]
     long long last_cloud = -1;
     double host_us[4] = {0, 0, 0, 0}; long long host_frames = 0;   // DF_KINFU_HOSTPROF: launch A, ICP wait, launch B, total
     unsigned long long *n_upd = nullptr;   // voxels written by the last integrate (filled when DF_KINFU_STAGE_TIMING)
@@ -135,11 +136,26 @@ int do_reset(KinFu &k)
 {
     if (k.frame_counter) { printf("Reset\n"); ++k.resets; }          // kinfu.cpp:198-199
     k.frame_counter = 0;
+    k.M = 0;                                                         // warp_->clear(), kinfu.cpp:206: the next first frame re-initialises the field
     k.poses.clear();
     k.poses.resize(12);
     dfh_aff_identity(k.poses.data());
     if (k.activity && cudaMemsetAsync(k.activity, 0, k.activity_bytes, k.stream) != cudaSuccess) return (int)cudaGetLastError();
     return df_clear_volume(vol_of(k), k.stream);
+}
+
+// A normal-matrix row that does not fit (solve.cu: more than ROWCAP coupled columns) makes the solve leave the warp field unchanged for
+// that frame and raise stats[5]; the flag is copied to pinned memory after every solve and reported here, loudly, at the next sync.
+void note_solve_overflow(KinFu &k)
+{
+    double f;
+    memcpy(&f, k.pinned + 14, sizeof f);
+    if (f != 0.0) {
+        ++k.solve_overflows;
+        fprintf(stderr, "df_kinfu: warp solve skipped for one frame: a normal-matrix row exceeded the row capacity (df_kinfu_get_info[11] = %lld)\n", k.solve_overflows);
+        f = 0.0;
+        memcpy(k.pinned + 14, &f, sizeof f);
+    }
 }
 
 static inline double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -276,6 +292,7 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_d
         int ok;
         memcpy(&ok, k.pinned + 12, sizeof(int));
         k.last_ok = ok;
+        note_solve_overflow(k);                                       // the previous frame's solve flag arrived with this sync
         if (!ok) { CKD(do_reset(k)); return 0; }                      // kinfu.cpp:276-277
     }
     mark(k, 2);
@@ -304,6 +321,8 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_d
                                p.solver_nonlinear_iters, p.solver_linear_iters,
                                (p.flags & DF_KINFU_REF_GRAPH_QUIRK) ? DF_SOLVE_REF_GRAPH_QUIRK : 0, k.solve_stats, k.solve_ws, s));   // :387
         k.launches += 5;                                               // prepare, scan, fill, rows, lm
+        // row-overflow flag of this solve (stats[5]): lands in pinned memory, looked at after the next stream synchronisation
+        CK(cudaMemcpyAsync(k.pinned + 14, k.solve_stats + 5, sizeof(double), cudaMemcpyDeviceToHost, s));
         mark(k, 5);
         {
             // second warp (:389) queries exactly the vertices the solve just built its graph for (CombinedSolver.h:66-84):
@@ -397,6 +416,8 @@ extern "C" void df_kinfu_default_params(df_kinfu_params *p, int which)
     p->flags = 0;
 }
 
+extern "C" void df_kinfu_destroy(void *kinfu);
+
 extern "C" void *df_kinfu_create(const df_kinfu_params *pp)
 {
     if (pp->volume_dims[0] % 32 != 0) {                               // CV_Assert, kinfu.cpp:97
@@ -452,9 +473,14 @@ extern "C" void *df_kinfu_create(const df_kinfu_params *pp)
     ok = ok && cudaMalloc(&k->project_ws, df_project_workspace_bytes(p.cols, p.rows)) == cudaSuccess;
     ok = ok && cudaMemset(k->project_ws, 0, df_project_workspace_bytes(p.cols, p.rows)) == cudaSuccess;
     ok = ok && cudaMemset(k->solve_stats, 0, 64) == cudaSuccess && cudaMemset(k->cloud_count, 0, 64) == cudaSuccess;
-    ok = ok && cudaMallocHost(&k->pinned, 64) == cudaSuccess && cudaMalloc(&k->n_upd, 64) == cudaSuccess && cudaMemset(k->n_upd, 0, 64) == cudaSuccess;
+    ok = ok && cudaMallocHost(&k->pinned, 64) == cudaSuccess && (memset(k->pinned, 0, 64), true) && cudaMalloc(&k->n_upd, 64) == cudaSuccess && cudaMemset(k->n_upd, 0, 64) == cudaSuccess;
+    for (int e = 0; e <= NSTAGES; ++e) k->ev[e] = nullptr;
     for (int e = 0; e <= NSTAGES && ok; ++e) ok = cudaEventCreate(&k->ev[e]) == cudaSuccess;
-    if (!ok) { fprintf(stderr, "df_kinfu_create: CUDA allocation failed: %s\n", cudaGetErrorString(cudaGetLastError())); delete k; return nullptr; }
+    if (!ok) {
+        fprintf(stderr, "df_kinfu_create: CUDA allocation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+        df_kinfu_destroy(k);                                          // frees whatever was allocated (cudaFree(nullptr) is a no-op)
+        return nullptr;
+    }
     memset(k->stage_ms, 0, sizeof k->stage_ms);
     do_reset(*k);
     cudaStreamSynchronize(k->stream);
@@ -475,7 +501,7 @@ extern "C" void df_kinfu_destroy(void *h)
     cudaFree(k->cloud); cudaFree(k->cloud_nrm); cudaFree(k->cloud_count); cudaFree(k->nodes); cudaFree(k->node_grid);
     cudaFree(k->icp_T); cudaFree(k->icp_ok); cudaFree(k->icp_scratch); cudaFree(k->solve_ws); cudaFree(k->solve_stats);
     cudaFree(k->extract_ws); cudaFree(k->project_ws); cudaFree(k->activity); cudaFree(k->integrate_ws); cudaFree(k->fusion_ws); cudaFree(k->extend_ws); cudaFree(k->M_dev); cudaFreeHost(k->pinned); cudaFree(k->n_upd);
-    for (int e = 0; e <= NSTAGES; ++e) cudaEventDestroy(k->ev[e]);
+    for (int e = 0; e <= NSTAGES; ++e) if (k->ev[e]) cudaEventDestroy(k->ev[e]);
     delete k;
 }
 
@@ -528,6 +554,7 @@ extern "C" int df_kinfu_process_host(void *h, const uint16_t *depth_host, size_t
     const int r = process(*k, (const uint16_t *)k->depth_in.ptr, k->depth_in.pitch);
     if (r < 0) return r;
     e = cudaStreamSynchronize(k->stream);        // the caller owns the result when the call returns (renderImage / getCameraPose next)
+    if (e == cudaSuccess) note_solve_overflow(*k);
     finish_timing(*k);
     return e == cudaSuccess ? r : -(int)e;
 }
@@ -558,9 +585,10 @@ extern "C" int df_kinfu_get_info(void *h, long long *info, int n)
     cudaMemcpyAsync(nu2, k->n_upd, 16, cudaMemcpyDeviceToHost, k->stream);
     cudaStreamSynchronize(k->stream);
     const unsigned long long nu = nu2[0];
-    const long long vals[11] = {k->frame_counter, k->M, k->last_cloud, (long long)(k->poses.size() / 12), k->last_ok, k->launches, k->resets,
-                                (long long)st[2], (long long)nu, (long long)st[4], (long long)nu2[1]};
-    for (int i = 0; i < n && i < 11; ++i) info[i] = vals[i];
+    note_solve_overflow(*k);
+    const long long vals[12] = {k->frame_counter, k->M, k->last_cloud, (long long)(k->poses.size() / 12), k->last_ok, k->launches, k->resets,
+                                (long long)st[2], (long long)nu, (long long)st[4], (long long)nu2[1], k->solve_overflows};
+    for (int i = 0; i < n && i < 12; ++i) info[i] = vals[i];
     return 0;
 }
 
@@ -583,6 +611,7 @@ extern "C" int df_kinfu_get_buffer(void *h, int which, void **ptr, size_t *pitch
         case 11: im.ptr = k->nodes; im.pitch = DF_NODE_STRIDE * 4; im.cols = 1; im.rows = k->M; break;
         case 12: im = k->canon_visible; break;
         case 13: im.ptr = k->solve_stats; im.pitch = 64; im.cols = 8; im.rows = 1; break;
+        case 14: im.ptr = k->activity; im.pitch = k->activity_bytes; im.cols = (int)k->activity_bytes; im.rows = 1; break;
         default: return (int)cudaErrorInvalidValue;
     }
     *ptr = im.ptr; *pitch = im.pitch; *cols = im.cols; *rows = im.rows;

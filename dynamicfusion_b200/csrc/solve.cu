@@ -392,6 +392,7 @@ __global__ void __launch_bounds__(LM_THREADS) solve_lm_kernel(float *nodes, int 
 
     double radius = 1e4, decrease = 2.0;          // solverGPUGaussNewton.t:26-39
     int it = 0, pcg_total = 0;
+    if (ws.flags[0]) nl_iters = 0;                // a row overflowed: leave the field unchanged (see solve_lm_v5_kernel)
     for (; it < nl_iters; ++it) {
         // g = gb - A x
         spmv(ws, M, x, Ap);
@@ -487,538 +488,14 @@ __global__ void __launch_bounds__(LM_THREADS) solve_lm_kernel(float *nodes, int 
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// LM / PCG on ONE THREAD-BLOCK CLUSTER (8 CTAs x 1024 threads on 8 SMs).  The linear system is tiny (M x M sparse,
-// ~2e5 non-zeros, L2-resident) and every PCG iteration needs two global dot products, so the iteration is bound by
-// barrier + reduction latency, not by bandwidth.  A whole-grid cooperative barrier costs microseconds; the cluster's
-// hardware barrier costs a few hundred cycles and the partial sums are exchanged through distributed shared memory,
-// so a PCG iteration is ~3 cluster barriers + one sparse mat-vec spread over 8192 threads (several threads per row,
-// combined with warp shuffles).  All sums are formed in a fixed order => every CTA sees bit-identical scalars and takes
-// the same branches; the result is deterministic for a given normal matrix.
+// LM / PCG on ONE THREAD-BLOCK CLUSTER.  The linear system is tiny (M x M sparse, ~1e5 non-zeros) and every PCG iteration needs
+// global dot products, so the iteration is bound by exchange latency, not by bandwidth.  History (profiles/): v1 = the
+// one-block kernel above (kept as the fallback for systems that do not fit a cluster's shared memory); v2 = 8-CTA cluster, vectors
+// through L2; v3 = matrix + vectors in shared memory, DSMEM pushes; v4 = CG vectors in registers, Morton row order + need-mask, one
+// cluster barrier per sum; v5 (below, the only cluster version left in the tree) = v4 with transaction barriers.
 constexpr int LMC_CTAS = 8;
 
-struct ClusterRed {
-    double part[2][4];       // this CTA's partial sums, double-buffered by reduction parity
-    double warp[32][4];
-    double bcast[4];
-};
-
-template <int NV>
-__device__ __forceinline__ void cluster_sum(cg::cluster_group &cluster, ClusterRed &sm, int &parity, double (&v)[NV])
-{
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-    for (int k = 0; k < NV; ++k)
-        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < NV; ++k) sm.warp[warp][k] = v[k];
-    }
-    __syncthreads();
-    if (warp == 0) {
-#pragma unroll
-        for (int k = 0; k < NV; ++k) {
-            double t = lane < (int)(blockDim.x >> 5) ? sm.warp[lane][k] : 0.0;
-            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-            if (lane == 0) sm.part[parity][k] = t;
-        }
-    }
-    cluster.sync();                                            // partials of all CTAs visible (release/acquire, cluster scope)
-    if (warp == 0) {
-#pragma unroll
-        for (int k = 0; k < NV; ++k) {
-            double t = 0.0;
-            if (lane < LMC_CTAS) {
-                const double *remote = cluster.map_shared_rank(&sm.part[parity][k], lane);
-                t = *remote;
-            }
-            for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);   // lanes 0..7, fixed tree
-            if (lane == 0) sm.bcast[k] = t;
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < NV; ++k) v[k] = sm.bcast[k];
-    parity ^= 1;
-    __syncthreads();
-}
-
-__global__ void __cluster_dims__(LMC_CTAS, 1, 1) __launch_bounds__(LM_THREADS)
-solve_lm_cluster_kernel(float *nodes, int M, SolveWs ws, int nl_iters, int lin_iters, double *stats, int use_smem)
-{
-    cg::cluster_group cluster = cg::this_cluster();
-    __shared__ ClusterRed sm;
-    int parity = 0;
-    const int T = LMC_CTAS * LM_THREADS;
-    const int gt = (int)cluster.block_rank() * LM_THREADS + threadIdx.x;
-    int tpr = 1;                                               // threads per row: power of two, <= 32, tpr * M <= T when possible
-    while (tpr < 32 && tpr * 2 * M <= T) tpr *= 2;
-    const int rpp = T / tpr;                                   // rows per pass
-    const int row0 = gt / tpr, sub = gt % tpr;
-    const bool owner = sub == 0;
-    const int M3 = 3 * M;
-    double *x = ws.vec, *g = x + M3, *dl = g + M3, *r = dl + M3, *z = r + M3, *p = z + M3, *Ap = p + M3;
-    double *cd = ws.cd, *minv = ws.minv;                       // per-LM-iteration damping and Jacobi preconditioner
-
-    // sparse mat-vec for this thread's rows: out (owner lanes) = A * in.  `in` was written by other SMs: every CTA first
-    // stages the whole vector (3M doubles, 49 KB at M = 2k) from L2 into its shared memory with coalesced loads, so the
-    // per-entry gathers cost a shared-memory access instead of an L2 round trip each.
-    extern __shared__ double svec[];
-    auto spmv = [&](const double *in, double *out) {
-        const double *src = in;
-        if (use_smem) {
-            for (int i = threadIdx.x; i < M3; i += LM_THREADS) svec[i] = __ldcg(in + i);
-            __syncthreads();
-            src = svec;
-        }
-        for (int base = 0; base < M; base += rpp) {           // uniform trip count: the shuffles below need the whole warp
-            const int n = base + row0;
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-            const int nnz = n < M ? ws.rownnz[n] : 0;
-            int e = sub;
-            for (; e + 3 * tpr < nnz; e += 4 * tpr) {          // 4 independent entries in flight
-                const int j0 = __ldg(ws.col + (size_t)e * M + n), j1 = __ldg(ws.col + (size_t)(e + tpr) * M + n);
-                const int j2 = __ldg(ws.col + (size_t)(e + 2 * tpr) * M + n), j3 = __ldg(ws.col + (size_t)(e + 3 * tpr) * M + n);
-                const double v0 = __ldg(ws.val + (size_t)e * M + n), v1 = __ldg(ws.val + (size_t)(e + tpr) * M + n);
-                const double v2 = __ldg(ws.val + (size_t)(e + 2 * tpr) * M + n), v3 = __ldg(ws.val + (size_t)(e + 3 * tpr) * M + n);
-                if (use_smem) {
-                    a0 += v0 * src[j0]; a1 += v0 * src[M + j0]; a2 += v0 * src[2 * M + j0];
-                    a0 += v1 * src[j1]; a1 += v1 * src[M + j1]; a2 += v1 * src[2 * M + j1];
-                    a0 += v2 * src[j2]; a1 += v2 * src[M + j2]; a2 += v2 * src[2 * M + j2];
-                    a0 += v3 * src[j3]; a1 += v3 * src[M + j3]; a2 += v3 * src[2 * M + j3];
-                } else {
-                    a0 += v0 * __ldcg(in + j0); a1 += v0 * __ldcg(in + M + j0); a2 += v0 * __ldcg(in + 2 * M + j0);
-                    a0 += v1 * __ldcg(in + j1); a1 += v1 * __ldcg(in + M + j1); a2 += v1 * __ldcg(in + 2 * M + j1);
-                    a0 += v2 * __ldcg(in + j2); a1 += v2 * __ldcg(in + M + j2); a2 += v2 * __ldcg(in + 2 * M + j2);
-                    a0 += v3 * __ldcg(in + j3); a1 += v3 * __ldcg(in + M + j3); a2 += v3 * __ldcg(in + 2 * M + j3);
-                }
-            }
-            for (; e < nnz; e += tpr) {
-                const int j = __ldg(ws.col + (size_t)e * M + n);
-                const double a = __ldg(ws.val + (size_t)e * M + n);
-                if (use_smem) { a0 += a * src[j]; a1 += a * src[M + j]; a2 += a * src[2 * M + j]; }
-                else { a0 += a * __ldcg(in + j); a1 += a * __ldcg(in + M + j); a2 += a * __ldcg(in + 2 * M + j); }
-            }
-            for (int o = tpr >> 1; o > 0; o >>= 1) {
-                a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-            }
-            if (owner && n < M) { out[n] = a0; out[M + n] = a1; out[2 * M + n] = a2; }
-        }
-    };
-
-    // x0 = current node translations (CombinedSolver.h:165-172)
-    if (owner)
-        for (int n = row0; n < M; n += rpp) {
-            const float4 *n4 = reinterpret_cast<const float4 *>(nodes + (size_t)n * DF_NODE_STRIDE);
-            const float4 a = n4[0], b = n4[1], c = n4[2];
-            const Quat t = dq_translation(Quat{a.w, b.x, b.y, b.z}, Quat{b.w, c.x, c.y, c.z});
-            x[n] = t.x; x[M + n] = t.y; x[2 * M + n] = t.z;
-        }
-    double c0n[3] = {0.0, 0.0, 0.0};
-    for (int i = gt; i < ws.prepare_blocks * (PREPARE_THREADS / 32); i += T) { c0n[0] += ws.c0_partials[2 * i]; c0n[1] += ws.c0_partials[2 * i + 1]; }
-    for (int n = gt; n < M; n += T) c0n[2] += (double)ws.rownnz[n];
-    cluster_sum(cluster, sm, parity, c0n);                     // also publishes x
-    const double nvalid = c0n[1], nnz_total = c0n[2];
-    spmv(x, Ap);
-    double t0[1] = {0.0};
-    if (owner)
-        for (int n = row0; n < M; n += rpp)
-            for (int d = 0; d < 3; ++d) t0[0] += x[d * M + n] * (0.5 * Ap[d * M + n] - ws.gb[d * M + n]);
-    cluster_sum(cluster, sm, parity, t0);
-    double cost = c0n[0] + t0[0];
-    const double cost0 = cost;
-
-    double radius = 1e4, decrease = 2.0;                       // solverGPUGaussNewton.t:26-39
-    int it = 0, pcg_total = 0;
-    for (; it < nl_iters; ++it) {
-        spmv(x, Ap);                                           // x was published by the previous cluster barrier
-        double rzv[1] = {0.0};
-        if (owner)
-            for (int n = row0; n < M; n += rpp) {
-                const double dgn = ws.diag[n];
-                const double cdn = fmin(fmax(dgn, 1e-6), 1e32) / radius;
-                const double mi = 1.0 / (dgn + cdn);
-                cd[n] = cdn; minv[n] = mi;
-                for (int d = 0; d < 3; ++d) {
-                    const int i = d * M + n;
-                    const double gi = ws.gb[i] - Ap[i];
-                    g[i] = gi; dl[i] = 0.0; r[i] = gi;
-                    const double zi = gi * mi;
-                    z[i] = zi; p[i] = zi;
-                    rzv[0] += gi * zi;
-                }
-            }
-        cluster_sum(cluster, sm, parity, rzv);                 // publishes p
-        double rz = rzv[0];
-        double Q0 = 0.0;
-        for (int l = 0; l < lin_iters && rz > 0.0; ++l) {
-            spmv(p, Ap);
-            double pap[1] = {0.0};
-            if (owner)
-                for (int n = row0; n < M; n += rpp)
-                    for (int d = 0; d < 3; ++d) {
-                        const int i = d * M + n;
-                        const double ap = Ap[i] + cd[n] * p[i];
-                        Ap[i] = ap;
-                        pap[0] += p[i] * ap;
-                    }
-            cluster_sum(cluster, sm, parity, pap);
-            if (!(pap[0] > 0.0)) break;
-            const double alpha = rz / pap[0];
-            double rq[2] = {0.0, 0.0};
-            if (owner)
-                for (int n = row0; n < M; n += rpp)
-                    for (int d = 0; d < 3; ++d) {
-                        const int i = d * M + n;
-                        const double dli = dl[i] + alpha * p[i];
-                        const double ri = r[i] - alpha * Ap[i];
-                        const double zi = ri * minv[n];
-                        dl[i] = dli; r[i] = ri; z[i] = zi;
-                        rq[0] += ri * zi;
-                        rq[1] += dli * (ri + g[i]);
-                    }
-            cluster_sum(cluster, sm, parity, rq);
-            const double rz_new = rq[0], Q1 = -0.5 * rq[1];
-            const double beta = rz_new / rz;
-            if (owner)
-                for (int n = row0; n < M; n += rpp)
-                    for (int d = 0; d < 3; ++d) { const int i = d * M + n; p[i] = z[i] + beta * p[i]; }
-            rz = rz_new;
-            ++pcg_total;
-            const double zeta = (double)(l + 1) * (Q1 - Q0) / Q1;   // Ceres/Opt q-tolerance, solverGPUGaussNewton.t:1093-1101
-            Q0 = Q1;
-            cluster.sync();                                    // publish p for the next mat-vec
-            if (zeta < 1e-4) break;
-        }
-        // model change = 0.5 dl.(g + r + C dl);  A dl = g - r - C dl  => new cost = cost - dl.g + 0.5 dl.(A dl)
-        double mad[3] = {0.0, 0.0, 0.0};
-        if (owner)
-            for (int n = row0; n < M; n += rpp)
-                for (int d = 0; d < 3; ++d) {
-                    const int i = d * M + n;
-                    const double c = cd[n] * dl[i];
-                    mad[0] += dl[i] * (g[i] + r[i] + c);
-                    mad[1] += dl[i] * (g[i] - r[i] - c);
-                    mad[2] += dl[i] * g[i];
-                }
-        cluster_sum(cluster, sm, parity, mad);
-        const double model = 0.5 * mad[0];
-        const double new_cost = cost - mad[2] + 0.5 * mad[1];
-        const double change = cost - new_cost;
-        const double rho = model > 0.0 ? change / model : 0.0;
-        bool stop = false;
-        if (change >= 0.0 && rho > 1e-3) {
-            if (owner)
-                for (int n = row0; n < M; n += rpp)
-                    for (int d = 0; d < 3; ++d) x[d * M + n] += dl[d * M + n];
-            stop = change <= cost * 1e-6;                       // function_tolerance, CombinedSolver.h:88
-            cost = new_cost;
-            const double f = 1.0 - (2.0 * rho - 1.0) * (2.0 * rho - 1.0) * (2.0 * rho - 1.0);
-            radius /= fmax(f, 1.0 / 3.0);
-            radius = fmin(radius, 1e16);
-            decrease = 2.0;
-        } else {
-            radius /= decrease; decrease *= 2.0;
-            if (radius <= 1e-32) stop = true;
-        }
-        cluster.sync();                                        // publish x
-        if (stop) { ++it; break; }
-    }
-    // write back: encodeTranslation (CombinedSolver.h:189-197, dual_quaternion.hpp:82-85)
-    if (owner)
-        for (int n = row0; n < M; n += rpp) {
-            float *nd = nodes + (size_t)n * DF_NODE_STRIDE;
-            const Quat rot = {nd[3], nd[4], nd[5], nd[6]};
-            const Quat h = qhalf(Quat{0.f, (float)x[n], (float)x[M + n], (float)x[2 * M + n]});
-            const Quat d = qmul(h, rot);
-            nd[7] = d.w; nd[8] = d.x; nd[9] = d.y; nd[10] = d.z;
-        }
-    if (gt == 0 && stats) {
-        stats[0] = cost0; stats[1] = cost; stats[2] = (double)it; stats[3] = nvalid; stats[4] = (double)pcg_total; stats[5] = (double)ws.flags[0];
-        stats[6] = nnz_total;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// v3: the same LM/PCG, with EVERYTHING the iteration touches resident on-chip for the whole solve:
-//   * each CTA owns a contiguous block of rows; its slice of the sparse matrix (packed per thread), its slices of the CG
-//     vectors (x, g, dl, r, z, p, Ap, damping, preconditioner) live in its shared memory;
-//   * the search direction p is the only vector other CTAs need: after updating its rows an owner thread PUSHES its three
-//     values into every CTA's full-length copy through distributed shared memory (no L2 round trip);
-//   * dot products: warp shuffles -> CTA partial in shared memory -> one cluster barrier -> 8 DSMEM reads, fixed order.
-// A PCG iteration is then 3 cluster barriers + shared-memory traffic only (measured: see profiles/).  ncu of v2 showed the
-// iteration was latency-bound on L2 round trips (issue-active 29 %, 27 cycles/instruction) with a 56 k-nonzero matrix.
-constexpr int LM3_THREADS = 512;   // v3: 512 threads x 128 registers -- no spills (local memory is an L2 round trip after every cluster barrier's L1 flush)
-
-struct LmSmemLayout {
-    int rpc;            // rows per CTA
-    int tpr;            // threads per row
-    int ent_cap;        // matrix entries per thread kept in shared memory
-    size_t off_svec, off_loc, off_col, off_val, total;
-};
-
-__host__ __device__ inline LmSmemLayout lm_layout(int M, int ent_cap)
-{
-    LmSmemLayout L;
-    L.rpc = (M + LMC_CTAS - 1) / LMC_CTAS;
-    L.tpr = 1;
-    while (L.tpr < 32 && L.tpr * 2 * L.rpc <= LM3_THREADS) L.tpr *= 2;
-    L.ent_cap = ent_cap;
-    size_t o = 0;
-    L.off_svec = o; o += (size_t)3 * M * 8;
-    L.off_loc = o; o += (size_t)(7 * 3 + 2) * L.rpc * 8;          // x g dl r z p Ap (3 each) + cd + minv
-    L.off_val = o; o += (size_t)L.ent_cap * LM3_THREADS * 8;
-    L.off_col = o; o += (size_t)L.ent_cap * LM3_THREADS * 4;
-    L.total = o;
-    return L;
-}
-
-__global__ void __cluster_dims__(LMC_CTAS, 1, 1) __launch_bounds__(LM3_THREADS)
-solve_lm_cluster_smem_kernel(float *nodes, int M, SolveWs ws, int nl_iters, int lin_iters, double *stats, int ent_cap)
-{
-    cg::cluster_group cluster = cg::this_cluster();
-    __shared__ ClusterRed sm;
-    extern __shared__ __align__(16) unsigned char dyn[];
-    const LmSmemLayout L = lm_layout(M, ent_cap);
-    double *svec = reinterpret_cast<double *>(dyn + L.off_svec);          // full-length copy of the vector being multiplied
-    double *loc = reinterpret_cast<double *>(dyn + L.off_loc);
-    double *mval = reinterpret_cast<double *>(dyn + L.off_val);           // [ent][thread]
-    int *mcol = reinterpret_cast<int *>(dyn + L.off_col);
-    const int rpc = L.rpc, tpr = L.tpr, R3 = 3 * rpc;
-    double *x = loc, *g = x + R3, *dl = g + R3, *r = dl + R3, *z = r + R3, *p = z + R3, *Ap = p + R3, *cd = Ap + R3, *minv = cd + rpc;
-
-    int parity = 0;
-    const int cta = (int)cluster.block_rank();
-    const int tid = threadIdx.x;
-    const int rl = tid / tpr, sub = tid % tpr;                 // local row, lane within the row
-    const int n = cta * rpc + rl;                              // global row
-    const bool has_row = rl < rpc && n < M;
-    const bool owner = has_row && sub == 0;
-    const int M3 = 3 * M;
-
-    // matrix slice -> shared memory (once)
-    const int nnz = has_row ? ws.rownnz[n] : 0;
-    int my_ent = 0;                                            // entries of this thread kept in shared memory (the first ent_cap)
-    for (int e = sub; e < nnz && my_ent < ent_cap; e += tpr, ++my_ent) {
-        mcol[my_ent * LM3_THREADS + tid] = ws.col[(size_t)e * M + n];
-        mval[my_ent * LM3_THREADS + tid] = ws.val[(size_t)e * M + n];
-    }
-    const int e_rest = sub + my_ent * tpr;                     // first entry that did not fit: streamed from L2 every time
-    const double diag_n = has_row ? ws.diag[n] : 0.0;
-    double gbn[3] = {0.0, 0.0, 0.0};
-    if (owner) { gbn[0] = ws.gb[n]; gbn[1] = ws.gb[M + n]; gbn[2] = ws.gb[2 * M + n]; }
-
-    // push this row's three values of a local vector into every CTA's svec
-    auto publish = [&](const double *v) {
-        if (owner) {
-            const double a0 = v[rl], a1 = v[rpc + rl], a2 = v[2 * rpc + rl];
-#pragma unroll
-            for (int c = 0; c < LMC_CTAS; ++c) {
-                double *remote = cluster.map_shared_rank(svec, c);
-                remote[n] = a0; remote[M + n] = a1; remote[2 * M + n] = a2;
-            }
-        }
-    };
-    // out (owner's local vector) = A * svec for this thread's row
-    auto spmv = [&](double *out) {
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-        for (int k = 0; k < my_ent; ++k) {
-            const int j = mcol[k * LM3_THREADS + tid];
-            const double a = mval[k * LM3_THREADS + tid];
-            a0 += a * svec[j]; a1 += a * svec[M + j]; a2 += a * svec[2 * M + j];
-        }
-        for (int e = e_rest; e < nnz; e += tpr) {
-            const int j = __ldg(ws.col + (size_t)e * M + n);
-            const double a = __ldg(ws.val + (size_t)e * M + n);
-            a0 += a * svec[j]; a1 += a * svec[M + j]; a2 += a * svec[2 * M + j];
-        }
-        for (int o = tpr >> 1; o > 0; o >>= 1) {
-            a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-        }
-        if (owner) { out[rl] = a0; out[rpc + rl] = a1; out[2 * rpc + rl] = a2; }
-    };
-
-    // x0 = current node translations (CombinedSolver.h:165-172)
-    if (owner) {
-        const float4 *n4 = reinterpret_cast<const float4 *>(nodes + (size_t)n * DF_NODE_STRIDE);
-        const float4 a = n4[0], b = n4[1], c = n4[2];
-        const Quat t = dq_translation(Quat{a.w, b.x, b.y, b.z}, Quat{b.w, c.x, c.y, c.z});
-        x[rl] = t.x; x[rpc + rl] = t.y; x[2 * rpc + rl] = t.z;
-    }
-    const int T = LMC_CTAS * LM3_THREADS, gt = cta * LM3_THREADS + tid;
-    double c0n[3] = {0.0, 0.0, 0.0};
-    for (int i = gt; i < ws.prepare_blocks * (PREPARE_THREADS / 32); i += T) { c0n[0] += ws.c0_partials[2 * i]; c0n[1] += ws.c0_partials[2 * i + 1]; }
-    c0n[2] = (owner ? (double)nnz : 0.0);
-    cluster.sync();                                            // every CTA is running: remote shared memory may be written
-    publish(x);
-    cluster_sum(cluster, sm, parity, c0n);                     // its barrier also completes the publish
-    const double nvalid = c0n[1], nnz_total = c0n[2];
-    spmv(Ap);
-    double t0[1] = {0.0};
-    if (owner)
-        for (int d = 0; d < 3; ++d) t0[0] += x[d * rpc + rl] * (0.5 * Ap[d * rpc + rl] - gbn[d]);
-    cluster_sum(cluster, sm, parity, t0);
-    double cost = c0n[0] + t0[0];
-    const double cost0 = cost;
-
-    double radius = 1e4, decrease = 2.0;                       // solverGPUGaussNewton.t:26-39
-    int it = 0, pcg_total = 0;
-    for (; it < nl_iters; ++it) {
-        spmv(Ap);                                              // svec holds x here
-        double rzv[1] = {0.0};
-        if (owner) {
-            const double cdn = fmin(fmax(diag_n, 1e-6), 1e32) / radius;
-            const double mi = 1.0 / (diag_n + cdn);
-            cd[rl] = cdn; minv[rl] = mi;
-            for (int d = 0; d < 3; ++d) {
-                const int i = d * rpc + rl;
-                const double gi = gbn[d] - Ap[i];
-                g[i] = gi; dl[i] = 0.0; r[i] = gi;
-                const double zi = gi * mi;
-                z[i] = zi; p[i] = zi;
-                rzv[0] += gi * zi;
-            }
-        }
-        __syncthreads();                                       // all spmv reads of svec (x) done in this CTA ...
-        cluster.sync();                                        // ... and in every other CTA, before p overwrites it
-        publish(p);
-        cluster_sum(cluster, sm, parity, rzv);
-        double rz = rzv[0];
-        double Q0 = 0.0;
-        for (int l = 0; l < lin_iters && rz > 0.0; ++l) {
-            spmv(Ap);
-            double pap[1] = {0.0};
-            if (owner)
-                for (int d = 0; d < 3; ++d) {
-                    const int i = d * rpc + rl;
-                    const double ap = Ap[i] + cd[rl] * p[i];
-                    Ap[i] = ap;
-                    pap[0] += p[i] * ap;
-                }
-            cluster_sum(cluster, sm, parity, pap);             // barrier: every CTA finished reading svec (p)
-            if (!(pap[0] > 0.0)) break;
-            const double alpha = rz / pap[0];
-            double rq[2] = {0.0, 0.0};
-            double znew[3] = {0.0, 0.0, 0.0};
-            if (owner)
-                for (int d = 0; d < 3; ++d) {
-                    const int i = d * rpc + rl;
-                    const double dli = dl[i] + alpha * p[i];
-                    const double ri = r[i] - alpha * Ap[i];
-                    const double zi = ri * minv[rl];
-                    dl[i] = dli; r[i] = ri; z[i] = zi; znew[d] = zi;
-                    rq[0] += ri * zi;
-                    rq[1] += dli * (ri + g[i]);
-                }
-            cluster_sum(cluster, sm, parity, rq);
-            const double rz_new = rq[0], Q1 = -0.5 * rq[1];
-            const double beta = rz_new / rz;
-            if (owner)
-                for (int d = 0; d < 3; ++d) { const int i = d * rpc + rl; p[i] = znew[d] + beta * p[i]; }
-            rz = rz_new;
-            ++pcg_total;
-            const double zeta = (double)(l + 1) * (Q1 - Q0) / Q1;   // Ceres/Opt q-tolerance, solverGPUGaussNewton.t:1093-1101
-            Q0 = Q1;
-            publish(p);
-            cluster.sync();                                    // publish complete everywhere
-            if (zeta < 1e-4) break;
-        }
-        // model change = 0.5 dl.(g + r + C dl);  A dl = g - r - C dl  => new cost = cost - dl.g + 0.5 dl.(A dl)
-        double mad[3] = {0.0, 0.0, 0.0};
-        if (owner)
-            for (int d = 0; d < 3; ++d) {
-                const int i = d * rpc + rl;
-                const double c = cd[rl] * dl[i];
-                mad[0] += dl[i] * (g[i] + r[i] + c);
-                mad[1] += dl[i] * (g[i] - r[i] - c);
-                mad[2] += dl[i] * g[i];
-            }
-        cluster_sum(cluster, sm, parity, mad);
-        const double model = 0.5 * mad[0];
-        const double new_cost = cost - mad[2] + 0.5 * mad[1];
-        const double change = cost - new_cost;
-        const double rho = model > 0.0 ? change / model : 0.0;
-        bool stop = false;
-        if (change >= 0.0 && rho > 1e-3) {
-            if (owner)
-                for (int d = 0; d < 3; ++d) x[d * rpc + rl] += dl[d * rpc + rl];
-            stop = change <= cost * 1e-6;                       // function_tolerance, CombinedSolver.h:88
-            cost = new_cost;
-            const double f = 1.0 - (2.0 * rho - 1.0) * (2.0 * rho - 1.0) * (2.0 * rho - 1.0);
-            radius /= fmax(f, 1.0 / 3.0);
-            radius = fmin(radius, 1e16);
-            decrease = 2.0;
-        } else {
-            radius /= decrease; decrease *= 2.0;
-            if (radius <= 1e-32) stop = true;
-        }
-        if (stop) { ++it; break; }
-        publish(x);                                            // svec <- x for the next linearisation (all CTAs passed the barrier
-        cluster.sync();                                        //  inside cluster_sum(mad), so nobody still reads p from svec)
-    }
-    cluster.sync();                                            // no CTA may exit while others can still write into its shared memory
-    // write back: encodeTranslation (CombinedSolver.h:189-197, dual_quaternion.hpp:82-85)
-    if (owner) {
-        float *nd = nodes + (size_t)n * DF_NODE_STRIDE;
-        const Quat rot = {nd[3], nd[4], nd[5], nd[6]};
-        const Quat h = qhalf(Quat{0.f, (float)x[rl], (float)x[rpc + rl], (float)x[2 * rpc + rl]});
-        const Quat d = qmul(h, rot);
-        nd[7] = d.w; nd[8] = d.x; nd[9] = d.y; nd[10] = d.z;
-    }
-    if (gt == 0 && stats) {
-        stats[0] = cost0; stats[1] = cost; stats[2] = (double)it; stats[3] = nvalid; stats[4] = (double)pcg_total; stats[5] = (double)ws.flags[0];
-        stats[6] = nnz_total;
-    }
-    (void)M3;
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// v4: v3's residency (matrix slice + full-length copy of the multiplied vector in shared memory, 8-CTA cluster), with the
-// iteration's critical path shortened.  ncu of v3 (profiles/r01_solve_lm_v3_ncu_raw.csv): 19 % issue-active, warps waiting on
-// barriers (23 %), shared-memory round trips of the CG vectors (18 %), the DSMEM store queue (13 %) and fences (12 %).  Here
-//   * every CG vector element lives in the REGISTERS of the lane that owns the row (x, g, dl, r, p, damping, preconditioner):
-//     the vector updates touch no memory at all;
-//   * a cluster-wide sum is one __syncthreads + one cluster barrier: each CTA pushes its partial into all eight CTAs and
-//     everybody adds the eight values it received, in CTA order (bit-identical scalars in every CTA);
-//   * matrix entries are (double value, u16 column*3): 10 B instead of 12, so ~68 entries per row stay on chip at 2 k nodes
-//     (rows grow past 42 once the camera has moved away from the node cloud), and the vector copy is interleaved xyz.
-// The arithmetic and its order are v3's; the scalars, and therefore the iterates, are identical.
 constexpr int LM4_THREADS = 512;
-
-struct Lm4Smem {
-    double wpart[LM4_THREADS / 32][4];
-    double red_in[2][LMC_CTAS][4];
-};
-
-template <int NV>
-__device__ __forceinline__ void cluster_sum4(cg::cluster_group &cluster, Lm4Smem &sm, int &parity, int cta, double (&v)[NV])
-{
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < NV; ++k)
-        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < NV; ++k) sm.wpart[warp][k] = v[k];
-    }
-    __syncthreads();
-    if (warp == 0) {
-#pragma unroll
-        for (int k = 0; k < NV; ++k) {
-            double t = lane < LM4_THREADS / 32 ? sm.wpart[lane][k] : 0.0;
-            for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-            if (lane < LMC_CTAS) *cluster.map_shared_rank(&sm.red_in[parity][cta][k], lane) = t;    // lane = destination CTA
-        }
-    }
-    cluster.sync();                                            // pushes of all CTAs have landed (release/acquire, cluster scope)
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        double t = 0.0;
-#pragma unroll
-        for (int c = 0; c < LMC_CTAS; ++c) t += sm.red_in[parity][c][k];
-        v[k] = t;
-    }
-    parity ^= 1;                                               // the other buffer is free: its readers passed the barrier above
-}
 
 struct Lm4Layout {
     int rpc, tpr, ent_cap;
@@ -1038,201 +515,6 @@ __host__ __device__ inline Lm4Layout lm4_layout(int M, int ent_cap, int ncta = L
     L.off_col = o; o += (((size_t)ent_cap * LM4_THREADS * 2) + 15) & ~(size_t)15;
     L.total = o;
     return L;
-}
-
-__global__ void __cluster_dims__(LMC_CTAS, 1, 1) __launch_bounds__(LM4_THREADS)
-solve_lm_v4_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_iters, int lin_iters, double *stats, int ent_cap)
-{
-    cg::cluster_group cluster = cg::this_cluster();
-    __shared__ Lm4Smem sm;
-    extern __shared__ __align__(16) unsigned char dyn[];
-    const Lm4Layout L = lm4_layout(M, ent_cap);
-    double *svec = reinterpret_cast<double *>(dyn + L.off_svec);          // full-length copy of the multiplied vector, [3 * node + axis]
-    double *mval = reinterpret_cast<double *>(dyn + L.off_val);           // [entry][thread]
-    unsigned short *mcol = reinterpret_cast<unsigned short *>(dyn + L.off_col);   // 3 * column
-    const int rpc = L.rpc, tpr = L.tpr;
-
-    int parity = 0;
-    const int cta = (int)cluster.block_rank();
-    const int tid = threadIdx.x;
-    const int rl = tid / tpr, sub = tid % tpr;
-    // Rows are dealt to the CTAs in the node grid's Morton order (nodegrid.cu step 5): a CTA's rows are neighbours in space, so
-    // most of the columns they touch are the CTA's own rows and a row's search-direction entry is needed by few other CTAs.
-    const int *order = grid ? nodegrid_order(grid) : nullptr;
-    const int *slot = grid ? nodegrid_slot(grid) : nullptr;
-    const int s_row = cta * rpc + rl;                          // slot of this thread's row
-    const bool has_row = rl < rpc && s_row < M;
-    const int n = has_row ? (order ? order[s_row] : s_row) : 0;   // node index = row/column index of the normal matrix
-    const bool owner = has_row && sub == 0;
-
-    const int nnz = has_row ? ws.rownnz[n] : 0;
-    int my_ent = 0;
-    unsigned need = 0u;                                        // CTAs that own a row coupled to this one (A is structurally symmetric)
-    for (int e = sub; e < nnz; e += tpr) {
-        const int j = ws.col[(size_t)e * M + n];
-        need |= 1u << ((slot ? slot[j] : j) / rpc);
-        if (my_ent < ent_cap) {
-            mcol[my_ent * LM4_THREADS + tid] = (unsigned short)(3 * j);
-            mval[my_ent * LM4_THREADS + tid] = ws.val[(size_t)e * M + n];
-            ++my_ent;
-        }
-    }
-    for (int o = tpr >> 1; o > 0; o >>= 1) need |= __shfl_xor_sync(0xffffffffu, need, o);
-    need |= 1u << cta;
-    const int e_rest = sub + my_ent * tpr;                     // entries that did not fit are streamed from L2 (rare)
-    const double diag_n = has_row ? ws.diag[n] : 0.0;
-    double gb0 = 0.0, gb1 = 0.0, gb2 = 0.0;
-    if (owner) { gb0 = ws.gb[n]; gb1 = ws.gb[M + n]; gb2 = ws.gb[2 * M + n]; }
-
-    auto publish = [&](double a0, double a1, double a2) {      // this row's three values -> every CTA's svec
-        if (owner) {
-#pragma unroll
-            for (int c = 0; c < LMC_CTAS; ++c) {
-                if (!((need >> c) & 1u)) continue;
-                double *remote = cluster.map_shared_rank(svec, c) + 3 * n;
-                remote[0] = a0; remote[1] = a1; remote[2] = a2;
-            }
-        }
-    };
-    auto spmv = [&](double &o0, double &o1, double &o2) {      // (A * svec)[row], valid in the owner lane
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-#pragma unroll 4
-        for (int k = 0; k < my_ent; ++k) {
-            const double *sv = svec + mcol[k * LM4_THREADS + tid];
-            const double a = mval[k * LM4_THREADS + tid];
-            a0 += a * sv[0]; a1 += a * sv[1]; a2 += a * sv[2];
-        }
-        for (int e = e_rest; e < nnz; e += tpr) {
-            const double *sv = svec + 3 * __ldg(ws.col + (size_t)e * M + n);
-            const double a = __ldg(ws.val + (size_t)e * M + n);
-            a0 += a * sv[0]; a1 += a * sv[1]; a2 += a * sv[2];
-        }
-        for (int o = tpr >> 1; o > 0; o >>= 1) {
-            a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-        }
-        o0 = a0; o1 = a1; o2 = a2;
-    };
-
-    // x0 = current node translations (CombinedSolver.h:165-172)
-    double x0 = 0.0, x1 = 0.0, x2 = 0.0;
-    if (owner) {
-        const float4 *n4 = reinterpret_cast<const float4 *>(nodes + (size_t)n * DF_NODE_STRIDE);
-        const float4 a = n4[0], b = n4[1], c = n4[2];
-        const Quat t = dq_translation(Quat{a.w, b.x, b.y, b.z}, Quat{b.w, c.x, c.y, c.z});
-        x0 = t.x; x1 = t.y; x2 = t.z;
-    }
-    const int T = LMC_CTAS * LM4_THREADS, gt = cta * LM4_THREADS + tid;
-    double c0n[3] = {0.0, 0.0, 0.0};
-    for (int i = gt; i < ws.prepare_blocks * (PREPARE_THREADS / 32); i += T) { c0n[0] += ws.c0_partials[2 * i]; c0n[1] += ws.c0_partials[2 * i + 1]; }
-    c0n[2] = (owner ? (double)nnz : 0.0);
-    cluster.sync();                                            // every CTA is running: remote shared memory may be written
-    publish(x0, x1, x2);
-    cluster_sum4(cluster, sm, parity, cta, c0n);               // its barrier also completes the publish
-    const double nvalid = c0n[1], nnz_total = c0n[2];
-    double Ap0, Ap1, Ap2;
-    spmv(Ap0, Ap1, Ap2);
-    double t0[1] = {0.0};
-    if (owner) {
-        t0[0] += x0 * (0.5 * Ap0 - gb0);
-        t0[0] += x1 * (0.5 * Ap1 - gb1);
-        t0[0] += x2 * (0.5 * Ap2 - gb2);
-    }
-    cluster_sum4(cluster, sm, parity, cta, t0);
-    double cost = c0n[0] + t0[0];
-    const double cost0 = cost;
-
-    double radius = 1e4, decrease = 2.0;                       // solverGPUGaussNewton.t:26-39
-    int it = 0, pcg_total = 0;
-    for (; it < nl_iters; ++it) {
-        spmv(Ap0, Ap1, Ap2);                                   // svec holds x here
-        double rzv[1] = {0.0};
-        double cdn = 0.0, mi = 0.0;
-        double g0 = 0.0, g1 = 0.0, g2 = 0.0, dl0 = 0.0, dl1 = 0.0, dl2 = 0.0, r0 = 0.0, r1 = 0.0, r2 = 0.0, p0 = 0.0, p1 = 0.0, p2 = 0.0;
-        if (owner) {
-            cdn = fmin(fmax(diag_n, 1e-6), 1e32) / radius;
-            mi = 1.0 / (diag_n + cdn);
-            g0 = gb0 - Ap0; g1 = gb1 - Ap1; g2 = gb2 - Ap2;
-            r0 = g0; r1 = g1; r2 = g2;
-            p0 = g0 * mi; p1 = g1 * mi; p2 = g2 * mi;
-            rzv[0] += g0 * p0; rzv[0] += g1 * p1; rzv[0] += g2 * p2;
-        }
-        cluster.sync();                                        // every CTA finished reading svec (x) before p overwrites it
-        publish(p0, p1, p2);
-        cluster_sum4(cluster, sm, parity, cta, rzv);
-        double rz = rzv[0];
-        double Q0 = 0.0;
-        for (int l = 0; l < lin_iters && rz > 0.0; ++l) {
-            spmv(Ap0, Ap1, Ap2);
-            double pap[1] = {0.0};
-            if (owner) {
-                Ap0 = Ap0 + cdn * p0; Ap1 = Ap1 + cdn * p1; Ap2 = Ap2 + cdn * p2;
-                pap[0] += p0 * Ap0; pap[0] += p1 * Ap1; pap[0] += p2 * Ap2;
-            }
-            cluster_sum4(cluster, sm, parity, cta, pap);       // barrier: every CTA finished reading svec (p)
-            if (!(pap[0] > 0.0)) break;
-            const double alpha = rz / pap[0];
-            double rq[2] = {0.0, 0.0};
-            double z0 = 0.0, z1 = 0.0, z2 = 0.0;
-            if (owner) {
-                dl0 = dl0 + alpha * p0; r0 = r0 - alpha * Ap0; z0 = r0 * mi; rq[0] += r0 * z0; rq[1] += dl0 * (r0 + g0);
-                dl1 = dl1 + alpha * p1; r1 = r1 - alpha * Ap1; z1 = r1 * mi; rq[0] += r1 * z1; rq[1] += dl1 * (r1 + g1);
-                dl2 = dl2 + alpha * p2; r2 = r2 - alpha * Ap2; z2 = r2 * mi; rq[0] += r2 * z2; rq[1] += dl2 * (r2 + g2);
-            }
-            cluster_sum4(cluster, sm, parity, cta, rq);
-            const double rz_new = rq[0], Q1 = -0.5 * rq[1];
-            const double beta = rz_new / rz;
-            if (owner) { p0 = z0 + beta * p0; p1 = z1 + beta * p1; p2 = z2 + beta * p2; }
-            rz = rz_new;
-            ++pcg_total;
-            const double zeta = (double)(l + 1) * (Q1 - Q0) / Q1;   // Ceres/Opt q-tolerance, solverGPUGaussNewton.t:1093-1101
-            Q0 = Q1;
-            publish(p0, p1, p2);
-            cluster.sync();                                    // publish complete everywhere
-            if (zeta < 1e-4) break;
-        }
-        // model change = 0.5 dl.(g + r + C dl);  A dl = g - r - C dl  => new cost = cost - dl.g + 0.5 dl.(A dl)
-        double mad[3] = {0.0, 0.0, 0.0};
-        if (owner) {
-            double c;
-            c = cdn * dl0; mad[0] += dl0 * (g0 + r0 + c); mad[1] += dl0 * (g0 - r0 - c); mad[2] += dl0 * g0;
-            c = cdn * dl1; mad[0] += dl1 * (g1 + r1 + c); mad[1] += dl1 * (g1 - r1 - c); mad[2] += dl1 * g1;
-            c = cdn * dl2; mad[0] += dl2 * (g2 + r2 + c); mad[1] += dl2 * (g2 - r2 - c); mad[2] += dl2 * g2;
-        }
-        cluster_sum4(cluster, sm, parity, cta, mad);
-        const double model = 0.5 * mad[0];
-        const double new_cost = cost - mad[2] + 0.5 * mad[1];
-        const double change = cost - new_cost;
-        const double rho = model > 0.0 ? change / model : 0.0;
-        bool stop = false;
-        if (change >= 0.0 && rho > 1e-3) {
-            if (owner) { x0 += dl0; x1 += dl1; x2 += dl2; }
-            stop = change <= cost * 1e-6;                       // function_tolerance, CombinedSolver.h:88
-            cost = new_cost;
-            const double f = 1.0 - (2.0 * rho - 1.0) * (2.0 * rho - 1.0) * (2.0 * rho - 1.0);
-            radius /= fmax(f, 1.0 / 3.0);
-            radius = fmin(radius, 1e16);
-            decrease = 2.0;
-        } else {
-            radius /= decrease; decrease *= 2.0;
-            if (radius <= 1e-32) stop = true;
-        }
-        if (stop) { ++it; break; }
-        publish(x0, x1, x2);                                   // svec <- x for the next linearisation (all CTAs passed the barrier
-        cluster.sync();                                        //  inside cluster_sum4(mad), so nobody still reads p from svec)
-    }
-    cluster.sync();                                            // no CTA may exit while others can still write into its shared memory
-    // write back: encodeTranslation (CombinedSolver.h:189-197, dual_quaternion.hpp:82-85)
-    if (owner) {
-        float *nd = nodes + (size_t)n * DF_NODE_STRIDE;
-        const Quat rot = {nd[3], nd[4], nd[5], nd[6]};
-        const Quat h = qhalf(Quat{0.f, (float)x0, (float)x1, (float)x2});
-        const Quat d = qmul(h, rot);
-        nd[7] = d.w; nd[8] = d.x; nd[9] = d.y; nd[10] = d.z;
-    }
-    if (gt == 0 && stats) {
-        stats[0] = cost0; stats[1] = cost; stats[2] = (double)it; stats[3] = nvalid; stats[4] = (double)pcg_total; stats[5] = (double)ws.flags[0];
-        stats[6] = nnz_total;
-    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1441,6 +723,7 @@ solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
 
     double radius = 1e4, decrease = 2.0;                       // solverGPUGaussNewton.t:26-39
     int it = 0, pcg_total = 0;
+    if (ws.flags[0]) nl_iters = 0;                             // a row overflowed (solve_rows): the stored system is truncated -> leave the field unchanged, stats[5] says so
     for (; it < nl_iters; ++it) {
         spmv(Ap0, Ap1, Ap2);                                   // svec holds x here
         double rzv[1] = {0.0};
@@ -1530,10 +813,9 @@ solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
     }
 }
 
-int solve_lm_impl()
+int solve_lm_impl()           // DF_SOLVE_LM_IMPL=1 forces the one-block fallback kernel (tests)
 {
-    static int impl = -1;
-    if (impl < 0) { const char *e = getenv("DF_SOLVE_LM_IMPL"); impl = e ? atoi(e) : 5; }
+    static const int impl = [] { const char *e = getenv("DF_SOLVE_LM_IMPL"); return e ? atoi(e) : 5; }();
     return impl;
 }
 
@@ -1572,63 +854,36 @@ extern "C" int df_solve_data_term(float *nodes, int M, const void *node_grid, co
     DF_LAUNCH_CHECK();
     launch_pdl(solve_rows_kernel, dim3(M), dim3(ROWS_THREADS), 0, s, ws, M, N, flags & DF_SOLVE_REF_GRAPH_QUIRK);
     DF_LAUNCH_CHECK();
-    const size_t smem_budget = 200 * 1024;
-    const LmSmemLayout L0 = lm_layout(M, 0);
-    const size_t smem4_budget = 224 * 1024;
-    const Lm4Layout L40 = lm4_layout(M, 0);
-    if (solve_lm_impl() >= 4 && L40.rpc * L40.tpr <= LM4_THREADS && L40.total + (size_t)LM4_THREADS * 10 * 8 <= smem4_budget) {
-        const int ent_cap = (int)((smem4_budget - L40.total - 16) / ((size_t)LM4_THREADS * 10));
-        const Lm4Layout L = lm4_layout(M, ent_cap);
-        static bool attr4 = false;
-        if (!attr4) { cudaFuncSetAttribute(solve_lm_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4_budget); attr4 = true; }
-        if (solve_lm_impl() >= 5) {
-            // 16-CTA clusters (non-portable size) when the rows divide usefully; DF_SOLVE_LM_CTAS overrides
-            static int want = -1;
-            if (want < 0) { const char *e = getenv("DF_SOLVE_LM_CTAS"); want = e ? atoi(e) : 16; }
-            const int ncta = (want == 16 && M >= 256) ? 16 : 8;
-            const Lm4Layout Lb = lm4_layout(M, 0, ncta);
-            const size_t budget = ncta == 16 ? (size_t)216 * 1024 : smem4_budget;      // the 16-CTA variant has 6 KB of static shared memory
-            const int cap = (int)((budget - Lb.total - 16) / ((size_t)LM4_THREADS * 10));
-            const Lm4Layout Lc = lm4_layout(M, cap, ncta);
-            static bool attr5 = false;
-            if (!attr5) {
-                cudaFuncSetAttribute(solve_lm_v5_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4_budget);
-                cudaFuncSetAttribute(solve_lm_v5_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
-                cudaFuncSetAttribute(solve_lm_v5_kernel<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-                attr5 = true;
-            }
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(ncta); cfg.blockDim = dim3(LM4_THREADS); cfg.dynamicSmemBytes = Lc.total; cfg.stream = s;
-            cudaLaunchAttribute at[2];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = ncta; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            at[1].val.programmaticStreamSerializationAllowed = pdl_enabled();
-            cfg.attrs = at; cfg.numAttrs = 2;
-            cudaError_t le;
-            if (ncta == 16) le = cudaLaunchKernelEx(&cfg, solve_lm_v5_kernel<16>, nodes, M, node_grid, ws, nonlinear_iters, linear_iters, stats_dev, cap);
-            else le = cudaLaunchKernelEx(&cfg, solve_lm_v5_kernel<8>, nodes, M, node_grid, ws, nonlinear_iters, linear_iters, stats_dev, cap);
-            if (le != cudaSuccess) return (int)le;
-        } else
-            solve_lm_v4_kernel<<<LMC_CTAS, LM4_THREADS, L.total, s>>>(nodes, M, node_grid, ws, nonlinear_iters, linear_iters, stats_dev, ent_cap);
-    }
-    else if (solve_lm_impl() >= 3 && L0.rpc * L0.tpr <= LM3_THREADS && L0.total + (size_t)LM3_THREADS * 12 <= smem_budget) {
-        const int ent_cap = (int)((smem_budget - L0.total) / ((size_t)LM3_THREADS * 12));
-        const LmSmemLayout L = lm_layout(M, ent_cap);
-        static bool attr3 = false;
-        if (!attr3) { cudaFuncSetAttribute(solve_lm_cluster_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_budget); attr3 = true; }
-        solve_lm_cluster_smem_kernel<<<LMC_CTAS, LM3_THREADS, L.total, s>>>(nodes, M, ws, nonlinear_iters, linear_iters, stats_dev, ent_cap);
-    }
-    else if (solve_lm_impl() == 1) solve_lm_kernel<<<1, LM_THREADS, 0, s>>>(nodes, M, ws, nonlinear_iters, linear_iters, stats_dev);
-    else {
-        const size_t vec_bytes = (size_t)3 * M * sizeof(double);
-        const int use_smem = vec_bytes <= 200 * 1024;
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(solve_lm_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            attr_set = true;
+    // v5 on one cluster when the system fits its shared memory (16 CTAs = the non-portable maximum: half the rows, hence half the
+    // mat-vec gather traffic, per SM; DF_SOLVE_LM_CTAS=8 selects the portable size); otherwise the one-block kernel (matrix in L2).
+    static const int want = [] { const char *e = getenv("DF_SOLVE_LM_CTAS"); return e ? atoi(e) : 16; }();
+    const int ncta = (want == 16 && M >= 256) ? 16 : 8;
+    const Lm4Layout Lb = lm4_layout(M, 0, ncta);
+    const size_t budget = ncta == 16 ? (size_t)216 * 1024 : (size_t)224 * 1024;      // the 16-CTA variant has 6 KB of static shared memory
+    if (solve_lm_impl() >= 5 && Lb.rpc * Lb.tpr <= LM4_THREADS && Lb.total + (size_t)LM4_THREADS * 10 * 8 <= budget) {
+        const int cap = (int)((budget - Lb.total - 16) / ((size_t)LM4_THREADS * 10));
+        const Lm4Layout Lc = lm4_layout(M, cap, ncta);
+        // function attributes are per device: set them on every launch (cheap) rather than once per process
+        if (ncta == 16) {
+            cudaFuncSetAttribute(solve_lm_v5_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+            cudaFuncSetAttribute(solve_lm_v5_kernel<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        } else {
+            cudaFuncSetAttribute(solve_lm_v5_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
         }
-        solve_lm_cluster_kernel<<<LMC_CTAS, LM_THREADS, use_smem ? vec_bytes : 0, s>>>(nodes, M, ws, nonlinear_iters, linear_iters, stats_dev, use_smem);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(ncta); cfg.blockDim = dim3(LM4_THREADS); cfg.dynamicSmemBytes = Lc.total; cfg.stream = s;
+        cudaLaunchAttribute at[2];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = ncta; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[1].val.programmaticStreamSerializationAllowed = pdl_enabled();
+        cfg.attrs = at; cfg.numAttrs = 2;
+        cudaError_t le;
+        if (ncta == 16) le = cudaLaunchKernelEx(&cfg, solve_lm_v5_kernel<16>, nodes, M, node_grid, ws, nonlinear_iters, linear_iters, stats_dev, cap);
+        else le = cudaLaunchKernelEx(&cfg, solve_lm_v5_kernel<8>, nodes, M, node_grid, ws, nonlinear_iters, linear_iters, stats_dev, cap);
+        if (le != cudaSuccess) return (int)le;
+    } else {
+        solve_lm_kernel<<<1, LM_THREADS, 0, s>>>(nodes, M, ws, nonlinear_iters, linear_iters, stats_dev);
     }
     DF_LAUNCH_CHECK();
     return 0;

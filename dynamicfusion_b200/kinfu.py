@@ -11,7 +11,7 @@ from . import capi
 
 BUF = {"volume": 0, "dists": 1, "curr_depth": 2, "curr_points": 3, "curr_normals": 4, "prev_points": 5, "prev_normals": 6,
        "canonical": 7, "canonical_normals": 8, "cloud": 9, "cloud_normals": 10, "nodes": 11, "canonical_visible": 12,
-       "solve_stats": 13}
+       "solve_stats": 13, "activity": 14}
 STAGES = ["preprocess", "icp", "raycast_canonical", "warp1", "solve", "warp2", "project_remove", "integrate", "extract", "raycast_prev"]
 
 RIGID_ONLY = 1
@@ -93,10 +93,10 @@ class KinFu:
         return a[:9].reshape(3, 3), a[9:]
 
     def info(self) -> dict:
-        v = (C.c_longlong * 11)()
-        self.lib.df_kinfu_get_info(self.h, v, 11)
+        v = (C.c_longlong * 12)()
+        self.lib.df_kinfu_get_info(self.h, v, 12)
         keys = ["frame_counter", "nodes", "cloud_points", "poses", "icp_ok", "launches", "resets", "lm_iters", "n_updated", "pcg_iters",
-                "n_warped"]
+                "n_warped", "solve_overflows"]
         return dict(zip(keys, [int(x) for x in v]))
 
     def state_digest(self) -> list:

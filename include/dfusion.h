@@ -238,7 +238,10 @@ int df_integrate_warped(df_volume vol, const uint16_t *depth, size_t depth_pitch
  * -> Opt LM/PCG on kfusion/solvers/dynamicfusion.t: translation-only data term solved on the device; node
  * translations are updated in place (encodeTranslation, CombinedSolver.h:189-197).
  * params: nonlinear (LM) iterations, linear (PCG) iterations; stats_dev (device, 8 doubles): initial cost, final cost,
- * LM iterations run, valid rows, PCG iterations run, row-overflow flag.  workspace from df_solve_workspace_bytes(M, N).
+ * LM iterations run, valid rows, PCG iterations run, row-overflow flag.  If a node's row of the normal matrix couples to more columns
+ * than the kernels store (512), the flag is raised and the solve leaves the node translations UNCHANGED (0 LM iterations) rather than
+ * solving a truncated, asymmetric system; callers must look at stats[5] (the frame loop reports it through df_kinfu_get_info[11] and on
+ * stderr, the C++ mirror prints an error).  workspace from df_solve_workspace_bytes(M, N).
  * Rows with a NaN in canon or live are skipped (the reference zero-fills them with stale k-NN scratch). */
 size_t df_solve_workspace_bytes(int M, int N);
 /* after df_solve_data_term: the per-vertex neighbour indices (N*8, -1 for skipped rows) and weights (N*8) it computed for
@@ -308,11 +311,12 @@ int df_kinfu_get_pose(void *kinfu, int time, float *pose12_host);
 /* info[0] frame counter, [1] warp nodes M, [2] extracted cloud points, [3] poses stored, [4] last ICP ok,
  * [5] kernels launched in the last frame, [6] resets so far, [7] solver LM iterations (last frame),
  * [8] voxels written by the last integrate (DF_KINFU_STAGE_TIMING only), [9] solver PCG iterations (last frame),
- * [10] voxels carried through the warp field by the last df_integrate_warped (DF_KINFU_WARPED_INTEGRATE + STAGE_TIMING) */
+ * [10] voxels carried through the warp field by the last df_integrate_warped (DF_KINFU_WARPED_INTEGRATE + STAGE_TIMING),
+ * [11] frames whose warp solve was skipped because a normal-matrix row overflowed (df_solve_data_term: stats[5]); also reported on stderr */
 int df_kinfu_get_info(void *kinfu, long long *info_host, int n);
 /* device buffers of the current state: 0 volume(u32), 1 dists, 2 curr depth L0, 3 curr points L0, 4 curr normals L0,
  * 5 prev points L0, 6 prev normals L0, 7 canonical (after 2nd warp), 8 canonical normals, 9 extracted cloud,
- * 10 extracted normals, 11 nodes, 12 canonical_visible, 13 solver stats (8 doubles) */
+ * 10 extracted normals, 11 nodes, 12 canonical_visible, 13 solver stats (8 doubles), 14 activity map (bytes) */
 int df_kinfu_get_buffer(void *kinfu, int which, void **ptr, size_t *pitch, int *cols, int *rows);
 /* synchronous device-to-host copy of one of those buffers (diagnostics / tests), at most `bytes` bytes */
 int df_kinfu_read_buffer(void *kinfu, int which, void *dst_host, size_t bytes);

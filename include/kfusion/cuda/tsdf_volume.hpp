@@ -6,6 +6,7 @@
 namespace kfusion
 {
     class WarpField;
+    class KinFu;
     namespace cuda
     {
         class KF_EXPORTS TsdfVolume
@@ -76,6 +77,14 @@ namespace kfusion
             std::vector<Entry> tsdf_entries_;
             mutable DeviceMemory workspace_;          // extraction / projection scratch (not in the reference)
             mutable DeviceMemory count_;
+            // When this object is KinFu's view over the frame loop's volume (KinFu::tsdf()): the loop's activity map (every integration
+            // of that volume must be tracked, dfusion.h) and the loop's extracted cloud / normals, copied to the host clouds on demand
+            // (the reference fills them every frame, kinfu.cpp:249-250,398-399).
+            friend class ::kfusion::KinFu;
+            unsigned char *activity_ = 0;
+            void *pipeline_ = 0;
+            mutable bool host_clouds_stale_ = false;
+            void refresh_host_clouds() const;
         };
     }
 }

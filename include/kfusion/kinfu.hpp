@@ -86,5 +86,6 @@ namespace kfusion
         std::vector<std::pair<utils::DualQuaternion<float>, utils::DualQuaternion<float>>> edges_;
         cv::Ptr<WarpFieldOptimiser> optimiser_;
         void *handle_;          // df_kinfu_* pipeline object (not in the reference)
+        long long resets_seen_ = 0;   // tracking-loss resets already mirrored into poses_
     };
 }
