@@ -63,7 +63,7 @@ _use_ref = False
 
 
 def reference_available() -> bool:
-    return REF_LIB.exists()
+    return REF_LIB.exists() and REF_LOCKSTEP_LIB.exists()
 
 
 def load_ref() -> C.CDLL:
@@ -77,6 +77,20 @@ def load_ref() -> C.CDLL:
 
 # libkfref_usedepth.so = proj_icp.cu compiled with the reference's compile-time USE_DEPTH alternative (internal.hpp:6); it defines the
 # same C++ symbols as libkfref.so, hence a library of its own (both are loaded RTLD_LOCAL)
+# libkfref_lockstep.so = tsdf_volume.cu once more, under the warp-lock-step executor (oracle/ref_shim/cudahost/lockstep.h): the reference's
+# warp-synchronous extract_kernel (tsdf_volume.cu:511-710) really runs, 32 lanes stepped together
+REF_LOCKSTEP_LIB = HERE / "_ref" / "libkfref_lockstep.so"
+_ref_lockstep_lib = None
+
+
+def load_ref_lockstep() -> C.CDLL:
+    global _ref_lockstep_lib
+    if _ref_lockstep_lib is None:
+        _ref_lockstep_lib = C.CDLL(str(REF_LOCKSTEP_LIB))
+        _ref_lockstep_lib.kfref_extract_cloud.restype = C.c_longlong
+    return _ref_lockstep_lib
+
+
 REF_DEPTH_LIB = HERE / "_ref" / "libkfref_usedepth.so"
 _ref_depth_lib = None
 
@@ -107,6 +121,8 @@ class reference:
 def _fn(name: str):
     if _use_ref and name == "icp_accumulate_depth":
         return load_ref_usedepth().kfref_icp_accumulate_depth
+    if _use_ref and name == "extract_cloud":
+        return load_ref_lockstep().kfref_extract_cloud
     if _use_ref:
         return getattr(load_ref(), "kfref_" + name)
     return getattr(load(), "orc_" + name)

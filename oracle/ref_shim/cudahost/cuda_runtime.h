@@ -31,7 +31,11 @@
 #define __global__
 #define __shared__ static
 #define __constant__ static
+#ifdef CUDAHOST_LOCKSTEP
+#define __forceinline__ inline __attribute__((always_inline))      /* lock-step mode: machine code order must be source order (lockstep.h) */
+#else
 #define __forceinline__ inline
+#endif
 #define __launch_bounds__(...)
 #define __restrict__
 
@@ -220,6 +224,7 @@ static inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
 static inline float min(float a, float b) { return std::fmin(a, b); }
 static inline float max(float a, float b) { return std::fmax(a, b); }
 using std::abs;
+using std::fabs;          // CUDA resolves fabs(float) to the float overload; plain C ::fabs would silently promote to double
 using std::isnan;
 using std::isinf;
 
@@ -231,9 +236,16 @@ namespace cudahost {
 }
 }
 static inline void __syncthreads() { cudahost::not_emulated("__syncthreads"); }
+#ifdef CUDAHOST_LOCKSTEP
+#include "lockstep.h"
+static inline unsigned __ballot(int p) { return cudahost::warp_vote(p); }
+static inline int __all(int p) { unsigned active; const unsigned m = cudahost::warp_vote(p, &active); return m == active; }
+static inline int __any(int p) { return cudahost::warp_vote(p) != 0u; }
+#else
 static inline unsigned __ballot(int) { cudahost::not_emulated("__ballot"); }
 static inline int __all(int) { cudahost::not_emulated("__all"); }
 static inline int __any(int) { cudahost::not_emulated("__any"); }
+#endif
 template <class T> static inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }
 static inline unsigned atomicInc(unsigned *p, unsigned lim) { unsigned o = *p; *p = o >= lim ? 0 : o + 1; return o; }
 
@@ -243,6 +255,31 @@ struct LaunchCfg {
     dim3 grid, block;
     LaunchCfg(dim3 g, dim3 b, size_t = 0, cudaStream_t = 0) : grid(g), block(b) {}
 };
+#ifdef CUDAHOST_LOCKSTEP
+// warp-lock-step launch (lockstep.h): blocks in launch order, the warps of a block one after another, 32 lanes per warp as fibers
+template <class F> static inline void launch(const LaunchCfg &c, F body)
+{
+    gridDim = c.grid; blockDim = c.block;
+    struct Thunk { static void call(void *p) { (*(F *)p)(); } };
+    const unsigned per_block = c.block.x * c.block.y * c.block.z;
+    for (unsigned bz = 0; bz < c.grid.z; ++bz)
+        for (unsigned by = 0; by < c.grid.y; ++by)
+            for (unsigned bx = 0; bx < c.grid.x; ++bx) {
+                blockIdx.x = bx; blockIdx.y = by; blockIdx.z = bz;
+                // warps in DESCENDING order: extract_kernel's thread 0 publishes the point count in an epilogue that no block barrier
+                // protects (tsdf_volume.cu:690-703); any interleaving is a legal GPU schedule, and this is the one under which that
+                // epilogue sees the points of every warp of its block -- the outcome the reference relies on
+                for (long first = (long)((per_block - 1) / 32) * 32; first >= 0; first -= 32) {
+                    uint3 tids[32];
+                    int n = 0;
+                    for (unsigned f = (unsigned)first; f < per_block && f < (unsigned)first + 32; ++f, ++n) {
+                        tids[n].x = f % c.block.x; tids[n].y = (f / c.block.x) % c.block.y; tids[n].z = f / (c.block.x * c.block.y);
+                    }
+                    run_warp(tids, n, &Thunk::call, (void *)&body);
+                }
+            }
+}
+#else
 template <class F> static inline void launch(const LaunchCfg &c, F body)
 {
     gridDim = c.grid; blockDim = c.block;
@@ -258,7 +295,15 @@ template <class F> static inline void launch(const LaunchCfg &c, F body)
                         }
             }
 }
+#endif
 }  // namespace cudahost
 
 // inline PTX (Warp::laneId, gmem::LdCs under __CUDA_ARCH__) has no host meaning; only kernels that are never launched here use it
+#ifdef CUDAHOST_LOCKSTEP
+// the only PTX the lock-step kernels execute reads a special register into a local named `ret` (Warp::laneId / laneMaskLt,
+// temp_utils.hpp:462-484); other asm statements (gmem::LdCs / StCs) have no such local, bind the dummy below and abort if executed
+static unsigned ret;
+#define asm(...) (ret = cudahost::ptx_special(#__VA_ARGS__))
+#else
 #define asm(...) cudahost::not_emulated("inline PTX")
+#endif

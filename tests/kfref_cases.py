@@ -34,26 +34,36 @@ def _identity():
     return np.eye(3, dtype=np.float32), np.zeros(3, np.float32)
 
 
-def tsdf_case(orc, dim, tilted, ref):
-    """compute_dists -> 2 x integrate -> raycast -> extract_normals -> project_and_remove"""
+def sort_points(p: np.ndarray) -> np.ndarray:
+    """order-independent form of a point list: rows sorted by their bit patterns (the reference appends in warp-completion order,
+    the oracle in (z, y, x, axis) order; parity is on the SET of points, bit for bit)"""
+    p = np.ascontiguousarray(p, np.float32)
+    u = p.view(np.uint32)
+    return p[np.lexsort(u.T[::-1])]
+
+
+def tsdf_case(orc, dim, tilted, ref, dims=None):
+    """compute_dists -> 2 x integrate -> raycast -> extract cloud -> extract_normals -> project_and_remove"""
     ctx = orc.reference() if ref else contextlib.nullcontext()
     out = {}
     depth = synth.sphere_wall_depth(seed=dim)
-    dims, vs = (dim,) * 3, (1.0 / dim,) * 3
+    dims, vs = dims or (dim,) * 3, (1.0 / dim,) * 3
     vol_pose = synth.volume_pose(1.0)
     cam = _tilted_pose() if tilted else _identity()
     with ctx:
         dists = orc.compute_dists(depth, K)
-        vol = np.full(dim ** 3, 0xdeadbeef, np.uint32)
+        vol = np.full(dims[0] * dims[1] * dims[2], 0xdeadbeef, np.uint32)
         orc.clear_volume(vol, dims, vs, TRUNC, MAXW)
         for pose in (cam, _mul(cam, (np.eye(3, dtype=np.float32), np.array([0.004, 0.0, 0.002], np.float32)))):
             orc.integrate(vol, dims, vs, TRUNC, MAXW, dists, _mul(_inv(pose), vol_pose), K)
         cam2vol = _mul(_inv(vol_pose), cam)
         pts, nrm, _ = orc.raycast_points(vol, dims, vs, TRUNC, MAXW, cam2vol, _inv(cam2vol)[0], K, 640, 480, 0.75, 0.5)
     out["dists"], out["volume"], out["ray_points"], out["ray_normals"] = dists, vol, pts, nrm
-    # zero-crossing cloud from the oracle in both arms (the reference's extract_kernel is warp-synchronous: not host-runnable)
-    cloud = orc.extract_cloud(vol, dims, vs, TRUNC, MAXW, vol_pose, 400000)
     with ctx:
+        # zero-crossing cloud: the oracle's restatement, or the reference's own warp-synchronous extract_kernel (tsdf_volume.cu:511-710)
+        # under the warp-lock-step executor (oracle/ref_shim/cudahost/lockstep.h -> libkfref_lockstep.so)
+        cloud = sort_points(orc.extract_cloud(vol, dims, vs, TRUNC, MAXW, vol_pose, 400000))
+        out["cloud_sorted"] = cloud
         out["cloud_normals"] = orc.extract_normals(vol, dims, vs, TRUNC, MAXW, cloud, vol_pose, _inv(vol_pose)[0], 0.5)
         # raycast points back in the camera frame, projected into the frame's dists (kinfu.cpp:300)
         proj = pts.copy()
@@ -104,7 +114,9 @@ def imgproc_icp_case(orc, ref):
 
 
 def all_cases(orc, ref):
-    cases = {"tsdf64_tilted": tsdf_case(orc, 64, True, ref), "tsdf96_identity": tsdf_case(orc, 96, False, ref), "imgproc_icp": imgproc_icp_case(orc, ref)}
+    cases = {"tsdf64_tilted": tsdf_case(orc, 64, True, ref), "tsdf96_identity": tsdf_case(orc, 96, False, ref),
+             # ragged dims: x not a multiple of the 32-wide block, y not a multiple of its 6 rows (partially and fully idle warps)
+             "tsdf_ragged": tsdf_case(orc, 48, True, ref, dims=(48, 50, 40)), "imgproc_icp": imgproc_icp_case(orc, ref)}
     return {f"{c}/{k}": v for c, d in cases.items() for k, v in d.items()}
 
 
