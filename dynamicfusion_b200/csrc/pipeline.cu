@@ -43,6 +43,10 @@ struct KinFu {
     float *pinned = nullptr;             // 16 floats: T(12) + ok
     std::vector<float> poses;            // 12 floats per pose
     int frame_counter = 0, resets = 0, last_ok = 1, launches = 0;
+    // df_kinfu_set_overrides (lock-step parity hook): one-shot replacements for the NEXT frame
+    std::vector<uint16_t> ov_depth; bool has_ov_depth = false;       // bilateral-filtered depth, dense cols x rows
+    float ov_pose[12]; bool has_ov_pose = false;                     // absolute camera pose of the frame
+    std::vector<float> ov_nodes; bool has_ov_nodes = false;          // node table after the solve
     long long solve_overflows = 0;       // frames whose solve was skipped because a normal-matrix row overflowed (solve.cu ROWCAP); info[11]
     long long last_cloud = -1;
     double host_us[4] = {0, 0, 0, 0}; long long host_frames = 0;   // DF_KINFU_HOSTPROF: launch A, ICP wait, launch B, total
@@ -174,9 +178,16 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_d
     if (!only_df) {
     // ---- pre-processing, kinfu.cpp:226-242 -----------------------------------------------------------------------
     CKD(df_compute_dists(depth_dev, depth_pitch, p.cols, p.rows, p.intr, (uint16_t *)k.dists.ptr, k.dists.pitch, s));
-    CKD(df_bilateral(depth_dev, depth_pitch, p.cols, p.rows, (uint16_t *)k.cur_depth[0].ptr, k.cur_depth[0].pitch,
-                     p.bilateral_kernel_size, p.bilateral_sigma_spatial, p.bilateral_sigma_depth, s));
-    k.launches += 2;
+    if (k.has_ov_depth) {              // lock-step parity hook: the caller's bilateral image instead of this frame's (expf differs by 1 LSB between CUDA and glibc)
+        CK(cudaMemcpy2DAsync(k.cur_depth[0].ptr, k.cur_depth[0].pitch, k.ov_depth.data(), (size_t)p.cols * 2, (size_t)p.cols * 2, p.rows, cudaMemcpyHostToDevice, s));
+        CK(cudaStreamSynchronize(s));  // the host vector may be replaced right after the call
+        k.has_ov_depth = false;
+        ++k.launches;
+    } else {
+        CKD(df_bilateral(depth_dev, depth_pitch, p.cols, p.rows, (uint16_t *)k.cur_depth[0].ptr, k.cur_depth[0].pitch,
+                         p.bilateral_kernel_size, p.bilateral_sigma_spatial, p.bilateral_sigma_depth, s));
+        k.launches += 2;
+    }
     if (p.icp_truncate_depth_dist > 0) {
         CKD(df_truncate_depth((uint16_t *)k.cur_depth[0].ptr, k.cur_depth[0].pitch, p.cols, p.rows, p.icp_truncate_depth_dist, s));
         ++k.launches;
@@ -272,7 +283,9 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_d
     }
 
     // ---- ICP, kinfu.cpp:268-278 (device-resident; one host read of {ok, T}) -----------------------------------------
-    if (!only_df) {
+    const bool pose_given = !only_df && k.has_ov_pose;               // lock-step parity hook: the caller's pose instead of this frame's ICP
+    if (pose_given) { k.last_ok = 1; CK(cudaStreamSynchronize(s)); note_solve_overflow(k); }
+    if (!only_df && !pose_given) {
         const float *vc[MAX_LEVELS], *nc[MAX_LEVELS], *vp[MAX_LEVELS], *np[MAX_LEVELS];
         int cols[MAX_LEVELS], rows[MAX_LEVELS]; size_t pitch[MAX_LEVELS];
         for (int i = 0; i < LEVELS; ++i) {
@@ -296,7 +309,10 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_d
         if (!ok) { CKD(do_reset(k)); return 0; }                      // kinfu.cpp:276-277
     }
     mark(k, 2);
-    if (!only_df) {
+    if (pose_given) {
+        k.poses.insert(k.poses.end(), k.ov_pose, k.ov_pose + 12);
+        k.has_ov_pose = false;
+    } else if (!only_df) {
         float pose[12];
         dfh_aff_mul(&k.poses[k.poses.size() - 12], k.pinned, pose);   // poses_.back() * affine, kinfu.cpp:280
         k.poses.insert(k.poses.end(), pose, pose + 12);
@@ -323,6 +339,13 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_d
         k.launches += 5;                                               // prepare, scan, fill, rows, lm
         // row-overflow flag of this solve (stats[5]): lands in pinned memory, looked at after the next stream synchronisation
         CK(cudaMemcpyAsync(k.pinned + 14, k.solve_stats + 5, sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (k.has_ov_nodes) {          // lock-step parity hook: the caller's solved node table (CPU and GPU PCG round differently in the last bits)
+            if (k.ov_nodes.size() == (size_t)k.M * DF_NODE_STRIDE) {
+                CK(cudaMemcpyAsync(k.nodes, k.ov_nodes.data(), k.ov_nodes.size() * 4, cudaMemcpyHostToDevice, s));
+                CK(cudaStreamSynchronize(s));
+            }
+            k.has_ov_nodes = false;
+        }
         mark(k, 5);
         {
             // second warp (:389) queries exactly the vertices the solve just built its graph for (CombinedSolver.h:66-84):
@@ -629,6 +652,21 @@ extern "C" int df_kinfu_read_buffer(void *h, int which, void *dst_host, size_t b
     if (e != cudaSuccess) return (int)e;
     e = cudaMemcpy(dst_host, ptr, bytes < have ? bytes : have, cudaMemcpyDeviceToHost);
     return (int)e;
+}
+
+extern "C" int df_kinfu_set_overrides(void *h, const uint16_t *bilateral_depth_host, size_t pitch, const float *pose12_host, const float *nodes_host, int M)
+{
+    KinFu *k = (KinFu *)h;
+    k->has_ov_depth = bilateral_depth_host != nullptr;
+    if (bilateral_depth_host) {
+        k->ov_depth.resize((size_t)k->p.cols * k->p.rows);
+        for (int y = 0; y < k->p.rows; ++y) memcpy(&k->ov_depth[(size_t)y * k->p.cols], (const char *)bilateral_depth_host + (size_t)y * pitch, (size_t)k->p.cols * 2);
+    }
+    k->has_ov_pose = pose12_host != nullptr;
+    if (pose12_host) memcpy(k->ov_pose, pose12_host, 48);
+    k->has_ov_nodes = nodes_host != nullptr && M > 0;
+    if (k->has_ov_nodes) k->ov_nodes.assign(nodes_host, nodes_host + (size_t)M * DF_NODE_STRIDE);
+    return 0;
 }
 
 extern "C" int df_kinfu_state_digest(void *h, unsigned long long *out4_host)

@@ -99,6 +99,19 @@ class KinFu:
                 "n_warped", "solve_overflows"]
         return dict(zip(keys, [int(x) for x in v]))
 
+    def set_overrides(self, bilateral_depth=None, pose=None, nodes=None) -> None:
+        """df_kinfu_set_overrides (lock-step parity hook): numpy u16 [rows, cols] / (R 3x3, t 3) / float32 [M, 12] for the next frame"""
+        keep = []
+        d = p12 = n = None
+        M = 0
+        if bilateral_depth is not None:
+            b = np.ascontiguousarray(bilateral_depth, np.uint16); keep.append(b); d = b.ctypes.data
+        if pose is not None:
+            a = np.concatenate([np.asarray(pose[0], np.float32).reshape(9), np.asarray(pose[1], np.float32).reshape(3)]); keep.append(a); p12 = a.ctypes.data
+        if nodes is not None:
+            t = np.ascontiguousarray(nodes, np.float32); keep.append(t); n = t.ctypes.data; M = len(t)
+        capi.check(self.lib.df_kinfu_set_overrides(self.h, d, (self.params.cols * 2), p12, n, M))
+
     def state_digest(self) -> list:
         """df_kinfu_state_digest: [volume checksum, node-table checksum, cloud points, pose-chain hash] (u64 each)"""
         v = (C.c_ulonglong * 4)()

@@ -320,6 +320,14 @@ int df_kinfu_get_info(void *kinfu, long long *info_host, int n);
 int df_kinfu_get_buffer(void *kinfu, int which, void **ptr, size_t *pitch, int *cols, int *rows);
 /* synchronous device-to-host copy of one of those buffers (diagnostics / tests), at most `bytes` bytes */
 int df_kinfu_read_buffer(void *kinfu, int which, void *dst_host, size_t bytes);
+/* Lock-step parity hook (tests; never used by the frame loop's callers): one-shot replacements for the NEXT df_kinfu_process_* call.
+ * Each non-NULL argument replaces the corresponding intermediate result of that frame, so that everything downstream can be compared
+ * with a CPU run of the same frame BIT FOR BIT instead of statistically:
+ *   bilateral_depth_host  cols x rows u16: used instead of this frame's bilateral filter output (CUDA expf vs glibc expf: +-1 LSB);
+ *   pose12_host           absolute camera pose of the frame (R row-major, t): used instead of poses.back() * ICP(affine); ICP is skipped;
+ *   nodes_host            M x DF_NODE_STRIDE floats: the node table after the data-term solve (ignored unless M equals the loop's node count).
+ * NULL = compute as usual. */
+int df_kinfu_set_overrides(void *kinfu, const uint16_t *bilateral_depth_host, size_t pitch, const float *pose12_host, const float *nodes_host, int M);
 /* digest of the current state (multi-GPU correctness record, SURVEY 8e: ranks exchange it and rank 0 compares every rank's with a
  * single-GPU run of the same sequence): out4_host[0] order-independent 64-bit checksum of the packed volume, [1] the same over the node
  * table, [2] extracted cloud points, [3] FNV-style hash of every camera pose so far (bit patterns).  Synchronous. */
