@@ -57,6 +57,8 @@ PROTOTYPES = {
     "df_integrate_launch_count": (_i, [Volume]),
     "df_integrate_tracked": (_i, [Volume, _vp, _sz, _i, _i, Aff3f, Intr, _vp, _vp, _vp, _vp]),
     "df_raycast_points": (_i, [Volume, Aff3f, C.POINTER(C.c_float), Intr, _i, _i, _f, _f, _vp, _sz, _vp, _sz, _vp]),
+    "df_raycast_points_tracked": (_i, [Volume, Aff3f, C.POINTER(C.c_float), Intr, _i, _i, _f, _f, _vp, _sz, _vp, _sz, _vp, _vp]),
+    "df_raycast_points_stats_tracked": (_i, [Volume, Aff3f, C.POINTER(C.c_float), Intr, _i, _i, _f, _f, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _vp]),
     "df_raycast_touched_bytes": (_sz, [Volume]),
     "df_raycast_points_stats": (_i, [Volume, Aff3f, C.POINTER(C.c_float), Intr, _i, _i, _f, _f, _vp, _sz, _vp, _sz, _vp, _vp, _vp]),
     "df_project_workspace_bytes": (_sz, [_i, _i]),

@@ -60,6 +60,32 @@ static inline int div_up(int a, int b) { return (a + b - 1) / b; }
 
 // a voxel takes part in surface extraction iff W != 0 && F != 1.f (tsdf_volume.cu:548-633); 0x3c00 = half(1.0)
 __device__ __forceinline__ bool vox_active(uint32_t v) { return (v >> 16) != 0 && (v & 0xffffu) != 0x3c00u; }
+// F < 0 as the ray-cast's float comparison sees it: sign bit set, not -0, not NaN (a stored tsdf is never NaN)
+__device__ __forceinline__ bool vox_negative(uint32_t v) { return (v & 0x8000u) != 0 && (v & 0x7fffu) != 0 && (v & 0x7fffu) <= 0x7c00u; }
+
+// Brick table of the activity map (dfusion.h DF_BRICK): one byte per 8 x 8 x 8 brick of voxels, behind the per-stretch bytes, set when
+// an integration stores a voxel with F < 0 in the brick.  Host + device view of where it lives.
+struct BrickTable {
+    unsigned char *bytes;      // nullptr: not tracked
+    int nbx, nby, nbz;
+};
+__host__ __device__ inline size_t activity_stretch_bytes(int Dx, int Dy, int Dz)
+{
+    const size_t nvox = (size_t)Dx * Dy * Dz;
+    return (((nvox + DF_ACTIVITY_VOXELS - 1) / DF_ACTIVITY_VOXELS + 16) + 255) & ~(size_t)255;
+}
+__host__ __device__ inline BrickTable brick_table(unsigned char *activity, int Dx, int Dy, int Dz)
+{
+    BrickTable b;
+    b.nbx = (Dx + DF_BRICK - 1) / DF_BRICK; b.nby = (Dy + DF_BRICK - 1) / DF_BRICK; b.nbz = (Dz + DF_BRICK - 1) / DF_BRICK;
+    b.bytes = activity ? activity + activity_stretch_bytes(Dx, Dy, Dz) : nullptr;
+    return b;
+}
+// mark the brick of voxel (x, y, z); a quad of 4 x-adjacent voxels starting at a multiple of 4 lies in one brick
+__device__ __forceinline__ void brick_mark(const BrickTable &b, int x, int y, int z)
+{
+    b.bytes[((size_t)(z >> 3) * b.nby + (y >> 3)) * b.nbx + (x >> 3)] = 1;
+}
 
 // Programmatic dependent launch (sm_90+): a kernel launched through launch_pdl may be scheduled while its predecessor in the
 // stream is still draining; it must execute pdl_wait() before it touches anything the predecessor wrote (or overwrites anything

@@ -58,6 +58,7 @@ struct FusionParams {
     int zchunk;
     unsigned long long *counters;          // [0] voxels written, [1] voxels warped
     unsigned char *activity;
+    BrickTable bricks;
 };
 
 // metric depth maxima per FUS_TILE x FUS_TILE pixel tile
@@ -297,7 +298,10 @@ __device__ __forceinline__ void integrate_warped_body(const FusionParams &p)
             const int weight_new = min(weight_prev + wq, p.max_weight);
             const uint32_t val = (uint32_t)float_to_half_bits(tsdf_new) | ((uint32_t)weight_new << 16);
             *vptr = val;
-            if (p.activity && vox_active(val)) p.activity[(size_t)(vptr - p.data) / DF_ACTIVITY_VOXELS] = 1;
+            if (p.activity && vox_active(val)) {
+                p.activity[(size_t)(vptr - p.data) / DF_ACTIVITY_VOXELS] = 1;
+                if (vox_negative(val)) brick_mark(p.bricks, x, y, z);
+            }
             ++n_upd;
         }
     }
@@ -379,18 +383,19 @@ extern "C" int df_integrate_warped(df_volume vol, const uint16_t *depth, size_t 
     p.vol2cam = make_aff(v2c);
     p.cull = orthonormal_defect(vol2world) < 1e-3 && orthonormal_defect(world2cam) < 1e-3;
     {
-        static const char *const e = getenv("DF_FUSION_CULL");
+        const char *e = getenv("DF_FUSION_CULL");      // test knob, looked up per call (tests toggle it in-process; the kernel runs for milliseconds)
         if (e && atoi(e) == 0) p.cull = 0;
     }
     p.fx = intr.fx; p.fy = intr.fy; p.cx = intr.cx; p.cy = intr.cy;
     p.nodes = nodes; p.M = M; p.grid = node_grid;
     p.weight_scale = weight_scale;
     p.counters = counters; p.activity = activity;
+    p.bricks = brick_table(activity, vol.dims[0], vol.dims[1], vol.dims[2]);
     p.tiles_x = div_up(cols, FUS_TILE); p.tiles_y = div_up(rows, FUS_TILE);
     p.ctiles_x = div_up(p.tiles_x, FUS_COARSE); p.ctiles_y = div_up(p.tiles_y, FUS_COARSE);
     p.zchunk = vol.dims[2] >= 64 ? 32 : vol.dims[2];
     {
-        static const char *const e = getenv("DF_FUSION_ZCHUNK");
+        const char *e = getenv("DF_FUSION_ZCHUNK");    // test knob, per call
         if (e && atoi(e) > 0) p.zchunk = atoi(e);
     }
     float *ws = (float *)workspace;

@@ -47,6 +47,7 @@ struct KinFu {
     std::vector<uint16_t> ov_depth; bool has_ov_depth = false;       // bilateral-filtered depth, dense cols x rows
     float ov_pose[12]; bool has_ov_pose = false;                     // absolute camera pose of the frame
     std::vector<float> ov_nodes; bool has_ov_nodes = false;          // node table after the solve
+    bool raycast_bricks = true;          // DF_RAYCAST_BRICKS=0: dense march (A/B)
     long long solve_overflows = 0;       // frames whose solve was skipped because a normal-matrix row overflowed (solve.cu ROWCAP); info[11]
     long long last_cloud = -1;
     double host_us[4] = {0, 0, 0, 0}; long long host_frames = 0;   // DF_KINFU_HOSTPROF: launch A, ICP wait, launch B, total
@@ -228,8 +229,9 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_d
         dfh_aff_mul(inv, cam_pose, cam2vol);                           // pose_.inv() * camera_pose, tsdf_volume.cpp:162
         dfh_mat3_inv(cam2vol, Rinv);
         ++k.launches;
-        return df_raycast_points(vol, to_aff(cam2vol), Rinv, p.intr, p.cols, p.rows, p.raycast_step_factor, p.gradient_delta_factor,
-                                 (float *)pts.ptr, pts.pitch, (float *)nrm.ptr, nrm.pitch, s);
+        // the loop's own volume is only ever integrated through the activity map, so the march may skip the bricks without negative voxels
+        return df_raycast_points_tracked(vol, to_aff(cam2vol), Rinv, p.intr, p.cols, p.rows, p.raycast_step_factor, p.gradient_delta_factor,
+                                         (float *)pts.ptr, pts.pitch, (float *)nrm.ptr, nrm.pitch, k.raycast_bricks ? k.activity : nullptr, s);
     };
     auto extract = [&]() -> int {                                      // compute_points + compute_normals, tsdf_volume.cpp:313-325
         int st = df_extract_cloud_tracked(vol, p.volume_pose, k.cloud, p.cloud_capacity, k.cloud_count, k.extract_ws, k.activity, s);
@@ -456,6 +458,8 @@ extern "C" void *df_kinfu_create(const df_kinfu_params *pp)
         if (x && atoi(x) != 0) k->p.flags |= DF_KINFU_EXTEND_FIELD;
         const char *xr = getenv("DF_EXTEND_RADIUS");
         if (xr) k->p.extend_radius = (float)atof(xr);
+        const char *rb = getenv("DF_RAYCAST_BRICKS");
+        if (rb && atoi(rb) == 0) k->raycast_bricks = false;
         const char *w = getenv("DF_FUSION_WEIGHT_SCALE");
         if (w) k->p.fusion_weight_scale = (float)atof(w);
     }

@@ -235,17 +235,24 @@ class TsdfVolume:
                                               self.activity_.data_ptr() if self.activity_ is not None else None, None, _stream()))
         return world2cam
 
-    def raycast(self, camera_pose, intr, cols: int, rows: int):
+    def raycast(self, camera_pose, intr, cols: int, rows: int, dense: bool = False):
+        """dense=True forces the plain march (df_raycast_points) on a tracked volume; by default a tracked volume's march skips the
+        bricks without negative voxels (df_raycast_points_tracked) -- same maps bit for bit"""
         cam2vol = aff_mul(aff_inv(self.pose_), camera_pose)                           # tsdf_volume.cpp:162
         Rinv = np.linalg.inv(cam2vol[0].astype(np.float64)).astype(np.float32)
         pts = torch.empty((rows, cols, 4), dtype=torch.float32, device=self.device)
         nrm = torch.empty_like(pts)
-        capi.check(_lib().df_raycast_points(self._vol(), capi.make_aff(*cam2vol), capi.f9(Rinv), capi.make_intr(*intr), cols, rows,
-                                            self.raycast_step_factor_, self.gradient_delta_factor_, pts.data_ptr(), cols * 16,
-                                            nrm.data_ptr(), cols * 16, _stream()))
+        if self.activity_ is not None and not dense:
+            capi.check(_lib().df_raycast_points_tracked(self._vol(), capi.make_aff(*cam2vol), capi.f9(Rinv), capi.make_intr(*intr), cols, rows,
+                                                        self.raycast_step_factor_, self.gradient_delta_factor_, pts.data_ptr(), cols * 16,
+                                                        nrm.data_ptr(), cols * 16, self.activity_.data_ptr(), _stream()))
+        else:
+            capi.check(_lib().df_raycast_points(self._vol(), capi.make_aff(*cam2vol), capi.f9(Rinv), capi.make_intr(*intr), cols, rows,
+                                                self.raycast_step_factor_, self.gradient_delta_factor_, pts.data_ptr(), cols * 16,
+                                                nrm.data_ptr(), cols * 16, _stream()))
         return pts, nrm, (cam2vol, Rinv)
 
-    def raycast_stats(self, camera_pose, intr, cols: int, rows: int) -> dict:
+    def raycast_stats(self, camera_pose, intr, cols: int, rows: int, activity_ptr: int | None = None) -> dict:
         """df_raycast_points_stats: the ray-cast kernel instantiated with counters (measurement only).  Returns the unique voxels the
         launch reads (U of SURVEY 8d), the rays that produced a vertex, the march samples, and the algorithmic bytes 4*U + 32*cols*rows."""
         cam2vol = aff_mul(aff_inv(self.pose_), camera_pose)
@@ -254,9 +261,16 @@ class TsdfVolume:
         nrm = torch.empty_like(pts)
         touched = torch.zeros(int(_lib().df_raycast_touched_bytes(self._vol())) // 4, dtype=torch.int32, device=self.device)
         stats = torch.zeros(2, dtype=torch.int64, device=self.device)
-        capi.check(_lib().df_raycast_points_stats(self._vol(), capi.make_aff(*cam2vol), capi.f9(Rinv), capi.make_intr(*intr), cols, rows,
-                                                  self.raycast_step_factor_, self.gradient_delta_factor_, pts.data_ptr(), cols * 16,
-                                                  nrm.data_ptr(), cols * 16, touched.data_ptr(), stats.data_ptr(), _stream()))
+        if activity_ptr is None and self.activity_ is not None:     # activity_ptr = 0 forces the dense march on a tracked volume
+            activity_ptr = self.activity_.data_ptr()
+        if activity_ptr:
+            capi.check(_lib().df_raycast_points_stats_tracked(self._vol(), capi.make_aff(*cam2vol), capi.f9(Rinv), capi.make_intr(*intr), cols, rows,
+                                                              self.raycast_step_factor_, self.gradient_delta_factor_, pts.data_ptr(), cols * 16,
+                                                              nrm.data_ptr(), cols * 16, touched.data_ptr(), stats.data_ptr(), activity_ptr, _stream()))
+        else:
+            capi.check(_lib().df_raycast_points_stats(self._vol(), capi.make_aff(*cam2vol), capi.f9(Rinv), capi.make_intr(*intr), cols, rows,
+                                                      self.raycast_step_factor_, self.gradient_delta_factor_, pts.data_ptr(), cols * 16,
+                                                      nrm.data_ptr(), cols * 16, touched.data_ptr(), stats.data_ptr(), _stream()))
         unique = int(_popcount32(touched).sum().item())
         hits, samples = (int(v) for v in stats.cpu().numpy())
         return {"unique_voxels": unique, "hit_rays": hits, "march_samples": samples, "algorithmic_bytes": 4 * unique + 32 * cols * rows,

@@ -64,6 +64,13 @@ int df_integrate(df_volume vol, const uint16_t *dists, size_t dists_pitch, int c
  * return exactly the full scan's points.  The caller zeroes the map whenever it clears the volume and must route EVERY
  * integration of that volume through df_integrate_tracked. */
 #define DF_ACTIVITY_VOXELS 1024
+/* Second part of the same allocation (behind the per-stretch bytes, see df_volume_activity_bytes): a BRICK table, one byte per
+ * DF_BRICK x DF_BRICK x DF_BRICK block of voxels (brick (bx, by, bz) at ((bz * nby) + by) * nbx + bx, n* = ceil(dims / DF_BRICK)), non-zero iff an
+ * integration stored a voxel with F < 0 there since the map was last zeroed.  The ray-cast's march only ever acts on a sample pair that
+ * contains a negative value (tsdf_volume.cu:311-336: (-,+) stops the ray, (+,-) is the surface), so df_raycast_points_tracked replays the
+ * march's float chain without fetching from bricks that hold no negative voxel and returns exactly the dense march's maps.  The volume
+ * itself stays the reference's dense array (TsdfVolume::data()/swap() are part of its API): sparse traversal, not sparse storage. */
+#define DF_BRICK 8
 size_t df_volume_activity_bytes(df_volume vol);
 /* workspace (optional, device memory, df_integrate_workspace_bytes(cols, rows) bytes): per-tile maximum ray length of the frame,
  * used to skip the parts of the volume that lie behind the observed surface; NULL = allocated stream-ordered per call. */
@@ -79,6 +86,12 @@ int df_raycast_points(df_volume vol, df_aff3f cam2vol, const float *Rinv_host9, 
                       float step_factor, float delta_factor,
                       float *points, size_t points_pitch, float *normals, size_t normals_pitch, void *stream);
 
+/* same maps, bit for bit; the march skips the bricks that hold no negative voxel (activity: the volume's activity map, maintained by
+ * df_integrate_tracked / df_integrate_warped -- NULL falls back to df_raycast_points) */
+int df_raycast_points_tracked(df_volume vol, df_aff3f cam2vol, const float *Rinv_host9, df_intr intr, int cols, int rows,
+                              float step_factor, float delta_factor, float *points, size_t points_pitch, float *normals, size_t normals_pitch,
+                              const unsigned char *activity, void *stream);
+
 /* Measurement variant of df_raycast_points (bench.py's ray-cast roofline; never on the frame path): the same kernel instantiated with
  * counters.  touched: df_raycast_touched_bytes(vol) bytes, zeroed by the caller, one bit per voxel the launch reads (its popcount is U of
  * algorithmic bytes = 4*U + 32*cols*rows); stats (device, 2 x u64, zeroed by the caller): [0] rays that produced a vertex,
@@ -87,6 +100,13 @@ size_t df_raycast_touched_bytes(df_volume vol);
 int df_raycast_points_stats(df_volume vol, df_aff3f cam2vol, const float *Rinv_host9, df_intr intr, int cols, int rows,
                             float step_factor, float delta_factor, float *points, size_t points_pitch,
                             float *normals, size_t normals_pitch, unsigned int *touched, unsigned long long *stats, void *stream);
+
+/* the counting instantiation of df_raycast_points_tracked (activity != NULL: [1] counts the march samples EXAMINED; only those in
+ * negative bricks are fetched and appear in `touched`) */
+int df_raycast_points_stats_tracked(df_volume vol, df_aff3f cam2vol, const float *Rinv_host9, df_intr intr, int cols, int rows,
+                                    float step_factor, float delta_factor, float *points, size_t points_pitch,
+                                    float *normals, size_t normals_pitch, unsigned int *touched, unsigned long long *stats,
+                                    const unsigned char *activity, void *stream);
 
 /* device::project_and_remove (internal.hpp:108-109, tsdf_volume.cu:114-137,164-177): `dists` is sampled as fp16 and
  * the pixels the vertices land on are zeroed; vertices become (u*Dp, v*Dp, Dp, 0) or NaN when off-image.

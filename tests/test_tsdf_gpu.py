@@ -167,6 +167,53 @@ def test_tracked_extraction_equals_full_scan(orc):
     assert int(vols[1].activity_.sum().item()) == 0 and int(vols[1].fetchCloud(1000)[1].item()) == 0
 
 
+def _roty(deg, t):
+    a = np.deg2rad(deg)
+    R = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]], np.float32)
+    return R, np.asarray(t, np.float32)
+
+
+@pytest.mark.parametrize("dim", [128, 256])
+def test_tracked_raycast_equals_dense_march(orc, dim):
+    """df_raycast_points_tracked: the march replays its float chain but only fetches from 8^3 bricks that hold a negative voxel (brick
+    table of the activity map).  Maps must be those of the dense march BIT FOR BIT from every viewpoint -- front, oblique, and from
+    BEHIND the surface (rays that meet unobserved -> negative -> positive, the (-,+) stop rule) -- and the table must cover exactly
+    the bricks that hold negative voxels."""
+    v = host.TsdfVolume((dim, dim, dim), track_activity=True)
+    v.setTruncDist(0.04); v.setMaxWeight(64); v.setSize((1.0, 1.0, 1.0)); v.setPose(synth.volume_pose(1.0))
+    v.setRaycastStepFactor(0.75); v.setGradientDeltaFactor(0.5); v.clear()
+    for t in range(3):
+        dists = host.computeDists(host.u16_to_device(synth.umbrella_depth(t)), K)
+        pose = synth.camera_drift(4 * t)
+        v.integrate(dists, (pose[0].astype(np.float32), pose[1].astype(np.float32)), K)
+    vol = v.data_.cpu().numpy().view(np.uint32)
+    f = (vol & 0xffff).astype(np.uint16).view(np.float16).astype(np.float32).reshape(dim, dim, dim)
+    nb = dim // 8
+    neg_bricks = (f < 0).reshape(nb, 8, nb, 8, nb, 8).any(axis=(1, 3, 5))
+    off = ((dim ** 3 // 1024 + 16) + 255) // 256 * 256
+    table = v.activity_.cpu().numpy()[off: off + nb ** 3].reshape(nb, nb, nb) != 0
+    assert np.array_equal(table, neg_bricks) and 0 < neg_bricks.mean() < 0.2
+    views = [host.identity_pose(), _tilted_pose(), _roty(30.0, (-0.55, 0.05, 0.25)), _roty(180.0, (0.0, 0.0, 2.3)), _roty(140.0, (0.5, -0.1, 1.9))]
+    hits = []
+    for cam in views:
+        pd, nd, (cam2vol, Rinv) = v.raycast(cam, K, 640, 480, dense=True)
+        pt, nt, _ = v.raycast(cam, K, 640, 480)
+        assert torch.equal(pd.view(torch.int32), pt.view(torch.int32)) and torch.equal(nd.view(torch.int32), nt.view(torch.int32))
+        hits.append(int((~torch.isnan(pd[..., 0])).sum().item()))
+    assert hits[0] > 100_000 and min(hits[:3]) > 20_000
+    # the dense march against the oracle for the view from behind (the other views are covered by the parity tests above)
+    cam = views[3]
+    pd, nd, (cam2vol, Rinv) = v.raycast(cam, K, 640, 480)
+    rp, rn, _ = orc.raycast_points(vol, v.getDims(), v.getVoxelSize(), v.getTruncDist(), v.getMaxWeight(), cam2vol, Rinv, K, 640, 480, 0.75, 0.5)
+    assert np.array_equal(pd.cpu().numpy().view(np.uint32), rp.view(np.uint32)) and np.array_equal(nd.cpu().numpy().view(np.uint32), rn.view(np.uint32))
+    # what the skipping buys: unique voxels read by one launch (counting instantiation), front view
+    dense = v.raycast_stats(views[0], K, 640, 480, activity_ptr=0)
+    tracked = v.raycast_stats(views[0], K, 640, 480)
+    assert tracked["hit_rays"] == dense["hit_rays"] == hits[0]
+    assert tracked["unique_voxels"] < 0.6 * dense["unique_voxels"]
+    print(f"dim {dim}: unique voxels read dense {dense['unique_voxels']} tracked {tracked['unique_voxels']}")
+
+
 @pytest.mark.parametrize("impl", ["1", "2"])
 def test_integrate_alternative_kernels_bit_exact_in_subprocess(orc, impl):
     """the integrate kernel is selected per process (DF_INTEGRATE_IMPL): 3 = default (v1 arithmetic + warp-level visibility culling,
