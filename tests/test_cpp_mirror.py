@@ -149,3 +149,37 @@ def test_ply_export_cpp_and_python_agree(tmp_path):
     nrm[5, 1] = np.nan
     assert host.save_ply(tmp_path / "py.ply", cloud, nrm) == 6
     assert (tmp_path / "py.ply").read_bytes() == (tmp_path / "with_normals.ply").read_bytes()
+
+
+def test_cmake_package_builds_installs_and_is_consumable(tmp_path):
+    """a CMake package for C++ consumers.  Configure + build + install the two libraries with the top-level
+    CMakeLists.txt, then build tests/cpp/demo_like.cpp in a separate CMake project through find_package(dynamicfusion_b200)."""
+    import shutil
+    cmake = shutil.which("cmake")
+    if not cmake or not Path("/usr/local/cuda/bin/nvcc").exists():
+        pytest.skip("cmake / nvcc not available")
+    gen = ["-G", "Ninja"] if shutil.which("ninja") else []
+    build, prefix = tmp_path / "build", tmp_path / "prefix"
+    env = dict(os.environ, CUDACXX="/usr/local/cuda/bin/nvcc")
+    for cmd in ([cmake, "-S", str(ROOT), "-B", str(build), *gen, "-DCMAKE_CUDA_COMPILER=/usr/local/cuda/bin/nvcc"],
+                [cmake, "--build", str(build), "-j", "8"], [cmake, "--install", str(build), "--prefix", str(prefix)]):
+        r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=1500)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert (prefix / "lib" / "libdfusion.so").exists() and (prefix / "lib" / "libkfusion.so").exists()
+    assert (prefix / "include" / "dfusion.h").exists() and (prefix / "include" / "kfusion" / "kinfu.hpp").exists()
+    # every symbol the header declares is exported by the CMake-built library too
+    from dynamicfusion_b200 import capi
+    syms = subprocess.run(["nm", "-D", "--defined-only", str(prefix / "lib" / "libdfusion.so")], capture_output=True, text=True).stdout
+    assert all(f" T {name}\n" in syms for name in capi.PROTOTYPES), [n for n in capi.PROTOTYPES if f" T {n}\n" not in syms]
+    consumer = tmp_path / "consumer"
+    consumer.mkdir()
+    (consumer / "CMakeLists.txt").write_text(
+        "cmake_minimum_required(VERSION 3.24)\nproject(consumer LANGUAGES CXX CUDA)\nset(CMAKE_CXX_STANDARD 17)\n"
+        "find_package(dynamicfusion_b200 CONFIG REQUIRED)\nfind_package(CUDAToolkit REQUIRED)\n"
+        f"add_executable(demo_like {ROOT / 'tests' / 'cpp' / 'demo_like.cpp'})\n"
+        "target_link_libraries(demo_like PRIVATE dynamicfusion_b200::kfusion CUDA::cudart)\n")
+    for cmd in ([cmake, "-S", str(consumer), "-B", str(consumer / "b"), *gen, f"-DCMAKE_PREFIX_PATH={prefix}", "-DCMAKE_CUDA_COMPILER=/usr/local/cuda/bin/nvcc",
+                 "-DCMAKE_CUDA_ARCHITECTURES=100a"], [cmake, "--build", str(consumer / "b")]):
+        r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert (consumer / "b" / "demo_like").exists()
