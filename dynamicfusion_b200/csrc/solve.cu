@@ -392,7 +392,8 @@ __global__ void __launch_bounds__(LM_THREADS) solve_lm_kernel(float *nodes, int 
 
     double radius = 1e4, decrease = 2.0;          // solverGPUGaussNewton.t:26-39
     int it = 0, pcg_total = 0;
-    if (ws.flags[0]) nl_iters = 0;                // a row overflowed: leave the field unchanged (see solve_lm_v5_kernel)
+    const bool overflow = ws.flags[0] != 0;       // a row overflowed: leave the field unchanged (see solve_lm_v5_kernel)
+    if (overflow) nl_iters = 0;
     for (; it < nl_iters; ++it) {
         // g = gb - A x
         spmv(ws, M, x, Ap);
@@ -475,7 +476,7 @@ __global__ void __launch_bounds__(LM_THREADS) solve_lm_kernel(float *nodes, int 
         }
     }
     // write back: encodeTranslation (CombinedSolver.h:189-197, dual_quaternion.hpp:82-85)
-    for (int n = tid; n < M; n += LM_THREADS) {
+    for (int n = tid; n < M && !overflow; n += LM_THREADS) {
         float *nd = nodes + (size_t)n * DF_NODE_STRIDE;
         const Quat rot = {nd[3], nd[4], nd[5], nd[6]};
         const Quat h = qhalf(Quat{0.f, (float)x[n], (float)x[M + n], (float)x[2 * M + n]});
@@ -598,8 +599,8 @@ __device__ __forceinline__ void cluster_sum5(Lm5Smem<NCTA> &sm, Lm5Sync &sy, int
 
 // NCTA = CTAs per cluster (8, or 16 = the non-portable maximum: half the rows, hence half the shared-memory gather traffic of the
 // mat-vec, per SM); the cluster shape is a launch attribute.
-template <int NCTA>
-__global__ void __launch_bounds__(LM4_THREADS)
+template <int NCTA, bool merged>
+__global__ void __launch_bounds__(LM4_THREADS, 1)
 solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_iters, int lin_iters, double *stats, int ent_cap)
 {
     DF_PDL_ENTRY();
@@ -723,7 +724,8 @@ solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
 
     double radius = 1e4, decrease = 2.0;                       // solverGPUGaussNewton.t:26-39
     int it = 0, pcg_total = 0;
-    if (ws.flags[0]) nl_iters = 0;                             // a row overflowed (solve_rows): the stored system is truncated -> leave the field unchanged, stats[5] says so
+    const bool overflow = ws.flags[0] != 0;                    // a row overflowed (solve_rows): the stored system is truncated -> leave the field
+    if (overflow) nl_iters = 0;                                // unchanged (not even re-encoded), stats[5] says so
     for (; it < nl_iters; ++it) {
         spmv(Ap0, Ap1, Ap2);                                   // svec holds x here
         double rzv[1] = {0.0};
@@ -741,7 +743,42 @@ solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
         publish(p0, p1, p2);                                   // ... so p may overwrite it
         double rz = rzv[0];
         double Q0 = 0.0;
-        for (int l = 0; l < lin_iters && rz > 0.0; ++l) {
+        // One cluster-wide reduction per PCG step instead of two (DF_SOLVE_MERGED, default on).  The second reduction of the textbook
+        // step only exists because r.z and the model value Q are formed AFTER alpha is known.  Both follow from sums that do not need
+        // alpha:   r' = r - alpha Ap,  z' = M r'   =>   r'.z' = r.Mr - 2 alpha (r.M Ap) + alpha^2 (Ap.M Ap)
+        //          Q(d + alpha p) = Q(d) - alpha p.r + alpha^2/2 p.Ap = Q(d) - alpha/2 (r.Mr)      (p.r = r.z, alpha = r.z / p.Ap)
+        // so p.Ap, r.Mr, r.MAp and Ap.MAp are summed in ONE exchange, after which every CTA knows alpha, beta and Q and updates its
+        // rows: the iterates are the textbook ones up to rounding (r.Mr is re-measured every step: nothing drifts), with two DSMEM
+        // round trips per step (sum, publish) instead of three.
+        for (int l = 0; merged && l < lin_iters && rz > 0.0; ++l) {
+            spmv(Ap0, Ap1, Ap2);
+            double v[4] = {0.0, 0.0, 0.0, 0.0};
+            if (owner) {
+                double m, n;
+                Ap0 = Ap0 + cdn * p0; m = mi * r0; n = mi * Ap0; v[0] += p0 * Ap0; v[1] += m * r0; v[2] += m * Ap0; v[3] += n * Ap0;
+                Ap1 = Ap1 + cdn * p1; m = mi * r1; n = mi * Ap1; v[0] += p1 * Ap1; v[1] += m * r1; v[2] += m * Ap1; v[3] += n * Ap1;
+                Ap2 = Ap2 + cdn * p2; m = mi * r2; n = mi * Ap2; v[0] += p2 * Ap2; v[1] += m * r2; v[2] += m * Ap2; v[3] += n * Ap2;
+            }
+            cluster_sum5<NCTA>(sm, sy, cta, v);                      // every CTA finished reading svec (p)
+            if (!(v[0] > 0.0) || !(v[1] > 0.0)) break;
+            const double rz_now = v[1];
+            const double alpha = rz_now / v[0];
+            const double rz_new = rz_now - 2.0 * alpha * v[2] + alpha * alpha * v[3];
+            const double Q1 = Q0 - 0.5 * alpha * rz_now;
+            const double beta = rz_new / rz_now;
+            if (owner) {
+                dl0 = dl0 + alpha * p0; r0 = r0 - alpha * Ap0; p0 = r0 * mi + beta * p0;
+                dl1 = dl1 + alpha * p1; r1 = r1 - alpha * Ap1; p1 = r1 * mi + beta * p1;
+                dl2 = dl2 + alpha * p2; r2 = r2 - alpha * Ap2; p2 = r2 * mi + beta * p2;
+            }
+            rz = rz_new;
+            ++pcg_total;
+            const double zeta = (double)(l + 1) * (Q1 - Q0) / Q1;   // Ceres/Opt q-tolerance, solverGPUGaussNewton.t:1093-1101
+            Q0 = Q1;
+            publish(p0, p1, p2);
+            if (zeta < 1e-4) break;
+        }
+        for (int l = 0; !merged && l < lin_iters && rz > 0.0; ++l) {
             spmv(Ap0, Ap1, Ap2);
             double pap[1] = {0.0};
             if (owner) {
@@ -800,7 +837,7 @@ solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
     }
     cluster.sync();                                            // no CTA may exit while others can still write into its shared memory
     // write back: encodeTranslation (CombinedSolver.h:189-197, dual_quaternion.hpp:82-85)
-    if (owner) {
+    if (owner && !overflow) {
         float *nd = nodes + (size_t)n * DF_NODE_STRIDE;
         const Quat rot = {nd[3], nd[4], nd[5], nd[6]};
         const Quat h = qhalf(Quat{0.f, (float)x0, (float)x1, (float)x2});
@@ -863,13 +900,13 @@ extern "C" int df_solve_data_term(float *nodes, int M, const void *node_grid, co
     if (solve_lm_impl() >= 5 && Lb.rpc * Lb.tpr <= LM4_THREADS && Lb.total + (size_t)LM4_THREADS * 10 * 8 <= budget) {
         const int cap = (int)((budget - Lb.total - 16) / ((size_t)LM4_THREADS * 10));
         const Lm4Layout Lc = lm4_layout(M, cap, ncta);
+        static const int merged = [] { const char *e = getenv("DF_SOLVE_MERGED"); return e ? atoi(e) : 1; }();
+        using KernelT = void (*)(float *, int, const void *, SolveWs, int, int, double *, int);
+        const KernelT kern = ncta == 16 ? (merged ? (KernelT)solve_lm_v5_kernel<16, true> : (KernelT)solve_lm_v5_kernel<16, false>)
+                                        : (merged ? (KernelT)solve_lm_v5_kernel<8, true> : (KernelT)solve_lm_v5_kernel<8, false>);
         // function attributes are per device: set them on every launch (cheap) rather than once per process
-        if (ncta == 16) {
-            cudaFuncSetAttribute(solve_lm_v5_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
-            cudaFuncSetAttribute(solve_lm_v5_kernel<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        } else {
-            cudaFuncSetAttribute(solve_lm_v5_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-        }
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ncta == 16 ? 216 * 1024 : 224 * 1024);
+        if (ncta == 16) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(ncta); cfg.blockDim = dim3(LM4_THREADS); cfg.dynamicSmemBytes = Lc.total; cfg.stream = s;
         cudaLaunchAttribute at[2];
@@ -878,9 +915,7 @@ extern "C" int df_solve_data_term(float *nodes, int M, const void *node_grid, co
         at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[1].val.programmaticStreamSerializationAllowed = pdl_enabled();
         cfg.attrs = at; cfg.numAttrs = 2;
-        cudaError_t le;
-        if (ncta == 16) le = cudaLaunchKernelEx(&cfg, solve_lm_v5_kernel<16>, nodes, M, node_grid, ws, nonlinear_iters, linear_iters, stats_dev, cap);
-        else le = cudaLaunchKernelEx(&cfg, solve_lm_v5_kernel<8>, nodes, M, node_grid, ws, nonlinear_iters, linear_iters, stats_dev, cap);
+        const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, nodes, M, node_grid, ws, nonlinear_iters, linear_iters, stats_dev, cap);
         if (le != cudaSuccess) return (int)le;
     } else {
         solve_lm_kernel<<<1, LM_THREADS, 0, s>>>(nodes, M, ws, nonlinear_iters, linear_iters, stats_dev);

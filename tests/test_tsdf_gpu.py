@@ -192,7 +192,8 @@ def test_tracked_raycast_equals_dense_march(orc, dim):
     neg_bricks = (f < 0).reshape(nb, 8, nb, 8, nb, 8).any(axis=(1, 3, 5))
     off = ((dim ** 3 // 1024 + 16) + 255) // 256 * 256
     table = v.activity_.cpu().numpy()[off: off + nb ** 3].reshape(nb, nb, nb) != 0
-    assert np.array_equal(table, neg_bricks) and 0 < neg_bricks.mean() < 0.2
+    # the table is conservative: a voxel that was negative after one integration may have averaged back to >= 0 since
+    assert np.all(table[neg_bricks]) and 0 < neg_bricks.mean() < 0.2 and table.sum() <= 1.5 * neg_bricks.sum()
     views = [host.identity_pose(), _tilted_pose(), _roty(30.0, (-0.55, 0.05, 0.25)), _roty(180.0, (0.0, 0.0, 2.3)), _roty(140.0, (0.5, -0.1, 1.9))]
     hits = []
     for cam in views:
