@@ -587,7 +587,8 @@ __device__ __forceinline__ void cluster_sum5(Lm5Smem<NCTA> &sm, Lm5Sync &sy, int
     }
     mbar_wait(bar, sy.phase_red[par]);
     sy.phase_red[par] ^= 1u;
-#pragma unroll
+    // (not unrolled over k: with NV = 4 and NCTA = 16 the compiler hoists all 64 loads and spills the PCG state)
+#pragma unroll 1
     for (int k = 0; k < NV; ++k) {
         double t = 0.0;
 #pragma unroll

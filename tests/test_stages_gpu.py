@@ -332,15 +332,17 @@ def test_solve_large_matches_matrix_free_oracle(orc):
 
 
 def test_solve_row_overflow_is_loud_and_leaves_the_field_unchanged():
-    """ADVICE r1 (solve.cu ROWCAP): a node row that couples to more columns than the kernels store must not be solved truncated.  700 nodes
-    on a sphere, 60k vertices near its centre: every vertex's 8 nearest nodes are an arbitrary subset, so every row couples to (nearly)
-    all 700 columns > 512.  Expected: stats[5] raised, 0 LM iterations, node translations bit-identical to their input."""
+    """ADVICE r1 (solve.cu ROWCAP): a node row that couples to more columns than the kernels store must not be solved truncated.  One
+    node at the centre of a sphere of 700 others, 60k vertices at 0.45 R in random directions: every vertex's nearest node is the
+    central one, its other seven are the sphere nodes in its direction -- the central node's row couples to (nearly) all 700 columns
+    > 512.  Expected: stats[5] raised, 0 LM iterations, the node table bit-identical to its input."""
     rng = np.random.default_rng(11)
-    M, N = 700, 60000
-    d = rng.normal(size=(M, 3))
-    node_pts = (0.5 * d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    M, N = 701, 60000
+    d = rng.normal(size=(M - 1, 3))
+    node_pts = np.concatenate([np.zeros((1, 3)), 0.5 * d / np.linalg.norm(d, axis=1, keepdims=True)]).astype(np.float32)
+    v = rng.normal(size=(N, 3))
     src = np.zeros((N, 4), np.float32)
-    src[:, :3] = rng.normal(scale=2e-3, size=(N, 3))
+    src[:, :3] = 0.45 * 0.5 * v / np.linalg.norm(v, axis=1, keepdims=True)
     dst = src.copy()
     dst[:, 0] += 0.01
     wf = host.WarpField()
@@ -349,4 +351,3 @@ def test_solve_row_overflow_is_loud_and_leaves_the_field_unchanged():
     stats = wf.optimiseWarpData(torch.from_numpy(src).cuda(), torch.from_numpy(dst).cuda(), 5, 100, 0).cpu().numpy()
     assert stats[5] == 1 and stats[2] == 0
     assert torch.equal(before, wf.nodes_)
-    # the one-block fallback kernel applies the same rule (covered through the environment switch in test_configs_gpu)
