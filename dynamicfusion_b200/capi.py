@@ -43,6 +43,12 @@ class KinfuParams(C.Structure):
                 ("fusion_weight_scale", C.c_float), ("extend_radius", C.c_float)]
 
 
+class F2Params(C.Structure):
+    """df_f2_params (include/dfusion.h)"""
+    _fields_ = [("reg_lambda", C.c_double), ("tukey_c", C.c_double), ("huber_delta", C.c_double), ("lm_mu", C.c_double),
+                ("gn_iters", C.c_int), ("reg_k", C.c_int), ("flags", C.c_int), ("lin_iters", C.c_int)]
+
+
 _vp, _sz, _i, _f = C.c_void_p, C.c_size_t, C.c_int, C.c_float
 
 # name -> (restype, argtypes); must list every symbol declared in include/dfusion.h
@@ -96,6 +102,9 @@ PROTOTYPES = {
     "df_solve_workspace_bytes": (_sz, [_i, _i]),
     "df_solve_knn_buffers": (_i, [_vp, _i, _i, C.POINTER(_vp), C.POINTER(_vp)]),
     "df_solve_data_term": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "df_solve_f2_workspace_bytes": (_sz, [_i, _i, _i]),
+    "df_solve_f2": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, C.POINTER(F2Params), _vp, _vp, _vp]),
+    "df_kinfu_set_f2_params": (_i, [_vp, C.POINTER(F2Params)]),
     "df_kinfu_default_params": (None, [C.POINTER(KinfuParams), _i]),
     "df_kinfu_create": (_vp, [C.POINTER(KinfuParams)]),
     "df_kinfu_destroy": (None, [_vp]),

@@ -35,6 +35,7 @@ struct KinFu {
     float *nodes = nullptr; int M = 0; void *node_grid = nullptr;
     float *icp_T = nullptr; int *icp_ok = nullptr; double *icp_scratch = nullptr;
     void *solve_ws = nullptr; size_t solve_ws_bytes = 0; double *solve_stats = nullptr;
+    double *f2_stats = nullptr;
     void *extract_ws = nullptr; void *project_ws = nullptr;
     void *integrate_ws = nullptr;
     void *extend_ws = nullptr; int *M_dev = nullptr;   // df_extend_field workspace / new node count (DF_KINFU_EXTEND_FIELD)
@@ -47,6 +48,7 @@ struct KinFu {
     std::vector<uint16_t> ov_depth; bool has_ov_depth = false;       // bilateral-filtered depth, dense cols x rows
     float ov_pose[12]; bool has_ov_pose = false;                     // absolute camera pose of the frame
     std::vector<float> ov_nodes; bool has_ov_nodes = false;          // node table after the solve
+    df_f2_params f2; void *f2_ws = nullptr;      // DF_KINFU_F2_SOLVE
     bool raycast_bricks = true;          // DF_RAYCAST_BRICKS=0: dense march (A/B)
     long long solve_overflows = 0;       // frames whose solve was skipped because a normal-matrix row overflowed (solve.cu ROWCAP); info[11]
     long long last_cloud = -1;
@@ -335,10 +337,17 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_d
         CKD(df_warp(k.nodes, k.M, k.node_grid, (float *)k.canon.ptr, (float *)k.canon_nrm.ptr, npix, 4, ident, 0, nullptr, nullptr, s));   // :385
         ++k.launches;
         mark(k, 4);
+        const bool f2_solve = (p.flags & DF_KINFU_F2_SOLVE) != 0;
+        if (f2_solve) {
+            // robust 6-DoF data term + regulariser instead of the reference's translation-only data term (opt-in)
+            CKD(df_solve_f2(k.nodes, k.M, k.node_grid, (const float *)k.canon.ptr, (const float *)k.cur_pts[0].ptr, npix, 4, &k.f2, k.f2_stats, k.f2_ws, s));
+            k.launches += 6 + (k.f2.gn_iters + 1) * 4 + k.f2.gn_iters * (3 + 3 * k.f2.lin_iters);
+        } else {
         CKD(df_solve_data_term(k.nodes, k.M, k.node_grid, (const float *)k.canon.ptr, (const float *)k.cur_pts[0].ptr, npix, 4,
                                p.solver_nonlinear_iters, p.solver_linear_iters,
                                (p.flags & DF_KINFU_REF_GRAPH_QUIRK) ? DF_SOLVE_REF_GRAPH_QUIRK : 0, k.solve_stats, k.solve_ws, s));   // :387
         k.launches += 5;                                               // prepare, scan, fill, rows, lm
+        }
         // row-overflow flag of this solve (stats[5]): lands in pinned memory, looked at after the next stream synchronisation
         CK(cudaMemcpyAsync(k.pinned + 14, k.solve_stats + 5, sizeof(double), cudaMemcpyDeviceToHost, s));
         if (k.has_ov_nodes) {          // lock-step parity hook: the caller's solved node table (CPU and GPU PCG round differently in the last bits)
@@ -349,7 +358,9 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_d
             k.has_ov_nodes = false;
         }
         mark(k, 5);
-        {
+        if (f2_solve) {
+            CKD(df_warp(k.nodes, k.M, k.node_grid, (float *)k.canon.ptr, (float *)k.canon_nrm.ptr, npix, 4, ident, 0, nullptr, nullptr, s));
+        } else {
             // second warp (:389) queries exactly the vertices the solve just built its graph for (CombinedSolver.h:66-84):
             // re-use those neighbours + weights instead of a third k-NN pass
             int32_t *knn_idx; float *knn_w;
@@ -458,6 +469,8 @@ extern "C" void *df_kinfu_create(const df_kinfu_params *pp)
         if (x && atoi(x) != 0) k->p.flags |= DF_KINFU_EXTEND_FIELD;
         const char *xr = getenv("DF_EXTEND_RADIUS");
         if (xr) k->p.extend_radius = (float)atof(xr);
+        const char *f2e = getenv("DF_KINFU_F2_SOLVE");
+        if (f2e && atoi(f2e) != 0) k->p.flags |= DF_KINFU_F2_SOLVE;
         const char *rb = getenv("DF_RAYCAST_BRICKS");
         if (rb && atoi(rb) == 0) k->raycast_bricks = false;
         const char *w = getenv("DF_FUSION_WEIGHT_SCALE");
@@ -490,6 +503,9 @@ extern "C" void *df_kinfu_create(const df_kinfu_params *pp)
          cudaMalloc(&k->icp_scratch, (size_t)DF_ICP_SCRATCH_DOUBLES * 8) == cudaSuccess;
     k->solve_ws_bytes = df_solve_workspace_bytes(maxM, p.cols * p.rows);
     ok = ok && cudaMalloc(&k->solve_ws, k->solve_ws_bytes) == cudaSuccess && cudaMalloc(&k->solve_stats, 64) == cudaSuccess;
+    k->f2 = df_f2_params{5.0, 0.05, 1e-4, 1e-4, 2, 4, DF_F2_TWIST | DF_F2_TUKEY | DF_F2_HUBER, 30};
+    if (p.flags & DF_KINFU_F2_SOLVE)
+        ok = ok && cudaMalloc(&k->f2_ws, df_solve_f2_workspace_bytes(maxM, p.cols * p.rows, 7)) == cudaSuccess && cudaMalloc(&k->f2_stats, 16 * 8) == cudaSuccess;
     df_volume v = vol_of(*k);
     ok = ok && cudaMalloc(&k->extract_ws, df_extract_workspace_bytes(v)) == cudaSuccess;
     ok = ok && cudaMalloc(&k->integrate_ws, df_integrate_workspace_bytes(p.cols, p.rows)) == cudaSuccess;
@@ -527,6 +543,7 @@ extern "C" void df_kinfu_destroy(void *h)
     cudaFree(k->canon.ptr); cudaFree(k->canon_nrm.ptr); cudaFree(k->canon_visible.ptr);
     cudaFree(k->cloud); cudaFree(k->cloud_nrm); cudaFree(k->cloud_count); cudaFree(k->nodes); cudaFree(k->node_grid);
     cudaFree(k->icp_T); cudaFree(k->icp_ok); cudaFree(k->icp_scratch); cudaFree(k->solve_ws); cudaFree(k->solve_stats);
+    cudaFree(k->f2_ws); cudaFree(k->f2_stats);
     cudaFree(k->extract_ws); cudaFree(k->project_ws); cudaFree(k->activity); cudaFree(k->integrate_ws); cudaFree(k->fusion_ws); cudaFree(k->extend_ws); cudaFree(k->M_dev); cudaFreeHost(k->pinned); cudaFree(k->n_upd);
     for (int e = 0; e <= NSTAGES; ++e) if (k->ev[e]) cudaEventDestroy(k->ev[e]);
     delete k;
@@ -638,6 +655,7 @@ extern "C" int df_kinfu_get_buffer(void *h, int which, void **ptr, size_t *pitch
         case 11: im.ptr = k->nodes; im.pitch = DF_NODE_STRIDE * 4; im.cols = 1; im.rows = k->M; break;
         case 12: im = k->canon_visible; break;
         case 13: im.ptr = k->solve_stats; im.pitch = 64; im.cols = 8; im.rows = 1; break;
+        case 15: im.ptr = k->f2_stats; im.pitch = 128; im.cols = 16; im.rows = 1; break;
         case 14: im.ptr = k->activity; im.pitch = k->activity_bytes; im.cols = (int)k->activity_bytes; im.rows = 1; break;
         default: return (int)cudaErrorInvalidValue;
     }
@@ -670,6 +688,15 @@ extern "C" int df_kinfu_set_overrides(void *h, const uint16_t *bilateral_depth_h
     if (pose12_host) memcpy(k->ov_pose, pose12_host, 48);
     k->has_ov_nodes = nodes_host != nullptr && M > 0;
     if (k->has_ov_nodes) k->ov_nodes.assign(nodes_host, nodes_host + (size_t)M * DF_NODE_STRIDE);
+    return 0;
+}
+
+extern "C" int df_kinfu_set_f2_params(void *h, const df_f2_params *prm)
+{
+    KinFu *k = (KinFu *)h;
+    if (!prm) return (int)cudaErrorInvalidValue;
+    k->f2 = *prm;
+    if (k->f2.reg_k > 7) k->f2.reg_k = 7;
     return 0;
 }
 

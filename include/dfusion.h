@@ -272,6 +272,30 @@ int df_solve_knn_buffers(void *workspace, int M, int N, int32_t **idx, float **w
 int df_solve_data_term(float *nodes, int M, const void *node_grid, const float *canon, const float *live, int N, int stride,
                        int nonlinear_iters, int linear_iters, int flags, double *stats_dev, void *workspace, void *stream);
 
+/* SURVEY.md 8f(2), OPT-IN beside df_solve_data_term: the robust data term over 6-DoF node increments plus the regularisation term -- the
+ * energy the reference defines piecewise and never assembles (6-wide parameter blocks optimisation.hpp:108-110,141-143; tukeyPenalty :84-88,
+ * dynamicfusion.t:43-51; huberPenalty optimisation.hpp:134-138, dynamicfusion.t:34-40; empty DynamicFusionRegEnergy :125-132 /
+ * WarpField::energy_reg warp_field.cpp:168-172; KinFu::edges_ kinfu.hpp:95).  PARITY UNPINNED (no reference code evaluates it); restated in
+ * oracle/orc_reg.c, solved in csrc/regsolve.cu:
+ *   E = sum_v sum_c rho_T(live_v - warp(canon_v))_c  +  reg_lambda sum_(i,j) max(weight_i, weight_j) sum_c rho_H(T_i(g_j) - T_j(g_j))_c
+ * warp = WarpField::DQB + transform over the 8 nearest nodes; T_k(p) = rotate(q_k, p) + t_k; j runs over the reg_k (<= 7) nearest other nodes
+ * of node i; rho_T' = tukeyPenalty(., tukey_c) (DF_F2_TUKEY, else squared loss); rho_H = huberPenalty(., huber_delta) (DF_F2_HUBER, else
+ * squared loss).  Unknowns per node: (omega, tau), q <- exp(omega) q, t <- t + tau (DF_F2_TWIST; without it omega = 0: translation-only).
+ * Gauss-Newton / IRLS, gn_iters steps, each solved by block-Jacobi PCG (at most lin_iters steps) with Levenberg damping lm_mu * diag(H).
+ * Nodes are updated in place (rotation + dual part).  stats_dev (device, 16 doubles): [0] energy before, [1] energy after, [2] GN steps,
+ * [3] valid vertices, [4] data energy after, [5] regularisation energy after, [6] edge slots, [7] PCG steps in total, [8 + i] energy before
+ * GN step i (i < 8).  workspace: df_solve_f2_workspace_bytes(M, N, reg_k). */
+typedef struct df_f2_params {
+    double reg_lambda, tukey_c, huber_delta, lm_mu;   /* 0 = no regulariser, 0.01, 1e-4 (the reference's defaults for c and delta), 1e-4 */
+    int gn_iters, reg_k, flags, lin_iters;
+} df_f2_params;
+#define DF_F2_TWIST 1
+#define DF_F2_TUKEY 2
+#define DF_F2_HUBER 4
+size_t df_solve_f2_workspace_bytes(int M, int N, int reg_k);
+int df_solve_f2(float *nodes, int M, const void *node_grid, const float *canon, const float *live, int N, int stride,
+                const df_f2_params *params, double *stats_dev, void *workspace, void *stream);
+
 /* ------------------------------------------------------------------ per-frame pipeline ----------------------------------------------------- */
 /* kfusion::KinFuParams (kinfu.hpp:15-47) as a POD, plus the solver settings KinFu::KinFu hard-codes (kinfu.cpp:114-120)
  * and the knobs of the GPU-resident warp field. */
@@ -306,6 +330,9 @@ typedef struct df_kinfu_params {
                                       (tsdf_volume.cpp:234-238).  Also switched on by the environment variable DF_KINFU_WARPED_INTEGRATE=1, so that an
                                       unchanged apps/demo.cpp can run it; DF_FUSION_WEIGHT_SCALE sets fusion_weight_scale the same way. */
 
+#define DF_KINFU_F2_SOLVE 32       /* the frame's warp solve is df_solve_f2 (robust 6-DoF data term + regulariser) instead of the reference's
+                                      translation-only data term; parameters from df_kinfu_set_f2_params (defaults: lambda 5, reg_k 4, twist + Tukey(0.05) + Huber(1e-4),
+                                      2 GN x 30 PCG steps).  Environment: DF_KINFU_F2_SOLVE=1. */
 #define DF_KINFU_EXTEND_FIELD 16    /* after every extraction the warp field is extended (df_extend_field, radius = extend_radius, step = node_step,
                                       up to max_nodes) and the node grid rebuilt; costs one 4-byte read-back per frame.  Environment: DF_KINFU_EXTEND_FIELD=1,
                                       DF_EXTEND_RADIUS. */
@@ -348,6 +375,8 @@ int df_kinfu_read_buffer(void *kinfu, int which, void *dst_host, size_t bytes);
  *   nodes_host            M x DF_NODE_STRIDE floats: the node table after the data-term solve (ignored unless M equals the loop's node count).
  * NULL = compute as usual. */
 int df_kinfu_set_overrides(void *kinfu, const uint16_t *bilateral_depth_host, size_t pitch, const float *pose12_host, const float *nodes_host, int M);
+/* parameters of the DF_KINFU_F2_SOLVE variant of the frame loop */
+int df_kinfu_set_f2_params(void *kinfu, const df_f2_params *params);
 /* digest of the current state (multi-GPU correctness record, SURVEY 8e: ranks exchange it and rank 0 compares every rank's with a
  * single-GPU run of the same sequence): out4_host[0] order-independent 64-bit checksum of the packed volume, [1] the same over the node
  * table, [2] extracted cloud points, [3] FNV-style hash of every camera pose so far (bit patterns).  Synchronous. */

@@ -369,3 +369,33 @@ def solve_data_term(nodes, canon, live, flags=0, lm_iters=5):
     stats = np.zeros(4, np.float64)
     _fn("solve_data_term")(_p(nodes), len(nodes), _p(c), _p(l), C.c_longlong(N), stride, flags, lm_iters, _p(stats))
     return stats
+
+
+# ------------------------------------------------------------------ robust data term + regularisation over 6-DoF increments
+class F2Params(C.Structure):
+    """orc_f2_params (oracle/orc_reg.c) == df_f2_params (include/dfusion.h)"""
+    _fields_ = [("reg_lambda", C.c_double), ("tukey_c", C.c_double), ("huber_delta", C.c_double), ("lm_mu", C.c_double),
+                ("gn_iters", C.c_int), ("reg_k", C.c_int), ("flags", C.c_int), ("lin_iters", C.c_int)]
+
+
+F2_TWIST, F2_TUKEY, F2_HUBER = 1, 2, 4
+
+
+def f2_params(reg_lambda=0.0, tukey_c=0.01, huber_delta=1e-4, lm_mu=1e-4, gn_iters=3, reg_k=4, flags=0, lin_iters=200) -> F2Params:
+    return F2Params(reg_lambda, tukey_c, huber_delta, lm_mu, gn_iters, reg_k, flags, lin_iters)
+
+
+def solve_f2(nodes: np.ndarray, canon: np.ndarray, live: np.ndarray, prm: F2Params) -> np.ndarray:
+    """orc_solve_f2: nodes [M, 12] float32 updated in place; returns the 16 stats"""
+    c = np.ascontiguousarray(canon, np.float32)
+    l = np.ascontiguousarray(live, np.float32)
+    assert nodes.dtype == np.float32 and nodes.flags.c_contiguous and c.shape == l.shape
+    stats = np.zeros(16, np.float64)
+    load().orc_solve_f2(_p(nodes), len(nodes), _p(c), _p(l), C.c_longlong(len(c)), c.shape[1], C.byref(prm), _p(stats))
+    return stats
+
+
+def f2_edges(nodes: np.ndarray, reg_k: int) -> np.ndarray:
+    e = np.empty((len(nodes), reg_k), np.int32)
+    load().orc_f2_edges(_p(nodes), len(nodes), reg_k, _p(e))
+    return e
