@@ -482,3 +482,17 @@ class WarpField:
         capi.check(_lib().df_solve_data_term(self.nodes_.data_ptr(), M, self._grid(), canonical.data_ptr(), live.data_ptr(), N, stride,
                                              nonlinear_iters, linear_iters, flags, stats.data_ptr(), self._ws.data_ptr(), _stream()))
         return stats
+
+    def optimiseWarpF2(self, canonical: torch.Tensor, live: torch.Tensor, reg_lambda=0.0, tukey_c=0.01, huber_delta=1e-4, lm_mu=1e-4,
+                       gn_iters=3, reg_k=4, flags=0, lin_iters=200):
+        """df_solve_f2 (opt-in): robust data term over 6-DoF node increments + regularisation; flags = DF_F2_TWIST (1) |
+        DF_F2_TUKEY (2) | DF_F2_HUBER (4).  Nodes (rotation + dual part) are updated in place; returns the 16 stats (device tensor)."""
+        import ctypes as C
+        N, stride = canonical.shape
+        M = self.nodes_.shape[0]
+        prm = capi.F2Params(float(reg_lambda), float(tukey_c), float(huber_delta), float(lm_mu), int(gn_iters), int(reg_k), int(flags), int(lin_iters))
+        ws = torch.empty(_lib().df_solve_f2_workspace_bytes(M, N, int(reg_k)), dtype=torch.uint8, device=self.device)
+        stats = torch.zeros(16, dtype=torch.float64, device=self.device)
+        capi.check(_lib().df_solve_f2(self.nodes_.data_ptr(), M, self._grid(), canonical.data_ptr(), live.data_ptr(), N, stride, C.byref(prm),
+                                      stats.data_ptr(), ws.data_ptr(), _stream()))
+        return stats
