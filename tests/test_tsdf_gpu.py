@@ -200,6 +200,16 @@ def test_tracked_raycast_equals_dense_march(orc, dim):
         pd, nd, (cam2vol, Rinv) = v.raycast(cam, K, 640, 480, dense=True)
         pt, nt, _ = v.raycast(cam, K, 640, 480)
         assert torch.equal(pd.view(torch.int32), pt.view(torch.int32)) and torch.equal(nd.view(torch.int32), nt.view(torch.int32))
+        # A/B variant: the hit phase reads a TMA-staged brick (DF_RAYCAST_TMA=1, looked up per call); same maps bit for bit
+        import os
+        os.environ["DF_RAYCAST_TMA"] = "1"
+        try:
+            pa, na, _ = v.raycast(cam, K, 640, 480)
+            pb, nb_, _ = v.raycast(cam, K, 640, 480, dense=True)
+        finally:
+            os.environ.pop("DF_RAYCAST_TMA", None)
+        assert torch.equal(pd.view(torch.int32), pa.view(torch.int32)) and torch.equal(nd.view(torch.int32), na.view(torch.int32))
+        assert torch.equal(pd.view(torch.int32), pb.view(torch.int32)) and torch.equal(nd.view(torch.int32), nb_.view(torch.int32))
         hits.append(int((~torch.isnan(pd[..., 0])).sum().item()))
     assert hits[0] > 100_000 and min(hits[:3]) > 20_000
     # the dense march against the oracle for the view from behind (the other views are covered by the parity tests above)
