@@ -132,12 +132,14 @@ __global__ void __launch_bounds__(NT) icp_accumulate_kernel(const IcpParams p)
             }
         }
     }
+    // the warp stage stays in float (the reference's whole reduction is a float tree, proj_icp.cu:111-348): 135 shuffles per warp instead
+    // of the 270 a double butterfly needs (ncu r02: they were 39 % of the ICP kernels' instructions); warps are then summed in double
 #pragma unroll
     for (int i = 0; i < 27; ++i) {
-        double v = (double)acc[i];
+        float v = acc[i];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) smem[warp][i] = v;
+        if (lane == 0) smem[warp][i] = (double)v;
     }
     __syncthreads();
     if (tid < 27) {
@@ -520,10 +522,10 @@ __global__ void __launch_bounds__(NT, 1) icp_persistent_kernel(const IcpPersistP
             }
 #pragma unroll
             for (int i = 0; i < 27; ++i) {
-                double v = (double)acc[i];
+                float v = acc[i];                                   // float warp stage, see icp_accumulate_kernel
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0) smem[warp][i] = v;
+                if (lane == 0) smem[warp][i] = (double)v;
             }
             __syncthreads();
             double *mine = q.partials + ((size_t)parity * gridDim.x + blockIdx.x) * 27;
@@ -656,7 +658,11 @@ int icp_estimate_impl(const float *const *vcurr, const unsigned short *const *dc
 {
     if ((size_t)scratch & 15) return (int)cudaErrorMisalignedAddress;
     // ---- one persistent launch for the whole loop (DF_ICP_PERSISTENT=0: the launch-per-iteration path below) -------------------
-    static const int persistent = [] { const char *e = getenv("DF_ICP_PERSISTENT"); return e ? atoi(e) : 1; }();
+    // Measured (profiles/r02_call04_*, r02_icp_persistent_by_line.txt): 0.309 ms vs 0.268 ms for the 38 PDL-chained launches -- the serial
+    // 6 x 6 solve + pose composition (26 % of the stall samples) and the barrier wait (13 %) are on the critical path either way, and a
+    // PDL launch boundary costs less than a grid barrier plus a redundant reduction in 148 CTAs.  Kept selectable (DF_ICP_PERSISTENT=1),
+    // tested, not the default.
+    static const int persistent = [] { const char *e = getenv("DF_ICP_PERSISTENT"); return e ? atoi(e) : 0; }();
     if (persistent && levels <= 4) {
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);

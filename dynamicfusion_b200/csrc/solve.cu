@@ -561,14 +561,19 @@ struct Lm5Smem {
 
 struct Lm5Sync { int parity; uint32_t phase_red[2]; uint32_t phase_pub; };
 
-template <int NCTA, int NV>
-__device__ __forceinline__ void cluster_sum5(Lm5Smem<NCTA> &sm, Lm5Sync &sy, int cta, double (&v)[NV])
+// kOwnerOnly: only the lanes that own a row (lane % tpr == 0) hold a non-zero contribution, so the warp butterfly can stop at
+// offset tpr (3 of 5 steps at the usual 4 threads per row).  ncu (profiles/r02_lm_*_by_line.txt): the shuffles of this function were
+// 20 % of the kernel's instructions and the final 16 x NV serial sum in every thread another 15 %; the final sum is now a 16-lane
+// butterfly per warp (every warp forms the same tree on the same data: all threads of all CTAs still hold bit-identical totals).
+template <int NCTA, int NV, bool kOwnerOnly = false>
+__device__ __forceinline__ void cluster_sum5(Lm5Smem<NCTA> &sm, Lm5Sync &sy, int cta, double (&v)[NV], int tpr = 1)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int par = sy.parity;
+    const int stop = kOwnerOnly ? tpr : 1;
 #pragma unroll
     for (int k = 0; k < NV; ++k)
-        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+        for (int o = 16; o >= stop; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
     if (lane == 0) {
 #pragma unroll
         for (int k = 0; k < NV; ++k) sm.wpart[warp][k] = v[k];
@@ -587,12 +592,11 @@ __device__ __forceinline__ void cluster_sum5(Lm5Smem<NCTA> &sm, Lm5Sync &sy, int
     }
     mbar_wait(bar, sy.phase_red[par]);
     sy.phase_red[par] ^= 1u;
-    // (not unrolled over k: with NV = 4 and NCTA = 16 the compiler hoists all 64 loads and spills the PCG state)
-#pragma unroll 1
-    for (int k = 0; k < NV; ++k) {
-        double t = 0.0;
 #pragma unroll
-        for (int c = 0; c < NCTA; ++c) t += sm.red_in[par][c][k];
+    for (int k = 0; k < NV; ++k) {
+        double t = sm.red_in[par][lane & (NCTA - 1)][k];
+#pragma unroll
+        for (int o = NCTA / 2; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
         v[k] = t;
     }
     sy.parity = par ^ 1;
@@ -719,7 +723,7 @@ solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
         t0[0] += x1 * (0.5 * Ap1 - gb1);
         t0[0] += x2 * (0.5 * Ap2 - gb2);
     }
-    cluster_sum5<NCTA>(sm, sy, cta, t0);
+    cluster_sum5<NCTA, sizeof(t0) / sizeof(double), true>(sm, sy, cta, t0, tpr);
     double cost = c0n[0] + t0[0];
     const double cost0 = cost;
 
@@ -740,7 +744,7 @@ solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
             p0 = g0 * mi; p1 = g1 * mi; p2 = g2 * mi;
             rzv[0] += g0 * p0; rzv[0] += g1 * p1; rzv[0] += g2 * p2;
         }
-        cluster_sum5<NCTA>(sm, sy, cta, rzv);                        // completes only when every CTA has finished reading svec (x) ...
+        cluster_sum5<NCTA, sizeof(rzv) / sizeof(double), true>(sm, sy, cta, rzv, tpr);                        // completes only when every CTA has finished reading svec (x) ...
         publish(p0, p1, p2);                                   // ... so p may overwrite it
         double rz = rzv[0];
         double Q0 = 0.0;
@@ -760,7 +764,7 @@ solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
                 Ap1 = Ap1 + cdn * p1; m = mi * r1; n = mi * Ap1; v[0] += p1 * Ap1; v[1] += m * r1; v[2] += m * Ap1; v[3] += n * Ap1;
                 Ap2 = Ap2 + cdn * p2; m = mi * r2; n = mi * Ap2; v[0] += p2 * Ap2; v[1] += m * r2; v[2] += m * Ap2; v[3] += n * Ap2;
             }
-            cluster_sum5<NCTA>(sm, sy, cta, v);                      // every CTA finished reading svec (p)
+            cluster_sum5<NCTA, sizeof(v) / sizeof(double), true>(sm, sy, cta, v, tpr);                      // every CTA finished reading svec (p)
             if (!(v[0] > 0.0) || !(v[1] > 0.0)) break;
             const double rz_now = v[1];
             const double alpha = rz_now / v[0];
@@ -786,7 +790,7 @@ solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
                 Ap0 = Ap0 + cdn * p0; Ap1 = Ap1 + cdn * p1; Ap2 = Ap2 + cdn * p2;
                 pap[0] += p0 * Ap0; pap[0] += p1 * Ap1; pap[0] += p2 * Ap2;
             }
-            cluster_sum5<NCTA>(sm, sy, cta, pap);                    // every CTA finished reading svec (p)
+            cluster_sum5<NCTA, sizeof(pap) / sizeof(double), true>(sm, sy, cta, pap, tpr);                    // every CTA finished reading svec (p)
             if (!(pap[0] > 0.0)) break;
             const double alpha = rz / pap[0];
             double rq[2] = {0.0, 0.0};
@@ -796,7 +800,7 @@ solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
                 dl1 = dl1 + alpha * p1; r1 = r1 - alpha * Ap1; z1 = r1 * mi; rq[0] += r1 * z1; rq[1] += dl1 * (r1 + g1);
                 dl2 = dl2 + alpha * p2; r2 = r2 - alpha * Ap2; z2 = r2 * mi; rq[0] += r2 * z2; rq[1] += dl2 * (r2 + g2);
             }
-            cluster_sum5<NCTA>(sm, sy, cta, rq);
+            cluster_sum5<NCTA, sizeof(rq) / sizeof(double), true>(sm, sy, cta, rq, tpr);
             const double rz_new = rq[0], Q1 = -0.5 * rq[1];
             const double beta = rz_new / rz;
             if (owner) { p0 = z0 + beta * p0; p1 = z1 + beta * p1; p2 = z2 + beta * p2; }
@@ -815,7 +819,7 @@ solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
             c = cdn * dl1; mad[0] += dl1 * (g1 + r1 + c); mad[1] += dl1 * (g1 - r1 - c); mad[2] += dl1 * g1;
             c = cdn * dl2; mad[0] += dl2 * (g2 + r2 + c); mad[1] += dl2 * (g2 - r2 - c); mad[2] += dl2 * g2;
         }
-        cluster_sum5<NCTA>(sm, sy, cta, mad);
+        cluster_sum5<NCTA, sizeof(mad) / sizeof(double), true>(sm, sy, cta, mad, tpr);
         const double model = 0.5 * mad[0];
         const double new_cost = cost - mad[2] + 0.5 * mad[1];
         const double change = cost - new_cost;

@@ -351,3 +351,17 @@ def test_solve_row_overflow_is_loud_and_leaves_the_field_unchanged():
     stats = wf.optimiseWarpData(torch.from_numpy(src).cuda(), torch.from_numpy(dst).cuda(), 5, 100, 0).cpu().numpy()
     assert stats[5] == 1 and stats[2] == 0
     assert torch.equal(before, wf.nodes_)
+
+
+@pytest.mark.parametrize("env", [{"DF_ICP_PERSISTENT": "1"}, {"DF_SOLVE_MERGED": "0"}, {"DF_SOLVE_LM_IMPL": "1"}, {"DF_SOLVE_LM_CTAS": "8"}])
+def test_alternative_icp_and_solve_kernels_in_subprocess(env):
+    """The A/B variants that are selected once per process: the one-launch persistent ICP (grid barrier per iteration), the PCG with two
+    reductions per step, the one-block LM fallback and the 8-CTA cluster.  Each re-runs this file's ICP / solve parity tests under
+    the switch in a fresh interpreter."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_stages_gpu.py", "-q", "-x", "-m", "gpu", "-k",
+                        "icp_accumulate_and_estimate or icp_depth or icp_degenerate or solve_reference or solve_large or solve_row_overflow"],
+                       cwd=root, env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout

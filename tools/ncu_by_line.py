@@ -20,6 +20,7 @@ def main():
     ap.add_argument("cubin", help="translation unit name inside libdfusion.so, e.g. fusion")
     ap.add_argument("kernel", help="substring of the kernel's mangled name")
     ap.add_argument("--top", type=int, default=25)
+    ap.add_argument("--by-samples", action="store_true", help="rank the lines by stall samples instead of executed instructions")
     a = ap.parse_args()
     raw = list(csv.reader(io.StringIO(subprocess.run(["ncu", "-i", a.report, "--page", "raw", "--csv"], capture_output=True, text=True).stdout)))
     hdr, units, vals = raw[0], raw[1], raw[2]
@@ -64,7 +65,8 @@ def main():
         tot += n; samples += s
     print(f"  executed warp instructions {tot}, stall samples {samples}")
     print("  share of warp instructions | share of samples | avg active threads | source line")
-    for loc, n in inst.most_common(a.top):
+    ranked = [(loc, inst[loc]) for loc, _ in smp.most_common(a.top)] if a.by_samples else inst.most_common(a.top)
+    for loc, n in ranked:
         text = ""
         f = next((p for p in (ROOT / "dynamicfusion_b200" / "csrc").rglob(loc[0])), None) if loc[0] != "?" else None
         if f:
