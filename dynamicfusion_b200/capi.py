@@ -110,6 +110,7 @@ PROTOTYPES = {
     "df_kinfu_destroy": (None, [_vp]),
     "df_kinfu_reset": (_i, [_vp]),
     "df_kinfu_process_host": (_i, [_vp, _vp, _sz]),
+    "df_kinfu_batch_process_host": (_i, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_sz), _i, C.POINTER(_i)]),
     "df_kinfu_process_device": (_i, [_vp, _vp, _sz]),
     "df_kinfu_get_stage_ms": (_i, [_vp, C.POINTER(C.c_float), _i]),
     "df_kinfu_dynamicfusion": (_i, [_vp, _vp, _sz, _vp, _sz]),

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <vector>
 #include <chrono>
+#include <thread>
 
 using namespace dfb;
 
@@ -23,6 +24,7 @@ struct Img { void *ptr = nullptr; size_t pitch = 0; int cols = 0, rows = 0; };
 
 struct KinFu {
     df_kinfu_params p;
+    int device = 0;                       // the CUDA device the object was created on; every entry point switches to it
     cudaStream_t stream = 0;
     int levels = 0;                       // icp used levels
     float trunc_dist = 0.f;
@@ -462,6 +464,7 @@ extern "C" void *df_kinfu_create(const df_kinfu_params *pp)
     }
     KinFu *k = new KinFu();
     k->p = *pp;
+    cudaGetDevice(&k->device);
     {
         const char *e = getenv("DF_KINFU_WARPED_INTEGRATE");
         if (e && atoi(e) != 0) k->p.flags |= DF_KINFU_WARPED_INTEGRATE;
@@ -534,6 +537,7 @@ extern "C" void df_kinfu_destroy(void *h)
 {
     KinFu *k = (KinFu *)h;
     if (!k) return;
+    cudaSetDevice(k->device);
     if (getenv("DF_KINFU_HOSTPROF") && k->host_frames)
         fprintf(stderr, "[df_kinfu host profile] frames %lld: launch-A %.1f us, ICP wait %.1f us, launch-B %.1f us, total %.1f us per frame\n", k->host_frames,
                 k->host_us[0] / k->host_frames, k->host_us[1] / k->host_frames, k->host_us[2] / k->host_frames, k->host_us[3] / k->host_frames);
@@ -566,9 +570,27 @@ static void finish_timing(KinFu &k)
     }
 }
 
+// Multi-device host entry (the path shards by SEQUENCE): n independent KinFu objects -- typically one per GPU, created after
+// cudaSetDevice(i) -- advance by one frame each, concurrently: one host thread per object (a frame has one host synchronisation, the ICP
+// status, so a sequential loop would serialise the devices).  results[i] receives what df_kinfu_process_host returns for object i.
+extern "C" int df_kinfu_batch_process_host(void *const *kinfus, const uint16_t *const *depth_host, const size_t *pitch, int n, int *results)
+{
+    if (n <= 0) return 0;
+    std::vector<std::thread> th;
+    th.reserve((size_t)n);
+    for (int i = 1; i < n; ++i)
+        th.emplace_back([=] { results[i] = df_kinfu_process_host(kinfus[i], depth_host[i], pitch[i]); });
+    results[0] = df_kinfu_process_host(kinfus[0], depth_host[0], pitch[0]);
+    for (auto &t : th) t.join();
+    int worst = 0;
+    for (int i = 0; i < n; ++i) if (results[i] < worst) worst = results[i];
+    return worst;                                                    // 0, or the first negative status (-cudaError) of any object
+}
+
 extern "C" int df_kinfu_process_device(void *h, const uint16_t *depth_dev, size_t pitch)
 {
     KinFu *k = (KinFu *)h;
+    cudaSetDevice(k->device);
     const int r = process(*k, depth_dev, pitch);
     finish_timing(*k);
     return r;
@@ -591,6 +613,7 @@ extern "C" int df_kinfu_dynamicfusion(void *h, uint16_t *depth_dev, size_t depth
 extern "C" int df_kinfu_process_host(void *h, const uint16_t *depth_host, size_t pitch)
 {
     KinFu *k = (KinFu *)h;
+    cudaSetDevice(k->device);                                         // per host thread: lets one process drive one object per GPU
     // depth_device_.upload(depth.data, depth.step, rows, cols), apps/demo.cpp:89
     cudaError_t e = cudaMemcpy2DAsync(k->depth_in.ptr, k->depth_in.pitch, depth_host, pitch, (size_t)k->p.cols * 2, k->p.rows,
                                       cudaMemcpyHostToDevice, k->stream);

@@ -350,6 +350,11 @@ int df_kinfu_reset(void *kinfu);
  * the device inside the call (the path apps/demo.cpp takes: imread -> upload -> operator()); _device: depth already in HBM. */
 int df_kinfu_process_host(void *kinfu, const uint16_t *depth_host, size_t pitch);
 int df_kinfu_process_device(void *kinfu, const uint16_t *depth_dev, size_t pitch);
+/* Multi-device host entry (config 5: independent sequences batched across the GPUs of one box).  A KinFu object belongs to the CUDA device
+ * that was current when it was created (cudaSetDevice(i) before df_kinfu_create) and every df_kinfu_* call switches to it.  This call
+ * advances n objects by one frame each CONCURRENTLY -- one host thread per object, because a frame contains one host synchronisation --
+ * and returns 0 or the most negative status; results[i] = what df_kinfu_process_host returns for object i. */
+int df_kinfu_batch_process_host(void *const *kinfus, const uint16_t *const *depth_host, const size_t *pitch, int n, int *results);
 /* KinFu::dynamicfusion(depth, live_frame, current_normals) (kinfu.hpp:87, kinfu.cpp:344-400) on caller-provided device buffers,
  * at the latest pose: raycast -> warp -> solve -> warp -> project/remove -> integrate -> extract.  depth is modified in place. */
 int df_kinfu_dynamicfusion(void *kinfu, uint16_t *depth_dev, size_t depth_pitch, const float *live_points_dev, size_t live_pitch);
