@@ -40,6 +40,7 @@ struct SolveWs {
     double *c0_partials;                           // per prepare-block 0.5*sum|b|^2 and valid count
     double *vec;                                   // 7 vectors of 3*M doubles
     int *flags;                                    // [0] overflow
+    int *row_order;                                // [M] node index per solve_rows block: heaviest incidence lists first
     int prepare_blocks;
 };
 
@@ -67,6 +68,7 @@ size_t layout(SolveWs &ws, char *base, int M, int N)
     ws.c0_partials = (double *)take((size_t)ws.prepare_blocks * 8 * 2 * 8);   // one (0.5*|b|^2, count) pair per warp
     ws.vec = (double *)take((size_t)M * 3 * 8 * 7);
     ws.flags = (int *)take(64);
+    ws.row_order = (int *)take((size_t)M * 4);
     return o;
 }
 
@@ -141,6 +143,17 @@ __global__ void __launch_bounds__(1024) solve_scan_kernel(SolveWs ws, int M)
     for (int i = b; i < e; ++i) { ws.off[i] = run; run += ws.cnt[i]; ws.cursor[i] = 0; }
     if (t == 1023) ws.off[M] = partial[1023];
     if (t == 0) ws.flags[0] = 0;
+    // Launch order of solve_rows: one block per node, and the rim nodes' lists are 100x the median -- scheduled last they are the
+    // kernel's tail.  Longest-processing-time-first: nodes grouped by floor(log2(count)), heaviest group first (the order inside a
+    // group is whatever the shared-memory atomics give: it affects only WHEN a row is assembled, never its value).
+    __shared__ int hist[32], start[32];
+    if (t < 32) hist[t] = 0;
+    __syncthreads();
+    for (int i = b; i < e; ++i) atomicAdd(&hist[31 - __clz(ws.cnt[i] | 1)], 1);
+    __syncthreads();
+    if (t == 0) { int acc = 0; for (int g = 31; g >= 0; --g) { start[g] = acc; acc += hist[g]; } }
+    __syncthreads();
+    for (int i = b; i < e; ++i) ws.row_order[atomicAdd(&start[31 - __clz(ws.cnt[i] | 1)], 1)] = i;
 }
 
 __global__ void __launch_bounds__(256) solve_fill_kernel(SolveWs ws, int N)
@@ -198,7 +211,7 @@ __global__ void __launch_bounds__(ROWS_THREADS) solve_rows_kernel(SolveWs ws, in
     __shared__ double priv[ROWS_WARPS][ROWS_PRIV];
     __shared__ int nlist;
     __shared__ double red[3][ROWS_WARPS];
-    const int i = blockIdx.x;
+    const int i = ws.row_order[blockIdx.x];
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     for (int s = tid; s < HCAP; s += ROWS_THREADS) { keys[s] = -1; vals[s] = 0.0; }
