@@ -32,6 +32,7 @@ struct KinFu {
     uint32_t *volume = nullptr;
     Img depth_in, dists;
     Img cur_depth[MAX_LEVELS], cur_pts[MAX_LEVELS], cur_nrm[MAX_LEVELS], prev_pts[MAX_LEVELS], prev_nrm[MAX_LEVELS];
+    Img prev_depth[MAX_LEVELS];           // DF_KINFU_USE_DEPTH only: the model's depth pyramid (prev_.depth_pyr)
     Img canon, canon_nrm, canon_visible;
     float *cloud = nullptr, *cloud_nrm = nullptr; int *cloud_count = nullptr;
     float *nodes = nullptr; int M = 0; void *node_grid = nullptr;
@@ -202,9 +203,23 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_d
                         (uint16_t *)k.cur_depth[i].ptr, k.cur_depth[i].pitch, p.bilateral_sigma_depth, s));
         ++k.launches;
     }
+    const bool use_depth = (p.flags & DF_KINFU_USE_DEPTH) != 0;
     for (int i = 0; i < LEVELS; ++i) {
         const int div = 1 << i;                                       // Intr::operator()(level), precomp.cpp:10-14
         const df_intr li = {p.intr.fx / div, p.intr.fy / div, p.intr.cx / div, p.intr.cy / div};
+        if (use_depth) {
+            // the reference's compile-time USE_DEPTH loop (internal.hpp:6, kinfu.cpp:237-238): normals from the depth map, depth masked
+            // where the normal is invalid; the vertex pyramid is not built.  KinFu::dynamicfusion is still handed curr_.points_pyr[0]
+            // (kinfu.cpp:284-287), which that build never writes; here it receives what the variable is meant to hold: the vertex map of
+            // the level-0 depth (computed before the masking, normals to a scratch map) -- documented divergence, DESIGN 5.
+            if (i == 0) {
+                CKD(df_points_normals(li, (const uint16_t *)k.cur_depth[0].ptr, k.cur_depth[0].pitch, k.cur_depth[0].cols, k.cur_depth[0].rows,
+                                      (float *)k.cur_pts[0].ptr, k.cur_pts[0].pitch, (float *)k.canon_nrm.ptr, k.canon_nrm.pitch, s));
+                ++k.launches;
+            }
+            CKD(df_normals_mask_depth(li, (uint16_t *)k.cur_depth[i].ptr, k.cur_depth[i].pitch, k.cur_depth[i].cols, k.cur_depth[i].rows,
+                                      (float *)k.cur_nrm[i].ptr, k.cur_nrm[i].pitch, s));
+        } else
         CKD(df_points_normals(li, (const uint16_t *)k.cur_depth[i].ptr, k.cur_depth[i].pitch, k.cur_depth[i].cols, k.cur_depth[i].rows,
                               (float *)k.cur_pts[i].ptr, k.cur_pts[i].pitch, (float *)k.cur_nrm[i].ptr, k.cur_nrm[i].pitch, s));
         ++k.launches;
@@ -283,7 +298,11 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_d
                 k.launches += 2;
             }
         }
-        for (int i = 0; i < MAX_LEVELS; ++i) { std::swap(k.cur_pts[i], k.prev_pts[i]); std::swap(k.cur_nrm[i], k.prev_nrm[i]); }
+        for (int i = 0; i < MAX_LEVELS; ++i) {                          // kinfu.cpp:253-261
+            if (p.flags & DF_KINFU_USE_DEPTH) std::swap(k.cur_depth[i], k.prev_depth[i]);
+            else std::swap(k.cur_pts[i], k.prev_pts[i]);
+            std::swap(k.cur_nrm[i], k.prev_nrm[i]);
+        }
         ++k.frame_counter;
         return 0;
     }
@@ -299,6 +318,16 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_d
             vp[i] = (const float *)k.prev_pts[i].ptr; np[i] = (const float *)k.prev_nrm[i].ptr;
             cols[i] = k.cur_pts[i].cols; rows[i] = k.cur_pts[i].rows; pitch[i] = k.cur_pts[i].pitch;
         }
+        if (p.flags & DF_KINFU_USE_DEPTH) {                            // estimateTransform(depth pyramids), kinfu.cpp:271
+            const unsigned short *dc[MAX_LEVELS], *dp[MAX_LEVELS];
+            size_t dpitch[MAX_LEVELS], npitch[MAX_LEVELS];
+            for (int i = 0; i < LEVELS; ++i) {
+                dc[i] = (const unsigned short *)k.cur_depth[i].ptr; dp[i] = (const unsigned short *)k.prev_depth[i].ptr;
+                dpitch[i] = k.cur_depth[i].pitch; npitch[i] = k.cur_nrm[i].pitch;
+            }
+            CKD(df_icp_estimate_depth(dc, nc, dp, np, cols, rows, dpitch, npitch, LEVELS, p.icp_iter_num, p.intr, p.icp_dist_thres, p.icp_angle_thres,
+                                      k.icp_T, k.icp_ok, k.icp_scratch, s));
+        } else
         CKD(df_icp_estimate(vc, nc, vp, np, cols, rows, pitch, LEVELS, p.icp_iter_num, p.intr, p.icp_dist_thres, p.icp_angle_thres,
                             k.icp_T, k.icp_ok, k.icp_scratch, s));
         for (int i = 0; i < LEVELS; ++i) k.launches += 2 * p.icp_iter_num[i];
@@ -410,6 +439,18 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_d
     if (only_df) return 1;
     // ---- ray-cast for the next frame's ICP, kinfu.cpp:297-301 --------------------------------------------------------
     CKD(raycast_to(cam_pose, k.prev_pts[0], k.prev_nrm[0]));
+    if (p.flags & DF_KINFU_USE_DEPTH) {
+        // TsdfVolume::raycast(pose, intr, Depth&, Normals&) (tsdf_volume.cu:273-339,441-456) = the same march storing ushort(vertex.z * 1000),
+        // then resizeDepthNormals per level (kinfu.cpp:293-295)
+        CKD(df_cloud_to_depth((const float *)k.prev_pts[0].ptr, k.prev_pts[0].pitch, p.cols, p.rows, (uint16_t *)k.prev_depth[0].ptr, k.prev_depth[0].pitch, s));
+        ++k.launches;
+        for (int i = 1; i < LEVELS; ++i) {
+            CKD(df_resize_depth_normals((const uint16_t *)k.prev_depth[i - 1].ptr, k.prev_depth[i - 1].pitch, (const float *)k.prev_nrm[i - 1].ptr,
+                                        k.prev_nrm[i - 1].pitch, k.prev_depth[i - 1].cols, k.prev_depth[i - 1].rows,
+                                        (uint16_t *)k.prev_depth[i].ptr, k.prev_depth[i].pitch, (float *)k.prev_nrm[i].ptr, k.prev_nrm[i].pitch, s));
+            ++k.launches;
+        }
+    } else
     for (int i = 1; i < LEVELS; ++i) {
         CKD(df_resize_points_normals((const float *)k.prev_pts[i - 1].ptr, k.prev_pts[i - 1].pitch, (const float *)k.prev_nrm[i - 1].ptr,
                                      k.prev_nrm[i - 1].pitch, k.prev_pts[i - 1].cols, k.prev_pts[i - 1].rows,
@@ -472,6 +513,8 @@ extern "C" void *df_kinfu_create(const df_kinfu_params *pp)
         if (x && atoi(x) != 0) k->p.flags |= DF_KINFU_EXTEND_FIELD;
         const char *xr = getenv("DF_EXTEND_RADIUS");
         if (xr) k->p.extend_radius = (float)atof(xr);
+        const char *ud = getenv("DF_KINFU_USE_DEPTH");
+        if (ud && atoi(ud) != 0) k->p.flags |= DF_KINFU_USE_DEPTH;
         const char *f2e = getenv("DF_KINFU_F2_SOLVE");
         if (f2e && atoi(f2e) != 0) k->p.flags |= DF_KINFU_F2_SOLVE;
         const char *rb = getenv("DF_RAYCAST_BRICKS");
@@ -493,7 +536,7 @@ extern "C" void *df_kinfu_create(const df_kinfu_params *pp)
     for (int l = 0; l < MAX_LEVELS && ok; ++l) {                      // allocate_buffers, kinfu.cpp:151-194
         ok = ok && alloc_img(k->cur_depth[l], rows, cols, 2) == 0 && alloc_img(k->cur_pts[l], rows, cols, 16) == 0 &&
              alloc_img(k->cur_nrm[l], rows, cols, 16) == 0 && alloc_img(k->prev_pts[l], rows, cols, 16) == 0 &&
-             alloc_img(k->prev_nrm[l], rows, cols, 16) == 0;
+             alloc_img(k->prev_nrm[l], rows, cols, 16) == 0 && alloc_img(k->prev_depth[l], rows, cols, 2) == 0;
         cols /= 2; rows /= 2;
     }
     ok = ok && alloc_img(k->canon, p.rows, p.cols, 16) == 0 && alloc_img(k->canon_nrm, p.rows, p.cols, 16) == 0 &&
@@ -543,7 +586,7 @@ extern "C" void df_kinfu_destroy(void *h)
                 k->host_us[0] / k->host_frames, k->host_us[1] / k->host_frames, k->host_us[2] / k->host_frames, k->host_us[3] / k->host_frames);
     cudaStreamSynchronize(k->stream);
     cudaFree(k->volume); cudaFree(k->depth_in.ptr); cudaFree(k->dists.ptr);
-    for (int l = 0; l < MAX_LEVELS; ++l) { cudaFree(k->cur_depth[l].ptr); cudaFree(k->cur_pts[l].ptr); cudaFree(k->cur_nrm[l].ptr); cudaFree(k->prev_pts[l].ptr); cudaFree(k->prev_nrm[l].ptr); }
+    for (int l = 0; l < MAX_LEVELS; ++l) { cudaFree(k->cur_depth[l].ptr); cudaFree(k->cur_pts[l].ptr); cudaFree(k->cur_nrm[l].ptr); cudaFree(k->prev_pts[l].ptr); cudaFree(k->prev_nrm[l].ptr); cudaFree(k->prev_depth[l].ptr); }
     cudaFree(k->canon.ptr); cudaFree(k->canon_nrm.ptr); cudaFree(k->canon_visible.ptr);
     cudaFree(k->cloud); cudaFree(k->cloud_nrm); cudaFree(k->cloud_count); cudaFree(k->nodes); cudaFree(k->node_grid);
     cudaFree(k->icp_T); cudaFree(k->icp_ok); cudaFree(k->icp_scratch); cudaFree(k->solve_ws); cudaFree(k->solve_stats);

@@ -18,6 +18,8 @@ RIGID_ONLY = 1
 STAGE_TIMING = 2
 REF_GRAPH_QUIRK = 4
 EXTEND_FIELD = 16         # DF_KINFU_EXTEND_FIELD: grow the warp field over unsupported canonical surface
+F2_SOLVE = 32             # DF_KINFU_F2_SOLVE: robust 6-DoF data term + regulariser instead of the translation-only solve
+USE_DEPTH = 64            # DF_KINFU_USE_DEPTH: the reference's compile-time USE_DEPTH frame loop (depth-pyramid ICP)
 WARPED_INTEGRATE = 8      # DF_KINFU_WARPED_INTEGRATE: per-voxel warped fusion instead of the rigid fallback
 
 

@@ -333,6 +333,9 @@ typedef struct df_kinfu_params {
 #define DF_KINFU_F2_SOLVE 32       /* the frame's warp solve is df_solve_f2 (robust 6-DoF data term + regulariser) instead of the reference's
                                       translation-only data term; parameters from df_kinfu_set_f2_params (defaults: lambda 5, reg_k 4, twist + Tukey(0.05) + Huber(1e-4),
                                       2 GN x 30 PCG steps).  Environment: DF_KINFU_F2_SOLVE=1. */
+#define DF_KINFU_USE_DEPTH 64       /* the reference's compile-time USE_DEPTH frame loop (internal.hpp:6; kinfu.cpp:237-238,253-255,271,293-295): normals from the depth
+                                      pyramid with masking (df_normals_mask_depth), ICP on depth pyramids (df_icp_estimate_depth), the model ray-cast stored as a depth map
+                                      (df_cloud_to_depth) and halved by df_resize_depth_normals.  Environment: DF_KINFU_USE_DEPTH=1. */
 #define DF_KINFU_EXTEND_FIELD 16    /* after every extraction the warp field is extended (df_extend_field, radius = extend_radius, step = node_step,
                                       up to max_nodes) and the node grid rebuilt; costs one 4-byte read-back per frame.  Environment: DF_KINFU_EXTEND_FIELD=1,
                                       DF_EXTEND_RADIUS. */
