@@ -41,6 +41,7 @@ struct SolveWs {
     double *vec;                                   // 7 vectors of 3*M doubles
     int *flags;                                    // [0] overflow
     int *row_order;                                // [M] node index per solve_rows block: heaviest incidence lists first
+    int *blockcnt;                                 // [M][prepare_blocks]: entries of node n contributed by vertex block b, then their exclusive prefix over b
     int prepare_blocks;
 };
 
@@ -69,6 +70,7 @@ size_t layout(SolveWs &ws, char *base, int M, int N)
     ws.vec = (double *)take((size_t)M * 3 * 8 * 7);
     ws.flags = (int *)take(64);
     ws.row_order = (int *)take((size_t)M * 4);
+    ws.blockcnt = (int *)take((size_t)M * ws.prepare_blocks * 4);
     return o;
 }
 
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(PREPARE_THREADS) solve_prepare_kernel(const fl
         const int n = valid ? nq : -1;
         // warp-aggregated incidence count: neighbouring pixels share nodes, one atomic per distinct node per warp
         const unsigned grp = __match_any_sync(0xffffffffu, n);
-        if (n >= 0 && (int)(__ffs(grp) - 1) == (int)(threadIdx.x & 31)) atomicAdd(ws.cnt + n, __popc(grp));
+        if (n >= 0 && (int)(__ffs(grp) - 1) == (int)(threadIdx.x & 31)) atomicAdd(ws.blockcnt + (size_t)n * gridDim.x + blockIdx.x, __popc(grp));
     }
     // deterministic per-WARP partials of 0.5*|b|^2 and of the valid-row count (no block barrier: a warp whose queries are far
     // from the node cloud takes several times longer than its neighbours, and nobody should wait for it)
@@ -156,22 +158,84 @@ __global__ void __launch_bounds__(1024) solve_scan_kernel(SolveWs ws, int M)
     for (int i = b; i < e; ++i) ws.row_order[atomicAdd(&start[31 - __clz(ws.cnt[i] | 1)], 1)] = i;
 }
 
+// per node: exclusive prefix of its per-block entry counts (in place) and the total -> cnt[n].  One warp per node, coalesced.
+__global__ void __launch_bounds__(256) solve_blockscan_kernel(SolveWs ws, int M)
+{
+    DF_PDL_ENTRY();
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (n >= M) return;
+    int *row = ws.blockcnt + (size_t)n * ws.prepare_blocks;
+    int run = 0;
+    for (int b0 = 0; b0 < ws.prepare_blocks; b0 += 32) {
+        const int b = b0 + lane;
+        const int c = b < ws.prepare_blocks ? row[b] : 0;
+        int inc = c;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (b < ws.prepare_blocks) row[b] = run + inc - c;
+        run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) ws.cnt[n] = run;
+}
+
+// Incidence lists node -> (vertex, k) in a CANONICAL order: by vertex block, then by entry id inside the block.  Round 1 handed out the
+// positions with an atomic cursor per node, which made the order -- and through it the rounding of every double sum solve_rows forms
+// over a list -- depend on kernel timing: a translation could differ in its last bit between two runs of the same frame (seen when
+// several frame loops fed one stream).  Here a block sorts its 256 x 8 (node, entry) pairs in shared memory (bitonic, 66 steps), every
+// run of equal nodes takes its base from the per-(node, block) prefix of solve_blockscan and its rank from its position in the run.
 __global__ void __launch_bounds__(256) solve_fill_kernel(SolveWs ws, int N)
 {
     DF_PDL_ENTRY();
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int NE = 256 * 8;
+    __shared__ unsigned long long key[NE];
+    const int tid = threadIdx.x;
+    const int v = blockIdx.x * blockDim.x + tid;
+    const bool valid = v < N && ws.b[v].w != 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const int n = (v < N && ws.b[v].w != 0.f) ? ws.idx[(size_t)v * 8 + k] : -1;
-        const unsigned grp = __match_any_sync(0xffffffffu, n);
-        if (n < 0) continue;
-        const int lane = threadIdx.x & 31;
-        const int leader = __ffs(grp) - 1;
-        int base = 0;
-        if (lane == leader) base = atomicAdd(ws.cursor + n, __popc(grp));
-        base = __shfl_sync(grp, base, leader);
-        const int rank = __popc(grp & ((1u << lane) - 1u));
-        ws.inc[ws.off[n] + base + rank] = v * 8 + k;
+        const int n = valid ? ws.idx[(size_t)v * 8 + k] : -1;
+        key[tid * 8 + k] = n >= 0 ? ((unsigned long long)(unsigned)n << 32) | (unsigned)(v * 8 + k) : ~0ull;
+    }
+    __syncthreads();
+    for (int size = 2; size <= NE; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+#pragma unroll
+            for (int q = 0; q < NE / 2 / 256; ++q) {
+                const int t = tid + q * 256;                       // compare-exchange number t of this step
+                const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const unsigned long long a = key[lo], b = key[hi];
+                if ((a > b) == up) { key[lo] = b; key[hi] = a; }
+            }
+            __syncthreads();
+        }
+    // position of every entry: base of its run + rank in the run.  A thread owns 8 consecutive sorted positions; the start of the run a
+    // position belongs to is the running maximum of the head positions (a block's vertices share their nodes: runs are ~256 long, so
+    // the start comes from a block-wide max-scan, not from walking back).
+    __shared__ int wcarry[8];
+    int node[8], start[8];
+    int cur = -1;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int pos = tid * 8 + q;
+        node[q] = (int)(key[pos] >> 32);
+        const bool head = pos == 0 || (int)(key[pos - 1] >> 32) != node[q];
+        if (head) cur = pos;
+        start[q] = cur;                                            // -1: the run began in an earlier thread's positions
+    }
+    int incl = cur;                                                // inclusive max-scan of the threads' last run starts
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl = max(incl, t); }
+    if (lane == 31) wcarry[warp] = incl;
+    __syncthreads();
+    int before = -1;                                               // exclusive: the last run start of all earlier threads
+    for (int w = 0; w < warp; ++w) before = max(before, wcarry[w]);
+    const int prev_lane = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane > 0) before = max(before, prev_lane);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        if (node[q] < 0) continue;                                 // (int)(~0ull >> 32) == -1: padding
+        const int pos = tid * 8 + q, first = start[q] >= 0 ? start[q] : before;
+        ws.inc[ws.off[node[q]] + ws.blockcnt[(size_t)node[q] * gridDim.x + blockIdx.x] + (pos - first)] = (int)(unsigned)key[pos];
     }
 }
 
@@ -201,7 +265,7 @@ __device__ __forceinline__ int rows_find_slot(const int *keys, int j)
     return 0;
 }
 
-__global__ void __launch_bounds__(ROWS_THREADS) solve_rows_kernel(SolveWs ws, int M, int N, int quirk)
+__global__ void __launch_bounds__(ROWS_THREADS) solve_rows_kernel(SolveWs ws, int M, int N, int quirk, int lpt)
 {
     DF_PDL_ENTRY();
     __shared__ int keys[HCAP];
@@ -211,7 +275,7 @@ __global__ void __launch_bounds__(ROWS_THREADS) solve_rows_kernel(SolveWs ws, in
     __shared__ double priv[ROWS_WARPS][ROWS_PRIV];
     __shared__ int nlist;
     __shared__ double red[3][ROWS_WARPS];
-    const int i = ws.row_order[blockIdx.x];
+    const int i = lpt ? ws.row_order[blockIdx.x] : (int)blockIdx.x;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     for (int s = tid; s < HCAP; s += ROWS_THREADS) { keys[s] = -1; vals[s] = 0.0; }
@@ -899,15 +963,18 @@ extern "C" int df_solve_data_term(float *nodes, int M, const void *node_grid, co
     SolveWs ws;
     char *base = (char *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     layout(ws, base, M, N);
-    cudaError_t e = cudaMemsetAsync(ws.cnt, 0, (size_t)(M + 1) * 4, s);
+    cudaError_t e = cudaMemsetAsync(ws.blockcnt, 0, (size_t)M * ws.prepare_blocks * 4, s);
     if (e != cudaSuccess) return (int)e;
     launch_pdl(solve_prepare_kernel, dim3(ws.prepare_blocks), dim3(256), 0, s, nodes, M, node_grid, canon, live, N, stride, ws);
+    DF_LAUNCH_CHECK();
+    launch_pdl(solve_blockscan_kernel, dim3(div_up(M, 8)), dim3(256), 0, s, ws, M);
     DF_LAUNCH_CHECK();
     launch_pdl(solve_scan_kernel, dim3(1), dim3(1024), 0, s, ws, M);
     DF_LAUNCH_CHECK();
     launch_pdl(solve_fill_kernel, dim3(ws.prepare_blocks), dim3(256), 0, s, ws, N);
     DF_LAUNCH_CHECK();
-    launch_pdl(solve_rows_kernel, dim3(M), dim3(ROWS_THREADS), 0, s, ws, M, N, flags & DF_SOLVE_REF_GRAPH_QUIRK);
+    static const int lpt = [] { const char *e = getenv("DF_SOLVE_LPT"); return e ? atoi(e) : 1; }();    // A/B: heaviest rows first
+    launch_pdl(solve_rows_kernel, dim3(M), dim3(ROWS_THREADS), 0, s, ws, M, N, flags & DF_SOLVE_REF_GRAPH_QUIRK, lpt);
     DF_LAUNCH_CHECK();
     // v5 on one cluster when the system fits its shared memory (16 CTAs = the non-portable maximum: half the rows, hence half the
     // mat-vec gather traffic, per SM; DF_SOLVE_LM_CTAS=8 selects the portable size); otherwise the one-block kernel (matrix in L2).
