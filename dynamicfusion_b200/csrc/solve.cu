@@ -177,65 +177,65 @@ __global__ void __launch_bounds__(256) solve_blockscan_kernel(SolveWs ws, int M)
     if (lane == 0) ws.cnt[n] = run;
 }
 
-// Incidence lists node -> (vertex, k) in a CANONICAL order: by vertex block, then by entry id inside the block.  Round 1 handed out the
-// positions with an atomic cursor per node, which made the order -- and through it the rounding of every double sum solve_rows forms
-// over a list -- depend on kernel timing: a translation could differ in its last bit between two runs of the same frame (seen when
-// several frame loops fed one stream).  Here a block sorts its 256 x 8 (node, entry) pairs in shared memory (bitonic, 66 steps), every
-// run of equal nodes takes its base from the per-(node, block) prefix of solve_blockscan and its rank from its position in the run.
+// Incidence lists node -> (vertex, k) in a CANONICAL order: by vertex block, then warp, then neighbour slot k, then lane.  Round 1 handed
+// out the positions with an atomic cursor per node, which made the order -- and through it the rounding of every double sum solve_rows
+// forms over a list -- depend on kernel timing: a translation could differ in its last bit between two runs of the same frame (seen when
+// several frame loops fed one stream).  Here a block owns, for every node its vertices touch, the range that solve_blockscan reserved for
+// (node, block); the block's cursors live in a small shared-memory hash and its warps take their turns one after the other, so every
+// entry's position is a pure function of the data.  (A first version sorted the block's 2,048 (node, entry) pairs with a bitonic
+// network: 132 us per frame; this one: see profiles/r02_*launches*.)
+constexpr int FILL_HASH = 1024;                                    // >= distinct nodes a block of 256 vertices can touch (<= 2,048 entries; typically ~30)
 __global__ void __launch_bounds__(256) solve_fill_kernel(SolveWs ws, int N)
 {
     DF_PDL_ENTRY();
-    constexpr int NE = 256 * 8;
-    __shared__ unsigned long long key[NE];
-    const int tid = threadIdx.x;
+    __shared__ int hkey[FILL_HASH], hcur[FILL_HASH];
+    __shared__ int overflow;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int v = blockIdx.x * blockDim.x + tid;
     const bool valid = v < N && ws.b[v].w != 0.f;
+    for (int s = tid; s < FILL_HASH; s += 256) hkey[s] = -1;
+    if (tid == 0) overflow = 0;
+    __syncthreads();
+    int nk[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const int n = valid ? ws.idx[(size_t)v * 8 + k] : -1;
-        key[tid * 8 + k] = n >= 0 ? ((unsigned long long)(unsigned)n << 32) | (unsigned)(v * 8 + k) : ~0ull;
-    }
-    __syncthreads();
-    for (int size = 2; size <= NE; size <<= 1)
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-#pragma unroll
-            for (int q = 0; q < NE / 2 / 256; ++q) {
-                const int t = tid + q * 256;                       // compare-exchange number t of this step
-                const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
-                const bool up = (lo & size) == 0;
-                const unsigned long long a = key[lo], b = key[hi];
-                if ((a > b) == up) { key[lo] = b; key[hi] = a; }
+        nk[k] = valid ? ws.idx[(size_t)v * 8 + k] : -1;
+        // one lane per distinct node of the warp claims the node's slot; whoever claims it first loads the block's base for that node
+        const unsigned grp = __match_any_sync(0xffffffffu, nk[k]);
+        if (nk[k] >= 0 && lane == __ffs(grp) - 1) {
+            unsigned slot = ((unsigned)nk[k] * 2654435761u) & (FILL_HASH - 1);
+            int probe = 0;
+            for (; probe < FILL_HASH; ++probe) {
+                const int prev = atomicCAS(&hkey[slot], -1, nk[k]);
+                if (prev == -1) { hcur[slot] = ws.blockcnt[(size_t)nk[k] * gridDim.x + blockIdx.x]; break; }
+                if (prev == nk[k]) break;
+                slot = (slot + 1) & (FILL_HASH - 1);
             }
-            __syncthreads();
+            if (probe == FILL_HASH) overflow = 1;
         }
-    // position of every entry: base of its run + rank in the run.  A thread owns 8 consecutive sorted positions; the start of the run a
-    // position belongs to is the running maximum of the head positions (a block's vertices share their nodes: runs are ~256 long, so
-    // the start comes from a block-wide max-scan, not from walking back).
-    __shared__ int wcarry[8];
-    int node[8], start[8];
-    int cur = -1;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        const int pos = tid * 8 + q;
-        node[q] = (int)(key[pos] >> 32);
-        const bool head = pos == 0 || (int)(key[pos - 1] >> 32) != node[q];
-        if (head) cur = pos;
-        start[q] = cur;                                            // -1: the run began in an earlier thread's positions
     }
-    int incl = cur;                                                // inclusive max-scan of the threads' last run starts
-    const int lane = tid & 31, warp = tid >> 5;
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl = max(incl, t); }
-    if (lane == 31) wcarry[warp] = incl;
     __syncthreads();
-    int before = -1;                                               // exclusive: the last run start of all earlier threads
-    for (int w = 0; w < warp; ++w) before = max(before, wcarry[w]);
-    const int prev_lane = __shfl_up_sync(0xffffffffu, incl, 1);
-    if (lane > 0) before = max(before, prev_lane);
+    if (overflow) { if (tid == 0) ws.flags[0] = 1; return; }        // cannot happen for 256-vertex blocks (<= 2,048 entries < capacity): reported like a row overflow
+    for (int w = 0; w < 8; ++w) {                                  // the warps take their turns: positions depend on the data only
+        if (warp == w) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        if (node[q] < 0) continue;                                 // (int)(~0ull >> 32) == -1: padding
-        const int pos = tid * 8 + q, first = start[q] >= 0 ? start[q] : before;
-        ws.inc[ws.off[node[q]] + ws.blockcnt[(size_t)node[q] * gridDim.x + blockIdx.x] + (pos - first)] = (int)(unsigned)key[pos];
+            for (int k = 0; k < 8; ++k) {
+                const int n = nk[k];
+                const unsigned grp = __match_any_sync(0xffffffffu, n);
+                int base = 0;
+                const int leader = __ffs(grp) - 1;
+                if (n >= 0 && lane == leader) {
+                    unsigned slot = ((unsigned)n * 2654435761u) & (FILL_HASH - 1);
+                    while (hkey[slot] != n) slot = (slot + 1) & (FILL_HASH - 1);
+                    base = hcur[slot];
+                    hcur[slot] = base + __popc(grp);               // leaders of one match hold distinct nodes: no conflict
+                }
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (n >= 0) ws.inc[ws.off[n] + base + __popc(grp & ((1u << lane) - 1u))] = v * 8 + k;
+                __syncwarp();
+            }
+        }
+        __syncthreads();
     }
 }
 

@@ -343,17 +343,30 @@ __device__ __forceinline__ void knn8_grid(const void *__restrict__ grid, bool va
             if (r == rmax) done = true;                       // every cell has been visited
         }
         if (!done) {
+            if (h.pad[2]) {
+                // Far query: branch-and-bound over the k-d BVH, SEEDED (round 2; the warped-fusion kernel showed what an unseeded search
+                // costs far from the cloud: ~30 nearly equidistant nodes, 18 of them inserted and evicted again per query).  The seed is
+                // the eight candidates the visited shells produced when there are eight, else the leaf a greedy descent reaches; either
+                // is eight real nodes with their exact distances, so the result is the exhaustive scan's (knn8_bvh_seeded).
+                const float4 *box = reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(grid) + h.pad[2]);
+                const float4 *leaf = reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(grid) + h.pad[3]);
+                bool seeded = bi[7] != 0x7fffffff;
+                if (!seeded) seeded = knn8_bvh_greedy_seed(box, leaf, h.pad[4], qx, qy, qz, bi, bd);
+                if (seeded) knn8_bvh_seeded(box, leaf, h.pad[4], qx, qy, qz, bi, bd);
+                else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { bi[i] = 0x7fffffff; bd[i] = 3.402823466e+38f; }
+                    knn8_bvh(box, leaf, h.pad[4], qx, qy, qz, bi, bd);
+                }
+            } else {
 #pragma unroll
             for (int i = 0; i < 8; ++i) { bi[i] = 0x7fffffff; bd[i] = 3.402823466e+38f; }
-            if (h.pad[2]) {
-                knn8_bvh(reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(grid) + h.pad[2]),
-                         reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(grid) + h.pad[3]), h.pad[4], qx, qy, qz, bi, bd);
-            } else
 #pragma unroll 4
             for (int it = 0; it < h.M; ++it) {
                 const float4 nd = __ldg(sorted + it);
                 const float d0 = qx - nd.x, d1 = qy - nd.y, d2 = qz - nd.z;
                 knn8_insert_lex(bi, bd, d0 * d0 + d1 * d1 + d2 * d2, __float_as_int(nd.w));
+            }
             }
         }
     }
