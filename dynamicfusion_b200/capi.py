@@ -119,6 +119,7 @@ PROTOTYPES = {
     "df_kinfu_get_buffer": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_sz), C.POINTER(_i), C.POINTER(_i)]),
     "df_kinfu_set_stream": (_i, [_vp, _vp]),
     "df_kinfu_read_buffer": (_i, [_vp, _i, _vp, _sz]),
+    "df_kinfu_join": (_i, [_vp]),
     "df_kinfu_set_overrides": (_i, [_vp, _vp, _sz, _vp, _vp, _i]),
     "df_kinfu_state_digest": (_i, [_vp, C.POINTER(C.c_ulonglong)]),
 }

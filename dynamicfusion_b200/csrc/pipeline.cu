@@ -57,6 +57,13 @@ struct KinFu {
     long long last_cloud = -1;
     double host_us[4] = {0, 0, 0, 0}; long long host_frames = 0;   // DF_KINFU_HOSTPROF: launch A, ICP wait, launch B, total
     unsigned long long *n_upd = nullptr;   // voxels written by the last integrate (filled when DF_KINFU_STAGE_TIMING)
+    // Extraction runs on a second stream: nothing later in the frame loop reads the extracted cloud (the reference recomputes it every
+    // frame for its host copies, kinfu.cpp:398-399), it only READS the volume, and the volume is not written again before the next
+    // frame's integrate -- so it overlaps the ray-cast and the next frame's pre-processing + ICP (0.3 ms of mostly launch latency).
+    cudaStream_t aux = nullptr;           // extraction stream (non-blocking)
+    cudaEvent_t ev_volume_ready = nullptr, ev_extract_done = nullptr;
+    bool extract_pending = false;         // an extraction is in flight on `aux`
+    bool overlap_extract = true;          // DF_KINFU_OVERLAP_EXTRACT=0: everything on one stream
     cudaEvent_t ev[NSTAGES + 1];
     float stage_ms[NSTAGES];
     int stage_mark[NSTAGES + 1];
@@ -136,6 +143,16 @@ __global__ void __launch_bounds__(256) digest_kernel(const uint32_t *__restrict_
     if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
 }
 
+// the main stream may not write the volume / activity map / cloud buffers while an extraction is still reading or writing them
+int wait_extract_on_main(KinFu &k)
+{
+    if (!k.extract_pending) return 0;
+    k.extract_pending = false;
+    return (int)cudaStreamWaitEvent(k.stream, k.ev_extract_done, 0);
+}
+// host-side readers of the cloud (count, buffers, digest) wait for the extraction itself
+void sync_extract(KinFu &k) { if (k.aux) cudaStreamSynchronize(k.aux); }
+
 void mark(KinFu &k, int stage)
 {
     if (k.p.flags & DF_KINFU_STAGE_TIMING) cudaEventRecord(k.ev[stage], k.stream);
@@ -150,6 +167,7 @@ int do_reset(KinFu &k)
     k.poses.clear();
     k.poses.resize(12);
     dfh_aff_identity(k.poses.data());
+    if (int w = wait_extract_on_main(k)) return w;
     if (k.activity && cudaMemsetAsync(k.activity, 0, k.activity_bytes, k.stream) != cudaSuccess) return (int)cudaGetLastError();
     return df_clear_volume(vol_of(k), k.stream);
 }
@@ -240,6 +258,7 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_d
         k.launches += df_integrate_launch_count(vol);
         unsigned long long *counter = (p.flags & DF_KINFU_STAGE_TIMING) ? k.n_upd : nullptr;
         if (counter) cudaMemsetAsync(counter, 0, 8, s);
+        if (int w = wait_extract_on_main(k)) return w;                 // write-after-read: the previous frame's extraction reads this volume
         return df_integrate_tracked(vol, (const uint16_t *)dists.ptr, dists.pitch, p.cols, p.rows, to_aff(vol2cam), p.intr, counter, k.activity, k.integrate_ws, s);
     };
     auto raycast_to = [&](const float *cam_pose, Img &pts, Img &nrm) -> int {
@@ -252,12 +271,25 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_d
         return df_raycast_points_tracked(vol, to_aff(cam2vol), Rinv, p.intr, p.cols, p.rows, p.raycast_step_factor, p.gradient_delta_factor,
                                          (float *)pts.ptr, pts.pitch, (float *)nrm.ptr, nrm.pitch, k.raycast_bricks ? k.activity : nullptr, s);
     };
-    auto extract = [&]() -> int {                                      // compute_points + compute_normals, tsdf_volume.cpp:313-325
-        int st = df_extract_cloud_tracked(vol, p.volume_pose, k.cloud, p.cloud_capacity, k.cloud_count, k.extract_ws, k.activity, s);
+    auto extract = [&](bool needed_now) -> int {                       // compute_points + compute_normals, tsdf_volume.cpp:313-325
+        // needed_now: the caller reads the cloud right after (first frame: node initialisation; field extension): stay on the main stream
+        const bool overlap = k.overlap_extract && !needed_now && !(p.flags & DF_KINFU_STAGE_TIMING);
+        cudaStream_t es = s;
+        if (overlap) {
+            if (cudaEventRecord(k.ev_volume_ready, s) != cudaSuccess || cudaStreamWaitEvent(k.aux, k.ev_volume_ready, 0) != cudaSuccess) return (int)cudaGetLastError();
+            es = k.aux;
+        } else if (int w = wait_extract_on_main(k)) return w;          // an older extraction may still own the cloud buffers
+        int st = df_extract_cloud_tracked(vol, p.volume_pose, k.cloud, p.cloud_capacity, k.cloud_count, k.extract_ws, k.activity, es);
         if (st) return st;
         k.launches += 5;                                               // count, 2 scans, emit + the normals kernel below
         k.last_cloud = -1;
-        return df_extract_normals(vol, k.cloud, p.cloud_capacity, k.cloud_count, p.volume_pose, Rinv_vol, p.gradient_delta_factor, k.cloud_nrm, s);
+        st = df_extract_normals(vol, k.cloud, p.cloud_capacity, k.cloud_count, p.volume_pose, Rinv_vol, p.gradient_delta_factor, k.cloud_nrm, es);
+        if (st) return st;
+        if (overlap) {
+            if (cudaEventRecord(k.ev_extract_done, k.aux) != cudaSuccess) return (int)cudaGetLastError();
+            k.extract_pending = true;
+        }
+        return 0;
     };
 
     auto extend = [&]() -> int {                                       // SURVEY 8f(3) / Report.md step 4, DF_KINFU_EXTEND_FIELD
@@ -282,7 +314,7 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_d
     // ---- first frame, kinfu.cpp:245-264 ----------------------------------------------------------------------------
     if (!only_df && k.frame_counter == 0) {
         CKD(integrate_with(k.dists, &k.poses[k.poses.size() - 12]));
-        CKD(extract());
+        CKD(extract(true));
         if (!(p.flags & DF_KINFU_RIGID_ONLY)) {
             int count = 0;
             CK(cudaMemcpyAsync(&count, k.cloud_count, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -410,7 +442,7 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_d
                                     p.intr, k.nodes, k.M, k.node_grid, p.fusion_weight_scale, counter, k.activity, k.fusion_ws, s));
             k.launches += df_integrate_warped_launch_count();
             mark(k, 8);
-            CKD(extract());
+            CKD(extract((p.flags & DF_KINFU_EXTEND_FIELD) != 0));
             CKD(extend());
             mark(k, 9);
         } else {
@@ -425,7 +457,7 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_d
         mark(k, 7);                                                    // stage "integrate" brackets the integrate kernel alone
         CKD(integrate_with(k.dists, cam_pose));
         mark(k, 8);
-        CKD(extract());                                                // compute_points / compute_normals, :398-399
+        CKD(extract((p.flags & DF_KINFU_EXTEND_FIELD) != 0));          // compute_points / compute_normals, :398-399
         CKD(extend());
         mark(k, 9);
         }
@@ -563,6 +595,10 @@ extern "C" void *df_kinfu_create(const df_kinfu_params *pp)
     ok = ok && cudaMemset(k->project_ws, 0, df_project_workspace_bytes(p.cols, p.rows)) == cudaSuccess;
     ok = ok && cudaMemset(k->solve_stats, 0, 64) == cudaSuccess && cudaMemset(k->cloud_count, 0, 64) == cudaSuccess;
     ok = ok && cudaMallocHost(&k->pinned, 64) == cudaSuccess && (memset(k->pinned, 0, 64), true) && cudaMalloc(&k->n_upd, 64) == cudaSuccess && cudaMemset(k->n_upd, 0, 64) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&k->aux, cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&k->ev_volume_ready, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&k->ev_extract_done, cudaEventDisableTiming) == cudaSuccess;
+    { const char *oe = getenv("DF_KINFU_OVERLAP_EXTRACT"); if (oe && atoi(oe) == 0) k->overlap_extract = false; }
     for (int e = 0; e <= NSTAGES; ++e) k->ev[e] = nullptr;
     for (int e = 0; e <= NSTAGES && ok; ++e) ok = cudaEventCreate(&k->ev[e]) == cudaSuccess;
     if (!ok) {
@@ -585,6 +621,9 @@ extern "C" void df_kinfu_destroy(void *h)
         fprintf(stderr, "[df_kinfu host profile] frames %lld: launch-A %.1f us, ICP wait %.1f us, launch-B %.1f us, total %.1f us per frame\n", k->host_frames,
                 k->host_us[0] / k->host_frames, k->host_us[1] / k->host_frames, k->host_us[2] / k->host_frames, k->host_us[3] / k->host_frames);
     cudaStreamSynchronize(k->stream);
+    if (k->aux) { cudaStreamSynchronize(k->aux); cudaStreamDestroy(k->aux); }
+    if (k->ev_volume_ready) cudaEventDestroy(k->ev_volume_ready);
+    if (k->ev_extract_done) cudaEventDestroy(k->ev_extract_done);
     cudaFree(k->volume); cudaFree(k->depth_in.ptr); cudaFree(k->dists.ptr);
     for (int l = 0; l < MAX_LEVELS; ++l) { cudaFree(k->cur_depth[l].ptr); cudaFree(k->cur_pts[l].ptr); cudaFree(k->cur_nrm[l].ptr); cudaFree(k->prev_pts[l].ptr); cudaFree(k->prev_nrm[l].ptr); cudaFree(k->prev_depth[l].ptr); }
     cudaFree(k->canon.ptr); cudaFree(k->canon_nrm.ptr); cudaFree(k->canon_visible.ptr);
@@ -682,6 +721,7 @@ extern "C" int df_kinfu_get_pose(void *h, int time, float *pose12)
 extern "C" int df_kinfu_get_info(void *h, long long *info, int n)
 {
     KinFu *k = (KinFu *)h;
+    sync_extract(*k);
     if (k->last_cloud < 0) {
         int c = 0;
         cudaMemcpyAsync(&c, k->cloud_count, sizeof(int), cudaMemcpyDeviceToHost, k->stream);
@@ -702,9 +742,17 @@ extern "C" int df_kinfu_get_info(void *h, long long *info, int n)
     return 0;
 }
 
+// stream-ordered join: the object's main stream waits for the extraction in flight on its auxiliary stream (no host synchronisation)
+extern "C" int df_kinfu_join(void *h)
+{
+    KinFu *k = (KinFu *)h;
+    return wait_extract_on_main(*k);
+}
+
 extern "C" int df_kinfu_get_buffer(void *h, int which, void **ptr, size_t *pitch, int *cols, int *rows)
 {
     KinFu *k = (KinFu *)h;
+    if (which == 9 || which == 10) sync_extract(*k);               // the caller is about to use the cloud on a stream of its own
     Img im;
     switch (which) {
         case 0: im.ptr = k->volume; im.pitch = (size_t)k->p.volume_dims[0] * 4; im.cols = k->p.volume_dims[0]; im.rows = k->p.volume_dims[1] * k->p.volume_dims[2]; break;
@@ -736,6 +784,7 @@ extern "C" int df_kinfu_read_buffer(void *h, int which, void *dst_host, size_t b
     const int st = df_kinfu_get_buffer(h, which, &ptr, &pitch, &cols, &rows);
     if (st) return st;
     const size_t have = pitch * (size_t)rows;
+    sync_extract(*k);
     cudaError_t e = cudaStreamSynchronize(k->stream);
     if (e != cudaSuccess) return (int)e;
     e = cudaMemcpy(dst_host, ptr, bytes < have ? bytes : have, cudaMemcpyDeviceToHost);
@@ -769,6 +818,7 @@ extern "C" int df_kinfu_set_f2_params(void *h, const df_f2_params *prm)
 extern "C" int df_kinfu_state_digest(void *h, unsigned long long *out4_host)
 {
     KinFu *k = (KinFu *)h;
+    sync_extract(*k);
     unsigned long long *d = nullptr;
     if (cudaMalloc((void **)&d, 32) != cudaSuccess) return (int)cudaGetLastError();
     cudaMemsetAsync(d, 0, 32, k->stream);

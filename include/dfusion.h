@@ -361,6 +361,12 @@ int df_kinfu_batch_process_host(void *const *kinfus, const uint16_t *const *dept
 /* KinFu::dynamicfusion(depth, live_frame, current_normals) (kinfu.hpp:87, kinfu.cpp:344-400) on caller-provided device buffers,
  * at the latest pose: raycast -> warp -> solve -> warp -> project/remove -> integrate -> extract.  depth is modified in place. */
 int df_kinfu_dynamicfusion(void *kinfu, uint16_t *depth_dev, size_t depth_pitch, const float *live_points_dev, size_t live_pitch);
+/* The surface extraction of a frame (compute_points / compute_normals, kinfu.cpp:398-399) runs on an auxiliary stream of the object and
+ * overlaps the frame's last ray-cast and the next frame's pre-processing + ICP: nothing later in the loop reads the cloud, and the volume it
+ * reads is not written before the next integrate (which waits for it).  Every accessor of the cloud (df_kinfu_get_info, _read_buffer,
+ * _get_buffer(9|10), _state_digest) waits for it; df_kinfu_join makes the object's MAIN stream wait for it without a host synchronisation
+ * (what a caller timing frames with events on that stream wants).  DF_KINFU_OVERLAP_EXTRACT=0 (environment) keeps everything on one stream. */
+int df_kinfu_join(void *kinfu);
 /* KinFu::getCameraPose(time) (kinfu.cpp:213-218): 12 floats, R row-major then t; time < 0 = latest */
 int df_kinfu_get_pose(void *kinfu, int time, float *pose12_host);
 /* info[0] frame counter, [1] warp nodes M, [2] extracted cloud points, [3] poses stored, [4] last ICP ok,
