@@ -108,6 +108,11 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// df_solve_data_term with one more argument: an event recorded on the stream right before the LM/PCG kernel is launched (the frame loop
+// starts the previous frame's surface extraction there: the solve occupies one 16-SM cluster for ~1 ms while 132 SMs idle).  solve.cu
+int solve_data_term_ev(float *nodes, int M, const void *node_grid, const float *canon, const float *live, int N, int stride, int nonlinear_iters,
+                       int linear_iters, int flags, double *stats_dev, void *workspace, cudaStream_t stream, cudaEvent_t before_lm);
+
 }  // namespace dfb
 
 // first statement of every kernel launched through launch_pdl

@@ -872,6 +872,7 @@ bool KinFu::operator()(const cuda::Depth& depth, const cuda::Image& /*image*/)
 {
     const int r = df_kinfu_process_device(handle_, depth.ptr(), depth.step());
     if (r < 0) kfusion::cuda::error(df_error_string(-r), __FILE__, __LINE__);
+    df_kinfu_join(handle_);                                             // the C++ API keeps the reference's contract: the frame's extraction is done on return
     cudaSafeCall(cudaDeviceSynchronize());                              // waitAllDefaultStream(), kinfu.cpp:301
     long long info[10];
     df_kinfu_get_info(handle_, info, 10);

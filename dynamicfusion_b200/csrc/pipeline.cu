@@ -60,8 +60,10 @@ struct KinFu {
     // Extraction runs on a second stream: nothing later in the frame loop reads the extracted cloud (the reference recomputes it every
     // frame for its host copies, kinfu.cpp:398-399), it only READS the volume, and the volume is not written again before the next
     // frame's integrate -- so it overlaps the ray-cast and the next frame's pre-processing + ICP (0.3 ms of mostly launch latency).
-    cudaStream_t aux = nullptr;           // extraction stream (non-blocking)
-    cudaEvent_t ev_volume_ready = nullptr, ev_extract_done = nullptr;
+    cudaStream_t aux = nullptr;           // extraction stream (non-blocking, lowest priority: the main stream's kernels are placed first)
+    cudaEvent_t ev_volume_ready = nullptr, ev_extract_done = nullptr, ev_before_lm = nullptr;
+    bool extract_deferred = false;        // frame t's extraction has not been launched yet: it starts when frame t+1's LM/PCG kernel does
+                                          // (one 16-SM cluster for ~1 ms, 132 SMs idle), or as soon as anybody needs the cloud or the volume
     bool extract_pending = false;         // an extraction is in flight on `aux`
     bool overlap_extract = true;          // DF_KINFU_OVERLAP_EXTRACT=0: everything on one stream
     cudaEvent_t ev[NSTAGES + 1];
@@ -143,15 +145,55 @@ __global__ void __launch_bounds__(256) digest_kernel(const uint32_t *__restrict_
     if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
 }
 
-// the main stream may not write the volume / activity map / cloud buffers while an extraction is still reading or writing them
+df_volume vol_of(const KinFu &k);
+
+// the extraction itself (compute_points + compute_normals, tsdf_volume.cpp:313-325) on stream `es`
+int run_extract(KinFu &k, cudaStream_t es)
+{
+    const df_kinfu_params &p = k.p;
+    float vol_pose[12], Rinv_vol[9];
+    memcpy(vol_pose, p.volume_pose.R, 36); memcpy(vol_pose + 9, p.volume_pose.t, 12);
+    dfh_mat3_inv(vol_pose, Rinv_vol);
+    const df_volume vol = vol_of(k);
+    int st = df_extract_cloud_tracked(vol, p.volume_pose, k.cloud, p.cloud_capacity, k.cloud_count, k.extract_ws, k.activity, es);
+    if (st) return st;
+    k.last_cloud = -1;
+    return df_extract_normals(vol, k.cloud, p.cloud_capacity, k.cloud_count, p.volume_pose, Rinv_vol, p.gradient_delta_factor, k.cloud_nrm, es);
+}
+
+// start the deferred extraction on the auxiliary stream once `after` (an event of the main stream) has happened
+int launch_deferred_extract(KinFu &k, cudaEvent_t after)
+{
+    if (!k.extract_deferred) return 0;
+    k.extract_deferred = false;
+    if (cudaStreamWaitEvent(k.aux, after, 0) != cudaSuccess) return (int)cudaGetLastError();
+    if (int st = run_extract(k, k.aux)) return st;
+    if (cudaEventRecord(k.ev_extract_done, k.aux) != cudaSuccess) return (int)cudaGetLastError();
+    k.extract_pending = true;
+    return 0;
+}
+
+// the main stream may not write the volume / activity map / cloud buffers while an extraction is still owed or in flight
 int wait_extract_on_main(KinFu &k)
 {
+    if (k.extract_deferred) {
+        if (cudaEventRecord(k.ev_volume_ready, k.stream) != cudaSuccess) return (int)cudaGetLastError();
+        if (int st = launch_deferred_extract(k, k.ev_volume_ready)) return st;
+    }
     if (!k.extract_pending) return 0;
     k.extract_pending = false;
     return (int)cudaStreamWaitEvent(k.stream, k.ev_extract_done, 0);
 }
-// host-side readers of the cloud (count, buffers, digest) wait for the extraction itself
-void sync_extract(KinFu &k) { if (k.aux) cudaStreamSynchronize(k.aux); }
+// host-side readers of the cloud (count, buffers, digest) make sure the extraction has been launched and wait for it
+void sync_extract(KinFu &k)
+{
+    if (!k.aux) return;
+    if (k.extract_deferred) {
+        cudaEventRecord(k.ev_volume_ready, k.stream);
+        launch_deferred_extract(k, k.ev_volume_ready);
+    }
+    cudaStreamSynchronize(k.aux);
+}
 
 void mark(KinFu &k, int stage)
 {
@@ -273,22 +315,12 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_d
     };
     auto extract = [&](bool needed_now) -> int {                       // compute_points + compute_normals, tsdf_volume.cpp:313-325
         // needed_now: the caller reads the cloud right after (first frame: node initialisation; field extension): stay on the main stream
+        k.launches += 5;                                               // count, 2 scans, emit + the normals kernel
         const bool overlap = k.overlap_extract && !needed_now && !(p.flags & DF_KINFU_STAGE_TIMING);
-        cudaStream_t es = s;
-        if (overlap) {
-            if (cudaEventRecord(k.ev_volume_ready, s) != cudaSuccess || cudaStreamWaitEvent(k.aux, k.ev_volume_ready, 0) != cudaSuccess) return (int)cudaGetLastError();
-            es = k.aux;
-        } else if (int w = wait_extract_on_main(k)) return w;          // an older extraction may still own the cloud buffers
-        int st = df_extract_cloud_tracked(vol, p.volume_pose, k.cloud, p.cloud_capacity, k.cloud_count, k.extract_ws, k.activity, es);
-        if (st) return st;
-        k.launches += 5;                                               // count, 2 scans, emit + the normals kernel below
+        if (int w = wait_extract_on_main(k)) return w;                 // an older extraction may still own the cloud buffers
+        if (!overlap) return run_extract(k, s);
+        k.extract_deferred = true;                                     // launched when the next frame's LM/PCG kernel starts, or on demand
         k.last_cloud = -1;
-        st = df_extract_normals(vol, k.cloud, p.cloud_capacity, k.cloud_count, p.volume_pose, Rinv_vol, p.gradient_delta_factor, k.cloud_nrm, es);
-        if (st) return st;
-        if (overlap) {
-            if (cudaEventRecord(k.ev_extract_done, k.aux) != cudaSuccess) return (int)cudaGetLastError();
-            k.extract_pending = true;
-        }
         return 0;
     };
 
@@ -406,10 +438,11 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_d
             CKD(df_solve_f2(k.nodes, k.M, k.node_grid, (const float *)k.canon.ptr, (const float *)k.cur_pts[0].ptr, npix, 4, &k.f2, k.f2_stats, k.f2_ws, s));
             k.launches += 6 + (k.f2.gn_iters + 1) * 4 + k.f2.gn_iters * (3 + 3 * k.f2.lin_iters);
         } else {
-        CKD(df_solve_data_term(k.nodes, k.M, k.node_grid, (const float *)k.canon.ptr, (const float *)k.cur_pts[0].ptr, npix, 4,
+        CKD(solve_data_term_ev(k.nodes, k.M, k.node_grid, (const float *)k.canon.ptr, (const float *)k.cur_pts[0].ptr, npix, 4,
                                p.solver_nonlinear_iters, p.solver_linear_iters,
-                               (p.flags & DF_KINFU_REF_GRAPH_QUIRK) ? DF_SOLVE_REF_GRAPH_QUIRK : 0, k.solve_stats, k.solve_ws, s));   // :387
-        k.launches += 5;                                               // prepare, scan, fill, rows, lm
+                               (p.flags & DF_KINFU_REF_GRAPH_QUIRK) ? DF_SOLVE_REF_GRAPH_QUIRK : 0, k.solve_stats, k.solve_ws, s, k.ev_before_lm));   // :387
+        k.launches += 6;                                               // prepare, blockscan, scan, fill, rows, lm
+        CKD(launch_deferred_extract(k, k.ev_before_lm));               // the previous frame's extraction rides on the 132 SMs the solve leaves idle
         }
         // row-overflow flag of this solve (stats[5]): lands in pinned memory, looked at after the next stream synchronisation
         CK(cudaMemcpyAsync(k.pinned + 14, k.solve_stats + 5, sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -595,7 +628,10 @@ extern "C" void *df_kinfu_create(const df_kinfu_params *pp)
     ok = ok && cudaMemset(k->project_ws, 0, df_project_workspace_bytes(p.cols, p.rows)) == cudaSuccess;
     ok = ok && cudaMemset(k->solve_stats, 0, 64) == cudaSuccess && cudaMemset(k->cloud_count, 0, 64) == cudaSuccess;
     ok = ok && cudaMallocHost(&k->pinned, 64) == cudaSuccess && (memset(k->pinned, 0, 64), true) && cudaMalloc(&k->n_upd, 64) == cudaSuccess && cudaMemset(k->n_upd, 0, 64) == cudaSuccess;
-    ok = ok && cudaStreamCreateWithFlags(&k->aux, cudaStreamNonBlocking) == cudaSuccess &&
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);              // lo = numerically greatest = lowest priority
+    ok = ok && cudaStreamCreateWithPriority(&k->aux, cudaStreamNonBlocking, prio_lo) == cudaSuccess &&
+         cudaEventCreateWithFlags(&k->ev_before_lm, cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&k->ev_volume_ready, cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&k->ev_extract_done, cudaEventDisableTiming) == cudaSuccess;
     { const char *oe = getenv("DF_KINFU_OVERLAP_EXTRACT"); if (oe && atoi(oe) == 0) k->overlap_extract = false; }
@@ -623,6 +659,7 @@ extern "C" void df_kinfu_destroy(void *h)
     cudaStreamSynchronize(k->stream);
     if (k->aux) { cudaStreamSynchronize(k->aux); cudaStreamDestroy(k->aux); }
     if (k->ev_volume_ready) cudaEventDestroy(k->ev_volume_ready);
+    if (k->ev_before_lm) cudaEventDestroy(k->ev_before_lm);
     if (k->ev_extract_done) cudaEventDestroy(k->ev_extract_done);
     cudaFree(k->volume); cudaFree(k->depth_in.ptr); cudaFree(k->dists.ptr);
     for (int l = 0; l < MAX_LEVELS; ++l) { cudaFree(k->cur_depth[l].ptr); cudaFree(k->cur_pts[l].ptr); cudaFree(k->cur_nrm[l].ptr); cudaFree(k->prev_pts[l].ptr); cudaFree(k->prev_nrm[l].ptr); cudaFree(k->prev_depth[l].ptr); }

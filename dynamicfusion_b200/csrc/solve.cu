@@ -958,8 +958,14 @@ extern "C" int df_solve_knn_buffers(void *workspace, int M, int N, int32_t **idx
 extern "C" int df_solve_data_term(float *nodes, int M, const void *node_grid, const float *canon, const float *live, int N, int stride,
                                   int nonlinear_iters, int linear_iters, int flags, double *stats_dev, void *workspace, void *stream)
 {
-    if (M <= 0 || N <= 0) return 0;
-    cudaStream_t s = (cudaStream_t)stream;
+    return dfb::solve_data_term_ev(nodes, M, node_grid, canon, live, N, stride, nonlinear_iters, linear_iters, flags, stats_dev, workspace,
+                                   (cudaStream_t)stream, nullptr);
+}
+
+int dfb::solve_data_term_ev(float *nodes, int M, const void *node_grid, const float *canon, const float *live, int N, int stride, int nonlinear_iters,
+                            int linear_iters, int flags, double *stats_dev, void *workspace, cudaStream_t s, cudaEvent_t before_lm)
+{
+    if (M <= 0 || N <= 0) { if (before_lm) cudaEventRecord(before_lm, s); return 0; }
     SolveWs ws;
     char *base = (char *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     layout(ws, base, M, N);
@@ -976,6 +982,7 @@ extern "C" int df_solve_data_term(float *nodes, int M, const void *node_grid, co
     static const int lpt = [] { const char *e = getenv("DF_SOLVE_LPT"); return e ? atoi(e) : 1; }();    // A/B: heaviest rows first
     launch_pdl(solve_rows_kernel, dim3(M), dim3(ROWS_THREADS), 0, s, ws, M, N, flags & DF_SOLVE_REF_GRAPH_QUIRK, lpt);
     DF_LAUNCH_CHECK();
+    if (before_lm && cudaEventRecord(before_lm, s) != cudaSuccess) return (int)cudaGetLastError();
     // v5 on one cluster when the system fits its shared memory (16 CTAs = the non-portable maximum: half the rows, hence half the
     // mat-vec gather traffic, per SM; DF_SOLVE_LM_CTAS=8 selects the portable size); otherwise the one-block kernel (matrix in L2).
     static const int want = [] { const char *e = getenv("DF_SOLVE_LM_CTAS"); return e ? atoi(e) : 16; }();
