@@ -48,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     for src in sources():
         obj = objdir / (src.stem + ".o")
         objs.append(obj)
-        cmd = [nvcc, *NVCC_FLAGS, "-x", "cu", "-c", str(src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("DF_NVCC_EXTRA", "").split(), "-x", "cu", "-c", str(src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -36,6 +36,8 @@ namespace {
 constexpr int FUS_SUB = 8;          // slices per visibility test
 constexpr int FUS_TILE = 16;        // fine depth tiles (pixels)
 constexpr int FUS_COARSE = 4;       // coarse tile = FUS_COARSE x FUS_COARSE fine tiles
+constexpr int FUS_LIST_CAP = 768;   // candidate nodes per warp run, as 16-bit positions in the block list (1.5 KB per warp)
+constexpr int FUS_BLOCK_CAP = 2048; // candidate nodes of a block's 32 x 8 x zchunk region (float4 each, 32 KB): what the warp runs select from
 
 struct FusionParams {
     uint32_t *data;
@@ -50,7 +52,7 @@ struct FusionParams {
     Aff vol2world, world2cam, vol2cam;     // vol2cam = world2cam o vol2world: used by the visibility test only
     float fx, fy, cx, cy;
     const float *nodes; int M; const void *grid;
-    const float4 *node_rec;                // per node: rotation quaternion, translation quaternion, (vertex, weight) (fusion_prepare_kernel)
+    const float4 *node_rec;                // three arrays of M records (fusion_prepare_kernel): [i] rotation quaternion, [M + i] translation quaternion, [2M + i] (vertex, weight)
     float weight_scale;
     int cull;                              // 0: the two poses are not rigid -> no visibility test
     const float *ws;                       // [0] displacement bound, [1] global depth maximum, [2] 1 = every node rotation is the identity, [16..] fine tile maxima, then coarse
@@ -59,6 +61,9 @@ struct FusionParams {
     unsigned long long *counters;          // [0] voxels written, [1] voxels warped
     unsigned char *activity;
     BrickTable bricks;
+    int use_list;                          // candidate lists per warp run (round 2, see integrate_warped_body); 0: branch-and-bound per voxel only
+    float half_diag;                       // upper bound on the distance (world space) from a run's centre to any of its voxel centres
+    float half_diag_block;                 // the same for the block's 32 x 8 x zchunk region
 };
 
 // metric depth maxima per FUS_TILE x FUS_TILE pixel tile
@@ -119,9 +124,9 @@ __global__ void __launch_bounds__(256) fusion_prepare_kernel(float *ws, int tile
             const Quat dual = {b.w, c.x, c.y, c.z};
             if (!(rot.w == 1.f && rot.x == 0.f && rot.y == 0.f && rot.z == 0.f)) rotated = true;
             const Quat tr = dq_translation(rot, dual);
-            node_rec[3 * i] = make_float4(rot.w, rot.x, rot.y, rot.z);      // the blend needs only these per neighbour: 8 normalisations
-            node_rec[3 * i + 1] = make_float4(tr.w, tr.x, tr.y, tr.z);      // and quaternion products per voxel leave the inner loop
-            node_rec[3 * i + 2] = make_float4(a.x, a.y, a.z, c.w);          // vertex + weight in one 16-byte load
+            node_rec[i] = make_float4(rot.w, rot.x, rot.y, rot.z);          // the blend needs only these per neighbour: 8 normalisations
+            node_rec[M + i] = make_float4(tr.w, tr.x, tr.y, tr.z);          // and quaternion products per voxel leave the inner loop.  Array by array:
+            node_rec[2 * M + i] = make_float4(a.x, a.y, a.z, c.w);          // the identity path never touches the rotations, 64 KB at 2 k nodes stay in L1
             const float len = sqrtf(tr.x * tr.x + tr.y * tr.y + tr.z * tr.z);
             tmax = fmaxf(tmax, len);
             if (!(len == len)) rotated = true;              // NaN translation: no bound
@@ -197,11 +202,11 @@ __device__ __forceinline__ float3 fusion_warp_point(const FusionParams &p, const
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         if (bi[i] >= 0) {
-            const float4 t = __ldg(p.node_rec + 3 * bi[i] + 1), pw = __ldg(p.node_rec + 3 * bi[i] + 2);
+            const float4 t = __ldg(p.node_rec + p.M + bi[i]), pw = __ldg(p.node_rec + 2 * p.M + bi[i]);
             const float w = node_weighting(bd[i], pw.w);
             tsum.w = tsum.w + w * t.x; tsum.x = tsum.x + w * t.y; tsum.y = tsum.y + w * t.z; tsum.z = tsum.z + w * t.w;
             if (!kIdentity) {
-                const float4 r = __ldg(p.node_rec + 3 * bi[i]);
+                const float4 r = __ldg(p.node_rec + bi[i]);
                 rsum.w = rsum.w + w * r.x; rsum.x = rsum.x + w * r.y; rsum.y = rsum.y + w * r.z; rsum.z = rsum.z + w * r.w;
             }
         }
@@ -225,6 +230,40 @@ __device__ __forceinline__ int fusion_sample_weight(const FusionParams &p, const
     return s < 1.f ? 1 : (s > (float)p.max_weight ? p.max_weight : (int)s);
 }
 
+// The per-voxel search of round 1 (branch-and-bound over the node BVH seeded with the z-predecessor's neighbours, or the grid walk when
+// the field has no BVH): now the fallback for runs without a candidate list.  Out of line on purpose -- three inlined tree walks with
+// unrolled leaf loops were most of the kernel's 200 KB of code, and the kernel is bound by instruction fetch.
+__device__ __noinline__ void fusion_tree_search(const void *grid, const float4 *node_pos, const float3 xc, bool have_prev, const int *prev, int *bi_out, float *bd_out)
+{
+    const NodeGridHeader h = *reinterpret_cast<const NodeGridHeader *>(grid);
+    const bool has_bvh = h.pad[2] != 0;
+    const float4 *bvh_box = reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(grid) + h.pad[2]);
+    const float4 *bvh_leaf = reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(grid) + h.pad[3]);
+    int bi[8]; float bd[8];
+    if (has_bvh) {
+        bool seeded = false;
+        if (have_prev) {                                           // the previous voxel's neighbours at this voxel's position
+            seeded = true;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float4 v = __ldg(node_pos + prev[k]);
+                const float d0 = xc.x - v.x, d1 = xc.y - v.y, d2 = xc.z - v.z;
+                bi[k] = prev[k];
+                bd[k] = d0 * d0 + d1 * d1 + d2 * d2;
+                seeded = seeded && bd[k] == bd[k];
+            }
+        } else {
+            seeded = knn8_bvh_greedy_seed(bvh_box, bvh_leaf, h.pad[4], xc.x, xc.y, xc.z, bi, bd);
+        }
+        if (seeded) knn8_bvh_seeded(bvh_box, bvh_leaf, h.pad[4], xc.x, xc.y, xc.z, bi, bd);
+        else knn8_bvh_bounded(bvh_box, bvh_leaf, h.pad[4], xc.x, xc.y, xc.z, 3.402823466e+38f, bi, bd);
+    } else {
+        knn8_grid(grid, true, xc.x, xc.y, xc.z, bi, bd);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { bi_out[k] = bi[k]; bd_out[k] = bd[k]; }
+}
+
 template <bool kIdentity>
 __device__ __forceinline__ void integrate_warped_body(const FusionParams &p)
 {
@@ -241,37 +280,207 @@ __device__ __forceinline__ void integrate_warped_body(const FusionParams &p)
     const float4 *bvh_box = reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(p.grid) + h.pad[2]);
     const float4 *bvh_leaf = reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(p.grid) + h.pad[3]);
 
+    // Candidate lists (round 2).  The exact 8-NN search per voxel was ~5 k instructions, 80 % of the kernel.  The 256 voxels of a warp run
+    // (8 x 4 x FUS_SUB) share almost all of their neighbours, and a superset of them is cheap to bound: with c the run's centre, h the
+    // largest distance from c to a voxel centre of the run and R >= d8(c) (distance from c to its 8th nearest node), every voxel x of the run has
+    // d8(x) <= d8(c) + h (the 8 nodes nearest to c are that close to x), so each of its eight nearest nodes n has |n - c| <= |n - x| + h <= R + 2h.
+    // The warp scans the node table twice (32 nodes per step, coalesced 16-byte records): pass 1 forms R as the 8th smallest of the 32 lane
+    // minima (distances of 32 distinct nodes, so >= d8(c)), pass 2 compacts the nodes within (R + 2h)(1 + 2e-4) of c into shared memory.
+    // Each voxel then ranks the list (a broadcast read per candidate) with the same float distance and the same (distance, index)
+    // order as every other search path, seeded with its z-predecessor's result: identical neighbours, ~10 instructions per candidate
+    // instead of a branch-and-bound.  The list also bounds the run's displacement by ITS nodes' translations (8 max |t|), which is what the
+    // visibility test needs: the global bound is useless in the live loop (rim nodes drift by decimetres), the local one is tight
+    // everywhere else.  A list that does not fit (first version: 256 float4 entries per run; far from the node cloud the shell holds more) falls
+    // back to the tree, at ten times the cost per voxel: lists are therefore 16-bit positions in the block list and practically never overflow.
+    // Two levels: the block first selects, once, the nodes its whole 32 x 8 x zchunk region can need (same argument with the region's
+    // centre and half diagonal; 256 threads, 8 nodes each at M = 2 k), and the warp runs then select from those few hundred instead of from
+    // the node table (the two passes over M nodes per run were 12 % of the kernel).  A block list that overflows is simply not used.
+    __shared__ unsigned short s_list[8][FUS_LIST_CAP];
+    __shared__ float4 s_block[FUS_BLOCK_CAP];
+    __shared__ float s_wmin[8][8];
+    __shared__ float s_rb2;
+    __shared__ int s_block_n;
+    unsigned short *list = s_list[warp];
+    const bool use_list = p.use_list && has_bvh && p.M >= 8;
+    const bool identity = __ldg(p.ws + 2) != 0.f;
+    int n_src = 0;                                                 // entries of the block list the runs select from
+    bool from_block = false;
+    if (use_list) {
+        const float3 cb = aff_mul(p.vol2world, make_float3(((float)(blockIdx.x * 32) + 15.5f) * p.vsx, ((float)(blockIdx.y * 8) + 3.5f) * p.vsy,
+                                                           ((float)z0 + 0.5f * (float)(p.zchunk - 1)) * p.vsz));
+        float mn = 3.402823466e+38f;
+        for (int i = threadIdx.x; i < p.M; i += 256) {
+            const float4 v = __ldg(p.node_rec + 2 * p.M + i);
+            const float d0 = cb.x - v.x, d1 = cb.y - v.y, d2 = cb.z - v.z;
+            mn = fminf(mn, d0 * d0 + d1 * d1 + d2 * d2);
+        }
+        if (threadIdx.x == 0) s_block_n = 0;
+#pragma unroll 1
+        for (int r = 0; r < 8; ++r) {                              // the warp's 8 smallest thread minima, ascending
+            const unsigned b = __reduce_min_sync(0xffffffffu, __float_as_uint(mn));
+            const unsigned who = __ballot_sync(0xffffffffu, __float_as_uint(mn) == b);
+            if (lane == __ffs(who) - 1) { mn = __int_as_float(0x7f800000); s_wmin[warp][r] = __uint_as_float(b); }
+        }
+        __syncthreads();
+        if (warp == 0) {                                           // 8th smallest of the 64: distances of distinct nodes, so >= d8(cb)
+            float a = (&s_wmin[0][0])[lane], b2 = (&s_wmin[0][0])[lane + 32];
+            unsigned r2 = 0u;
+#pragma unroll 1
+            for (int r = 0; r < 8; ++r) {
+                const float m = fminf(a, b2);
+                r2 = __reduce_min_sync(0xffffffffu, __float_as_uint(m));
+                const unsigned who = __ballot_sync(0xffffffffu, __float_as_uint(m) == r2);
+                if (lane == __ffs(who) - 1) { if (__float_as_uint(a) == r2) a = __int_as_float(0x7f800000); else b2 = __int_as_float(0x7f800000); }
+            }
+            if (lane == 0) s_rb2 = __uint_as_float(r2);
+        }
+        __syncthreads();
+        const float rb2 = s_rb2;
+        if (rb2 < 1e30f) {
+            const float thr = (sqrtf(rb2) + 2.f * p.half_diag_block) * 1.0002f + 1e-6f, thr2 = thr * thr;
+            for (int i0 = 0; i0 < p.M; i0 += 256) {
+                const int i = i0 + threadIdx.x;
+                bool in = false;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < p.M) {
+                    v = __ldg(p.node_rec + 2 * p.M + i);
+                    const float d0 = cb.x - v.x, d1 = cb.y - v.y, d2 = cb.z - v.z;
+                    in = d0 * d0 + d1 * d1 + d2 * d2 <= thr2;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, in);
+                int base = 0;
+                if (lane == 0 && m) base = atomicAdd(&s_block_n, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (in) {
+                    const int pos = base + __popc(m & ((1u << lane) - 1u));
+                    if (pos < FUS_BLOCK_CAP) s_block[pos] = make_float4(v.x, v.y, v.z, __int_as_float(i));
+                }
+            }
+            __syncthreads();
+            if (s_block_n >= 8 && s_block_n <= FUS_BLOCK_CAP) { from_block = true; n_src = s_block_n; }
+        }
+    }
+
     int prev[8];
     bool have_prev = false;
     unsigned int n_upd = 0, n_warp = 0;
     const size_t slice = (size_t)p.Dx * p.Dy;
     for (int za = z0; za < z1; za += FUS_SUB) {
         const int zb = min(z1, za + FUS_SUB);
-        if (can_cull && fusion_run_invisible(p, lane, delta, xw, min(xw + 7, p.Dx - 1), yw, min(yw + 3, p.Dy - 1), za, zb - 1)) continue;
-        if (!inb) continue;
+        int L = -1;                                                // candidates in the list; -1: no list for this run
+        bool culled = false;
+        // pass 0 tests the run against the field's global displacement bound before any work is spent on it; pass 1 builds the candidate
+        // list and tests again with the list's own bound.  (A loop so that the visibility test exists once in the kernel's code.)
+#pragma unroll 1
+        for (int pass = 0; pass < 2 && !culled; ++pass) {
+            float run_delta = delta;
+            if (pass == 1) {
+                if (!from_block) break;
+                run_delta = 3.402823466e+38f;
+                __syncwarp();                                      // the previous run's readers are done with the list
+                const float3 c = aff_mul(p.vol2world, make_float3(((float)xw + 3.5f) * p.vsx, ((float)yw + 1.5f) * p.vsy, ((float)za + 0.5f * (float)(FUS_SUB - 1)) * p.vsz));
+                float mn = 3.402823466e+38f;
+                for (int i = lane; i < n_src; i += 32) {
+                    const float4 v = s_block[i];
+                    const float d0 = c.x - v.x, d1 = c.y - v.y, d2 = c.z - v.z;
+                    mn = fminf(mn, d0 * d0 + d1 * d1 + d2 * d2);   // a NaN node never lowers the minimum, like it never enters a neighbour set
+                }
+                unsigned r2bits = 0u;
+#pragma unroll 1
+                for (int r = 0; r < 8; ++r) {                      // 8th smallest lane minimum (non-negative floats order like their bit patterns)
+                    r2bits = __reduce_min_sync(0xffffffffu, __float_as_uint(mn));
+                    const unsigned who = __ballot_sync(0xffffffffu, __float_as_uint(mn) == r2bits);
+                    if (lane == __ffs(who) - 1) mn = __int_as_float(0x7f800000);
+                }
+                const float R2 = __uint_as_float(r2bits);
+                if (R2 < 1e30f) {
+                    const float thr = (sqrtf(R2) + 2.f * p.half_diag) * 1.0002f + 1e-6f, thr2 = thr * thr;
+                    int base = 0;
+                    float tmax = 0.f;
+                    for (int i0 = 0; i0 < n_src; i0 += 32) {
+                        const int i = i0 + lane;
+                        bool in = false;
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (i < n_src) {
+                            v = s_block[i];
+                            const float d0 = c.x - v.x, d1 = c.y - v.y, d2 = c.z - v.z;
+                            in = d0 * d0 + d1 * d1 + d2 * d2 <= thr2;
+                        }
+                        const unsigned m = __ballot_sync(0xffffffffu, in);
+                        if (in) {
+                            const int pos = base + __popc(m & ((1u << lane) - 1u));
+                            if (pos < FUS_LIST_CAP) list[pos] = (unsigned short)i;
+                            const float4 t = __ldg(p.node_rec + p.M + __float_as_int(v.w));
+                            tmax = fmaxf(tmax, sqrtf(t.y * t.y + t.z * t.z + t.w * t.w));
+                        }
+                        base += __popc(m);
+                    }
+                    if (base <= FUS_LIST_CAP) {
+                        L = base;
+                        if (identity) {                            // this run moves by at most 8 max |t| over ITS candidate nodes
+                            for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+                            const float local = 8.f * tmax * 1.0001f + 1e-6f;
+                            if (local < delta) run_delta = local;
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            if (can_cull && run_delta < 3.0e38f)
+                culled = fusion_run_invisible(p, lane, run_delta, xw, min(xw + 7, p.Dx - 1), yw, min(yw + 3, p.Dy - 1), za, zb - 1);
+        }
+        if (culled || !inb) continue;
         uint32_t *vptr = p.data + x + (size_t)p.Dx * y + slice * za;
         for (int z = za; z < zb; ++z, vptr += slice) {
             const float3 xc = aff_mul(p.vol2world, make_float3((float)x * p.vsx, (float)y * p.vsy, (float)z * p.vsz));
             int bi[8]; float bd[8];
-            if (has_bvh) {
-                bool seeded = false;
-                if (have_prev) {                                   // the previous voxel's neighbours at this voxel's position
-                    seeded = true;
+            if (L >= 0) {
+                bool seeded = have_prev;
+                if (have_prev) {
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        const float4 v = __ldg(p.node_rec + 3 * prev[k] + 2);
+                        const float4 v = __ldg(p.node_rec + 2 * p.M + prev[k]);
                         const float d0 = xc.x - v.x, d1 = xc.y - v.y, d2 = xc.z - v.z;
                         bi[k] = prev[k];
                         bd[k] = d0 * d0 + d1 * d1 + d2 * d2;
                         seeded = seeded && bd[k] == bd[k];
                     }
-                } else {
-                    seeded = knn8_bvh_greedy_seed(bvh_box, bvh_leaf, h.pad[4], xc.x, xc.y, xc.z, bi, bd);
                 }
-                if (seeded) knn8_bvh_seeded(bvh_box, bvh_leaf, h.pad[4], xc.x, xc.y, xc.z, bi, bd);
-                else knn8_bvh_bounded(bvh_box, bvh_leaf, h.pad[4], xc.x, xc.y, xc.z, 3.402823466e+38f, bi, bd);
-            } else {
-                knn8_grid(p.grid, true, xc.x, xc.y, xc.z, bi, bd);
+                if (seeded) {
+#define DF_CS(a, b) knn8_cswap_lex(bd[a], bi[a], bd[b], bi[b])
+                    DF_CS(0, 1); DF_CS(2, 3); DF_CS(4, 5); DF_CS(6, 7);
+                    DF_CS(0, 2); DF_CS(1, 3); DF_CS(4, 6); DF_CS(5, 7);
+                    DF_CS(1, 2); DF_CS(5, 6);
+                    DF_CS(0, 4); DF_CS(1, 5); DF_CS(2, 6); DF_CS(3, 7);
+                    DF_CS(2, 4); DF_CS(3, 5);
+                    DF_CS(1, 2); DF_CS(3, 4); DF_CS(5, 6);
+#undef DF_CS
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { bi[k] = 0x7fffffff; bd[k] = 3.402823466e+38f; }
+                }
+#pragma unroll 1
+                for (int j = 0; j < L; ++j) {
+                    const float4 nd = s_block[list[j]];
+                    const float d0 = xc.x - nd.x, d1 = xc.y - nd.y, d2 = xc.z - nd.z;
+                    const float dist = d0 * d0 + d1 * d1 + d2 * d2;
+                    if (dist <= bd[7]) {                           // one compare on the common (reject) path; ties and seeds sorted out inside
+                        const int idx = __float_as_int(nd.w);
+                        if (dist < bd[7] || idx < bi[7]) {
+                            const bool held = idx == bi[0] || idx == bi[1] || idx == bi[2] || idx == bi[3] || idx == bi[4] || idx == bi[5] || idx == bi[6];
+                            if (!held) knn8_insert_lex(bi, bd, dist, idx);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) if (bi[k] == 0x7fffffff) bi[k] = -1;
+            } else {                                               // cold path: copies keep bi / bd / prev themselves in registers
+                int tp[8], tb[8]; float td[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) tp[k] = prev[k];
+                fusion_tree_search(p.grid, p.node_rec + 2 * p.M, xc, have_prev, tp, tb, td);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { bi[k] = tb[k]; bd[k] = td[k]; }
             }
             have_prev = bi[7] >= 0;
 #pragma unroll
@@ -393,10 +602,32 @@ extern "C" int df_integrate_warped(df_volume vol, const uint16_t *depth, size_t 
     p.bricks = brick_table(activity, vol.dims[0], vol.dims[1], vol.dims[2]);
     p.tiles_x = div_up(cols, FUS_TILE); p.tiles_y = div_up(rows, FUS_TILE);
     p.ctiles_x = div_up(p.tiles_x, FUS_COARSE); p.ctiles_y = div_up(p.tiles_y, FUS_COARSE);
+    {
+        const char *e = getenv("DF_FUSION_LIST");      // test knob, per call: 0 = branch-and-bound per voxel only (round 1)
+        p.use_list = !(e && atoi(e) == 0);
+        double worst = 0.0;                             // half the longest diagonal of the box of voxel centres of a warp run, in world space
+        for (int sgn = 0; sgn < 4; ++sgn) {
+            const double ex = 7.0 * p.vsx, ey = ((sgn & 1) ? -3.0 : 3.0) * p.vsy, ez = ((sgn & 2) ? -(double)(FUS_SUB - 1) : (double)(FUS_SUB - 1)) * p.vsz;
+            double d2 = 0.0;
+            for (int i = 0; i < 3; ++i) { const double v = vol2world.R[3 * i] * ex + vol2world.R[3 * i + 1] * ey + vol2world.R[3 * i + 2] * ez; d2 += v * v; }
+            worst = fmax(worst, sqrt(d2));
+        }
+        p.half_diag = (float)(0.5 * worst * 1.001 + 1e-7);
+    }
     p.zchunk = vol.dims[2] >= 64 ? 32 : vol.dims[2];
     {
         const char *e = getenv("DF_FUSION_ZCHUNK");    // test knob, per call
         if (e && atoi(e) > 0) p.zchunk = atoi(e);
+    }
+    {
+        double worst = 0.0;
+        for (int sgn = 0; sgn < 4; ++sgn) {
+            const double ex = 31.0 * p.vsx, ey = ((sgn & 1) ? -7.0 : 7.0) * p.vsy, ez = ((sgn & 2) ? -1.0 : 1.0) * (double)(p.zchunk - 1) * p.vsz;
+            double d2 = 0.0;
+            for (int i = 0; i < 3; ++i) { const double v = vol2world.R[3 * i] * ex + vol2world.R[3 * i + 1] * ey + vol2world.R[3 * i + 2] * ez; d2 += v * v; }
+            worst = fmax(worst, sqrt(d2));
+        }
+        p.half_diag_block = (float)(0.5 * worst * 1.001 + 1e-7);
     }
     float *ws = (float *)workspace;
     const bool own = ws == nullptr;

@@ -20,6 +20,7 @@
 #include "warp_common.cuh"
 #include <cooperative_groups.h>
 #include <cstdlib>
+#include <cstdio>
 
 namespace cg = cooperative_groups;
 
@@ -636,7 +637,15 @@ struct Lm5Smem {
     unsigned long long bar_pub;
 };
 
+// -DDF_LM_PROFILE (build.py: DF_NVCC_EXTRA): thread-local clock64 accounting of the LM kernel's phases, printed per CTA at exit.
+// 0 mat-vec, 1 per-row arithmetic, 2 sum: shuffles + block barrier + sends, 3 sum: wait, 4 sum: final tree, 5 publish: sends, 6 publish: wait
+#ifdef DF_LM_PROFILE
+#define LMP_MARK(sy, i) do { const long long t_ = clock64(); (sy).t[i] += t_ - (sy).last; (sy).last = t_; } while (0)
+struct Lm5Sync { int parity; uint32_t phase_red[2]; uint32_t phase_pub; long long t[8]; long long last; };
+#else
+#define LMP_MARK(sy, i) do { } while (0)
 struct Lm5Sync { int parity; uint32_t phase_red[2]; uint32_t phase_pub; };
+#endif
 
 // kOwnerOnly: only the lanes that own a row (lane % tpr == 0) hold a non-zero contribution, so the warp butterfly can stop at
 // offset tpr (3 of 5 steps at the usual 4 threads per row).  ncu (profiles/r02_lm_*_by_line.txt): the shuffles of this function were
@@ -648,6 +657,7 @@ __device__ __forceinline__ void cluster_sum5(Lm5Smem<NCTA> &sm, Lm5Sync &sy, int
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int par = sy.parity;
     const int stop = kOwnerOnly ? tpr : 1;
+    LMP_MARK(sy, 1);
 #pragma unroll
     for (int k = 0; k < NV; ++k)
         for (int o = 16; o >= stop; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
@@ -667,7 +677,9 @@ __device__ __forceinline__ void cluster_sum5(Lm5Smem<NCTA> &sm, Lm5Sync &sy, int
         }
         if (lane == 0) mbar_arrive_expect(bar, (uint32_t)(NCTA * NV * 8));
     }
+    LMP_MARK(sy, 2);
     mbar_wait(bar, sy.phase_red[par]);
+    LMP_MARK(sy, 3);
     sy.phase_red[par] ^= 1u;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
@@ -677,13 +689,14 @@ __device__ __forceinline__ void cluster_sum5(Lm5Smem<NCTA> &sm, Lm5Sync &sy, int
         v[k] = t;
     }
     sy.parity = par ^ 1;
+    LMP_MARK(sy, 4);
 }
 
 // NCTA = CTAs per cluster (8, or 16 = the non-portable maximum: half the rows, hence half the shared-memory gather traffic of the
 // mat-vec, per SM); the cluster shape is a launch attribute.
 template <int NCTA, bool merged>
 __global__ void __launch_bounds__(LM4_THREADS, 1)
-solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_iters, int lin_iters, double *stats, int ent_cap)
+solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_iters, int lin_iters, double *stats, int ent_cap, int balanced)
 {
     DF_PDL_ENTRY();
     cg::cluster_group cluster = cg::this_cluster();
@@ -693,16 +706,73 @@ solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
     double *svec = reinterpret_cast<double *>(dyn + L.off_svec);          // full-length copy of the multiplied vector, [3 * node + axis]
     double *mval = reinterpret_cast<double *>(dyn + L.off_val);           // [entry][thread]
     unsigned short *mcol = reinterpret_cast<unsigned short *>(dyn + L.off_col);   // 3 * column
-    const int rpc = L.rpc, tpr = L.tpr;
+    const int rpc = L.rpc;
 
     Lm5Sync sy; sy.parity = 0; sy.phase_red[0] = sy.phase_red[1] = 0u; sy.phase_pub = 0u;
     const int cta = (int)cluster.block_rank();
     const int tid = threadIdx.x;
-    const int rl = tid / tpr, sub = tid % tpr;
     // Rows are dealt to the CTAs in the node grid's Morton order (nodegrid.cu step 5): a CTA's rows are neighbours in space, so
     // most of the columns they touch are the CTA's own rows and a row's search-direction entry is needed by few other CTAs.
     const int *order = grid ? nodegrid_order(grid) : nullptr;
     const int *slot = grid ? nodegrid_slot(grid) : nullptr;
+    // Lanes per row in proportion to the row's length (round 2).  With a fixed 4 lanes per row the mat-vec of a step took as long as the
+    // CTA's longest row (rim rows: 60-100 entries against a median of 20) while most lanes had 5 entries; a row now gets
+    // 1, 2, 4, ... 32 consecutive lanes ~ nnz / target, target = the smallest entries-per-lane for which the CTA's rows fit its 512
+    // lanes.  Groups are laid out longest first, so every group is aligned to its size and never straddles a warp; the position of a
+    // row depends on its rank among the rows of its class only (deterministic: the order in which rows enter the sums is fixed).
+    __shared__ unsigned short t_rl[LM4_THREADS];
+    __shared__ unsigned char t_sub[LM4_THREADS], t_tr[LM4_THREADS];
+    __shared__ unsigned char row_cls[LM4_THREADS];
+    __shared__ int cls_cnt[8], cls_start[8], bal_sum[2];
+    if (!balanced) {                                           // DF_SOLVE_BALANCED=0: the fixed power-of-two lanes per row of round 1
+        const int r = tid / L.tpr;
+        t_rl[tid] = (unsigned short)r; t_sub[tid] = (unsigned char)(tid % L.tpr); t_tr[tid] = (unsigned char)(r < rpc ? L.tpr : 0);
+        __syncthreads();
+    } else {
+        int my_nnz = 0;
+        const bool row_here = tid < rpc && cta * rpc + tid < M;
+        if (row_here) my_nnz = ws.rownnz[order ? order[cta * rpc + tid] : cta * rpc + tid];
+        if (tid < 2) bal_sum[tid] = 0;
+        if (tid < 8) cls_cnt[tid] = 0;
+        t_tr[tid] = 0; t_rl[tid] = 0; t_sub[tid] = 0;
+        __syncthreads();
+        if (row_here) atomicAdd(&bal_sum[0], my_nnz);
+        __syncthreads();
+        int target = max(1, (bal_sum[0] + LM4_THREADS - 1) / LM4_THREADS);
+        int my_t = 0;
+        for (int round = 0; round < 40; ++round) {              // block-uniform loop: every thread sees the same sums
+            my_t = 0;
+            if (row_here) {
+                const int want = (my_nnz + target - 1) / target;
+                my_t = 1;
+                while (my_t < want && my_t < 32) my_t <<= 1;
+            }
+            __syncthreads();
+            if (tid == 0) bal_sum[1] = 0;
+            __syncthreads();
+            if (my_t) atomicAdd(&bal_sum[1], my_t);
+            __syncthreads();
+            if (bal_sum[1] <= LM4_THREADS) break;
+            target = target + (target >> 2) + 1;
+        }
+        const int cls = my_t ? 31 - __clz(my_t) : 7;            // 0..5; 7 = no row
+        row_cls[tid] = (unsigned char)cls;
+        if (my_t) atomicAdd(&cls_cnt[cls], 1);
+        __syncthreads();
+        if (tid == 0) { int acc = 0; for (int c = 5; c >= 0; --c) { cls_start[c] = acc; acc += cls_cnt[c] << c; } }
+        __syncthreads();
+        if (my_t) {
+            int rank = 0;                                       // rows of my class with a smaller slot index
+            for (int j = 0; j < tid; ++j) rank += row_cls[j] == cls;
+            const int first = cls_start[cls] + (rank << cls);
+            for (int l = 0; l < my_t; ++l) { t_rl[first + l] = (unsigned short)tid; t_sub[first + l] = (unsigned char)l; t_tr[first + l] = (unsigned char)my_t; }
+        }
+        __syncthreads();
+    }
+    const int tpr = t_tr[tid];                                 // lanes serving this thread's row (0: idle lane)
+    const int rl = tpr ? (int)t_rl[tid] : rpc, sub = t_sub[tid];
+    const int wtpr = __reduce_min_sync(0xffffffffu, tpr ? tpr : 32);   // the warp's smallest group: owner lanes sit at multiples of it
+    const int wmax = __reduce_max_sync(0xffffffffu, tpr);             // ... and its largest: the row sums need log2(wmax) shuffle steps
     const int s_row = cta * rpc + rl;                          // slot of this thread's row
     const bool has_row = rl < rpc && s_row < M;
     const int n = has_row ? (order ? order[s_row] : s_row) : 0;   // node index = row/column index of the normal matrix
@@ -711,7 +781,7 @@ solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
     const int nnz = has_row ? ws.rownnz[n] : 0;
     int my_ent = 0;
     unsigned need = 0u;                                        // CTAs that own a row coupled to this one (A is structurally symmetric)
-    for (int e = sub; e < nnz; e += tpr) {
+    for (int e = sub; e < nnz; e += max(tpr, 1)) {
         const int j = ws.col[(size_t)e * M + n];
         need |= 1u << ((slot ? slot[j] : j) / rpc);
         if (my_ent < ent_cap) {
@@ -720,7 +790,7 @@ solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
             ++my_ent;
         }
     }
-    for (int o = tpr >> 1; o > 0; o >>= 1) need |= __shfl_xor_sync(0xffffffffu, need, o);
+    for (int o = wmax >> 1; o > 0; o >>= 1) { const unsigned t = __shfl_xor_sync(0xffffffffu, need, o); if (o < tpr) need |= t; }
     need |= 1u << cta;
     const int e_rest = sub + my_ent * tpr;                     // entries that did not fit are streamed from L2 (rare)
     const double diag_n = has_row ? ws.diag[n] : 0.0;
@@ -731,6 +801,7 @@ solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
     uint32_t pub_bytes = 0;                                    // bytes this CTA receives per exchange (set once below)
     // this row's three values -> the svec of every CTA that multiplies by them; then wait until this CTA's own svec is complete
     auto publish = [&](double a0, double a1, double a2) {
+        LMP_MARK(sy, 1);
         if (owner) {
 #pragma unroll
             for (int c = 0; c < NCTA; ++c) {
@@ -740,26 +811,31 @@ solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
             }
         }
         if (tid == 0) mbar_arrive_expect(pub_bar, pub_bytes);
+        LMP_MARK(sy, 5);
         mbar_wait(pub_bar, sy.phase_pub);
+        LMP_MARK(sy, 6);
         sy.phase_pub ^= 1u;
     };
     auto spmv = [&](double &o0, double &o1, double &o2) {      // (A * svec)[row], valid in the owner lane
         double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        LMP_MARK(sy, 1);
 #pragma unroll 4
         for (int k = 0; k < my_ent; ++k) {
             const double *sv = svec + mcol[k * LM4_THREADS + tid];
             const double a = mval[k * LM4_THREADS + tid];
             a0 += a * sv[0]; a1 += a * sv[1]; a2 += a * sv[2];
         }
-        for (int e = e_rest; e < nnz; e += tpr) {
+        for (int e = e_rest; e < nnz; e += max(tpr, 1)) {
             const double *sv = svec + 3 * __ldg(ws.col + (size_t)e * M + n);
             const double a = __ldg(ws.val + (size_t)e * M + n);
             a0 += a * sv[0]; a1 += a * sv[1]; a2 += a * sv[2];
         }
-        for (int o = tpr >> 1; o > 0; o >>= 1) {
-            a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+        for (int o = wmax >> 1; o > 0; o >>= 1) {              // group sizes differ inside a warp: everybody shuffles, a lane adds what is in its group
+            const double b0 = __shfl_xor_sync(0xffffffffu, a0, o), b1 = __shfl_xor_sync(0xffffffffu, a1, o), b2 = __shfl_xor_sync(0xffffffffu, a2, o);
+            if (o < tpr) { a0 += b0; a1 += b1; a2 += b2; }
         }
         o0 = a0; o1 = a1; o2 = a2;
+        LMP_MARK(sy, 0);
     };
 
     // x0 = current node translations (CombinedSolver.h:165-172)
@@ -800,12 +876,17 @@ solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
         t0[0] += x1 * (0.5 * Ap1 - gb1);
         t0[0] += x2 * (0.5 * Ap2 - gb2);
     }
-    cluster_sum5<NCTA, sizeof(t0) / sizeof(double), true>(sm, sy, cta, t0, tpr);
+    cluster_sum5<NCTA, sizeof(t0) / sizeof(double), true>(sm, sy, cta, t0, wtpr);
     double cost = c0n[0] + t0[0];
     const double cost0 = cost;
 
     double radius = 1e4, decrease = 2.0;                       // solverGPUGaussNewton.t:26-39
     int it = 0, pcg_total = 0;
+#ifdef DF_LM_PROFILE
+    for (int i = 0; i < 8; ++i) sy.t[i] = 0;
+    sy.last = clock64();
+    const long long lmp_begin = sy.last;
+#endif
     const bool overflow = ws.flags[0] != 0;                    // a row overflowed (solve_rows): the stored system is truncated -> leave the field
     if (overflow) nl_iters = 0;                                // unchanged (not even re-encoded), stats[5] says so
     for (; it < nl_iters; ++it) {
@@ -821,7 +902,7 @@ solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
             p0 = g0 * mi; p1 = g1 * mi; p2 = g2 * mi;
             rzv[0] += g0 * p0; rzv[0] += g1 * p1; rzv[0] += g2 * p2;
         }
-        cluster_sum5<NCTA, sizeof(rzv) / sizeof(double), true>(sm, sy, cta, rzv, tpr);                        // completes only when every CTA has finished reading svec (x) ...
+        cluster_sum5<NCTA, sizeof(rzv) / sizeof(double), true>(sm, sy, cta, rzv, wtpr);                        // completes only when every CTA has finished reading svec (x) ...
         publish(p0, p1, p2);                                   // ... so p may overwrite it
         double rz = rzv[0];
         double Q0 = 0.0;
@@ -841,7 +922,7 @@ solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
                 Ap1 = Ap1 + cdn * p1; m = mi * r1; n = mi * Ap1; v[0] += p1 * Ap1; v[1] += m * r1; v[2] += m * Ap1; v[3] += n * Ap1;
                 Ap2 = Ap2 + cdn * p2; m = mi * r2; n = mi * Ap2; v[0] += p2 * Ap2; v[1] += m * r2; v[2] += m * Ap2; v[3] += n * Ap2;
             }
-            cluster_sum5<NCTA, sizeof(v) / sizeof(double), true>(sm, sy, cta, v, tpr);                      // every CTA finished reading svec (p)
+            cluster_sum5<NCTA, sizeof(v) / sizeof(double), true>(sm, sy, cta, v, wtpr);                      // every CTA finished reading svec (p)
             if (!(v[0] > 0.0) || !(v[1] > 0.0)) break;
             const double rz_now = v[1];
             const double alpha = rz_now / v[0];
@@ -867,7 +948,7 @@ solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
                 Ap0 = Ap0 + cdn * p0; Ap1 = Ap1 + cdn * p1; Ap2 = Ap2 + cdn * p2;
                 pap[0] += p0 * Ap0; pap[0] += p1 * Ap1; pap[0] += p2 * Ap2;
             }
-            cluster_sum5<NCTA, sizeof(pap) / sizeof(double), true>(sm, sy, cta, pap, tpr);                    // every CTA finished reading svec (p)
+            cluster_sum5<NCTA, sizeof(pap) / sizeof(double), true>(sm, sy, cta, pap, wtpr);                    // every CTA finished reading svec (p)
             if (!(pap[0] > 0.0)) break;
             const double alpha = rz / pap[0];
             double rq[2] = {0.0, 0.0};
@@ -877,7 +958,7 @@ solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
                 dl1 = dl1 + alpha * p1; r1 = r1 - alpha * Ap1; z1 = r1 * mi; rq[0] += r1 * z1; rq[1] += dl1 * (r1 + g1);
                 dl2 = dl2 + alpha * p2; r2 = r2 - alpha * Ap2; z2 = r2 * mi; rq[0] += r2 * z2; rq[1] += dl2 * (r2 + g2);
             }
-            cluster_sum5<NCTA, sizeof(rq) / sizeof(double), true>(sm, sy, cta, rq, tpr);
+            cluster_sum5<NCTA, sizeof(rq) / sizeof(double), true>(sm, sy, cta, rq, wtpr);
             const double rz_new = rq[0], Q1 = -0.5 * rq[1];
             const double beta = rz_new / rz;
             if (owner) { p0 = z0 + beta * p0; p1 = z1 + beta * p1; p2 = z2 + beta * p2; }
@@ -896,7 +977,7 @@ solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
             c = cdn * dl1; mad[0] += dl1 * (g1 + r1 + c); mad[1] += dl1 * (g1 - r1 - c); mad[2] += dl1 * g1;
             c = cdn * dl2; mad[0] += dl2 * (g2 + r2 + c); mad[1] += dl2 * (g2 - r2 - c); mad[2] += dl2 * g2;
         }
-        cluster_sum5<NCTA, sizeof(mad) / sizeof(double), true>(sm, sy, cta, mad, tpr);
+        cluster_sum5<NCTA, sizeof(mad) / sizeof(double), true>(sm, sy, cta, mad, wtpr);
         const double model = 0.5 * mad[0];
         const double new_cost = cost - mad[2] + 0.5 * mad[1];
         const double change = cost - new_cost;
@@ -917,6 +998,12 @@ solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
         if (stop) { ++it; break; }
         publish(x0, x1, x2);                                   // svec <- x for the next linearisation (the mad reduction proves nobody reads p any more)
     }
+#ifdef DF_LM_PROFILE
+    LMP_MARK(sy, 1);
+    if ((tid == 0 || tid == LM4_THREADS - 1) && (cta == 0 || cta == NCTA - 1 || cta == NCTA / 2))
+        printf("LMP cta %d tid %d my_ent %d tpr %d steps %d total %lld | spmv %lld arith %lld sum_send %lld sum_wait %lld sum_tree %lld pub_send %lld pub_wait %lld\n",
+               cta, tid, my_ent, tpr, pcg_total, clock64() - lmp_begin, sy.t[0], sy.t[1], sy.t[2], sy.t[3], sy.t[4], sy.t[5], sy.t[6]);
+#endif
     cluster.sync();                                            // no CTA may exit while others can still write into its shared memory
     // write back: encodeTranslation (CombinedSolver.h:189-197, dual_quaternion.hpp:82-85)
     if (owner && !overflow) {
@@ -988,16 +1075,17 @@ int dfb::solve_data_term_ev(float *nodes, int M, const void *node_grid, const fl
     static const int want = [] { const char *e = getenv("DF_SOLVE_LM_CTAS"); return e ? atoi(e) : 16; }();
     const int ncta = (want == 16 && M >= 256) ? 16 : 8;
     const Lm4Layout Lb = lm4_layout(M, 0, ncta);
-    const size_t budget = ncta == 16 ? (size_t)216 * 1024 : (size_t)224 * 1024;      // the 16-CTA variant has 6 KB of static shared memory
+    const size_t budget = ncta == 16 ? (size_t)216 * 1024 : (size_t)220 * 1024;      // 227 KB minus the static shared memory (8.6 KB with 16 CTAs, 4.6 KB with 8)
     if (solve_lm_impl() >= 5 && Lb.rpc * Lb.tpr <= LM4_THREADS && Lb.total + (size_t)LM4_THREADS * 10 * 8 <= budget) {
         const int cap = (int)((budget - Lb.total - 16) / ((size_t)LM4_THREADS * 10));
         const Lm4Layout Lc = lm4_layout(M, cap, ncta);
         static const int merged = [] { const char *e = getenv("DF_SOLVE_MERGED"); return e ? atoi(e) : 1; }();
-        using KernelT = void (*)(float *, int, const void *, SolveWs, int, int, double *, int);
+        using KernelT = void (*)(float *, int, const void *, SolveWs, int, int, double *, int, int);
+        static const int balanced = [] { const char *e = getenv("DF_SOLVE_BALANCED"); return e ? atoi(e) : 1; }();
         const KernelT kern = ncta == 16 ? (merged ? (KernelT)solve_lm_v5_kernel<16, true> : (KernelT)solve_lm_v5_kernel<16, false>)
                                         : (merged ? (KernelT)solve_lm_v5_kernel<8, true> : (KernelT)solve_lm_v5_kernel<8, false>);
         // function attributes are per device: set them on every launch (cheap) rather than once per process
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ncta == 16 ? 216 * 1024 : 224 * 1024);
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ncta == 16 ? 216 * 1024 : 220 * 1024);
         if (ncta == 16) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(ncta); cfg.blockDim = dim3(LM4_THREADS); cfg.dynamicSmemBytes = Lc.total; cfg.stream = s;
@@ -1007,7 +1095,7 @@ int dfb::solve_data_term_ev(float *nodes, int M, const void *node_grid, const fl
         at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[1].val.programmaticStreamSerializationAllowed = pdl_enabled();
         cfg.attrs = at; cfg.numAttrs = 2;
-        const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, nodes, M, node_grid, ws, nonlinear_iters, linear_iters, stats_dev, cap);
+        const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, nodes, M, node_grid, ws, nonlinear_iters, linear_iters, stats_dev, cap, balanced);
         if (le != cudaSuccess) return (int)le;
     } else {
         solve_lm_kernel<<<1, LM_THREADS, 0, s>>>(nodes, M, ws, nonlinear_iters, linear_iters, stats_dev);

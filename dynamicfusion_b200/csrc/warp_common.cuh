@@ -420,7 +420,40 @@ __device__ __forceinline__ float3 qrotate(const Quat q, const float3 v)
     return make_float3(v.x + c.x, v.y + c.y, v.z + c.z);
 }
 // WarpField::weighting, warp_field.cpp:238-241: double exp of a float argument, narrowed to float
-__device__ __forceinline__ float node_weighting(float d2, float node_w) { return (float)exp((double)(-d2 / (2 * node_w * node_w))); }
+// WarpField::weighting (warp_field.cpp:262-265): (float)exp((double)x), x = -d2 / (2 w^2) in float.  The generic double exp is ~60 instructions and
+// was 19 % of the warped-fusion kernel (profiles/r02_fusion_list_by_line.txt).  With the reference's node weight (3, i.e. sigma = 3 m) x
+// lies in [-0.06, 0]; for x in [-0.5, 0] the value is formed as exp(-1/4) * P13(x + 1/4), a degree-13 Taylor polynomial in fused double
+// arithmetic (truncation 2.4e-18, |r| <= 1/4): after the rounding to float it equals (float)exp((double)x) of a correctly rounded libm for
+// EVERY float in the interval -- checked exhaustively, 1,056,964,609 values, by tests/test_weight_exp.py against glibc (the oracle's exp).
+// Anything else (other node weights, NaN) takes the generic path.
+__device__ __forceinline__ float node_weighting_generic(float d2, float node_w) { return (float)exp((double)(-d2 / (2 * node_w * node_w))); }
+// out of line: the generic exp is ~60 instructions, and kernels that weight eight neighbours per element would carry eight copies of it next to
+// the polynomial -- the warped-fusion kernel turned out to be bound by instruction fetch (profiles/r02_fusion_list2_ncu_raw.csv)
+static __device__ __noinline__ float node_weighting_slow(float x) { return (float)exp((double)x); }
+
+__device__ __forceinline__ float node_weighting(float d2, float node_w)
+{
+    const float x = -d2 / (2 * node_w * node_w);
+    if (x >= -0.5f && x <= 0.f) {
+        const double r = (double)x + 0.25;
+        double p = 1.0 / 6227020800.0;
+        p = __fma_rn(p, r, 1.0 / 479001600.0);
+        p = __fma_rn(p, r, 1.0 / 39916800.0);
+        p = __fma_rn(p, r, 1.0 / 3628800.0);
+        p = __fma_rn(p, r, 1.0 / 362880.0);
+        p = __fma_rn(p, r, 1.0 / 40320.0);
+        p = __fma_rn(p, r, 1.0 / 5040.0);
+        p = __fma_rn(p, r, 1.0 / 720.0);
+        p = __fma_rn(p, r, 1.0 / 120.0);
+        p = __fma_rn(p, r, 1.0 / 24.0);
+        p = __fma_rn(p, r, 1.0 / 6.0);
+        p = __fma_rn(p, r, 0.5);
+        p = __fma_rn(p, r, 1.0);
+        p = __fma_rn(p, r, 1.0);
+        return (float)(0.77880078307140486825 * p);              // exp(-1/4)
+    }
+    return node_weighting_slow(x);
+}
 
 struct Dqb { Quat rot, dual; };
 

@@ -206,6 +206,40 @@ def test_culling_is_invisible(orc):
     print(f"256^3: {int(ca[0])} voxels written; warped {int(ca[1])} with culling vs {int(cb[1])} without")
 
 
+def test_candidate_lists_equal_the_tree_search(orc):
+    """round 2: per-run candidate lists (DF_FUSION_LIST, default on) must find exactly the neighbours the per-voxel branch-and-bound finds, and
+    their local displacement bound may only skip voxels that would not have been written -- 256^3, ~2 k nodes, a handful of 'rim' nodes
+    carrying decimetre translations so that the global bound (8 max |t| = metres) culls nothing, as in the live loop"""
+    dim = 256
+    depth = synth.umbrella_depth(3)
+    nodes = _surface_nodes(orc, 2000, seed=1, t_scale=0.0015)
+    lib = orc.load()
+    for i in (5, 700, 1500):
+        lib.orc_node_encode_translation(C.c_void_p(nodes[i].ctypes.data), C.c_float(0.3), C.c_float(-0.2), C.c_float(0.25))
+    wf = host.WarpField()
+    wf.setNodes(torch.from_numpy(nodes).cuda())
+    d_depth = host.u16_to_device(depth)
+    out = []
+    for use_list in ("1", "0"):
+        os.environ["DF_FUSION_LIST"] = use_list
+        try:
+            vol = _volume(dim, 1.0)
+            counters = torch.zeros(2, dtype=torch.int64, device="cuda")
+            for _ in range(2):
+                vol.integrate_warped(d_depth, _tilted_pose(), K, wf, 100.0, counters)
+            torch.cuda.synchronize()
+            out.append((vol.data_.clone(), vol.activity_.clone(), counters.cpu().numpy().copy()))
+            del vol
+        finally:
+            os.environ.pop("DF_FUSION_LIST", None)
+    (va, aa, ca), (vb, ab, cb) = out
+    assert int(ca[0]) == int(cb[0]) and int(ca[0]) > 100_000
+    assert torch.equal(va, vb) and torch.equal(aa, ab)
+    assert int(cb[1]) == 2 * dim ** 3, "the global bound was expected to cull nothing here"
+    assert int(ca[1]) < int(cb[1])
+    print(f"256^3: {int(ca[0])} voxels written; warped {int(ca[1])} with candidate lists (local bound) vs {int(cb[1])} with the global bound")
+
+
 def test_pipeline_with_warped_integration_tracks_the_oracle_pipeline(orc):
     """DF_KINFU_WARPED_INTEGRATE through the frame loop (df_kinfu_*) against the oracle's loop with the same flag, 64^3, 3 frames (two
     warped fusions).  Statistical like tests/test_pipeline_gpu.py: the two solves stop on the reference's PCG tolerance a few per cent

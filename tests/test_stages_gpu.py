@@ -353,7 +353,7 @@ def test_solve_row_overflow_is_loud_and_leaves_the_field_unchanged():
     assert torch.equal(before, wf.nodes_)
 
 
-@pytest.mark.parametrize("env", [{"DF_ICP_PERSISTENT": "1"}, {"DF_SOLVE_MERGED": "0"}, {"DF_SOLVE_LM_IMPL": "1"}, {"DF_SOLVE_LM_CTAS": "8"}])
+@pytest.mark.parametrize("env", [{"DF_ICP_PERSISTENT": "1"}, {"DF_SOLVE_MERGED": "0"}, {"DF_SOLVE_BALANCED": "0"}, {"DF_SOLVE_LM_IMPL": "1"}, {"DF_SOLVE_LM_CTAS": "8"}])
 def test_alternative_icp_and_solve_kernels_in_subprocess(env):
     """The A/B variants that are selected once per process: the one-launch persistent ICP (grid barrier per iteration), the PCG with two
     reductions per step, the one-block LM fallback and the 8-CTA cluster.  Each re-runs this file's ICP / solve parity tests under
