@@ -7,10 +7,12 @@ library is missing -- there is no CPU fallback in the product path.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
-_LIB_PATH = _HERE / "libdfusion.so"
+# DF_LIB_VARIANT=<tag> loads libdfusion_<tag>.so instead (instrumented / A-B builds made by tools/build_variant.py; measurement only)
+_LIB_PATH = _HERE / (f"libdfusion_{os.environ['DF_LIB_VARIANT']}.so" if os.environ.get("DF_LIB_VARIANT") else "libdfusion.so")
 _lib = None
 MISSING: list[str] = []
 

@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(1024) solve_scan_kernel(SolveWs ws, int M)
     int run = partial[t] - s;
     for (int i = b; i < e; ++i) { ws.off[i] = run; run += ws.cnt[i]; ws.cursor[i] = 0; }
     if (t == 1023) ws.off[M] = partial[1023];
-    if (t == 0) ws.flags[0] = 0;
+    if (t == 0) { ws.flags[0] = 0; ws.flags[1] = 0; }          // [0] row overflow, [1] v6 handed the frame to v5
     // Launch order of solve_rows: one block per node, and the rim nodes' lists are 100x the median -- scheduled last they are the
     // kernel's tail.  Longest-processing-time-first: nodes grouped by floor(log2(count)), heaviest group first (the order inside a
     // group is whatever the shared-memory atomics give: it affects only WHEN a row is assembled, never its value).
@@ -629,6 +629,68 @@ __device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uin
     asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr), "l"(__double_as_longlong(v)), "r"(remote_bar) : "memory");
 }
 
+// Row -> lane mapping of the cluster LM kernels (shared by v5 and v6).
+struct LmRowMap {
+    unsigned short t_rl[LM4_THREADS];
+    unsigned char t_sub[LM4_THREADS], t_tr[LM4_THREADS], row_cls[LM4_THREADS];
+    int cls_cnt[8], cls_start[8], bal_sum[2];
+};
+
+__device__ __forceinline__ void lm_map_rows(LmRowMap &mp, const SolveWs &ws, const int *order, int cta, int rpc, int tpr_fixed, int M, int balanced)
+{
+    const int tid = threadIdx.x;
+    // Lanes per row in proportion to the row's length (round 2).  With a fixed 4 lanes per row the mat-vec of a step took as long as the
+    // CTA's longest row (rim rows: 60-100 entries against a median of 20) while most lanes had 5 entries; a row now gets
+    // 1, 2, 4, ... 32 consecutive lanes ~ nnz / target, target = the smallest entries-per-lane for which the CTA's rows fit its 512
+    // lanes.  Groups are laid out longest first, so every group is aligned to its size and never straddles a warp; the position of a
+    // row depends on its rank among the rows of its class only (deterministic: the order in which rows enter the sums is fixed).
+    if (!balanced) {                                           // DF_SOLVE_BALANCED=0: the fixed power-of-two lanes per row of round 1
+        const int r = tid / tpr_fixed;
+        mp.t_rl[tid] = (unsigned short)r; mp.t_sub[tid] = (unsigned char)(tid % tpr_fixed); mp.t_tr[tid] = (unsigned char)(r < rpc ? tpr_fixed : 0);
+        __syncthreads();
+    } else {
+        int my_nnz = 0;
+        const bool row_here = tid < rpc && cta * rpc + tid < M;
+        if (row_here) my_nnz = ws.rownnz[order ? order[cta * rpc + tid] : cta * rpc + tid];
+        if (tid < 2) mp.bal_sum[tid] = 0;
+        if (tid < 8) mp.cls_cnt[tid] = 0;
+        mp.t_tr[tid] = 0; mp.t_rl[tid] = 0; mp.t_sub[tid] = 0;
+        __syncthreads();
+        if (row_here) atomicAdd(&mp.bal_sum[0], my_nnz);
+        __syncthreads();
+        int target = max(1, (mp.bal_sum[0] + LM4_THREADS - 1) / LM4_THREADS);
+        int my_t = 0;
+        for (int round = 0; round < 40; ++round) {              // block-uniform loop: every thread sees the same sums
+            my_t = 0;
+            if (row_here) {
+                const int want = (my_nnz + target - 1) / target;
+                my_t = 1;
+                while (my_t < want && my_t < 32) my_t <<= 1;
+            }
+            __syncthreads();
+            if (tid == 0) mp.bal_sum[1] = 0;
+            __syncthreads();
+            if (my_t) atomicAdd(&mp.bal_sum[1], my_t);
+            __syncthreads();
+            if (mp.bal_sum[1] <= LM4_THREADS) break;
+            target = target + (target >> 2) + 1;
+        }
+        const int cls = my_t ? 31 - __clz(my_t) : 7;            // 0..5; 7 = no row
+        mp.row_cls[tid] = (unsigned char)cls;
+        if (my_t) atomicAdd(&mp.cls_cnt[cls], 1);
+        __syncthreads();
+        if (tid == 0) { int acc = 0; for (int c = 5; c >= 0; --c) { mp.cls_start[c] = acc; acc += mp.cls_cnt[c] << c; } }
+        __syncthreads();
+        if (my_t) {
+            int rank = 0;                                       // rows of my class with a smaller slot index
+            for (int j = 0; j < tid; ++j) rank += mp.row_cls[j] == cls;
+            const int first = mp.cls_start[cls] + (rank << cls);
+            for (int l = 0; l < my_t; ++l) { mp.t_rl[first + l] = (unsigned short)tid; mp.t_sub[first + l] = (unsigned char)l; mp.t_tr[first + l] = (unsigned char)my_t; }
+        }
+        __syncthreads();
+    }
+}
+
 template <int NCTA>
 struct Lm5Smem {
     double wpart[LM4_THREADS / 32][NCTA];
@@ -696,9 +758,10 @@ __device__ __forceinline__ void cluster_sum5(Lm5Smem<NCTA> &sm, Lm5Sync &sy, int
 // mat-vec, per SM); the cluster shape is a launch attribute.
 template <int NCTA, bool merged>
 __global__ void __launch_bounds__(LM4_THREADS, 1)
-solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_iters, int lin_iters, double *stats, int ent_cap, int balanced)
+solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_iters, int lin_iters, double *stats, int ent_cap, int balanced, int only_if_flag)
 {
     DF_PDL_ENTRY();
+    if (only_if_flag && ws.flags[1] == 0) return;               // launched behind v6 as its fallback: v6 solved the frame (cluster-uniform)
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ Lm5Smem<NCTA> sm;
     extern __shared__ __align__(16) unsigned char dyn[];
@@ -715,62 +778,10 @@ solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
     // most of the columns they touch are the CTA's own rows and a row's search-direction entry is needed by few other CTAs.
     const int *order = grid ? nodegrid_order(grid) : nullptr;
     const int *slot = grid ? nodegrid_slot(grid) : nullptr;
-    // Lanes per row in proportion to the row's length (round 2).  With a fixed 4 lanes per row the mat-vec of a step took as long as the
-    // CTA's longest row (rim rows: 60-100 entries against a median of 20) while most lanes had 5 entries; a row now gets
-    // 1, 2, 4, ... 32 consecutive lanes ~ nnz / target, target = the smallest entries-per-lane for which the CTA's rows fit its 512
-    // lanes.  Groups are laid out longest first, so every group is aligned to its size and never straddles a warp; the position of a
-    // row depends on its rank among the rows of its class only (deterministic: the order in which rows enter the sums is fixed).
-    __shared__ unsigned short t_rl[LM4_THREADS];
-    __shared__ unsigned char t_sub[LM4_THREADS], t_tr[LM4_THREADS];
-    __shared__ unsigned char row_cls[LM4_THREADS];
-    __shared__ int cls_cnt[8], cls_start[8], bal_sum[2];
-    if (!balanced) {                                           // DF_SOLVE_BALANCED=0: the fixed power-of-two lanes per row of round 1
-        const int r = tid / L.tpr;
-        t_rl[tid] = (unsigned short)r; t_sub[tid] = (unsigned char)(tid % L.tpr); t_tr[tid] = (unsigned char)(r < rpc ? L.tpr : 0);
-        __syncthreads();
-    } else {
-        int my_nnz = 0;
-        const bool row_here = tid < rpc && cta * rpc + tid < M;
-        if (row_here) my_nnz = ws.rownnz[order ? order[cta * rpc + tid] : cta * rpc + tid];
-        if (tid < 2) bal_sum[tid] = 0;
-        if (tid < 8) cls_cnt[tid] = 0;
-        t_tr[tid] = 0; t_rl[tid] = 0; t_sub[tid] = 0;
-        __syncthreads();
-        if (row_here) atomicAdd(&bal_sum[0], my_nnz);
-        __syncthreads();
-        int target = max(1, (bal_sum[0] + LM4_THREADS - 1) / LM4_THREADS);
-        int my_t = 0;
-        for (int round = 0; round < 40; ++round) {              // block-uniform loop: every thread sees the same sums
-            my_t = 0;
-            if (row_here) {
-                const int want = (my_nnz + target - 1) / target;
-                my_t = 1;
-                while (my_t < want && my_t < 32) my_t <<= 1;
-            }
-            __syncthreads();
-            if (tid == 0) bal_sum[1] = 0;
-            __syncthreads();
-            if (my_t) atomicAdd(&bal_sum[1], my_t);
-            __syncthreads();
-            if (bal_sum[1] <= LM4_THREADS) break;
-            target = target + (target >> 2) + 1;
-        }
-        const int cls = my_t ? 31 - __clz(my_t) : 7;            // 0..5; 7 = no row
-        row_cls[tid] = (unsigned char)cls;
-        if (my_t) atomicAdd(&cls_cnt[cls], 1);
-        __syncthreads();
-        if (tid == 0) { int acc = 0; for (int c = 5; c >= 0; --c) { cls_start[c] = acc; acc += cls_cnt[c] << c; } }
-        __syncthreads();
-        if (my_t) {
-            int rank = 0;                                       // rows of my class with a smaller slot index
-            for (int j = 0; j < tid; ++j) rank += row_cls[j] == cls;
-            const int first = cls_start[cls] + (rank << cls);
-            for (int l = 0; l < my_t; ++l) { t_rl[first + l] = (unsigned short)tid; t_sub[first + l] = (unsigned char)l; t_tr[first + l] = (unsigned char)my_t; }
-        }
-        __syncthreads();
-    }
-    const int tpr = t_tr[tid];                                 // lanes serving this thread's row (0: idle lane)
-    const int rl = tpr ? (int)t_rl[tid] : rpc, sub = t_sub[tid];
+    __shared__ LmRowMap mp;
+    lm_map_rows(mp, ws, order, cta, rpc, L.tpr, M, balanced);
+    const int tpr = mp.t_tr[tid];                              // lanes serving this thread's row (0: idle lane)
+    const int rl = tpr ? (int)mp.t_rl[tid] : rpc, sub = mp.t_sub[tid];
     const int wtpr = __reduce_min_sync(0xffffffffu, tpr ? tpr : 32);   // the warp's smallest group: owner lanes sit at multiples of it
     const int wmax = __reduce_max_sync(0xffffffffu, tpr);             // ... and its largest: the row sums need log2(wmax) shuffle steps
     const int s_row = cta * rpc + rl;                          // slot of this thread's row
@@ -1019,9 +1030,488 @@ solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// v6 (round 2, default): ONE DSMEM exchange per PCG step.
+//
+// clock64 accounting of v5 (tools/build_variant.py lmprof, profiles/r02_s2_c02_lmprof.log) on a 251-step solve: a step costs 7.4 k cycles
+// and the two mbarrier waits are only ~1.1 k of them; the rest is issue/latency inside the CTA -- the gather of the mat-vec (2.2 k:
+// random 24-byte reads of shared memory, bank conflicts), four cluster-wide sums with three shuffle trees each (3.4 k) and the
+// per-row st.async loop of the vector exchange (1.0 k).  A CTA's step is a serial chain on 4 warps per scheduler; what shortens it is
+// fewer links, not faster links:
+//   * Chronopoulos-Gear form of the preconditioned CG step: with u = M r and w = (A + C) u the step needs only gamma = r.u and
+//     delta = w.u (beta = gamma/gamma', alpha = gamma / (delta - beta gamma / alpha'), p = u + beta p, s = w + beta s, x += alpha p,
+//     r -= alpha s): TWO sums per step instead of four, formed in one exchange, and the same iterates as the textbook step in exact
+//     arithmetic (the model value Q for the q-tolerance follows from Q' = Q - alpha gamma / 2 as before);
+//   * the exchange of the multiplied vector rides on the same exchange: a row's owner sends w_j to the CTAs that multiply by column j
+//     TOGETHER with its CTA's partial sums; every CTA keeps (r_j, s_j, 1/M_jj) of its halo columns and, once alpha and beta are
+//     known, advances them with the very operations the owner applies -- bit-identical replicas, no second round trip;
+//   * the sends come from a flat (row, destination) list walked by all 512 threads (no predicated loop over 16 CTAs per owner lane).
+// A step is: mat-vec -> partial sums + halo sends -> ONE wait -> scalars -> update of own + halo rows -> block barrier.
+// Set-up finds a CTA's halo (bitmap of the columns its rows touch), ranks it, and lets every owner look up its rows' positions in the
+// destination CTAs' halos through DSMEM loads; both sides verify the other's view (A is structurally symmetric), and a system whose
+// halo or send list does not fit -- or any mismatch -- raises ws.flags[1] and leaves the solve to v5 (launched right behind, a no-op
+// otherwise).
+constexpr int LM6_HALO = 512;      // halo columns per CTA (one per thread)
+constexpr int LM6_SEND = 1536;     // (row, destination) pairs per CTA
+constexpr int LM6_BITW = 128;      // bitmap words: M <= 4096
+
+struct Lm6Layout {
+    int rpc, tpr, ent_cap;
+    size_t off_svec, off_win, off_hr, off_hs, off_hdiag, off_hmi, off_hj, off_wown, off_need, off_srl, off_sdst, off_sbar, off_val, off_col, total;
+};
+
+__host__ __device__ inline Lm6Layout lm6_layout(int M, int ent_cap, int ncta)
+{
+    Lm6Layout L;
+    L.rpc = (M + ncta - 1) / ncta;
+    L.tpr = 1;
+    while (L.tpr < 32 && L.tpr * 2 * L.rpc <= LM4_THREADS) L.tpr *= 2;
+    L.ent_cap = ent_cap;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { const size_t at = o; o += (bytes + 15) & ~(size_t)15; return at; };
+    L.off_svec = take((size_t)3 * M * 8);
+    L.off_win = take((size_t)2 * LM6_HALO * 3 * 8);
+    L.off_hr = take((size_t)LM6_HALO * 3 * 8);
+    L.off_hs = take((size_t)LM6_HALO * 3 * 8);
+    L.off_hdiag = take((size_t)LM6_HALO * 8);
+    L.off_hmi = take((size_t)LM6_HALO * 8);
+    L.off_hj = take((size_t)LM6_HALO * 4);
+    L.off_wown = take((size_t)L.rpc * 3 * 8);
+    L.off_need = take((size_t)L.rpc * 4);
+    L.off_srl = take((size_t)LM6_SEND * 2);
+    L.off_sdst = take((size_t)LM6_SEND * 4);
+    L.off_sbar = take((size_t)LM6_SEND * 4);
+    L.off_val = take((size_t)ent_cap * LM4_THREADS * 8);
+    L.off_col = take((size_t)ent_cap * LM4_THREADS * 2);
+    L.total = o;
+    return L;
+}
+
+template <int NCTA>
+struct Lm6Smem {
+    double wpart[LM4_THREADS / 32][4];
+    double red_in[2][NCTA][4];
+    unsigned long long bar[2];
+    unsigned refbits[LM6_BITW];      // columns this CTA's rows touch, then: its halo (columns owned by other CTAs)
+    int haloprefix[LM6_BITW];        // halo columns below word w
+    int scan[LM4_THREADS / 32 + 1];
+    int H, nsend, bad;
+};
+
+struct Lm6Sync { int parity; uint32_t phase[2]; };
+
+struct Lm6Ctx {
+    int cta, H, nsend;
+    const double *wown;
+    const unsigned short *send_rl;
+    const uint32_t *send_dst, *send_bar;
+};
+
+__device__ __forceinline__ uint32_t ld_cluster_u32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+// One exchange: cluster-wide sums of v[0..NV) (every thread of every CTA ends up with bit-identical totals: fixed trees) and, with
+// kHalo, the three doubles the owner lanes put into wown[] go to the halos that hold their rows (w_in[parity] over there).
+// Returns the parity (= which w_in / red_in buffer the data of this exchange sits in).  Buffers and barriers alternate: a CTA can be
+// one exchange ahead of another, never two (its next wait needs everybody's partial sums of this one).
+template <int NCTA, int NV, bool kHalo>
+__device__ __forceinline__ int lm6_exchange(Lm6Smem<NCTA> &sm, Lm6Sync &sy, const Lm6Ctx &cx, double (&v)[NV], int wtpr)
+{
+    static_assert(NV >= 1 && NV <= 4, "partial-sum slots");
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int par = sy.parity;
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+        for (int o = 16; o >= wtpr; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) sm.wpart[warp][k] = v[k];
+    }
+    __syncthreads();                                           // wpart and wown are complete
+    const uint32_t bar = smem_u32(&sm.bar[par]);
+    if (warp == 0) {
+        const uint32_t rbar = mapa_u32(bar, (uint32_t)(lane & (NCTA - 1)));
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double t = lane < LM4_THREADS / 32 ? sm.wpart[lane][k] : 0.0;
+            for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (lane < NCTA) st_async_f64(mapa_u32(smem_u32(&sm.red_in[par][cx.cta][k]), (uint32_t)lane), t, rbar);   // lane = destination CTA
+        }
+    }
+    if (kHalo) {
+        const uint32_t dpar = par ? (uint32_t)(LM6_HALO * 24) : 0u, bpar = par ? 8u : 0u;
+        for (int i = tid; i < cx.nsend; i += LM4_THREADS) {
+            const double *src = cx.wown + 3 * (int)cx.send_rl[i];
+            const uint32_t dst = cx.send_dst[i] + dpar, rb = cx.send_bar[i] + bpar;
+            st_async_f64(dst, src[0], rb); st_async_f64(dst + 8u, src[1], rb); st_async_f64(dst + 16u, src[2], rb);
+        }
+    }
+    if (tid == 0) mbar_arrive_expect(bar, (uint32_t)(NCTA * NV * 8 + (kHalo ? 24 * cx.H : 0)));
+    mbar_wait(bar, sy.phase[par]);
+    sy.phase[par] ^= 1u;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double t = sm.red_in[par][lane & (NCTA - 1)][k];
+#pragma unroll
+        for (int o = NCTA / 2; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        v[k] = t;
+    }
+    sy.parity = par ^ 1;
+    return par;
+}
+
+template <int NCTA>
+__global__ void __launch_bounds__(LM4_THREADS, 1)
+solve_lm_v6_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_iters, int lin_iters, double *stats, int ent_cap, int balanced)
+{
+    DF_PDL_ENTRY();
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ Lm6Smem<NCTA> sm;
+    __shared__ LmRowMap mp;
+    extern __shared__ __align__(16) unsigned char dyn[];
+    const Lm6Layout L = lm6_layout(M, ent_cap, NCTA);
+    double *svec = reinterpret_cast<double *>(dyn + L.off_svec);          // the multiplied vector, [3 * node + axis]: own rows + halo columns
+    double *w_in = reinterpret_cast<double *>(dyn + L.off_win);           // [parity][halo slot][3]: what the owners sent
+    double *hr = reinterpret_cast<double *>(dyn + L.off_hr);              // replicas of the halo columns' residual ...
+    double *hs = reinterpret_cast<double *>(dyn + L.off_hs);              // ... and A-conjugate direction
+    double *hdiag = reinterpret_cast<double *>(dyn + L.off_hdiag);
+    double *hmi = reinterpret_cast<double *>(dyn + L.off_hmi);
+    int *hj = reinterpret_cast<int *>(dyn + L.off_hj);                    // halo slot -> node index
+    double *wown = reinterpret_cast<double *>(dyn + L.off_wown);          // [local row][3]: what this CTA's rows send
+    unsigned *needmask = reinterpret_cast<unsigned *>(dyn + L.off_need);  // [local row]: CTAs whose rows couple to it
+    unsigned short *send_rl = reinterpret_cast<unsigned short *>(dyn + L.off_srl);
+    uint32_t *send_dst = reinterpret_cast<uint32_t *>(dyn + L.off_sdst);
+    uint32_t *send_bar = reinterpret_cast<uint32_t *>(dyn + L.off_sbar);
+    double *mval = reinterpret_cast<double *>(dyn + L.off_val);           // [entry][thread]
+    unsigned short *mcol = reinterpret_cast<unsigned short *>(dyn + L.off_col);   // 3 * column
+    const int rpc = L.rpc;
+
+    Lm6Sync sy; sy.parity = 0; sy.phase[0] = sy.phase[1] = 0u;
+    const int cta = (int)cluster.block_rank();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int *order = grid ? nodegrid_order(grid) : nullptr;
+    const int *slot = grid ? nodegrid_slot(grid) : nullptr;
+    if (tid == 0) {
+        mbar_init(smem_u32(&sm.bar[0]), 1u); mbar_init(smem_u32(&sm.bar[1]), 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        sm.bad = 0;
+    }
+    for (int w = tid; w < LM6_BITW; w += LM4_THREADS) sm.refbits[w] = 0u;
+    for (int r = tid; r < rpc; r += LM4_THREADS) needmask[r] = 0u;
+    const bool force_fallback = (balanced & 2) != 0;            // DF_SOLVE_V6_FORCE_FALLBACK (tests): behave as if the set-up had not fitted
+    lm_map_rows(mp, ws, order, cta, rpc, L.tpr, M, balanced & 1);   // (ends with a block barrier)
+    const int tpr = mp.t_tr[tid];
+    const int rl = tpr ? (int)mp.t_rl[tid] : rpc, sub = mp.t_sub[tid];
+    const int wtpr = __reduce_min_sync(0xffffffffu, tpr ? tpr : 32);
+    const int wmax = __reduce_max_sync(0xffffffffu, tpr);
+    const int s_row = cta * rpc + rl;
+    const bool has_row = rl < rpc && s_row < M;
+    const int n = has_row ? (order ? order[s_row] : s_row) : 0;
+    const bool owner = has_row && sub == 0;
+
+    const int nnz = has_row ? ws.rownnz[n] : 0;
+    int my_ent = 0;
+    unsigned need = 0u;
+    for (int e = sub; e < nnz; e += max(tpr, 1)) {
+        const int j = ws.col[(size_t)e * M + n];
+        need |= 1u << ((slot ? slot[j] : j) / rpc);
+        atomicOr(&sm.refbits[j >> 5], 1u << (j & 31));
+        if (my_ent < ent_cap) {
+            mcol[my_ent * LM4_THREADS + tid] = (unsigned short)(3 * j);
+            mval[my_ent * LM4_THREADS + tid] = ws.val[(size_t)e * M + n];
+            ++my_ent;
+        }
+    }
+    for (int o = wmax >> 1; o > 0; o >>= 1) { const unsigned t = __shfl_xor_sync(0xffffffffu, need, o); if (o < tpr) need |= t; }
+    need &= ~(1u << cta);                                      // remote CTAs only
+    if (owner) needmask[rl] = need;
+    const int e_rest = sub + my_ent * tpr;
+    const double diag_n = has_row ? ws.diag[n] : 0.0;
+    double gb0 = 0.0, gb1 = 0.0, gb2 = 0.0;
+    if (owner) { gb0 = ws.gb[n]; gb1 = ws.gb[M + n]; gb2 = ws.gb[2 * M + n]; }
+    __syncthreads();
+
+    // ---- the halo: touched columns that belong to other CTAs, ranked by node index
+    const int words = (M + 31) >> 5;
+    int hcount = 0;
+    if (tid < words) {
+        unsigned bits = sm.refbits[tid];
+        for (unsigned m = bits; m; m &= m - 1u) {
+            const int j = 32 * tid + (__ffs(m) - 1);
+            if (((slot ? slot[j] : j) / rpc) == cta) bits &= ~(1u << (j & 31));
+        }
+        sm.refbits[tid] = bits;
+        hcount = __popc(bits);
+    }
+    {   // exclusive prefix of hcount over the first `words` threads (words <= 128: four warps)
+        int inc = hcount;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) sm.scan[warp] = inc;
+        __syncthreads();
+        if (tid == 0) { int acc = 0; for (int w = 0; w < LM4_THREADS / 32; ++w) { const int c = sm.scan[w]; sm.scan[w] = acc; acc += c; } sm.scan[LM4_THREADS / 32] = acc; }
+        __syncthreads();
+        const int excl = sm.scan[warp] + inc - hcount;
+        if (tid < words) sm.haloprefix[tid] = excl;
+        if (tid == 0) { sm.H = sm.scan[LM4_THREADS / 32]; if (sm.H > LM6_HALO) sm.bad = 1; }
+        if (tid < words) {
+            int h = excl;
+            for (unsigned m = sm.refbits[tid]; m; m &= m - 1u, ++h) {
+                const int j = 32 * tid + (__ffs(m) - 1);
+                if (h < LM6_HALO) { hj[h] = j; hdiag[h] = ws.diag[j]; }
+            }
+        }
+    }
+    cluster.sync();                                            // barriers initialised, halo tables and need masks readable by the peers
+    const int H = min(sm.H, LM6_HALO);
+
+    // ---- the send list: for every row and every remote CTA that multiplies by it, where its values go over there
+    const int ndst = owner ? __popc(need) : 0;
+    int send_at = 0, nsend = 0;
+    {
+        int inc = ndst;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) sm.scan[warp] = inc;
+        __syncthreads();
+        if (tid == 0) { int acc = 0; for (int w = 0; w < LM4_THREADS / 32; ++w) { const int c = sm.scan[w]; sm.scan[w] = acc; acc += c; } sm.scan[LM4_THREADS / 32] = acc; }
+        __syncthreads();
+        send_at = sm.scan[warp] + inc - ndst;
+        nsend = sm.scan[LM4_THREADS / 32];
+    }
+    bool bad = nsend > LM6_SEND || force_fallback;
+    if (owner && !bad) {
+        int at = send_at;
+        for (unsigned m = need; m; m &= m - 1u, ++at) {
+            const uint32_t c = (uint32_t)(__ffs(m) - 1);
+            const uint32_t bits = ld_cluster_u32(mapa_u32(smem_u32(&sm.refbits[n >> 5]), c));
+            const uint32_t pre = ld_cluster_u32(mapa_u32(smem_u32(&sm.haloprefix[n >> 5]), c));
+            if (!((bits >> (n & 31)) & 1u)) bad = true;         // the peer does not list this row: structure not symmetric
+            const uint32_t h = pre + (uint32_t)__popc(bits & ((1u << (n & 31)) - 1u));
+            send_rl[at] = (unsigned short)rl;
+            send_dst[at] = mapa_u32(smem_u32(w_in + 3 * min(h, (uint32_t)(LM6_HALO - 1))), c);
+            send_bar[at] = mapa_u32(smem_u32(&sm.bar[0]), c);
+        }
+    }
+    // ... and the other direction: every halo column's owner must list this CTA
+    for (int h = tid; h < H; h += LM4_THREADS) {
+        const int sl = slot ? slot[hj[h]] : hj[h];
+        const uint32_t o = (uint32_t)(sl / rpc);
+        const uint32_t nm = ld_cluster_u32(mapa_u32(smem_u32(&needmask[sl - (int)o * rpc]), o));
+        if (!((nm >> cta) & 1u)) bad = true;
+    }
+    if (bad) sm.bad = 1;                                       // benign race: everybody writes 1
+    __syncthreads();
+    Lm6Ctx cx; cx.cta = cta; cx.H = H; cx.nsend = min(nsend, LM6_SEND); cx.wown = wown; cx.send_rl = send_rl; cx.send_dst = send_dst; cx.send_bar = send_bar;
+
+    // first exchange: does the set-up hold everywhere?  (+ the constant part of the cost, the row count, the non-zero count)
+    const int T = NCTA * LM4_THREADS, gt = cta * LM4_THREADS + tid;
+    double c0n[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i = gt; i < ws.prepare_blocks * (PREPARE_THREADS / 32); i += T) { c0n[0] += ws.c0_partials[2 * i]; c0n[1] += ws.c0_partials[2 * i + 1]; }
+    c0n[2] = (owner ? (double)nnz : 0.0);
+    c0n[3] = (tid == 0 && sm.bad) ? 1.0 : 0.0;
+    lm6_exchange<NCTA, 4, false>(sm, sy, cx, c0n, 1);
+    const double nvalid = c0n[1], nnz_total = c0n[2];
+    const bool overflow = ws.flags[0] != 0;                    // a row overflowed (solve_rows): the stored system is truncated -> leave the field
+    if (c0n[3] > 0.0) {                                        // cluster-uniform: hand the frame to v5
+        if (gt == 0) ws.flags[1] = 1;
+        cluster.sync();
+        return;
+    }
+    int hmax_i = 0;
+    {
+        double hm[1] = {0.0};
+        // max over the CTAs through a sum of one-hot-free values is not available: report this CTA's halo from CTA 0 and the total
+        hm[0] = tid == 0 ? (double)H : 0.0;
+        lm6_exchange<NCTA, 1, false>(sm, sy, cx, hm, 1);
+        hmax_i = (int)hm[0];                                   // total halo columns of the cluster
+    }
+
+    auto spmv = [&](double &o0, double &o1, double &o2) {      // (A * svec)[row], valid in the owner lane
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll 4
+        for (int k = 0; k < my_ent; ++k) {
+            const double *sv = svec + mcol[k * LM4_THREADS + tid];
+            const double a = mval[k * LM4_THREADS + tid];
+            a0 += a * sv[0]; a1 += a * sv[1]; a2 += a * sv[2];
+        }
+        for (int e = e_rest; e < nnz; e += max(tpr, 1)) {
+            const double *sv = svec + 3 * __ldg(ws.col + (size_t)e * M + n);
+            const double a = __ldg(ws.val + (size_t)e * M + n);
+            a0 += a * sv[0]; a1 += a * sv[1]; a2 += a * sv[2];
+        }
+        for (int o = wmax >> 1; o > 0; o >>= 1) {
+            const double b0 = __shfl_xor_sync(0xffffffffu, a0, o), b1 = __shfl_xor_sync(0xffffffffu, a1, o), b2 = __shfl_xor_sync(0xffffffffu, a2, o);
+            if (o < tpr) { a0 += b0; a1 += b1; a2 += b2; }
+        }
+        o0 = a0; o1 = a1; o2 = a2;
+    };
+
+    // x0 = current node translations (CombinedSolver.h:165-172)
+    double x0 = 0.0, x1 = 0.0, x2 = 0.0;
+    if (owner) {
+        const float4 *n4 = reinterpret_cast<const float4 *>(nodes + (size_t)n * DF_NODE_STRIDE);
+        const float4 a = n4[0], b = n4[1], c = n4[2];
+        const Quat t = dq_translation(Quat{a.w, b.x, b.y, b.z}, Quat{b.w, c.x, c.y, c.z});
+        x0 = t.x; x1 = t.y; x2 = t.z;
+    }
+    double cost = 0.0, cost0 = 0.0;
+    double radius = 1e4, decrease = 2.0;                       // solverGPUGaussNewton.t:26-39
+    int it = 0, pcg_total = 0;
+    if (overflow) nl_iters = 0;                                // unchanged (not even re-encoded), stats[5] says so
+    for (; it < nl_iters; ++it) {
+        // svec <- x (own rows directly, halo columns from their owners)
+        if (owner) { wown[3 * rl] = x0; wown[3 * rl + 1] = x1; wown[3 * rl + 2] = x2; svec[3 * n] = x0; svec[3 * n + 1] = x1; svec[3 * n + 2] = x2; }
+        {
+            double z[1] = {0.0};
+            const int par = lm6_exchange<NCTA, 1, true>(sm, sy, cx, z, 1);
+            for (int h = tid; h < H; h += LM4_THREADS) {
+                const double *wi = w_in + (par * LM6_HALO + h) * 3;
+                double *sv = svec + 3 * hj[h];
+                sv[0] = wi[0]; sv[1] = wi[1]; sv[2] = wi[2];
+            }
+        }
+        __syncthreads();
+        double Ap0, Ap1, Ap2;
+        spmv(Ap0, Ap1, Ap2);
+        double cdn = 0.0, mi = 0.0;
+        double g0 = 0.0, g1 = 0.0, g2 = 0.0, dl0 = 0.0, dl1 = 0.0, dl2 = 0.0, r0 = 0.0, r1 = 0.0, r2 = 0.0, p0 = 0.0, p1 = 0.0, p2 = 0.0;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, u0 = 0.0, u1 = 0.0, u2 = 0.0;
+        double t0[1] = {0.0};
+        if (owner) {
+            cdn = fmin(fmax(diag_n, 1e-6), 1e32) / radius;
+            mi = 1.0 / (diag_n + cdn);
+            g0 = gb0 - Ap0; g1 = gb1 - Ap1; g2 = gb2 - Ap2;
+            r0 = g0; r1 = g1; r2 = g2;
+            u0 = g0 * mi; u1 = g1 * mi; u2 = g2 * mi;
+            t0[0] += x0 * (0.5 * Ap0 - gb0);
+            t0[0] += x1 * (0.5 * Ap1 - gb1);
+            t0[0] += x2 * (0.5 * Ap2 - gb2);
+            wown[3 * rl] = g0; wown[3 * rl + 1] = g1; wown[3 * rl + 2] = g2;
+        }
+        {   // gradient -> the halos (replicas start as r = g, s = 0, u = M g); everybody finished reading svec (x) when this completes
+            const int par = lm6_exchange<NCTA, 1, true>(sm, sy, cx, t0, wtpr);
+            if (it == 0) { cost = c0n[0] + t0[0]; cost0 = cost; }
+            if (owner) { svec[3 * n] = u0; svec[3 * n + 1] = u1; svec[3 * n + 2] = u2; }
+            for (int h = tid; h < H; h += LM4_THREADS) {
+                const double *wi = w_in + (par * LM6_HALO + h) * 3;
+                const double d = hdiag[h];
+                const double m = 1.0 / (d + fmin(fmax(d, 1e-6), 1e32) / radius);
+                hmi[h] = m;
+                double *sv = svec + 3 * hj[h];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { const double gj = wi[c]; hr[3 * h + c] = gj; hs[3 * h + c] = 0.0; sv[c] = gj * m; }
+            }
+        }
+        __syncthreads();
+        double Q0 = 0.0, gamma_prev = 0.0, alpha_prev = 0.0;
+        for (int l = 0; l < lin_iters; ++l) {
+            spmv(Ap0, Ap1, Ap2);                               // svec holds u = M r
+            double v[2] = {0.0, 0.0};
+            double w0 = 0.0, w1 = 0.0, w2 = 0.0;
+            if (owner) {
+                w0 = Ap0 + cdn * u0; w1 = Ap1 + cdn * u1; w2 = Ap2 + cdn * u2;
+                v[0] += r0 * u0; v[0] += r1 * u1; v[0] += r2 * u2;
+                v[1] += w0 * u0; v[1] += w1 * u1; v[1] += w2 * u2;
+                wown[3 * rl] = w0; wown[3 * rl + 1] = w1; wown[3 * rl + 2] = w2;
+            }
+            const int par = lm6_exchange<NCTA, 2, true>(sm, sy, cx, v, wtpr);
+            const double gamma = v[0], delta = v[1];
+            if (!(gamma > 0.0)) break;
+            const double beta = l == 0 ? 0.0 : gamma / gamma_prev;
+            const double pap = l == 0 ? delta : delta - beta * gamma / alpha_prev;   // p.(A + C)p of the textbook step
+            if (!(pap > 0.0)) break;
+            const double alpha = gamma / pap;
+            if (owner) {
+                p0 = u0 + beta * p0; s0 = w0 + beta * s0; dl0 = dl0 + alpha * p0; r0 = r0 - alpha * s0; u0 = r0 * mi;
+                p1 = u1 + beta * p1; s1 = w1 + beta * s1; dl1 = dl1 + alpha * p1; r1 = r1 - alpha * s1; u1 = r1 * mi;
+                p2 = u2 + beta * p2; s2 = w2 + beta * s2; dl2 = dl2 + alpha * p2; r2 = r2 - alpha * s2; u2 = r2 * mi;
+                svec[3 * n] = u0; svec[3 * n + 1] = u1; svec[3 * n + 2] = u2;
+            }
+            for (int h = tid; h < H; h += LM4_THREADS) {       // the same operations on the replicas of the halo columns
+                const double *wi = w_in + (par * LM6_HALO + h) * 3;
+                const double m = hmi[h];
+                double *sv = svec + 3 * hj[h];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const double sj = wi[c] + beta * hs[3 * h + c];
+                    const double rj = hr[3 * h + c] - alpha * sj;
+                    hs[3 * h + c] = sj; hr[3 * h + c] = rj; sv[c] = rj * m;
+                }
+            }
+            const double Q1 = Q0 - 0.5 * alpha * gamma;
+            gamma_prev = gamma; alpha_prev = alpha;
+            ++pcg_total;
+            const double zeta = (double)(l + 1) * (Q1 - Q0) / Q1;   // Ceres/Opt q-tolerance, solverGPUGaussNewton.t:1093-1101
+            Q0 = Q1;
+            __syncthreads();                                   // svec (own + halo) is complete
+            if (zeta < 1e-4) break;
+        }
+        // model change = 0.5 dl.(g + r + C dl);  A dl = g - r - C dl  => new cost = cost - dl.g + 0.5 dl.(A dl)
+        double mad[3] = {0.0, 0.0, 0.0};
+        if (owner) {
+            double c;
+            c = cdn * dl0; mad[0] += dl0 * (g0 + r0 + c); mad[1] += dl0 * (g0 - r0 - c); mad[2] += dl0 * g0;
+            c = cdn * dl1; mad[0] += dl1 * (g1 + r1 + c); mad[1] += dl1 * (g1 - r1 - c); mad[2] += dl1 * g1;
+            c = cdn * dl2; mad[0] += dl2 * (g2 + r2 + c); mad[1] += dl2 * (g2 - r2 - c); mad[2] += dl2 * g2;
+        }
+        lm6_exchange<NCTA, 3, false>(sm, sy, cx, mad, wtpr);
+        const double model = 0.5 * mad[0];
+        const double new_cost = cost - mad[2] + 0.5 * mad[1];
+        const double change = cost - new_cost;
+        const double rho = model > 0.0 ? change / model : 0.0;
+        bool stop = false;
+        if (change >= 0.0 && rho > 1e-3) {
+            if (owner) { x0 += dl0; x1 += dl1; x2 += dl2; }
+            stop = change <= cost * 1e-6;                       // function_tolerance, CombinedSolver.h:88
+            cost = new_cost;
+            const double f = 1.0 - (2.0 * rho - 1.0) * (2.0 * rho - 1.0) * (2.0 * rho - 1.0);
+            radius /= fmax(f, 1.0 / 3.0);
+            radius = fmin(radius, 1e16);
+            decrease = 2.0;
+        } else {
+            radius /= decrease; decrease *= 2.0;
+            if (radius <= 1e-32) stop = true;
+        }
+        if (stop) { ++it; break; }
+    }
+    if (nl_iters == 0 || overflow) {                           // the cost of the unchanged field, as v5 reports it
+        if (owner) { wown[3 * rl] = x0; wown[3 * rl + 1] = x1; wown[3 * rl + 2] = x2; svec[3 * n] = x0; svec[3 * n + 1] = x1; svec[3 * n + 2] = x2; }
+        double z[1] = {0.0};
+        const int par = lm6_exchange<NCTA, 1, true>(sm, sy, cx, z, 1);
+        for (int h = tid; h < H; h += LM4_THREADS) {
+            const double *wi = w_in + (par * LM6_HALO + h) * 3;
+            double *sv = svec + 3 * hj[h];
+            sv[0] = wi[0]; sv[1] = wi[1]; sv[2] = wi[2];
+        }
+        __syncthreads();
+        double Ap0, Ap1, Ap2;
+        spmv(Ap0, Ap1, Ap2);
+        double t0[1] = {0.0};
+        if (owner) { t0[0] += x0 * (0.5 * Ap0 - gb0); t0[0] += x1 * (0.5 * Ap1 - gb1); t0[0] += x2 * (0.5 * Ap2 - gb2); }
+        lm6_exchange<NCTA, 1, false>(sm, sy, cx, t0, wtpr);
+        cost = c0n[0] + t0[0]; cost0 = cost;
+    }
+    cluster.sync();                                            // no CTA may exit while others can still write into its shared memory
+    // write back: encodeTranslation (CombinedSolver.h:189-197, dual_quaternion.hpp:82-85)
+    if (owner && !overflow) {
+        float *nd = nodes + (size_t)n * DF_NODE_STRIDE;
+        const Quat rot = {nd[3], nd[4], nd[5], nd[6]};
+        const Quat h = qhalf(Quat{0.f, (float)x0, (float)x1, (float)x2});
+        const Quat d = qmul(h, rot);
+        nd[7] = d.w; nd[8] = d.x; nd[9] = d.y; nd[10] = d.z;
+    }
+    if (gt == 0 && stats) {
+        stats[0] = cost0; stats[1] = cost; stats[2] = (double)it; stats[3] = nvalid; stats[4] = (double)pcg_total; stats[5] = (double)ws.flags[0];
+        stats[6] = nnz_total; stats[7] = (double)hmax_i;
+    }
+}
+
 int solve_lm_impl()           // DF_SOLVE_LM_IMPL=1 forces the one-block fallback kernel (tests)
 {
-    static const int impl = [] { const char *e = getenv("DF_SOLVE_LM_IMPL"); return e ? atoi(e) : 5; }();
+    static const int impl = [] { const char *e = getenv("DF_SOLVE_LM_IMPL"); return e ? atoi(e) : 6; }();
     return impl;
 }
 
@@ -1070,32 +1560,51 @@ int dfb::solve_data_term_ev(float *nodes, int M, const void *node_grid, const fl
     launch_pdl(solve_rows_kernel, dim3(M), dim3(ROWS_THREADS), 0, s, ws, M, N, flags & DF_SOLVE_REF_GRAPH_QUIRK, lpt);
     DF_LAUNCH_CHECK();
     if (before_lm && cudaEventRecord(before_lm, s) != cudaSuccess) return (int)cudaGetLastError();
-    // v5 on one cluster when the system fits its shared memory (16 CTAs = the non-portable maximum: half the rows, hence half the
-    // mat-vec gather traffic, per SM; DF_SOLVE_LM_CTAS=8 selects the portable size); otherwise the one-block kernel (matrix in L2).
+    // One cluster when the system fits its shared memory (16 CTAs = the non-portable maximum: half the rows, hence half the mat-vec
+    // gather traffic, per SM; DF_SOLVE_LM_CTAS=8 selects the portable size); otherwise the one-block kernel (matrix in L2).
+    // DF_SOLVE_LM_IMPL: 6 (default) = v6 with v5 launched behind it as its fallback, 5 = v5 alone, 1 = the one-block kernel.
     static const int want = [] { const char *e = getenv("DF_SOLVE_LM_CTAS"); return e ? atoi(e) : 16; }();
     const int ncta = (want == 16 && M >= 256) ? 16 : 8;
-    const Lm4Layout Lb = lm4_layout(M, 0, ncta);
-    const size_t budget = ncta == 16 ? (size_t)216 * 1024 : (size_t)220 * 1024;      // 227 KB minus the static shared memory (8.6 KB with 16 CTAs, 4.6 KB with 8)
-    if (solve_lm_impl() >= 5 && Lb.rpc * Lb.tpr <= LM4_THREADS && Lb.total + (size_t)LM4_THREADS * 10 * 8 <= budget) {
-        const int cap = (int)((budget - Lb.total - 16) / ((size_t)LM4_THREADS * 10));
-        const Lm4Layout Lc = lm4_layout(M, cap, ncta);
-        static const int merged = [] { const char *e = getenv("DF_SOLVE_MERGED"); return e ? atoi(e) : 1; }();
-        using KernelT = void (*)(float *, int, const void *, SolveWs, int, int, double *, int, int);
-        static const int balanced = [] { const char *e = getenv("DF_SOLVE_BALANCED"); return e ? atoi(e) : 1; }();
-        const KernelT kern = ncta == 16 ? (merged ? (KernelT)solve_lm_v5_kernel<16, true> : (KernelT)solve_lm_v5_kernel<16, false>)
-                                        : (merged ? (KernelT)solve_lm_v5_kernel<8, true> : (KernelT)solve_lm_v5_kernel<8, false>);
+    static const int balanced = [] { const char *e = getenv("DF_SOLVE_BALANCED"); return e ? atoi(e) : 1; }();
+    auto launch_cluster = [&](auto kern, size_t smem, auto... args) -> cudaError_t {
         // function attributes are per device: set them on every launch (cheap) rather than once per process
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ncta == 16 ? 216 * 1024 : 220 * 1024);
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (ncta == 16) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(ncta); cfg.blockDim = dim3(LM4_THREADS); cfg.dynamicSmemBytes = Lc.total; cfg.stream = s;
+        cfg.gridDim = dim3(ncta); cfg.blockDim = dim3(LM4_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
         cudaLaunchAttribute at[2];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = ncta; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[1].val.programmaticStreamSerializationAllowed = pdl_enabled();
         cfg.attrs = at; cfg.numAttrs = 2;
-        const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, nodes, M, node_grid, ws, nonlinear_iters, linear_iters, stats_dev, cap, balanced);
+        return cudaLaunchKernelEx(&cfg, kern, args...);
+    };
+    const Lm4Layout Lb = lm4_layout(M, 0, ncta);
+    const size_t budget = ncta == 16 ? (size_t)216 * 1024 : (size_t)220 * 1024;      // 227 KB minus the static shared memory (8.6 KB with 16 CTAs, 4.6 KB with 8)
+    if (solve_lm_impl() >= 5 && Lb.rpc * Lb.tpr <= LM4_THREADS && Lb.total + (size_t)LM4_THREADS * 10 * 8 <= budget) {
+        bool v6 = false;
+        if (solve_lm_impl() >= 6 && M <= 32 * LM6_BITW) {
+            const Lm6Layout L6 = lm6_layout(M, 0, ncta);
+            const size_t budget6 = (size_t)220 * 1024;                                  // 227 KB minus v6's static shared memory (5.5 KB)
+            if (L6.total + (size_t)LM4_THREADS * 10 * 6 <= budget6) {                   // room for at least 6 entries per lane
+                const int cap6 = (int)((budget6 - L6.total - 32) / ((size_t)LM4_THREADS * 10));
+                const Lm6Layout Lc6 = lm6_layout(M, cap6, ncta);
+                using K6 = void (*)(float *, int, const void *, SolveWs, int, int, double *, int, int);
+                const K6 k6 = ncta == 16 ? (K6)solve_lm_v6_kernel<16> : (K6)solve_lm_v6_kernel<8>;
+                static const int force_fb = [] { const char *e = getenv("DF_SOLVE_V6_FORCE_FALLBACK"); return e ? atoi(e) : 0; }();
+                const cudaError_t le = launch_cluster(k6, Lc6.total, nodes, M, node_grid, ws, nonlinear_iters, linear_iters, stats_dev, cap6, balanced | (force_fb ? 2 : 0));
+                if (le != cudaSuccess) return (int)le;
+                v6 = true;
+            }
+        }
+        const int cap = (int)((budget - Lb.total - 16) / ((size_t)LM4_THREADS * 10));
+        const Lm4Layout Lc = lm4_layout(M, cap, ncta);
+        static const int merged = [] { const char *e = getenv("DF_SOLVE_MERGED"); return e ? atoi(e) : 1; }();
+        using KernelT = void (*)(float *, int, const void *, SolveWs, int, int, double *, int, int, int);
+        const KernelT kern = ncta == 16 ? (merged ? (KernelT)solve_lm_v5_kernel<16, true> : (KernelT)solve_lm_v5_kernel<16, false>)
+                                        : (merged ? (KernelT)solve_lm_v5_kernel<8, true> : (KernelT)solve_lm_v5_kernel<8, false>);
+        const cudaError_t le = launch_cluster(kern, Lc.total, nodes, M, node_grid, ws, nonlinear_iters, linear_iters, stats_dev, cap, balanced, v6 ? 1 : 0);
         if (le != cudaSuccess) return (int)le;
     } else {
         solve_lm_kernel<<<1, LM_THREADS, 0, s>>>(nodes, M, ws, nonlinear_iters, linear_iters, stats_dev);
