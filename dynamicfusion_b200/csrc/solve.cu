@@ -31,6 +31,8 @@ namespace {
 constexpr int HCAP = 1024;      // hash slots per node row
 constexpr int ROWCAP = 512;     // stored nonzeros per row (ELL stride); overflow is reported in stats[5]
 constexpr int LM_THREADS = 1024;
+constexpr int TILE_W = 16, TILE_H = 8, TILE_PIX = TILE_W * TILE_H;   // image tile of the tile-record assembly
+constexpr int TILE_LCAP = 64;   // distinct nodes a tile's records hold; a tile with more hands the frame to the per-entry kernels
 
 struct SolveWs {
     int *idx; float *w; float4 *b;                 // per vertex
@@ -44,6 +46,11 @@ struct SolveWs {
     int *row_order;                                // [M] node index per solve_rows block: heaviest incidence lists first
     int *blockcnt;                                 // [M][prepare_blocks]: entries of node n contributed by vertex block b, then their exclusive prefix over b
     int prepare_blocks;
+    // tile records of the image-shaped assembly (solve_tiles / solve_rows_tiles): NT = N / 128 tiles of 16 x 8 pixels, 0 = not available
+    int ntiles;
+    int *rec_L, *rec_nodes;                        // [NT], [NT][TILE_LCAP]: the tile's distinct nodes, ascending
+    double *rec_T, *rec_g;                         // [NT][TILE_LCAP][TILE_LCAP], [NT][TILE_LCAP][4]: sum over the tile's vertices of w_a w_b, w_a b
+    unsigned char *touch;                          // [M][NT]: 1 + local index of node n in tile t, 0 = the tile does not hold it
 };
 
 size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -72,6 +79,12 @@ size_t layout(SolveWs &ws, char *base, int M, int N)
     ws.flags = (int *)take(64);
     ws.row_order = (int *)take((size_t)M * 4);
     ws.blockcnt = (int *)take((size_t)M * ws.prepare_blocks * 4);
+    ws.ntiles = N % TILE_PIX == 0 ? N / TILE_PIX : 0;
+    ws.rec_L = (int *)take((size_t)ws.ntiles * 4);
+    ws.rec_nodes = (int *)take((size_t)ws.ntiles * TILE_LCAP * 4);
+    ws.rec_T = (double *)take((size_t)ws.ntiles * TILE_LCAP * TILE_LCAP * 8);
+    ws.rec_g = (double *)take((size_t)ws.ntiles * TILE_LCAP * 4 * 8);
+    ws.touch = (unsigned char *)take((size_t)M * ws.ntiles);
     return o;
 }
 
@@ -145,7 +158,7 @@ __global__ void __launch_bounds__(1024) solve_scan_kernel(SolveWs ws, int M)
     int run = partial[t] - s;
     for (int i = b; i < e; ++i) { ws.off[i] = run; run += ws.cnt[i]; ws.cursor[i] = 0; }
     if (t == 1023) ws.off[M] = partial[1023];
-    if (t == 0) { ws.flags[0] = 0; ws.flags[1] = 0; }          // [0] row overflow, [1] v6 handed the frame to v5
+    if (t == 0) { ws.flags[0] = 0; ws.flags[1] = 0; ws.flags[2] = 0; ws.flags[3] = 0; }   // [0] row overflow, [1] v6 handed the frame to v5, [2] the tile assembly handed it to fill + rows, [3] the tile assembly ran
     // Launch order of solve_rows: one block per node, and the rim nodes' lists are 100x the median -- scheduled last they are the
     // kernel's tail.  Longest-processing-time-first: nodes grouped by floor(log2(count)), heaviest group first (the order inside a
     // group is whatever the shared-memory atomics give: it affects only WHEN a row is assembled, never its value).
@@ -186,9 +199,10 @@ __global__ void __launch_bounds__(256) solve_blockscan_kernel(SolveWs ws, int M)
 // entry's position is a pure function of the data.  (A first version sorted the block's 2,048 (node, entry) pairs with a bitonic
 // network: 132 us per frame; this one: see profiles/r02_*launches*.)
 constexpr int FILL_HASH = 1024;                                    // >= distinct nodes a block of 256 vertices can touch (<= 2,048 entries; typically ~30)
-__global__ void __launch_bounds__(256) solve_fill_kernel(SolveWs ws, int N)
+__global__ void __launch_bounds__(256) solve_fill_kernel(SolveWs ws, int N, int only_if_flag)
 {
     DF_PDL_ENTRY();
+    if (only_if_flag && ws.flags[2] == 0) return;                  // launched behind the tile assembly as its fallback: nothing to do
     __shared__ int hkey[FILL_HASH], hcur[FILL_HASH];
     __shared__ int overflow;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -266,9 +280,10 @@ __device__ __forceinline__ int rows_find_slot(const int *keys, int j)
     return 0;
 }
 
-__global__ void __launch_bounds__(ROWS_THREADS) solve_rows_kernel(SolveWs ws, int M, int N, int quirk, int lpt)
+__global__ void __launch_bounds__(ROWS_THREADS) solve_rows_kernel(SolveWs ws, int M, int N, int quirk, int lpt, int only_if_flag)
 {
     DF_PDL_ENTRY();
+    if (only_if_flag && ws.flags[2] == 0) return;
     __shared__ int keys[HCAP];
     __shared__ int slot_rank[HCAP];
     __shared__ int list[HCAP];
@@ -407,6 +422,242 @@ __global__ void __launch_bounds__(ROWS_THREADS) solve_rows_kernel(SolveWs ws, in
         for (int q = 0; q < ROWS_WARPS; ++q) { a += red[0][q]; b += red[1][q]; c += red[2][q]; }
         ws.gb[i] = a; ws.gb[M + i] = b; ws.gb[2 * M + i] = c;
         if (end == beg && !quirk_row) ws.diag[i] = 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Tile-record assembly (round 2, second session; default when the vertices are an image, DF_SOLVE_IMAGE_COLS in the flags).
+//
+// solve_fill + solve_rows above assemble A = W^T W entry by entry: every vertex is visited once per neighbour (8 x), each visit pushes 8
+// products through match.any + shuffle groups into the node's hash -- 12 M contributions per frame, 0.28 ms, the largest kernels after the
+// LM solve.  But the 128 pixels of a 16 x 8 image tile see the same dozen nodes (measured on the bench sequence: 16 distinct nodes on
+// average, 42 at most), so the tile's contribution to A is a small DENSE block T = W_t^T W_t over its L local nodes.  One 128-thread
+// block per tile builds the tile's node table (hash, ranked by node index: local indices are a function of the data), scatters its
+// weights into a 128 x L shared-memory matrix and lets warp w form rows a = w, w+4, ... of T with lane = column: only the vertices that
+// hold node a are visited (bit masks from ballots, in pixel order), products of two floats are exact in double, sums run in a fixed
+// order.  The row of the normal matrix for node i is then the sum of row local(i) of the ~12 tiles that hold it (a byte map touch[i][tile]
+// written by the tiles), accumulated by 8 warps in private shared-memory slots and combined in warp order: no atomics on values, bit-
+// reproducible, and ~40 x fewer operations than the per-entry path.  Tiles with more than TILE_LCAP nodes or rows with more than
+// RT_HCAP * 3/4 columns raise ws.flags[2] and the per-entry kernels (launched right behind, no-ops otherwise) redo the frame.
+constexpr int TW_STRIDE = TILE_LCAP + 1;     // row stride of the tile's weight matrix (floats): odd -> scattered writes hit distinct banks
+constexpr int TILE_HASH = 256;
+
+__global__ void __launch_bounds__(TILE_PIX) solve_tiles_kernel(SolveWs ws, int cols, int rows)
+{
+    DF_PDL_ENTRY();
+    __shared__ float wloc[TILE_PIX * TW_STRIDE];
+    __shared__ float bvec[TILE_PIX][3];
+    __shared__ unsigned long long vmask[TILE_PIX];
+    __shared__ unsigned amask[TILE_LCAP][TILE_PIX / 32];
+    __shared__ int hkey[TILE_HASH], hval[TILE_HASH];
+    __shared__ int list[TILE_HASH];
+    __shared__ int sorted[TILE_LCAP];
+    __shared__ int nl;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tiles_x = cols / TILE_W;
+    const int tile = blockIdx.x, tx = tile % tiles_x, ty = tile / tiles_x;
+    const int px = tx * TILE_W + (tid % TILE_W), py = ty * TILE_H + (tid / TILE_W);
+    const int v = py * cols + px;
+    const float4 b = ws.b[v];
+    const bool valid = b.w != 0.f;
+    if (blockIdx.x == 0 && tid == 0) ws.flags[3] = 1;
+    if (!__syncthreads_or(valid)) { if (tid == 0) ws.rec_L[tile] = 0; return; }
+    int nk[8]; float wk[8];
+    {
+        const int4 ia = *reinterpret_cast<const int4 *>(ws.idx + (size_t)v * 8), ib = *reinterpret_cast<const int4 *>(ws.idx + (size_t)v * 8 + 4);
+        const float4 wa = *reinterpret_cast<const float4 *>(ws.w + (size_t)v * 8), wb = *reinterpret_cast<const float4 *>(ws.w + (size_t)v * 8 + 4);
+        nk[0] = ia.x; nk[1] = ia.y; nk[2] = ia.z; nk[3] = ia.w; nk[4] = ib.x; nk[5] = ib.y; nk[6] = ib.z; nk[7] = ib.w;
+        wk[0] = wa.x; wk[1] = wa.y; wk[2] = wa.z; wk[3] = wa.w; wk[4] = wb.x; wk[5] = wb.y; wk[6] = wb.z; wk[7] = wb.w;
+    }
+    for (int s = tid; s < TILE_HASH; s += TILE_PIX) hkey[s] = -1;
+    if (tid == 0) nl = 0;
+    __syncthreads();
+    // ---- the tile's node set
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int j = valid ? nk[k] : -1;
+        const unsigned grp = __match_any_sync(0xffffffffu, j);
+        if (j < 0 || lane != __ffs(grp) - 1) continue;
+        unsigned slot = ((unsigned)j * 2654435761u) & (TILE_HASH - 1);
+        for (int probe = 0; probe < TILE_HASH; ++probe) {
+            const int prev = atomicCAS(&hkey[slot], -1, j);
+            if (prev == -1 || prev == j) break;
+            slot = (slot + 1) & (TILE_HASH - 1);
+        }
+    }
+    __syncthreads();
+    for (int s = tid; s < TILE_HASH; s += TILE_PIX)
+        if (hkey[s] >= 0) list[atomicAdd(&nl, 1)] = s;
+    __syncthreads();
+    const int L = nl;
+    if (L > TILE_LCAP) { if (tid == 0) { ws.flags[2] = 1; ws.rec_L[tile] = 0; } return; }   // (<= 1,024 distinct nodes fit the hash: 128 x 8 entries)
+    if (tid < L) {                                             // local index = rank of the node index
+        const int sa = list[tid], ka = hkey[sa];
+        int rank = 0;
+        for (int q = 0; q < L; ++q) rank += hkey[list[q]] < ka;
+        hval[sa] = rank;
+        sorted[rank] = ka;
+    }
+    for (int e = tid; e < TILE_PIX * TW_STRIDE; e += TILE_PIX) wloc[e] = 0.f;
+    __syncthreads();
+    // ---- scatter: weights into the vertex's row, the vertex into its nodes' masks
+    unsigned long long vm = 0ull;
+    if (valid) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int j = nk[k];
+            if (j < 0) continue;
+            unsigned slot = ((unsigned)j * 2654435761u) & (TILE_HASH - 1);
+            while (hkey[slot] != j) slot = (slot + 1) & (TILE_HASH - 1);
+            const int a = hval[slot];
+            wloc[tid * TW_STRIDE + a] = wk[k];
+            vm |= 1ull << a;
+        }
+    }
+    vmask[tid] = vm;
+    bvec[tid][0] = b.x; bvec[tid][1] = b.y; bvec[tid][2] = b.z;
+    for (int a = 0; a < L; ++a) {
+        const unsigned m = __ballot_sync(0xffffffffu, (vm >> a) & 1ull);
+        if (lane == 0) amask[a][warp] = m;
+    }
+    __syncthreads();
+    // ---- rows of T: warp w takes local rows w, w + 4, ...; lane = column (and column + 32)
+    const bool two = L > 32;
+    for (int a = warp; a < L; a += TILE_PIX / 32) {
+        double t0 = 0.0, t1 = 0.0, g = 0.0;
+        for (int w4 = 0; w4 < TILE_PIX / 32; ++w4) {
+            for (unsigned m = amask[a][w4]; m; m &= m - 1u) {
+                const int u = w4 * 32 + (__ffs(m) - 1);
+                const float *row = wloc + u * TW_STRIDE;
+                const double wa = (double)row[a];
+                t0 += wa * (double)row[lane];
+                if (two) t1 += wa * (double)row[lane + 32];
+                if (lane < 3) g += wa * (double)bvec[u][lane];
+            }
+        }
+        double *T = ws.rec_T + ((size_t)tile * TILE_LCAP + a) * TILE_LCAP;
+        if (lane < L) T[lane] = t0;
+        if (lane + 32 < L) T[lane + 32] = t1;
+        if (lane < 3) ws.rec_g[((size_t)tile * TILE_LCAP + a) * 4 + lane] = g;
+        if (lane == 0) ws.touch[(size_t)sorted[a] * ws.ntiles + tile] = (unsigned char)(a + 1);
+    }
+    if (tid < L) ws.rec_nodes[(size_t)tile * TILE_LCAP + tid] = sorted[tid];
+    if (tid == 0) ws.rec_L[tile] = L;
+}
+
+constexpr int RT_THREADS = 256;
+constexpr int RT_WARPS = RT_THREADS / 32;
+constexpr int RT_HCAP = 256;                 // hash slots per row; rows with more than 3/4 of them in use go to the per-entry kernels
+constexpr int RT_LIST = 4096;                // tiles per node kept in shared memory; longer lists are re-read from the byte map
+
+__global__ void __launch_bounds__(RT_THREADS) solve_rows_tiles_kernel(SolveWs ws, int M, int N, int quirk, int lpt)
+{
+    DF_PDL_ENTRY();
+    __shared__ int keys[RT_HCAP];
+    __shared__ int slot_rank[RT_HCAP];
+    __shared__ int occ[RT_HCAP];
+    __shared__ double priv[RT_WARPS][RT_HCAP];
+    __shared__ double gpart[RT_WARPS][3];
+    __shared__ int tlist[RT_LIST];                      // (tile << 6) | local index
+    __shared__ int wsum[RT_WARPS + 1];
+    __shared__ int nocc, skip;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) skip = ws.flags[2];                    // a tile (or an earlier row) overflowed: fill + rows behind this kernel take the frame
+    __syncthreads();                                     // (one reader: other blocks may raise the flag while this one starts)
+    if (skip) return;
+    const int i = lpt ? ws.row_order[blockIdx.x] : (int)blockIdx.x;
+    const int NT = ws.ntiles;
+    for (int s = tid; s < RT_HCAP; s += RT_THREADS) keys[s] = -1;
+    for (int s = tid; s < RT_WARPS * RT_HCAP; s += RT_THREADS) (&priv[0][0])[s] = 0.0;
+    if (tid == 0) nocc = 0;
+    // ---- the tiles that hold node i, in tile order (thread t owns a contiguous stretch of the byte map)
+    const unsigned char *trow = ws.touch + (size_t)i * NT;
+    const int per = (NT + RT_THREADS - 1) / RT_THREADS;
+    const int t_beg = min(NT, tid * per), t_end = min(NT, t_beg + per);
+    int mine = 0;
+    for (int t = t_beg; t < t_end; ++t) mine += trow[t] != 0;
+    int inc = mine;
+    for (int o = 1; o < 32; o <<= 1) { const int x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (tid == 0) { int acc = 0; for (int w = 0; w < RT_WARPS; ++w) { const int c = wsum[w]; wsum[w] = acc; acc += c; } wsum[RT_WARPS] = acc; }
+    __syncthreads();
+    const int ntl = wsum[RT_WARPS];
+    if (ntl > RT_LIST) { if (tid == 0) ws.flags[2] = 1; return; }
+    {
+        int at = wsum[warp] + inc - mine;
+        for (int t = t_beg; t < t_end; ++t) { const int l = trow[t]; if (l) tlist[at++] = (t << 6) | (l - 1); }
+    }
+    __syncthreads();
+    // ---- accumulate: warp w takes list entries w, w + 8, ... (tile order); lane = column of the tile's block
+    double g = 0.0;
+    bool over = false;
+    for (int e = warp; e < ntl; e += RT_WARPS) {
+        const int tile = tlist[e] >> 6, a = tlist[e] & 63;
+        const int L = ws.rec_L[tile];
+        const double *T = ws.rec_T + ((size_t)tile * TILE_LCAP + a) * TILE_LCAP;
+        const int *nd = ws.rec_nodes + (size_t)tile * TILE_LCAP;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int c = lane + 32 * h;
+            if (c >= L) continue;
+            const double val = T[c];
+            if (val == 0.0) continue;                      // the two nodes share no vertex of this tile (or a weight underflowed: a zero entry)
+            const int j = nd[c];
+            unsigned slot = ((unsigned)j * 2654435761u) & (RT_HCAP - 1);
+            int probe = 0;
+            for (; probe < RT_HCAP; ++probe) {
+                const int prev = atomicCAS(&keys[slot], -1, j);
+                if (prev == -1 || prev == j) break;
+                slot = (slot + 1) & (RT_HCAP - 1);
+            }
+            if (probe == RT_HCAP) { over = true; continue; }
+            priv[warp][slot] += val;                       // the lanes of one step hold distinct columns: no conflict
+        }
+        if (lane < 3) g += ws.rec_g[((size_t)tile * TILE_LCAP + a) * 4 + lane];
+        __syncwarp();
+    }
+    if (lane < 3) gpart[warp][lane] = g;
+    const bool quirk_row = quirk && i == 0 && N > 0 && ws.b[0].w != 0.f;
+    __syncthreads();
+    if (quirk_row && tid == 0) {                          // CombinedSolver.h:70-79: N extra edges on (node 0, node 0)
+        double sw = 0.0;
+        for (int k = 0; k < 8; ++k) sw += (double)ws.w[k];
+        unsigned slot = 0u;
+        for (int probe = 0; probe < RT_HCAP; ++probe) {
+            const int prev = atomicCAS(&keys[slot], -1, 0);
+            if (prev == -1 || prev == 0) break;
+            slot = (slot + 1) & (RT_HCAP - 1);
+        }
+        priv[0][slot] += (double)N * sw * sw;
+        const float4 b = ws.b[0];
+        gpart[0][0] += (double)N * sw * (double)b.x; gpart[0][1] += (double)N * sw * (double)b.y; gpart[0][2] += (double)N * sw * (double)b.z;
+    }
+    __syncthreads();
+    for (int s = tid; s < RT_HCAP; s += RT_THREADS)
+        if (keys[s] >= 0) occ[atomicAdd(&nocc, 1)] = s;
+    __syncthreads();
+    const int nn = nocc;
+    if (over || nn > RT_HCAP * 3 / 4) ws.flags[2] = 1;    // too many columns for this kernel: the per-entry kernels redo the frame
+    if (tid == 0) ws.diag[i] = 0.0;                       // a row whose own weights all underflowed has no diagonal entry
+    __syncthreads();
+    for (int q = tid; q < nn; q += RT_THREADS) {          // rank by key = position in the sorted row
+        const int sa = occ[q], ka = keys[sa];
+        int rank = 0;
+        for (int r = 0; r < nn; ++r) rank += keys[occ[r]] < ka;
+        double total = 0.0;
+#pragma unroll
+        for (int w = 0; w < RT_WARPS; ++w) total += priv[w][sa];
+        ws.col[(size_t)rank * M + i] = ka;
+        ws.val[(size_t)rank * M + i] = total;
+        if (ka == i) ws.diag[i] = total;
+    }
+    if (tid == 0) {
+        ws.rownnz[i] = nn;
+        double a = 0.0, b = 0.0, c = 0.0;
+        for (int w = 0; w < RT_WARPS; ++w) { a += gpart[w][0]; b += gpart[w][1]; c += gpart[w][2]; }
+        ws.gb[i] = a; ws.gb[M + i] = b; ws.gb[2 * M + i] = c;
+        if (ntl == 0 && !quirk_row) ws.diag[i] = 0.0;
     }
 }
 
@@ -1026,7 +1277,7 @@ solve_lm_v5_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
     }
     if (gt == 0 && stats) {
         stats[0] = cost0; stats[1] = cost; stats[2] = (double)it; stats[3] = nvalid; stats[4] = (double)pcg_total; stats[5] = (double)ws.flags[0];
-        stats[6] = nnz_total;
+        stats[6] = nnz_total; stats[7] = (ws.flags[3] && !ws.flags[2]) ? -0.5 : -1.0;   // < 0: solved by v5; -0.5: matrix from the tile records
     }
 }
 
@@ -1335,7 +1586,7 @@ solve_lm_v6_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
         for (int k = 0; k < my_ent; ++k) {
             const double *sv = svec + mcol[k * LM4_THREADS + tid];
             const double a = mval[k * LM4_THREADS + tid];
-            a0 += a * sv[0]; a1 += a * sv[1]; a2 += a * sv[2];
+            a0 += a * sv[0]; a1 += a * sv[1]; a2 += a * sv[2];   // (contracted multiply-adds measured: no gain, profiles/r02_s2_c04_trace_fma.log)
         }
         for (int e = e_rest; e < nnz; e += max(tpr, 1)) {
             const double *sv = svec + 3 * __ldg(ws.col + (size_t)e * M + n);
@@ -1505,7 +1756,7 @@ solve_lm_v6_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
     }
     if (gt == 0 && stats) {
         stats[0] = cost0; stats[1] = cost; stats[2] = (double)it; stats[3] = nvalid; stats[4] = (double)pcg_total; stats[5] = (double)ws.flags[0];
-        stats[6] = nnz_total; stats[7] = (double)hmax_i;
+        stats[6] = nnz_total; stats[7] = (double)hmax_i + ((ws.flags[3] && !ws.flags[2]) ? 0.5 : 0.0);   // halo columns of the cluster; + 0.5: matrix from the tile records
     }
 }
 
@@ -1548,16 +1799,30 @@ int dfb::solve_data_term_ev(float *nodes, int M, const void *node_grid, const fl
     layout(ws, base, M, N);
     cudaError_t e = cudaMemsetAsync(ws.blockcnt, 0, (size_t)M * ws.prepare_blocks * 4, s);
     if (e != cudaSuccess) return (int)e;
+    if (ws.ntiles > 0 && ((flags >> 8) & 0xffff) > 0) {
+        e = cudaMemsetAsync(ws.touch, 0, (size_t)M * ws.ntiles, s);
+        if (e != cudaSuccess) return (int)e;
+    }
     launch_pdl(solve_prepare_kernel, dim3(ws.prepare_blocks), dim3(256), 0, s, nodes, M, node_grid, canon, live, N, stride, ws);
     DF_LAUNCH_CHECK();
     launch_pdl(solve_blockscan_kernel, dim3(div_up(M, 8)), dim3(256), 0, s, ws, M);
     DF_LAUNCH_CHECK();
     launch_pdl(solve_scan_kernel, dim3(1), dim3(1024), 0, s, ws, M);
     DF_LAUNCH_CHECK();
-    launch_pdl(solve_fill_kernel, dim3(ws.prepare_blocks), dim3(256), 0, s, ws, N);
-    DF_LAUNCH_CHECK();
     static const int lpt = [] { const char *e = getenv("DF_SOLVE_LPT"); return e ? atoi(e) : 1; }();    // A/B: heaviest rows first
-    launch_pdl(solve_rows_kernel, dim3(M), dim3(ROWS_THREADS), 0, s, ws, M, N, flags & DF_SOLVE_REF_GRAPH_QUIRK, lpt);
+    // image-shaped vertices: tile records (DF_SOLVE_TILES=0 disables), with the per-entry kernels behind them as the fallback
+    static const int want_tiles = [] { const char *e = getenv("DF_SOLVE_TILES"); return e ? atoi(e) : 1; }();
+    const int cols = (flags >> 8) & 0xffff;
+    const bool tiles = want_tiles && cols > 0 && ws.ntiles > 0 && N % cols == 0 && cols % TILE_W == 0 && (N / cols) % TILE_H == 0 && M * (size_t)ws.ntiles > 0;
+    if (tiles) {
+        launch_pdl(solve_tiles_kernel, dim3(ws.ntiles), dim3(TILE_PIX), 0, s, ws, cols, N / cols);
+        DF_LAUNCH_CHECK();
+        launch_pdl(solve_rows_tiles_kernel, dim3(M), dim3(RT_THREADS), 0, s, ws, M, N, flags & DF_SOLVE_REF_GRAPH_QUIRK, lpt);
+        DF_LAUNCH_CHECK();
+    }
+    launch_pdl(solve_fill_kernel, dim3(ws.prepare_blocks), dim3(256), 0, s, ws, N, tiles ? 1 : 0);
+    DF_LAUNCH_CHECK();
+    launch_pdl(solve_rows_kernel, dim3(M), dim3(ROWS_THREADS), 0, s, ws, M, N, flags & DF_SOLVE_REF_GRAPH_QUIRK, lpt, tiles ? 1 : 0);
     DF_LAUNCH_CHECK();
     if (before_lm && cudaEventRecord(before_lm, s) != cudaSuccess) return (int)cudaGetLastError();
     // One cluster when the system fits its shared memory (16 CTAs = the non-portable maximum: half the rows, hence half the mat-vec

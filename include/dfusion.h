@@ -258,7 +258,8 @@ int df_integrate_warped(df_volume vol, const uint16_t *depth, size_t depth_pitch
  * -> Opt LM/PCG on kfusion/solvers/dynamicfusion.t: translation-only data term solved on the device; node
  * translations are updated in place (encodeTranslation, CombinedSolver.h:189-197).
  * params: nonlinear (LM) iterations, linear (PCG) iterations; stats_dev (device, 8 doubles): initial cost, final cost,
- * LM iterations run, valid rows, PCG iterations run, row-overflow flag.  If a node's row of the normal matrix couples to more columns
+ * LM iterations run, valid rows, PCG iterations run, row-overflow flag, [6] non-zeros of the normal matrix, [7] diagnostics (>= 0: solved
+ * by the one-exchange cluster kernel, value = halo columns exchanged per PCG step; < 0: by its fallback; fraction .5: matrix assembled from tile records).  If a node's row of the normal matrix couples to more columns
  * than the kernels store (512), the flag is raised and the solve leaves the node translations UNCHANGED (0 LM iterations) rather than
  * solving a truncated, asymmetric system; callers must look at stats[5] (the frame loop reports it through df_kinfu_get_info[11] and on
  * stderr, the C++ mirror prints an error).  workspace from df_solve_workspace_bytes(M, N).
@@ -269,6 +270,10 @@ size_t df_solve_workspace_bytes(int M, int N);
  * k-NN pass (DF_WARP_REUSE_KNN) */
 int df_solve_knn_buffers(void *workspace, int M, int N, int32_t **idx, float **w);
 #define DF_SOLVE_REF_GRAPH_QUIRK 1
+/* flags bits 8..23: the vertices are an image of that many columns (N = cols * rows, row-major, cols % 16 == 0, rows % 8 == 0): lets the
+ * assembly of the normal matrix work tile by tile (16 x 8 pixels share a dozen nodes) instead of entry by entry.  Same result up to the
+ * order of the double sums; 0 (a flat vertex list) always takes the per-entry path. */
+#define DF_SOLVE_IMAGE_COLS(c) (((c) & 0xffff) << 8)
 int df_solve_data_term(float *nodes, int M, const void *node_grid, const float *canon, const float *live, int N, int stride,
                        int nonlinear_iters, int linear_iters, int flags, double *stats_dev, void *workspace, void *stream);
 

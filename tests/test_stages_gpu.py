@@ -367,3 +367,56 @@ def test_alternative_icp_and_solve_kernels_in_subprocess(env):
                        cwd=root, env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " passed" in r.stdout and "failed" not in r.stdout
+
+
+def _image_problem(coherent, cols=256, rows=160, M=600, seed=3):
+    """an image-shaped solve: canonical vertices on a smooth height field (neighbouring pixels see the same nodes) or scattered at random
+    (every tile sees hundreds of nodes: the tile assembly must hand the frame to the per-entry kernels)"""
+    rng = np.random.default_rng(seed)
+    N = cols * rows
+    if coherent:
+        u, v = np.meshgrid(np.linspace(-0.3, 0.3, cols), np.linspace(-0.2, 0.2, rows))
+        pts = np.stack([u, v, 0.05 * np.sin(6 * u) * np.cos(5 * v)], -1).reshape(N, 3)
+        node_pts = pts[rng.choice(N, M, replace=False)].astype(np.float32)
+    else:
+        pts = rng.uniform(-0.3, 0.3, (N, 3))
+        node_pts = rng.uniform(-0.3, 0.3, (M, 3)).astype(np.float32)
+    src = np.zeros((N, 4), np.float32)
+    src[:, :3] = pts
+    dst = src.copy()
+    dst[:, :3] += (0.01 * np.stack([np.sin(5 * src[:, 0]), np.cos(4 * src[:, 1]), src[:, 2]], 1)).astype(np.float32)
+    src[7::50, 1] = np.nan                                      # (vertex 0 stays valid: the graph quirk hangs its extra edges on it)
+    dst[11::77, 2] = np.nan
+    src[40 * cols:48 * cols, 0] = np.nan                        # a band of empty tiles
+    return node_pts, src, dst, cols
+
+
+@pytest.mark.parametrize("coherent", [True, False])
+def test_solve_tile_assembly_matches_per_entry_path_and_oracle(orc, coherent):
+    """DF_SOLVE_IMAGE_COLS: the normal matrix assembled from 16 x 8-pixel tile records (round 2) against the per-entry kernels (same
+    solve from a flat vertex list) and against the matrix-free oracle.  stats[7]'s fraction tells which path built the matrix."""
+    from oracle import orc_pipe
+    node_pts, src, dst, cols = _image_problem(coherent)
+    out = {}
+    for name, flags in (("flat", 0), ("tiles", cols << 8), ("tiles_quirk", (cols << 8) | 1), ("flat_quirk", 1)):
+        wf = host.WarpField()
+        wf.init(node_pts)
+        stats = wf.optimiseWarpData(torch.from_numpy(src).cuda(), torch.from_numpy(dst).cuda(), 5, 100, flags).cpu().numpy()
+        out[name] = (stats, wf.nodes_.cpu().numpy())
+        assert stats[5] == 0
+        used_tiles = abs(stats[7]) % 1 == 0.5
+        assert used_tiles == (coherent and name.startswith("tiles")), (name, stats)
+    for a, b in (("flat", "tiles"), ("flat_quirk", "tiles_quirk")):
+        sa, na = out[a]; sb, nb = out[b]
+        assert sa[3] == sb[3] and sa[2] == sb[2]
+        assert abs(sa[0] - sb[0]) <= 1e-12 * abs(sa[0]) and abs(sa[1] - sb[1]) <= 1e-9 * abs(sa[1])
+        assert sa[6] >= sb[6]                                      # the tile path drops exact-zero products, nothing else
+        t_a, t_b = 2 * na[:, 8:11], 2 * nb[:, 8:11]
+        assert np.abs(t_a - t_b).max() <= 1e-4 * np.abs(t_a).max()
+    nodes_ref = orc.make_nodes(node_pts)
+    ostats = orc_pipe.solve_data_term_big(nodes_ref, src, dst, flags=0, lm_iters=5, lin_iters=100)
+    stats, got = out["tiles"]
+    assert stats[3] == ostats[3]
+    assert abs(stats[0] - ostats[0]) <= 1e-6 * ostats[0] and abs(stats[1] - ostats[1]) <= 1e-4 * ostats[1]
+    t_got, t_ref = 2 * got[:, 8:11], orc.node_translations(nodes_ref)[:, 1:]
+    assert np.abs(t_got - t_ref).max() <= 1e-3 * np.abs(t_ref).max()

@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--pipeline", action="store_true")
     ap.add_argument("--frames", type=int, default=12)
     ap.add_argument("--trace", action="store_true")
+    ap.add_argument("--trace-all", action="store_true", help="with --trace: a line for every frame")
     ap.add_argument("--warped", action="store_true", help="with --pipeline: DF_KINFU_WARPED_INTEGRATE (per-voxel warped fusion, SURVEY 8f(1))")
     ap.add_argument("--weight-scale", type=float, default=100.0)
     ap.add_argument("--hd", action="store_true", help="config C4: 1280x720 depth, volume edge 1.5 m (use with --dim 768)")
@@ -55,10 +56,11 @@ def main():
         for t in range(a.frames):
             d = torch.from_numpy(synth.umbrella_depth(t).view(np.int16).copy()).cuda()
             k(d)
-            if a.trace and (t < 6 or t % 5 == 0):
+            if a.trace and (t < 6 or t % 5 == 0 or a.trace_all):
                 i, sm = k.info(), k.stage_ms()
+                st = [float(v) for v in k.buffer("solve_stats")]
                 print(f"frame {t:3d} lm {i['lm_iters']} pcg {i['pcg_iters']:4d} cloud {i['cloud_points']:7d} n_upd {i['n_updated']:9d} n_warped {i['n_warped']:9d} "
-                      f"solve {sm['solve']:.3f} icp {sm['icp']:.3f} integ {sm['integrate']:.3f} extract {sm['extract']:.3f} total {sum(sm.values()):.3f}", flush=True)
+                      f"solve {sm['solve']:.3f} icp {sm['icp']:.3f} integ {sm['integrate']:.3f} extract {sm['extract']:.3f} total {sum(sm.values()):.3f} nnz {int(st[6])} lm-diag {st[7]}", flush=True)
             if t >= 3:
                 for name, v in k.stage_ms().items():
                     acc[name] = acc.get(name, 0.0) + v
