@@ -80,10 +80,11 @@ size_t layout(SolveWs &ws, char *base, int M, int N)
     ws.row_order = (int *)take((size_t)M * 4);
     ws.blockcnt = (int *)take((size_t)M * ws.prepare_blocks * 4);
     ws.ntiles = N % TILE_PIX == 0 ? N / TILE_PIX : 0;
-    ws.rec_L = (int *)take((size_t)ws.ntiles * 4);
-    ws.rec_nodes = (int *)take((size_t)ws.ntiles * TILE_LCAP * 4);
-    ws.rec_T = (double *)take((size_t)ws.ntiles * TILE_LCAP * TILE_LCAP * 8);
-    ws.rec_g = (double *)take((size_t)ws.ntiles * TILE_LCAP * 4 * 8);
+    const size_t nrec = ws.ntiles ? (size_t)ws.ntiles + 256 * 8 : 0;   // one record per tile + TILE_OV_CAP * TILE_STRIPS strip records
+    ws.rec_L = (int *)take(nrec * 4);
+    ws.rec_nodes = (int *)take(nrec * TILE_LCAP * 4);
+    ws.rec_T = (double *)take(nrec * TILE_LCAP * TILE_LCAP * 8);
+    ws.rec_g = (double *)take(nrec * TILE_LCAP * 4 * 8);
     ws.touch = (unsigned char *)take((size_t)M * ws.ntiles);
     return o;
 }
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(1024) solve_scan_kernel(SolveWs ws, int M)
     int run = partial[t] - s;
     for (int i = b; i < e; ++i) { ws.off[i] = run; run += ws.cnt[i]; ws.cursor[i] = 0; }
     if (t == 1023) ws.off[M] = partial[1023];
-    if (t == 0) { ws.flags[0] = 0; ws.flags[1] = 0; ws.flags[2] = 0; ws.flags[3] = 0; }   // [0] row overflow, [1] v6 handed the frame to v5, [2] the tile assembly handed it to fill + rows, [3] the tile assembly ran
+    if (t == 0) { ws.flags[0] = 0; ws.flags[1] = 0; ws.flags[2] = 0; ws.flags[3] = 0; ws.flags[4] = 0; ws.flags[5] = 0; ws.flags[6] = 0; ws.flags[7] = 0; }   // [0] row overflow, [1] v6 handed the frame to v5, [2] the tile assembly handed it to fill + rows, [3] the tile assembly ran
     // Launch order of solve_rows: one block per node, and the rim nodes' lists are 100x the median -- scheduled last they are the
     // kernel's tail.  Longest-processing-time-first: nodes grouped by floor(log2(count)), heaviest group first (the order inside a
     // group is whatever the shared-memory atomics give: it affects only WHEN a row is assembled, never its value).
@@ -442,17 +443,20 @@ __global__ void __launch_bounds__(ROWS_THREADS) solve_rows_kernel(SolveWs ws, in
 constexpr int TW_STRIDE = TILE_LCAP + 1;     // row stride of the tile's weight matrix (floats): odd -> scattered writes hit distinct banks
 constexpr int TILE_HASH = 256;
 
+constexpr int TILE_STRIPS = TILE_PIX / TILE_W;   // an overflowing tile is redone as its 8 pixel rows, one record each
+constexpr int TILE_OV_CAP = 256;                 // overflowing tiles per frame that get strip records (beyond that: the per-entry kernels)
+constexpr unsigned char TOUCH_STRIPS = 255;      // byte-map code: look the node up in the tile's strip records
+
 __global__ void __launch_bounds__(TILE_PIX) solve_tiles_kernel(SolveWs ws, int cols, int rows)
 {
     DF_PDL_ENTRY();
     __shared__ float wloc[TILE_PIX * TW_STRIDE];
     __shared__ float bvec[TILE_PIX][3];
-    __shared__ unsigned long long vmask[TILE_PIX];
     __shared__ unsigned amask[TILE_LCAP][TILE_PIX / 32];
     __shared__ int hkey[TILE_HASH], hval[TILE_HASH];
     __shared__ int list[TILE_HASH];
     __shared__ int sorted[TILE_LCAP];
-    __shared__ int nl;
+    __shared__ int nl, ov_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tiles_x = cols / TILE_W;
     const int tile = blockIdx.x, tx = tile % tiles_x, ty = tile / tiles_x;
@@ -469,80 +473,106 @@ __global__ void __launch_bounds__(TILE_PIX) solve_tiles_kernel(SolveWs ws, int c
         nk[0] = ia.x; nk[1] = ia.y; nk[2] = ia.z; nk[3] = ia.w; nk[4] = ib.x; nk[5] = ib.y; nk[6] = ib.z; nk[7] = ib.w;
         wk[0] = wa.x; wk[1] = wa.y; wk[2] = wa.z; wk[3] = wa.w; wk[4] = wb.x; wk[5] = wb.y; wk[6] = wb.z; wk[7] = wb.w;
     }
-    for (int s = tid; s < TILE_HASH; s += TILE_PIX) hkey[s] = -1;
-    if (tid == 0) nl = 0;
-    __syncthreads();
-    // ---- the tile's node set
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int j = valid ? nk[k] : -1;
-        const unsigned grp = __match_any_sync(0xffffffffu, j);
-        if (j < 0 || lane != __ffs(grp) - 1) continue;
-        unsigned slot = ((unsigned)j * 2654435761u) & (TILE_HASH - 1);
-        for (int probe = 0; probe < TILE_HASH; ++probe) {
-            const int prev = atomicCAS(&hkey[slot], -1, j);
-            if (prev == -1 || prev == j) break;
-            slot = (slot + 1) & (TILE_HASH - 1);
-        }
-    }
-    __syncthreads();
-    for (int s = tid; s < TILE_HASH; s += TILE_PIX)
-        if (hkey[s] >= 0) list[atomicAdd(&nl, 1)] = s;
-    __syncthreads();
-    const int L = nl;
-    if (L > TILE_LCAP) { if (tid == 0) { ws.flags[2] = 1; ws.rec_L[tile] = 0; } return; }   // (<= 1,024 distinct nodes fit the hash: 128 x 8 entries)
-    if (tid < L) {                                             // local index = rank of the node index
-        const int sa = list[tid], ka = hkey[sa];
-        int rank = 0;
-        for (int q = 0; q < L; ++q) rank += hkey[list[q]] < ka;
-        hval[sa] = rank;
-        sorted[rank] = ka;
-    }
-    for (int e = tid; e < TILE_PIX * TW_STRIDE; e += TILE_PIX) wloc[e] = 0.f;
-    __syncthreads();
-    // ---- scatter: weights into the vertex's row, the vertex into its nodes' masks
-    unsigned long long vm = 0ull;
-    if (valid) {
+    bvec[tid][0] = b.x; bvec[tid][1] = b.y; bvec[tid][2] = b.z;
+
+    // the node set of the member vertices -> nl distinct nodes in hkey / list (block-uniform result)
+    auto build_table = [&](bool member) -> int {
+        __syncthreads();                                           // the previous pass is done with the tables
+        for (int s = tid; s < TILE_HASH; s += TILE_PIX) hkey[s] = -1;
+        if (tid == 0) nl = 0;
+        __syncthreads();
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const int j = nk[k];
-            if (j < 0) continue;
+            const int j = member ? nk[k] : -1;
+            const unsigned grp = __match_any_sync(0xffffffffu, j);
+            if (j < 0 || lane != __ffs(grp) - 1) continue;
             unsigned slot = ((unsigned)j * 2654435761u) & (TILE_HASH - 1);
-            while (hkey[slot] != j) slot = (slot + 1) & (TILE_HASH - 1);
-            const int a = hval[slot];
-            wloc[tid * TW_STRIDE + a] = wk[k];
-            vm |= 1ull << a;
-        }
-    }
-    vmask[tid] = vm;
-    bvec[tid][0] = b.x; bvec[tid][1] = b.y; bvec[tid][2] = b.z;
-    for (int a = 0; a < L; ++a) {
-        const unsigned m = __ballot_sync(0xffffffffu, (vm >> a) & 1ull);
-        if (lane == 0) amask[a][warp] = m;
-    }
-    __syncthreads();
-    // ---- rows of T: warp w takes local rows w, w + 4, ...; lane = column (and column + 32)
-    const bool two = L > 32;
-    for (int a = warp; a < L; a += TILE_PIX / 32) {
-        double t0 = 0.0, t1 = 0.0, g = 0.0;
-        for (int w4 = 0; w4 < TILE_PIX / 32; ++w4) {
-            for (unsigned m = amask[a][w4]; m; m &= m - 1u) {
-                const int u = w4 * 32 + (__ffs(m) - 1);
-                const float *row = wloc + u * TW_STRIDE;
-                const double wa = (double)row[a];
-                t0 += wa * (double)row[lane];
-                if (two) t1 += wa * (double)row[lane + 32];
-                if (lane < 3) g += wa * (double)bvec[u][lane];
+            for (int probe = 0; probe < TILE_HASH; ++probe) {
+                const int prev = atomicCAS(&hkey[slot], -1, j);
+                if (prev == -1 || prev == j) break;
+                slot = (slot + 1) & (TILE_HASH - 1);
             }
         }
-        double *T = ws.rec_T + ((size_t)tile * TILE_LCAP + a) * TILE_LCAP;
-        if (lane < L) T[lane] = t0;
-        if (lane + 32 < L) T[lane + 32] = t1;
-        if (lane < 3) ws.rec_g[((size_t)tile * TILE_LCAP + a) * 4 + lane] = g;
-        if (lane == 0) ws.touch[(size_t)sorted[a] * ws.ntiles + tile] = (unsigned char)(a + 1);
+        __syncthreads();
+        for (int s = tid; s < TILE_HASH; s += TILE_PIX)
+            if (hkey[s] >= 0) list[atomicAdd(&nl, 1)] = s;
+        __syncthreads();
+        return nl;
+    };
+    // the record `rid` of the member vertices (L <= TILE_LCAP distinct nodes in the table)
+    auto emit = [&](bool member, int L, int rid, bool write_touch) {
+        if (tid < L) {                                             // local index = rank of the node index
+            const int sa = list[tid], ka = hkey[sa];
+            int rank = 0;
+            for (int q = 0; q < L; ++q) rank += hkey[list[q]] < ka;
+            hval[sa] = rank;
+            sorted[rank] = ka;
+        }
+        for (int e = tid; e < TILE_PIX * TW_STRIDE; e += TILE_PIX) wloc[e] = 0.f;
+        __syncthreads();
+        // scatter: weights into the vertex's row, the vertex into its nodes' masks
+        unsigned long long vm = 0ull;
+        if (member) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int j = nk[k];
+                if (j < 0) continue;
+                unsigned slot = ((unsigned)j * 2654435761u) & (TILE_HASH - 1);
+                while (hkey[slot] != j) slot = (slot + 1) & (TILE_HASH - 1);
+                const int a = hval[slot];
+                wloc[tid * TW_STRIDE + a] = wk[k];
+                vm |= 1ull << a;
+            }
+        }
+        for (int a = 0; a < L; ++a) {
+            const unsigned m = __ballot_sync(0xffffffffu, (vm >> a) & 1ull);
+            if (lane == 0) amask[a][warp] = m;
+        }
+        __syncthreads();
+        // rows of T: warp w takes local rows w, w + 4, ...; lane = column (and column + 32)
+        const bool two = L > 32;
+        for (int a = warp; a < L; a += TILE_PIX / 32) {
+            double t0 = 0.0, t1 = 0.0, g = 0.0;
+            for (int w4 = 0; w4 < TILE_PIX / 32; ++w4) {
+                for (unsigned m = amask[a][w4]; m; m &= m - 1u) {
+                    const int u = w4 * 32 + (__ffs(m) - 1);
+                    const float *row = wloc + u * TW_STRIDE;
+                    const double wa = (double)row[a];
+                    t0 += wa * (double)row[lane];
+                    if (two) t1 += wa * (double)row[lane + 32];
+                    if (lane < 3) g += wa * (double)bvec[u][lane];
+                }
+            }
+            double *T = ws.rec_T + ((size_t)rid * TILE_LCAP + a) * TILE_LCAP;
+            if (lane < L) T[lane] = t0;
+            if (lane + 32 < L) T[lane + 32] = t1;
+            if (lane < 3) ws.rec_g[((size_t)rid * TILE_LCAP + a) * 4 + lane] = g;
+            if (write_touch && lane == 0) ws.touch[(size_t)sorted[a] * ws.ntiles + tile] = (unsigned char)(a + 1);
+        }
+        if (tid < L) ws.rec_nodes[(size_t)rid * TILE_LCAP + tid] = sorted[tid];
+        if (tid == 0) ws.rec_L[rid] = L;
+    };
+
+    const int L = build_table(valid);
+    if (tid == 0) atomicMax(&ws.flags[4], L);                      // diagnostics (DF_SOLVE_TRACE): the frame's largest tile
+    if (L <= TILE_LCAP) { emit(valid, L, tile, true); return; }
+    // More nodes than a record holds (late in a sequence the warped rim scatters: 88 nodes seen in one tile).  The tile is redone as its
+    // 8 pixel rows, each a record of its own in the overflow pool; the byte map sends the rows kernel there.  A full hash table (the
+    // node set is then incomplete), a strip that still overflows or an exhausted pool hand the frame to the per-entry kernels.
+    if (L >= TILE_HASH - 1) { if (tid == 0) { ws.flags[2] = 1; ws.rec_L[tile] = 0; } return; }
+    if (tid == 0) ov_base = atomicAdd(&ws.flags[7], 1);
+    __syncthreads();
+    const int ov = ov_base;
+    if (ov >= TILE_OV_CAP) { if (tid == 0) { ws.flags[2] = 1; ws.rec_L[tile] = 0; } return; }
+    for (int q = tid; q < L; q += TILE_PIX) ws.touch[(size_t)hkey[list[q]] * ws.ntiles + tile] = TOUCH_STRIPS;
+    if (tid == 0) ws.rec_L[tile] = -(ov + 1);                      // where the tile's strip records start: ntiles + ov * TILE_STRIPS
+    for (int sidx = 0; sidx < TILE_STRIPS; ++sidx) {
+        const bool member = valid && (tid / TILE_W) == sidx;
+        const int Ls = build_table(member);
+        const int rid = ws.ntiles + ov * TILE_STRIPS + sidx;
+        if (Ls > TILE_LCAP) { if (tid == 0) { ws.flags[2] = 1; ws.rec_L[rid] = 0; } continue; }   // (16 vertices x 8 neighbours = 128 possible)
+        emit(member, Ls, rid, false);
     }
-    if (tid < L) ws.rec_nodes[(size_t)tile * TILE_LCAP + tid] = sorted[tid];
-    if (tid == 0) ws.rec_L[tile] = L;
 }
 
 constexpr int RT_THREADS = 256;
@@ -558,7 +588,7 @@ __global__ void __launch_bounds__(RT_THREADS) solve_rows_tiles_kernel(SolveWs ws
     __shared__ int occ[RT_HCAP];
     __shared__ double priv[RT_WARPS][RT_HCAP];
     __shared__ double gpart[RT_WARPS][3];
-    __shared__ int tlist[RT_LIST];                      // (tile << 6) | local index
+    __shared__ int tlist[RT_LIST];                      // (tile << 8) | byte-map code
     __shared__ int wsum[RT_WARPS + 1];
     __shared__ int nocc, skip;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -583,20 +613,19 @@ __global__ void __launch_bounds__(RT_THREADS) solve_rows_tiles_kernel(SolveWs ws
     if (tid == 0) { int acc = 0; for (int w = 0; w < RT_WARPS; ++w) { const int c = wsum[w]; wsum[w] = acc; acc += c; } wsum[RT_WARPS] = acc; }
     __syncthreads();
     const int ntl = wsum[RT_WARPS];
-    if (ntl > RT_LIST) { if (tid == 0) ws.flags[2] = 1; return; }
+    if (tid == 0) atomicMax(&ws.flags[5], ntl);
+    if (ntl > RT_LIST) { if (tid == 0) ws.flags[2] = 2; return; }
     {
         int at = wsum[warp] + inc - mine;
-        for (int t = t_beg; t < t_end; ++t) { const int l = trow[t]; if (l) tlist[at++] = (t << 6) | (l - 1); }
+        for (int t = t_beg; t < t_end; ++t) { const int l = trow[t]; if (l) tlist[at++] = (t << 8) | l; }
     }
     __syncthreads();
     // ---- accumulate: warp w takes list entries w, w + 8, ... (tile order); lane = column of the tile's block
     double g = 0.0;
     bool over = false;
-    for (int e = warp; e < ntl; e += RT_WARPS) {
-        const int tile = tlist[e] >> 6, a = tlist[e] & 63;
-        const int L = ws.rec_L[tile];
-        const double *T = ws.rec_T + ((size_t)tile * TILE_LCAP + a) * TILE_LCAP;
-        const int *nd = ws.rec_nodes + (size_t)tile * TILE_LCAP;
+    auto add_row = [&](int rid, int a, int L) {             // row a of record rid into this warp's slots
+        const double *T = ws.rec_T + ((size_t)rid * TILE_LCAP + a) * TILE_LCAP;
+        const int *nd = ws.rec_nodes + (size_t)rid * TILE_LCAP;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int c = lane + 32 * h;
@@ -614,8 +643,22 @@ __global__ void __launch_bounds__(RT_THREADS) solve_rows_tiles_kernel(SolveWs ws
             if (probe == RT_HCAP) { over = true; continue; }
             priv[warp][slot] += val;                       // the lanes of one step hold distinct columns: no conflict
         }
-        if (lane < 3) g += ws.rec_g[((size_t)tile * TILE_LCAP + a) * 4 + lane];
+        if (lane < 3) g += ws.rec_g[((size_t)rid * TILE_LCAP + a) * 4 + lane];
         __syncwarp();
+    };
+    for (int e = warp; e < ntl; e += RT_WARPS) {
+        const int tile = tlist[e] >> 8, code = tlist[e] & 255;
+        if (code != TOUCH_STRIPS) { add_row(tile, code - 1, ws.rec_L[tile]); continue; }
+        const int first = ws.ntiles + (-ws.rec_L[tile] - 1) * TILE_STRIPS;   // the tile overflowed: its pixel rows are records of their own
+        for (int sidx = 0; sidx < TILE_STRIPS; ++sidx) {
+            const int rid = first + sidx, L = ws.rec_L[rid];
+            const int *nd = ws.rec_nodes + (size_t)rid * TILE_LCAP;
+            const unsigned hit = __ballot_sync(0xffffffffu, (lane < L && nd[lane] == i) || (lane + 32 < L && nd[lane + 32] == i));
+            if (!hit) continue;
+            const int l0 = __ffs(hit) - 1;                  // the lane that saw node i: in column l0 or l0 + 32
+            const int a = __shfl_sync(0xffffffffu, (lane < L && nd[lane] == i) ? lane : lane + 32, l0);
+            add_row(rid, a, L);
+        }
     }
     if (lane < 3) gpart[warp][lane] = g;
     const bool quirk_row = quirk && i == 0 && N > 0 && ws.b[0].w != 0.f;
@@ -638,7 +681,8 @@ __global__ void __launch_bounds__(RT_THREADS) solve_rows_tiles_kernel(SolveWs ws
         if (keys[s] >= 0) occ[atomicAdd(&nocc, 1)] = s;
     __syncthreads();
     const int nn = nocc;
-    if (over || nn > RT_HCAP * 3 / 4) ws.flags[2] = 1;    // too many columns for this kernel: the per-entry kernels redo the frame
+    if (tid == 0) atomicMax(&ws.flags[6], nn);
+    if (over || nn > RT_HCAP * 3 / 4) ws.flags[2] = 3;    // too many columns for this kernel: the per-entry kernels redo the frame
     if (tid == 0) ws.diag[i] = 0.0;                       // a row whose own weights all underflowed has no diagonal entry
     __syncthreads();
     for (int q = tid; q < nn; q += RT_THREADS) {          // rank by key = position in the sorted row
@@ -1754,6 +1798,9 @@ solve_lm_v6_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
         const Quat d = qmul(h, rot);
         nd[7] = d.w; nd[8] = d.x; nd[9] = d.y; nd[10] = d.z;
     }
+    if (gt == 0 && (balanced & 4))                             // DF_SOLVE_TRACE=1
+        printf("solve: tiles ran %d fallback reason %d (1 tile nodes, 2 tile list, 3 row columns) max tile nodes %d overflowing tiles %d max tiles/node %d max row columns %d | halo total %d pcg %d\n",
+               ws.flags[3], ws.flags[2], ws.flags[4], ws.flags[7], ws.flags[5], ws.flags[6], hmax_i, pcg_total);
     if (gt == 0 && stats) {
         stats[0] = cost0; stats[1] = cost; stats[2] = (double)it; stats[3] = nvalid; stats[4] = (double)pcg_total; stats[5] = (double)ws.flags[0];
         stats[6] = nnz_total; stats[7] = (double)hmax_i + ((ws.flags[3] && !ws.flags[2]) ? 0.5 : 0.0);   // halo columns of the cluster; + 0.5: matrix from the tile records
@@ -1857,8 +1904,9 @@ int dfb::solve_data_term_ev(float *nodes, int M, const void *node_grid, const fl
                 const Lm6Layout Lc6 = lm6_layout(M, cap6, ncta);
                 using K6 = void (*)(float *, int, const void *, SolveWs, int, int, double *, int, int);
                 const K6 k6 = ncta == 16 ? (K6)solve_lm_v6_kernel<16> : (K6)solve_lm_v6_kernel<8>;
+                static const int trace = [] { const char *e = getenv("DF_SOLVE_TRACE"); return e ? atoi(e) : 0; }();
                 static const int force_fb = [] { const char *e = getenv("DF_SOLVE_V6_FORCE_FALLBACK"); return e ? atoi(e) : 0; }();
-                const cudaError_t le = launch_cluster(k6, Lc6.total, nodes, M, node_grid, ws, nonlinear_iters, linear_iters, stats_dev, cap6, balanced | (force_fb ? 2 : 0));
+                const cudaError_t le = launch_cluster(k6, Lc6.total, nodes, M, node_grid, ws, nonlinear_iters, linear_iters, stats_dev, cap6, balanced | (force_fb ? 2 : 0) | (trace ? 4 : 0));
                 if (le != cudaSuccess) return (int)le;
                 v6 = true;
             }

@@ -381,6 +381,10 @@ def _image_problem(coherent, cols=256, rows=160, M=600, seed=3):
     else:
         pts = rng.uniform(-0.3, 0.3, (N, 3))
         node_pts = rng.uniform(-0.3, 0.3, (M, 3)).astype(np.float32)
+    if coherent == "band":                                      # every 8th pixel of 16 image rows lands somewhere else: those tiles see ~140 nodes
+        jit = np.zeros(N, bool)                                 # (more than a record holds -> redone as pixel-row records), their strips ~25
+        jit[80 * cols:96 * cols:8] = True
+        pts[jit] += rng.uniform(-0.15, 0.15, (int(jit.sum()), 3))
     src = np.zeros((N, 4), np.float32)
     src[:, :3] = pts
     dst = src.copy()
@@ -391,7 +395,7 @@ def _image_problem(coherent, cols=256, rows=160, M=600, seed=3):
     return node_pts, src, dst, cols
 
 
-@pytest.mark.parametrize("coherent", [True, False])
+@pytest.mark.parametrize("coherent", [True, False, "band"])
 def test_solve_tile_assembly_matches_per_entry_path_and_oracle(orc, coherent):
     """DF_SOLVE_IMAGE_COLS: the normal matrix assembled from 16 x 8-pixel tile records (round 2) against the per-entry kernels (same
     solve from a flat vertex list) and against the matrix-free oracle.  stats[7]'s fraction tells which path built the matrix."""
@@ -405,7 +409,7 @@ def test_solve_tile_assembly_matches_per_entry_path_and_oracle(orc, coherent):
         out[name] = (stats, wf.nodes_.cpu().numpy())
         assert stats[5] == 0
         used_tiles = abs(stats[7]) % 1 == 0.5
-        assert used_tiles == (coherent and name.startswith("tiles")), (name, stats)
+        assert used_tiles == (bool(coherent) and name.startswith("tiles")), (name, stats)
     for a, b in (("flat", "tiles"), ("flat_quirk", "tiles_quirk")):
         sa, na = out[a]; sb, nb = out[b]
         assert sa[3] == sb[3] and sa[2] == sb[2]
