@@ -503,7 +503,7 @@ def main():
                 "ms_per_step": ms_e2e / K, "frame_ms": frame_stats_ms(per_e2e)},
         "gpu_launches": int(info["launches"]) * K,
         "clocks": clocks,
-        "roofline": {"kernel": {"1": "integrate_kernel<4>", "2": "integrate_kernel_v2<4>"}.get(os.environ.get("DF_INTEGRATE_IMPL", "3"), "integrate_kernel_v3"), "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"kernel": {"1": "integrate_kernel<4>", "2": "integrate_kernel_v2<4>", "4": "integrate_kernel_v3<true>"}.get(os.environ.get("DF_INTEGRATE_IMPL", "3"), "integrate_kernel_v3"), "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
                      "traffic_over_algorithmic": (traffic / alg_bytes) if (traffic and alg_bytes) else None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "voxels_written_per_launch": n_upd, "kernel_ms": integ_ms,

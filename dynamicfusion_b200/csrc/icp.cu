@@ -370,7 +370,7 @@ __device__ __forceinline__ void icp_unpack_sums(const double *sums, double (&A)[
 }
 
 // StreamHelper::get (projective_icp.cpp:43-62) + host step :195-209, on the device
-__global__ void __launch_bounds__(256) icp_solve_kernel(const double *partials, int nblocks, float *T, int *ok)
+__global__ void __launch_bounds__(256) icp_solve_kernel(const double *partials, int nblocks, float *T, int *ok, const float *T_src, const int *ok_src)
 {
     __shared__ double sums[27];
     __shared__ __align__(16) double stage[RED_ROWS * 27];
@@ -378,8 +378,9 @@ __global__ void __launch_bounds__(256) icp_solve_kernel(const double *partials, 
     pdl_trigger();
     float Tin[12];                                                       // loaded up front: in flight with the partials
 #pragma unroll
-    for (int i = 0; i < 12; ++i) Tin[i] = T[i];
-    if (*ok == 0) return;
+    for (int i = 0; i < 12; ++i) Tin[i] = T_src[i];
+    if (*ok_src == 0) { if (ok != ok_src && threadIdx.x == 0) *ok = 0; return; }
+    if (ok != ok_src && threadIdx.x == 0) *ok = 1;
     reduce_partials(partials, nblocks, sums, stage);
     if (threadIdx.x != 0) return;
     double A[36], b[6];
@@ -569,6 +570,95 @@ __global__ void __launch_bounds__(NT, 1) icp_persistent_kernel(const IcpPersistP
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Chained variant (round 2, second session; DF_ICP_CHAINED=1, measured and kept opt-in): one launch per ITERATION instead of two.  Every CTA of iteration
+// k first sums the partials of iteration k-1 in the fixed order and solves the same 6 x 6 system on the lanes of warp 0 (the persistent
+// kernel's code: identical arithmetic on identical data in every CTA, nobody broadcasts a pose), then accumulates with the new pose.  What
+// the persistent kernel paid a grid barrier for is a programmatic-dependent-launch boundary here, and the 19 separate solve launches of the
+// two-kernel chain are gone: 19 + 1 launches instead of 38.  Pose, gate and partials are double-buffered by iteration parity (block 0
+// publishes the pose the others are still reading the old copy of).  Measured (profiles/r02_s2_c11_*): 0.270 ms against 0.242 ms for the
+// two-kernel chain -- the same verdict as for the persistent kernel: with the solve as every CTA's prologue its serial latency (plus the
+// 148-way redundant reduction) sits in front of all 148 accumulate blocks, while the one-block solve kernel overlaps its launch with the
+// accumulate blocks' drain.  A launch boundary saved is worth less than that.
+template <bool DEPTH, int NT>
+__global__ void __launch_bounds__(NT, 1) icp_chain_kernel(const IcpParams p, const double *prev_partials, int prev_blocks, const float *T_in, const int *ok_in,
+                                                       float *T_out, int *ok_out)
+{
+    constexpr int NW = NT / 32;
+    __shared__ double smem[NW][27];
+    __shared__ double sums[27];
+    __shared__ __align__(16) double stage[RED_ROWS * 27];
+    __shared__ double sA[36], sL[36], sb[6], sr[6];
+    __shared__ float Ts[12];
+    __shared__ int ok_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    pdl_wait();
+    pdl_trigger();
+    if (tid < 12) Ts[tid] = T_in[tid];
+    if (tid == 0) ok_s = *ok_in;
+    __syncthreads();
+    if (prev_blocks > 0 && ok_s) {                                       // the solve of the previous iteration (block-uniform condition)
+        reduce_partials(prev_partials, prev_blocks, sums, stage);
+        if (warp == 0) {
+            if (lane == 0) {                                            // A (symmetric), b from the 27 sums; the reference's buffer is float
+                int shift = 0;
+                for (int i = 0; i < 6; ++i)
+                    for (int j = i; j < 7; ++j) {
+                        const double value = (double)(float)sums[shift++];
+                        if (j == 6) sb[i] = value; else sA[j * 6 + i] = sA[i * 6 + j] = value;
+                    }
+            }
+            __syncwarp();
+            const int st = chol6_warp(sA, sb, sL, sr);
+            if (lane == 0) {
+                bool good = st == 1;
+                if (st == 2) good = icp_fallback_smem(sA, sb, sr);      // not safely SPD (or NaN): the general path of icp_solve_kernel
+                if (good) icp_compose_pose_smem(sr, Ts);
+                else ok_s = 0;
+            }
+        }
+        __syncthreads();
+    }
+    if (blockIdx.x == 0) {
+        if (tid < 12) T_out[tid] = Ts[tid];
+        if (tid == 0) *ok_out = ok_s;
+    }
+    float acc[27];
+#pragma unroll
+    for (int i = 0; i < 27; ++i) acc[i] = 0.f;
+    if (ok_s) {
+        Aff T;
+        T.r0 = make_float3(Ts[0], Ts[1], Ts[2]); T.r1 = make_float3(Ts[3], Ts[4], Ts[5]); T.r2 = make_float3(Ts[6], Ts[7], Ts[8]);
+        T.t = make_float3(Ts[9], Ts[10], Ts[11]);
+        const int npix = p.cols * p.rows;
+        for (int i = blockIdx.x * NT + tid; i < npix; i += gridDim.x * NT) {
+            const int y = i / p.cols, x = i - y * p.cols;
+            float row[7];
+            if (icp_row<DEPTH>(p, T, x, y, row)) {
+                int k = 0;
+#pragma unroll
+                for (int a = 0; a < 6; ++a)
+#pragma unroll
+                    for (int j = a; j < 7; ++j) acc[k++] += row[a] * row[j];
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 27; ++i) {
+        float v = acc[i];                                               // float warp stage, see icp_accumulate_kernel
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) smem[warp][i] = (double)v;
+    }
+    __syncthreads();
+    if (tid < 27) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) v += smem[w][tid];
+        p.partials[(size_t)blockIdx.x * 27 + tid] = v;
+    }
+}
+
 __global__ void icp_init_kernel(float *T, int *ok)
 {
     if (threadIdx.x < 12) T[threadIdx.x] = (threadIdx.x < 9 && threadIdx.x % 4 == 0) ? 1.f : 0.f;
@@ -698,8 +788,13 @@ int icp_estimate_impl(const float *const *vcurr, const unsigned short *const *dc
         if (le == cudaSuccess) return 0;
         (void)cudaGetLastError();                            // e.g. the device cannot co-schedule the grid: fall through to the per-iteration path
     }
-    icp_init_kernel<<<1, 32, 0, s>>>(T_dev, ok_dev);        // affine = Identity, projective_icp.cpp:175
+    static const int chained = [] { const char *e = getenv("DF_ICP_CHAINED"); return e ? atoi(e) : 0; }();
+    double *const part0 = scratch + 32;
+    float *Tbuf[2] = {reinterpret_cast<float *>(part0 + 2 * ICP_MAX_PARTIAL_BLOCKS * 27), reinterpret_cast<float *>(part0 + 2 * ICP_MAX_PARTIAL_BLOCKS * 27) + 16};
+    int *okbuf[2] = {reinterpret_cast<int *>(Tbuf[1] + 16), reinterpret_cast<int *>(Tbuf[1] + 16) + 1};
+    icp_init_kernel<<<1, 32, 0, s>>>(chained ? Tbuf[0] : T_dev, chained ? okbuf[0] : ok_dev);        // affine = Identity, projective_icp.cpp:175
     DF_LAUNCH_CHECK();
+    int cur = 0, prev_blocks = 0, ppar = 0;
     for (int level = levels - 1; level >= 0; --level) {
         const int div = 1 << level;                          // setLevelIntr, projective_icp.cpp:17-23
         IcpParams p;
@@ -718,12 +813,35 @@ int icp_estimate_impl(const float *const *vcurr, const unsigned short *const *dc
         // (tried and dropped, round 1: running the solve as a last-block tail of the accumulate kernel -- the tail's 190 registers
         //  become the whole kernel's allocation, occupancy falls to one block per SM and the stage got 25 % slower; replacing the
         //  substitutions' divisions by reciprocal multiplies made the one-thread tail 2.4 us slower per iteration, not faster)
-        for (int it = 0; it < iters[level]; ++it) {
+        for (int it = 0; chained && it < iters[level]; ++it) {
+            p.partials = part0 + (size_t)ppar * ICP_MAX_PARTIAL_BLOCKS * 27;
+            const double *prev = part0 + (size_t)(ppar ^ 1) * ICP_MAX_PARTIAL_BLOCKS * 27;
+            const int npix = p.cols * p.rows;
+            int blocks;
+            if (npix >= ICP_MAX_PARTIAL_BLOCKS * 768) {
+                blocks = ICP_MAX_PARTIAL_BLOCKS;
+                if (p.dcurr) launch_pdl(icp_chain_kernel<true, 768>, dim3(blocks), dim3(768), 0, s, p, prev, prev_blocks, (const float *)Tbuf[cur], (const int *)okbuf[cur], Tbuf[cur ^ 1], okbuf[cur ^ 1]);
+                else launch_pdl(icp_chain_kernel<false, 768>, dim3(blocks), dim3(768), 0, s, p, prev, prev_blocks, (const float *)Tbuf[cur], (const int *)okbuf[cur], Tbuf[cur ^ 1], okbuf[cur ^ 1]);
+            } else {
+                blocks = div_up(npix, 256) < ICP_MAX_PARTIAL_BLOCKS ? div_up(npix, 256) : ICP_MAX_PARTIAL_BLOCKS;
+                if (blocks < 1) blocks = 1;
+                if (p.dcurr) launch_pdl(icp_chain_kernel<true, 256>, dim3(blocks), dim3(256), 0, s, p, prev, prev_blocks, (const float *)Tbuf[cur], (const int *)okbuf[cur], Tbuf[cur ^ 1], okbuf[cur ^ 1]);
+                else launch_pdl(icp_chain_kernel<false, 256>, dim3(blocks), dim3(256), 0, s, p, prev, prev_blocks, (const float *)Tbuf[cur], (const int *)okbuf[cur], Tbuf[cur ^ 1], okbuf[cur ^ 1]);
+            }
+            DF_LAUNCH_CHECK();
+            prev_blocks = blocks; ppar ^= 1; cur ^= 1;
+        }
+        for (int it = 0; !chained && it < iters[level]; ++it) {
             const int blocks = launch_accumulate(p, s);
             if (blocks < 0) return -blocks;
-            launch_pdl(icp_solve_kernel, dim3(1), dim3(256), 0, s, (const double *)p.partials, blocks, T_dev, ok_dev);
+            launch_pdl(icp_solve_kernel, dim3(1), dim3(256), 0, s, (const double *)p.partials, blocks, T_dev, ok_dev, (const float *)T_dev, (const int *)ok_dev);
             DF_LAUNCH_CHECK();
         }
+    }
+    if (chained) {                                           // the last iteration's solve; with no iteration at all the pose stays the identity
+        launch_pdl(icp_solve_kernel, dim3(1), dim3(256), 0, s, (const double *)(part0 + (size_t)(ppar ^ 1) * ICP_MAX_PARTIAL_BLOCKS * 27), prev_blocks, T_dev, ok_dev,
+                   (const float *)Tbuf[cur], (const int *)okbuf[cur]);
+        DF_LAUNCH_CHECK();
     }
     return 0;
 }

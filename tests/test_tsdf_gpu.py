@@ -225,21 +225,22 @@ def test_tracked_raycast_equals_dense_march(orc, dim):
     print(f"dim {dim}: unique voxels read dense {dense['unique_voxels']} tracked {tracked['unique_voxels']}")
 
 
-@pytest.mark.parametrize("impl", ["1", "2"])
-def test_integrate_alternative_kernels_bit_exact_in_subprocess(orc, impl):
-    """the integrate kernel is selected per process (DF_INTEGRATE_IMPL): 3 = default (v1 arithmetic + warp-level visibility culling,
-    covered by every other test), 1 = plain, 2 = approximate-reciprocal projection with exact fallback; all must store the same u32
-    voxels as the oracle"""
+@pytest.mark.parametrize("impl,maxw,frames", [("1", 64, 3), ("2", 64, 3), ("3", 3, 7), ("4", 64, 3), ("4", 3, 7)])
+def test_integrate_alternative_kernels_bit_exact_in_subprocess(orc, impl, maxw, frames):
+    """the integrate kernel is selected per process (DF_INTEGRATE_IMPL): 1 = plain, 2 = approximate-reciprocal projection with exact
+    fallback, 3 = v1 arithmetic + warp-level visibility culling, 4 = 3 + the exact shortcuts of 2 behind the exact projection (no square
+    root outside the truncation band, no division for free space that already holds 1, no store of an unchanged quad); all must store the
+    same u32 voxels as the oracle -- also once the weights saturate (max weight 3, 7 frames)"""
     import os, subprocess, sys
     script = (
         "import numpy as np, torch\n"
         "from dynamicfusion_b200 import host, synth\n"
         "from oracle import orc\n"
         "K = synth.DEFAULT_K; dim = 96\n"
-        "vol = host.TsdfVolume((dim, dim, dim)); vol.setTruncDist(0.04); vol.setMaxWeight(64); vol.setSize((1.0, 1.0, 1.0))\n"
+        f"vol = host.TsdfVolume((dim, dim, dim)); vol.setTruncDist(0.04); vol.setMaxWeight({maxw}); vol.setSize((1.0, 1.0, 1.0))\n"
         "vol.setPose(synth.volume_pose(1.0)); vol.clear()\n"
         "ref = np.zeros(dim ** 3, np.uint32)\n"
-        "for t in range(3):\n"
+        f"for t in range({frames}):\n"
         "    depth = synth.umbrella_depth(t)\n"
         "    dists = host.computeDists(host.u16_to_device(depth), K)\n"
         "    R, tr = synth.camera_drift(5 * t); pose = (R.astype(np.float32), tr.astype(np.float32))\n"
