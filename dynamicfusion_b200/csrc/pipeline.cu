@@ -429,7 +429,7 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_d
         ++k.launches;
         mark(k, 3);
         df_aff3f ident; float id12[12]; dfh_aff_identity(id12); ident = to_aff(id12);    // warp_to_live_ stays identity (never set)
-        CKD(df_warp(k.nodes, k.M, k.node_grid, (float *)k.canon.ptr, (float *)k.canon_nrm.ptr, npix, 4, ident, 0, nullptr, nullptr, s));   // :385
+        CKD(df_warp(k.nodes, k.M, k.node_grid, (float *)k.canon.ptr, (float *)k.canon_nrm.ptr, npix, 4, ident, DF_WARP_IMAGE_COLS(p.cols), nullptr, nullptr, s));   // :385
         ++k.launches;
         mark(k, 4);
         const bool f2_solve = (p.flags & DF_KINFU_F2_SOLVE) != 0;

@@ -94,11 +94,12 @@ constexpr int PREPARE_THREADS = 256;
 
 __global__ void __launch_bounds__(PREPARE_THREADS) solve_prepare_kernel(const float *__restrict__ nodes, int M, const void *__restrict__ grid,
                                                             const float *__restrict__ canon, const float *__restrict__ live, int N, int stride,
-                                                            SolveWs ws)
+                                                            SolveWs ws, int cols, int warp_list)
 {
     DF_PDL_ENTRY();
     __shared__ KnnSmem sm;
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float4 knn_wl[PREPARE_THREADS / 32][KNN_WL_CAP];
+    const int v = patch_vertex(blockIdx.x, threadIdx.x, cols);      // cols > 0: 8 x 4 pixel patches per warp (solve_fill maps the same way)
     float3 c = make_float3(0.f, 0.f, 0.f), l = c;
     bool valid = false, valid_c = false;       // valid_c: the vertex can be queried; valid: the row enters the solve
     if (v < N) {
@@ -108,7 +109,8 @@ __global__ void __launch_bounds__(PREPARE_THREADS) solve_prepare_kernel(const fl
         valid = valid_c && !(isnan(l.x) || isnan(l.y) || isnan(l.z));
     }
     int bi[8]; float bd[8];
-    if (grid) knn8_grid(grid, valid_c, c.x, c.y, c.z, bi, bd);
+    if (grid && warp_list) knn8_grid_warp(grid, valid_c, c.x, c.y, c.z, knn_wl[threadIdx.x >> 5], bi, bd);
+    else if (grid) knn8_grid(grid, valid_c, c.x, c.y, c.z, bi, bd);
     else knn8_scan(nodes, M, valid_c, c.x, c.y, c.z, sm, bi, bd);
     double half_b2 = 0.0;
     if (v < N) {
@@ -200,14 +202,14 @@ __global__ void __launch_bounds__(256) solve_blockscan_kernel(SolveWs ws, int M)
 // entry's position is a pure function of the data.  (A first version sorted the block's 2,048 (node, entry) pairs with a bitonic
 // network: 132 us per frame; this one: see profiles/r02_*launches*.)
 constexpr int FILL_HASH = 1024;                                    // >= distinct nodes a block of 256 vertices can touch (<= 2,048 entries; typically ~30)
-__global__ void __launch_bounds__(256) solve_fill_kernel(SolveWs ws, int N, int only_if_flag)
+__global__ void __launch_bounds__(256) solve_fill_kernel(SolveWs ws, int N, int only_if_flag, int cols)
 {
     DF_PDL_ENTRY();
     if (only_if_flag && ws.flags[2] == 0) return;                  // launched behind the tile assembly as its fallback: nothing to do
     __shared__ int hkey[FILL_HASH], hcur[FILL_HASH];
     __shared__ int overflow;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int v = blockIdx.x * blockDim.x + tid;
+    const int v = patch_vertex(blockIdx.x, tid, cols);             // the vertex -> block map of solve_prepare (its per-block counts are this block's bases)
     const bool valid = v < N && ws.b[v].w != 0.f;
     for (int s = tid; s < FILL_HASH; s += 256) hkey[s] = -1;
     if (tid == 0) overflow = 0;
@@ -1850,7 +1852,9 @@ int dfb::solve_data_term_ev(float *nodes, int M, const void *node_grid, const fl
         e = cudaMemsetAsync(ws.touch, 0, (size_t)M * ws.ntiles, s);
         if (e != cudaSuccess) return (int)e;
     }
-    launch_pdl(solve_prepare_kernel, dim3(ws.prepare_blocks), dim3(256), 0, s, nodes, M, node_grid, canon, live, N, stride, ws);
+    const int img_cols = (flags >> 8) & 0xffff;
+    const int patch_cols = (img_cols > 0 && N % img_cols == 0 && img_cols % 32 == 0 && (N / img_cols) % 8 == 0) ? img_cols : 0;
+    launch_pdl(solve_prepare_kernel, dim3(ws.prepare_blocks), dim3(256), 0, s, nodes, M, node_grid, canon, live, N, stride, ws, patch_cols, knn_warp_list_enabled());
     DF_LAUNCH_CHECK();
     launch_pdl(solve_blockscan_kernel, dim3(div_up(M, 8)), dim3(256), 0, s, ws, M);
     DF_LAUNCH_CHECK();
@@ -1867,7 +1871,7 @@ int dfb::solve_data_term_ev(float *nodes, int M, const void *node_grid, const fl
         launch_pdl(solve_rows_tiles_kernel, dim3(M), dim3(RT_THREADS), 0, s, ws, M, N, flags & DF_SOLVE_REF_GRAPH_QUIRK, lpt);
         DF_LAUNCH_CHECK();
     }
-    launch_pdl(solve_fill_kernel, dim3(ws.prepare_blocks), dim3(256), 0, s, ws, N, tiles ? 1 : 0);
+    launch_pdl(solve_fill_kernel, dim3(ws.prepare_blocks), dim3(256), 0, s, ws, N, tiles ? 1 : 0, patch_cols);
     DF_LAUNCH_CHECK();
     launch_pdl(solve_rows_kernel, dim3(M), dim3(ROWS_THREADS), 0, s, ws, M, N, flags & DF_SOLVE_REF_GRAPH_QUIRK, lpt, tiles ? 1 : 0);
     DF_LAUNCH_CHECK();

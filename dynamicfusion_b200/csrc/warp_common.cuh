@@ -374,6 +374,136 @@ __device__ __forceinline__ void knn8_grid(const void *__restrict__ grid, bool va
     for (int i = 0; i < 8; ++i) if (bi[i] == 0x7fffffff) bi[i] = -1;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Warp-cooperative 8-NN (round 2, second session).  The 32 queries of a warp are neighbours in the image (an 8 x 4 pixel patch, or 32
+// consecutive vertices), so their neighbour sets overlap almost completely and a small superset is cheap to certify: with c the centroid
+// of the warp's valid queries, h >= |x - c| for each of them and R >= d8(c) (distance from c to its 8th nearest node), every query x has
+// d8(x) <= R + h (the eight nodes nearest to c are that close to x), hence each of its eight nearest nodes n has |n - c| <= |n - x| + h
+// <= R + 2h.  The warp scans the grid cells around c together (lane-strided over the contiguous node runs of the grid rows): pass A forms R
+// as the 8th smallest of the 32 lane minima (distances of distinct nodes, so >= d8(c)), pass B compacts the nodes within (R + 2h)(1 + 2e-4)
+// of c into shared memory (ballot ranks), and every lane then ranks those ~20-60 candidates (broadcast reads) with the float distance and the
+// (distance, index) order of every other search path: the result IS knn8_grid's, at a fraction of the divergent per-lane cell walk
+// (12-17 of 32 lanes active).  Warps whose queries are far from the nodes or spread out (depth edges: large h) get no list
+// -- fewer than eight nodes within three cells of c, more than KNN_WL_CAP candidates or more than KNN_WL_ROWS grid rows -- and fall
+// back to knn8_grid lane by lane.  ALL 32 lanes of the warp must call this.
+// Measured in the frame loop (profiles/r02_s2_c12_*): bit-exact, but no faster than the lane-by-lane walk once a warp's queries are an
+// 8 x 4 pixel patch (warp 0.179 vs 0.175 ms, solve 1.029 vs 1.006 ms) -- the two cooperative passes are chains of dependent row-bound
+// loads of their own.  What DID pay is the patch mapping itself (patch_vertex below: 0.215 -> 0.175 ms and 1.039 -> 1.006 ms: tighter
+// queries walk the same cells).  The lists are therefore opt-in (DF_KNN_WARP_LIST=1), the patch mapping is the default.
+constexpr int KNN_WL_CAP = 96;        // candidates per warp: 1.5 KB of float4 (x, y, z, index bits)
+constexpr int KNN_WL_ROWS = 49;       // grid rows (fixed y, z) pass B may touch
+
+__device__ __forceinline__ void knn8_grid_warp(const void *__restrict__ grid, bool valid, float qx, float qy, float qz, float4 *__restrict__ wl,
+                                               int (&bi)[8], float (&bd)[8])
+{
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned vmask = __ballot_sync(full, valid);
+    int K = -1;                                                    // candidates in wl; -1: no list
+    if (vmask) {                                                   // (warp-uniform)
+        const NodeGridHeader h = *reinterpret_cast<const NodeGridHeader *>(grid);
+        const int *cell_start = nodegrid_cell_start(grid);
+        const float4 *sorted = nodegrid_sorted(grid, h.ncell);
+        float sx = valid ? qx : 0.f, sy = valid ? qy : 0.f, sz = valid ? qz : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { sx += __shfl_xor_sync(full, sx, o); sy += __shfl_xor_sync(full, sy, o); sz += __shfl_xor_sync(full, sz, o); }
+        const float inv_n = 1.f / (float)__popc(vmask);
+        const float cx = sx * inv_n, cy = sy * inv_n, cz = sz * inv_n;       // any point works as the centre: h is measured from it
+        float hh = 0.f;
+        if (valid) { const float a = qx - cx, b = qy - cy, c = qz - cz; hh = a * a + b * b + c * c; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) hh = fmaxf(hh, __shfl_xor_sync(full, hh, o));
+        const float hr = sqrtf(hh) * 1.00001f;
+        if (cx == cx && cy == cy && cz == cz && hr < 3.0e37f) {
+            const int ccx = min(max((int)floorf((cx - h.ox) * h.inv_cell), 0), h.gx - 1);
+            const int ccy = min(max((int)floorf((cy - h.oy) * h.inv_cell), 0), h.gy - 1);
+            const int ccz = min(max((int)floorf((cz - h.oz) * h.inv_cell), 0), h.gz - 1);
+            // pass A: lane minima over the cells within Chebyshev distance r of c's cell (every node is visited by exactly one lane)
+            float m = 3.402823466e+38f;
+            int have = 0;
+            for (int r = 1; r <= 3 && have < 8; ++r) {
+                m = 3.402823466e+38f;
+                for (int z = max(ccz - r, 0); z <= min(ccz + r, h.gz - 1); ++z)
+                    for (int y = max(ccy - r, 0); y <= min(ccy + r, h.gy - 1); ++y) {
+                        const int row = h.gx * (y + h.gy * z);
+                        const int b = __ldg(cell_start + row + max(ccx - r, 0)), e = __ldg(cell_start + row + min(ccx + r, h.gx - 1) + 1);
+                        for (int it = b + lane; it < e; it += 32) {
+                            const float4 nd = __ldg(sorted + it);
+                            const float d0 = cx - nd.x, d1 = cy - nd.y, d2 = cz - nd.z;
+                            m = fminf(m, d0 * d0 + d1 * d1 + d2 * d2);        // (a NaN node never lowers the minimum)
+                        }
+                    }
+                have = __popc(__ballot_sync(full, m < 3.0e38f));
+            }
+            if (have >= 8) {
+                float R2 = 0.f;
+                for (int k = 0; k < 8; ++k) {                      // 8th smallest lane minimum: distances of eight distinct nodes
+                    float t = m;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) t = fminf(t, __shfl_xor_sync(full, t, o));
+                    R2 = t;
+                    const unsigned holders = __ballot_sync(full, m == t);
+                    if (lane == __ffs(holders) - 1) m = 3.402823466e+38f;
+                }
+                const float rho = (sqrtf(R2) * 1.00001f + 2.f * hr) * 1.0002f + h.cell * 1e-4f;
+                const float rho2 = rho * rho;
+                const int x0 = max((int)floorf((cx - rho - h.ox) * h.inv_cell), 0), x1 = min((int)floorf((cx + rho - h.ox) * h.inv_cell), h.gx - 1);
+                const int y0 = max((int)floorf((cy - rho - h.oy) * h.inv_cell), 0), y1 = min((int)floorf((cy + rho - h.oy) * h.inv_cell), h.gy - 1);
+                const int z0 = max((int)floorf((cz - rho - h.oz) * h.inv_cell), 0), z1 = min((int)floorf((cz + rho - h.oz) * h.inv_cell), h.gz - 1);
+                if (x0 <= x1 && y0 <= y1 && z0 <= z1 && (y1 - y0 + 1) * (z1 - z0 + 1) <= KNN_WL_ROWS && rho < 3.0e18f) {
+                    // pass B: the nodes within rho of c, compacted in visiting order (a function of the data only)
+                    K = 0;
+                    for (int z = z0; z <= z1; ++z)
+                        for (int y = y0; y <= y1; ++y) {
+                            const int row = h.gx * (y + h.gy * z);
+                            const int b = __ldg(cell_start + row + x0), e = __ldg(cell_start + row + x1 + 1);
+                            for (int it0 = b; it0 < e; it0 += 32) {
+                                const int it = it0 + lane;
+                                float4 nd = make_float4(0.f, 0.f, 0.f, 0.f);
+                                bool in = false;
+                                if (it < e) {
+                                    nd = __ldg(sorted + it);
+                                    const float d0 = cx - nd.x, d1 = cy - nd.y, d2 = cz - nd.z;
+                                    in = d0 * d0 + d1 * d1 + d2 * d2 <= rho2;
+                                }
+                                const unsigned mk = __ballot_sync(full, in);
+                                if (in) { const int pos = K + __popc(mk & ((1u << lane) - 1u)); if (pos < KNN_WL_CAP) wl[pos] = nd; }
+                                K += __popc(mk);
+                            }
+                        }
+                    if (K > KNN_WL_CAP) K = -1;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    if (K < 0) { knn8_grid(grid, valid, qx, qy, qz, bi, bd); return; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { bi[i] = 0x7fffffff; bd[i] = 3.402823466e+38f; }
+    if (valid) {
+#pragma unroll 4
+        for (int k = 0; k < K; ++k) {
+            const float4 nd = wl[k];
+            const float d0 = qx - nd.x, d1 = qy - nd.y, d2 = qz - nd.z;
+            knn8_insert_lex(bi, bd, d0 * d0 + d1 * d1 + d2 * d2, __float_as_int(nd.w));
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) if (bi[i] == 0x7fffffff) bi[i] = -1;
+    __syncwarp();                                                  // the list may be rebuilt by the caller's next search
+}
+
+// Vertex handled by thread `tid` of 256-thread block `blk`: 256 consecutive vertices, or -- for an image of `cols` columns (cols % 32 == 0,
+// rows % 8 == 0) -- a 32 x 8 pixel region whose warps are 8 x 4 patches (the tighter a warp's queries, the shorter its candidate list).
+__device__ __forceinline__ int patch_vertex(int blk, int tid, int cols)
+{
+    if (cols <= 0) return blk * 256 + tid;
+    const int bpr = cols >> 5;
+    const int bx = blk % bpr, by = blk / bpr;
+    const int warp = tid >> 5, lane = tid & 31;
+    return (by * 8 + (warp >> 2) * 4 + (lane >> 3)) * cols + bx * 32 + (warp & 3) * 8 + (lane & 7);
+}
+
 struct Quat { float w, x, y, z; };
 
 // Quaternion::operator*, quaternion.hpp:191-199

@@ -235,6 +235,9 @@ int df_extend_field(float *nodes, int M, int max_nodes, const void *node_grid, c
 #define DF_WARP_REF_NORMAL_INDEX 1
 #define DF_WARP_NORMAL_ROTATE_ONLY 2
 #define DF_WARP_REUSE_KNN 4        /* idx_out / w_out are INPUTS: neighbours + weights of these points from an earlier pass */
+/* flags bits 8..23: the points are an image of that many columns (N = cols * rows, cols % 32 == 0, rows % 8 == 0): a warp then takes an
+ * 8 x 4 pixel patch, whose queries share one short candidate list in the 8-NN search.  Results do not depend on it. */
+#define DF_WARP_IMAGE_COLS(c) (((c) & 0xffff) << 8)
 int df_warp(const float *nodes, int M, const void *node_grid, float *points, float *normals, int N, int stride, df_aff3f warp_to_live,
             int flags, int32_t *idx_out, float *w_out, void *stream);
 

@@ -354,17 +354,17 @@ def test_solve_row_overflow_is_loud_and_leaves_the_field_unchanged():
 
 
 @pytest.mark.parametrize("env", [{"DF_ICP_PERSISTENT": "1"}, {"DF_ICP_CHAINED": "1"}, {"DF_SOLVE_LM_IMPL": "5", "DF_SOLVE_MERGED": "0"}, {"DF_SOLVE_LM_IMPL": "5", "DF_SOLVE_BALANCED": "0"},
-                                 {"DF_SOLVE_V6_FORCE_FALLBACK": "1"}, {"DF_SOLVE_LM_IMPL": "1"}, {"DF_SOLVE_LM_CTAS": "8"}])
+                                 {"DF_SOLVE_V6_FORCE_FALLBACK": "1"}, {"DF_SOLVE_LM_IMPL": "1"}, {"DF_SOLVE_LM_CTAS": "8"}, {"DF_KNN_WARP_LIST": "1"}])
 def test_alternative_icp_and_solve_kernels_in_subprocess(env):
     """The A/B variants that are selected once per process: the one-launch persistent ICP (grid barrier per iteration), the chained ICP (one launch per
     iteration with the previous iteration's solve as every CTA's prologue; the default is the two-kernel accumulate + solve chain), the v5 cluster LM
     (two exchanges per PCG step) with two reductions per step / fixed lanes per row, v5 as the fallback the default v6 kernel hands a frame
-    to when its halo tables do not fit, the one-block LM fallback and the 8-CTA cluster.  Each re-runs this file's ICP / solve parity tests under
+    to when its halo tables do not fit, the one-block LM fallback, the 8-CTA cluster and the warp-cooperative candidate lists of the 8-NN.  Each re-runs this file's ICP / solve parity tests under
     the switch in a fresh interpreter."""
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_stages_gpu.py", "-q", "-x", "-m", "gpu", "-k",
-                        "icp_accumulate_and_estimate or icp_depth or icp_degenerate or solve_reference or solve_large or solve_row_overflow"],
+                        "icp_accumulate_and_estimate or icp_depth or icp_degenerate or solve_reference or solve_large or solve_row_overflow or knn"],
                        cwd=root, env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " passed" in r.stdout and "failed" not in r.stdout
@@ -425,3 +425,41 @@ def test_solve_tile_assembly_matches_per_entry_path_and_oracle(orc, coherent):
     assert abs(stats[0] - ostats[0]) <= 1e-6 * ostats[0] and abs(stats[1] - ostats[1]) <= 1e-4 * ostats[1]
     t_got, t_ref = 2 * got[:, 8:11], orc.node_translations(nodes_ref)[:, 1:]
     assert np.abs(t_got - t_ref).max() <= 1e-3 * np.abs(t_ref).max()
+
+
+@pytest.mark.parametrize("cols,rows", [(256, 160), (200, 100)])
+def test_knn_warp_lists_on_image_shaped_queries(orc, cols, rows):
+    """The warp-cooperative candidate lists of the 8-NN (knn8_grid_warp): queries that are neighbours in the image -- the case the lists are
+    built for, which the random point sets of test_knn_and_warp never produce -- against the oracle's exhaustive search: indices and squared
+    distances bit for bit, through df_knn8 (32 consecutive queries per warp) and through df_warp's neighbour output with the 8 x 4 patch
+    mapping of DF_WARP_IMAGE_COLS (256 x 160; 200 x 100 does not qualify and keeps the linear map).  Includes duplicated nodes (ties at
+    every rank), NaN pixels, a depth edge (a warp whose queries straddle two surfaces) and a far region (no list: lane-by-lane fallback)."""
+    rng = np.random.default_rng(cols)
+    N = cols * rows
+    u, v = np.meshgrid(np.linspace(-0.3, 0.3, cols), np.linspace(-0.2, 0.2, rows))
+    z = 0.05 * np.sin(6 * u) * np.cos(5 * v)
+    z[:, cols // 2:] += 0.08                                      # a depth edge down the middle of the image
+    pts3 = np.stack([u, v, z], -1).reshape(N, 3).astype(np.float32)
+    M = 700
+    nodes = _random_nodes(rng, M)
+    nodes[:, :3] = pts3[rng.choice(N, M, replace=False)]
+    nodes[40:48, :3] = nodes[39, :3]                              # nine coincident nodes: ties decide a whole neighbour set
+    pts = np.zeros((N, 4), np.float32)
+    pts[:, :3] = pts3
+    pts[3::29, 0] = np.nan
+    far = np.zeros((rows, cols), bool); far[: rows // 8] = True   # the top rows look at a region 0.6 m off the node cloud
+    pts[far.reshape(-1), 2] += 0.6
+    nrm = np.zeros((N, 4), np.float32); nrm[:, 2] = 1
+    ridx, rd2 = orc.knn8(nodes, pts)
+    wf = host.WarpField(use_grid=True)
+    wf.setNodes(torch.from_numpy(nodes).cuda())
+    idx, d2 = wf.KNN(torch.from_numpy(pts).cuda())
+    assert np.array_equal(idx.cpu().numpy(), ridx)
+    assert np.array_equal(d2.cpu().numpy().view(np.uint32), rd2.view(np.uint32))
+    p_dev, n_dev = torch.from_numpy(pts).cuda(), torch.from_numpy(nrm).cuda()
+    kidx, kw = wf.warp(p_dev, n_dev, flags=cols << 8, want_knn=True)
+    valid = ~np.isnan(pts[:, 0])
+    assert np.array_equal(kidx.cpu().numpy()[valid], ridx[valid])
+    p_ref, n_ref = pts.copy(), nrm.copy()
+    orc.warp(nodes, p_ref, n_ref)
+    np.testing.assert_allclose(p_dev.cpu().numpy()[valid], p_ref[valid], rtol=1e-4, atol=1e-6)
