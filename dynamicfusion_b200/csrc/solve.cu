@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(ROWS_THREADS) solve_rows_kernel(SolveWs ws, in
 // written by the tiles), accumulated by 8 warps in private shared-memory slots and combined in warp order: no atomics on values, bit-
 // reproducible, and ~40 x fewer operations than the per-entry path.  Tiles with more than TILE_LCAP nodes or rows with more than
 // RT_HCAP * 3/4 columns raise ws.flags[2] and the per-entry kernels (launched right behind, no-ops otherwise) redo the frame.
-constexpr int TW_STRIDE = TILE_LCAP + 1;     // row stride of the tile's weight matrix (floats): odd -> scattered writes hit distinct banks
+constexpr int TW_STRIDE = TILE_LCAP + 4;     // a vertex's row of the tile matrix (floats): 64 node columns, then (b.x, b.y, b.z, 0); 16-byte aligned quads
 constexpr int TILE_HASH = 256;
 
 constexpr int TILE_STRIPS = TILE_PIX / TILE_W;   // an overflowing tile is redone as its 8 pixel rows, one record each
@@ -452,9 +452,7 @@ constexpr unsigned char TOUCH_STRIPS = 255;      // byte-map code: look the node
 __global__ void __launch_bounds__(TILE_PIX) solve_tiles_kernel(SolveWs ws, int cols, int rows)
 {
     DF_PDL_ENTRY();
-    __shared__ float wloc[TILE_PIX * TW_STRIDE];
-    __shared__ float bvec[TILE_PIX][3];
-    __shared__ unsigned amask[TILE_LCAP][TILE_PIX / 32];
+    __shared__ __align__(16) float wloc[TILE_PIX * TW_STRIDE];
     __shared__ int hkey[TILE_HASH], hval[TILE_HASH];
     __shared__ int list[TILE_HASH];
     __shared__ int sorted[TILE_LCAP];
@@ -475,7 +473,6 @@ __global__ void __launch_bounds__(TILE_PIX) solve_tiles_kernel(SolveWs ws, int c
         nk[0] = ia.x; nk[1] = ia.y; nk[2] = ia.z; nk[3] = ia.w; nk[4] = ib.x; nk[5] = ib.y; nk[6] = ib.z; nk[7] = ib.w;
         wk[0] = wa.x; wk[1] = wa.y; wk[2] = wa.z; wk[3] = wa.w; wk[4] = wb.x; wk[5] = wb.y; wk[6] = wb.z; wk[7] = wb.w;
     }
-    bvec[tid][0] = b.x; bvec[tid][1] = b.y; bvec[tid][2] = b.z;
 
     // the node set of the member vertices -> nl distinct nodes in hkey / list (block-uniform result)
     auto build_table = [&](bool member) -> int {
@@ -510,10 +507,9 @@ __global__ void __launch_bounds__(TILE_PIX) solve_tiles_kernel(SolveWs ws, int c
             hval[sa] = rank;
             sorted[rank] = ka;
         }
-        for (int e = tid; e < TILE_PIX * TW_STRIDE; e += TILE_PIX) wloc[e] = 0.f;
+        for (int e = tid; e < TILE_PIX * TW_STRIDE / 4; e += TILE_PIX) reinterpret_cast<float4 *>(wloc)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncthreads();
-        // scatter: weights into the vertex's row, the vertex into its nodes' masks
-        unsigned long long vm = 0ull;
+        // scatter: the vertex's weights into its row (column = local node index), its right-hand side into columns 64..66
         if (member) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -521,35 +517,60 @@ __global__ void __launch_bounds__(TILE_PIX) solve_tiles_kernel(SolveWs ws, int c
                 if (j < 0) continue;
                 unsigned slot = ((unsigned)j * 2654435761u) & (TILE_HASH - 1);
                 while (hkey[slot] != j) slot = (slot + 1) & (TILE_HASH - 1);
-                const int a = hval[slot];
-                wloc[tid * TW_STRIDE + a] = wk[k];
-                vm |= 1ull << a;
+                wloc[tid * TW_STRIDE + hval[slot]] = wk[k];
             }
-        }
-        for (int a = 0; a < L; ++a) {
-            const unsigned m = __ballot_sync(0xffffffffu, (vm >> a) & 1ull);
-            if (lane == 0) amask[a][warp] = m;
+            wloc[tid * TW_STRIDE + TILE_LCAP] = b.x; wloc[tid * TW_STRIDE + TILE_LCAP + 1] = b.y; wloc[tid * TW_STRIDE + TILE_LCAP + 2] = b.z;
         }
         __syncthreads();
-        // rows of T: warp w takes local rows w, w + 4, ...; lane = column (and column + 32)
-        const bool two = L > 32;
-        for (int a = warp; a < L; a += TILE_PIX / 32) {
-            double t0 = 0.0, t1 = 0.0, g = 0.0;
-            for (int w4 = 0; w4 < TILE_PIX / 32; ++w4) {
-                for (unsigned m = amask[a][w4]; m; m &= m - 1u) {
-                    const int u = w4 * 32 + (__ffs(m) - 1);
-                    const float *row = wloc + u * TW_STRIDE;
-                    const double wa = (double)row[a];
-                    t0 += wa * (double)row[lane];
-                    if (two) t1 += wa * (double)row[lane + 32];
-                    if (lane < 3) g += wa * (double)bvec[u][lane];
+        // [T | g] = W^T [W | b] as a small dense product: a thread owns a 4 x 4 block of the result and one of KS interleaved slices of the
+        // 128 vertices (quads of floats per load, products of two floats are exact in double, so the fused multiply-add rounds like mul + add);
+        // the slices are lanes of one warp and are summed by a fixed butterfly.  (The first version walked, per row, the bit mask of the vertices
+        // that hold the node: ~16 instructions per non-zero product, 25 k warp instructions per tile -- ncu r02_s2_c15; the zeros cost less.)
+        const int nA = (L + 3) >> 2, nsb = nA * (nA + 1);        // blocks of four rows x (blocks of four node columns + the right-hand side)
+        const int KS = nsb <= 16 ? 8 : (nsb <= 32 ? 4 : (nsb <= 64 ? 2 : 1));
+        for (int sb0 = 0; sb0 < nsb; sb0 += TILE_PIX / KS) {
+            const int sb = sb0 + tid / KS, ks = tid % KS;
+            const bool act = sb < nsb;
+            const int sa = act ? sb / (nA + 1) : 0, sq = act ? sb % (nA + 1) : 0;
+            const int cb = sq == nA ? TILE_LCAP : 4 * sq;
+            double acc[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+            if (act) {
+                for (int u = ks; u < TILE_PIX; u += KS) {
+                    const float4 A = *reinterpret_cast<const float4 *>(wloc + u * TW_STRIDE + 4 * sa);
+                    const float4 B = *reinterpret_cast<const float4 *>(wloc + u * TW_STRIDE + cb);
+                    const double av[4] = {(double)A.x, (double)A.y, (double)A.z, (double)A.w}, bv[4] = {(double)B.x, (double)B.y, (double)B.z, (double)B.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
                 }
             }
-            double *T = ws.rec_T + ((size_t)rid * TILE_LCAP + a) * TILE_LCAP;
-            if (lane < L) T[lane] = t0;
-            if (lane + 32 < L) T[lane + 32] = t1;
-            if (lane < 3) ws.rec_g[((size_t)rid * TILE_LCAP + a) * 4 + lane] = g;
-            if (write_touch && lane == 0) ws.touch[(size_t)sorted[a] * ws.ntiles + tile] = (unsigned char)(a + 1);
+            for (int o = 1; o < KS; o <<= 1) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] += __shfl_xor_sync(0xffffffffu, acc[i][j], o);
+            }
+            if (act && ks == 0) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int a = 4 * sa + i;
+                    if (a >= L) continue;
+                    if (sq == nA) {
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) ws.rec_g[((size_t)rid * TILE_LCAP + a) * 4 + j] = acc[i][j];
+                    } else {
+                        double *T = ws.rec_T + ((size_t)rid * TILE_LCAP + a) * TILE_LCAP + cb;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) if (cb + j < L) T[j] = acc[i][j];
+                        if (write_touch && sq == 0) ws.touch[(size_t)sorted[a] * ws.ntiles + tile] = (unsigned char)(a + 1);
+                    }
+                }
+            }
         }
         if (tid < L) ws.rec_nodes[(size_t)rid * TILE_LCAP + tid] = sorted[tid];
         if (tid == 0) ws.rec_L[rid] = L;

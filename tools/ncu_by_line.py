@@ -57,6 +57,8 @@ def main():
     for r in src[2:]:
         if len(r) <= iT or not r[iA]:
             continue
+        if r[iA] == "Address":                      # a report with several kernels: the next kernel's table begins -- only the first is summarised
+            break
         ad = int(r[iA], 16) if r[iA].startswith("0x") else int(r[iA])
         base = ad if base is None else base
         loc = addr2loc.get(ad - base, ("?", 0))
