@@ -442,7 +442,7 @@ int process(KinFu &k, const uint16_t *depth_dev, size_t depth_pitch, bool only_d
                                p.solver_nonlinear_iters, p.solver_linear_iters,
                                ((p.flags & DF_KINFU_REF_GRAPH_QUIRK) ? DF_SOLVE_REF_GRAPH_QUIRK : 0) | DF_SOLVE_IMAGE_COLS(p.cols), k.solve_stats, k.solve_ws, s,
                                k.ev_before_lm));   // :387
-        k.launches += 10;                                              // prepare, blockscan, scan, tiles, rows (tiles), fill + rows (fallback), lm v6, lm v5 (fallback)
+        k.launches += 9;                                               // prepare, blockscan, scan, tiles, rows (tiles), fill + rows (fallback), lm v6, lm v5 (fallback)
         CKD(launch_deferred_extract(k, k.ev_before_lm));               // the previous frame's extraction rides on the 132 SMs the solve leaves idle
         }
         // row-overflow flag of this solve (stats[5]): lands in pinned memory, looked at after the next stream synchronisation

@@ -92,7 +92,7 @@ size_t layout(SolveWs &ws, char *base, int M, int N)
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int PREPARE_THREADS = 256;
 
-__global__ void __launch_bounds__(PREPARE_THREADS) solve_prepare_kernel(const float *__restrict__ nodes, int M, const void *__restrict__ grid,
+__global__ void __launch_bounds__(PREPARE_THREADS, 4) solve_prepare_kernel(const float *__restrict__ nodes, int M, const void *__restrict__ grid,
                                                             const float *__restrict__ canon, const float *__restrict__ live, int N, int stride,
                                                             SolveWs ws, int cols, int warp_list)
 {
