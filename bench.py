@@ -249,6 +249,16 @@ def frame_stats_ms(per_s):
     return {"min": v[0], "median": v[len(v) // 2], "max": v[-1]} if v else None
 
 
+def integrate_kernel_name():
+    """the integrate kernel the frame loop's last call launched (df_integrate_last_kernel: the packed-arithmetic kernel falls back to
+    the scalar culling kernel when a launch is outside its checked domain)"""
+    from dynamicfusion_b200 import capi
+    code = capi.load().df_integrate_last_kernel()
+    env = os.environ.get("DF_INTEGRATE_IMPL", "5")
+    return {5: "integrate_kernel_v5", 4: "integrate_kernel_v3<true>", 3: "integrate_kernel_v3"}.get(
+        code, {"1": "integrate_kernel<4>", "2": "integrate_kernel_v2<4>"}.get(env, "integrate_kernel<4>"))
+
+
 def bench_config(world: int, first: int, K: int):
     """the SAME dict in both arms (the driver compares them): workload + the timed window, nothing measured"""
     return {"workload": WORKLOAD, "node_cap": MAX_NODES, "knn": 8, "solver": "LM 5 x PCG 100 (early-out)", "sequences": world,
@@ -503,7 +513,7 @@ def main():
                 "ms_per_step": ms_e2e / K, "frame_ms": frame_stats_ms(per_e2e)},
         "gpu_launches": int(info["launches"]) * K,
         "clocks": clocks,
-        "roofline": {"kernel": {"1": "integrate_kernel<4>", "2": "integrate_kernel_v2<4>", "4": "integrate_kernel_v3<true>"}.get(os.environ.get("DF_INTEGRATE_IMPL", "3"), "integrate_kernel_v3"), "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"kernel": integrate_kernel_name(), "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
                      "traffic_over_algorithmic": (traffic / alg_bytes) if (traffic and alg_bytes) else None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "voxels_written_per_launch": n_upd, "kernel_ms": integ_ms,

@@ -76,6 +76,7 @@ size_t df_volume_activity_bytes(df_volume vol);
  * used to skip the parts of the volume that lie behind the observed surface; NULL = allocated stream-ordered per call. */
 size_t df_integrate_workspace_bytes(int cols, int rows);
 int df_integrate_launch_count(df_volume vol);   /* kernels one integrate call launches for this volume (bookkeeping for gpu_launches) */
+int df_integrate_last_kernel(void);             /* diagnostic: which integrate kernel the last call of this process launched (5 = packed-arithmetic kernel, 3 / 4 = scalar culling kernels, 0 = plain) */
 int df_integrate_tracked(df_volume vol, const uint16_t *dists, size_t dists_pitch, int cols, int rows,
                          df_aff3f vol2cam, df_intr intr, unsigned long long *n_updated, unsigned char *activity, void *workspace,
                          void *stream);

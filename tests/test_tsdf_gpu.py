@@ -225,7 +225,7 @@ def test_tracked_raycast_equals_dense_march(orc, dim):
     print(f"dim {dim}: unique voxels read dense {dense['unique_voxels']} tracked {tracked['unique_voxels']}")
 
 
-@pytest.mark.parametrize("impl,maxw,frames", [("1", 64, 3), ("2", 64, 3), ("3", 3, 7), ("4", 64, 3), ("4", 3, 7)])
+@pytest.mark.parametrize("impl,maxw,frames", [("1", 64, 3), ("2", 64, 3), ("3", 64, 3), ("3", 3, 7), ("4", 64, 3), ("4", 3, 7), ("5", 64, 3), ("5", 3, 7)])
 def test_integrate_alternative_kernels_bit_exact_in_subprocess(orc, impl, maxw, frames):
     """the integrate kernel is selected per process (DF_INTEGRATE_IMPL): 1 = plain, 2 = approximate-reciprocal projection with exact
     fallback, 3 = v1 arithmetic + warp-level visibility culling, 4 = 3 + the exact shortcuts of 2 behind the exact projection (no square
@@ -248,8 +248,55 @@ def test_integrate_alternative_kernels_bit_exact_in_subprocess(orc, impl, maxw, 
         "    orc.integrate(ref, vol.getDims(), vol.getVoxelSize(), vol.getTruncDist(), vol.getMaxWeight(), orc.compute_dists(depth, K), vol2cam, K)\n"
         "got = vol.data_.cpu().numpy().view(np.uint32)\n"
         "assert np.count_nonzero(ref) > 100000\n"
+        "from dynamicfusion_b200 import capi\n"
+        f"want = {{'3': 3, '4': 4, '5': 5}}.get('{impl}')\n"
+        "if want is not None and capi.load().df_integrate_last_kernel() != want: raise SystemExit(4)\n"
         "raise SystemExit(0 if np.array_equal(got, ref) else 3)\n")
     env = dict(os.environ, DF_INTEGRATE_IMPL=impl)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", script], cwd=root, env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("case", ["camera_inside", "camera_behind_tilted", "far_volume_falls_back"])
+def test_integrate_packed_kernel_domain_edges(orc, case):
+    """integrate_kernel_v5 (packed arithmetic) hands runs of voxels next to the camera plane to the scalar slice body and whole launches
+    outside its checked domain to v3: the stored voxels must be the oracle's in every case -- a camera inside the volume (voxels behind
+    the camera, on its plane, and millimetres in front of it), a tilted camera whose plane cuts the volume obliquely, and intrinsics outside
+    the packed kernel's checked domain (df_integrate_last_kernel says which kernel ran)"""
+    from dynamicfusion_b200 import capi
+    dim = 128
+    depth = synth.sphere_wall_depth(seed=7)
+    vol = _setup(dim, 1.0, depth)
+    Kc = K
+    if case == "camera_inside":
+        vol.setPose((np.eye(3, dtype=np.float32), np.array([-0.5, -0.5, -0.25], np.float32)))       # camera plane at voxel slice 32
+        poses = [host.identity_pose(), (np.eye(3, dtype=np.float32), np.array([0.0, 0.0, 2.0 / dim], np.float32))]   # plane exactly on a slice
+        want = 5
+    elif case == "camera_behind_tilted":
+        vol.setPose((np.eye(3, dtype=np.float32), np.array([-0.5, -0.5, -0.1], np.float32)))
+        a = np.deg2rad(25.0)
+        R = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]], np.float32)
+        poses = [(R, np.array([0.02, 0.01, 0.0], np.float32)), _tilted_pose()]
+        want = 5
+    else:
+        # principal point at column 0.5: |cx| < 1 is outside the packed kernel's checked domain (it relies on fma(fx, q, cx) == cx for
+        # quotients below 2^-57), so the launch must go to v3
+        Kc = (K[0], K[1], 0.5, K[3])
+        vol.setPose((np.eye(3, dtype=np.float32), np.array([0.0, -0.5, 0.5], np.float32)))
+        poses = [host.identity_pose()]
+        want = 3
+    vol.clear()
+    dists = host.computeDists(host.u16_to_device(depth), Kc)
+    dists_ref = orc.compute_dists(depth, Kc)
+    ref_vol = np.zeros(dim ** 3, np.uint32)
+    n_upd = torch.zeros(1, dtype=torch.int64, device="cuda")
+    total = 0
+    for pose in poses:
+        vol2cam = vol.integrate(dists, pose, Kc, n_upd)
+        assert capi.load().df_integrate_last_kernel() == want
+        total += orc.integrate(ref_vol, vol.getDims(), vol.getVoxelSize(), vol.getTruncDist(), vol.getMaxWeight(), dists_ref, vol2cam, Kc)
+    got = vol.data_.cpu().numpy().view(np.uint32)
+    assert total > 10000 and int(n_upd.item()) == total
+    mism = np.count_nonzero(got != ref_vol)
+    assert mism == 0, f"{case}: {mism} voxels differ"

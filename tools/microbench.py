@@ -14,7 +14,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--dim", type=int, default=512)
-    ap.add_argument("--integrate-impl", type=int, default=3)
+    ap.add_argument("--integrate-impl", type=int, default=5)
     ap.add_argument("--zchunk", type=int, default=0)
     ap.add_argument("--pipeline", action="store_true")
     ap.add_argument("--frames", type=int, default=12)
