@@ -217,9 +217,13 @@ __device__ double det6_dev(const double *Ain)
 // Cholesky solve, fully unrolled so that L, y, x live in registers (the tail is one thread: local-memory round trips
 // were 20 us per ICP iteration).  Returns false when a pivot is not safely positive (caller falls back to LU + the eigen
 // solve).  *det receives det(A) = (prod L_jj)^2.
+// The tail is the serial part of every one of a frame's 19 ICP iterations, so its LATENCY is what counts: a double sqrt or division is
+// a ~250-cycle dependent chain, and the textbook form needs 6 + 18 of them.  Here each pivot costs one rsqrt (L_jj = d * rsqrt(d),
+// 1 / L_jj = rsqrt(d)) and the substitutions multiply by the stored inverses: ~1.5 k cycles instead of ~6.5 k.  The solution moves by
+// a few double ulps (the pose is cast to float right after; parity bar 1e-5, tests/test_stages_gpu.py::test_icp_*).
 __device__ __forceinline__ bool chol6_solve(const double (&A)[36], const double (&b)[6], double (&x)[6], double *det)
 {
-    double L[36];
+    double L[36], inv[6];
     double dmax = 0.0;
 #pragma unroll
     for (int i = 0; i < 6; ++i) dmax = fmax(dmax, fabs(A[i * 6 + i]));
@@ -231,10 +235,11 @@ __device__ __forceinline__ bool chol6_solve(const double (&A)[36], const double 
 #pragma unroll
         for (int k = 0; k < j; ++k) d -= L[j * 6 + k] * L[j * 6 + k];
         if (!(d > dmax * 1e-13)) { ok = false; d = 1.0; }
-        d = sqrt(d);
+        const double dinv = rsqrt(d);
+        d = d * dinv;
         dprod *= d;
         L[j * 6 + j] = d;
-        const double dinv = 1.0 / d;
+        inv[j] = dinv;
 #pragma unroll
         for (int i = j + 1; i < 6; ++i) {
             double s = A[i * 6 + j];
@@ -249,14 +254,14 @@ __device__ __forceinline__ bool chol6_solve(const double (&A)[36], const double 
         double s = b[i];
 #pragma unroll
         for (int k = 0; k < i; ++k) s -= L[i * 6 + k] * y[k];
-        y[i] = s / L[i * 6 + i];
+        y[i] = s * inv[i];
     }
 #pragma unroll
     for (int i = 5; i >= 0; --i) {
         double s = y[i];
 #pragma unroll
         for (int k = i + 1; k < 6; ++k) s -= L[k * 6 + i] * x[k];
-        x[i] = s / L[i * 6 + i];
+        x[i] = s * inv[i];
     }
     *det = dprod * dprod;
     return ok;
@@ -315,11 +320,14 @@ __device__ void icp_compose_pose(const double (&r)[6], const float *Tin, float *
     for (int i = 0; i < 6; ++i) rf[i] = (float)r[i];
     // cv::Affine3f(rvec, t): Rodrigues evaluated in double on float inputs (opencv2/core/affine.hpp)
     float Rinc[9];
-    const double theta = sqrt((double)rf[0] * rf[0] + (double)rf[1] * rf[1] + (double)rf[2] * rf[2]);
-    if (theta < DBL_EPSILON) {
+    const double theta2 = (double)rf[0] * rf[0] + (double)rf[1] * rf[1] + (double)rf[2] * rf[2];
+    if (theta2 < DBL_EPSILON * DBL_EPSILON) {                      // theta < DBL_EPSILON
         for (int i = 0; i < 9; ++i) Rinc[i] = (i % 4 == 0) ? 1.f : 0.f;
     } else {
-        const double c = cos(theta), s = sin(theta), c1 = 1. - c, itheta = 1. / theta;
+        const double itheta = rsqrt(theta2), theta = theta2 * itheta;   // one dependent chain instead of sqrt, then 1 / theta
+        double s, c;
+        sincos(theta, &s, &c);                                     // one argument reduction for both (this tail is latency-bound)
+        const double c1 = 1. - c;
         const float rx = (float)(rf[0] * itheta), ry = (float)(rf[1] * itheta), rz = (float)(rf[2] * itheta);
         const float rrt[9] = {rx * rx, rx * ry, rx * rz, rx * ry, ry * ry, ry * rz, rx * rz, ry * rz, rz * rz};
         const float r_x[9] = {0, -rz, ry, rz, 0, -rx, -ry, rx, 0};
