@@ -1724,7 +1724,7 @@ solve_lm_v6_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
             }
         }
         __syncthreads();
-        double Q0 = 0.0, gamma_prev = 0.0, alpha_prev = 0.0;
+        double Q0 = 0.0, inv_gamma_prev = 0.0, inv_alpha_prev = 0.0;
         for (int l = 0; l < lin_iters; ++l) {
             spmv(Ap0, Ap1, Ap2);                               // svec holds u = M r
             double v[2] = {0.0, 0.0};
@@ -1738,9 +1738,12 @@ solve_lm_v6_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
             const int par = lm6_exchange<NCTA, 2, true>(sm, sy, cx, v, wtpr);
             const double gamma = v[0], delta = v[1];
             if (!(gamma > 0.0)) break;
-            const double beta = l == 0 ? 0.0 : gamma / gamma_prev;
-            const double pap = l == 0 ? delta : delta - beta * gamma / alpha_prev;   // p.(A + C)p of the textbook step
+            // every thread of the cluster waits for these scalars: ONE double division (a ~150-cycle dependent chain) on the path from the
+            // sums to alpha instead of three -- 1 / gamma and 1 / alpha of the previous step were formed next to its own division
+            const double beta = l == 0 ? 0.0 : gamma * inv_gamma_prev;
+            const double pap = l == 0 ? delta : delta - beta * gamma * inv_alpha_prev;   // p.(A + C)p of the textbook step
             if (!(pap > 0.0)) break;
+            const double inv_gamma = 1.0 / gamma;              // independent of alpha: the two divisions overlap
             const double alpha = gamma / pap;
             if (owner) {
                 p0 = u0 + beta * p0; s0 = w0 + beta * s0; dl0 = dl0 + alpha * p0; r0 = r0 - alpha * s0; u0 = r0 * mi;
@@ -1760,12 +1763,15 @@ solve_lm_v6_kernel(float *nodes, int M, const void *grid, SolveWs ws, int nl_ite
                 }
             }
             const double Q1 = Q0 - 0.5 * alpha * gamma;
-            gamma_prev = gamma; alpha_prev = alpha;
+            inv_gamma_prev = inv_gamma; inv_alpha_prev = pap * inv_gamma;
             ++pcg_total;
-            const double zeta = (double)(l + 1) * (Q1 - Q0) / Q1;   // Ceres/Opt q-tolerance, solverGPUGaussNewton.t:1093-1101
+            // Ceres/Opt q-tolerance, solverGPUGaussNewton.t:1093-1101: zeta = (l + 1) (Q1 - Q0) / Q1 < 1e-4, without the division
+            // (Q decreases from 0, so Q1 < 0 in every regular step; a zero or NaN Q1 never stops the loop, as with the quotient)
+            const double znum = (double)(l + 1) * (Q1 - Q0), zthr = 1e-4 * Q1;
+            const bool q_stop = Q1 < 0.0 ? znum > zthr : (Q1 > 0.0 ? znum < zthr : false);
             Q0 = Q1;
             __syncthreads();                                   // svec (own + halo) is complete
-            if (zeta < 1e-4) break;
+            if (q_stop) break;
         }
         // model change = 0.5 dl.(g + r + C dl);  A dl = g - r - C dl  => new cost = cost - dl.g + 0.5 dl.(A dl)
         double mad[3] = {0.0, 0.0, 0.0};
