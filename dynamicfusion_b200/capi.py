@@ -64,6 +64,7 @@ PROTOTYPES = {
     "df_integrate_workspace_bytes": (_sz, [_i, _i]),
     "df_integrate_launch_count": (_i, [Volume]),
     "df_integrate_last_kernel": (_i, []),
+    "df_integrate_selftest": (_i, [_vp, _vp]),
     "df_integrate_tracked": (_i, [Volume, _vp, _sz, _i, _i, Aff3f, Intr, _vp, _vp, _vp, _vp]),
     "df_raycast_points": (_i, [Volume, Aff3f, C.POINTER(C.c_float), Intr, _i, _i, _f, _f, _vp, _sz, _vp, _sz, _vp]),
     "df_raycast_points_tracked": (_i, [Volume, Aff3f, C.POINTER(C.c_float), Intr, _i, _i, _f, _f, _vp, _sz, _vp, _sz, _vp, _vp]),

@@ -77,6 +77,7 @@ size_t df_volume_activity_bytes(df_volume vol);
 size_t df_integrate_workspace_bytes(int cols, int rows);
 int df_integrate_launch_count(df_volume vol);   /* kernels one integrate call launches for this volume (bookkeeping for gpu_launches) */
 int df_integrate_last_kernel(void);             /* diagnostic: which integrate kernel the last call of this process launched (5 = packed-arithmetic kernel, 3 / 4 = scalar culling kernels, 0 = plain) */
+int df_integrate_selftest(unsigned long long *mismatch_dev4, void *stream);   /* test hook: the packed integrate kernel's division / square-root sequences against the '/' operator and sqrtf() on this device; 4 mismatch counters (all 0 on a conforming device) */
 int df_integrate_tracked(df_volume vol, const uint16_t *dists, size_t dists_pitch, int cols, int rows,
                          df_aff3f vol2cam, df_intr intr, unsigned long long *n_updated, unsigned char *activity, void *workspace,
                          void *stream);

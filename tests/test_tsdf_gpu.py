@@ -300,3 +300,15 @@ def test_integrate_packed_kernel_domain_edges(orc, case):
     assert total > 10000 and int(n_upd.item()) == total
     mism = np.count_nonzero(got != ref_vol)
     assert mism == 0, f"{case}: {mism} voxels differ"
+
+
+def test_packed_arithmetic_selftest_on_device():
+    """df_integrate_selftest: the packed kernel's division / square-root / running-average sequences against the '/' operator and sqrtf()
+    of the same device -- every divisor mantissa at three exponents x 16 dividends (incl. the hard cases a CPU model with a perturbed seed
+    fails: all-ones divisor mantissa, power-of-two dividend), every mantissa of the square root's operand at six exponents, 2.7e8 hashed
+    pairs over the whole checked domain, every denominator of the running average.  All four counters must be zero."""
+    from dynamicfusion_b200 import capi
+    mism = torch.full((4,), -1, dtype=torch.int64, device="cuda")
+    capi.check(capi.load().df_integrate_selftest(mism.data_ptr(), None))
+    torch.cuda.synchronize()
+    assert mism.tolist() == [0, 0, 0, 0], mism.tolist()
