@@ -254,9 +254,7 @@ def integrate_kernel_name():
     the scalar culling kernel when a launch is outside its checked domain)"""
     from dynamicfusion_b200 import capi
     code = capi.load().df_integrate_last_kernel()
-    env = os.environ.get("DF_INTEGRATE_IMPL", "5")
-    return {5: "integrate_kernel_v5", 4: "integrate_kernel_v3<true>", 3: "integrate_kernel_v3"}.get(
-        code, {"1": "integrate_kernel<4>", "2": "integrate_kernel_v2<4>"}.get(env, "integrate_kernel<4>"))
+    return {5: "integrate_kernel_v5", 3: "integrate_kernel_v3"}.get(code, "integrate_kernel<4>")
 
 
 def bench_config(world: int, first: int, K: int):

@@ -225,12 +225,12 @@ def test_tracked_raycast_equals_dense_march(orc, dim):
     print(f"dim {dim}: unique voxels read dense {dense['unique_voxels']} tracked {tracked['unique_voxels']}")
 
 
-@pytest.mark.parametrize("impl,maxw,frames", [("1", 64, 3), ("2", 64, 3), ("3", 64, 3), ("3", 3, 7), ("4", 64, 3), ("4", 3, 7), ("5", 64, 3), ("5", 3, 7)])
+@pytest.mark.parametrize("impl,maxw,frames", [("1", 64, 3), ("3", 64, 3), ("3", 3, 7), ("5", 64, 3), ("5", 3, 7)])
 def test_integrate_alternative_kernels_bit_exact_in_subprocess(orc, impl, maxw, frames):
-    """the integrate kernel is selected per process (DF_INTEGRATE_IMPL): 1 = plain, 2 = approximate-reciprocal projection with exact
-    fallback, 3 = v1 arithmetic + warp-level visibility culling, 4 = 3 + the exact shortcuts of 2 behind the exact projection (no square
-    root outside the truncation band, no division for free space that already holds 1, no store of an unchanged quad); all must store the
-    same u32 voxels as the oracle -- also once the weights saturate (max weight 3, 7 frames)"""
+    """the integrate kernel is selected per process (DF_INTEGRATE_IMPL): 1 = plain, 3 = v1 arithmetic + warp-level visibility culling,
+    5 (the default) = 3's culling around packed two-voxels-per-instruction arithmetic that replays the IEEE division / square-root fast
+    paths; all must store the same u32 voxels as the oracle -- also once the weights saturate (max weight 3, 7 frames); exit code 4 =
+    the requested kernel was not the one launched"""
     import os, subprocess, sys
     script = (
         "import numpy as np, torch\n"
@@ -249,7 +249,7 @@ def test_integrate_alternative_kernels_bit_exact_in_subprocess(orc, impl, maxw, 
         "got = vol.data_.cpu().numpy().view(np.uint32)\n"
         "assert np.count_nonzero(ref) > 100000\n"
         "from dynamicfusion_b200 import capi\n"
-        f"want = {{'3': 3, '4': 4, '5': 5}}.get('{impl}')\n"
+        f"want = {{'3': 3, '5': 5}}.get('{impl}')\n"
         "if want is not None and capi.load().df_integrate_last_kernel() != want: raise SystemExit(4)\n"
         "raise SystemExit(0 if np.array_equal(got, ref) else 3)\n")
     env = dict(os.environ, DF_INTEGRATE_IMPL=impl)

@@ -1,5 +1,5 @@
 """Per-kernel CUDA-event timings at the bench configuration (512^3, 640x480) -- development aid, not the bench.
-   python tools/microbench.py [--dim 512] [--integrate-impl 1|2] [--zchunk N] [--pipeline]"""
+   python tools/microbench.py [--dim 512] [--integrate-impl 1|3|5] [--zchunk N] [--pipeline]"""
 import argparse
 import json
 import os
