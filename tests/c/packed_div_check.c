@@ -114,5 +114,25 @@ int main(void)
     }
     printf("running_average n %lld k0 %lld perturbed %lld outside_hard_case %lld\n", n, bad0, bad, bad);
     fail += bad0 + bad;
+    /* 5. every divisor mantissa (the sweep df_integrate_selftest runs on the device), exact seed: powers of two, all-ones and a few odd
+     *    dividends; and every mantissa of the square root's operand at both exponent parities */
+    bad0 = 0; n = 0;
+    {
+        const float xs[8] = {1.f, 0x1p-11f, -0x1p3f, 0x1.fffffep-4f, -0x1.fffffep2f, 0x1.555556p-1f, 0x1.000002p0f, -0x1.b6db6ep1f};
+        for (uint32_t m = 0; m < (1u << 23); ++m) {
+            const float z = f_from_bits((127u << 23) | m);
+            const float rt = (float)(1.0 / (double)z);
+            for (int j = 0; j < 8; ++j) { ++n; if (div_seq(xs[j], z, rt) != xs[j] / z) ++bad0; }
+            for (int par = 0; par < 2; ++par) {
+                const float v = f_from_bits(((127u + (uint32_t)par) << 23) | m);
+                const float rs = (float)(1.0 / sqrt((double)v));
+                const float sq = v * rs, h = rs * 0.5f;
+                ++n;
+                if (fmaf(fmaf(-sq, sq, v), h, sq) != sqrtf(v)) ++bad0;
+            }
+        }
+    }
+    printf("every_mantissa n %lld k0 %lld perturbed 0 outside_hard_case 0\n", n, bad0);
+    fail += bad0;
     return fail ? 1 : 0;
 }

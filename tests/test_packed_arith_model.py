@@ -22,7 +22,7 @@ def test_sequences_are_exact_with_a_correctly_rounded_seed(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout
     rows = {ln.split()[0]: dict(zip(ln.split()[1::2], map(int, ln.split()[2::2]))) for ln in r.stdout.strip().splitlines()}
-    assert set(rows) == {"division", "tiny_numerators", "square_root", "running_average"}
+    assert set(rows) == {"division", "tiny_numerators", "square_root", "running_average", "every_mantissa"}
     for name, row in rows.items():
         assert row["n"] > 5_000_000 and row["k0"] == 0, (name, row)
     assert rows["division"]["outside_hard_case"] == 0              # perturbed seeds only fail for all-ones divisor mantissas
